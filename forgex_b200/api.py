@@ -1,0 +1,240 @@
+"""Host-side mirror of Forgex's public interface (reference: src/forgex.F90:24-54) over the C ABI.
+
+    reference                              here
+    -------------------------------------  ---------------------------------------------
+    pattern .in. text                      op_in(pattern, text)
+    pattern .match. text                   op_match(pattern, text)
+    call regex(pattern, text, res, length, from, to, status, err_msg)
+                                           regex(pattern, text) -> RegexResult
+    regex_f(pattern, text)                 regex_f(pattern, text)
+    is_valid_regex(pattern)                is_valid_regex(pattern)
+    (new) one pattern against N strings    Pattern(...).match_fixed / in_fixed / match_batch / in_batch / regex_batch
+    (new) one pattern, one huge buffer     Pattern(...).regex_buffer
+
+Same argument meaning and error behaviour as the reference: an invalid pattern makes the operators
+return False, and makes regex return res=b'', length=0, from=to=-9999 with the SYNTAX_* status and
+its message (src/forgex.F90:101-104, :197-200, :266-274).  Byte strings in, byte strings out; indices
+are 1-based inclusive like Fortran's.  All matching runs on the GPU through libforgex_b200.so.
+"""
+import ctypes as C
+from collections import namedtuple
+
+import numpy as np
+
+from . import _lib as L
+
+INVALID_CHAR_INDEX = -9999
+
+RegexResult = namedtuple("RegexResult", "res length from_ to status err_msg")
+
+
+class ForgexError(RuntimeError):
+    def __init__(self, status, where=""):
+        self.status = status
+        super().__init__("%s: status %d: %s" % (where, status, status_message(status)))
+
+
+def status_message(status):
+    return L.lib().fx_status_message(status).decode()
+
+
+def _b(x):
+    if isinstance(x, str):
+        return x.encode("utf-8")
+    return bytes(x)
+
+
+def _check(rc, where):
+    if rc != 0:
+        raise ForgexError(rc, where)
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x):
+    """data pointer of a numpy array or a torch tensor"""
+    if _is_torch(x):
+        return x.data_ptr()
+    return x.ctypes.data
+
+
+class Pattern:
+    """A pattern compiled once for one entry point (op = 'match' | 'in' | 'regex')."""
+
+    OPS = {"match": L.FX_OP_MATCH, "in": L.FX_OP_IN, "regex": L.FX_OP_REGEX}
+
+    def __init__(self, pattern, op, residency="auto"):
+        self.pattern = _b(pattern)
+        self.op = self.OPS[op] if isinstance(op, str) else op
+        h = C.c_void_p()
+        self.status = L.lib().fx_compile(self.pattern, len(self.pattern), self.op, C.byref(h))
+        self.h = h
+        if residency != "auto":
+            self.set_residency(residency)
+
+    def close(self):
+        if getattr(self, "h", None):
+            L.lib().fx_pattern_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def valid(self):
+        return self.status == 0
+
+    def set_residency(self, mode):
+        m = {"auto": L.FX_TABLE_AUTO, "smem": L.FX_TABLE_SMEM, "global": L.FX_TABLE_GLOBAL}[mode]
+        _check(L.lib().fx_pattern_set_residency(self.h, m), "fx_pattern_set_residency")
+
+    def info(self):
+        inf = L.PatternInfo()
+        _check(L.lib().fx_pattern_get_info(self.h, C.byref(inf)), "fx_pattern_get_info")
+        return {n: getattr(inf, n) for n, _ in inf._fields_}
+
+    def literals(self):
+        inf = self.info()
+        bufs = [C.create_string_buffer(max(1, inf[k])) for k in
+                ("literal_all_len", "literal_prefix_len", "literal_suffix_len")]
+        _check(L.lib().fx_pattern_literals(self.h, *bufs), "fx_pattern_literals")
+        return tuple(b.raw[:inf[k]] for b, k in zip(bufs, ("literal_all_len", "literal_prefix_len",
+                                                           "literal_suffix_len")))
+
+    def tables(self):
+        """host copies of the device tables as numpy arrays (tests / tools)"""
+        inf = self.info()
+        ptrs = [C.c_void_p() for _ in range(4)]
+        sc = (C.c_int32 * 5)()
+        _check(L.lib().fx_pattern_tables(self.h, *[C.byref(p) for p in ptrs], C.byref(sc)), "fx_pattern_tables")
+        ns, rs = inf["byte_states"], inf["row_shift"]
+
+        def arr(p, n, dt):
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(dt)), shape=(n,)).copy()
+        return {
+            "table": arr(ptrs[0], ns << rs, C.c_uint16).reshape(ns, 1 << rs),
+            "direct": arr(ptrs[1], ns * 256, C.c_uint16).reshape(ns, 256),
+            "classmap": arr(ptrs[2], 256, C.c_uint8),
+            "flags": arr(ptrs[3], ns, C.c_uint8),
+            "start": sc[0], "start_nul": sc[1], "q0": sc[2], "matched": sc[3], "q0_accepting": bool(sc[4]),
+            "row_shift": rs,
+        }
+
+    # ---- host-buffer batch calls (numpy in, numpy out; copies happen inside the library) ----
+    def _bool_fixed(self, fn, buf, n, stride):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        assert buf.size >= n * stride
+        out = np.empty(n, dtype=np.uint8)
+        _check(fn(self.h, _ptr(buf), n, stride, _ptr(out)), fn.__name__)
+        return out
+
+    def match_fixed(self, buf, n, stride):
+        return self._bool_fixed(L.lib().fx_match_fixed, buf, n, stride)
+
+    def in_fixed(self, buf, n, stride):
+        return self._bool_fixed(L.lib().fx_in_fixed, buf, n, stride)
+
+    def _bool_batch(self, fn, buf, offsets):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        out = np.empty(n, dtype=np.uint8)
+        _check(fn(self.h, _ptr(buf), _ptr(offsets), n, _ptr(out)), fn.__name__)
+        return out
+
+    def match_batch(self, buf, offsets):
+        return self._bool_batch(L.lib().fx_match_batch, buf, offsets)
+
+    def in_batch(self, buf, offsets):
+        return self._bool_batch(L.lib().fx_in_batch, buf, offsets)
+
+    def regex_batch(self, buf, offsets):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        f = np.empty(n, dtype=np.int64)
+        t = np.empty(n, dtype=np.int64)
+        _check(L.lib().fx_regex_batch(self.h, _ptr(buf), _ptr(offsets), n, _ptr(f), _ptr(t)), "fx_regex_batch")
+        return f, t
+
+    def regex_buffer(self, buf):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        f, t = C.c_int64(0), C.c_int64(0)
+        _check(L.lib().fx_regex_buffer(self.h, _ptr(buf), buf.size, C.byref(f), C.byref(t)), "fx_regex_buffer")
+        return f.value, t.value
+
+    # ---- device-resident calls (torch CUDA tensors; nothing is copied; runs on torch's current stream) ----
+    @staticmethod
+    def _stream():
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+
+    def match_fixed_dev(self, d_buf, n, stride, d_out):
+        _check(L.lib().fx_match_fixed_dev(self.h, _ptr(d_buf), n, stride, _ptr(d_out), self._stream()),
+               "fx_match_fixed_dev")
+
+    def in_fixed_dev(self, d_buf, n, stride, d_out):
+        _check(L.lib().fx_in_fixed_dev(self.h, _ptr(d_buf), n, stride, _ptr(d_out), self._stream()),
+               "fx_in_fixed_dev")
+
+    def match_batch_dev(self, d_buf, d_offsets, n, total, d_out):
+        _check(L.lib().fx_match_batch_dev(self.h, _ptr(d_buf), _ptr(d_offsets), n, total, _ptr(d_out),
+                                          self._stream()), "fx_match_batch_dev")
+
+    def in_batch_dev(self, d_buf, d_offsets, n, total, d_out):
+        _check(L.lib().fx_in_batch_dev(self.h, _ptr(d_buf), _ptr(d_offsets), n, total, _ptr(d_out),
+                                       self._stream()), "fx_in_batch_dev")
+
+    def regex_batch_dev(self, d_buf, d_offsets, n, total, d_from, d_to):
+        _check(L.lib().fx_regex_batch_dev(self.h, _ptr(d_buf), _ptr(d_offsets), n, total, _ptr(d_from), _ptr(d_to),
+                                          self._stream()), "fx_regex_batch_dev")
+
+    def regex_buffer_dev(self, d_buf, length, d_from_to, d_work):
+        _check(L.lib().fx_regex_buffer_dev(self.h, _ptr(d_buf), length, _ptr(d_from_to), _ptr(d_work),
+                                           self._stream()), "fx_regex_buffer_dev")
+
+
+# ---- the reference's public API: one pattern, one text, compiled per call -----------------------
+def is_valid_regex(pattern):
+    p = _b(pattern)
+    st = C.c_int(0)
+    return bool(L.lib().fx_is_valid_regex(p, len(p), C.byref(st)))
+
+
+def op_in(pattern, text):
+    """`pattern .in. text` (src/forgex.F90:74)"""
+    p, t = _b(pattern), _b(text)
+    r = C.c_int(0)
+    _check(L.lib().fx_in(p, len(p), t, len(t), C.byref(r)), "fx_in")
+    return bool(r.value)
+
+
+def op_match(pattern, text):
+    """`pattern .match. text` (src/forgex.F90:163)"""
+    p, t = _b(pattern), _b(text)
+    r = C.c_int(0)
+    _check(L.lib().fx_match(p, len(p), t, len(t), C.byref(r)), "fx_match")
+    return bool(r.value)
+
+
+def regex(pattern, text):
+    """`call regex(pattern, text, res, length, from, to, status, err_msg)` (src/forgex.F90:235)"""
+    p, t = _b(pattern), _b(text)
+    f, to, ln, st = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int(0)
+    _check(L.lib().fx_regex(p, len(p), t, len(t), C.byref(f), C.byref(to), C.byref(ln), C.byref(st)), "fx_regex")
+    res = t[f.value - 1:to.value] if f.value > 0 and to.value > 0 else b""
+    return RegexResult(res, ln.value, f.value, to.value, st.value, status_message(st.value))
+
+
+def regex_f(pattern, text):
+    """`regex_f(pattern, text)` (src/forgex.F90:351)"""
+    return regex(pattern, text).res
+
+
+def launch_count():
+    return L.lib().fx_launch_count()

@@ -1,0 +1,560 @@
+// fx_automata.cpp -- syntax tree -> NFA -> eagerly built automata -> byte-level DFA tables.
+//
+// Replaces, on the host, what the reference does lazily per input character
+// (src/automaton_m.F90:199-381, src/lazy_dfa/*): every reachable subset state is built up
+// front (with a stated cap), then the code-point automaton is turned into a DFA over raw bytes
+// in which Forgex's text decoder (src/essential/utf8_m.f90:168-246, src/api_internal_m.F90:127-133:
+// structural UTF-8, anything malformed = ONE byte presented as U+FFFF) is compiled into the
+// transitions.  The result is the `.match.` / `.in.` / `regex` semantics of
+// src/api_internal_m.F90:31-303 expressed as "walk a table, read a flag".
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <unordered_map>
+
+#include "fx_internal.hpp"
+
+namespace fx {
+
+// ---------------------------------------------------------------------------------------------
+// Thompson construction (reference: src/nfa/nfa_node_m.F90:166-322)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// The reference stores the outgoing transitions of a state in slots of at most 16 segments that
+// share a destination (nfa_node_m.F90:324-372): a non-epsilon segment joins the LAST slot with
+// the same destination that still has room -- even one created by an epsilon move -- otherwise
+// it opens a new slot; an epsilon move always opens a new slot.  Each slot is later sorted and
+// its touching segments fused (nfa_node_m.F90:667-692).  Because epsilon is the pseudo segment
+// (-1,-1), it fuses with a segment that starts at U+0000; whether the epsilon move survives
+// that depends on the alphabet split (see finish()).  The slots are kept only to reproduce this.
+struct Slot {
+    int dst;
+    std::vector<Range> segs;
+};
+const int EPS = -1;
+const int SLOT_CAP = 16;
+
+struct Builder {
+    const Syntax& syn;
+    std::vector<std::vector<Slot> > out;  // out[s] : slots of state s (1-based states)
+    int nstates = 0;
+
+    explicit Builder(const Syntax& s) : syn(s) { out.resize(1); }
+
+    int fresh() { out.emplace_back(); return ++nstates; }
+
+    void arc(int src, int dst, Range seg) {
+        std::vector<Slot>& slots = out[(size_t)src];
+        int pick = -1;
+        if (!(seg.lo == EPS && seg.hi == EPS))
+            for (size_t j = 0; j < slots.size(); j++)
+                if (slots[j].dst == dst && (int)slots[j].segs.size() < SLOT_CAP) pick = (int)j;
+        if (pick < 0) { slots.push_back(Slot{dst, {}}); pick = (int)slots.size() - 1; }
+        slots[(size_t)pick].segs.push_back(seg);
+    }
+    void eps(int src, int dst) { arc(src, dst, Range{EPS, EPS}); }
+
+    void star(int operand, int from, int to) {  // nfa_node_m.F90:292-322
+        int a = fresh(), b = fresh();
+        eps(from, a);
+        emit(operand, a, b);
+        eps(b, a);
+        eps(a, to);
+    }
+
+    void emit(int idx, int from, int to) {
+        if (idx < 0) return;
+        const Node& n = syn.nodes[(size_t)idx];
+        switch (n.op) {
+            case N_CHAR:
+                for (const Range& r : n.set) arc(from, to, r);
+                break;
+            case N_EMPTY: eps(from, to); break;
+            case N_UNION: emit(n.left, from, to); emit(n.right, from, to); break;
+            case N_CLOSURE: star(n.left, from, to); break;
+            case N_CONCAT: {
+                int mid = fresh();
+                emit(n.left, from, mid);
+                emit(n.right, mid, to);
+                break;
+            }
+            case N_REPEAT: {  // nfa_node_m.F90:215-262 (note the final unconditional copy)
+                bool inf = n.rmax == REPEAT_INF;
+                int cur = from;
+                int mandatory = n.rmin - 1 + (inf ? 1 : 0);
+                for (int j = 0; j < mandatory; j++) { int s = fresh(); emit(n.left, cur, s); cur = s; }
+                int optional = n.rmin == 0 ? n.rmax - 1 : n.rmax - n.rmin;
+                for (int j = 0; j < optional; j++) { int s = fresh(); emit(n.left, cur, s); eps(s, to); cur = s; }
+                if (n.rmin == 0) eps(from, to);
+                if (inf) star(n.left, cur, to);
+                else emit(n.left, cur, to);
+                break;
+            }
+            default: break;
+        }
+    }
+
+    // sort + fuse one slot the way segment_m.F90:450-506 does (sentinel cuts the list)
+    static void settle(std::vector<Range>& v) {
+        std::stable_sort(v.begin(), v.end(), [](const Range& a, const Range& b) { return a.lo < b.lo; });
+        size_t n = 1;
+        while (n < v.size() && !(v[n].lo == CP_SENTINEL && v[n].hi == CP_SENTINEL)) n++;
+        v.resize(std::min(n, v.size()));
+        std::vector<Range> r;
+        for (const Range& x : v) {
+            if (!r.empty() && r.back().hi >= x.lo - 1) r.back().hi = std::max(r.back().hi, x.hi);
+            else r.push_back(x);
+        }
+        v.swap(r);
+    }
+
+    void finish(Nfa& nfa) {
+        for (auto& slots : out)
+            for (auto& s : slots) settle(s.segs);
+        // Does the reference's alphabet split keep -1 apart from 0?  (segment_disjoin_m.F90:98-163:
+        // a piece ends at -1 when some segment starts at 0, when two distinct segments start at
+        // -1, or when some segment ends at -1.)  Only then does a fused (-1..x) slot still act as
+        // an epsilon move.
+        bool starts_at_zero = false, ends_at_eps = false;
+        std::vector<Range> starting_at_eps;
+        for (auto& slots : out)
+            for (auto& s : slots)
+                for (const Range& r : s.segs) {
+                    if (r.lo == CP_SENTINEL) continue;
+                    if (r.lo == 0) starts_at_zero = true;
+                    if (r.hi == EPS) ends_at_eps = true;
+                    if (r.lo == EPS) {
+                        bool seen = false;
+                        for (const Range& q : starting_at_eps) seen = seen || (q.lo == r.lo && q.hi == r.hi);
+                        if (!seen) starting_at_eps.push_back(r);
+                    }
+                }
+        bool eps_splits = starts_at_zero || ends_at_eps || starting_at_eps.size() > 1;
+
+        nfa.n = nstates;
+        nfa.entry = 1;
+        nfa.exit = 2;
+        nfa.eps.assign((size_t)nstates + 1, {});
+        nfa.edges.assign((size_t)nstates + 1, {});
+        std::vector<int> cuts;
+        cuts.push_back(0);
+        cuts.push_back(CP_MAX + 1);
+        cuts.push_back(CP_TOP + 1);  // 4-byte sequences decode up to 0x1FFFFF; nothing matches above U+10FFFF
+        for (int s = 1; s <= nstates; s++)
+            for (auto& slot : out[(size_t)s])
+                for (Range r : slot.segs) {
+                    if (r.lo == CP_SENTINEL) continue;
+                    if (r.lo == EPS) {
+                        if (r.hi == EPS || eps_splits) nfa.eps[(size_t)s].push_back(slot.dst);
+                        if (r.hi == EPS) continue;
+                        r.lo = 0;
+                    }
+                    if (r.hi > CP_MAX) r.hi = CP_MAX;
+                    if (r.lo > r.hi) continue;
+                    nfa.edges[(size_t)s].push_back({r, slot.dst});
+                    cuts.push_back(r.lo);
+                    cuts.push_back(r.hi + 1);
+                }
+        std::sort(cuts.begin(), cuts.end());
+        cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+        nfa.cuts = cuts;
+    }
+};
+
+}  // namespace
+
+int build_nfa(const Syntax& syn, Nfa& nfa) {
+    Builder b(syn);
+    int entry = b.fresh(), exit = b.fresh();
+    b.emit(syn.root, entry, exit);
+    b.finish(nfa);
+    return OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// eager subset construction
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+typedef std::vector<uint64_t> Bits;
+
+struct BitsHash {
+    size_t operator()(const Bits& b) const {
+        uint64_t h = 0x9E3779B97F4A7C15ull;
+        for (uint64_t w : b) { h ^= w + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); }
+        return (size_t)h;
+    }
+};
+
+struct Subsets {
+    const Nfa& nfa;
+    size_t words;
+    std::vector<std::vector<std::pair<int, int> > > by_class;  // per state: (class, dst) expanded from ranges
+    Bits entry_closure;
+
+    explicit Subsets(const Nfa& n) : nfa(n), words(((size_t)n.n + 64) / 64) {
+        int ncls = (int)nfa.cuts.size() - 1;
+        by_class.assign((size_t)nfa.n + 1, {});
+        for (int s = 1; s <= nfa.n; s++)
+            for (auto& e : nfa.edges[(size_t)s]) {
+                int c0 = (int)(std::lower_bound(nfa.cuts.begin(), nfa.cuts.end(), e.first.lo) - nfa.cuts.begin());
+                for (int c = c0; c < ncls && nfa.cuts[(size_t)c] <= e.first.hi; c++) by_class[(size_t)s].push_back({c, e.second});
+            }
+        entry_closure = Bits(words, 0);
+        close_from(entry_closure, nfa.entry);
+    }
+    static bool has(const Bits& b, int s) { return (b[(size_t)s >> 6] >> (s & 63)) & 1; }
+    static void put(Bits& b, int s) { b[(size_t)s >> 6] |= 1ull << (s & 63); }
+    bool any(const Bits& b) const { for (uint64_t w : b) if (w) return true; return false; }
+
+    void close_from(Bits& b, int s) const {  // epsilon closure, iterative
+        std::vector<int> stack;
+        if (!has(b, s)) { put(b, s); }
+        stack.push_back(s);
+        while (!stack.empty()) {
+            int u = stack.back();
+            stack.pop_back();
+            for (int v : nfa.eps[(size_t)u])
+                if (!has(b, v)) { put(b, v); stack.push_back(v); }
+        }
+    }
+    // all successors of `from` (plus the entry closure when inject) on every class at once
+    void step_all(const Bits& from, bool inject, std::vector<Bits>& next) const {
+        int ncls = (int)nfa.cuts.size() - 1;
+        next.assign((size_t)ncls, Bits(words, 0));
+        for (int s = 1; s <= nfa.n; s++) {
+            if (!(has(from, s) || (inject && has(entry_closure, s)))) continue;
+            for (auto& cd : by_class[(size_t)s])
+                if (!has(next[(size_t)cd.first], cd.second)) close_from(next[(size_t)cd.first], cd.second);
+        }
+    }
+};
+
+}  // namespace
+
+int CpAutomaton::class_of(int cp) const {
+    if (cp < 0 || cp > CP_TOP) return -1;
+    return (int)(std::upper_bound(cuts.begin(), cuts.end(), cp) - cuts.begin()) - 1;
+}
+
+// Modes (all from the same NFA):
+//  MATCH : anchored.  start = delta(q0, NUL) if alive else q0 (api_internal_m.F90:280-289);
+//          end_accept[s] = exit in s  or  exit in delta(s, NUL)   (:261, :298)
+//  IN    : search automaton: a new attempt is injected at every character boundary
+//          (api_internal_m.F90:108-155), an accept after >= 1 symbol is absorbing ("matched");
+//          start = state after the leading NUL; end_accept[s] = exit in delta_noinject(s, NUL)
+//          (the trailing NUL is consumed by running attempts but is not a start, :108).
+//          If the lone leading NUL is itself a match, the reference returns from that first
+//          attempt (to = 0 unless it extends), so the automaton is then anchored at start 1.
+//  REGEX : anchored, no absorption; accept[] per state; q0 and start_nul = delta(q0, NUL).
+int build_cp_automaton(const Nfa& nfa, Mode mode, int state_cap, CpAutomaton& a) {
+    Subsets ss(nfa);
+    int ncls = (int)nfa.cuts.size() - 1;
+    a = CpAutomaton();
+    a.nclasses = ncls;
+    a.cuts = nfa.cuts;
+    int nul_class = a.class_of(0);
+    a.q0_accepting = Subsets::has(ss.entry_closure, nfa.exit);
+
+    std::unordered_map<Bits, int, BitsHash> index;
+    std::vector<Bits> sets;
+    std::vector<char> pinned;  // state whose own acceptance must not absorb (start states)
+    auto intern = [&](const Bits& b) -> int {
+        if (!ss.any(b) && mode != MODE_IN) return 0;
+        auto it = index.find(b);
+        if (it != index.end()) return it->second;
+        int id = (int)sets.size();
+        sets.push_back(b);
+        index.emplace(b, id);
+        return id;
+    };
+    sets.push_back(Bits(ss.words, 0));  // state 0: dead (MATCH/REGEX).  In IN mode the empty set is a live state, interned separately below.
+    bool inject = false, absorb = false;
+    Bits after_nul(ss.words, 0);
+    {
+        std::vector<Bits> nx;
+        ss.step_all(Bits(ss.words, 0), true, nx);
+        after_nul = nx[(size_t)nul_class];
+    }
+    std::vector<int> work;
+    int matched = -1;
+    if (mode == MODE_MATCH) {
+        int q0 = intern(ss.entry_closure);
+        int sn = intern(after_nul);
+        a.start = sn != 0 ? sn : q0;
+        a.q0 = q0;
+        a.start_nul = sn;
+    } else if (mode == MODE_REGEX) {
+        a.q0 = intern(ss.entry_closure);
+        a.start_nul = intern(after_nul);
+        a.start = a.q0;
+    } else {
+        absorb = true;
+        // sets[0] stays the unused dead row; a dedicated id marks "matched"
+        matched = (int)sets.size();
+        sets.push_back(Bits(ss.words, 0));  // placeholder row for the matched sink (never looked up by set)
+        bool nul_is_match = Subsets::has(after_nul, nfa.exit);
+        inject = !nul_is_match;
+        // start state: its own acceptance does not count (the attempt must extend past the NUL)
+        int id = (int)sets.size();
+        sets.push_back(after_nul);
+        if (!nul_is_match) index.emplace(after_nul, id);  // reusable only when it cannot be confused with a counted accept
+        a.start = id;
+        a.matched = matched;
+    }
+    // breadth-first closure over all classes
+    std::vector<int> delta;
+    auto grow = [&]() { delta.resize(sets.size() * (size_t)ncls, 0); };
+    grow();
+    std::vector<char> done;
+    std::vector<Bits> nx;
+    for (size_t cur = 0; cur < sets.size(); cur++) {
+        if ((int)cur == 0 || (int)cur == matched) continue;
+        ss.step_all(sets[cur], inject, nx);
+        for (int c = 0; c < ncls; c++) {
+            int dst;
+            if (absorb && Subsets::has(nx[(size_t)c], nfa.exit)) dst = matched;
+            else dst = intern(nx[(size_t)c]);
+            if ((int)sets.size() > state_cap) return ERR_DFA_STATE_CAP;
+            grow();
+            delta[cur * (size_t)ncls + (size_t)c] = dst;
+        }
+    }
+    if (matched >= 0)
+        for (int c = 0; c < ncls; c++) delta[(size_t)matched * (size_t)ncls + (size_t)c] = matched;
+    a.nstates = (int)sets.size();
+    a.delta = delta;
+    a.accept.assign((size_t)a.nstates, 0);
+    a.end_accept.assign((size_t)a.nstates, 0);
+    for (int s = 0; s < a.nstates; s++) {
+        if (s == matched) { a.accept[(size_t)s] = 1; a.end_accept[(size_t)s] = 1; continue; }
+        if (s == 0) continue;
+        bool acc = Subsets::has(sets[(size_t)s], nfa.exit);
+        a.accept[(size_t)s] = acc;
+        if (mode == MODE_MATCH) {
+            int t = delta[(size_t)s * (size_t)ncls + (size_t)nul_class];
+            a.end_accept[(size_t)s] = acc || (t != 0 && Subsets::has(sets[(size_t)t], nfa.exit));
+        } else if (mode == MODE_IN) {
+            std::vector<Bits> t;
+            ss.step_all(sets[(size_t)s], false, t);  // trailing NUL: consumed, but not a start
+            a.end_accept[(size_t)s] = Subsets::has(t[(size_t)nul_class], nfa.exit);
+            a.accept[(size_t)s] = 0;  // only the matched sink "accepts" in this mode
+        } else {
+            a.end_accept[(size_t)s] = acc;
+        }
+    }
+    return OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// byte-level DFA
+// ---------------------------------------------------------------------------------------------
+// Boundary states are the code-point automaton's states.  A lead byte moves to an INTER state
+// that remembers (origin state, sequence length, bytes still missing, which code-point window
+// is still possible); the last continuation byte lands on the destination boundary state.  If a
+// byte that is not 10xxxxxx arrives inside a sequence, the reference would have presented each
+// pending byte as U+FFFF (api_internal_m.F90:129-133; utf8_m.f90:168-191 consumes one byte) and
+// then handled the new byte from scratch -- so that entry is delta*(origin, FFFF^k) followed by
+// the new byte's own boundary transition.  Sequences are decoded by bit concatenation only: no
+// overlong / surrogate / range rejection (utf8_m.f90:383-429), code points above U+10FFFF match
+// nothing.
+namespace {
+
+// Two INTER states are the same state when they agree on: how many bytes are still missing, where
+// every completion lands, what the pending bytes replay to from here on (now, and after each further
+// continuation byte), and the accept marks of the replay so far.  Neither the origin state nor the
+// sequence length is part of the identity, so e.g. every search state of an ASCII-only pattern shares
+// one small set of INTER states, and the overlong 3- and 4-byte forms share their tails.
+struct InterKey {
+    int missing;
+    int failacc;
+    std::vector<int> tail;  // replay states chain[pending-1 .. total-2]
+    std::vector<int> sig;   // (window-relative lo, dst) pairs, run-length form
+    bool operator<(const InterKey& o) const {
+        if (missing != o.missing) return missing < o.missing;
+        if (failacc != o.failacc) return failacc < o.failacc;
+        if (tail != o.tail) return tail < o.tail;
+        return sig < o.sig;
+    }
+};
+
+struct ByteBuilder {
+    const CpAutomaton& a;
+    bool flag_bits;
+    std::map<InterKey, int> inter_index;
+    struct Inter { int origin, total, missing; long long lo; int chain[3]; int failacc; };  // window = [lo, lo + 64^missing)
+    std::vector<Inter> inters;
+    std::vector<std::vector<int> > rows;  // rows[state][byte]
+    std::vector<uint8_t> flags;
+
+    ByteBuilder(const CpAutomaton& au, bool fb) : a(au), flag_bits(fb) {}
+
+    int cp_delta(int s, long long cp) const {
+        return a.delta[(size_t)s * (size_t)a.nclasses + (size_t)a.class_of((int)cp)];
+    }
+
+    std::vector<int> signature(int s, long long lo, long long hi) const {
+        std::vector<int> sig;
+        long long p = lo;
+        int last = -2;
+        while (p <= hi) {
+            int c = a.class_of((int)p);
+            int d = a.delta[(size_t)s * (size_t)a.nclasses + (size_t)c];
+            if (d != last) { sig.push_back((int)(p - lo)); sig.push_back(d); last = d; }
+            p = a.cuts[(size_t)c + 1];
+        }
+        return sig;
+    }
+
+    // INTER state reached from `origin` after the lead byte and (total-1-missing) continuation
+    // bytes, the code points still possible being [lo, lo + 64^missing).
+    int inter_state(int origin, int total, int missing, long long lo) {
+        long long span = 1ll << (6 * missing);
+        int chain[3] = {-1, -1, -1};
+        int st = origin;
+        for (int i = 0; i < total - 1; i++) { st = cp_delta(st, 0xFFFF); chain[i] = st; }
+        int pending = total - missing;
+        InterKey k;
+        k.missing = missing;
+        k.failacc = 0;
+        for (int i = 1; i <= pending; i++)
+            if (a.accept[(size_t)chain[i - 1]]) k.failacc |= 1 << (i - 1);
+        if (!flag_bits) k.failacc = 0;  // only the span kernels look at the replay marks
+        for (int i = pending - 1; i <= total - 2; i++) k.tail.push_back(chain[i]);
+        k.sig = signature(origin, lo, lo + span - 1);
+        if (k.sig.size() == 2 && k.sig[1] == 0 && k.failacc == 0) {
+            // every completion is dead: the state is dead iff every possible replay is dead too
+            bool all_dead = true;
+            for (int t : k.tail) all_dead = all_dead && t == 0;
+            if (all_dead) return 0;
+        }
+        auto it = inter_index.find(k);
+        if (it != inter_index.end()) return it->second;
+        int id = a.nstates + (int)inters.size();
+        Inter in{origin, total, missing, lo, {chain[0], chain[1], chain[2]}, k.failacc};
+        inters.push_back(in);
+        inter_index.emplace(k, id);
+        return id;
+    }
+
+    int build(ByteTable& out) {
+        rows.assign((size_t)a.nstates, std::vector<int>(256, 0));
+        for (int s = 0; s < a.nstates; s++) {
+            std::vector<int>& row = rows[(size_t)s];
+            for (int b = 0; b < 0x80; b++) row[(size_t)b] = cp_delta(s, b);
+            int bad = cp_delta(s, 0xFFFF);  // stray continuation byte, or 11111xxx
+            for (int b = 0x80; b < 0xC0; b++) row[(size_t)b] = bad;
+            for (int b = 0xF8; b < 0x100; b++) row[(size_t)b] = bad;
+            for (int b = 0xC0; b < 0xE0; b++) row[(size_t)b] = inter_state(s, 2, 1, (long long)(b & 31) << 6);
+            for (int b = 0xE0; b < 0xF0; b++) row[(size_t)b] = inter_state(s, 3, 2, (long long)(b & 15) << 12);
+            for (int b = 0xF0; b < 0xF8; b++) row[(size_t)b] = inter_state(s, 4, 3, (long long)(b & 7) << 18);
+        }
+        // INTER rows (the list grows while it is processed)
+        for (size_t i = 0; i < inters.size(); i++) {
+            Inter in = inters[i];
+            std::vector<int> row(256, 0);
+            int pending = in.total - in.missing;        // bytes swallowed so far
+            int fallback = in.chain[pending - 1];       // origin after replaying them as U+FFFF
+            for (int b = 0; b < 256; b++) {
+                if ((b >> 6) == 2) {
+                    long long lo = in.lo + ((long long)(b & 63) << (6 * (in.missing - 1)));
+                    if (in.missing == 1) row[(size_t)b] = cp_delta(in.origin, lo);
+                    else row[(size_t)b] = inter_state(in.origin, in.total, in.missing - 1, lo);
+                } else {
+                    row[(size_t)b] = rows[(size_t)fallback][(size_t)b];
+                }
+            }
+            rows.push_back(row);
+        }
+        int total_states = a.nstates + (int)inters.size();
+        if (total_states > (flag_bits ? (int)W_STATE : 0xFFFF)) return ERR_DFA_STATE_CAP;
+        // flags
+        flags.assign((size_t)total_states, 0);
+        for (int s = 0; s < a.nstates; s++) {
+            uint8_t f = 0;
+            if (a.accept[(size_t)s]) f |= SF_ACC;
+            if (a.end_accept[(size_t)s]) f |= SF_END;
+            if (s == a.matched) f |= SF_MATCHED;
+            flags[(size_t)s] = f;
+        }
+        for (size_t i = 0; i < inters.size(); i++) {
+            const Inter& in = inters[i];
+            int pending = in.total - in.missing;
+            uint8_t f = SF_INTER;
+            for (int k = 1; k <= pending; k++)
+                if (in.failacc & (1 << (k - 1))) f |= (uint8_t)(SF_FAILACC1 << (k - 1));
+            int st = in.chain[pending - 1];
+            if (a.end_accept[(size_t)st]) f |= SF_END;   // text ends inside the sequence: pending bytes replay as U+FFFF
+            if (st == a.matched) f |= SF_MATCHED;
+            flags[(size_t)a.nstates + i] = f;
+        }
+        // byte classes: bytes whose columns agree in every state
+        std::map<std::vector<int>, int> colid;
+        out.nclasses = 0;
+        for (int b = 0; b < 256; b++) {
+            std::vector<int> col((size_t)total_states);
+            for (int s = 0; s < total_states; s++) col[(size_t)s] = rows[(size_t)s][(size_t)b];
+            auto it = colid.find(col);
+            if (it == colid.end()) { it = colid.emplace(col, out.nclasses++).first; }
+            out.classmap[b] = (uint8_t)it->second;
+        }
+        out.row_shift = 0;
+        while ((1 << out.row_shift) < out.nclasses) out.row_shift++;
+        out.nstates = total_states;
+        out.nboundary = a.nstates;
+        auto word = [&](int dst) -> uint16_t {
+            uint16_t w = (uint16_t)dst;
+            if (!flag_bits) return w;  // boolean kernels only read flags[] at the end of the text
+            uint8_t f = flags[(size_t)dst];
+            if (f & (SF_ACC | SF_MATCHED)) w |= W_ACC;
+            if (f & SF_INTER) w |= W_INTER;
+            return w;
+        };
+        out.table.assign((size_t)total_states << out.row_shift, 0);
+        for (int s = 0; s < total_states; s++)
+            for (int b = 0; b < 256; b++)
+                out.table[((size_t)s << out.row_shift) + out.classmap[b]] = word(rows[(size_t)s][(size_t)b]);
+        out.direct.assign((size_t)total_states * 256, 0);
+        for (int s = 0; s < total_states; s++)
+            for (int b = 0; b < 256; b++) out.direct[(size_t)s * 256 + (size_t)b] = word(rows[(size_t)s][(size_t)b]);
+        out.flags = flags;
+        out.start = a.start; out.start_nul = a.start_nul; out.q0 = a.q0; out.matched = a.matched;
+        out.q0_accepting = a.q0_accepting;
+        out.flag_bits = flag_bits;
+        return OK;
+    }
+};
+
+}  // namespace
+
+int build_byte_table(const CpAutomaton& a, bool flag_bits, ByteTable& out) {
+    ByteBuilder bb(a, flag_bits);
+    return bb.build(out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// whole program
+// ---------------------------------------------------------------------------------------------
+int compile_program(const std::string& pattern, int op, int state_cap, Program& p) {
+    p = Program();
+    p.op = op;
+    p.prepared = prepare_pattern(pattern, op == MODE_MATCH);
+    Syntax syn;
+    parse_pattern(p.prepared, syn);
+    p.status = syn.status;
+    if (!syn.valid()) return p.status;
+    extract_literals(syn, p.lit);
+    p.literal_only = !fortran_blank(p.lit.all);
+    p.prefix_active = !fortran_blank(p.lit.prefix);
+    Nfa nfa;
+    build_nfa(syn, nfa);
+    p.nfa_states = nfa.n;
+    int rc = build_cp_automaton(nfa, (Mode)op, state_cap, p.cp);
+    if (rc != OK) { p.status = rc; return rc; }
+    rc = build_byte_table(p.cp, op == MODE_REGEX, p.bt);
+    if (rc != OK) { p.status = rc; return rc; }
+    return OK;
+}
+
+}  // namespace fx

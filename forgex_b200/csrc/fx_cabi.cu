@@ -1,0 +1,668 @@
+// fx_cabi.cu -- the C ABI of include/forgex_b200.h: pattern handles, table upload, kernel launches.
+// Product code; never links oracle/.  No CPU fallback: every matching entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/forgex_b200.h"
+#include "fx_internal.hpp"
+#include "fx_kernels.cuh"
+
+using namespace fxk;
+
+namespace {
+
+std::atomic<long long> g_launches{0};
+
+constexpr int STATE_CAP = 16383;                 // Forgex's own ceiling (lazy_dfa_graph_m.F90:90-92 with parameters_m.f90:126-130)
+constexpr int DIRECT_LIMIT_BYTES = 40 * 1024;    // 256-column table kept in shared memory up to this size
+constexpr int SMEM_TABLE_LIMIT_BYTES = 160 * 1024;
+
+struct DeviceTables {
+    int device = -1;
+    uint16_t* table = nullptr;   // class-compressed
+    uint16_t* direct = nullptr;  // 256 columns (only when small)
+    uint8_t* classmap = nullptr;
+    uint8_t* flags = nullptr;
+    uint8_t* lits = nullptr;
+    // anchored (REGEX-mode) tables of an `.in.` pattern with an active prefix
+    uint16_t* a_table = nullptr;
+    uint8_t* a_classmap = nullptr;
+    uint8_t* a_flags = nullptr;
+    // grow-only scratch for the host-pointer entry points
+    uint8_t* w_buf = nullptr; size_t w_buf_cap = 0;
+    int64_t* w_off = nullptr; size_t w_off_cap = 0;
+    uint8_t* w_out = nullptr; size_t w_out_cap = 0;
+    int64_t* w_span = nullptr; size_t w_span_cap = 0;
+    unsigned long long* w_best = nullptr;
+    int sm_count = 0;
+};
+
+}  // namespace
+
+struct fx_pattern {
+    fx::Program prog;
+    int residency = FX_TABLE_AUTO;
+    int last_residency = 0, last_direct = 0;
+    fx::Program anchored;        // only for FX_OP_IN with an active prefix
+    bool has_anchored = false;
+    int prefix_mode = 0;         // see KParams::prefix_mode
+    DeviceTables dev;
+    std::mutex mu;
+};
+
+namespace {
+
+#define CUDA_TRY(expr)                                        \
+    do {                                                      \
+        cudaError_t e__ = (expr);                             \
+        if (e__ != cudaSuccess) return cuda_status(e__);      \
+    } while (0)
+
+int cuda_status(cudaError_t e) {
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInitializationError) return FX_ERR_NO_DEVICE;
+    return -(int)e;
+}
+
+// Is Forgex's prefix prefilter (api_internal_m.F90:76-104, utility_m.f90:58-117) result-neutral for
+// this pattern as long as the text is pure ASCII, so that trying every character boundary gives the
+// same answer?  Sufficient: the suffix is blank; the prefix has no border (occurrences cannot overlap,
+// so the non-overlapping occurrence list is the full list), holds no NUL, and is a true prefix of every
+// match: walking its code points from q0 in the anchored automaton, every other class is dead and no
+// accept is seen before it ends.  (With bytes >= 0x80 in the text an overlong encoding could start a
+// match that the byte-wise prefix search does not see; the kernels re-check such texts exactly.)
+bool prefilter_is_neutral(const fx::Program& anchored) {
+    const std::string& pre = anchored.lit.prefix;
+    if (fx::fortran_blank(pre)) return true;
+    if (!fx::fortran_blank(anchored.lit.suffix)) return false;
+    if (pre.find('\0') != std::string::npos) return false;
+    size_t n = pre.size();
+    for (size_t k = 1; k < n; k++)
+        if (pre.compare(0, k, pre, n - k, k) == 0) return false;   // border
+    for (unsigned char c : pre) if (c >= 0x80) return false;         // keep the argument to ASCII prefixes
+    const fx::CpAutomaton& a = anchored.cp;
+    int st = a.q0;
+    for (size_t i = 0; i < n; i++) {
+        if (i > 0 && a.accept[(size_t)st]) return false;
+        int want = a.class_of((unsigned char)pre[i]);
+        if (a.cuts[(size_t)want] != (unsigned char)pre[i] || a.cuts[(size_t)want + 1] != (unsigned char)pre[i] + 1) return false;
+        for (int c = 0; c < a.nclasses; c++)
+            if (c != want && a.delta[(size_t)st * (size_t)a.nclasses + (size_t)c] != 0) return false;
+        st = a.delta[(size_t)st * (size_t)a.nclasses + (size_t)want];
+        if (st == 0) return false;
+    }
+    return true;
+}
+
+int ensure_device(fx_pattern* p) {
+    DeviceTables& d = p->dev;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (d.device == dev) return FX_OK;
+    if (d.device >= 0) return FX_ERR_BAD_ARGUMENT;  // one device per handle
+    const fx::ByteTable& bt = p->prog.bt;
+    size_t tb = (bt.table.size() * 2 + 15) & ~(size_t)15, db = (bt.direct.size() * 2 + 15) & ~(size_t)15;
+    CUDA_TRY(cudaMalloc(&d.table, tb + 16));
+    CUDA_TRY(cudaMemset(d.table, 0, tb + 16));
+    CUDA_TRY(cudaMemcpy(d.table, bt.table.data(), bt.table.size() * 2, cudaMemcpyHostToDevice));
+    if ((int)db <= DIRECT_LIMIT_BYTES) {
+        CUDA_TRY(cudaMalloc(&d.direct, db + 16));
+        CUDA_TRY(cudaMemset(d.direct, 0, db + 16));
+        CUDA_TRY(cudaMemcpy(d.direct, bt.direct.data(), bt.direct.size() * 2, cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(cudaMalloc(&d.classmap, 256));
+    CUDA_TRY(cudaMemcpy(d.classmap, bt.classmap, 256, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&d.flags, (bt.flags.size() + 15) & ~(size_t)15));
+    CUDA_TRY(cudaMemcpy(d.flags, bt.flags.data(), bt.flags.size(), cudaMemcpyHostToDevice));
+    std::string lits = p->prog.lit.all + p->prog.lit.prefix + p->prog.lit.suffix;
+    CUDA_TRY(cudaMalloc(&d.lits, lits.size() + 16));
+    if (!lits.empty()) CUDA_TRY(cudaMemcpy(d.lits, lits.data(), lits.size(), cudaMemcpyHostToDevice));
+    if (p->has_anchored) {
+        const fx::ByteTable& at = p->anchored.bt;
+        CUDA_TRY(cudaMalloc(&d.a_table, at.table.size() * 2 + 16));
+        CUDA_TRY(cudaMemcpy(d.a_table, at.table.data(), at.table.size() * 2, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&d.a_classmap, 256));
+        CUDA_TRY(cudaMemcpy(d.a_classmap, at.classmap, 256, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&d.a_flags, at.flags.size() + 16));
+        CUDA_TRY(cudaMemcpy(d.a_flags, at.flags.data(), at.flags.size(), cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(cudaMalloc(&d.w_best, 8));
+    CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    d.device = dev;
+    return FX_OK;
+}
+
+struct Plan {
+    bool direct, tsmem;
+    int table_bytes;   // bytes of the selected table
+    KParams kp;
+};
+
+int make_plan(fx_pattern* p, Plan& pl) {
+    const fx::ByteTable& bt = p->prog.bt;
+    const DeviceTables& d = p->dev;
+    int classed_bytes = (int)bt.table.size() * 2, direct_bytes = (int)bt.direct.size() * 2;
+    bool direct_ok = d.direct != nullptr && direct_bytes <= DIRECT_LIMIT_BYTES;
+    bool classed_smem_ok = classed_bytes <= SMEM_TABLE_LIMIT_BYTES;
+    int res = p->residency;
+    if (res == FX_TABLE_SMEM && !direct_ok && !classed_smem_ok) return FX_ERR_BAD_ARGUMENT;
+    if (res == FX_TABLE_GLOBAL) { pl.direct = false; pl.tsmem = false; }
+    else if (direct_ok) { pl.direct = true; pl.tsmem = true; }
+    else if (classed_smem_ok) { pl.direct = false; pl.tsmem = true; }
+    else { pl.direct = false; pl.tsmem = false; }
+    pl.table_bytes = pl.direct ? direct_bytes : classed_bytes;
+    KParams& k = pl.kp;
+    k.table = pl.direct ? d.direct : d.table;
+    k.classmap = d.classmap;
+    k.flags = d.flags;
+    k.lits = d.lits;
+    k.table_words = pl.table_bytes / 2;
+    k.nstates = bt.nstates;
+    k.row_shift = pl.direct ? 8 : bt.row_shift;
+    k.start = bt.start; k.start_nul = bt.start_nul; k.q0 = bt.q0; k.q0_accepting = bt.q0_accepting ? 1 : 0;
+    const fx::Literals& L = p->prog.lit;
+    k.all_len = (int)L.all.size(); k.pre_len = (int)L.prefix.size(); k.suf_len = (int)L.suffix.size();
+    k.all_active = p->prog.literal_only ? 1 : 0;
+    k.pre_active = fx::fortran_blank(L.prefix) ? 0 : 1;
+    k.suf_active = fx::fortran_blank(L.suffix) ? 0 : 1;
+    k.a_table = d.a_table; k.a_classmap = d.a_classmap; k.a_flags = d.a_flags;
+    k.a_row_shift = p->has_anchored ? p->anchored.bt.row_shift : 0;
+    k.a_start_nul = p->has_anchored ? p->anchored.bt.start_nul : 0;
+    k.a_q0 = p->has_anchored ? p->anchored.bt.q0 : 0;
+    k.prefix_mode = p->prefix_mode;
+    p->last_residency = pl.tsmem ? FX_TABLE_SMEM : FX_TABLE_GLOBAL;
+    p->last_direct = pl.direct ? 1 : 0;
+    return FX_OK;
+}
+
+int check_ready(fx_pattern* p, int op) {
+    if (!p) return FX_ERR_BAD_ARGUMENT;
+    if (p->prog.status != fx::OK) return p->prog.status;
+    if (p->prog.op != op) return FX_ERR_BAD_ARGUMENT;
+    return ensure_device(p);
+}
+
+template <typename K>
+int occupancy_grid(K kernel, int threads, size_t smem, int sm_count, int& blocks_per_sm) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e);
+    }
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, threads, smem);
+    if (e != cudaSuccess) return cuda_status(e);
+    if (blocks_per_sm < 1) return FX_ERR_BAD_ARGUMENT;
+    (void)sm_count;
+    return FX_OK;
+}
+
+// ---- launchers -----------------------------------------------------------------------------
+template <int OP, bool DIRECT, bool TSMEM, int VEC>
+int launch_fixed_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, int64_t n, int64_t stride, uint8_t* out,
+                   cudaStream_t s, int generic) {
+    auto kern = k_bool_fixed<OP, DIRECT, TSMEM, VEC>;
+    size_t smem = 256 + (TSMEM ? (size_t)((pl.table_bytes + 15) & ~15) : 0);
+    int bps = 0;
+    int rc = occupancy_grid(kern, 256, smem, p->dev.sm_count, bps);
+    if (rc) return rc;
+    long long want = (n + 255) / 256;
+    long long cap = (long long)p->dev.sm_count * bps * 4;   // a few waves, grid-stride inside
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    kern<<<grid, 256, smem, s>>>(pl.kp, buf, n, stride, out, generic);
+    g_launches++;
+    return cuda_status(cudaGetLastError());
+}
+
+template <int OP, bool DIRECT, bool TSMEM>
+int launch_fixed_v(fx_pattern* p, const Plan& pl, const uint8_t* buf, int64_t n, int64_t stride, uint8_t* out,
+                   cudaStream_t s, int generic) {
+    uintptr_t a = reinterpret_cast<uintptr_t>(buf);
+    if (!generic && stride > 0 && stride % 16 == 0 && a % 16 == 0) return launch_fixed_t<OP, DIRECT, TSMEM, 16>(p, pl, buf, n, stride, out, s, generic);
+    if (!generic && stride > 0 && stride % 8 == 0 && a % 8 == 0) return launch_fixed_t<OP, DIRECT, TSMEM, 8>(p, pl, buf, n, stride, out, s, generic);
+    return launch_fixed_t<OP, DIRECT, TSMEM, 1>(p, pl, buf, n, stride, out, s, generic);
+}
+
+template <int OP>
+int launch_fixed(fx_pattern* p, const uint8_t* buf, int64_t n, int64_t stride, uint8_t* out, cudaStream_t s) {
+    if (n < 0 || stride < 0) return FX_ERR_BAD_ARGUMENT;
+    if (n == 0) return FX_OK;
+    Plan pl;
+    int rc = make_plan(p, pl);
+    if (rc) return rc;
+    int generic = (pl.kp.all_active || (OP == 0 && (pl.kp.pre_active || pl.kp.suf_active)) || (OP == 1 && pl.kp.prefix_mode == 2)) ? 1 : 0;
+    if (pl.direct) return launch_fixed_v<OP, true, true>(p, pl, buf, n, stride, out, s, generic);
+    if (pl.tsmem) return launch_fixed_v<OP, false, true>(p, pl, buf, n, stride, out, s, generic);
+    return launch_fixed_v<OP, false, false>(p, pl, buf, n, stride, out, s, generic);
+}
+
+struct Tiling {
+    int tile_bytes, slack;
+    int64_t ntiles;
+    int table_smem;  // rounded so that the tile starts 128-byte aligned
+    size_t smem;
+};
+
+Tiling make_tiling(const Plan& pl, int64_t n, int64_t total) {
+    Tiling t;
+    int64_t avg = n > 0 ? (total + n - 1) / n : 1;
+    if (avg < 1) avg = 1;
+    int64_t tb = avg * 256;
+    tb = (tb + 1023) & ~(int64_t)1023;
+    if (tb < 4096) tb = 4096;
+    if (tb > 32768) tb = 32768;
+    int64_t sl = 2 * avg;
+    sl = (sl + 255) & ~(int64_t)255;
+    if (sl < 256) sl = 256;
+    if (sl > 8192) sl = 8192;
+    t.tile_bytes = (int)tb;
+    t.slack = (int)sl;
+    t.ntiles = total / tb + 1;
+    int tbytes = pl.tsmem ? pl.table_bytes : 0;
+    t.table_smem = ((16 + 256 + tbytes + 127) & ~127) - (16 + 256);
+    t.smem = (size_t)(16 + 256 + t.table_smem) + (size_t)tb + (size_t)sl + 64;
+    return t;
+}
+
+template <int OP, bool DIRECT, bool TSMEM>
+int launch_ragged_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int64_t* off, int64_t n, int64_t total,
+                    uint8_t* out, cudaStream_t s, int generic) {
+    auto kern = k_bool_ragged<OP, DIRECT, TSMEM>;
+    Tiling t = make_tiling(pl, n, total);
+    int bps = 0;
+    int rc = occupancy_grid(kern, 256, t.smem, p->dev.sm_count, bps);
+    if (rc) return rc;
+    long long cap = (long long)p->dev.sm_count * bps;
+    int grid = (int)(t.ntiles < cap ? t.ntiles : cap);
+    if (grid < 1) grid = 1;
+    kern<<<grid, 256, t.smem, s>>>(pl.kp, buf, off, n, total, out, t.tile_bytes, t.slack, t.ntiles, t.table_smem, generic);
+    g_launches++;
+    return cuda_status(cudaGetLastError());
+}
+
+template <int OP>
+int launch_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, int64_t n, int64_t total, uint8_t* out,
+                  cudaStream_t s) {
+    if (n < 0 || total < 0) return FX_ERR_BAD_ARGUMENT;
+    if (n == 0) return FX_OK;
+    Plan pl;
+    int rc = make_plan(p, pl);
+    if (rc) return rc;
+    int generic = (pl.kp.all_active || (OP == 0 && (pl.kp.pre_active || pl.kp.suf_active)) || (OP == 1 && pl.kp.prefix_mode == 2)) ? 1 : 0;
+    if (pl.direct) return launch_ragged_t<OP, true, true>(p, pl, buf, off, n, total, out, s, generic);
+    if (pl.tsmem) return launch_ragged_t<OP, false, true>(p, pl, buf, off, n, total, out, s, generic);
+    return launch_ragged_t<OP, false, false>(p, pl, buf, off, n, total, out, s, generic);
+}
+
+template <bool DIRECT, bool TSMEM>
+int launch_regex_ragged_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int64_t* off, int64_t n,
+                          int64_t total, int64_t* from, int64_t* to, cudaStream_t s) {
+    auto kern = k_regex_ragged<DIRECT, TSMEM>;
+    Tiling t = make_tiling(pl, n, total);
+    int bps = 0;
+    int rc = occupancy_grid(kern, 256, t.smem, p->dev.sm_count, bps);
+    if (rc) return rc;
+    long long cap = (long long)p->dev.sm_count * bps;
+    int grid = (int)(t.ntiles < cap ? t.ntiles : cap);
+    if (grid < 1) grid = 1;
+    kern<<<grid, 256, t.smem, s>>>(pl.kp, buf, off, n, total, from, to, t.tile_bytes, t.slack, t.ntiles, t.table_smem);
+    g_launches++;
+    return cuda_status(cudaGetLastError());
+}
+
+int launch_regex_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, int64_t n, int64_t total,
+                        int64_t* from, int64_t* to, cudaStream_t s) {
+    if (n < 0 || total < 0) return FX_ERR_BAD_ARGUMENT;
+    if (n == 0) return FX_OK;
+    Plan pl;
+    int rc = make_plan(p, pl);
+    if (rc) return rc;
+    if (pl.direct) return launch_regex_ragged_t<true, true>(p, pl, buf, off, n, total, from, to, s);
+    if (pl.tsmem) return launch_regex_ragged_t<false, true>(p, pl, buf, off, n, total, from, to, s);
+    return launch_regex_ragged_t<false, false>(p, pl, buf, off, n, total, from, to, s);
+}
+
+template <bool DIRECT, bool TSMEM>
+int launch_buffer_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, int64_t len, int64_t* from_to,
+                    unsigned long long* best, cudaStream_t s) {
+    CUDA_TRY(cudaMemsetAsync(best, 0xFF, 8, s));
+    bool trivial = pl.kp.all_active || len <= 1;
+    if (!trivial) {
+        auto kern = k_buffer_scan<DIRECT, TSMEM>;
+        size_t smem = 256 + (TSMEM ? (size_t)((pl.table_bytes + 15) & ~15) : 0);
+        int bps = 0;
+        int rc = occupancy_grid(kern, 256, smem, p->dev.sm_count, bps);
+        if (rc) return rc;
+        long long units = (len >> 4) + 1;
+        long long want = (units + 255) / 256;
+        long long cap = (long long)p->dev.sm_count * bps;
+        int grid = (int)(want < cap ? want : cap);
+        if (grid < 1) grid = 1;
+        kern<<<grid, 256, smem, s>>>(pl.kp, buf, len, best);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (DIRECT) k_buffer_finish<true><<<1, 1, 0, s>>>(pl.kp, buf, len, best, from_to);
+    else k_buffer_finish<false><<<1, 1, 0, s>>>(pl.kp, buf, len, best, from_to);
+    g_launches++;
+    return cuda_status(cudaGetLastError());
+}
+
+int launch_buffer(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* from_to, unsigned long long* best,
+                  cudaStream_t s) {
+    if (len < 0) return FX_ERR_BAD_ARGUMENT;
+    // the parallel start sweep tries every character boundary; a pattern whose extracted prefix restricts
+    // the candidate starts (api_internal_m.F90:76-104) is not handled on this path yet
+    if (p->prog.prefix_active && !p->prog.literal_only) return FX_ERR_PREFILTER_UNSUPPORTED;
+    Plan pl;
+    int rc = make_plan(p, pl);
+    if (rc) return rc;
+    if (pl.direct) return launch_buffer_t<true, true>(p, pl, buf, len, from_to, best, s);
+    if (pl.tsmem) return launch_buffer_t<false, true>(p, pl, buf, len, from_to, best, s);
+    return launch_buffer_t<false, false>(p, pl, buf, len, from_to, best, s);
+}
+
+template <typename T>
+int grow(T*& ptr, size_t& cap, size_t need_bytes) {
+    if (need_bytes <= cap && ptr) return FX_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    size_t want = need_bytes + need_bytes / 8 + 256;
+    CUDA_TRY(cudaMalloc(&ptr, want));
+    cap = want;
+    return FX_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char* fx_status_message(int status) {
+    if (status < 0) return cudaGetErrorString((cudaError_t)(-status));
+    return fx::status_message(status);
+}
+
+int fx_compile(const void* pattern, int64_t plen, int op, fx_pattern** out) {
+    if (!out || plen < 0 || (plen > 0 && !pattern) || op < FX_OP_MATCH || op > FX_OP_REGEX) return FX_ERR_BAD_ARGUMENT;
+    fx_pattern* p = new (std::nothrow) fx_pattern();
+    if (!p) return fx::ERR_ALLOCATION;
+    std::string pat(static_cast<const char*>(pattern), (size_t)plen);
+    fx::compile_program(pat, op, STATE_CAP, p->prog);
+    if (p->prog.status == fx::OK && op == FX_OP_IN && p->prog.prefix_active && !p->prog.literal_only) {
+        // `.in.` consults the prefix prefilter; keep the anchored automaton to replay it exactly when needed
+        fx::compile_program(pat, FX_OP_REGEX, STATE_CAP, p->anchored);
+        if (p->anchored.status != fx::OK) p->prog.status = p->anchored.status;
+        else {
+            p->has_anchored = true;
+            p->prefix_mode = prefilter_is_neutral(p->anchored) ? 1 : 2;
+        }
+    }
+    *out = p;
+    return p->prog.status;
+}
+
+int fx_pattern_free(fx_pattern* p) {
+    if (!p) return FX_OK;
+    DeviceTables& d = p->dev;
+    if (d.device >= 0) {
+        cudaFree(d.table); cudaFree(d.direct); cudaFree(d.classmap); cudaFree(d.flags); cudaFree(d.lits);
+        cudaFree(d.a_table); cudaFree(d.a_classmap); cudaFree(d.a_flags);
+        cudaFree(d.w_buf); cudaFree(d.w_off); cudaFree(d.w_out); cudaFree(d.w_span); cudaFree(d.w_best);
+    }
+    delete p;
+    return FX_OK;
+}
+
+int fx_pattern_get_info(const fx_pattern* p, fx_pattern_info* info) {
+    if (!p || !info) return FX_ERR_BAD_ARGUMENT;
+    const fx::Program& g = p->prog;
+    memset(info, 0, sizeof(*info));
+    info->op = g.op;
+    info->status = g.status;
+    info->nfa_states = g.nfa_states;
+    info->cp_states = g.cp.nstates;
+    info->cp_classes = g.cp.nclasses;
+    info->byte_states = g.bt.nstates;
+    info->byte_classes = g.bt.nclasses;
+    info->row_shift = g.bt.row_shift;
+    info->table_bytes = (int32_t)g.bt.table.size() * 2;
+    info->direct_bytes = (int32_t)g.bt.direct.size() * 2;
+    info->literal_all_len = (int32_t)g.lit.all.size();
+    info->literal_prefix_len = (int32_t)g.lit.prefix.size();
+    info->literal_suffix_len = (int32_t)g.lit.suffix.size();
+    info->literal_only = g.literal_only ? 1 : 0;
+    info->residency = p->last_residency;
+    info->direct = p->last_direct;
+    info->prefix_mode = p->prefix_mode;
+    return FX_OK;
+}
+
+int fx_pattern_set_residency(fx_pattern* p, int residency) {
+    if (!p || residency < FX_TABLE_AUTO || residency > FX_TABLE_GLOBAL) return FX_ERR_BAD_ARGUMENT;
+    p->residency = residency;
+    return FX_OK;
+}
+
+int fx_pattern_literals(const fx_pattern* p, void* all, void* prefix, void* suffix) {
+    if (!p) return FX_ERR_BAD_ARGUMENT;
+    const fx::Literals& L = p->prog.lit;
+    if (all && !L.all.empty()) memcpy(all, L.all.data(), L.all.size());
+    if (prefix && !L.prefix.empty()) memcpy(prefix, L.prefix.data(), L.prefix.size());
+    if (suffix && !L.suffix.empty()) memcpy(suffix, L.suffix.data(), L.suffix.size());
+    return FX_OK;
+}
+
+int fx_pattern_tables(const fx_pattern* p, const uint16_t** table, const uint16_t** direct, const uint8_t** classmap,
+                      const uint8_t** flags, int32_t scalars[5]) {
+    if (!p || p->prog.status != fx::OK) return FX_ERR_BAD_ARGUMENT;
+    const fx::ByteTable& bt = p->prog.bt;
+    if (table) *table = bt.table.data();
+    if (direct) *direct = bt.direct.data();
+    if (classmap) *classmap = bt.classmap;
+    if (flags) *flags = bt.flags.data();
+    if (scalars) {
+        scalars[0] = bt.start; scalars[1] = bt.start_nul; scalars[2] = bt.q0; scalars[3] = bt.matched;
+        scalars[4] = bt.q0_accepting ? 1 : 0;
+    }
+    return FX_OK;
+}
+
+int fx_is_valid_regex(const void* pattern, int64_t plen, int* status) {  // forgex.F90:58-71
+    if (plen < 0 || (plen > 0 && !pattern)) return FX_ERR_BAD_ARGUMENT;
+    fx::Syntax syn;
+    fx::parse_pattern(fx::prepare_pattern(std::string(static_cast<const char*>(pattern), (size_t)plen), false), syn);
+    if (status) *status = syn.status;
+    return syn.valid() ? 1 : 0;
+}
+
+// ---- device-pointer entry points ------------------------------------------------------------
+int fx_match_fixed_dev(fx_pattern* p, const uint8_t* d_buf, int64_t n, int64_t stride, uint8_t* d_out, void* stream) {
+    int rc = check_ready(p, FX_OP_MATCH);
+    if (rc) return rc;
+    return launch_fixed<0>(p, d_buf, n, stride, d_out, (cudaStream_t)stream);
+}
+int fx_in_fixed_dev(fx_pattern* p, const uint8_t* d_buf, int64_t n, int64_t stride, uint8_t* d_out, void* stream) {
+    int rc = check_ready(p, FX_OP_IN);
+    if (rc) return rc;
+    return launch_fixed<1>(p, d_buf, n, stride, d_out, (cudaStream_t)stream);
+}
+int fx_match_batch_dev(fx_pattern* p, const uint8_t* d_buf, const int64_t* d_offsets, int64_t n, int64_t total_bytes,
+                       uint8_t* d_out, void* stream) {
+    int rc = check_ready(p, FX_OP_MATCH);
+    if (rc) return rc;
+    return launch_ragged<0>(p, d_buf, d_offsets, n, total_bytes, d_out, (cudaStream_t)stream);
+}
+int fx_in_batch_dev(fx_pattern* p, const uint8_t* d_buf, const int64_t* d_offsets, int64_t n, int64_t total_bytes,
+                    uint8_t* d_out, void* stream) {
+    int rc = check_ready(p, FX_OP_IN);
+    if (rc) return rc;
+    return launch_ragged<1>(p, d_buf, d_offsets, n, total_bytes, d_out, (cudaStream_t)stream);
+}
+int fx_regex_batch_dev(fx_pattern* p, const uint8_t* d_buf, const int64_t* d_offsets, int64_t n, int64_t total_bytes,
+                       int64_t* d_from, int64_t* d_to, void* stream) {
+    int rc = check_ready(p, FX_OP_REGEX);
+    if (rc) return rc;
+    return launch_regex_ragged(p, d_buf, d_offsets, n, total_bytes, d_from, d_to, (cudaStream_t)stream);
+}
+int64_t fx_regex_buffer_work_bytes(int64_t len) { (void)len; return 64; }
+int fx_regex_buffer_dev(fx_pattern* p, const uint8_t* d_buf, int64_t len, int64_t* d_from_to, void* d_work, void* stream) {
+    int rc = check_ready(p, FX_OP_REGEX);
+    if (rc) return rc;
+    if (!d_work) return FX_ERR_BAD_ARGUMENT;
+    return launch_buffer(p, d_buf, len, d_from_to, static_cast<unsigned long long*>(d_work), (cudaStream_t)stream);
+}
+
+// ---- host-pointer entry points ----------------------------------------------------------------
+static int host_bool_fixed(fx_pattern* p, int op, const uint8_t* buf, int64_t n, int64_t stride, uint8_t* out) {
+    int rc = check_ready(p, op);
+    if (rc) return rc;
+    if (n < 0 || stride < 0) return FX_ERR_BAD_ARGUMENT;
+    if (n == 0) return FX_OK;
+    std::lock_guard<std::mutex> lock(p->mu);
+    DeviceTables& d = p->dev;
+    size_t bytes = (size_t)n * (size_t)stride;
+    if ((rc = grow(d.w_buf, d.w_buf_cap, bytes + 16))) return rc;
+    if ((rc = grow(d.w_out, d.w_out_cap, (size_t)n))) return rc;
+    if (bytes) CUDA_TRY(cudaMemcpyAsync(d.w_buf, buf, bytes, cudaMemcpyHostToDevice, 0));
+    rc = op == FX_OP_MATCH ? launch_fixed<0>(p, d.w_buf, n, stride, d.w_out, 0) : launch_fixed<1>(p, d.w_buf, n, stride, d.w_out, 0);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, d.w_out, (size_t)n, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return FX_OK;
+}
+int fx_match_fixed(fx_pattern* p, const uint8_t* buf, int64_t n, int64_t stride, uint8_t* out) {
+    return host_bool_fixed(p, FX_OP_MATCH, buf, n, stride, out);
+}
+int fx_in_fixed(fx_pattern* p, const uint8_t* buf, int64_t n, int64_t stride, uint8_t* out) {
+    return host_bool_fixed(p, FX_OP_IN, buf, n, stride, out);
+}
+
+static int host_stage_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* offsets, int64_t n, int64_t& total) {
+    DeviceTables& d = p->dev;
+    int64_t base = offsets[0];
+    total = offsets[n] - base;
+    if (total < 0 || base != 0) return FX_ERR_BAD_ARGUMENT;   // offsets must start at 0
+    int rc;
+    if ((rc = grow(d.w_buf, d.w_buf_cap, (size_t)total + 16))) return rc;
+    if ((rc = grow(d.w_off, d.w_off_cap, (size_t)(n + 1) * 8))) return rc;
+    if (total) CUDA_TRY(cudaMemcpyAsync(d.w_buf, buf, (size_t)total, cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemcpyAsync(d.w_off, offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, 0));
+    return FX_OK;
+}
+static int host_bool_ragged(fx_pattern* p, int op, const uint8_t* buf, const int64_t* offsets, int64_t n, uint8_t* out) {
+    int rc = check_ready(p, op);
+    if (rc) return rc;
+    if (n < 0 || !offsets) return FX_ERR_BAD_ARGUMENT;
+    if (n == 0) return FX_OK;
+    std::lock_guard<std::mutex> lock(p->mu);
+    DeviceTables& d = p->dev;
+    int64_t total = 0;
+    if ((rc = host_stage_ragged(p, buf, offsets, n, total))) return rc;
+    if ((rc = grow(d.w_out, d.w_out_cap, (size_t)n))) return rc;
+    rc = op == FX_OP_MATCH ? launch_ragged<0>(p, d.w_buf, d.w_off, n, total, d.w_out, 0)
+                           : launch_ragged<1>(p, d.w_buf, d.w_off, n, total, d.w_out, 0);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, d.w_out, (size_t)n, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return FX_OK;
+}
+int fx_match_batch(fx_pattern* p, const uint8_t* buf, const int64_t* offsets, int64_t n, uint8_t* out) {
+    return host_bool_ragged(p, FX_OP_MATCH, buf, offsets, n, out);
+}
+int fx_in_batch(fx_pattern* p, const uint8_t* buf, const int64_t* offsets, int64_t n, uint8_t* out) {
+    return host_bool_ragged(p, FX_OP_IN, buf, offsets, n, out);
+}
+int fx_regex_batch(fx_pattern* p, const uint8_t* buf, const int64_t* offsets, int64_t n, int64_t* from, int64_t* to) {
+    int rc = check_ready(p, FX_OP_REGEX);
+    if (rc) return rc;
+    if (n < 0 || !offsets) return FX_ERR_BAD_ARGUMENT;
+    if (n == 0) return FX_OK;
+    std::lock_guard<std::mutex> lock(p->mu);
+    DeviceTables& d = p->dev;
+    int64_t total = 0;
+    if ((rc = host_stage_ragged(p, buf, offsets, n, total))) return rc;
+    if ((rc = grow(d.w_span, d.w_span_cap, (size_t)n * 16))) return rc;
+    rc = launch_regex_ragged(p, d.w_buf, d.w_off, n, total, d.w_span, d.w_span + n, 0);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(from, d.w_span, (size_t)n * 8, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaMemcpyAsync(to, d.w_span + n, (size_t)n * 8, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return FX_OK;
+}
+int fx_regex_buffer(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* from, int64_t* to) {
+    int rc = check_ready(p, FX_OP_REGEX);
+    if (rc) return rc;
+    if (len < 0) return FX_ERR_BAD_ARGUMENT;
+    std::lock_guard<std::mutex> lock(p->mu);
+    DeviceTables& d = p->dev;
+    if ((rc = grow(d.w_buf, d.w_buf_cap, (size_t)len + 16))) return rc;
+    if ((rc = grow(d.w_span, d.w_span_cap, 16))) return rc;
+    if (len) CUDA_TRY(cudaMemcpyAsync(d.w_buf, buf, (size_t)len, cudaMemcpyHostToDevice, 0));
+    rc = launch_buffer(p, d.w_buf, len, d.w_span, d.w_best, 0);
+    if (rc) return rc;
+    int64_t ft[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(ft, d.w_span, 16, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    if (from) *from = ft[0];
+    if (to) *to = ft[1];
+    return FX_OK;
+}
+
+// ---- one pattern, one text ----------------------------------------------------------------------
+int fx_in(const void* pattern, int64_t plen, const void* text, int64_t tlen, int* result) {
+    if (!result || tlen < 0) return FX_ERR_BAD_ARGUMENT;
+    fx_pattern* p = nullptr;
+    int rc = fx_compile(pattern, plen, FX_OP_IN, &p);
+    if (rc >= 1 && rc <= 24) { *result = 0; fx_pattern_free(p); return FX_OK; }   // invalid pattern -> .false. (forgex.F90:101-104)
+    if (rc) { fx_pattern_free(p); return rc; }
+    uint8_t out = 0;
+    rc = fx_in_fixed(p, static_cast<const uint8_t*>(text), 1, tlen, &out);
+    *result = out;
+    fx_pattern_free(p);
+    return rc;
+}
+int fx_match(const void* pattern, int64_t plen, const void* text, int64_t tlen, int* result) {
+    if (!result || tlen < 0) return FX_ERR_BAD_ARGUMENT;
+    fx_pattern* p = nullptr;
+    int rc = fx_compile(pattern, plen, FX_OP_MATCH, &p);
+    if (rc >= 1 && rc <= 24) { *result = 0; fx_pattern_free(p); return FX_OK; }   // forgex.F90:197-200
+    if (rc) { fx_pattern_free(p); return rc; }
+    uint8_t out = 0;
+    rc = fx_match_fixed(p, static_cast<const uint8_t*>(text), 1, tlen, &out);
+    *result = out;
+    fx_pattern_free(p);
+    return rc;
+}
+int fx_regex(const void* pattern, int64_t plen, const void* text, int64_t tlen, int64_t* from, int64_t* to,
+             int64_t* length, int* status) {
+    if (tlen < 0) return FX_ERR_BAD_ARGUMENT;
+    fx_pattern* p = nullptr;
+    int rc = fx_compile(pattern, plen, FX_OP_REGEX, &p);
+    if (status) *status = (rc >= 1 && rc <= 24) ? rc : 0;
+    if (rc >= 1 && rc <= 24) {   // forgex.F90:266-274
+        if (from) *from = -9999;
+        if (to) *to = -9999;
+        if (length) *length = 0;
+        fx_pattern_free(p);
+        return FX_OK;
+    }
+    if (rc) { fx_pattern_free(p); return rc; }
+    int64_t off[2] = {0, tlen}, f = 0, t = 0;
+    rc = fx_regex_batch(p, static_cast<const uint8_t*>(text), off, 1, &f, &t);
+    if (from) *from = f;
+    if (to) *to = t;
+    if (length) *length = (f > 0 && t > 0) ? t - f + 1 : 0;
+    fx_pattern_free(p);
+    return rc;
+}
+
+int64_t fx_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"

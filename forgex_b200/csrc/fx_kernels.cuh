@@ -1,0 +1,700 @@
+// fx_kernels.cuh -- sm_100a kernels of the Forgex matching path.
+//
+// Every kernel is "walk the byte-level DFA table, read a flag": the transition loop that the
+// reference executes per character in do_matching_exactly / do_matching_including
+// (/root/reference/src/api_internal_m.F90:119-137, :258-295) with automaton%construct
+// (/root/reference/src/automaton_m.F90:333-381) replaced by one table lookup per BYTE.
+// This is HBM-bound integer work: no tensor cores.  What matters: text is read
+// from HBM exactly once in coalesced 16-byte pieces (TMA bulk copies into shared memory for
+// ragged batches), the table lives in shared memory, one dependent LDS per byte per thread and
+// enough threads per SM to hide its latency.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fxk {
+
+// word layout (must match fx_internal.hpp)
+static constexpr uint32_t W_ACC = 0x8000u, W_INTER = 0x4000u, W_STATE = 0x3FFFu;
+static constexpr uint32_t SF_ACC = 1, SF_END = 2, SF_INTER = 4, SF_MATCHED = 8, SF_FAILACC1 = 16;
+
+struct KParams {
+    const uint16_t* table;    // selected table in global memory (class-compressed or 256-column)
+    const uint8_t* classmap;  // 256 bytes
+    const uint8_t* flags;     // nstates bytes
+    const uint8_t* lits;      // all | prefix | suffix, back to back
+    int table_words;
+    int nstates;
+    int row_shift;            // 8 for the 256-column table
+    int start, start_nul, q0, q0_accepting;
+    int all_len, pre_len, suf_len;
+    int all_active;           // `all` is not blank: literal fast path (forgex.F90:111-130, :207-213, :281-307)
+    int pre_active, suf_active;  // prefix / suffix not blank
+    // `.in.` with an active prefix: the anchored (REGEX-mode, flag-bit) class-compressed table, used to
+    // replay Forgex's prefix-candidate search exactly (api_internal_m.F90:76-164) when it can matter
+    const uint16_t* a_table;
+    const uint8_t* a_classmap;
+    const uint8_t* a_flags;
+    int a_row_shift, a_start_nul, a_q0;
+    int prefix_mode;          // 0: none; 1: neutral unless the text holds bytes >= 0x80; 2: always replay
+};
+
+// ---- small PTX helpers ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {  // streaming 16-byte load, no L1 allocation
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_nc_v2(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t phase) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok) : "r"(mbar), "r"(phase) : "memory");
+    } while (!ok);
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+// ---- table access --------------------------------------------------------------------------
+// TSMEM: table (and classmap) staged in shared memory; otherwise read through L1/L2 with __ldg.
+template <bool DIRECT, bool TSMEM>
+struct Table {
+    uint32_t s_table, s_cmap;  // shared addresses (TSMEM)
+    const uint16_t* g_table;
+    const uint8_t* g_cmap;
+    int shift;
+    __device__ __forceinline__ uint32_t next(uint32_t state, uint32_t byte) const {
+        if (TSMEM) {
+            if (DIRECT) return lds_u16(s_table + (((state << 8) | byte) << 1));
+            uint32_t c = lds_u8(s_cmap + byte);
+            return lds_u16(s_table + (((state << shift) + c) << 1));
+        } else {
+            if (DIRECT) return __ldg(g_table + ((state << 8) | byte));
+            uint32_t c = __ldg(g_cmap + byte);
+            return __ldg(g_table + ((state << shift) + c));
+        }
+    }
+};
+
+// cooperative copy of the table into shared memory; returns the filled Table
+template <bool DIRECT, bool TSMEM>
+__device__ __forceinline__ Table<DIRECT, TSMEM> stage_table(const KParams& p, uint8_t* smem_table, uint8_t* smem_cmap) {
+    Table<DIRECT, TSMEM> t;
+    t.g_table = p.table; t.g_cmap = p.classmap; t.shift = p.row_shift;
+    t.s_table = 0; t.s_cmap = 0;
+    if (TSMEM) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.table);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem_table);
+        int words32 = (p.table_words + 1) >> 1;
+        for (int i = threadIdx.x; i < words32; i += blockDim.x) dst[i] = __ldg(src + i);
+        if (!DIRECT)
+            for (int i = threadIdx.x; i < 64; i += blockDim.x)
+                reinterpret_cast<uint32_t*>(smem_cmap)[i] = __ldg(reinterpret_cast<const uint32_t*>(p.classmap) + i);
+        t.s_table = smem_u32(smem_table);
+        t.s_cmap = smem_u32(smem_cmap);
+    }
+    return t;
+}
+
+__device__ __forceinline__ bool result_flag(const KParams& p, uint32_t state) {
+    return (__ldg(p.flags + state) & (SF_END | SF_MATCHED)) != 0;
+}
+
+// Text of length 0, or one blank, never reaches the `.in.`/`regex` loop (api_internal_m.F90:68-74);
+// empty text never reaches the `.match.` loop (:247-250).
+template <int OP>
+__device__ __forceinline__ bool degenerate_text(int64_t len, uint32_t first_byte) {
+    if (OP == 0) return len == 0;
+    return len == 0 || (len == 1 && first_byte == 0x20);
+}
+
+// ---------------------------------------------------------------------------------------------
+// spans: leftmost start, longest end -- the loop of do_matching_including (api_internal_m.F90:108-164)
+// ---------------------------------------------------------------------------------------------
+struct FetchGeneric {
+    const uint8_t* s;
+    __device__ __forceinline__ uint32_t operator()(int64_t i) const { return s[i]; }
+};
+struct FetchGlobal {
+    const uint8_t* s;
+    __device__ __forceinline__ uint32_t operator()(int64_t i) const { return __ldg(s + i); }
+};
+struct FetchShared {
+    uint32_t a;
+    __device__ __forceinline__ uint32_t operator()(int64_t i) const { return lds_u8(a + (uint32_t)i); }
+};
+
+// the anchored automaton a span search runs on (flag-bit table)
+struct Anchored {
+    const uint8_t* flags;
+    int start_nul, q0;
+};
+
+// One anchored attempt starting with `st` before text index `pos`.  `last` is -1 or the number of
+// text bytes consumed at the last accepting boundary (len+1 = the trailing NUL was consumed too).
+// A malformed multi-byte sequence is replayed by the table as U+FFFF per byte; accepts that fall
+// between those replayed bytes are recovered from the SF_FAILACC bits of the in-sequence state.
+template <class TBL, class FETCH>
+__device__ __forceinline__ int64_t run_attempt(const Anchored& A, const TBL& T, FETCH fetch, int64_t len, uint32_t st,
+                                               int64_t pos, int64_t last) {
+    uint32_t w = st;           // previous word (INTER bit tells whether we are inside a sequence)
+    int64_t seq = 0;           // index of the lead byte of the sequence in flight
+    bool inter = false;
+    if ((w & W_STATE) == 0) return last;
+    for (int64_t j = pos; j <= len; j++) {
+        const uint32_t b = j < len ? fetch(j) : 0u;     // virtual trailing NUL at j == len
+        if (inter && (b & 0xC0) != 0x80) {              // sequence broken: pending bytes replay as U+FFFF
+            const uint32_t f = __ldg(A.flags + (w & W_STATE));
+            const int pending = (int)(j - seq);
+            for (int k = 1; k <= pending; k++)
+                if (f & (SF_FAILACC1 << (k - 1))) last = seq + k;
+            inter = false;                              // byte j starts afresh (it may itself be a lead byte)
+        }
+        const uint32_t nw = T.next(w & W_STATE, b);
+        if ((nw & W_INTER) && !inter) seq = j;
+        inter = (nw & W_INTER) != 0;
+        w = nw;
+        if (w & W_ACC) last = j + 1;
+        if ((w & W_STATE) == 0) break;
+    }
+    return last;
+}
+
+// attempt from position `start` of S = NUL || text || NUL (1-based, as in the reference)
+template <class TBL, class FETCH>
+__device__ __forceinline__ int64_t attempt_at(const Anchored& A, const TBL& T, FETCH fetch, int64_t len, int64_t start) {
+    if (start == 1) {
+        if (A.start_nul == 0) return -1;
+        int64_t last = (__ldg(A.flags + A.start_nul) & SF_ACC) ? 0 : -1;
+        return run_attempt(A, T, fetch, len, (uint32_t)A.start_nul, 0, last);
+    }
+    return run_attempt(A, T, fetch, len, (uint32_t)A.q0, start - 2, -1);
+}
+
+// length of the character at `pos` under the reference's strict decoder (utf8_m.f90:168-246)
+template <class FETCH>
+__device__ __forceinline__ int char_len(FETCH fetch, int64_t len, int64_t pos) {
+    const uint32_t b = fetch(pos);
+    int n;
+    if (b < 0x80) return 1;
+    else if ((b >> 5) == 6) n = 2;
+    else if ((b >> 4) == 14) n = 3;
+    else if ((b >> 3) == 30) n = 4;
+    else return 1;
+    if (pos + n > len) return 1;
+    for (int k = 1; k < n; k++)
+        if ((fetch(pos + k) & 0xC0) != 0x80) return 1;
+    return n;
+}
+
+// S(i): byte i (1-based) of NUL || text || NUL
+template <class FETCH>
+__device__ __forceinline__ uint32_t framed(FETCH fetch, int64_t len, int64_t i) {
+    return (i <= 1 || i >= len + 2) ? 0u : fetch(i - 2);
+}
+// index(S(from:), lit) + from - 1, or 0 (Fortran index(): an empty literal is found at `from`)
+template <class FETCH>
+__device__ inline int64_t framed_index(FETCH fetch, int64_t len, const uint8_t* lit, int n, int64_t from) {
+    const int64_t m = len + 2;
+    for (int64_t pos = from; pos + n - 1 <= m; pos++) {
+        bool eq = true;
+        for (int k = 0; k < n && eq; k++) eq = framed(fetch, len, pos + k) == __ldg(lit + k);
+        if (eq) return pos;
+    }
+    return 0;
+}
+// index(x, lit, back=.true.) over S (framed != 0) or over the bare text; 0 if absent
+template <class FETCH>
+__device__ inline int64_t index_back(FETCH fetch, int64_t len, const uint8_t* lit, int n, bool over_frame) {
+    const int64_t m = over_frame ? len + 2 : len;
+    if (n > m) return 0;
+    for (int64_t pos = m - n + 1; pos >= 1; pos--) {
+        bool eq = true;
+        for (int k = 0; k < n && eq; k++)
+            eq = (over_frame ? framed(fetch, len, pos + k) : fetch(pos - 1 + k)) == __ldg(lit + k);
+        if (eq) return pos;
+    }
+    return 0;
+}
+
+// do_matching_including for a non-blank text (api_internal_m.F90:76-164): candidate starts are either
+// every character boundary (no usable prefix) or the non-overlapping occurrences of the extracted
+// prefix in S (utility_m.f90:58-117), cut short by the last occurrence of the extracted suffix.
+// Writes the reference's (from, to) before the wrapper's `from>0 .and. to>0` test.
+template <class TBL, class FETCH>
+__device__ inline void including_exact(const Anchored& A, const TBL& T, FETCH fetch, int64_t len,
+                                       const uint8_t* pre, int pre_len, bool pre_active,
+                                       const uint8_t* suf, int suf_len, bool suf_active,
+                                       int64_t& from, int64_t& to) {
+    const int64_t NONE = -9999;
+    const int64_t m = len + 2;
+    from = 0; to = 0;
+    bool brute = !pre_active;
+    int64_t first = NONE, frame_suf = NONE, offset = 0;
+    bool more = false;
+    if (!brute) {
+        const int64_t idx = framed_index(fetch, len, pre, pre_len, 1);
+        frame_suf = index_back(fetch, len, suf, suf_len, true);
+        if (frame_suf == 0) frame_suf = NONE;
+        if (idx > 0) {
+            if (frame_suf != NONE) { if (idx <= frame_suf) first = idx; }
+            else first = idx;
+            offset = idx + pre_len - 1;
+            more = true;
+        }
+        if (first == NONE) brute = true;
+    }
+    if (brute) {
+        int64_t last = attempt_at(A, T, fetch, len, 1);
+        if (last >= 0) { from = 1; to = last < len ? last : len; return; }
+        int64_t pos = 0;
+        while (pos < len) {
+            last = run_attempt(A, T, fetch, len, (uint32_t)A.q0, pos, -1);
+            if (last >= 0) { from = pos + 1; to = last < len ? last : len; return; }
+            pos += char_len(fetch, len, pos);
+        }
+        return;
+    }
+    bool at_zero = first == 2;                 // "i = 0": try the leading NUL before the first occurrence
+    int64_t start = at_zero ? 1 : first;
+    int64_t text_suf = NONE;
+    if (suf_active) {
+        text_suf = index_back(fetch, len, suf, suf_len, false);
+        if (text_suf == 0) return;
+    }
+    while (start < m) {
+        if (text_suf != NONE && text_suf < start) return;
+        const int64_t last = attempt_at(A, T, fetch, len, start);
+        if (last >= 0) {
+            from = start - 1 < 1 ? 1 : start - 1;
+            to = last < len ? last : len;      // max_match >= len(str) -> len(string), else max_match - 2
+            return;
+        }
+        if (at_zero) { at_zero = false; start = first; continue; }
+        if (!more || !(offset < m)) return;
+        const int64_t hit = framed_index(fetch, len, pre, pre_len, offset + 1);
+        if (hit <= 0) return;
+        start = hit;
+        offset = hit + pre_len - 1;            // offset + idx + len_pre - 1 with idx = hit - offset
+        if (frame_suf != NONE && offset > frame_suf) more = false;
+    }
+}
+
+// `.in.` through the exact prefix-candidate search (pattern has a non-blank prefix, `all` is blank)
+template <class FETCH>
+__device__ inline bool in_with_prefix(const KParams& p, FETCH fetch, int64_t len) {
+    if (len == 0 || (len == 1 && fetch(0) == 0x20)) return p.q0_accepting != 0;
+    Table<false, false> T;
+    T.g_table = p.a_table; T.g_cmap = p.a_classmap; T.shift = p.a_row_shift; T.s_table = 0; T.s_cmap = 0;
+    Anchored A{p.a_flags, p.a_start_nul, p.a_q0};
+    int64_t f, t;
+    including_exact(A, T, fetch, len, p.lits + p.all_len, p.pre_len, p.pre_active != 0,
+                    p.lits + p.all_len + p.pre_len, p.suf_len, p.suf_active != 0, f, t);
+    return f > 0 && t > 0;
+}
+
+// full regex() semantics for one text; writes Forgex's (from, to) (0,0 = no match)
+template <class TBL, class FETCH>
+__device__ inline void eval_regex(const KParams& p, const TBL& T, FETCH fetch, int64_t len, int64_t& from, int64_t& to) {
+    from = 0; to = 0;
+    if (p.all_active) {  // literal fast path (forgex.F90:281-307)
+        const int n = p.all_len;
+        for (int64_t i = 0; i + n <= len; i++) {
+            bool eq = true;
+            for (int k = 0; k < n && eq; k++) eq = fetch(i + k) == __ldg(p.lits + k);
+            if (eq) { from = i + 1; to = i + n; return; }
+        }
+        return;
+    }
+    if (len == 0 || (len == 1 && fetch(0) == 0x20)) return;      // api_internal_m.F90:68-74 -> '' / 0 / 0
+    Anchored A{p.flags, p.start_nul, p.q0};
+    int64_t f, t;
+    including_exact(A, T, fetch, len, p.lits + p.all_len, p.pre_len, p.pre_active != 0,
+                    p.lits + p.all_len + p.pre_len, p.suf_len, p.suf_active != 0, f, t);
+    if (f > 0 && t > 0) { from = f; to = t; }                    // forgex.F90:332-343
+}
+
+// ---- generic (slow) evaluation: full wrapper semantics incl. literal paths -------------------
+// Used when a pattern has literal gates, and by strings that do not fit a staged tile.
+__device__ __forceinline__ bool lit_equal(const uint8_t* a, const uint8_t* lit, int n) {
+    for (int i = 0; i < n; i++) if (a[i] != __ldg(lit + i)) return false;
+    return true;
+}
+// index(text, lit): 1-based position of the first occurrence, 0 if none (forgex.F90:114, :284)
+__device__ inline int64_t lit_index(const uint8_t* s, int64_t len, const uint8_t* lit, int n) {
+    if (n > len) return 0;
+    if (n == 0) return 1;
+    for (int64_t i = 0; i + n <= len; i++)
+        if (lit_equal(s + i, lit, n)) return i + 1;
+    return 0;
+}
+
+template <int OP, bool DIRECT, bool TSMEM>
+__device__ inline bool eval_bool_generic(const KParams& p, const Table<DIRECT, TSMEM>& T, const uint8_t* s, int64_t len) {
+    const uint8_t* all = p.lits;
+    const uint8_t* pre = p.lits + p.all_len;
+    const uint8_t* suf = pre + p.pre_len;
+    if (OP == 1) {
+        if (p.all_active) return lit_index(s, len, all, p.all_len) > 0;
+        if (p.prefix_mode == 2) return in_with_prefix(p, FetchGeneric{s}, len);
+    } else {
+        if (p.all_active && len == p.all_len) return lit_equal(s, all, p.all_len);
+        // prefix / suffix gate of do_matching_exactly (api_internal_m.F90:199-233)
+        int64_t lp = p.pre_len, ls = p.suf_len;
+        if (len > 0 && lp > 0 && lp == len && lit_equal(s, pre, (int)lp)) return true;
+        if (lp > len || ls > len) return false;
+        if (len > 0) {
+            if (p.pre_active && !lit_equal(s, pre, (int)lp)) return false;
+            if (p.suf_active && !lit_equal(s + (len - ls), suf, (int)ls)) return false;
+        } else {
+            if (p.pre_active && lp != 0) return false;
+            if (p.suf_active && ls != 0) return false;
+        }
+    }
+    if (degenerate_text<OP>(len, len ? s[0] : 0)) return p.q0_accepting != 0;
+    uint32_t st = (uint32_t)p.start;
+    uint32_t high = 0;
+    for (int64_t i = 0; i < len; i++) { uint32_t b = s[i]; high |= b; st = T.next(st, b); }
+    bool r = result_flag(p, st);
+    if (OP == 1 && r && p.prefix_mode == 1 && (high & 0x80)) r = in_with_prefix(p, FetchGeneric{s}, len);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: fixed-stride batch, boolean result (configs C1 `.match.` 8-byte strings, C5 `.in.` 64-byte)
+// One thread per string; consecutive threads read consecutive strings, so a warp's loads cover a
+// contiguous 32*stride-byte span.
+// ---------------------------------------------------------------------------------------------
+template <bool DIRECT, bool TSMEM>
+__device__ __forceinline__ uint32_t step4(const Table<DIRECT, TSMEM>& T, uint32_t st, uint32_t w) {
+    st = T.next(st, w & 0xFF);
+    st = T.next(st, (w >> 8) & 0xFF);
+    st = T.next(st, (w >> 16) & 0xFF);
+    st = T.next(st, w >> 24);
+    return st;
+}
+
+template <int OP, bool DIRECT, bool TSMEM, int VEC>
+__global__ void __launch_bounds__(256) k_bool_fixed(KParams p, const uint8_t* __restrict__ buf, int64_t n, int64_t stride,
+                                                    uint8_t* __restrict__ out, int generic) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_cmap = smem;
+    uint8_t* s_table = smem + 256;
+    Table<DIRECT, TSMEM> T = stage_table<DIRECT, TSMEM>(p, s_table, s_cmap);
+    if (TSMEM) __syncthreads();
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gstride) {
+        const uint8_t* s = buf + i * stride;
+        bool r;
+        if (generic) {
+            r = eval_bool_generic<OP, DIRECT, TSMEM>(p, T, s, stride);
+        } else if (degenerate_text<OP>(stride, stride ? s[0] : 0)) {
+            r = p.q0_accepting != 0;
+        } else {
+            uint32_t st = (uint32_t)p.start;
+            uint32_t high = 0;
+            if (VEC == 16) {
+                for (int64_t k = 0; k < stride; k += 16) {
+                    uint4 v = ldg_nc_v4(s + k);
+                    high |= v.x | v.y | v.z | v.w;
+                    st = step4(T, st, v.x); st = step4(T, st, v.y); st = step4(T, st, v.z); st = step4(T, st, v.w);
+                }
+            } else if (VEC == 8) {
+                for (int64_t k = 0; k < stride; k += 8) {
+                    uint2 v = ldg_nc_v2(s + k);
+                    high |= v.x | v.y;
+                    st = step4(T, st, v.x); st = step4(T, st, v.y);
+                }
+            } else {
+                for (int64_t k = 0; k < stride; k++) { uint32_t b = __ldg(s + k); high |= b; st = T.next(st, b); }
+            }
+            r = result_flag(p, st);
+            if (OP == 1 && r && p.prefix_mode == 1 && (high & 0x80808080u)) r = in_with_prefix(p, FetchGlobal{s}, stride);
+        }
+        out[i] = r ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: ragged batch (flat buffer + int64 offsets), boolean result (config C2 `.in.`)
+// A CTA owns tile t = bytes [t*tile_bytes, (t+1)*tile_bytes) of the flat buffer and the strings that
+// START inside it.  The tile (plus `slack` bytes so that most strings end inside the staged region)
+// is brought into shared memory by ONE TMA bulk copy; each thread then walks one string out of
+// shared memory.  Strings that run past the staged region are walked from global memory.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t lower_bound_i64(const int64_t* __restrict__ a, int64_t n, int64_t key) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Stage bytes [t0, t1) of buf into shared memory at `tile` such that byte x lives at tile[x - base],
+// base = t0 rounded down so that the global source is 16-byte aligned.  Returns base.
+__device__ __forceinline__ int64_t stage_tile(const uint8_t* __restrict__ buf, int64_t t0, int64_t t1, int64_t total,
+                                              uint8_t* tile, uint32_t mbar, uint32_t& phase) {
+    const uintptr_t g0 = reinterpret_cast<uintptr_t>(buf) + (uintptr_t)t0;
+    const int64_t base = t0 - (int64_t)(g0 & 15);                       // may be < 0 by up to 15 (stays inside the allocation)
+    const uintptr_t gend = reinterpret_cast<uintptr_t>(buf) + (uintptr_t)total;
+    uintptr_t gcopy_end = (reinterpret_cast<uintptr_t>(buf) + (uintptr_t)t1 + 15) & ~(uintptr_t)15;
+    const uintptr_t gsafe_end = gend & ~(uintptr_t)15;                   // never bulk-read past the last whole 16-byte block
+    if (gcopy_end > gsafe_end) gcopy_end = gsafe_end;
+    const uintptr_t gsrc = g0 & ~(uintptr_t)15;
+    const uint32_t bulk = gcopy_end > gsrc ? (uint32_t)(gcopy_end - gsrc) : 0u;
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(mbar, bulk);
+            bulk_g2s(smem_u32(tile), reinterpret_cast<const void*>(gsrc), bulk, mbar);
+        }
+    }
+    // tail (< 16 bytes at the very end of the buffer): plain loads
+    const int64_t copied_to = (int64_t)(gsrc + bulk - reinterpret_cast<uintptr_t>(buf));
+    for (int64_t x = copied_to + threadIdx.x; x < t1; x += blockDim.x)
+        if (x >= 0) tile[x - base] = __ldg(buf + x);
+    if (bulk) { mbar_wait(mbar, phase); phase ^= 1; }
+    __syncthreads();
+    return base;
+}
+
+template <bool DIRECT, bool TSMEM>
+__device__ __forceinline__ uint32_t walk_smem(const Table<DIRECT, TSMEM>& T, uint32_t st, uint32_t addr, int len, uint32_t& high) {
+    int i = 0;
+    while (i < len && ((addr + i) & 3)) { uint32_t b = lds_u8(addr + i); high |= b; st = T.next(st, b); i++; }
+    for (; i + 4 <= len; i += 4) { uint32_t w = lds_u32(addr + i); high |= w; st = step4(T, st, w); }
+    for (; i < len; i++) { uint32_t b = lds_u8(addr + i); high |= b; st = T.next(st, b); }
+    return st;
+}
+
+template <int OP, bool DIRECT, bool TSMEM>
+__global__ void __launch_bounds__(256) k_bool_ragged(KParams p, const uint8_t* __restrict__ buf,
+                                                     const int64_t* __restrict__ offsets, int64_t n, int64_t total,
+                                                     uint8_t* __restrict__ out, int tile_bytes, int slack,
+                                                     int64_t ntiles, int table_smem_bytes, int generic) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    // layout: [0,16) mbarrier | classmap 256 | table | tile (16-byte aligned)
+    uint8_t* s_cmap = smem + 16;
+    uint8_t* s_table = smem + 16 + 256;
+    uint8_t* tile = smem + 16 + 256 + table_smem_bytes;
+    const uint32_t mbar = smem_u32(smem);
+    Table<DIRECT, TSMEM> T = stage_table<DIRECT, TSMEM>(p, s_table, s_cmap);
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t t0 = t * tile_bytes;
+        int64_t t1 = t0 + tile_bytes + slack;
+        if (t1 > total) t1 = total;
+        const int64_t s_begin = lower_bound_i64(offsets, n, t0);
+        const int64_t s_end = lower_bound_i64(offsets, n, t0 + tile_bytes);
+        if (s_begin >= s_end) continue;   // uniform across the CTA
+        const int64_t base = t0 < t1 ? stage_tile(buf, t0, t1, total, tile, mbar, phase) : t0;
+        const uint32_t tile_addr = smem_u32(tile);
+        for (int64_t s = s_begin + threadIdx.x; s < s_end; s += blockDim.x) {
+            const int64_t o0 = __ldg(offsets + s), o1 = __ldg(offsets + s + 1);
+            const int64_t len = o1 - o0;
+            bool r;
+            if (generic || o1 > t1) {
+                r = eval_bool_generic<OP, DIRECT, TSMEM>(p, T, buf + o0, len);
+            } else {
+                const uint32_t a = tile_addr + (uint32_t)(o0 - base);
+                if (degenerate_text<OP>(len, len ? lds_u8(a) : 0)) r = p.q0_accepting != 0;
+                else {
+                    uint32_t high = 0;
+                    r = result_flag(p, walk_smem(T, (uint32_t)p.start, a, (int)len, high));
+                    if (OP == 1 && r && p.prefix_mode == 1 && (high & 0x80808080u)) r = in_with_prefix(p, FetchShared{a}, len);
+                }
+            }
+            out[s] = r ? 1 : 0;
+        }
+        __syncthreads();  // everyone is done with the tile before the next bulk copy overwrites it
+    }
+}
+
+// K3: ragged batch, span result (config C3).  Same tiling as K2.
+template <bool DIRECT, bool TSMEM>
+__global__ void __launch_bounds__(256) k_regex_ragged(KParams p, const uint8_t* __restrict__ buf,
+                                                      const int64_t* __restrict__ offsets, int64_t n, int64_t total,
+                                                      int64_t* __restrict__ from, int64_t* __restrict__ to,
+                                                      int tile_bytes, int slack, int64_t ntiles, int table_smem_bytes) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_cmap = smem + 16;
+    uint8_t* s_table = smem + 16 + 256;
+    uint8_t* tile = smem + 16 + 256 + table_smem_bytes;
+    const uint32_t mbar = smem_u32(smem);
+    Table<DIRECT, TSMEM> T = stage_table<DIRECT, TSMEM>(p, s_table, s_cmap);
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t t0 = t * tile_bytes;
+        int64_t t1 = t0 + tile_bytes + slack;
+        if (t1 > total) t1 = total;
+        const int64_t s_begin = lower_bound_i64(offsets, n, t0);
+        const int64_t s_end = lower_bound_i64(offsets, n, t0 + tile_bytes);
+        if (s_begin >= s_end) continue;
+        const int64_t base = t0 < t1 ? stage_tile(buf, t0, t1, total, tile, mbar, phase) : t0;
+        const uint32_t tile_addr = smem_u32(tile);
+        for (int64_t s = s_begin + threadIdx.x; s < s_end; s += blockDim.x) {
+            const int64_t o0 = __ldg(offsets + s), o1 = __ldg(offsets + s + 1);
+            int64_t f, e;
+            if (o1 > t1) eval_regex(p, T, FetchGlobal{buf + o0}, o1 - o0, f, e);
+            else eval_regex(p, T, FetchShared{tile_addr + (uint32_t)(o0 - base)}, o1 - o0, f, e);
+            from[s] = f;
+            to[s] = e;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: one long buffer, span result (config C4).
+// The reference tries every character boundary as a start, in order, and returns at the first one
+// whose anchored run accepts after >= 1 symbol (api_internal_m.F90:108-155).  The attempts are
+// independent of each other, so they run in parallel: every thread takes 16 consecutive start
+// candidates out of a coalesced 16-byte load, filters them with the first transition out of q0,
+// and runs the surviving attempts forward through global memory.  The smallest winning start is
+// kept with a 64-bit atomicMin; a second tiny kernel re-runs that one attempt to get the longest
+// end.  Blocks sweep the buffer front to back and stop once their region lies behind the best
+// start found so far.
+// ---------------------------------------------------------------------------------------------
+static constexpr unsigned long long NO_START = ~0ull;
+
+// is text index pos a character boundary of the sequential strict decoder?  (pos holds a 10xxxxxx byte)
+__device__ inline bool continuation_is_boundary(const uint8_t* __restrict__ s, int64_t len, int64_t pos) {
+    for (int back = 1; back <= 3; back++) {
+        const int64_t q = pos - back;
+        if (q < 0) return true;
+        const uint32_t b = __ldg(s + q);
+        if ((b & 0xC0) == 0x80) continue;            // still inside a run of continuation bytes
+        int n = (b >> 5) == 6 ? 2 : (b >> 4) == 14 ? 3 : (b >> 3) == 30 ? 4 : 1;
+        if (n <= back) return true;                  // the sequence that starts at q ends before pos
+        if (q + n > len) return true;                // truncated sequence: every byte stands alone
+        for (int k = 1; k < n; k++)
+            if ((__ldg(s + q + k) & 0xC0) != 0x80) return true;   // malformed: every byte stands alone
+        return false;                                // pos is inside a well-formed sequence
+    }
+    return true;                                     // three continuation bytes in front: pos cannot be covered
+}
+
+template <bool DIRECT, bool TSMEM>
+__global__ void __launch_bounds__(256) k_buffer_scan(KParams p, const uint8_t* __restrict__ buf, int64_t len,
+                                                     unsigned long long* __restrict__ best) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_cmap = smem;
+    uint8_t* s_table = smem + 256;
+    Table<DIRECT, TSMEM> T = stage_table<DIRECT, TSMEM>(p, s_table, s_cmap);
+    if (TSMEM) __syncthreads();
+    FetchGlobal fetch{buf};
+    const uint32_t q0 = (uint32_t)p.q0;
+    const Anchored A{p.flags, p.start_nul, p.q0};
+    // head: bytes before the first 16-byte aligned address are handled by block 0 / thread 0 one by one
+    const uintptr_t g = reinterpret_cast<uintptr_t>(buf);
+    int64_t head = (int64_t)((16 - (g & 15)) & 15);
+    if (head > len) head = len;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // start 1 = the leading NUL sentinel; key 1
+        if (attempt_at(A, T, fetch, len, 1) >= 0) atomicMin(best, 1ull);
+        for (int64_t pos = 0; pos < head; pos++) {
+            const uint32_t b = fetch(pos);
+            if ((T.next(q0, b) & W_STATE) == 0) continue;
+            if ((b & 0xC0) == 0x80 && !continuation_is_boundary(buf, len, pos)) continue;
+            if (run_attempt(A, T, fetch, len, q0, pos, -1) >= 0) { atomicMin(best, (unsigned long long)pos + 2); break; }
+        }
+    }
+    const int64_t nvec = (len - head) >> 4;          // whole 16-byte units
+    const int64_t units_per_block = (int64_t)blockDim.x;
+    for (int64_t u0 = (int64_t)blockIdx.x * units_per_block; u0 < nvec; u0 += (int64_t)gridDim.x * units_per_block) {
+        const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(best);
+        if (cur != NO_START && (unsigned long long)(head + (u0 << 4)) + 2 > cur) break;   // everything here lies behind the winner
+        const int64_t u = u0 + threadIdx.x;
+        if (u >= nvec) continue;
+        const int64_t pos0 = head + (u << 4);
+        const uint4 v = ldg_nc_v4(buf + pos0);
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+        bool done = false;
+#pragma unroll
+        for (int q = 0; q < 4 && !done; q++) {
+#pragma unroll
+            for (int r = 0; r < 4 && !done; r++) {
+                const uint32_t b = (wv[q] >> (8 * r)) & 0xFF;
+                if ((T.next(q0, b) & W_STATE) == 0) continue;
+                const int64_t pos = pos0 + q * 4 + r;
+                if ((b & 0xC0) == 0x80 && !continuation_is_boundary(buf, len, pos)) continue;
+                if (run_attempt(A, T, fetch, len, q0, pos, -1) >= 0) {
+                    atomicMin(best, (unsigned long long)pos + 2);
+                    done = true;
+                }
+            }
+        }
+    }
+    // tail: the last (len - head) % 16 bytes, by the last block's thread 0
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        for (int64_t pos = head + (nvec << 4); pos < len; pos++) {
+            const uint32_t b = fetch(pos);
+            if ((T.next(q0, b) & W_STATE) == 0) continue;
+            if ((b & 0xC0) == 0x80 && !continuation_is_boundary(buf, len, pos)) continue;
+            if (run_attempt(A, T, fetch, len, q0, pos, -1) >= 0) { atomicMin(best, (unsigned long long)pos + 2); break; }
+        }
+    }
+}
+
+// second step: longest end for the winning start; also the literal / degenerate cases
+template <bool DIRECT>
+__global__ void k_buffer_finish(KParams p, const uint8_t* __restrict__ buf, int64_t len,
+                                const unsigned long long* __restrict__ best, int64_t* __restrict__ from_to) {
+    Table<DIRECT, false> T;
+    T.g_table = p.table; T.g_cmap = p.classmap; T.shift = p.row_shift; T.s_table = 0; T.s_cmap = 0;
+    FetchGlobal fetch{buf};
+    int64_t from = 0, to = 0;
+    if (p.all_active || len == 0 || (len == 1 && fetch(0) == 0x20)) {
+        eval_regex(p, T, fetch, len, from, to);
+    } else {
+        const unsigned long long key = *best;
+        const Anchored A{p.flags, p.start_nul, p.q0};
+        if (key != NO_START) {
+            const int64_t start = (int64_t)key;
+            const int64_t last = attempt_at(A, T, fetch, len, start);
+            const int64_t f = start - 1 < 1 ? 1 : start - 1;
+            const int64_t t = last < len ? last : len;
+            if (f > 0 && t > 0) { from = f; to = t; }
+        }
+    }
+    from_to[0] = from;
+    from_to[1] = to;
+}
+
+}  // namespace fxk

@@ -1,0 +1,144 @@
+/* forgex_b200.h -- C ABI of the B200-native Forgex matching path.
+ *
+ * One shared library (forgex_b200/libforgex_b200.so) = host-side pattern compiler (C++) +
+ * hand-written sm_100a kernels.  The entry points are what a `bind(C)` interface block in
+ * Forgex's api_internal_m / forgex modules would bind (INTEGRATION.md shows the Fortran side):
+ *
+ *   reference interface                                   replaced by
+ *   ----------------------------------------------------  ---------------------------------------
+ *   do_matching_exactly    (src/api_internal_m.F90:171)    fx_match_fixed / fx_match_batch
+ *   do_matching_including  (src/api_internal_m.F90:31)     fx_in_fixed / fx_in_batch,
+ *                                                          fx_regex_batch / fx_regex_buffer
+ *   automaton%preprocess + %init (src/automaton_m.F90:53-100,
+ *     called per API call at src/forgex.F90:139-140)       fx_compile (once per pattern)
+ *   operator(.in.)    (src/forgex.F90:74)                  fx_in        (one pattern, one text)
+ *   operator(.match.) (src/forgex.F90:163)                 fx_match
+ *   regex / regex_f   (src/forgex.F90:235, :351)           fx_regex
+ *   is_valid_regex    (src/forgex.F90:58)                  fx_is_valid_regex
+ *
+ * Conventions
+ *   - plain pointers and sizes only; byte strings are (pointer, int64 length), never NUL terminated.
+ *   - every call returns an int status: 0 = ok; 1..24 = Forgex's own SYNTAX_* codes
+ *     (src/essential/error_m.F90:12-38); 101.. = conditions listed below; negative = -(cudaError_t).
+ *   - results are Forgex's: booleans as one byte (0/1) per string; spans as 1-based inclusive
+ *     (from, to) in text coordinates, (0, 0) = no match, exactly what `regex` would return in its
+ *     `from=` / `to=` arguments (src/forgex.F90:323-343).
+ *   - `_dev` variants take DEVICE pointers and a cudaStream_t (as void*; NULL = default stream),
+ *     enqueue asynchronously and copy nothing.  The variants without suffix take HOST pointers,
+ *     copy in, run, copy out and return when the results are in host memory.
+ *   - a compiled pattern is immutable after fx_compile; concurrent calls on distinct streams are safe.
+ *   - there is no CPU fallback: without a usable CUDA device every matching call fails with
+ *     FX_ERR_NO_DEVICE.  fx_compile and the fx_pattern_* queries are host-only.
+ */
+#ifndef FORGEX_B200_H
+#define FORGEX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fx_pattern fx_pattern;
+
+enum {               /* which entry point the pattern is compiled for (each has its own preprocessing
+                        of the pattern text and its own automaton, src/forgex.F90:95, :182-190, :260) */
+    FX_OP_MATCH = 0, /* .match.  */
+    FX_OP_IN = 1,    /* .in.     */
+    FX_OP_REGEX = 2  /* regex / regex_f (spans) */
+};
+
+enum {               /* where the transition table lives while a kernel runs */
+    FX_TABLE_AUTO = 0,   /* shared memory when it fits, else global (L2-resident) */
+    FX_TABLE_SMEM = 1,   /* force shared memory (error if it does not fit) */
+    FX_TABLE_GLOBAL = 2  /* force the global / L2 path */
+};
+
+enum {
+    FX_OK = 0,
+    FX_ERR_TREE_NODE_LIMIT = 101,      /* Forgex `error stop`s here (src/ast/syntax_tree_graph_m.F90:115-117) */
+    FX_ERR_DFA_STATE_CAP = 102,        /* eager construction exceeds 16383 states (Forgex's own ceiling for the
+                                          lazily visited states: src/lazy_dfa/lazy_dfa_graph_m.F90:90-92) */
+    FX_ERR_PREFILTER_UNSUPPORTED = 103,/* pattern whose literal prefilter (src/api_internal_m.F90:76-104) is not
+                                          provably result-neutral; see DESIGN.md "out of contract" */
+    FX_ERR_BAD_ARGUMENT = 104,
+    FX_ERR_NO_DEVICE = 105
+};
+
+typedef struct fx_pattern_info {
+    int32_t op;
+    int32_t status;
+    int32_t nfa_states;
+    int32_t cp_states;        /* states of the eager code-point automaton */
+    int32_t cp_classes;
+    int32_t byte_states;      /* states of the byte-level DFA (boundary + in-sequence states) */
+    int32_t byte_classes;     /* byte equivalence classes */
+    int32_t row_shift;        /* log2 of the padded row length of the class-compressed table */
+    int32_t table_bytes;      /* class-compressed table size */
+    int32_t direct_bytes;     /* 256-column table size */
+    int32_t literal_all_len;  /* Forgex's extracted literals (src/ast/syntax_tree_optimize_m.F90:42) */
+    int32_t literal_prefix_len;
+    int32_t literal_suffix_len;
+    int32_t literal_only;     /* 1: `all` is non-blank, the automaton is never consulted by .in./regex */
+    int32_t residency;        /* FX_TABLE_* actually used by the last launch (0 before any launch) */
+    int32_t direct;           /* 1: last launch used the 256-column table */
+    int32_t prefix_mode;      /* `.in.` with an extracted prefix: 0 none, 1 prefilter is result-neutral for ASCII
+                                 text (texts with bytes >= 0x80 are re-checked exactly), 2 always replayed exactly */
+} fx_pattern_info;
+
+/* ---- host-only ------------------------------------------------------------------------- */
+const char* fx_status_message(int status);
+
+/* Compile `pattern` for one entry point.  Always returns a handle in *out (unless arguments are
+ * bad); the return value is the pattern's status (0 or a SYNTAX_* / FX_ERR_* code). */
+int fx_compile(const void* pattern, int64_t plen, int op, fx_pattern** out);
+int fx_pattern_free(fx_pattern* p);
+int fx_pattern_get_info(const fx_pattern* p, fx_pattern_info* info);
+int fx_pattern_set_residency(fx_pattern* p, int residency);
+/* copies of the extracted literals (buffers of at least the lengths reported by get_info) */
+int fx_pattern_literals(const fx_pattern* p, void* all, void* prefix, void* suffix);
+/* read-only views of the host copies of the device tables (for tests / tools):
+ * table: byte_states << row_shift uint16 words; direct: byte_states * 256 words;
+ * classmap: 256 bytes; flags: byte_states bytes; scalars: {start, start_nul, q0, matched, q0_accepting} */
+int fx_pattern_tables(const fx_pattern* p, const uint16_t** table, const uint16_t** direct,
+                      const uint8_t** classmap, const uint8_t** flags, int32_t scalars[5]);
+int fx_is_valid_regex(const void* pattern, int64_t plen, int* status);
+
+/* ---- device-pointer entry points (asynchronous on `stream`) ---------------------------- */
+int fx_match_fixed_dev(fx_pattern* p, const uint8_t* d_buf, int64_t n, int64_t stride, uint8_t* d_out, void* stream);
+int fx_in_fixed_dev(fx_pattern* p, const uint8_t* d_buf, int64_t n, int64_t stride, uint8_t* d_out, void* stream);
+/* offsets: n+1 ascending int64 byte offsets into d_buf; string i = d_buf[offsets[i] .. offsets[i+1]) */
+int fx_match_batch_dev(fx_pattern* p, const uint8_t* d_buf, const int64_t* d_offsets, int64_t n, int64_t total_bytes,
+                       uint8_t* d_out, void* stream);
+int fx_in_batch_dev(fx_pattern* p, const uint8_t* d_buf, const int64_t* d_offsets, int64_t n, int64_t total_bytes,
+                    uint8_t* d_out, void* stream);
+int fx_regex_batch_dev(fx_pattern* p, const uint8_t* d_buf, const int64_t* d_offsets, int64_t n, int64_t total_bytes,
+                       int64_t* d_from, int64_t* d_to, void* stream);
+/* one buffer of `len` bytes; d_from_to[0] = from, d_from_to[1] = to (64-bit, 1-based inclusive, 0/0 = none).
+ * d_work: device scratch of fx_regex_buffer_work_bytes(len) bytes. */
+int64_t fx_regex_buffer_work_bytes(int64_t len);
+int fx_regex_buffer_dev(fx_pattern* p, const uint8_t* d_buf, int64_t len, int64_t* d_from_to, void* d_work, void* stream);
+
+/* ---- host-pointer entry points (copy in, run, copy out, synchronous) ------------------- */
+int fx_match_fixed(fx_pattern* p, const uint8_t* buf, int64_t n, int64_t stride, uint8_t* out);
+int fx_in_fixed(fx_pattern* p, const uint8_t* buf, int64_t n, int64_t stride, uint8_t* out);
+int fx_match_batch(fx_pattern* p, const uint8_t* buf, const int64_t* offsets, int64_t n, uint8_t* out);
+int fx_in_batch(fx_pattern* p, const uint8_t* buf, const int64_t* offsets, int64_t n, uint8_t* out);
+int fx_regex_batch(fx_pattern* p, const uint8_t* buf, const int64_t* offsets, int64_t n, int64_t* from, int64_t* to);
+int fx_regex_buffer(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* from, int64_t* to);
+
+/* ---- one pattern, one text: the reference's public API, compiled per call like the reference does */
+int fx_in(const void* pattern, int64_t plen, const void* text, int64_t tlen, int* result);
+int fx_match(const void* pattern, int64_t plen, const void* text, int64_t tlen, int* result);
+/* regex(pattern, text, res, length, from, to, status): res = text(from:to).  Invalid pattern:
+ * from = to = -9999, length = 0, *status = SYNTAX_* code, return value 0 (src/forgex.F90:266-274). */
+int fx_regex(const void* pattern, int64_t plen, const void* text, int64_t tlen, int64_t* from, int64_t* to,
+             int64_t* length, int* status);
+
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t fx_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FORGEX_B200_H */

@@ -1,0 +1,237 @@
+"""Python model of what the kernels do with the device tables (forgex_b200/csrc/fx_kernels.cuh).
+
+Used by the CPU-only tests to check the HOST side of the product (pattern compiler + table builder)
+against the oracle without a GPU: same tables, same walk, written independently in Python.
+It lives under tests/ on purpose -- it is a checker, not a fallback: the product never imports it.
+"""
+import forgex_b200 as fx
+
+W_ACC, W_INTER, W_STATE = 0x8000, 0x4000, 0x3FFF
+SF_ACC, SF_END, SF_INTER, SF_MATCHED, SF_FAILACC1 = 1, 2, 4, 8, 16
+NONE = -9999
+
+
+def blank(b: bytes):
+    return b.strip(b" ") == b""
+
+
+class Anchored:
+    """run_attempt / attempt_at / including_exact on a REGEX-mode (flag-bit) table"""
+
+    def __init__(self, pattern_obj, use_direct):
+        self.t = pattern_obj.tables()
+        self.lit = pattern_obj.literals()
+        self.use_direct = use_direct
+
+    def nxt(self, state, byte):
+        if self.use_direct:
+            return int(self.t["direct"][state, byte])
+        return int(self.t["table"][state, self.t["classmap"][byte]])
+
+    def attempt(self, s, st, pos, last):
+        flags = self.t["flags"]
+        w = st
+        seq = 0
+        inter = False
+        n = len(s)
+        if (w & W_STATE) == 0:
+            return last
+        j = pos
+        while j <= n:
+            b = s[j] if j < n else 0
+            if inter and (b & 0xC0) != 0x80:
+                f = int(flags[w & W_STATE])
+                for k in range(1, j - seq + 1):
+                    if f & (SF_FAILACC1 << (k - 1)):
+                        last = seq + k
+                inter = False
+            nw = self.nxt(w & W_STATE, b)
+            if (nw & W_INTER) and not inter:
+                seq = j
+            inter = bool(nw & W_INTER)
+            w = nw
+            if w & W_ACC:
+                last = j + 1
+            if (w & W_STATE) == 0:
+                break
+            j += 1
+        return last
+
+    def attempt_at(self, s, start):
+        t = self.t
+        if start == 1:
+            if t["start_nul"] == 0:
+                return -1
+            last = 0 if (t["flags"][t["start_nul"]] & SF_ACC) else -1
+            return self.attempt(s, t["start_nul"], 0, last)
+        return self.attempt(s, t["q0"], start - 2, -1)
+
+    @staticmethod
+    def char_len(s, pos):
+        b = s[pos]
+        if b < 0x80:
+            return 1
+        if (b >> 5) == 6:
+            n = 2
+        elif (b >> 4) == 14:
+            n = 3
+        elif (b >> 3) == 30:
+            n = 4
+        else:
+            return 1
+        if pos + n > len(s):
+            return 1
+        for k in range(1, n):
+            if (s[pos + k] & 0xC0) != 0x80:
+                return 1
+        return n
+
+    def including_exact(self, s):
+        _, pre, suf = self.lit
+        n = len(s)
+        m = n + 2
+        S = b"\0" + s + b"\0"
+        pre_active, suf_active = not blank(pre), not blank(suf)
+
+        def findex(lit, frm):     # framed_index: 1-based position in S at or after frm, 0 if none
+            i = S.find(lit, frm - 1)
+            return i + 1 if i >= 0 else 0
+
+        def rindex(hay, lit):     # index(hay, lit, back=.true.)
+            if len(lit) > len(hay):
+                return 0
+            i = hay.rfind(lit)
+            return i + 1 if i >= 0 else 0
+        brute = not pre_active
+        first, frame_suf, offset, more = NONE, NONE, 0, False
+        if not brute:
+            idx = findex(pre, 1)
+            frame_suf = rindex(S, suf) or NONE
+            if idx > 0:
+                if frame_suf != NONE:
+                    if idx <= frame_suf:
+                        first = idx
+                else:
+                    first = idx
+                offset = idx + len(pre) - 1
+                more = True
+            if first == NONE:
+                brute = True
+        if brute:
+            last = self.attempt_at(s, 1)
+            if last >= 0:
+                return 1, min(last, n)
+            pos = 0
+            while pos < n:
+                last = self.attempt(s, self.t["q0"], pos, -1)
+                if last >= 0:
+                    return pos + 1, min(last, n)
+                pos += self.char_len(s, pos)
+            return 0, 0
+        at_zero = first == 2
+        start = 1 if at_zero else first
+        text_suf = NONE
+        if suf_active:
+            text_suf = rindex(s, suf)
+            if text_suf == 0:
+                return 0, 0
+        while start < m:
+            if text_suf != NONE and text_suf < start:
+                return 0, 0
+            last = self.attempt_at(s, start)
+            if last >= 0:
+                return max(start - 1, 1), min(last, n)
+            if at_zero:
+                at_zero = False
+                start = first
+                continue
+            if not more or not (offset < m):
+                return 0, 0
+            hit = findex(pre, offset + 1)
+            if hit <= 0:
+                return 0, 0
+            start = hit
+            offset = hit + len(pre) - 1
+            if frame_suf != NONE and offset > frame_suf:
+                more = False
+        return 0, 0
+
+    def regex(self, s: bytes):   # eval_regex
+        all_ = self.lit[0]
+        if not blank(all_):
+            i = s.find(all_)
+            return (i + 1, i + len(all_)) if i >= 0 else (0, 0)
+        if len(s) == 0 or s == b" ":
+            return (0, 0)
+        f, t = self.including_exact(s)
+        return (f, t) if f > 0 and t > 0 else (0, 0)
+
+
+class Model:
+    """one compiled pattern, evaluated the way the kernels evaluate it"""
+
+    def __init__(self, pattern_obj, use_direct=True):
+        self.p = pattern_obj
+        self.op = pattern_obj.op
+        self.use_direct = use_direct
+        self.t = pattern_obj.tables()
+        self.lit = pattern_obj.literals()
+        self.prefix_mode = pattern_obj.info()["prefix_mode"]
+        self.anch = None
+        if self.op == 2:
+            self.anch = Anchored(pattern_obj, use_direct)
+        elif self.prefix_mode:
+            self._anch_pat = fx.Pattern(pattern_obj.pattern, "regex")
+            self.anch = Anchored(self._anch_pat, False)
+
+    def nxt(self, state, byte):
+        if self.use_direct:
+            return int(self.t["direct"][state, byte])
+        return int(self.t["table"][state, self.t["classmap"][byte]])
+
+    def in_with_prefix(self, s):
+        if len(s) == 0 or s == b" ":
+            return self.t["q0_accepting"]
+        f, t = self.anch.including_exact(s)
+        return f > 0 and t > 0
+
+    def boolean(self, s: bytes):   # k_bool_* incl. eval_bool_generic
+        all_, pre, suf = self.lit
+        t = self.t
+        if self.op == 1:
+            if not blank(all_):
+                return all_ in s
+            if self.prefix_mode == 2:
+                return self.in_with_prefix(s)
+        else:
+            if not blank(all_) and len(s) == len(all_):
+                return s == all_
+            lp, ls = len(pre), len(suf)
+            if len(s) > 0 and lp > 0 and lp == len(s) and s == pre:
+                return True
+            if lp > len(s) or ls > len(s):
+                return False
+            if len(s) > 0:
+                if not blank(pre) and s[:lp] != pre:
+                    return False
+                if not blank(suf) and s[len(s) - ls:] != suf:
+                    return False
+            else:
+                if not blank(pre) and lp != 0:
+                    return False
+                if not blank(suf) and ls != 0:
+                    return False
+        if len(s) == 0 or (self.op == 1 and s == b" "):
+            return t["q0_accepting"]
+        st = t["start"]
+        high = 0
+        for b in s:
+            high |= b
+            st = self.nxt(st, b)
+        r = bool(t["flags"][st] & (SF_END | SF_MATCHED))
+        if self.op == 1 and r and self.prefix_mode == 1 and (high & 0x80):
+            r = self.in_with_prefix(s)
+        return r
+
+    def regex(self, s: bytes):
+        return self.anch.regex(s)

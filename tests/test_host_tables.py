@@ -1,0 +1,191 @@
+"""CPU-only checks of the product's HOST side (pattern compiler, literal extraction, byte-level tables).
+
+The tables the kernels would walk are walked here by tests/table_model.py (a Python model of the
+kernels) and compared with (1) the reference's own known-answer vectors and (2) the oracle on
+generated patterns/texts.  No GPU, no compute call into the library.
+"""
+import json
+import os
+import random
+
+import pytest
+
+import forgex_b200 as fx
+from forgex_b200 import _lib
+from tests import oracle_lib as O
+from tests.table_model import Model
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+OPS = {"match": "match", "in": "in", "regex": "regex"}
+
+# Reference vectors whose pattern cannot be built EAGERLY within the state cap: Forgex only
+# visits a handful of their DFA states lazily.  The product reports FX_ERR_DFA_STATE_CAP for them.
+EAGER_CAP_PATTERNS = {b".*a(a|b){500}c{20}", b"[ab]*a[ab]{20}"}
+
+
+def load(name):
+    with open(os.path.join(GOLD, "reference_%s.json" % name)) as fh:
+        return json.load(fh)["vectors"]
+
+
+_cache = {}
+
+
+def model_for(pattern, op):
+    key = (pattern, op)
+    if key not in _cache:
+        p = fx.Pattern(pattern, op)
+        _cache[key] = (p, Model(p, use_direct=(len(_cache) % 2 == 0)) if p.status == 0 else None)
+    return _cache[key]
+
+
+def product_answer(kind, pattern, text):
+    p, m = model_for(pattern, kind)
+    if p.status != 0:
+        if 1 <= p.status <= 24:       # invalid pattern: operators give .false., regex gives ''
+            return False if kind != "regex" else b""
+        return ("status", p.status)
+    if kind == "regex":
+        f, t = m.regex(text)
+        return text[f - 1:t] if f > 0 and t > 0 else b""
+    return m.boolean(text)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.lib()
+    hdr = open(os.path.join(os.path.dirname(GOLD), "..", "include", "forgex_b200.h")).read()
+    for name in _lib.SYMBOLS:
+        assert hasattr(lib, name), name
+        assert name + "(" in hdr, "%s is bound but not declared in include/forgex_b200.h" % name
+    import re
+    declared = set(re.findall(r"\b(fx_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+
+
+def test_reference_api_vectors_through_product_tables():
+    bad, capped = [], 0
+    for v in load("api"):
+        pat, text = bytes.fromhex(v["pattern"]), bytes.fromhex(v["text"])
+        got = product_answer(v["kind"], pat, text)
+        if isinstance(got, tuple):
+            assert got[1] == _lib.FX_ERR_DFA_STATE_CAP and pat in EAGER_CAP_PATTERNS, (v["src"], got)
+            capped += 1
+            continue
+        exp = bytes.fromhex(v["expect"]) if v["kind"] == "regex" else v["expect"]
+        if got != exp:
+            bad.append("%s %s %r -> %r, expected %r" % (v["src"], v["kind"], pat, got, exp))
+    assert not bad, "%d vectors fail:\n%s" % (len(bad), "\n".join(bad[:40]))
+    assert capped == 4
+
+
+def f_eq(a, b):
+    n = max(len(a), len(b))
+    return a.ljust(n, b" ") == b.ljust(n, b" ")
+
+
+def test_reference_literal_vectors():
+    bad = []
+    for v in load("ast"):
+        pat = bytes.fromhex(v["pattern"])
+        # the reference test builds the tree from the pattern as written (no trimming): REGEX op with
+        # a pattern that has no trailing blanks is the same thing
+        assert pat == pat.rstrip(b" ")
+        p = fx.Pattern(pat, "regex")
+        if not (p.status == 0 or p.status > 24):
+            bad.append("%s invalid %r" % (v["src"], pat))
+            continue
+        lit = p.literals()
+        got = lit[1] if v["kind"] == "prefix" else lit[2]
+        exp = bytes.fromhex(v["expect"])
+        if not (len(exp.decode("utf-8", "replace")) == len(got.decode("utf-8", "replace")) and f_eq(exp, got)):
+            bad.append("%s %s %r -> %r, expected %r" % (v["src"], v["kind"], pat, got, exp))
+    assert not bad, "\n".join(bad[:40])
+
+
+def test_reference_status_and_validity_vectors():
+    bad = []
+    for v in load("error"):
+        pat = bytes.fromhex(v["pattern"])
+        r = fx.regex(pat, b"") if False else None   # regex() needs a GPU; the status comes from the compile step
+        st = fx.Pattern(pat, "regex").status
+        st = st if st <= 24 else 0
+        if st != v["expect"] or fx.status_message(st) != O.error_message(v["expect"]):
+            bad.append("%s %r -> %d, expected %d" % (v["src"], pat, st, v["expect"]))
+    for v in load("validate"):
+        pat = bytes.fromhex(v["pattern"])
+        if fx.is_valid_regex(pat) != v["expect"]:
+            bad.append("%s %r validity" % (v["src"], pat))
+    assert not bad, "\n".join(bad[:40])
+
+
+# ---- generated patterns and texts: product tables vs oracle -------------------------------------
+ATOMS = ["a", "b", "c", "ab", "ba", ".", "\\d", "\\w", "\\s", "\\S", "\\D", "[ab]", "[^a]", "[a-c]", "[^a-cx]", "\\n",
+         "^", "$", "x", " ", "é", "あ", "[ぁ-ん]", "[α-ω]", "\\x41", "\\x{3042}", "[\\x00-\\x20]", "\\t", "-", "}",
+         "\\.", "[\\n]", "[\\d-]", "(|^)", "\\x00", "[^\\n]"]
+SUFFIXES = ["", "", "", "*", "+", "?", "{2}", "{0,2}", "{1,}", "{,3}", "{0}", "{2,3}"]
+
+
+def gen_pattern(rng, depth=0):
+    n = rng.randint(1, 4)
+    parts = []
+    for _ in range(n):
+        r = rng.random()
+        if depth < 2 and r < 0.25:
+            inner = gen_pattern(rng, depth + 1)
+            if rng.random() < 0.5:
+                inner += "|" + gen_pattern(rng, depth + 1)
+            atom = "(" + inner + ")"
+        else:
+            atom = rng.choice(ATOMS)
+        parts.append(atom + rng.choice(SUFFIXES))
+    return "".join(parts)
+
+
+TEXT_PIECES = [b"a", b"b", b"c", b"ab", b"x", b" ", b"\n", b"\r\n", b"\t", b"0", b"7", b"_", "é".encode(), "あ".encode(),
+               "ん".encode(), "α".encode(), "ω".encode(), "　".encode(), b"\x00", b"\x80", b"\xbf", b"\xc3", b"\xe3\x81",
+               b"\xf0\x9f\x98", b"\xff", b"\xc0\x80", b"\xc1\xa1", b"\xe0\x81\xa1", b"\xf0\x80\x81\xa1", b"\xef\xbf\xbf",
+               b"\xf4\x90\x80\x81", b"\xf7\xbf\xbf\xbf", b"A", b"-", b".", b"}", b"\x1f", b"\x0b"]
+
+
+def gen_text(rng):
+    return b"".join(rng.choice(TEXT_PIECES) for _ in range(rng.randint(0, 8)))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_generated_patterns_match_oracle(seed):
+    rng = random.Random(1000 + seed)
+    bad = []
+    checked = 0
+    for _ in range(120):
+        pat = gen_pattern(rng).encode()
+        texts = [gen_text(rng) for _ in range(12)] + [b"", b" "]
+        for kind in ("match", "in", "regex"):
+            p = fx.Pattern(pat, kind)
+            valid = O.is_valid(pat if kind != "match" else b"x")[0]  # placeholder, real check below
+            if 1 <= p.status <= 24:
+                # both sides must reject: the oracle answers False / '' for an invalid pattern
+                for t in texts[:2]:
+                    o = O.op_match(pat, t) if kind == "match" else O.op_in(pat, t) if kind == "in" else O.regex(pat, t)[4]
+                    if kind == "regex":
+                        if o != p.status:
+                            bad.append("status %r: product %d oracle %d" % (pat, p.status, o))
+                    elif o != 0:
+                        bad.append("invalid-on-product only: %s %r" % (kind, pat))
+                continue
+            if p.status != 0:
+                continue  # cap
+            m = Model(p, use_direct=rng.random() < 0.5)
+            for t in texts:
+                checked += 1
+                if kind == "regex":
+                    res, ln, f, to, st = O.regex(pat, t)
+                    got = m.regex(t)
+                    if st != 0 or got != (f, to):
+                        bad.append("regex %r on %r: product %r oracle %r (status %d)" % (pat, t, got, (f, to), st))
+                else:
+                    o = O.op_match(pat, t) if kind == "match" else O.op_in(pat, t)
+                    got = m.boolean(t)
+                    if o < 0 or bool(o) != got:
+                        bad.append("%s %r on %r: product %r oracle %r" % (kind, pat, t, got, o))
+    assert not bad, "%d mismatches (of %d):\n%s" % (len(bad), checked, "\n".join(bad[:30]))
+    assert checked > 1000
