@@ -1,0 +1,460 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the Forgex matching hot path on B200 (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2] [--lines L] [--impl reference]
+
+Default workload = BASELINE.json configs[1] ("c2"): `foo(bar|baz)` .in. over 100 M random ASCII lines of
+64-256 bytes, one pattern against N strings (flat buffer + int64 offsets).  A step = one pass of the
+hot path over that batch.  `value` = input GB/s with the batch resident in HBM; `e2e` = the same through
+the host-pointer C-ABI call (pinned host buffers, H2D + kernel + D2H inside the timed region).
+Multi-GPU: one process per GPU (torchrun), strings sharded across ranks, no data-path collective; the
+per-rank match counts are all-reduced once (NCCL) after the timed region.  Scaling is weak: every rank
+holds --lines lines.
+
+`--impl reference` times the CPU restatement of Forgex's own loop (oracle/, kind "port": the Fortran
+reference cannot be built in this image) on all host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from tools import synth  # noqa: E402
+
+WORKLOADS = {
+    "c1": "c1: '\\d{3}-\\d{4}' .match. over fixed 8-byte ASCII strings",
+    "c2": "c2: 'foo(bar|baz)' .in. over random ASCII lines of 64-256 bytes (flat buffer + int64 offsets)",
+    "c3": "c3: '[α-ωぁ-ん]+\\s\\w{2,8}' regex() spans over mixed Greek/Japanese/ASCII strings incl. invalid bytes",
+    "c4": "c4: '^ERROR.*timeout=\\d+$' regex() over one synthetic log buffer",
+    "c5": "c5: '(a|b)*a(a|b){12}' .in. over fixed 64-byte strings, table in global memory (L2)",
+}
+DEFAULT_UNITS = {"c1": 1 << 30, "c2": 100_000_000, "c3": 16_000_000, "c4": 32 << 30, "c5": 10_000_000}
+# algorithmic bytes per unit besides the text itself: offsets read + result written
+EXTRA_BYTES = {"c1": 1, "c2": 8 + 1, "c3": 8 + 16, "c4": 0, "c5": 1}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def known_traffic(cfg):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if one exists"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh).get(cfg)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [x.strip() for x in s.split(",")]
+            try:
+                sm.append(float(parts[0]))
+                mx = max(mx, float(parts[1]))
+                for nm, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- device-side synthetic data (torch; same shapes as tools/synth.py) ----------------------------
+def make_c2_device(torch, n, seed):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    lens = torch.randint(64, 257, (n,), device="cuda", generator=g, dtype=torch.int64)
+    offsets = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    torch.cumsum(lens, 0, out=offsets[1:])
+    total = int(offsets[-1].item())
+    buf = torch.empty(total, dtype=torch.uint8, device="cuda")
+    chunk = 1 << 30
+    for a in range(0, total, chunk):
+        b = min(total, a + chunk)
+        buf[a:b] = torch.randint(0x20, 0x7F, (b - a,), device="cuda", generator=g, dtype=torch.uint8)
+    kind = torch.randint(0, 16, (n,), device="cuda", generator=g)
+    where = (torch.rand(n, device="cuda", generator=g) * (lens - 6).float()).long().clamp_(min=0)
+    which = torch.randint(0, 2, (n,), device="cuda", generator=g)
+    words = [b"foobar", b"foobaz", b"foobax", b"fooba "]
+    ar = torch.arange(6, device="cuda")
+    for k, base in ((0, 0), (1, 2)):
+        for w in (0, 1):
+            rows = torch.nonzero((kind == k) & (which == w)).squeeze(1)
+            lit = torch.tensor(list(words[base + w]), dtype=torch.uint8, device="cuda")
+            idx = (offsets[rows] + where[rows])[:, None] + ar[None, :]
+            buf[idx.reshape(-1)] = lit.repeat(rows.numel())
+    del lens, kind, where, which
+    return buf, offsets, total
+
+
+def tile_ragged_device(torch, buf_np, off_np, n):
+    """replicate a host-generated ragged batch on the device until it holds n strings"""
+    m = len(off_np) - 1
+    reps = (n + m - 1) // m
+    d_buf = torch.from_numpy(buf_np).cuda().repeat(reps)
+    lens = torch.from_numpy(np.diff(off_np)).cuda().repeat(reps)[:n]
+    offsets = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    torch.cumsum(lens, 0, out=offsets[1:])
+    total = int(offsets[-1].item())
+    return d_buf[:total].contiguous(), offsets, total
+
+
+def build_workload(torch, cfg, units, rank):
+    """returns dict(run=callable, text_bytes, units, verify=callable or None, host=(...) for e2e/cpu legs)"""
+    import forgex_b200 as fx
+    pat = synth.PATTERNS[cfg]
+    op = synth.OPS[cfg]
+    w = {"cfg": cfg, "pattern": pat, "op": op}
+    if cfg == "c2":
+        p = fx.Pattern(pat, "in")
+        buf, off, total = make_c2_device(torch, units, synth.SEEDS[cfg] + rank)
+        out = torch.empty(units, dtype=torch.uint8, device="cuda")
+        w.update(run=lambda: p.in_batch_dev(buf, off, units, total, out), text_bytes=total, units=units, out=out,
+                 buf=buf, off=off, pattern_obj=p)
+    elif cfg in ("c1", "c5"):
+        gen = synth.gen_c1 if cfg == "c1" else synth.gen_c5
+        block_n = min(units, 1 << 20)
+        hb, _, stride = gen(block_n, seed_stream=rank)
+        reps = (units + block_n - 1) // block_n
+        buf = torch.from_numpy(hb).cuda().repeat(reps)[: units * stride].contiguous()
+        out = torch.empty(units, dtype=torch.uint8, device="cuda")
+        p = fx.Pattern(pat, op, residency="global" if cfg == "c5" else "auto")
+        fn = p.match_fixed_dev if op == "match" else p.in_fixed_dev
+        w.update(run=lambda: fn(buf, units, stride, out), text_bytes=units * stride, units=units, out=out, buf=buf,
+                 stride=stride, pattern_obj=p)
+    elif cfg == "c3":
+        block_n = min(units, 1 << 17)
+        hb, ho = synth.gen_c3(block_n, seed_stream=rank)
+        buf, off, total = tile_ragged_device(torch, hb, ho, units)
+        f = torch.empty(units, dtype=torch.int64, device="cuda")
+        t = torch.empty(units, dtype=torch.int64, device="cuda")
+        p = fx.Pattern(pat, "regex")
+        w.update(run=lambda: p.regex_batch_dev(buf, off, units, total, f, t), text_bytes=total, units=units, out=f,
+                 out2=t, buf=buf, off=off, pattern_obj=p)
+    elif cfg == "c4":
+        block = min(units, 256 << 20)
+        hb = synth.gen_c4_block(block, seed_stream=rank)
+        # cut the block at its last line end so that tiling it keeps lines whole
+        last_nl = int(np.nonzero(hb == 10)[0][-1]) + 1
+        d_block = torch.from_numpy(hb[:last_nl]).cuda()
+        reps = (units + last_nl - 1) // last_nl
+        buf = d_block.repeat(reps)[:units].contiguous()
+        line = torch.tensor(list(synth.C4_MATCH_LINE + b"\n"), dtype=torch.uint8, device="cuda")
+        pos = int(units * 0.999)
+        seg = buf[:pos]
+        # previous line start
+        back = seg[max(0, pos - 4096):]
+        nl = torch.nonzero(back == 10).squeeze(1)
+        start = max(0, pos - 4096) + int(nl[-1].item()) + 1
+        buf[start:start + line.numel()] = line
+        after = start + line.numel()
+        buf[after:after + 5] = torch.tensor(list(b"INFO "), dtype=torch.uint8, device="cuda")
+        ft = torch.zeros(2, dtype=torch.int64, device="cuda")
+        work = torch.zeros(64, dtype=torch.uint8, device="cuda")
+        p = fx.Pattern(pat, "regex")
+        w.update(run=lambda: p.regex_buffer_dev(buf, units, ft, work), text_bytes=units, units=1, out=ft, buf=buf,
+                 pattern_obj=p, expect_from=start)
+    else:
+        raise SystemExit("unknown config " + cfg)
+    return w
+
+
+# ---- CPU legs (oracle; the only place bench.py executes oracle/) ------------------------------------
+def _oracle_worker(args):
+    cfg, buf, off, stride = args
+    from tests import oracle_lib as O
+    pat = synth.PATTERNS[cfg]
+    op = synth.OPS[cfg]
+    c = O.Compiled(pat, 1 if op == "match" else 0)
+    t0 = time.perf_counter()
+    if op == "regex":
+        if off is None:
+            r = c.regex_buffer(buf)
+        else:
+            r = c.regex_batch(buf, off)
+    elif off is None:
+        r = c.bool_fixed(1 if op == "match" else 0, buf, len(buf) // stride, stride)
+    else:
+        r = c.bool_batch(1 if op == "match" else 0, buf, off)
+    return time.perf_counter() - t0, r
+
+
+def host_sample(cfg, w, torch, nunits):
+    """first nunits units of this rank's device data, on the host"""
+    if cfg in ("c2", "c3"):
+        off = w["off"][: nunits + 1].cpu().numpy().copy()
+        buf = w["buf"][: int(off[-1])].cpu().numpy()
+        return buf, off, None
+    if cfg in ("c1", "c5"):
+        return w["buf"][: nunits * w["stride"]].cpu().numpy(), None, w["stride"]
+    return w["buf"][:nunits].cpu().numpy(), None, None
+
+
+def cpu_baseline_leg(cfg, w, torch, target_seconds=12.0):
+    """single-threaded oracle on a bounded prefix of the same data; also cross-checks the GPU results"""
+    probe = {"c1": 20000, "c2": 4000, "c3": 3000, "c4": 1 << 20, "c5": 300}[cfg]
+    buf, off, stride = host_sample(cfg, w, torch, probe)
+    dt, _ = _oracle_worker((cfg, buf, off, stride))
+    n = int(min(w["units"] if cfg != "c4" else w["text_bytes"], max(probe, probe * target_seconds / max(dt, 1e-6))))
+    buf, off, stride = host_sample(cfg, w, torch, n)
+    dt, res = _oracle_worker((cfg, buf, off, stride))
+    nbytes = int(off[-1]) if off is not None else len(buf)
+    ok = None
+    if cfg in ("c1", "c2", "c5"):
+        ok = bool(np.array_equal(w["out"][:n].cpu().numpy(), res))
+    elif cfg == "c3":
+        ok = bool(np.array_equal(w["out"][:n].cpu().numpy(), res[0]) and np.array_equal(w["out2"][:n].cpu().numpy(), res[1]))
+    return {"value": nbytes / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+            "sample": "first %d %s of rank 0's batch (%d bytes), oracle/forgex_oracle.cpp single thread, pattern compiled once"
+                      % (n, "bytes" if cfg == "c4" else "strings", nbytes),
+            "strings_per_s": (n / dt) if cfg != "c4" else None, "seconds": dt, "gpu_results_equal_oracle": ok}
+
+
+def reference_arm(args):
+    """--impl reference: the CPU restatement on all host cores, bounded sample per step"""
+    import multiprocessing as mp
+    cfg = args.config
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    per_core = {"c1": 400000, "c2": 40000, "c3": 30000, "c4": 4 << 20, "c5": 2500}[cfg]
+    shards = []
+    for c in range(cores):
+        if cfg == "c2":
+            b, o = synth.gen_c2(per_core, seed_stream=1000 + c)
+            shards.append((cfg, b, o, None))
+        elif cfg == "c3":
+            b, o = synth.gen_c3(min(per_core, 8000), seed_stream=1000 + c)
+            shards.append((cfg, b, o, None))
+        elif cfg in ("c1", "c5"):
+            b, _, s = (synth.gen_c1 if cfg == "c1" else synth.gen_c5)(per_core, seed_stream=1000 + c)
+            shards.append((cfg, b, None, s))
+        else:
+            shards.append((cfg, synth.gen_c4(per_core, None, seed_stream=1000 + c), None, None))
+    nbytes = sum(int(s[2][-1]) if s[2] is not None else len(s[1]) for s in shards)
+    nunits = sum((len(s[2]) - 1) if s[2] is not None else (len(s[1]) // s[3] if s[3] else 1) for s in shards)
+    from tests import oracle_lib as O
+    O.build()
+    times = []
+    with mp.get_context("fork").Pool(cores) as pool:
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            pool.map(_oracle_worker, shards)
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    ms = 1000.0 * sum(times) / len(times)
+    val = nbytes / (ms / 1000.0) / 1e9
+    line = {
+        "impl": "reference", "metric": "input_GBps", "value": val, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOADS[cfg], "sample_strings_per_step": nunits, "sample_bytes_per_step": nbytes},
+        "strings_per_s": nunits / (ms / 1000.0),
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "port",
+                         "sample": "%d strings (%d bytes) per step, one oracle process per host core (fork pool), "
+                                   "pattern compiled once per process per step" % (nunits, nbytes)},
+        "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of Forgex's own per-character subset-step loop (oracle/); the Fortran original cannot "
+                "be compiled in this image and carries extra allocation / formatted-I/O overhead (SURVEY 3.4)",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--lines", type=int, default=0, help="units per GPU (strings; bytes for c4); default = BASELINE size")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-lines", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200" and not os.environ.get("FX_BENCH_ALLOW_SHORT_WARMUP"):
+        args.warmup = 3
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import forgex_b200 as fx
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the matching path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = args.config
+    units = args.lines or DEFAULT_UNITS[cfg]
+    w = build_workload(torch, cfg, units, rank)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        w["run"]()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = fx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        w["run"]()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = fx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+
+    # match counts: the only cross-GPU exchange of a sharded batch (8 bytes per rank), outside the timed region
+    if cfg == "c4":
+        count = torch.tensor([int(w["out"][0].item() > 0)], dtype=torch.int64, device="cuda")
+    elif cfg == "c3":
+        count = (w["out"] > 0).sum().to(torch.int64).reshape(1)
+    else:
+        count = w["out"].sum(dtype=torch.int64).reshape(1)
+    if world > 1:
+        dist.all_reduce(count)
+    text_bytes_all = w["text_bytes"] * world
+    units_all = (w["units"] if cfg != "c4" else 1) * world
+    value = text_bytes_all / (ms_step / 1000.0) / 1e9
+
+    # ---- e2e: host-pointer C-ABI call, pinned host buffers, H2D + kernel + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        p = w["pattern_obj"]
+        n_e = min(w["units"], args.e2e_lines or {"c1": 1 << 27, "c2": 25_000_000, "c3": 8_000_000, "c5": 10_000_000}.get(cfg, 0))
+        if cfg == "c4":
+            nb = min(w["text_bytes"], 4 << 30)
+            hbuf = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+            hbuf.copy_(w["buf"][:nb])
+            call = lambda: p.regex_buffer(hbuf.numpy())
+            h2d, d2h, ebytes, eunits = nb, 16, nb, 1
+        elif cfg in ("c2", "c3"):
+            off = w["off"][: n_e + 1]
+            nb = int(off[-1].item())
+            hbuf = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+            hbuf.copy_(w["buf"][:nb])
+            hoff = torch.empty(n_e + 1, dtype=torch.int64, pin_memory=True)
+            hoff.copy_(off)
+            hb, ho = hbuf.numpy(), hoff.numpy()
+            call = (lambda: p.in_batch(hb, ho)) if cfg == "c2" else (lambda: p.regex_batch(hb, ho))
+            h2d, d2h, ebytes, eunits = nb + 8 * (n_e + 1), n_e * (1 if cfg == "c2" else 16), nb, n_e
+        else:
+            nb = n_e * w["stride"]
+            hbuf = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+            hbuf.copy_(w["buf"][:nb])
+            hb = hbuf.numpy()
+            fn = p.match_fixed if cfg == "c1" else p.in_fixed
+            call = lambda: fn(hb, n_e, w["stride"])
+            h2d, d2h, ebytes, eunits = nb, n_e, nb, n_e
+        call()  # warm-up (grows the library's device scratch)
+        barrier()
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            res = call()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": ebytes * world / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "strings_per_step_per_gpu": int(eunits), "ms_per_step": dt * 1000.0, "strings_per_s": eunits * world / dt,
+               "api": "forgex_b200.Pattern.%s (fx_*_batch / fx_*_fixed host-pointer entry points)" %
+                      {"c1": "match_fixed", "c2": "in_batch", "c3": "regex_batch", "c4": "regex_buffer", "c5": "in_fixed"}[cfg]}
+        del hbuf
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        algo_bytes = w["text_bytes"] + EXTRA_BYTES[cfg] * (w["units"] if cfg != "c4" else 0)
+        kernel_ms = ms_step  # one kernel launch per step per GPU (c4: scan + a 1-thread finish kernel)
+        achieved = algo_bytes / (kernel_ms / 1000.0) / 1e9
+        line = {
+            "metric": "input_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOADS[cfg], "strings_per_gpu": w["units"] if cfg != "c4" else 1,
+                       "text_bytes_per_gpu": w["text_bytes"], "pattern": synth.PATTERNS[cfg].decode("utf-8"),
+                       "l2": "inputs larger than L2 (no flush needed)" if w["text_bytes"] > (256 << 20) else "input fits L2: latency-bound case",
+                       "table": w["pattern_obj"].info()},
+            "strings_per_s": units_all / (ms_step / 1000.0),
+            "matches": int(count.item()),
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": known_traffic(cfg), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": kernel_ms},
+            "e2e": e2e,
+        }
+        if not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_leg(cfg, w, torch)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,255 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle (bit-exact).
+
+Run on the B200 box with `pytest -m gpu`.  Inputs are seeded (tools/synth.py) at sizes the oracle
+finishes in seconds; the reference's own vectors go through the one-pattern-one-text entry points.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import forgex_b200 as fx
+from forgex_b200 import _lib
+from tests import oracle_lib as O
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+EAGER_CAP_PATTERNS = {b".*a(a|b){500}c{20}", b"[ab]*a[ab]{20}"}
+
+
+def oracle_bool(pattern, op, buf, offsets=None, n=None, stride=None):
+    c = O.Compiled(pattern, 1 if op == "match" else 0)
+    o = 1 if op == "match" else 0
+    return c.bool_batch(o, buf, offsets) if offsets is not None else c.bool_fixed(o, buf, n, stride)
+
+
+def pack(strings):
+    offsets = np.zeros(len(strings) + 1, dtype=np.int64)
+    np.cumsum([len(s) for s in strings], out=offsets[1:])
+    return np.frombuffer(b"".join(strings), dtype=np.uint8).copy(), offsets
+
+
+# ---- the reference's own vectors through fx_in / fx_match / fx_regex ---------------------------
+def test_reference_vectors_on_gpu():
+    with open(os.path.join(GOLD, "reference_api.json")) as fh:
+        vecs = json.load(fh)["vectors"]
+    bad, capped = [], 0
+    for v in vecs:
+        pat, text = bytes.fromhex(v["pattern"]), bytes.fromhex(v["text"])
+        try:
+            if v["kind"] == "match":
+                ok = fx.op_match(pat, text) == v["expect"]
+            elif v["kind"] == "in":
+                ok = fx.op_in(pat, text) == v["expect"]
+            else:
+                ok = fx.regex_f(pat, text) == bytes.fromhex(v["expect"])
+        except fx.ForgexError as e:
+            assert e.status == _lib.FX_ERR_DFA_STATE_CAP and pat in EAGER_CAP_PATTERNS, (v["src"], e)
+            capped += 1
+            continue
+        if not ok:
+            bad.append("%s %s %r" % (v["src"], v["kind"], pat))
+    assert not bad, "%d reference vectors fail on the GPU path:\n%s" % (len(bad), "\n".join(bad[:40]))
+    assert capped == 4
+
+
+def test_regex_out_arguments_like_reference():
+    r = fx.regex(b"[d-f]{3}", b"abcdefghi")            # README.md:204-220
+    assert (r.res, r.length, r.from_, r.to, r.status) == (b"def", 3, 4, 6, 0)
+    r = fx.regex(b"(a", b"x")                           # forgex.F90:266-274
+    assert (r.res, r.length, r.from_, r.to, r.status) == (b"", 0, -9999, -9999, 2)
+    assert r.err_msg == O.error_message(2)
+    r = fx.regex(b"zzz", b"abc")
+    assert (r.res, r.length, r.from_, r.to, r.status) == (b"", 0, 0, 0, 0)
+
+
+@pytest.mark.unpinned
+def test_source_derived_expectations_on_gpu():
+    """read off the reference source, never executed there; oracle and GPU must agree"""
+    LF = b"\n"
+    cases = [
+        ("in", b"^", b"abc", False), ("in", b"^", b"a" + LF + b"b", False),
+        ("in", rb"\s", b" ", False), ("match", rb"\s", b" ", True),
+        ("match", b"^abc$", b"abc" + LF, True), ("match", b"abc$", b"abc" + LF, False),
+        ("match", b"a{0}", b"a", True), ("in", b"aa[bc]", b"aaab", False),
+        ("in", b"/", b"\xc0\xaf", False), ("in", b"[/x]", b"\xc0\xaf", True),
+        ("match", b".", b"\t", False), ("match", b".", b"\xc8", True),
+    ]
+    for op, pat, text, exp in cases:
+        got = fx.op_in(pat, text) if op == "in" else fx.op_match(pat, text)
+        ora = O.op_in(pat, text) if op == "in" else O.op_match(pat, text)
+        assert got == exp == bool(ora), (op, pat, text, got, ora)
+    r = fx.regex(b"^abc$", b"def" + LF + b"abc")
+    assert (r.res, r.from_, r.to) == (LF + b"abc", 4, 7)
+    assert fx.regex_f(b"a{1,7}", b"aaa") == b"a" and fx.regex_f(b"[ab]{1,7}", b"aaa") == b"aaa"
+
+
+# ---- config-shaped batches -----------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 31, 4097, 200000])
+def test_c1_match_fixed(n):
+    buf, n, stride = synth.gen_c1(n)
+    p = fx.Pattern(synth.PATTERNS["c1"], "match")
+    got = p.match_fixed(buf, n, stride)
+    exp = oracle_bool(synth.PATTERNS["c1"], "match", buf, n=n, stride=stride)
+    assert np.array_equal(got, exp)
+    assert 0 < got.mean() < 1 or n < 31
+
+
+@pytest.mark.parametrize("residency", ["auto", "global"])
+@pytest.mark.parametrize("n", [1, 257, 30000])
+def test_c2_in_ragged(n, residency):
+    buf, off = synth.gen_c2(n)
+    p = fx.Pattern(synth.PATTERNS["c2"], "in", residency=residency)
+    got = p.in_batch(buf, off)
+    exp = oracle_bool(synth.PATTERNS["c2"], "in", buf, offsets=off)
+    assert np.array_equal(got, exp)
+    info = p.info()
+    assert info["residency"] == (_lib.FX_TABLE_GLOBAL if residency == "global" else _lib.FX_TABLE_SMEM)
+
+
+def test_c2_overlong_and_prefix_candidates():
+    """texts with bytes >= 0x80 take the exact prefix-candidate replay (api_internal_m.F90:76-104)"""
+    strings = [b"xx\xc1\xa6oobar yy", b"\xc1\xa6oobar fooba!", b"foobax \xc1\xa6oobaz", b"foobar\xff", b"\xe3\x81\x82foobaz",
+               b"fooba", b"foofoobar", b"", b" ", b"foobafoobar", b"\x00foobar\x00"]
+    buf, off = pack(strings)
+    p = fx.Pattern(synth.PATTERNS["c2"], "in")
+    assert p.info()["prefix_mode"] == 1
+    got = p.in_batch(buf, off)
+    exp = oracle_bool(synth.PATTERNS["c2"], "in", buf, offsets=off)
+    assert np.array_equal(got, exp), (got, exp)
+
+
+@pytest.mark.parametrize("n", [1, 300, 20000])
+def test_c3_regex_spans(n):
+    buf, off = synth.gen_c3(n)
+    p = fx.Pattern(synth.PATTERNS["c3"], "regex")
+    f, t = p.regex_batch(buf, off)
+    ef, et = O.Compiled(synth.PATTERNS["c3"], 0).regex_batch(buf, off)
+    assert np.array_equal(f, ef) and np.array_equal(t, et)
+    if n >= 300:
+        assert 0.2 < (f > 0).mean() < 1.0
+
+
+@pytest.mark.parametrize("match_at,crlf", [(0.001, False), (0.5, True), (0.999, False), (None, False)])
+@pytest.mark.parametrize("nbytes", [4099, 3_000_001])
+def test_c4_regex_buffer(nbytes, match_at, crlf):
+    if nbytes < 10000 and match_at is not None and match_at < 0.01:
+        match_at = 0.2
+    buf = synth.gen_c4(nbytes, match_at, crlf=crlf)
+    p = fx.Pattern(synth.PATTERNS["c4"], "regex")
+    got = p.regex_buffer(buf)
+    exp = O.Compiled(synth.PATTERNS["c4"], 0).regex_buffer(buf)
+    assert got == exp
+    if match_at is not None:
+        # the span includes the line terminators the anchors consumed
+        s = bytes(buf[got[0] - 1:got[1]])
+        assert s.startswith(b"\n") or got[0] == 1
+        assert synth.C4_MATCH_LINE in s and s.endswith(b"\n")
+    else:
+        assert got == (0, 0)
+
+
+def test_c4_unaligned_and_tiny_buffers():
+    p = fx.Pattern(synth.PATTERNS["c4"], "regex")
+    c = O.Compiled(synth.PATTERNS["c4"], 0)
+    line = synth.C4_MATCH_LINE
+    for text in [b"", b" ", line, line + b"\n", b"x\n" + line, b"x\r\n" + line + b"\r\nrest", b"INFO a\nINFO b\n",
+                 b"\n" * 40 + line, b"ERROR timeout=1", b"ERROR timeout=", b"\xe3\x81" + line + b"\xe3"]:
+        for shift in (0, 1, 7):
+            arr = np.frombuffer(b"#" * shift + text, dtype=np.uint8)[shift:]
+            assert p.regex_buffer(arr) == c.regex_buffer(np.ascontiguousarray(arr)), (text, shift)
+
+
+@pytest.mark.parametrize("residency", ["auto", "global"])
+def test_c5_in_fixed_big_table(residency):
+    buf, n, stride = synth.gen_c5(3000)
+    p = fx.Pattern(synth.PATTERNS["c5"], "in", residency=residency)
+    got = p.in_fixed(buf, n, stride)
+    exp = oracle_bool(synth.PATTERNS["c5"], "in", buf, n=n, stride=stride)
+    assert np.array_equal(got, exp)
+    assert p.info()["residency"] == _lib.FX_TABLE_GLOBAL   # 10252 byte-states x 16 classes does not fit shared memory
+
+
+# ---- edge cases: empty / ragged / long / unaligned -------------------------------------------------
+def test_ragged_edge_cases():
+    rng = np.random.default_rng(7)
+    strings = [b"", b" ", b"a", b"", b"", b"foobar", b"x" * 5000 + b"foobaz", b"y" * 70000, b"foobar" * 3, b"",
+               bytes(rng.integers(0, 256, size=300, dtype=np.uint8)), b"\x00", b"\xe3\x81", b"fooba", b""]
+    strings += [bytes(rng.integers(0x20, 0x7F, size=int(k), dtype=np.uint8)) for k in rng.integers(0, 40, size=500)]
+    strings += [b"", b""]
+    buf, off = pack(strings)
+    for pat, op in [(b"foo(bar|baz)", "in"), (rb"\d{3}-\d{4}", "match"), (b"[a-z]+", "in"), (b"", "match"), (b"a*", "in"),
+                    (b"x*y+", "match"), (b"foobar", "in"), (b"foobar", "match"), (b"fo+bar", "match"), (b"^$", "in")]:
+        p = fx.Pattern(pat, op)
+        got = p.in_batch(buf, off) if op == "in" else p.match_batch(buf, off)
+        exp = oracle_bool(pat, op, buf, offsets=off)
+        assert np.array_equal(got, exp), (pat, op, np.nonzero(got != exp)[0][:10])
+    for pat in [b"[a-z]+", b"o+b", b"foobar", b"(foo|y+)$", b"^", b"\\s\\S+", b"aa[bc]"]:
+        p = fx.Pattern(pat, "regex")
+        f, t = p.regex_batch(buf, off)
+        ef, et = O.Compiled(pat, 0).regex_batch(buf, off)
+        assert np.array_equal(f, ef) and np.array_equal(t, et), pat
+
+
+def test_fixed_strides_and_alignment():
+    rng = np.random.default_rng(11)
+    for stride in (0, 1, 3, 8, 16, 24, 64, 100):
+        n = 1000
+        raw = rng.integers(0x20, 0x7F, size=n * max(stride, 1) + 16, dtype=np.uint8)
+        raw[rng.random(raw.size) < 0.3] = ord("a")
+        for shift in (0, 5):
+            buf = raw[shift:shift + n * stride]
+            for pat, op in [(b"a+b?", "in"), (b"[a-m ]*", "match"), (b"(a|b)*a(a|b){3}", "in")]:
+                p = fx.Pattern(pat, op)
+                got = p.in_fixed(buf, n, stride) if op == "in" else p.match_fixed(buf, n, stride)
+                exp = oracle_bool(pat, op, np.ascontiguousarray(buf), n=n, stride=stride)
+                assert np.array_equal(got, exp), (stride, shift, pat)
+
+
+def test_utf8_and_invalid_bytes_batch():
+    rng = np.random.default_rng(5)
+    pieces = [b"a", b"z", b" ", "あ".encode(), "ん".encode(), "α".encode(), "　".encode(), b"\x80", b"\xbf", b"\xc3", b"\xe3\x81",
+              b"\xf0\x9f\x98", b"\xff", b"\xc0\x80", b"\xc1\xa1", b"\xe0\x81\xa1", b"\xef\xbf\xbf", b"\xf4\x90\x80\x81", b"\n", b"\r\n", b"_", b"7"]
+    strings = [b"".join(pieces[i] for i in rng.integers(0, len(pieces), size=int(k))) for k in rng.integers(0, 24, size=4000)]
+    buf, off = pack(strings)
+    for pat in [synth.PATTERNS["c3"], b"[a-z]+", b".+", rb"\S+", "[ぁ-ん]+".encode(), b"a.", rb"[^a]{2,3}$", rb"^\w"]:
+        p = fx.Pattern(pat, "regex")
+        f, t = p.regex_batch(buf, off)
+        ef, et = O.Compiled(pat, 0).regex_batch(buf, off)
+        assert np.array_equal(f, ef) and np.array_equal(t, et), pat
+        for op in ("in", "match"):
+            q = fx.Pattern(pat, op)
+            got = q.in_batch(buf, off) if op == "in" else q.match_batch(buf, off)
+            assert np.array_equal(got, oracle_bool(pat, op, buf, offsets=off)), (pat, op)
+
+
+def test_device_pointer_entry_points():
+    import torch
+    buf, off = synth.gen_c2(50000)
+    d_buf = torch.from_numpy(buf).cuda()
+    d_off = torch.from_numpy(off).cuda()
+    d_out = torch.empty(len(off) - 1, dtype=torch.uint8, device="cuda")
+    p = fx.Pattern(synth.PATTERNS["c2"], "in")
+    before = fx.launch_count()
+    p.in_batch_dev(d_buf, d_off, len(off) - 1, int(off[-1]), d_out)
+    torch.cuda.synchronize()
+    assert fx.launch_count() == before + 1
+    assert np.array_equal(d_out.cpu().numpy(), oracle_bool(synth.PATTERNS["c2"], "in", buf, offsets=off))
+    # size-independent property: a line is true iff it holds foobar or foobaz (ASCII data)
+    truth = np.array([(b"foobar" in bytes(buf[off[i]:off[i + 1]])) or (b"foobaz" in bytes(buf[off[i]:off[i + 1]]))
+                      for i in range(2000)], dtype=np.uint8)
+    assert np.array_equal(d_out[:2000].cpu().numpy(), truth)
+
+
+def test_invalid_pattern_and_wrong_op_errors():
+    p = fx.Pattern(b"(a", "in")
+    assert p.status == 2
+    with pytest.raises(fx.ForgexError):
+        p.in_batch(np.zeros(4, np.uint8), np.array([0, 4], np.int64))
+    q = fx.Pattern(b"a", "in")
+    with pytest.raises(fx.ForgexError):
+        q.match_batch(np.zeros(4, np.uint8), np.array([0, 4], np.int64))
+    assert fx.op_in(b"(a", b"a") is False and fx.op_match(b"a)", b"a") is False
