@@ -52,7 +52,7 @@ def lib():
     L.fx_pattern_set_residency.argtypes = [vp, C.c_int]
     L.fx_pattern_literals.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
     L.fx_pattern_tables.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
-                                    C.POINTER(C.c_int32 * 5)]
+                                    C.POINTER(C.c_int32 * 6)]
     L.fx_is_valid_regex.argtypes = [C.c_char_p, i64, C.POINTER(C.c_int)]
     for name in ("fx_match_fixed_dev", "fx_in_fixed_dev"):
         getattr(L, name).argtypes = [vp, u8p, i64, i64, u8p, vp]

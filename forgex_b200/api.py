@@ -110,7 +110,7 @@ class Pattern:
         """host copies of the device tables as numpy arrays (tests / tools)"""
         inf = self.info()
         ptrs = [C.c_void_p() for _ in range(4)]
-        sc = (C.c_int32 * 5)()
+        sc = (C.c_int32 * 6)()
         _check(L.lib().fx_pattern_tables(self.h, *[C.byref(p) for p in ptrs], C.byref(sc)), "fx_pattern_tables")
         ns, rs = inf["byte_states"], inf["row_shift"]
 
@@ -121,7 +121,7 @@ class Pattern:
             "direct": arr(ptrs[1], ns * 256, C.c_uint16).reshape(ns, 256),
             "classmap": arr(ptrs[2], 256, C.c_uint8),
             "flags": arr(ptrs[3], ns, C.c_uint8),
-            "start": sc[0], "start_nul": sc[1], "q0": sc[2], "matched": sc[3], "q0_accepting": bool(sc[4]),
+            "start": sc[0], "start_nul": sc[1], "q0": sc[2], "matched": sc[3], "q0_accepting": bool(sc[4]), "result_threshold": sc[5],
             "row_shift": rs,
         }
 

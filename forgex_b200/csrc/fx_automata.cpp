@@ -387,6 +387,7 @@ struct ByteBuilder {
     std::vector<Inter> inters;
     std::vector<std::vector<int> > rows;  // rows[state][byte]
     std::vector<uint8_t> flags;
+    std::vector<int> remap;               // old state id -> new id (boolean tables)
 
     ByteBuilder(const CpAutomaton& au, bool fb) : a(au), flag_bits(fb) {}
 
@@ -489,6 +490,29 @@ struct ByteBuilder {
             if (st == a.matched) f |= SF_MATCHED;
             flags[(size_t)a.nstates + i] = f;
         }
+        // Boolean tables: renumber so that every "result is true" state has an id >= result_threshold; the
+        // kernels then decide with one compare instead of a flags[] lookup.  State 0 keeps its id.
+        out.result_threshold = total_states;
+        if (!flag_bits) {
+            std::vector<int> perm((size_t)total_states, 0);
+            int next = 1;
+            for (int s = 1; s < total_states; s++)
+                if (!(flags[(size_t)s] & (SF_END | SF_MATCHED))) perm[(size_t)s] = next++;
+            out.result_threshold = next;
+            for (int s = 1; s < total_states; s++)
+                if (flags[(size_t)s] & (SF_END | SF_MATCHED)) perm[(size_t)s] = next++;
+            std::vector<std::vector<int> > nrows((size_t)total_states);
+            std::vector<uint8_t> nflags((size_t)total_states, 0);
+            for (int s = 0; s < total_states; s++) {
+                std::vector<int> r(256);
+                for (int b = 0; b < 256; b++) r[(size_t)b] = perm[(size_t)rows[(size_t)s][(size_t)b]];
+                nrows[(size_t)perm[(size_t)s]].swap(r);
+                nflags[(size_t)perm[(size_t)s]] = flags[(size_t)s];
+            }
+            rows.swap(nrows);
+            flags.swap(nflags);
+            remap = perm;
+        }
         // byte classes: bytes whose columns agree in every state
         std::map<std::vector<int>, int> colid;
         out.nclasses = 0;
@@ -518,8 +542,15 @@ struct ByteBuilder {
         out.direct.assign((size_t)total_states * 256, 0);
         for (int s = 0; s < total_states; s++)
             for (int b = 0; b < 256; b++) out.direct[(size_t)s * 256 + (size_t)b] = word(rows[(size_t)s][(size_t)b]);
+        out.direct8.clear();
+        if (!flag_bits && total_states <= 255) {
+            out.direct8.assign((size_t)total_states * 256, 0);
+            for (int s = 0; s < total_states; s++)
+                for (int b = 0; b < 256; b++) out.direct8[(size_t)s * 256 + (size_t)b] = (uint8_t)rows[(size_t)s][(size_t)b];
+        }
         out.flags = flags;
-        out.start = a.start; out.start_nul = a.start_nul; out.q0 = a.q0; out.matched = a.matched;
+        auto mapped = [&](int s) { return (s >= 0 && !remap.empty()) ? remap[(size_t)s] : s; };
+        out.start = mapped(a.start); out.start_nul = mapped(a.start_nul); out.q0 = mapped(a.q0); out.matched = mapped(a.matched);
         out.q0_accepting = a.q0_accepting;
         out.flag_bits = flag_bits;
         return OK;

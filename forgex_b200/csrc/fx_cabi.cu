@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -28,6 +29,7 @@ struct DeviceTables {
     int device = -1;
     uint16_t* table = nullptr;   // class-compressed
     uint16_t* direct = nullptr;  // 256 columns (only when small)
+    uint8_t* table8 = nullptr;   // 256 columns, one byte per entry (boolean tables with <= 255 states)
     uint8_t* classmap = nullptr;
     uint8_t* flags = nullptr;
     uint8_t* lits = nullptr;
@@ -116,6 +118,10 @@ int ensure_device(fx_pattern* p) {
         CUDA_TRY(cudaMemset(d.direct, 0, db + 16));
         CUDA_TRY(cudaMemcpy(d.direct, bt.direct.data(), bt.direct.size() * 2, cudaMemcpyHostToDevice));
     }
+    if (!bt.direct8.empty()) {
+        CUDA_TRY(cudaMalloc(&d.table8, bt.direct8.size() + 16));
+        CUDA_TRY(cudaMemcpy(d.table8, bt.direct8.data(), bt.direct8.size(), cudaMemcpyHostToDevice));
+    }
     CUDA_TRY(cudaMalloc(&d.classmap, 256));
     CUDA_TRY(cudaMemcpy(d.classmap, bt.classmap, 256, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&d.flags, (bt.flags.size() + 15) & ~(size_t)15));
@@ -139,32 +145,45 @@ int ensure_device(fx_pattern* p) {
 }
 
 struct Plan {
-    bool direct, tsmem;
-    int table_bytes;   // bytes of the selected table
+    int kind;          // fxk::Table<KIND>: 0 u8 direct smem, 1 u16 direct smem, 2 classed smem, 3 classed global
+    int table_bytes;   // bytes of the table staged in shared memory (0 for kind 3)
     KParams kp;
 };
+
+// tuning knobs for experiments (environment, read per launch)
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
 
 int make_plan(fx_pattern* p, Plan& pl) {
     const fx::ByteTable& bt = p->prog.bt;
     const DeviceTables& d = p->dev;
+    const bool span = bt.flag_bits;
     int classed_bytes = (int)bt.table.size() * 2, direct_bytes = (int)bt.direct.size() * 2;
-    bool direct_ok = d.direct != nullptr && direct_bytes <= DIRECT_LIMIT_BYTES;
+    bool direct16_ok = span && d.direct != nullptr && direct_bytes <= env_int("FX_DIRECT_LIMIT_BYTES", DIRECT_LIMIT_BYTES);
+    bool direct8_ok = !span && d.table8 != nullptr && env_int("FX_USE_TABLE8", 1);
     bool classed_smem_ok = classed_bytes <= SMEM_TABLE_LIMIT_BYTES;
     int res = p->residency;
-    if (res == FX_TABLE_SMEM && !direct_ok && !classed_smem_ok) return FX_ERR_BAD_ARGUMENT;
-    if (res == FX_TABLE_GLOBAL) { pl.direct = false; pl.tsmem = false; }
-    else if (direct_ok) { pl.direct = true; pl.tsmem = true; }
-    else if (classed_smem_ok) { pl.direct = false; pl.tsmem = true; }
-    else { pl.direct = false; pl.tsmem = false; }
-    pl.table_bytes = pl.direct ? direct_bytes : classed_bytes;
+    if (res == FX_TABLE_SMEM && !direct16_ok && !direct8_ok && !classed_smem_ok) return FX_ERR_BAD_ARGUMENT;
+    if (res == FX_TABLE_GLOBAL) pl.kind = 3;
+    else if (direct8_ok) pl.kind = 0;
+    else if (direct16_ok) pl.kind = 1;
+    else if (classed_smem_ok) pl.kind = 2;
+    else pl.kind = 3;
+    pl.table_bytes = pl.kind == 0 ? bt.nstates * 256 : pl.kind == 1 ? direct_bytes : pl.kind == 2 ? classed_bytes : 0;
     KParams& k = pl.kp;
-    k.table = pl.direct ? d.direct : d.table;
+    k.table = pl.kind == 1 ? d.direct : d.table;
+    k.table8 = d.table8;
+    k.ctable = d.table;
     k.classmap = d.classmap;
     k.flags = d.flags;
     k.lits = d.lits;
-    k.table_words = pl.table_bytes / 2;
+    k.table_words = (pl.kind == 1 ? direct_bytes : classed_bytes) / 2;
     k.nstates = bt.nstates;
-    k.row_shift = pl.direct ? 8 : bt.row_shift;
+    k.row_shift = pl.kind == 1 ? 8 : bt.row_shift;
+    k.c_row_shift = bt.row_shift;
+    k.result_threshold = bt.result_threshold;
     k.start = bt.start; k.start_nul = bt.start_nul; k.q0 = bt.q0; k.q0_accepting = bt.q0_accepting ? 1 : 0;
     const fx::Literals& L = p->prog.lit;
     k.all_len = (int)L.all.size(); k.pre_len = (int)L.prefix.size(); k.suf_len = (int)L.suffix.size();
@@ -176,8 +195,8 @@ int make_plan(fx_pattern* p, Plan& pl) {
     k.a_start_nul = p->has_anchored ? p->anchored.bt.start_nul : 0;
     k.a_q0 = p->has_anchored ? p->anchored.bt.q0 : 0;
     k.prefix_mode = p->prefix_mode;
-    p->last_residency = pl.tsmem ? FX_TABLE_SMEM : FX_TABLE_GLOBAL;
-    p->last_direct = pl.direct ? 1 : 0;
+    p->last_residency = pl.kind == 3 ? FX_TABLE_GLOBAL : FX_TABLE_SMEM;
+    p->last_direct = pl.kind <= 1 ? 1 : 0;
     return FX_OK;
 }
 
@@ -202,11 +221,13 @@ int occupancy_grid(K kernel, int threads, size_t smem, int sm_count, int& blocks
 }
 
 // ---- launchers -----------------------------------------------------------------------------
-template <int OP, bool DIRECT, bool TSMEM, int VEC>
+inline size_t staged_bytes(const Plan& pl) { return (size_t)((pl.table_bytes + 15) & ~15); }
+
+template <int OP, int KIND, int VEC>
 int launch_fixed_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, int64_t n, int64_t stride, uint8_t* out,
                    cudaStream_t s, int generic) {
-    auto kern = k_bool_fixed<OP, DIRECT, TSMEM, VEC>;
-    size_t smem = 256 + (TSMEM ? (size_t)((pl.table_bytes + 15) & ~15) : 0);
+    auto kern = k_bool_fixed<OP, KIND, VEC>;
+    size_t smem = 256 + staged_bytes(pl);
     int bps = 0;
     int rc = occupancy_grid(kern, 256, smem, p->dev.sm_count, bps);
     if (rc) return rc;
@@ -219,13 +240,17 @@ int launch_fixed_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, int64_t n,
     return cuda_status(cudaGetLastError());
 }
 
-template <int OP, bool DIRECT, bool TSMEM>
+template <int OP, int KIND>
 int launch_fixed_v(fx_pattern* p, const Plan& pl, const uint8_t* buf, int64_t n, int64_t stride, uint8_t* out,
                    cudaStream_t s, int generic) {
     uintptr_t a = reinterpret_cast<uintptr_t>(buf);
-    if (!generic && stride > 0 && stride % 16 == 0 && a % 16 == 0) return launch_fixed_t<OP, DIRECT, TSMEM, 16>(p, pl, buf, n, stride, out, s, generic);
-    if (!generic && stride > 0 && stride % 8 == 0 && a % 8 == 0) return launch_fixed_t<OP, DIRECT, TSMEM, 8>(p, pl, buf, n, stride, out, s, generic);
-    return launch_fixed_t<OP, DIRECT, TSMEM, 1>(p, pl, buf, n, stride, out, s, generic);
+    if (!generic && stride > 0 && stride % 16 == 0 && a % 16 == 0) return launch_fixed_t<OP, KIND, 16>(p, pl, buf, n, stride, out, s, generic);
+    if (!generic && stride > 0 && stride % 8 == 0 && a % 8 == 0) return launch_fixed_t<OP, KIND, 8>(p, pl, buf, n, stride, out, s, generic);
+    return launch_fixed_t<OP, KIND, 1>(p, pl, buf, n, stride, out, s, generic);
+}
+
+inline int generic_mode(const Plan& pl, int op) {
+    return (pl.kp.all_active || (op == 0 && (pl.kp.pre_active || pl.kp.suf_active)) || (op == 1 && pl.kp.prefix_mode == 2)) ? 1 : 0;
 }
 
 template <int OP>
@@ -235,16 +260,17 @@ int launch_fixed(fx_pattern* p, const uint8_t* buf, int64_t n, int64_t stride, u
     Plan pl;
     int rc = make_plan(p, pl);
     if (rc) return rc;
-    int generic = (pl.kp.all_active || (OP == 0 && (pl.kp.pre_active || pl.kp.suf_active)) || (OP == 1 && pl.kp.prefix_mode == 2)) ? 1 : 0;
-    if (pl.direct) return launch_fixed_v<OP, true, true>(p, pl, buf, n, stride, out, s, generic);
-    if (pl.tsmem) return launch_fixed_v<OP, false, true>(p, pl, buf, n, stride, out, s, generic);
-    return launch_fixed_v<OP, false, false>(p, pl, buf, n, stride, out, s, generic);
+    int generic = generic_mode(pl, OP);
+    if (pl.kind == 0) return launch_fixed_v<OP, 0>(p, pl, buf, n, stride, out, s, generic);
+    if (pl.kind == 2) return launch_fixed_v<OP, 2>(p, pl, buf, n, stride, out, s, generic);
+    return launch_fixed_v<OP, 3>(p, pl, buf, n, stride, out, s, generic);
 }
 
+// tiles of `spt` consecutive strings; up to `cap` bytes of their text are staged in shared memory
 struct Tiling {
-    int tile_bytes, slack;
+    int spt, cap;
     int64_t ntiles;
-    int table_smem;  // rounded so that the tile starts 128-byte aligned
+    int table_smem;  // staged table bytes, 16-byte rounded
     size_t smem;
 };
 
@@ -252,27 +278,26 @@ Tiling make_tiling(const Plan& pl, int64_t n, int64_t total) {
     Tiling t;
     int64_t avg = n > 0 ? (total + n - 1) / n : 1;
     if (avg < 1) avg = 1;
-    int64_t tb = avg * 256;
-    tb = (tb + 1023) & ~(int64_t)1023;
-    if (tb < 4096) tb = 4096;
-    if (tb > 32768) tb = 32768;
-    int64_t sl = 2 * avg;
-    sl = (sl + 255) & ~(int64_t)255;
-    if (sl < 256) sl = 256;
-    if (sl > 8192) sl = 8192;
-    t.tile_bytes = (int)tb;
-    t.slack = (int)sl;
-    t.ntiles = total / tb + 1;
-    int tbytes = pl.tsmem ? pl.table_bytes : 0;
-    t.table_smem = ((16 + 256 + tbytes + 127) & ~127) - (16 + 256);
-    t.smem = (size_t)(16 + 256 + t.table_smem) + (size_t)tb + (size_t)sl + 64;
+    int64_t target = env_int("FX_TILE_BYTES", 36 * 1024);
+    int64_t spt = target / avg;
+    spt = (spt / 32) * 32;
+    if (spt < 32) spt = 32;
+    if (spt > 2048) spt = 2048;
+    spt = env_int("FX_TILE_STRINGS", (int)spt);
+    t.spt = (int)spt;
+    t.cap = (int)(target + target / 4);
+    t.ntiles = (n + spt - 1) / spt;
+    t.table_smem = (int)staged_bytes(pl);
+    size_t lay = (size_t)(16 + 256 + t.table_smem) + (size_t)(t.spt + 4) * 4 + (size_t)t.spt;
+    lay = (lay + 127) & ~(size_t)127;
+    t.smem = lay + (size_t)t.cap + 64;
     return t;
 }
 
-template <int OP, bool DIRECT, bool TSMEM>
+template <int OP, int KIND>
 int launch_ragged_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int64_t* off, int64_t n, int64_t total,
                     uint8_t* out, cudaStream_t s, int generic) {
-    auto kern = k_bool_ragged<OP, DIRECT, TSMEM>;
+    auto kern = k_bool_ragged<OP, KIND>;
     Tiling t = make_tiling(pl, n, total);
     int bps = 0;
     int rc = occupancy_grid(kern, 256, t.smem, p->dev.sm_count, bps);
@@ -280,7 +305,7 @@ int launch_ragged_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int
     long long cap = (long long)p->dev.sm_count * bps;
     int grid = (int)(t.ntiles < cap ? t.ntiles : cap);
     if (grid < 1) grid = 1;
-    kern<<<grid, 256, t.smem, s>>>(pl.kp, buf, off, n, total, out, t.tile_bytes, t.slack, t.ntiles, t.table_smem, generic);
+    kern<<<grid, 256, t.smem, s>>>(pl.kp, buf, off, n, total, out, t.spt, t.cap, t.ntiles, t.table_smem, generic);
     g_launches++;
     return cuda_status(cudaGetLastError());
 }
@@ -293,16 +318,16 @@ int launch_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, int64_t
     Plan pl;
     int rc = make_plan(p, pl);
     if (rc) return rc;
-    int generic = (pl.kp.all_active || (OP == 0 && (pl.kp.pre_active || pl.kp.suf_active)) || (OP == 1 && pl.kp.prefix_mode == 2)) ? 1 : 0;
-    if (pl.direct) return launch_ragged_t<OP, true, true>(p, pl, buf, off, n, total, out, s, generic);
-    if (pl.tsmem) return launch_ragged_t<OP, false, true>(p, pl, buf, off, n, total, out, s, generic);
-    return launch_ragged_t<OP, false, false>(p, pl, buf, off, n, total, out, s, generic);
+    int generic = generic_mode(pl, OP);
+    if (pl.kind == 0) return launch_ragged_t<OP, 0>(p, pl, buf, off, n, total, out, s, generic);
+    if (pl.kind == 2) return launch_ragged_t<OP, 2>(p, pl, buf, off, n, total, out, s, generic);
+    return launch_ragged_t<OP, 3>(p, pl, buf, off, n, total, out, s, generic);
 }
 
-template <bool DIRECT, bool TSMEM>
+template <int KIND>
 int launch_regex_ragged_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int64_t* off, int64_t n,
                           int64_t total, int64_t* from, int64_t* to, cudaStream_t s) {
-    auto kern = k_regex_ragged<DIRECT, TSMEM>;
+    auto kern = k_regex_ragged<KIND>;
     Tiling t = make_tiling(pl, n, total);
     int bps = 0;
     int rc = occupancy_grid(kern, 256, t.smem, p->dev.sm_count, bps);
@@ -310,7 +335,7 @@ int launch_regex_ragged_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, con
     long long cap = (long long)p->dev.sm_count * bps;
     int grid = (int)(t.ntiles < cap ? t.ntiles : cap);
     if (grid < 1) grid = 1;
-    kern<<<grid, 256, t.smem, s>>>(pl.kp, buf, off, n, total, from, to, t.tile_bytes, t.slack, t.ntiles, t.table_smem);
+    kern<<<grid, 256, t.smem, s>>>(pl.kp, buf, off, n, total, from, to, t.spt, t.cap, t.ntiles, t.table_smem);
     g_launches++;
     return cuda_status(cudaGetLastError());
 }
@@ -322,19 +347,19 @@ int launch_regex_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, i
     Plan pl;
     int rc = make_plan(p, pl);
     if (rc) return rc;
-    if (pl.direct) return launch_regex_ragged_t<true, true>(p, pl, buf, off, n, total, from, to, s);
-    if (pl.tsmem) return launch_regex_ragged_t<false, true>(p, pl, buf, off, n, total, from, to, s);
-    return launch_regex_ragged_t<false, false>(p, pl, buf, off, n, total, from, to, s);
+    if (pl.kind == 1) return launch_regex_ragged_t<1>(p, pl, buf, off, n, total, from, to, s);
+    if (pl.kind == 2) return launch_regex_ragged_t<2>(p, pl, buf, off, n, total, from, to, s);
+    return launch_regex_ragged_t<3>(p, pl, buf, off, n, total, from, to, s);
 }
 
-template <bool DIRECT, bool TSMEM>
+template <int KIND>
 int launch_buffer_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, int64_t len, int64_t* from_to,
                     unsigned long long* best, cudaStream_t s) {
     CUDA_TRY(cudaMemsetAsync(best, 0xFF, 8, s));
     bool trivial = pl.kp.all_active || len <= 1;
     if (!trivial) {
-        auto kern = k_buffer_scan<DIRECT, TSMEM>;
-        size_t smem = 256 + (TSMEM ? (size_t)((pl.table_bytes + 15) & ~15) : 0);
+        auto kern = k_buffer_scan<KIND>;
+        size_t smem = 256 + staged_bytes(pl) + 256;
         int bps = 0;
         int rc = occupancy_grid(kern, 256, smem, p->dev.sm_count, bps);
         if (rc) return rc;
@@ -347,8 +372,7 @@ int launch_buffer_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, int64_t l
         g_launches++;
         CUDA_TRY(cudaGetLastError());
     }
-    if (DIRECT) k_buffer_finish<true><<<1, 1, 0, s>>>(pl.kp, buf, len, best, from_to);
-    else k_buffer_finish<false><<<1, 1, 0, s>>>(pl.kp, buf, len, best, from_to);
+    k_buffer_finish<<<1, 1, 0, s>>>(pl.kp, buf, len, best, from_to);
     g_launches++;
     return cuda_status(cudaGetLastError());
 }
@@ -362,9 +386,9 @@ int launch_buffer(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* from_
     Plan pl;
     int rc = make_plan(p, pl);
     if (rc) return rc;
-    if (pl.direct) return launch_buffer_t<true, true>(p, pl, buf, len, from_to, best, s);
-    if (pl.tsmem) return launch_buffer_t<false, true>(p, pl, buf, len, from_to, best, s);
-    return launch_buffer_t<false, false>(p, pl, buf, len, from_to, best, s);
+    if (pl.kind == 1) return launch_buffer_t<1>(p, pl, buf, len, from_to, best, s);
+    if (pl.kind == 2) return launch_buffer_t<2>(p, pl, buf, len, from_to, best, s);
+    return launch_buffer_t<3>(p, pl, buf, len, from_to, best, s);
 }
 
 template <typename T>
@@ -412,7 +436,7 @@ int fx_pattern_free(fx_pattern* p) {
     if (!p) return FX_OK;
     DeviceTables& d = p->dev;
     if (d.device >= 0) {
-        cudaFree(d.table); cudaFree(d.direct); cudaFree(d.classmap); cudaFree(d.flags); cudaFree(d.lits);
+        cudaFree(d.table); cudaFree(d.direct); cudaFree(d.table8); cudaFree(d.classmap); cudaFree(d.flags); cudaFree(d.lits);
         cudaFree(d.a_table); cudaFree(d.a_classmap); cudaFree(d.a_flags);
         cudaFree(d.w_buf); cudaFree(d.w_off); cudaFree(d.w_out); cudaFree(d.w_span); cudaFree(d.w_best);
     }
@@ -460,7 +484,7 @@ int fx_pattern_literals(const fx_pattern* p, void* all, void* prefix, void* suff
 }
 
 int fx_pattern_tables(const fx_pattern* p, const uint16_t** table, const uint16_t** direct, const uint8_t** classmap,
-                      const uint8_t** flags, int32_t scalars[5]) {
+                      const uint8_t** flags, int32_t scalars[6]) {
     if (!p || p->prog.status != fx::OK) return FX_ERR_BAD_ARGUMENT;
     const fx::ByteTable& bt = p->prog.bt;
     if (table) *table = bt.table.data();
@@ -470,6 +494,7 @@ int fx_pattern_tables(const fx_pattern* p, const uint16_t** table, const uint16_
     if (scalars) {
         scalars[0] = bt.start; scalars[1] = bt.start_nul; scalars[2] = bt.q0; scalars[3] = bt.matched;
         scalars[4] = bt.q0_accepting ? 1 : 0;
+        scalars[5] = bt.result_threshold;
     }
     return FX_OK;
 }

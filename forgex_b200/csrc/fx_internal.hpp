@@ -147,6 +147,10 @@ struct ByteTable {
     bool flag_bits = false;
     // direct form: 256 columns, no classmap lookup (filled when it fits, see fx_cabi.cu)
     std::vector<uint16_t> direct;  // nstates * 256
+    // boolean tables only: result states are numbered last (state >= result_threshold <=> SF_END|SF_MATCHED),
+    // and with <= 255 states a one-byte-per-entry 256-column table exists
+    int result_threshold = 0;
+    std::vector<uint8_t> direct8;  // nstates * 256, or empty
 };
 
 int build_byte_table(const CpAutomaton& a, bool flag_bits, ByteTable& out);

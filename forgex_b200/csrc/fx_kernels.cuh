@@ -37,6 +37,12 @@ struct KParams {
     const uint8_t* a_flags;
     int a_row_shift, a_start_nul, a_q0;
     int prefix_mode;          // 0: none; 1: neutral unless the text holds bytes >= 0x80; 2: always replay
+    // boolean tables: one-byte entries (<= 255 states) and "state >= result_threshold <=> result is true"
+    const uint8_t* table8;
+    int result_threshold;
+    // the class-compressed table in global memory, whatever `table` points to (slow paths, finish kernel)
+    const uint16_t* ctable;
+    int c_row_shift;
 };
 
 // ---- small PTX helpers ---------------------------------------------------------------------
@@ -88,38 +94,37 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 
 // ---- table access --------------------------------------------------------------------------
-// TSMEM: table (and classmap) staged in shared memory; otherwise read through L1/L2 with __ldg.
-template <bool DIRECT, bool TSMEM>
+// KIND 0: one-byte entries, 256 columns, shared memory (boolean tables with <= 255 states).  A row is 64
+//         words: for ASCII text the 32 banks see distinct words, so lanes in the same state never conflict.
+// KIND 1: 16-bit entries, 256 columns, shared memory (span tables, flag bits in the word)
+// KIND 2: 16-bit entries, class-compressed rows + classmap, shared memory
+// KIND 3: 16-bit entries, class-compressed rows + classmap, global memory through L1/L2
+template <int KIND>
 struct Table {
-    uint32_t s_table, s_cmap;  // shared addresses (TSMEM)
+    uint32_t s_table, s_cmap;  // shared addresses
     const uint16_t* g_table;
     const uint8_t* g_cmap;
     int shift;
     __device__ __forceinline__ uint32_t next(uint32_t state, uint32_t byte) const {
-        if (TSMEM) {
-            if (DIRECT) return lds_u16(s_table + (((state << 8) | byte) << 1));
-            uint32_t c = lds_u8(s_cmap + byte);
-            return lds_u16(s_table + (((state << shift) + c) << 1));
-        } else {
-            if (DIRECT) return __ldg(g_table + ((state << 8) | byte));
-            uint32_t c = __ldg(g_cmap + byte);
-            return __ldg(g_table + ((state << shift) + c));
-        }
+        if (KIND == 0) return lds_u8(s_table + ((state << 8) | byte));
+        if (KIND == 1) return lds_u16(s_table + (((state << 8) | byte) << 1));
+        if (KIND == 2) return lds_u16(s_table + (((state << shift) + lds_u8(s_cmap + byte)) << 1));
+        return __ldg(g_table + ((state << shift) + __ldg(g_cmap + byte)));
     }
 };
 
 // cooperative copy of the table into shared memory; returns the filled Table
-template <bool DIRECT, bool TSMEM>
-__device__ __forceinline__ Table<DIRECT, TSMEM> stage_table(const KParams& p, uint8_t* smem_table, uint8_t* smem_cmap) {
-    Table<DIRECT, TSMEM> t;
+template <int KIND>
+__device__ __forceinline__ Table<KIND> stage_table(const KParams& p, uint8_t* smem_table, uint8_t* smem_cmap) {
+    Table<KIND> t;
     t.g_table = p.table; t.g_cmap = p.classmap; t.shift = p.row_shift;
     t.s_table = 0; t.s_cmap = 0;
-    if (TSMEM) {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.table);
+    if (KIND != 3) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(KIND == 0 ? (const void*)p.table8 : (const void*)p.table);
         uint32_t* dst = reinterpret_cast<uint32_t*>(smem_table);
-        int words32 = (p.table_words + 1) >> 1;
+        const int words32 = KIND == 0 ? p.nstates * 64 : (p.table_words + 1) >> 1;
         for (int i = threadIdx.x; i < words32; i += blockDim.x) dst[i] = __ldg(src + i);
-        if (!DIRECT)
+        if (KIND == 2)
             for (int i = threadIdx.x; i < 64; i += blockDim.x)
                 reinterpret_cast<uint32_t*>(smem_cmap)[i] = __ldg(reinterpret_cast<const uint32_t*>(p.classmap) + i);
         t.s_table = smem_u32(smem_table);
@@ -129,7 +134,7 @@ __device__ __forceinline__ Table<DIRECT, TSMEM> stage_table(const KParams& p, ui
 }
 
 __device__ __forceinline__ bool result_flag(const KParams& p, uint32_t state) {
-    return (__ldg(p.flags + state) & (SF_END | SF_MATCHED)) != 0;
+    return state >= (uint32_t)p.result_threshold;   // boolean tables number their result states last
 }
 
 // Text of length 0, or one blank, never reaches the `.in.`/`regex` loop (api_internal_m.F90:68-74);
@@ -316,7 +321,7 @@ __device__ inline void including_exact(const Anchored& A, const TBL& T, FETCH fe
 template <class FETCH>
 __device__ inline bool in_with_prefix(const KParams& p, FETCH fetch, int64_t len) {
     if (len == 0 || (len == 1 && fetch(0) == 0x20)) return p.q0_accepting != 0;
-    Table<false, false> T;
+    Table<3> T;
     T.g_table = p.a_table; T.g_cmap = p.a_classmap; T.shift = p.a_row_shift; T.s_table = 0; T.s_cmap = 0;
     Anchored A{p.a_flags, p.a_start_nul, p.a_q0};
     int64_t f, t;
@@ -346,10 +351,10 @@ __device__ inline void eval_regex(const KParams& p, const TBL& T, FETCH fetch, i
     if (f > 0 && t > 0) { from = f; to = t; }                    // forgex.F90:332-343
 }
 
-// ---- generic (slow) evaluation: full wrapper semantics incl. literal paths -------------------
-// Used when a pattern has literal gates, and by strings that do not fit a staged tile.
+// ---- slow path: full wrapper semantics incl. literal gates, text read from global memory ------------
+// Kept out of line so that the hot loops stay small.  Uses the class-compressed table in global memory.
 __device__ __forceinline__ bool lit_equal(const uint8_t* a, const uint8_t* lit, int n) {
-    for (int i = 0; i < n; i++) if (a[i] != __ldg(lit + i)) return false;
+    for (int i = 0; i < n; i++) if (__ldg(a + i) != __ldg(lit + i)) return false;
     return true;
 }
 // index(text, lit): 1-based position of the first occurrence, 0 if none (forgex.F90:114, :284)
@@ -361,14 +366,14 @@ __device__ inline int64_t lit_index(const uint8_t* s, int64_t len, const uint8_t
     return 0;
 }
 
-template <int OP, bool DIRECT, bool TSMEM>
-__device__ inline bool eval_bool_generic(const KParams& p, const Table<DIRECT, TSMEM>& T, const uint8_t* s, int64_t len) {
+template <int OP>
+__device__ __noinline__ bool eval_bool_slow(const KParams& p, const uint8_t* s, int64_t len) {
     const uint8_t* all = p.lits;
     const uint8_t* pre = p.lits + p.all_len;
     const uint8_t* suf = pre + p.pre_len;
     if (OP == 1) {
         if (p.all_active) return lit_index(s, len, all, p.all_len) > 0;
-        if (p.prefix_mode == 2) return in_with_prefix(p, FetchGeneric{s}, len);
+        if (p.prefix_mode == 2) return in_with_prefix(p, FetchGlobal{s}, len);
     } else {
         if (p.all_active && len == p.all_len) return lit_equal(s, all, p.all_len);
         // prefix / suffix gate of do_matching_exactly (api_internal_m.F90:199-233)
@@ -383,22 +388,22 @@ __device__ inline bool eval_bool_generic(const KParams& p, const Table<DIRECT, T
             if (p.suf_active && ls != 0) return false;
         }
     }
-    if (degenerate_text<OP>(len, len ? s[0] : 0)) return p.q0_accepting != 0;
+    if (degenerate_text<OP>(len, len ? __ldg(s) : 0)) return p.q0_accepting != 0;
+    Table<3> T;
+    T.g_table = p.ctable; T.g_cmap = p.classmap; T.shift = p.c_row_shift; T.s_table = 0; T.s_cmap = 0;
     uint32_t st = (uint32_t)p.start;
     uint32_t high = 0;
-    for (int64_t i = 0; i < len; i++) { uint32_t b = s[i]; high |= b; st = T.next(st, b); }
+    for (int64_t i = 0; i < len; i++) { uint32_t b = __ldg(s + i); high |= b; st = T.next(st, b); }
     bool r = result_flag(p, st);
-    if (OP == 1 && r && p.prefix_mode == 1 && (high & 0x80)) r = in_with_prefix(p, FetchGeneric{s}, len);
+    if (OP == 1 && r && p.prefix_mode == 1 && (high & 0x80)) r = in_with_prefix(p, FetchGlobal{s}, len);
     return r;
 }
+__device__ __noinline__ bool recheck_in_with_prefix(const KParams& p, const uint8_t* s, int64_t len) {
+    return in_with_prefix(p, FetchGlobal{s}, len);
+}
 
-// ---------------------------------------------------------------------------------------------
-// K1: fixed-stride batch, boolean result (configs C1 `.match.` 8-byte strings, C5 `.in.` 64-byte)
-// One thread per string; consecutive threads read consecutive strings, so a warp's loads cover a
-// contiguous 32*stride-byte span.
-// ---------------------------------------------------------------------------------------------
-template <bool DIRECT, bool TSMEM>
-__device__ __forceinline__ uint32_t step4(const Table<DIRECT, TSMEM>& T, uint32_t st, uint32_t w) {
+template <int KIND>
+__device__ __forceinline__ uint32_t step4(const Table<KIND>& T, uint32_t st, uint32_t w) {
     st = T.next(st, w & 0xFF);
     st = T.next(st, (w >> 8) & 0xFF);
     st = T.next(st, (w >> 16) & 0xFF);
@@ -406,21 +411,26 @@ __device__ __forceinline__ uint32_t step4(const Table<DIRECT, TSMEM>& T, uint32_
     return st;
 }
 
-template <int OP, bool DIRECT, bool TSMEM, int VEC>
+// ---------------------------------------------------------------------------------------------
+// K1: fixed-stride batch, boolean result (configs C1 `.match.` 8-byte strings, C5 `.in.` 64-byte)
+// One thread per string; consecutive threads read consecutive strings, so a warp's loads cover a
+// contiguous 32*stride-byte span.
+// ---------------------------------------------------------------------------------------------
+template <int OP, int KIND, int VEC>
 __global__ void __launch_bounds__(256) k_bool_fixed(KParams p, const uint8_t* __restrict__ buf, int64_t n, int64_t stride,
                                                     uint8_t* __restrict__ out, int generic) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_cmap = smem;
     uint8_t* s_table = smem + 256;
-    Table<DIRECT, TSMEM> T = stage_table<DIRECT, TSMEM>(p, s_table, s_cmap);
-    if (TSMEM) __syncthreads();
+    Table<KIND> T = stage_table<KIND>(p, s_table, s_cmap);
+    if (KIND != 3) __syncthreads();
     const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gstride) {
         const uint8_t* s = buf + i * stride;
         bool r;
         if (generic) {
-            r = eval_bool_generic<OP, DIRECT, TSMEM>(p, T, s, stride);
-        } else if (degenerate_text<OP>(stride, stride ? s[0] : 0)) {
+            r = eval_bool_slow<OP>(p, s, stride);
+        } else if (degenerate_text<OP>(stride, stride ? __ldg(s) : 0)) {
             r = p.q0_accepting != 0;
         } else {
             uint32_t st = (uint32_t)p.start;
@@ -441,7 +451,7 @@ __global__ void __launch_bounds__(256) k_bool_fixed(KParams p, const uint8_t* __
                 for (int64_t k = 0; k < stride; k++) { uint32_t b = __ldg(s + k); high |= b; st = T.next(st, b); }
             }
             r = result_flag(p, st);
-            if (OP == 1 && r && p.prefix_mode == 1 && (high & 0x80808080u)) r = in_with_prefix(p, FetchGlobal{s}, stride);
+            if (OP == 1 && r && p.prefix_mode == 1 && (high & 0x80808080u)) r = recheck_in_with_prefix(p, s, stride);
         }
         out[i] = r ? 1 : 0;
     }
@@ -449,24 +459,16 @@ __global__ void __launch_bounds__(256) k_bool_fixed(KParams p, const uint8_t* __
 
 // ---------------------------------------------------------------------------------------------
 // K2: ragged batch (flat buffer + int64 offsets), boolean result (config C2 `.in.`)
-// A CTA owns tile t = bytes [t*tile_bytes, (t+1)*tile_bytes) of the flat buffer and the strings that
-// START inside it.  The tile (plus `slack` bytes so that most strings end inside the staged region)
-// is brought into shared memory by ONE TMA bulk copy; each thread then walks one string out of
-// shared memory.  Strings that run past the staged region are walked from global memory.
+// A CTA owns tile t = strings [t*spt, (t+1)*spt).  Their bytes are contiguous in the flat buffer, so the
+// tile is brought into shared memory by ONE TMA bulk copy (up to `cap` bytes; strings that reach past the
+// staged region are walked from global memory by the slow path).  The tile's offsets are staged next to it
+// as 32-bit tile-relative values, each thread walks one string at a time out of shared memory, and the
+// results are written back as one coalesced run.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int64_t lower_bound_i64(const int64_t* __restrict__ a, int64_t n, int64_t key) {
-    int64_t lo = 0, hi = n;
-    while (lo < hi) {
-        int64_t mid = (lo + hi) >> 1;
-        if (__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
 // Stage bytes [t0, t1) of buf into shared memory at `tile` such that byte x lives at tile[x - base],
 // base = t0 rounded down so that the global source is 16-byte aligned.  Returns base.
 __device__ __forceinline__ int64_t stage_tile(const uint8_t* __restrict__ buf, int64_t t0, int64_t t1, int64_t total,
-                                              uint8_t* tile, uint32_t mbar, uint32_t& phase) {
+                                              uint8_t* tile, uint32_t mbar, bool& armed) {
     const uintptr_t g0 = reinterpret_cast<uintptr_t>(buf) + (uintptr_t)t0;
     const int64_t base = t0 - (int64_t)(g0 & 15);                       // may be < 0 by up to 15 (stays inside the allocation)
     const uintptr_t gend = reinterpret_cast<uintptr_t>(buf) + (uintptr_t)total;
@@ -475,23 +477,20 @@ __device__ __forceinline__ int64_t stage_tile(const uint8_t* __restrict__ buf, i
     if (gcopy_end > gsafe_end) gcopy_end = gsafe_end;
     const uintptr_t gsrc = g0 & ~(uintptr_t)15;
     const uint32_t bulk = gcopy_end > gsrc ? (uint32_t)(gcopy_end - gsrc) : 0u;
-    if (bulk) {
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(mbar, bulk);
-            bulk_g2s(smem_u32(tile), reinterpret_cast<const void*>(gsrc), bulk, mbar);
-        }
+    armed = bulk != 0;
+    if (bulk && threadIdx.x == 0) {
+        mbar_expect_tx(mbar, bulk);
+        bulk_g2s(smem_u32(tile), reinterpret_cast<const void*>(gsrc), bulk, mbar);
     }
     // tail (< 16 bytes at the very end of the buffer): plain loads
     const int64_t copied_to = (int64_t)(gsrc + bulk - reinterpret_cast<uintptr_t>(buf));
     for (int64_t x = copied_to + threadIdx.x; x < t1; x += blockDim.x)
         if (x >= 0) tile[x - base] = __ldg(buf + x);
-    if (bulk) { mbar_wait(mbar, phase); phase ^= 1; }
-    __syncthreads();
     return base;
 }
 
-template <bool DIRECT, bool TSMEM>
-__device__ __forceinline__ uint32_t walk_smem(const Table<DIRECT, TSMEM>& T, uint32_t st, uint32_t addr, int len, uint32_t& high) {
+template <int KIND>
+__device__ __forceinline__ uint32_t walk_smem(const Table<KIND>& T, uint32_t st, uint32_t addr, int len, uint32_t& high) {
     int i = 0;
     while (i < len && ((addr + i) & 3)) { uint32_t b = lds_u8(addr + i); high |= b; st = T.next(st, b); i++; }
     for (; i + 4 <= len; i += 4) { uint32_t w = lds_u32(addr + i); high |= w; st = step4(T, st, w); }
@@ -499,82 +498,111 @@ __device__ __forceinline__ uint32_t walk_smem(const Table<DIRECT, TSMEM>& T, uin
     return st;
 }
 
-template <int OP, bool DIRECT, bool TSMEM>
+static constexpr int32_t OFF_BEYOND = 0x7FFFFFFF;   // staged offset of a position past the staged bytes
+
+// common tile prologue of K2 / K3: stages text + offsets of tile t, returns string count (0 = empty tile)
+struct TileCtx {
+    int64_t first;     // first string of the tile
+    int count;         // strings in the tile
+    int64_t base;      // buffer position of tile[0]
+    int64_t t1;        // end of the staged bytes (buffer position)
+};
+__device__ __forceinline__ TileCtx load_tile(const uint8_t* __restrict__ buf, const int64_t* __restrict__ offsets,
+                                             int64_t n, int64_t total, int64_t t, int spt, int cap, uint8_t* tile,
+                                             int32_t* s_off, uint32_t mbar, uint32_t& phase) {
+    TileCtx c;
+    c.first = t * spt;
+    c.count = (int)((n - c.first) < spt ? (n - c.first) : spt);
+    const int64_t t0 = __ldg(offsets + c.first);
+    const int64_t tend = __ldg(offsets + c.first + c.count);
+    c.t1 = tend - t0 > cap ? t0 + cap : tend;
+    bool armed = false;
+    c.base = t0;
+    if (t0 < c.t1) c.base = stage_tile(buf, t0, c.t1, total, tile, mbar, armed);
+    for (int i = threadIdx.x; i <= c.count; i += blockDim.x) {          // overlaps with the bulk copy in flight
+        const int64_t o = __ldg(offsets + c.first + i);
+        s_off[i] = o > c.t1 ? OFF_BEYOND : (int32_t)(o - c.base);
+    }
+    if (armed) { mbar_wait(mbar, phase); phase ^= 1; }
+    __syncthreads();
+    return c;
+}
+
+template <int OP, int KIND>
 __global__ void __launch_bounds__(256) k_bool_ragged(KParams p, const uint8_t* __restrict__ buf,
                                                      const int64_t* __restrict__ offsets, int64_t n, int64_t total,
-                                                     uint8_t* __restrict__ out, int tile_bytes, int slack,
-                                                     int64_t ntiles, int table_smem_bytes, int generic) {
+                                                     uint8_t* __restrict__ out, int spt, int cap, int64_t ntiles,
+                                                     int table_smem_bytes, int generic) {
     extern __shared__ __align__(128) uint8_t smem[];
-    // layout: [0,16) mbarrier | classmap 256 | table | tile (16-byte aligned)
+    // layout: [0,16) mbarrier | classmap 256 | table | offsets (spt+1) x int32 | results spt | tile (128-byte aligned)
     uint8_t* s_cmap = smem + 16;
     uint8_t* s_table = smem + 16 + 256;
-    uint8_t* tile = smem + 16 + 256 + table_smem_bytes;
+    int32_t* s_off = reinterpret_cast<int32_t*>(smem + 16 + 256 + table_smem_bytes);
+    uint8_t* s_res = reinterpret_cast<uint8_t*>(s_off + spt + 4);
+    uint8_t* tile = smem + ((16 + 256 + table_smem_bytes + (spt + 4) * 4 + spt + 127) & ~127);
     const uint32_t mbar = smem_u32(smem);
-    Table<DIRECT, TSMEM> T = stage_table<DIRECT, TSMEM>(p, s_table, s_cmap);
+    Table<KIND> T = stage_table<KIND>(p, s_table, s_cmap);
     if (threadIdx.x == 0) mbar_init(mbar, 1);
     __syncthreads();
     uint32_t phase = 0;
+    const uint32_t tile_addr = smem_u32(tile);
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int64_t t0 = t * tile_bytes;
-        int64_t t1 = t0 + tile_bytes + slack;
-        if (t1 > total) t1 = total;
-        const int64_t s_begin = lower_bound_i64(offsets, n, t0);
-        const int64_t s_end = lower_bound_i64(offsets, n, t0 + tile_bytes);
-        if (s_begin >= s_end) continue;   // uniform across the CTA
-        const int64_t base = t0 < t1 ? stage_tile(buf, t0, t1, total, tile, mbar, phase) : t0;
-        const uint32_t tile_addr = smem_u32(tile);
-        for (int64_t s = s_begin + threadIdx.x; s < s_end; s += blockDim.x) {
-            const int64_t o0 = __ldg(offsets + s), o1 = __ldg(offsets + s + 1);
-            const int64_t len = o1 - o0;
+        const TileCtx c = load_tile(buf, offsets, n, total, t, spt, cap, tile, s_off, mbar, phase);
+        for (int i = threadIdx.x; i < c.count; i += blockDim.x) {
+            const int32_t r0 = s_off[i], r1 = s_off[i + 1];
             bool r;
-            if (generic || o1 > t1) {
-                r = eval_bool_generic<OP, DIRECT, TSMEM>(p, T, buf + o0, len);
+            if (generic || r1 == OFF_BEYOND) {
+                const int64_t o0 = __ldg(offsets + c.first + i), o1 = __ldg(offsets + c.first + i + 1);
+                r = eval_bool_slow<OP>(p, buf + o0, o1 - o0);
             } else {
-                const uint32_t a = tile_addr + (uint32_t)(o0 - base);
+                const int len = r1 - r0;
+                const uint32_t a = tile_addr + (uint32_t)r0;
                 if (degenerate_text<OP>(len, len ? lds_u8(a) : 0)) r = p.q0_accepting != 0;
                 else {
                     uint32_t high = 0;
-                    r = result_flag(p, walk_smem(T, (uint32_t)p.start, a, (int)len, high));
-                    if (OP == 1 && r && p.prefix_mode == 1 && (high & 0x80808080u)) r = in_with_prefix(p, FetchShared{a}, len);
+                    r = result_flag(p, walk_smem(T, (uint32_t)p.start, a, len, high));
+                    if (OP == 1 && r && p.prefix_mode == 1 && (high & 0x80808080u))
+                        r = recheck_in_with_prefix(p, buf + (c.base + r0), len);
                 }
             }
-            out[s] = r ? 1 : 0;
+            s_res[i] = r ? 1 : 0;
         }
-        __syncthreads();  // everyone is done with the tile before the next bulk copy overwrites it
+        __syncthreads();                 // results complete; everyone is done with the tile
+        for (int i = threadIdx.x; i < c.count; i += blockDim.x) out[c.first + i] = s_res[i];
+        __syncthreads();                 // before the next tile overwrites offsets / results / text
     }
 }
 
-// K3: ragged batch, span result (config C3).  Same tiling as K2.
-template <bool DIRECT, bool TSMEM>
+// K3: ragged batch, span result (config C3).  Same tiling as K2; the table words carry flag bits.
+template <int KIND>
 __global__ void __launch_bounds__(256) k_regex_ragged(KParams p, const uint8_t* __restrict__ buf,
                                                       const int64_t* __restrict__ offsets, int64_t n, int64_t total,
                                                       int64_t* __restrict__ from, int64_t* __restrict__ to,
-                                                      int tile_bytes, int slack, int64_t ntiles, int table_smem_bytes) {
+                                                      int spt, int cap, int64_t ntiles, int table_smem_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_cmap = smem + 16;
     uint8_t* s_table = smem + 16 + 256;
-    uint8_t* tile = smem + 16 + 256 + table_smem_bytes;
+    int32_t* s_off = reinterpret_cast<int32_t*>(smem + 16 + 256 + table_smem_bytes);
+    uint8_t* tile = smem + ((16 + 256 + table_smem_bytes + (spt + 4) * 4 + spt + 127) & ~127);
     const uint32_t mbar = smem_u32(smem);
-    Table<DIRECT, TSMEM> T = stage_table<DIRECT, TSMEM>(p, s_table, s_cmap);
+    Table<KIND> T = stage_table<KIND>(p, s_table, s_cmap);
     if (threadIdx.x == 0) mbar_init(mbar, 1);
     __syncthreads();
     uint32_t phase = 0;
+    const uint32_t tile_addr = smem_u32(tile);
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int64_t t0 = t * tile_bytes;
-        int64_t t1 = t0 + tile_bytes + slack;
-        if (t1 > total) t1 = total;
-        const int64_t s_begin = lower_bound_i64(offsets, n, t0);
-        const int64_t s_end = lower_bound_i64(offsets, n, t0 + tile_bytes);
-        if (s_begin >= s_end) continue;
-        const int64_t base = t0 < t1 ? stage_tile(buf, t0, t1, total, tile, mbar, phase) : t0;
-        const uint32_t tile_addr = smem_u32(tile);
-        for (int64_t s = s_begin + threadIdx.x; s < s_end; s += blockDim.x) {
-            const int64_t o0 = __ldg(offsets + s), o1 = __ldg(offsets + s + 1);
+        const TileCtx c = load_tile(buf, offsets, n, total, t, spt, cap, tile, s_off, mbar, phase);
+        for (int i = threadIdx.x; i < c.count; i += blockDim.x) {
+            const int32_t r0 = s_off[i], r1 = s_off[i + 1];
             int64_t f, e;
-            if (o1 > t1) eval_regex(p, T, FetchGlobal{buf + o0}, o1 - o0, f, e);
-            else eval_regex(p, T, FetchShared{tile_addr + (uint32_t)(o0 - base)}, o1 - o0, f, e);
-            from[s] = f;
-            to[s] = e;
+            if (r1 == OFF_BEYOND) {
+                const int64_t o0 = __ldg(offsets + c.first + i), o1 = __ldg(offsets + c.first + i + 1);
+                eval_regex(p, T, FetchGlobal{buf + o0}, o1 - o0, f, e);
+            } else {
+                eval_regex(p, T, FetchShared{tile_addr + (uint32_t)r0}, (int64_t)(r1 - r0), f, e);
+            }
+            from[c.first + i] = f;
+            to[c.first + i] = e;
         }
         __syncthreads();
     }
@@ -610,29 +638,39 @@ __device__ inline bool continuation_is_boundary(const uint8_t* __restrict__ s, i
     return true;                                     // three continuation bytes in front: pos cannot be covered
 }
 
-template <bool DIRECT, bool TSMEM>
+// candidate at text index pos whose first byte b survives the first transition: run it (out of line)
+template <int KIND>
+__device__ __noinline__ bool try_start(const KParams& p, const Table<KIND>& T, const uint8_t* __restrict__ buf, int64_t len,
+                                       int64_t pos, uint32_t b) {
+    if ((b & 0xC0) == 0x80 && !continuation_is_boundary(buf, len, pos)) return false;
+    const Anchored A{p.flags, p.start_nul, p.q0};
+    return run_attempt(A, T, FetchGlobal{buf}, len, (uint32_t)p.q0, pos, -1) >= 0;
+}
+
+template <int KIND>
 __global__ void __launch_bounds__(256) k_buffer_scan(KParams p, const uint8_t* __restrict__ buf, int64_t len,
                                                      unsigned long long* __restrict__ best) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_cmap = smem;
     uint8_t* s_table = smem + 256;
-    Table<DIRECT, TSMEM> T = stage_table<DIRECT, TSMEM>(p, s_table, s_cmap);
-    if (TSMEM) __syncthreads();
-    FetchGlobal fetch{buf};
+    uint8_t* s_first = smem + 256 + (KIND == 3 ? 0 : ((p.table_words * 2 + 15) & ~15));   // 256 bytes: does byte b survive the step out of q0?
+    Table<KIND> T = stage_table<KIND>(p, s_table, s_cmap);
+    if (KIND != 3) __syncthreads();
     const uint32_t q0 = (uint32_t)p.q0;
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) s_first[b] = (T.next(q0, (uint32_t)b) & W_STATE) != 0;
+    __syncthreads();
+    const uint32_t first_addr = smem_u32(s_first);
+    FetchGlobal fetch{buf};
     const Anchored A{p.flags, p.start_nul, p.q0};
     // head: bytes before the first 16-byte aligned address are handled by block 0 / thread 0 one by one
     const uintptr_t g = reinterpret_cast<uintptr_t>(buf);
     int64_t head = (int64_t)((16 - (g & 15)) & 15);
     if (head > len) head = len;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        // start 1 = the leading NUL sentinel; key 1
-        if (attempt_at(A, T, fetch, len, 1) >= 0) atomicMin(best, 1ull);
+        if (attempt_at(A, T, fetch, len, 1) >= 0) atomicMin(best, 1ull);   // start 1 = the leading NUL sentinel
         for (int64_t pos = 0; pos < head; pos++) {
             const uint32_t b = fetch(pos);
-            if ((T.next(q0, b) & W_STATE) == 0) continue;
-            if ((b & 0xC0) == 0x80 && !continuation_is_boundary(buf, len, pos)) continue;
-            if (run_attempt(A, T, fetch, len, q0, pos, -1) >= 0) { atomicMin(best, (unsigned long long)pos + 2); break; }
+            if (lds_u8(first_addr + b) && try_start(p, T, buf, len, pos, b)) { atomicMin(best, (unsigned long long)pos + 2); break; }
         }
     }
     const int64_t nvec = (len - head) >> 4;          // whole 16-byte units
@@ -645,39 +683,34 @@ __global__ void __launch_bounds__(256) k_buffer_scan(KParams p, const uint8_t* _
         const int64_t pos0 = head + (u << 4);
         const uint4 v = ldg_nc_v4(buf + pos0);
         const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-        bool done = false;
+        // fast filter: one shared-memory byte per candidate, no dependent chain
+        uint32_t hits = 0;
 #pragma unroll
-        for (int q = 0; q < 4 && !done; q++) {
+        for (int q = 0; q < 4; q++) {
 #pragma unroll
-            for (int r = 0; r < 4 && !done; r++) {
-                const uint32_t b = (wv[q] >> (8 * r)) & 0xFF;
-                if ((T.next(q0, b) & W_STATE) == 0) continue;
-                const int64_t pos = pos0 + q * 4 + r;
-                if ((b & 0xC0) == 0x80 && !continuation_is_boundary(buf, len, pos)) continue;
-                if (run_attempt(A, T, fetch, len, q0, pos, -1) >= 0) {
-                    atomicMin(best, (unsigned long long)pos + 2);
-                    done = true;
-                }
-            }
+            for (int r = 0; r < 4; r++) hits |= lds_u8(first_addr + ((wv[q] >> (8 * r)) & 0xFF)) << (q * 4 + r);
+        }
+        while (hits) {
+            const int k = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const uint32_t b = (wv[k >> 2] >> (8 * (k & 3))) & 0xFF;
+            if (try_start(p, T, buf, len, pos0 + k, b)) { atomicMin(best, (unsigned long long)(pos0 + k) + 2); break; }
         }
     }
     // tail: the last (len - head) % 16 bytes, by the last block's thread 0
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
         for (int64_t pos = head + (nvec << 4); pos < len; pos++) {
             const uint32_t b = fetch(pos);
-            if ((T.next(q0, b) & W_STATE) == 0) continue;
-            if ((b & 0xC0) == 0x80 && !continuation_is_boundary(buf, len, pos)) continue;
-            if (run_attempt(A, T, fetch, len, q0, pos, -1) >= 0) { atomicMin(best, (unsigned long long)pos + 2); break; }
+            if (lds_u8(first_addr + b) && try_start(p, T, buf, len, pos, b)) { atomicMin(best, (unsigned long long)pos + 2); break; }
         }
     }
 }
 
 // second step: longest end for the winning start; also the literal / degenerate cases
-template <bool DIRECT>
 __global__ void k_buffer_finish(KParams p, const uint8_t* __restrict__ buf, int64_t len,
                                 const unsigned long long* __restrict__ best, int64_t* __restrict__ from_to) {
-    Table<DIRECT, false> T;
-    T.g_table = p.table; T.g_cmap = p.classmap; T.shift = p.row_shift; T.s_table = 0; T.s_cmap = 0;
+    Table<3> T;
+    T.g_table = p.ctable; T.g_cmap = p.classmap; T.shift = p.c_row_shift; T.s_table = 0; T.s_cmap = 0;
     FetchGlobal fetch{buf};
     int64_t from = 0, to = 0;
     if (p.all_active || len == 0 || (len == 1 && fetch(0) == 0x20)) {

@@ -99,9 +99,9 @@ int fx_pattern_set_residency(fx_pattern* p, int residency);
 int fx_pattern_literals(const fx_pattern* p, void* all, void* prefix, void* suffix);
 /* read-only views of the host copies of the device tables (for tests / tools):
  * table: byte_states << row_shift uint16 words; direct: byte_states * 256 words;
- * classmap: 256 bytes; flags: byte_states bytes; scalars: {start, start_nul, q0, matched, q0_accepting} */
+ * classmap: 256 bytes; flags: byte_states bytes; scalars: {start, start_nul, q0, matched, q0_accepting, result_threshold} */
 int fx_pattern_tables(const fx_pattern* p, const uint16_t** table, const uint16_t** direct,
-                      const uint8_t** classmap, const uint8_t** flags, int32_t scalars[5]);
+                      const uint8_t** classmap, const uint8_t** flags, int32_t scalars[6]);
 int fx_is_valid_regex(const void* pattern, int64_t plen, int* status);
 
 /* ---- device-pointer entry points (asynchronous on `stream`) ---------------------------- */

@@ -229,6 +229,7 @@ class Model:
             high |= b
             st = self.nxt(st, b)
         r = bool(t["flags"][st] & (SF_END | SF_MATCHED))
+        assert r == (st >= t["result_threshold"])   # the kernels decide with this compare
         if self.op == 1 and r and self.prefix_mode == 1 and (high & 0x80):
             r = self.in_with_prefix(s)
         return r
