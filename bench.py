@@ -35,10 +35,11 @@ WORKLOADS = {
     "c3": "c3: '[α-ωぁ-ん]+\\s\\w{2,8}' regex() spans over mixed Greek/Japanese/ASCII strings incl. invalid bytes",
     "c4": "c4: '^ERROR.*timeout=\\d+$' regex() over one synthetic log buffer",
     "c5": "c5: '(a|b)*a(a|b){12}' .in. over fixed 64-byte strings, table in global memory (L2)",
+    "c2f": "c2f (experiment): 'foo(bar|baz)' .in. over FIXED 160-byte random ASCII strings (per-lane 16-byte global loads)",
 }
-DEFAULT_UNITS = {"c1": 1 << 30, "c2": 100_000_000, "c3": 16_000_000, "c4": 32 << 30, "c5": 10_000_000}
+DEFAULT_UNITS = {"c2f": 20_000_000, "c1": 1 << 30, "c2": 100_000_000, "c3": 16_000_000, "c4": 32 << 30, "c5": 10_000_000}
 # algorithmic bytes per unit besides the text itself: offsets read + result written
-EXTRA_BYTES = {"c1": 1, "c2": 8 + 1, "c3": 8 + 16, "c4": 0, "c5": 1}
+EXTRA_BYTES = {"c2f": 1, "c1": 1, "c2": 8 + 1, "c3": 8 + 16, "c4": 0, "c5": 1}
 
 
 def measured_peak():
@@ -142,8 +143,8 @@ def tile_ragged_device(torch, buf_np, off_np, n):
 def build_workload(torch, cfg, units, rank):
     """returns dict(run=callable, text_bytes, units, verify=callable or None, host=(...) for e2e/cpu legs)"""
     import forgex_b200 as fx
-    pat = synth.PATTERNS[cfg]
-    op = synth.OPS[cfg]
+    pat = synth.PATTERNS.get(cfg, synth.PATTERNS["c2"])
+    op = synth.OPS.get(cfg, "in")
     w = {"cfg": cfg, "pattern": pat, "op": op}
     if cfg == "c2":
         p = fx.Pattern(pat, "in")
@@ -151,6 +152,15 @@ def build_workload(torch, cfg, units, rank):
         out = torch.empty(units, dtype=torch.uint8, device="cuda")
         w.update(run=lambda: p.in_batch_dev(buf, off, units, total, out), text_bytes=total, units=units, out=out,
                  buf=buf, off=off, pattern_obj=p)
+    elif cfg == "c2f":
+        p = fx.Pattern(synth.PATTERNS["c2"], "in")
+        g = torch.Generator(device="cuda")
+        g.manual_seed(1234 + rank)
+        stride = int(os.environ.get("FX_C2F_STRIDE", "160"))
+        buf = torch.randint(0x20, 0x7F, (units * stride,), device="cuda", generator=g, dtype=torch.uint8)
+        out = torch.empty(units, dtype=torch.uint8, device="cuda")
+        w.update(run=lambda: p.in_fixed_dev(buf, units, stride, out), text_bytes=units * stride, units=units, out=out,
+                 buf=buf, stride=stride, pattern_obj=p)
     elif cfg in ("c1", "c5"):
         gen = synth.gen_c1 if cfg == "c1" else synth.gen_c5
         block_n = min(units, 1 << 20)
@@ -435,7 +445,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOADS[cfg], "strings_per_gpu": w["units"] if cfg != "c4" else 1,
-                       "text_bytes_per_gpu": w["text_bytes"], "pattern": synth.PATTERNS[cfg].decode("utf-8"),
+                       "text_bytes_per_gpu": w["text_bytes"], "pattern": synth.PATTERNS.get(cfg, synth.PATTERNS["c2"]).decode("utf-8"),
                        "l2": "inputs larger than L2 (no flush needed)" if w["text_bytes"] > (256 << 20) else "input fits L2: latency-bound case",
                        "table": w["pattern_obj"].info()},
             "strings_per_s": units_all / (ms_step / 1000.0),

@@ -266,7 +266,8 @@ int launch_fixed(fx_pattern* p, const uint8_t* buf, int64_t n, int64_t stride, u
     return launch_fixed_v<OP, 3>(p, pl, buf, n, stride, out, s, generic);
 }
 
-// tiles of `spt` consecutive strings; up to `cap` bytes of their text are staged in shared memory
+// tiles of `spt` consecutive strings; up to `cap` bytes of a tile's text are staged in shared memory.  The tile is
+// sized so that `ctas_per_sm` CTAs fit one SM's shared memory (227 KB usable, 1 KB reserved per CTA).
 struct Tiling {
     int spt, cap;
     int64_t ntiles;
@@ -278,19 +279,26 @@ Tiling make_tiling(const Plan& pl, int64_t n, int64_t total) {
     Tiling t;
     int64_t avg = n > 0 ? (total + n - 1) / n : 1;
     if (avg < 1) avg = 1;
-    int64_t target = env_int("FX_TILE_BYTES", 36 * 1024);
-    int64_t spt = target / avg;
-    spt = (spt / 32) * 32;
-    if (spt < 32) spt = 32;
-    if (spt > 2048) spt = 2048;
+    t.table_smem = (int)staged_bytes(pl);
+    int ctas = env_int("FX_CTAS_PER_SM", 4);
+    int64_t per_cta = (227 * 1024) / ctas - 1024;
+    // strings per tile: about one per thread, fewer when strings are long, more when they are short
+    int64_t spt = 0, cap = 0;
+    for (int iter = 0; iter < 2; iter++) {
+        int64_t fixed = tile_offset(t.table_smem, (int)(spt ? spt : 256)) + 64 + 128;
+        cap = per_cta - fixed;
+        if (cap < 8192) cap = 8192;
+        cap &= ~(int64_t)127;
+        spt = (cap * 4 / 5) / avg;           // expect the tile to fill ~80 % of the staged capacity
+        spt = (spt / 32) * 32;
+        if (spt < 32) spt = 32;
+        if (spt > 2048) spt = 2048;
+    }
     spt = env_int("FX_TILE_STRINGS", (int)spt);
     t.spt = (int)spt;
-    t.cap = (int)(target + target / 4);
+    t.cap = (int)cap;
     t.ntiles = (n + spt - 1) / spt;
-    t.table_smem = (int)staged_bytes(pl);
-    size_t lay = (size_t)(16 + 256 + t.table_smem) + (size_t)(t.spt + 4) * 4 + (size_t)t.spt;
-    lay = (lay + 127) & ~(size_t)127;
-    t.smem = lay + (size_t)t.cap + 64;
+    t.smem = (size_t)tile_offset(t.table_smem, t.spt) + (size_t)t.cap + 64;
     return t;
 }
 

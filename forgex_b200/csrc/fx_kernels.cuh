@@ -467,8 +467,8 @@ __global__ void __launch_bounds__(256) k_bool_fixed(KParams p, const uint8_t* __
 // ---------------------------------------------------------------------------------------------
 // Stage bytes [t0, t1) of buf into shared memory at `tile` such that byte x lives at tile[x - base],
 // base = t0 rounded down so that the global source is 16-byte aligned.  Returns base.
-__device__ __forceinline__ int64_t stage_tile(const uint8_t* __restrict__ buf, int64_t t0, int64_t t1, int64_t total,
-                                              uint8_t* tile, uint32_t mbar, bool& armed) {
+__device__ __forceinline__ int64_t stage_tile(const uint8_t* __restrict__ buf, int64_t t0, int64_t t1,
+                                              int64_t total, uint8_t* tile, uint32_t mbar, bool& armed) {
     const uintptr_t g0 = reinterpret_cast<uintptr_t>(buf) + (uintptr_t)t0;
     const int64_t base = t0 - (int64_t)(g0 & 15);                       // may be < 0 by up to 15 (stays inside the allocation)
     const uintptr_t gend = reinterpret_cast<uintptr_t>(buf) + (uintptr_t)total;
@@ -500,16 +500,17 @@ __device__ __forceinline__ uint32_t walk_smem(const Table<KIND>& T, uint32_t st,
 
 static constexpr int32_t OFF_BEYOND = 0x7FFFFFFF;   // staged offset of a position past the staged bytes
 
-// common tile prologue of K2 / K3: stages text + offsets of tile t, returns string count (0 = empty tile)
+// common tile prologue of K2 / K3: stages text + offsets of tile t
 struct TileCtx {
     int64_t first;     // first string of the tile
     int count;         // strings in the tile
     int64_t base;      // buffer position of tile[0]
     int64_t t1;        // end of the staged bytes (buffer position)
 };
-__device__ __forceinline__ TileCtx load_tile(const uint8_t* __restrict__ buf, const int64_t* __restrict__ offsets,
-                                             int64_t n, int64_t total, int64_t t, int spt, int cap, uint8_t* tile,
-                                             int32_t* s_off, uint32_t mbar, uint32_t& phase) {
+__device__ __forceinline__ TileCtx load_tile(const uint8_t* __restrict__ buf,
+                                             const int64_t* __restrict__ offsets, int64_t n, int64_t total, int64_t t,
+                                             int spt, int cap, uint8_t* tile, int32_t* s_off, uint32_t mbar,
+                                             uint32_t& phase) {
     TileCtx c;
     c.first = t * spt;
     c.count = (int)((n - c.first) < spt ? (n - c.first) : spt);
@@ -528,18 +529,23 @@ __device__ __forceinline__ TileCtx load_tile(const uint8_t* __restrict__ buf, co
     return c;
 }
 
+// shared-memory layout of the ragged kernels (must match make_tiling() in fx_cabi.cu):
+//   [0,16) mbarrier | classmap 256 | table | offsets (spt+4) x int32 | results spt | pad to 128 | tile (cap+64)
+__host__ __device__ __forceinline__ int tile_offset(int table_smem_bytes, int spt) {
+    return (16 + 256 + table_smem_bytes + (spt + 4) * 4 + spt + 127) & ~127;
+}
+
 template <int OP, int KIND>
-__global__ void __launch_bounds__(256) k_bool_ragged(KParams p, const uint8_t* __restrict__ buf,
-                                                     const int64_t* __restrict__ offsets, int64_t n, int64_t total,
-                                                     uint8_t* __restrict__ out, int spt, int cap, int64_t ntiles,
-                                                     int table_smem_bytes, int generic) {
+__global__ void __launch_bounds__(256, 4) k_bool_ragged(KParams p, const uint8_t* __restrict__ buf,
+                                                        const int64_t* __restrict__ offsets, int64_t n, int64_t total,
+                                                        uint8_t* __restrict__ out, int spt, int cap, int64_t ntiles,
+                                                        int table_smem_bytes, int generic) {
     extern __shared__ __align__(128) uint8_t smem[];
-    // layout: [0,16) mbarrier | classmap 256 | table | offsets (spt+1) x int32 | results spt | tile (128-byte aligned)
     uint8_t* s_cmap = smem + 16;
     uint8_t* s_table = smem + 16 + 256;
     int32_t* s_off = reinterpret_cast<int32_t*>(smem + 16 + 256 + table_smem_bytes);
     uint8_t* s_res = reinterpret_cast<uint8_t*>(s_off + spt + 4);
-    uint8_t* tile = smem + ((16 + 256 + table_smem_bytes + (spt + 4) * 4 + spt + 127) & ~127);
+    uint8_t* tile = smem + tile_offset(table_smem_bytes, spt);
     const uint32_t mbar = smem_u32(smem);
     Table<KIND> T = stage_table<KIND>(p, s_table, s_cmap);
     if (threadIdx.x == 0) mbar_init(mbar, 1);
@@ -583,7 +589,7 @@ __global__ void __launch_bounds__(256) k_regex_ragged(KParams p, const uint8_t* 
     uint8_t* s_cmap = smem + 16;
     uint8_t* s_table = smem + 16 + 256;
     int32_t* s_off = reinterpret_cast<int32_t*>(smem + 16 + 256 + table_smem_bytes);
-    uint8_t* tile = smem + ((16 + 256 + table_smem_bytes + (spt + 4) * 4 + spt + 127) & ~127);
+    uint8_t* tile = smem + tile_offset(table_smem_bytes, spt);
     const uint32_t mbar = smem_u32(smem);
     Table<KIND> T = stage_table<KIND>(p, s_table, s_cmap);
     if (threadIdx.x == 0) mbar_init(mbar, 1);
