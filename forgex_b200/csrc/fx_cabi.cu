@@ -318,6 +318,26 @@ int launch_ragged_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int
     return cuda_status(cudaGetLastError());
 }
 
+template <int OP, int KIND>
+int launch_stream_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int64_t* off, int64_t n, int64_t total,
+                    uint8_t* out, cudaStream_t s) {
+    auto kern = k_bool_stream<OP, KIND>;
+    size_t smem = 256 + staged_bytes(pl);
+    int bps = 0;
+    int rc = occupancy_grid(kern, 256, smem, p->dev.sm_count, bps);
+    if (rc) return rc;
+    int window = env_int("FX_WINDOW", 1024);
+    if (window < 64) window = 64;
+    int64_t nwindows = total / window + 1;
+    long long want = (nwindows + 255) / 256;
+    long long cap = (long long)p->dev.sm_count * bps;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    kern<<<grid, 256, smem, s>>>(pl.kp, buf, off, n, total, out, window, nwindows);
+    g_launches++;
+    return cuda_status(cudaGetLastError());
+}
+
 template <int OP>
 int launch_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, int64_t n, int64_t total, uint8_t* out,
                   cudaStream_t s) {
@@ -327,6 +347,11 @@ int launch_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, int64_t
     int rc = make_plan(p, pl);
     if (rc) return rc;
     int generic = generic_mode(pl, OP);
+    if (!generic && env_int("FX_RAGGED_FORM", 0) == 1) {      // streaming form (K2s)
+        if (pl.kind == 0) return launch_stream_t<OP, 0>(p, pl, buf, off, n, total, out, s);
+        if (pl.kind == 2) return launch_stream_t<OP, 2>(p, pl, buf, off, n, total, out, s);
+        return launch_stream_t<OP, 3>(p, pl, buf, off, n, total, out, s);
+    }
     if (pl.kind == 0) return launch_ragged_t<OP, 0>(p, pl, buf, off, n, total, out, s, generic);
     if (pl.kind == 2) return launch_ragged_t<OP, 2>(p, pl, buf, off, n, total, out, s, generic);
     return launch_ragged_t<OP, 3>(p, pl, buf, off, n, total, out, s, generic);
@@ -367,16 +392,17 @@ int launch_buffer_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, int64_t l
     bool trivial = pl.kp.all_active || len <= 1;
     if (!trivial) {
         auto kern = k_buffer_scan<KIND>;
-        size_t smem = 256 + staged_bytes(pl) + 256;
+        int table_smem = (int)staged_bytes(pl);
+        int tile_bytes = env_int("FX_SCAN_TILE_BYTES", 32 * 1024);
+        size_t smem = (size_t)scan_tile_offset(table_smem) + (size_t)tile_bytes + 64;
         int bps = 0;
         int rc = occupancy_grid(kern, 256, smem, p->dev.sm_count, bps);
         if (rc) return rc;
-        long long units = (len >> 4) + 1;
-        long long want = (units + 255) / 256;
+        long long ntiles = (len + tile_bytes - 1) / tile_bytes;
         long long cap = (long long)p->dev.sm_count * bps;
-        int grid = (int)(want < cap ? want : cap);
+        int grid = (int)(ntiles < cap ? ntiles : cap);
         if (grid < 1) grid = 1;
-        kern<<<grid, 256, smem, s>>>(pl.kp, buf, len, best);
+        kern<<<grid, 256, smem, s>>>(pl.kp, buf, len, best, tile_bytes, ntiles, table_smem);
         g_launches++;
         CUDA_TRY(cudaGetLastError());
     }

@@ -579,6 +579,126 @@ __global__ void __launch_bounds__(256, 4) k_bool_ragged(KParams p, const uint8_t
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K2s: ragged batch, boolean result, streaming form.
+// The flat buffer is cut into windows of `window` bytes; a thread owns the strings that START inside its
+// window and streams through them in address order (they are contiguous), reading the text straight from
+// global memory as aligned 16-byte loads with the next chunk always in flight.  A string boundary is just
+// "record the result, reset the state".  Compared with the tile form there is no shared-memory text (shared
+// memory only holds the table, so text reads cost no bank conflicts), no block barrier, and a thread's work
+// is its window plus/minus one string, which keeps the 32 lanes of a warp busy regardless of how ragged the
+// strings are.  Consecutive lanes own consecutive windows, so a warp sweeps one contiguous region.
+// ---------------------------------------------------------------------------------------------
+struct StreamCold {   // per-thread bookkeeping that only the (rare, out-of-line) string-boundary code touches
+    int64_t s;        // current string
+    int64_t o0;       // its start
+    int64_t o2;       // offsets[s + 2], prefetched
+};
+
+// The current string [C.o0, o1) ends after the byte just consumed (b): write its result and move to the next
+// string that starts inside the window (empty strings in between are answered on the spot).  Returns the end
+// offset of the new current string, or -1 when the thread's window is exhausted.
+template <int OP>
+__device__ __noinline__ int64_t stream_emit(const KParams& p, const uint8_t* __restrict__ buf,
+                                            const int64_t* __restrict__ offsets, int64_t n, int64_t w1,
+                                            uint8_t* __restrict__ out, StreamCold& C, int64_t o1, uint32_t st,
+                                            uint32_t b, uint32_t high) {
+    bool r = result_flag(p, st);
+    const int64_t len = o1 - C.o0;
+    if (OP == 1 && len == 1 && b == 0x20) r = p.q0_accepting != 0;     // single blank: api_internal_m.F90:68-74
+    if (OP == 1 && r && p.prefix_mode == 1 && (high & 0x80808080u)) r = recheck_in_with_prefix(p, buf + C.o0, len);
+    out[C.s] = r ? 1 : 0;
+    C.s++;
+    C.o0 = o1;
+    o1 = C.o2;
+    while (C.s < n && C.o0 < w1 && o1 == C.o0) {                       // empty strings
+        out[C.s] = p.q0_accepting ? 1 : 0;
+        C.s++;
+        o1 = C.s + 1 <= n ? __ldg(offsets + C.s + 1) : o1;
+    }
+    if (C.s >= n || C.o0 >= w1) return -1;
+    C.o2 = C.s + 2 <= n ? __ldg(offsets + C.s + 2) : o1;
+    return o1;
+}
+
+template <int OP, int KIND>
+__global__ void __launch_bounds__(256, 4) k_bool_stream(KParams p, const uint8_t* __restrict__ buf,
+                                                        const int64_t* __restrict__ offsets, int64_t n, int64_t total,
+                                                        uint8_t* __restrict__ out, int window, int64_t nwindows) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_cmap = smem;
+    uint8_t* s_table = smem + 256;
+    Table<KIND> T = stage_table<KIND>(p, s_table, s_cmap);
+    if (KIND != 3) __syncthreads();
+    const uintptr_t gbuf = reinterpret_cast<uintptr_t>(buf);
+    const uintptr_t glast = (gbuf + (uintptr_t)total + 15) & ~(uintptr_t)15;   // end of the last 16-byte block that holds text
+    const uint32_t start = (uint32_t)p.start;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwindows;
+         w += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t w0 = w * window;
+        const int64_t w1 = (w == nwindows - 1) ? total + 1 : w0 + window;   // strings with o0 in [w0, w1)
+        StreamCold C;
+        {   // first string that starts at or after w0
+            int64_t lo = 0, hi = n;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (__ldg(offsets + mid) < w0) lo = mid + 1; else hi = mid;
+            }
+            C.s = lo;
+        }
+        if (C.s >= n) continue;
+        C.o0 = __ldg(offsets + C.s);
+        if (C.o0 >= w1) continue;
+        int64_t o1 = __ldg(offsets + C.s + 1);
+        bool done = false;
+        while (o1 == C.o0) {                                             // leading empty strings
+            out[C.s] = p.q0_accepting ? 1 : 0;
+            C.s++;
+            if (C.s >= n) { done = true; break; }
+            o1 = __ldg(offsets + C.s + 1);
+        }
+        if (done) continue;
+        C.o2 = C.s + 2 <= n ? __ldg(offsets + C.s + 2) : o1;
+        uint32_t st = start;
+        // the thread's private stream: aligned 16-byte chunks; (cp, k0) = next unread byte
+        const uint4* cp = reinterpret_cast<const uint4*>((gbuf + (uintptr_t)C.o0) & ~(uintptr_t)15);
+        int k0 = (int)((gbuf + (uintptr_t)C.o0) & 15);
+        int64_t cbase = C.o0 - k0;                                       // buffer offset of the chunk's first byte
+        uint4 cur = __ldg(cp);
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        if (reinterpret_cast<uintptr_t>(cp + 1) < glast) nxt = __ldg(cp + 1);
+        uint32_t high = 0;
+        while (true) {
+            const uint32_t wv[4] = {cur.x, cur.y, cur.z, cur.w};
+            const uint32_t chigh = cur.x | cur.y | cur.z | cur.w;
+            high |= chigh;
+            const int64_t rem64 = o1 - (cbase + k0);                        // bytes until the current string ends (>= 1)
+            const int kend = rem64 < (int64_t)(16 - k0) ? k0 + (int)rem64 : 16;
+            const uint32_t mask = (0xFFFFu >> (16 - kend)) & (0xFFFFu << k0);
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                if (mask & (1u << k)) st = T.next(st, (wv[k >> 2] >> (8 * (k & 3))) & 0xFF);
+            }
+            if ((int64_t)(kend - k0) == rem64) {                            // the string ended inside this chunk
+                const uint32_t b = (wv[(kend - 1) >> 2] >> (8 * ((kend - 1) & 3))) & 0xFF;
+                o1 = stream_emit<OP>(p, buf, offsets, n, w1, out, C, o1, st, b, high);
+                if (o1 < 0) break;
+                st = start;
+                high = chigh;
+            }
+            if (kend == 16) {                                               // move to the next chunk, keep one in flight
+                cp++;
+                cbase += 16;
+                k0 = 0;
+                cur = nxt;
+                if (reinterpret_cast<uintptr_t>(cp + 1) < glast) nxt = __ldg(cp + 1);
+            } else {
+                k0 = kend;
+            }
+        }
+    }
+}
+
 // K3: ragged batch, span result (config C3).  Same tiling as K2; the table words carry flag bits.
 template <int KIND>
 __global__ void __launch_bounds__(256) k_regex_ragged(KParams p, const uint8_t* __restrict__ buf,
@@ -644,71 +764,120 @@ __device__ inline bool continuation_is_boundary(const uint8_t* __restrict__ s, i
     return true;                                     // three continuation bytes in front: pos cannot be covered
 }
 
+// text access for attempts launched from a staged tile: shared memory inside the tile, global memory beyond it
+struct FetchTile {
+    uint32_t saddr;          // shared address of buffer position `tbase`
+    int64_t tbase, tend;     // staged range
+    const uint8_t* g;
+    __device__ __forceinline__ uint32_t operator()(int64_t i) const {
+        return (i >= tbase && i < tend) ? lds_u8(saddr + (uint32_t)(i - tbase)) : __ldg(g + i);
+    }
+};
+
 // candidate at text index pos whose first byte b survives the first transition: run it (out of line)
 template <int KIND>
-__device__ __noinline__ bool try_start(const KParams& p, const Table<KIND>& T, const uint8_t* __restrict__ buf, int64_t len,
-                                       int64_t pos, uint32_t b) {
+__device__ __noinline__ bool try_start(const KParams& p, const Table<KIND>& T, const FetchTile& fetch,
+                                       const uint8_t* __restrict__ buf, int64_t len, int64_t pos, uint32_t b) {
     if ((b & 0xC0) == 0x80 && !continuation_is_boundary(buf, len, pos)) return false;
     const Anchored A{p.flags, p.start_nul, p.q0};
-    return run_attempt(A, T, FetchGlobal{buf}, len, (uint32_t)p.q0, pos, -1) >= 0;
+    return run_attempt(A, T, fetch, len, (uint32_t)p.q0, pos, -1) >= 0;
 }
 
+// shared-memory layout of K4: classmap 256 | table | first-byte filter 256 | mbarrier + flags 16 |
+//                             candidate queue (SCAN_QUEUE x int32) | pad to 128 | tile
+static constexpr int SCAN_QUEUE = 2048;
+__host__ __device__ __forceinline__ int scan_tile_offset(int table_smem_bytes) {
+    return (256 + table_smem_bytes + 256 + 16 + SCAN_QUEUE * 4 + 127) & ~127;
+}
+
+// Two phases per tile.  Filter: every thread looks at 16 consecutive candidate starts out of one conflict-free
+// 16-byte shared-memory load; a candidate survives if its first byte leaves q0 alive and its second byte does
+// not kill it right away (or if that cannot be decided from two bytes); survivors go to a small queue.
+// Attempts: the queued starts are handed out one per thread, so the (few, long) attempts run side by side
+// instead of one lane at a time inside the filter loop.
 template <int KIND>
 __global__ void __launch_bounds__(256) k_buffer_scan(KParams p, const uint8_t* __restrict__ buf, int64_t len,
-                                                     unsigned long long* __restrict__ best) {
+                                                     unsigned long long* __restrict__ best, int tile_bytes,
+                                                     int64_t ntiles, int table_smem_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_cmap = smem;
     uint8_t* s_table = smem + 256;
-    uint8_t* s_first = smem + 256 + (KIND == 3 ? 0 : ((p.table_words * 2 + 15) & ~15));   // 256 bytes: does byte b survive the step out of q0?
+    uint8_t* s_first = smem + 256 + table_smem_bytes;   // does byte b survive the step out of q0?
+    const uint32_t mbar = smem_u32(smem + 256 + table_smem_bytes + 256);
+    volatile int* s_stop = reinterpret_cast<volatile int*>(smem + 256 + table_smem_bytes + 256 + 8);
+    int* s_qn = reinterpret_cast<int*>(smem + 256 + table_smem_bytes + 256 + 12);
+    int32_t* s_queue = reinterpret_cast<int32_t*>(smem + 256 + table_smem_bytes + 256 + 16);
+    uint8_t* tile = smem + scan_tile_offset(table_smem_bytes);
     Table<KIND> T = stage_table<KIND>(p, s_table, s_cmap);
-    if (KIND != 3) __syncthreads();
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
     const uint32_t q0 = (uint32_t)p.q0;
     for (int b = threadIdx.x; b < 256; b += blockDim.x) s_first[b] = (T.next(q0, (uint32_t)b) & W_STATE) != 0;
     __syncthreads();
     const uint32_t first_addr = smem_u32(s_first);
-    FetchGlobal fetch{buf};
-    const Anchored A{p.flags, p.start_nul, p.q0};
-    // head: bytes before the first 16-byte aligned address are handled by block 0 / thread 0 one by one
-    const uintptr_t g = reinterpret_cast<uintptr_t>(buf);
-    int64_t head = (int64_t)((16 - (g & 15)) & 15);
-    if (head > len) head = len;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (attempt_at(A, T, fetch, len, 1) >= 0) atomicMin(best, 1ull);   // start 1 = the leading NUL sentinel
-        for (int64_t pos = 0; pos < head; pos++) {
-            const uint32_t b = fetch(pos);
-            if (lds_u8(first_addr + b) && try_start(p, T, buf, len, pos, b)) { atomicMin(best, (unsigned long long)pos + 2); break; }
-        }
+    const uint32_t tile_addr = smem_u32(tile);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {          // start 1 = the leading NUL sentinel
+        const Anchored A{p.flags, p.start_nul, p.q0};
+        if (attempt_at(A, T, FetchGlobal{buf}, len, 1) >= 0) atomicMin(best, 1ull);
     }
-    const int64_t nvec = (len - head) >> 4;          // whole 16-byte units
-    const int64_t units_per_block = (int64_t)blockDim.x;
-    for (int64_t u0 = (int64_t)blockIdx.x * units_per_block; u0 < nvec; u0 += (int64_t)gridDim.x * units_per_block) {
-        const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(best);
-        if (cur != NO_START && (unsigned long long)(head + (u0 << 4)) + 2 > cur) break;   // everything here lies behind the winner
-        const int64_t u = u0 + threadIdx.x;
-        if (u >= nvec) continue;
-        const int64_t pos0 = head + (u << 4);
-        const uint4 v = ldg_nc_v4(buf + pos0);
-        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-        // fast filter: one shared-memory byte per candidate, no dependent chain
-        uint32_t hits = 0;
+    uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t t0 = t * tile_bytes;
+        const int64_t t1 = t0 + tile_bytes < len ? t0 + tile_bytes : len;
+        if (threadIdx.x == 0) {   // one thread decides, so that the whole CTA leaves the loop together
+            const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(best);
+            *s_stop = (cur != NO_START && (unsigned long long)t0 + 2 > cur) ? 1 : 0;   // everything from here on lies behind the winner
+            *s_qn = 0;
+        }
+        __syncthreads();
+        if (*s_stop) break;
+        bool armed = false;
+        // stage one extra 16-byte block so that the second-byte test of the tile's last candidate stays in shared memory
+        const int64_t t1s = t1 + 16 < len ? t1 + 16 : len;
+        const int64_t base = stage_tile(buf, t0, t1s, len, tile, mbar, armed);
+        if (armed) { mbar_wait(mbar, phase); phase ^= 1; }
+        __syncthreads();
+        const FetchTile fetch{tile_addr, base, t1s, buf};
+        const int nunits = (int)((t1 - base + 15) >> 4);
+        for (int u = threadIdx.x; u < nunits; u += blockDim.x) {
+            const uint32_t ua = tile_addr + ((uint32_t)u << 4);
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ua));
+            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+            const int64_t pos0 = base + ((int64_t)u << 4);
+            uint32_t hits = 0;   // first-byte filter: one shared-memory byte per candidate, no dependent chain
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < 4; q++) {
 #pragma unroll
-            for (int r = 0; r < 4; r++) hits |= lds_u8(first_addr + ((wv[q] >> (8 * r)) & 0xFF)) << (q * 4 + r);
+                for (int r = 0; r < 4; r++) hits |= lds_u8(first_addr + ((wv[q] >> (8 * r)) & 0xFF)) << (q * 4 + r);
+            }
+            // bytes of the unit outside [t0, t1) belong to the neighbouring tiles (or to nobody)
+            if (pos0 < t0) hits &= 0xFFFFu << (int)(t0 - pos0);
+            if (pos0 + 16 > t1) hits &= 0xFFFFu >> (int)(pos0 + 16 - t1);
+            while (hits) {
+                const int k = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const int64_t pos = pos0 + k;
+                const uint32_t b = (wv[k >> 2] >> (8 * (k & 3))) & 0xFF;
+                // second-byte filter: drop the start if two bytes already prove it dead.  Not decidable (keep) when
+                // the first step accepts or enters a multi-byte sequence (a broken sequence replays as U+FFFF).
+                const uint32_t w1 = T.next(q0, b);
+                if (!(w1 & (W_ACC | W_INTER))) {
+                    const uint32_t b1 = pos + 1 < len ? fetch(pos + 1) : 0u;   // the trailing NUL sentinel follows the text
+                    if ((T.next(w1 & W_STATE, b1) & W_STATE) == 0 && !(T.next(w1 & W_STATE, b1) & W_ACC)) continue;
+                }
+                const int slot = atomicAdd(s_qn, 1);
+                if (slot < SCAN_QUEUE) s_queue[slot] = (int32_t)(pos - base);
+                else if (try_start(p, T, fetch, buf, len, pos, b)) atomicMin(best, (unsigned long long)pos + 2);
+            }
         }
-        while (hits) {
-            const int k = __ffs(hits) - 1;
-            hits &= hits - 1;
-            const uint32_t b = (wv[k >> 2] >> (8 * (k & 3))) & 0xFF;
-            if (try_start(p, T, buf, len, pos0 + k, b)) { atomicMin(best, (unsigned long long)(pos0 + k) + 2); break; }
+        __syncthreads();
+        const int qn = *s_qn < SCAN_QUEUE ? *s_qn : SCAN_QUEUE;
+        for (int i = threadIdx.x; i < qn; i += blockDim.x) {
+            const int64_t pos = base + s_queue[i];
+            if (try_start(p, T, fetch, buf, len, pos, fetch(pos))) atomicMin(best, (unsigned long long)pos + 2);
         }
-    }
-    // tail: the last (len - head) % 16 bytes, by the last block's thread 0
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
-        for (int64_t pos = head + (nvec << 4); pos < len; pos++) {
-            const uint32_t b = fetch(pos);
-            if (lds_u8(first_addr + b) && try_start(p, T, buf, len, pos, b)) { atomicMin(best, (unsigned long long)pos + 2); break; }
-        }
+        __syncthreads();   // tile and queue are reused
     }
 }
 

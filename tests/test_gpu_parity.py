@@ -253,3 +253,22 @@ def test_invalid_pattern_and_wrong_op_errors():
     with pytest.raises(fx.ForgexError):
         q.match_batch(np.zeros(4, np.uint8), np.array([0, 4], np.int64))
     assert fx.op_in(b"(a", b"a") is False and fx.op_match(b"a)", b"a") is False
+
+
+def test_streaming_form_matches_tile_form(monkeypatch):
+    """K2s (streaming windows) and K2 (TMA tiles) are two forms of the same ragged boolean kernel"""
+    rng = np.random.default_rng(3)
+    strings = [b"", b"", b" ", b"foobar", b"x" * 3000 + b"foobaz", b"", b"fooba", b"\xc1\xa6oobar fooba!"]
+    strings += [bytes(rng.integers(0x20, 0x7F, size=int(k), dtype=np.uint8)) for k in rng.integers(0, 300, size=3000)]
+    strings += [b"foobaz", b"", b""]
+    buf, off = pack(strings)
+    buf2, off2 = synth.gen_c2(40000)
+    for window in ("64", "1024", "100000"):
+        monkeypatch.setenv("FX_RAGGED_FORM", "1")
+        monkeypatch.setenv("FX_WINDOW", window)
+        for pat, op in [(b"foo(bar|baz)", "in"), (rb"\d{3}-\d{4}", "match"), (b"[a-z]+", "in"), (b"a*", "in"), (b"x*y+", "match")]:
+            p = fx.Pattern(pat, op)
+            for b_, o_ in ((buf, off), (buf2, off2)):
+                got = p.in_batch(b_, o_) if op == "in" else p.match_batch(b_, o_)
+                exp = oracle_bool(pat, op, b_, offsets=o_)
+                assert np.array_equal(got, exp), (window, pat, op, np.nonzero(got != exp)[0][:10])
