@@ -19,7 +19,7 @@ SYMBOLS = [
     "fx_status_message", "fx_compile", "fx_pattern_free", "fx_pattern_get_info", "fx_pattern_set_residency",
     "fx_pattern_literals", "fx_pattern_tables", "fx_is_valid_regex",
     "fx_match_fixed_dev", "fx_in_fixed_dev", "fx_match_batch_dev", "fx_in_batch_dev", "fx_regex_batch_dev",
-    "fx_regex_buffer_work_bytes", "fx_regex_buffer_dev",
+    "fx_regex_buffer_work_bytes", "fx_regex_buffer_dev", "fx_buffer_scan_dev", "fx_buffer_finish_dev",
     "fx_match_fixed", "fx_in_fixed", "fx_match_batch", "fx_in_batch", "fx_regex_batch", "fx_regex_buffer",
     "fx_in", "fx_match", "fx_regex", "fx_launch_count",
 ]
@@ -62,6 +62,8 @@ def lib():
     L.fx_regex_buffer_work_bytes.restype = i64
     L.fx_regex_buffer_work_bytes.argtypes = [i64]
     L.fx_regex_buffer_dev.argtypes = [vp, u8p, i64, vp, vp, vp]
+    L.fx_buffer_scan_dev.argtypes = [vp, u8p, i64, i64, i64, i64, C.c_int, C.c_int, vp, vp]
+    L.fx_buffer_finish_dev.argtypes = [vp, u8p, i64, i64, C.c_int, vp, vp, vp]
     for name in ("fx_match_fixed", "fx_in_fixed"):
         getattr(L, name).argtypes = [vp, u8p, i64, i64, u8p]
     for name in ("fx_match_batch", "fx_in_batch"):

@@ -138,7 +138,7 @@ int ensure_device(fx_pattern* p) {
         CUDA_TRY(cudaMalloc(&d.a_flags, at.flags.size() + 16));
         CUDA_TRY(cudaMemcpy(d.a_flags, at.flags.data(), at.flags.size(), cudaMemcpyHostToDevice));
     }
-    CUDA_TRY(cudaMalloc(&d.w_best, 8));
+    CUDA_TRY(cudaMalloc(&d.w_best, 16));
     CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
     d.device = dev;
     return FX_OK;
@@ -386,27 +386,46 @@ int launch_regex_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, i
 }
 
 template <int KIND>
-int launch_buffer_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, int64_t len, int64_t* from_to,
-                    unsigned long long* best, cudaStream_t s) {
-    CUDA_TRY(cudaMemsetAsync(best, 0xFF, 8, s));
-    bool trivial = pl.kp.all_active || len <= 1;
-    if (!trivial) {
-        auto kern = k_buffer_scan<KIND>;
-        int table_smem = (int)staged_bytes(pl);
-        int tile_bytes = env_int("FX_SCAN_TILE_BYTES", 32 * 1024);
-        size_t smem = (size_t)scan_tile_offset(table_smem) + (size_t)tile_bytes + 64;
-        int bps = 0;
-        int rc = occupancy_grid(kern, 256, smem, p->dev.sm_count, bps);
-        if (rc) return rc;
-        long long ntiles = (len + tile_bytes - 1) / tile_bytes;
-        long long cap = (long long)p->dev.sm_count * bps;
-        int grid = (int)(ntiles < cap ? ntiles : cap);
-        if (grid < 1) grid = 1;
-        kern<<<grid, 256, smem, s>>>(pl.kp, buf, len, best, tile_bytes, ntiles, table_smem);
-        g_launches++;
-        CUDA_TRY(cudaGetLastError());
-    }
-    k_buffer_finish<<<1, 1, 0, s>>>(pl.kp, buf, len, best, from_to);
+int launch_scan_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const ScanWindow& W, unsigned long long* best,
+                  cudaStream_t s) {
+    auto kern = k_buffer_scan<KIND>;
+    int table_smem = (int)staged_bytes(pl);
+    size_t smem = (size_t)scan_smem_bytes(table_smem);
+    int bps = 0;
+    int rc = occupancy_grid(kern, 256, smem, p->dev.sm_count, bps);
+    if (rc) return rc;
+    long long units = ((W.start_hi - W.start_lo) >> 4) + 1;
+    long long want = (units + 255) / 256;
+    long long cap = (long long)p->dev.sm_count * bps;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    kern<<<grid, 256, smem, s>>>(pl.kp, buf, W, best, table_smem);
+    g_launches++;
+    return cuda_status(cudaGetLastError());
+}
+
+// scan starts [start_lo, start_hi) of a window; d_best[0] (min key) and d_best[1] (undecided attempts) must have been
+// initialised by the caller
+int launch_scan(fx_pattern* p, const uint8_t* buf, const ScanWindow& W, unsigned long long* best, cudaStream_t s) {
+    if (W.len < 0 || W.start_lo < 0 || W.start_hi > W.len || W.start_lo > W.start_hi) return FX_ERR_BAD_ARGUMENT;
+    // the parallel start sweep tries every character boundary; a pattern whose extracted prefix restricts
+    // the candidate starts (api_internal_m.F90:76-104) is not handled on this path yet (DESIGN.md)
+    if (p->prog.prefix_active && !p->prog.literal_only) return FX_ERR_PREFILTER_UNSUPPORTED;
+    Plan pl;
+    int rc = make_plan(p, pl);
+    if (rc) return rc;
+    if (pl.kp.all_active || W.start_lo == W.start_hi) return FX_OK;
+    if (pl.kind == 1) return launch_scan_t<1>(p, pl, buf, W, best, s);
+    if (pl.kind == 2) return launch_scan_t<2>(p, pl, buf, W, best, s);
+    return launch_scan_t<3>(p, pl, buf, W, best, s);
+}
+
+int launch_finish(fx_pattern* p, const uint8_t* buf, const ScanWindow& W, const unsigned long long* best,
+                  int64_t* from_to, int whole_text, cudaStream_t s) {
+    Plan pl;
+    int rc = make_plan(p, pl);
+    if (rc) return rc;
+    k_buffer_finish<<<1, 1, 0, s>>>(pl.kp, buf, W, best, from_to, whole_text);
     g_launches++;
     return cuda_status(cudaGetLastError());
 }
@@ -414,15 +433,16 @@ int launch_buffer_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, int64_t l
 int launch_buffer(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* from_to, unsigned long long* best,
                   cudaStream_t s) {
     if (len < 0) return FX_ERR_BAD_ARGUMENT;
-    // the parallel start sweep tries every character boundary; a pattern whose extracted prefix restricts
-    // the candidate starts (api_internal_m.F90:76-104) is not handled on this path yet (DESIGN.md)
-    if (p->prog.prefix_active && !p->prog.literal_only) return FX_ERR_PREFILTER_UNSUPPORTED;
-    Plan pl;
-    int rc = make_plan(p, pl);
-    if (rc) return rc;
-    if (pl.kind == 1) return launch_buffer_t<1>(p, pl, buf, len, from_to, best, s);
-    if (pl.kind == 2) return launch_buffer_t<2>(p, pl, buf, len, from_to, best, s);
-    return launch_buffer_t<3>(p, pl, buf, len, from_to, best, s);
+    CUDA_TRY(cudaMemsetAsync(best, 0xFF, 8, s));
+    CUDA_TRY(cudaMemsetAsync(best + 1, 0, 8, s));
+    ScanWindow W{len, 0, len, 0, 1, 1};
+    if (len > 1) {
+        int rc = launch_scan(p, buf, W, best, s);
+        if (rc) return rc;
+    } else if (p->prog.prefix_active && !p->prog.literal_only) {
+        return FX_ERR_PREFILTER_UNSUPPORTED;
+    }
+    return launch_finish(p, buf, W, best, from_to, 1, s);
 }
 
 template <typename T>
@@ -576,6 +596,23 @@ int fx_regex_buffer_dev(fx_pattern* p, const uint8_t* d_buf, int64_t len, int64_
     if (rc) return rc;
     if (!d_work) return FX_ERR_BAD_ARGUMENT;
     return launch_buffer(p, d_buf, len, d_from_to, static_cast<unsigned long long*>(d_work), (cudaStream_t)stream);
+}
+
+int fx_buffer_scan_dev(fx_pattern* p, const uint8_t* d_window, int64_t window_len, int64_t start_lo, int64_t start_hi,
+                       int64_t origin, int is_first, int is_last, uint64_t* d_best, void* stream) {
+    int rc = check_ready(p, FX_OP_REGEX);
+    if (rc) return rc;
+    if (!d_best) return FX_ERR_BAD_ARGUMENT;
+    ScanWindow W{window_len, start_lo, start_hi, origin, is_first ? 1 : 0, is_last ? 1 : 0};
+    return launch_scan(p, d_window, W, reinterpret_cast<unsigned long long*>(d_best), (cudaStream_t)stream);
+}
+int fx_buffer_finish_dev(fx_pattern* p, const uint8_t* d_window, int64_t window_len, int64_t origin, int is_last,
+                         const uint64_t* d_key, int64_t* d_from_to, void* stream) {
+    int rc = check_ready(p, FX_OP_REGEX);
+    if (rc) return rc;
+    if (!d_key || !d_from_to) return FX_ERR_BAD_ARGUMENT;
+    ScanWindow W{window_len, 0, window_len, origin, origin == 0 ? 1 : 0, is_last ? 1 : 0};
+    return launch_finish(p, d_window, W, reinterpret_cast<const unsigned long long*>(d_key), d_from_to, 0, (cudaStream_t)stream);
 }
 
 // ---- host-pointer entry points ----------------------------------------------------------------

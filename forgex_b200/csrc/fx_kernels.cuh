@@ -254,6 +254,57 @@ __device__ inline int64_t index_back(FETCH fetch, int64_t len, const uint8_t* li
     return 0;
 }
 
+// Brute-force search (api_internal_m.F90:108-155): starts = the leading NUL, then every character boundary of the
+// text, in order; the first start whose anchored run accepts after >= 1 symbol wins, with its last accept as the end.
+// Written as ONE flat loop -- each iteration is a single byte step of the attempt in flight -- so that the lanes of a
+// warp, which are all at different starts of different strings, still execute the same instructions.
+template <class TBL, class FETCH>
+__device__ __forceinline__ void brute_force_flat(const Anchored& A, const TBL& T, FETCH fetch, int64_t len,
+                                                 int64_t& from, int64_t& to) {
+    from = 0; to = 0;
+    int64_t cur = -1;          // text index of the attempt's start; -1 = the leading NUL sentinel (S position 1)
+    int64_t j = 0, seq = 0, last = -1;
+    uint32_t w = (uint32_t)A.start_nul;
+    bool inter = false;
+    if (A.start_nul != 0) {
+        last = (__ldg(A.flags + A.start_nul) & SF_ACC) ? 0 : -1;
+    } else {
+        if (len == 0) return;
+        cur = 0;
+        w = (uint32_t)A.q0;
+    }
+    while (true) {
+        const uint32_t b = j < len ? fetch(j) : 0u;     // virtual trailing NUL at j == len
+        if (inter && (b & 0xC0) != 0x80) {              // sequence broken: pending bytes replay as U+FFFF
+            const uint32_t f = __ldg(A.flags + (w & W_STATE));
+            const int pending = (int)(j - seq);
+            for (int k = 1; k <= pending; k++)
+                if (f & (SF_FAILACC1 << (k - 1))) last = seq + k;
+            inter = false;
+        }
+        const uint32_t nw = T.next(w & W_STATE, b);
+        if ((nw & W_INTER) && !inter) seq = j;
+        inter = (nw & W_INTER) != 0;
+        w = nw;
+        j++;
+        if (w & W_ACC) last = j;
+        if ((w & W_STATE) == 0 || j > len) {            // this attempt is over
+            if (last >= 0) {
+                const int64_t e = last < len ? last : len;
+                if (cur < 0) { if (e > 0) { from = 1; to = e; } }   // the NUL start wins even with an empty span
+                else { from = cur + 1; to = e; }
+                return;
+            }
+            cur = cur < 0 ? 0 : cur + char_len(fetch, len, cur);
+            if (cur >= len) return;
+            w = (uint32_t)A.q0;
+            j = cur;
+            last = -1;
+            inter = false;
+        }
+    }
+}
+
 // do_matching_including for a non-blank text (api_internal_m.F90:76-164): candidate starts are either
 // every character boundary (no usable prefix) or the non-overlapping occurrences of the extracted
 // prefix in S (utility_m.f90:58-117), cut short by the last occurrence of the extracted suffix.
@@ -281,17 +332,7 @@ __device__ inline void including_exact(const Anchored& A, const TBL& T, FETCH fe
         }
         if (first == NONE) brute = true;
     }
-    if (brute) {
-        int64_t last = attempt_at(A, T, fetch, len, 1);
-        if (last >= 0) { from = 1; to = last < len ? last : len; return; }
-        int64_t pos = 0;
-        while (pos < len) {
-            last = run_attempt(A, T, fetch, len, (uint32_t)A.q0, pos, -1);
-            if (last >= 0) { from = pos + 1; to = last < len ? last : len; return; }
-            pos += char_len(fetch, len, pos);
-        }
-        return;
-    }
+    if (brute) { brute_force_flat(A, T, fetch, len, from, to); return; }
     bool at_zero = first == 2;                 // "i = 0": try the leading NUL before the first occurrence
     int64_t start = at_zero ? 1 : first;
     int64_t text_suf = NONE;
@@ -764,141 +805,227 @@ __device__ inline bool continuation_is_boundary(const uint8_t* __restrict__ s, i
     return true;                                     // three continuation bytes in front: pos cannot be covered
 }
 
-// text access for attempts launched from a staged tile: shared memory inside the tile, global memory beyond it
-struct FetchTile {
-    uint32_t saddr;          // shared address of buffer position `tbase`
-    int64_t tbase, tend;     // staged range
-    const uint8_t* g;
-    __device__ __forceinline__ uint32_t operator()(int64_t i) const {
-        return (i >= tbase && i < tend) ? lds_u8(saddr + (uint32_t)(i - tbase)) : __ldg(g + i);
-    }
-};
-
-// candidate at text index pos whose first byte b survives the first transition: run it (out of line)
+// One candidate start (text index pos, first byte b): boundary check, then the anchored attempt, reading the text
+// from global memory.  `open_end`: the window is followed by more text that this GPU does not hold; an attempt
+// that is still alive at the window end cannot be decided here and is reported through *overflow.
 template <int KIND>
-__device__ __noinline__ bool try_start(const KParams& p, const Table<KIND>& T, const FetchTile& fetch,
-                                       const uint8_t* __restrict__ buf, int64_t len, int64_t pos, uint32_t b) {
+__device__ __forceinline__ bool try_start(const KParams& p, const Table<KIND>& T, const uint8_t* __restrict__ buf,
+                                          int64_t len, int64_t pos, uint32_t b, bool open_end,
+                                          unsigned long long* overflow) {
     if ((b & 0xC0) == 0x80 && !continuation_is_boundary(buf, len, pos)) return false;
     const Anchored A{p.flags, p.start_nul, p.q0};
-    return run_attempt(A, T, fetch, len, (uint32_t)p.q0, pos, -1) >= 0;
+    if (!open_end) return run_attempt(A, T, FetchGlobal{buf}, len, (uint32_t)p.q0, pos, -1) >= 0;
+    // open end: walk only the bytes we have; alive at the end -> undecided
+    uint32_t w = (uint32_t)p.q0;
+    int64_t seq = 0, last = -1;
+    bool inter = false;
+    for (int64_t j = pos; j < len; j++) {
+        const uint32_t c = __ldg(buf + j);
+        if (inter && (c & 0xC0) != 0x80) {
+            const uint32_t f = __ldg(A.flags + (w & W_STATE));
+            for (int k = 1; k <= (int)(j - seq); k++) if (f & (SF_FAILACC1 << (k - 1))) last = seq + k;
+            inter = false;
+        }
+        const uint32_t nw = T.next(w & W_STATE, c);
+        if ((nw & W_INTER) && !inter) seq = j;
+        inter = (nw & W_INTER) != 0;
+        w = nw;
+        if (w & W_ACC) last = j + 1;
+        if ((w & W_STATE) == 0) return last >= 0;
+    }
+    if (last >= 0) return true;        // already a counted accept: this start wins whatever follows
+    atomicAdd(overflow, 1ull);
+    return false;
 }
 
-// shared-memory layout of K4: classmap 256 | table | first-byte filter 256 | mbarrier + flags 16 |
-//                             candidate queue (SCAN_QUEUE x int32) | pad to 128 | tile
-static constexpr int SCAN_QUEUE = 2048;
-__host__ __device__ __forceinline__ int scan_tile_offset(int table_smem_bytes) {
-    return (256 + table_smem_bytes + 256 + 16 + SCAN_QUEUE * 4 + 127) & ~127;
+// K4 window description: the kernel scans starts [start_lo, start_hi) of a window of `len` bytes that is a piece of
+// a longer text; `origin` = text position of window byte 0 (keys written to `best` are global S positions).
+struct ScanWindow {
+    int64_t len, start_lo, start_hi, origin;
+    int first;   // window begins at the true start of the text (the leading-NUL start belongs to it)
+    int last;    // window ends at the true end of the text (the trailing NUL follows it)
+};
+
+// shared-memory layout of K4: classmap 256 | table | first-byte filter 256 | per-warp queues 8 x 64 x int64
+__host__ __device__ __forceinline__ int scan_smem_bytes(int table_smem_bytes) {
+    return 256 + table_smem_bytes + 256 + 8 * 64 * 8;
 }
 
-// Two phases per tile.  Filter: every thread looks at 16 consecutive candidate starts out of one conflict-free
-// 16-byte shared-memory load; a candidate survives if its first byte leaves q0 alive and its second byte does
-// not kill it right away (or if that cannot be decided from two bytes); survivors go to a small queue.
-// Attempts: the queued starts are handed out one per thread, so the (few, long) attempts run side by side
-// instead of one lane at a time inside the filter loop.
+// Filter + attempts in one sweep, organised per warp.  A warp takes 32 consecutive 16-byte units with one
+// coalesced load (each lane = 16 candidate starts).  First-byte filter: one shared-memory byte per candidate.
+// Second-byte filter: drop a start when two bytes already prove it dead.  Survivors are compacted into a
+// warp-private queue; whenever 32 are waiting, the 32 lanes run 32 attempts side by side (reading the text
+// through L1/L2), so the rare long attempts never leave 31 lanes idle.
 template <int KIND>
-__global__ void __launch_bounds__(256) k_buffer_scan(KParams p, const uint8_t* __restrict__ buf, int64_t len,
-                                                     unsigned long long* __restrict__ best, int tile_bytes,
-                                                     int64_t ntiles, int table_smem_bytes) {
+__global__ void __launch_bounds__(256) k_buffer_scan(KParams p, const uint8_t* __restrict__ buf, ScanWindow W,
+                                                     unsigned long long* __restrict__ best, int table_smem_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_cmap = smem;
     uint8_t* s_table = smem + 256;
     uint8_t* s_first = smem + 256 + table_smem_bytes;   // does byte b survive the step out of q0?
-    const uint32_t mbar = smem_u32(smem + 256 + table_smem_bytes + 256);
-    volatile int* s_stop = reinterpret_cast<volatile int*>(smem + 256 + table_smem_bytes + 256 + 8);
-    int* s_qn = reinterpret_cast<int*>(smem + 256 + table_smem_bytes + 256 + 12);
-    int32_t* s_queue = reinterpret_cast<int32_t*>(smem + 256 + table_smem_bytes + 256 + 16);
-    uint8_t* tile = smem + scan_tile_offset(table_smem_bytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t* queue = reinterpret_cast<int64_t*>(smem + 256 + table_smem_bytes + 256) + warp * 64;
     Table<KIND> T = stage_table<KIND>(p, s_table, s_cmap);
-    if (threadIdx.x == 0) mbar_init(mbar, 1);
     __syncthreads();
     const uint32_t q0 = (uint32_t)p.q0;
     for (int b = threadIdx.x; b < 256; b += blockDim.x) s_first[b] = (T.next(q0, (uint32_t)b) & W_STATE) != 0;
     __syncthreads();
     const uint32_t first_addr = smem_u32(s_first);
-    const uint32_t tile_addr = smem_u32(tile);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {          // start 1 = the leading NUL sentinel
+    const int64_t len = W.len;
+    const bool open_end = !W.last;
+    unsigned long long* overflow = best + 1;
+    const uint32_t FULL = 0xffffffffu;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && W.first) {   // start 1 = the leading NUL sentinel
         const Anchored A{p.flags, p.start_nul, p.q0};
         if (attempt_at(A, T, FetchGlobal{buf}, len, 1) >= 0) atomicMin(best, 1ull);
     }
-    uint32_t phase = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int64_t t0 = t * tile_bytes;
-        const int64_t t1 = t0 + tile_bytes < len ? t0 + tile_bytes : len;
-        if (threadIdx.x == 0) {   // one thread decides, so that the whole CTA leaves the loop together
-            const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(best);
-            *s_stop = (cur != NO_START && (unsigned long long)t0 + 2 > cur) ? 1 : 0;   // everything from here on lies behind the winner
-            *s_qn = 0;
+    // 16-byte units aligned to the buffer ADDRESS; the unaligned head and the tail go through the same filter
+    // one byte at a time (warp 0 of block 0 / last block)
+    const uintptr_t g = reinterpret_cast<uintptr_t>(buf) + (uintptr_t)W.start_lo;
+    int64_t head = W.start_lo + (int64_t)((16 - (g & 15)) & 15);
+    if (head > W.start_hi) head = W.start_hi;
+    const int64_t nvec = (W.start_hi - head) >> 4;
+    const int64_t tail = head + (nvec << 4);
+    int qn = 0;   // warp-uniform queue fill
+
+    auto run_batch = [&](int count) {
+        __syncwarp();
+        if (lane < count) {
+            const int64_t pos = queue[lane];
+            if (try_start(p, T, buf, len, pos, __ldg(buf + pos), open_end, overflow))
+                atomicMin(best, (unsigned long long)(W.origin + pos) + 2);
         }
-        __syncthreads();
-        if (*s_stop) break;
-        bool armed = false;
-        // stage one extra 16-byte block so that the second-byte test of the tile's last candidate stays in shared memory
-        const int64_t t1s = t1 + 16 < len ? t1 + 16 : len;
-        const int64_t base = stage_tile(buf, t0, t1s, len, tile, mbar, armed);
-        if (armed) { mbar_wait(mbar, phase); phase ^= 1; }
-        __syncthreads();
-        const FetchTile fetch{tile_addr, base, t1s, buf};
-        const int nunits = (int)((t1 - base + 15) >> 4);
-        for (int u = threadIdx.x; u < nunits; u += blockDim.x) {
-            const uint32_t ua = tile_addr + ((uint32_t)u << 4);
-            uint4 v;
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ua));
-            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-            const int64_t pos0 = base + ((int64_t)u << 4);
-            uint32_t hits = 0;   // first-byte filter: one shared-memory byte per candidate, no dependent chain
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-#pragma unroll
-                for (int r = 0; r < 4; r++) hits |= lds_u8(first_addr + ((wv[q] >> (8 * r)) & 0xFF)) << (q * 4 + r);
+        __syncwarp();
+    };
+    auto push = [&](bool survive, int64_t pos) {
+        const uint32_t m = __ballot_sync(FULL, survive);
+        if (survive) queue[qn + __popc(m & ((1u << lane) - 1))] = pos;
+        qn += __popc(m);
+        if (qn >= 32) {
+            run_batch(32);
+            if (lane < qn - 32) { const int64_t v = queue[32 + lane]; queue[lane] = v; }
+            qn -= 32;
+            __syncwarp();
+        }
+    };
+    auto second_byte_ok = [&](uint32_t b, uint32_t b1) -> bool {
+        // keep the start unless two bytes prove it dead; undecidable (keep) when the first step accepts or enters a
+        // multi-byte sequence (a broken sequence replays as U+FFFF and may accept on the way)
+        const uint32_t w1 = T.next(q0, b);
+        if (w1 & (W_ACC | W_INTER)) return true;
+        const uint32_t w2 = T.next(w1 & W_STATE, b1);
+        return (w2 & (W_STATE | W_ACC)) != 0;
+    };
+
+    const int64_t gwarp = (int64_t)blockIdx.x * 8 + warp, nwarps = (int64_t)gridDim.x * 8;
+    if (gwarp == 0) {   // head and tail bytes, 32 at a time
+        for (int64_t base = W.start_lo; base < head; base += 32) {
+            const int64_t pos = base + lane;
+            bool sv = false;
+            if (pos < head) {
+                const uint32_t b = __ldg(buf + pos);
+                const uint32_t b1 = pos + 1 < len ? __ldg(buf + pos + 1) : 0u;
+                sv = lds_u8(first_addr + b) && (pos + 1 < len || !open_end ? second_byte_ok(b, b1) : true);
             }
-            // bytes of the unit outside [t0, t1) belong to the neighbouring tiles (or to nobody)
-            if (pos0 < t0) hits &= 0xFFFFu << (int)(t0 - pos0);
-            if (pos0 + 16 > t1) hits &= 0xFFFFu >> (int)(pos0 + 16 - t1);
-            while (hits) {
+            push(sv, pos);
+        }
+        for (int64_t base = tail; base < W.start_hi; base += 32) {
+            const int64_t pos = base + lane;
+            bool sv = false;
+            if (pos < W.start_hi) {
+                const uint32_t b = __ldg(buf + pos);
+                const uint32_t b1 = pos + 1 < len ? __ldg(buf + pos + 1) : 0u;
+                sv = lds_u8(first_addr + b) && (pos + 1 < len || !open_end ? second_byte_ok(b, b1) : true);
+            }
+            push(sv, pos);
+        }
+    }
+    for (int64_t u0 = gwarp * 32; u0 < nvec; u0 += nwarps * 32) {
+        unsigned long long cur = 0;
+        if (lane == 0) cur = *reinterpret_cast<volatile unsigned long long*>(best);
+        cur = __shfl_sync(FULL, cur, 0);
+        if (cur != NO_START && (unsigned long long)(W.origin + head + (u0 << 4)) + 2 > cur) break;   // behind the winner
+        const int64_t u = u0 + lane;
+        const bool valid = u < nvec;
+        const int64_t pos0 = head + (u << 4);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (valid) v = ldg_nc_v4(buf + pos0);
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+        uint32_t hits = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+#pragma unroll
+            for (int r = 0; r < 4; r++) hits |= lds_u8(first_addr + ((wv[q] >> (8 * r)) & 0xFF)) << (q * 4 + r);
+        }
+        if (!valid) hits = 0;
+        // byte that follows this unit: the next lane's first byte, or a load for the last lane / last unit
+        uint32_t follow = __shfl_down_sync(FULL, v.x & 0xFF, 1);
+        const bool has_follow = pos0 + 16 < len;
+        if (valid && (lane == 31 || u + 1 >= nvec)) follow = has_follow ? __ldg(buf + pos0 + 16) : 0u;
+        while (__any_sync(FULL, hits != 0)) {
+            bool sv = false;
+            int64_t pos = 0;
+            if (hits) {
                 const int k = __ffs(hits) - 1;
                 hits &= hits - 1;
-                const int64_t pos = pos0 + k;
+                pos = pos0 + k;
                 const uint32_t b = (wv[k >> 2] >> (8 * (k & 3))) & 0xFF;
-                // second-byte filter: drop the start if two bytes already prove it dead.  Not decidable (keep) when
-                // the first step accepts or enters a multi-byte sequence (a broken sequence replays as U+FFFF).
-                const uint32_t w1 = T.next(q0, b);
-                if (!(w1 & (W_ACC | W_INTER))) {
-                    const uint32_t b1 = pos + 1 < len ? fetch(pos + 1) : 0u;   // the trailing NUL sentinel follows the text
-                    if ((T.next(w1 & W_STATE, b1) & W_STATE) == 0 && !(T.next(w1 & W_STATE, b1) & W_ACC)) continue;
-                }
-                const int slot = atomicAdd(s_qn, 1);
-                if (slot < SCAN_QUEUE) s_queue[slot] = (int32_t)(pos - base);
-                else if (try_start(p, T, fetch, buf, len, pos, b)) atomicMin(best, (unsigned long long)pos + 2);
+                const uint32_t b1 = k < 15 ? (wv[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xFF : follow;
+                const bool know_b1 = k < 15 || has_follow || !open_end;   // at an open window end the next byte is unknown
+                sv = know_b1 ? second_byte_ok(b, b1) : true;
             }
+            push(sv, pos);
         }
-        __syncthreads();
-        const int qn = *s_qn < SCAN_QUEUE ? *s_qn : SCAN_QUEUE;
-        for (int i = threadIdx.x; i < qn; i += blockDim.x) {
-            const int64_t pos = base + s_queue[i];
-            if (try_start(p, T, fetch, buf, len, pos, fetch(pos))) atomicMin(best, (unsigned long long)pos + 2);
-        }
-        __syncthreads();   // tile and queue are reused
     }
+    if (qn > 0) run_batch(qn);
 }
 
-// second step: longest end for the winning start; also the literal / degenerate cases
-__global__ void k_buffer_finish(KParams p, const uint8_t* __restrict__ buf, int64_t len,
-                                const unsigned long long* __restrict__ best, int64_t* __restrict__ from_to) {
+// second step: longest end for the winning start; also the literal / degenerate cases.  `key` is the winning
+// start as an S position of the whole text; the window must hold the text from that start to the end of its match.
+__global__ void k_buffer_finish(KParams p, const uint8_t* __restrict__ buf, ScanWindow W,
+                                const unsigned long long* __restrict__ best, int64_t* __restrict__ from_to, int whole_text) {
     Table<3> T;
     T.g_table = p.ctable; T.g_cmap = p.classmap; T.shift = p.c_row_shift; T.s_table = 0; T.s_cmap = 0;
     FetchGlobal fetch{buf};
+    const int64_t len = W.len;
     int64_t from = 0, to = 0;
-    if (p.all_active || len == 0 || (len == 1 && fetch(0) == 0x20)) {
+    if (whole_text && (p.all_active || len == 0 || (len == 1 && fetch(0) == 0x20))) {
         eval_regex(p, T, fetch, len, from, to);
     } else {
         const unsigned long long key = *best;
         const Anchored A{p.flags, p.start_nul, p.q0};
         if (key != NO_START) {
-            const int64_t start = (int64_t)key;
-            const int64_t last = attempt_at(A, T, fetch, len, start);
-            const int64_t f = start - 1 < 1 ? 1 : start - 1;
-            const int64_t t = last < len ? last : len;
-            if (f > 0 && t > 0) { from = f; to = t; }
+            const int64_t start = (int64_t)key - W.origin;      // S position relative to this window
+            if (W.last) {
+                const int64_t last = attempt_at(A, T, fetch, len, start);
+                const int64_t f = start - 1 < 1 ? 1 : start - 1;
+                const int64_t t = last < len ? last : len;
+                if (f > 0 && t > 0) { from = W.origin + f; to = W.origin + t; }
+            } else {
+                // open window: walk the bytes we have; still alive at the window end -> the end is not known here
+                uint32_t w = start == 1 ? (uint32_t)A.start_nul : (uint32_t)A.q0;
+                int64_t seq = 0, last = (start == 1 && (__ldg(A.flags + A.start_nul) & SF_ACC)) ? 0 : -1;
+                bool inter = false, alive = (w & W_STATE) != 0;
+                for (int64_t j = start == 1 ? 0 : start - 2; alive && j < len; j++) {
+                    const uint32_t c = fetch(j);
+                    if (inter && (c & 0xC0) != 0x80) {
+                        const uint32_t fl = __ldg(A.flags + (w & W_STATE));
+                        for (int k = 1; k <= (int)(j - seq); k++) if (fl & (SF_FAILACC1 << (k - 1))) last = seq + k;
+                        inter = false;
+                    }
+                    const uint32_t nw = T.next(w & W_STATE, c);
+                    if ((nw & W_INTER) && !inter) seq = j;
+                    inter = (nw & W_INTER) != 0;
+                    w = nw;
+                    if (w & W_ACC) last = j + 1;
+                    alive = (w & W_STATE) != 0;
+                }
+                if (alive) { from = -1; to = -1; }          // undecided: the caller needs a longer window
+                else {
+                    const int64_t f = start - 1 < 1 ? 1 : start - 1;
+                    if (f > 0 && last > 0) { from = W.origin + f; to = W.origin + last; }
+                }
+            }
         }
     }
     from_to[0] = from;

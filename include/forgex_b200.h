@@ -119,6 +119,20 @@ int fx_regex_batch_dev(fx_pattern* p, const uint8_t* d_buf, const int64_t* d_off
 int64_t fx_regex_buffer_work_bytes(int64_t len);
 int fx_regex_buffer_dev(fx_pattern* p, const uint8_t* d_buf, int64_t len, int64_t* d_from_to, void* d_work, void* stream);
 
+/* Window forms of the buffer search, for a text that is split across GPUs.  A window is a contiguous piece of the
+ * text held by this GPU: window byte 0 is text position `origin` (0-based).  fx_buffer_scan_dev tries the starts
+ * [start_lo, start_hi) of the window (attempts may read on to the end of the window) and lowers d_best[0] to the
+ * smallest winning start, expressed as a 1-based position in NUL||text||NUL of the WHOLE text (so results of several
+ * GPUs combine with a plain MIN); d_best[1] counts attempts that were still alive at an open window end (they could
+ * not be decided: widen the halo).  The caller initialises d_best[0] = ~0, d_best[1] = 0.  is_first / is_last say
+ * whether the window begins / ends where the text does.  Windows that do not begin the text need >= 3 bytes in
+ * front of start_lo (character-boundary look-back).  fx_buffer_finish_dev turns a winning start (*d_key) into the
+ * (from, to) span; it needs a window that holds the whole match, and answers (-1, -1) if the window ends first. */
+int fx_buffer_scan_dev(fx_pattern* p, const uint8_t* d_window, int64_t window_len, int64_t start_lo, int64_t start_hi,
+                       int64_t origin, int is_first, int is_last, uint64_t* d_best, void* stream);
+int fx_buffer_finish_dev(fx_pattern* p, const uint8_t* d_window, int64_t window_len, int64_t origin, int is_last,
+                         const uint64_t* d_key, int64_t* d_from_to, void* stream);
+
 /* ---- host-pointer entry points (copy in, run, copy out, synchronous) ------------------- */
 int fx_match_fixed(fx_pattern* p, const uint8_t* buf, int64_t n, int64_t stride, uint8_t* out);
 int fx_in_fixed(fx_pattern* p, const uint8_t* buf, int64_t n, int64_t stride, uint8_t* out);

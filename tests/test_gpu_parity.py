@@ -272,3 +272,38 @@ def test_streaming_form_matches_tile_form(monkeypatch):
                 got = p.in_batch(b_, o_) if op == "in" else p.match_batch(b_, o_)
                 exp = oracle_bool(pat, op, b_, offsets=o_)
                 assert np.array_equal(got, exp), (window, pat, op, np.nonzero(got != exp)[0][:10])
+
+
+def test_buffer_windows_like_two_gpus():
+    """the window entry points (fx_buffer_scan_dev / fx_buffer_finish_dev) driven the way forgex_b200.dist drives
+    them on 2..4 GPUs, here one slab after the other on one device"""
+    import torch
+    from forgex_b200 import dist as fxd
+    p = fx.Pattern(synth.PATTERNS["c4"], "regex")
+    c = O.Compiled(synth.PATTERNS["c4"], 0)
+    for nbytes, match_at, world in [(200_000, 0.7, 2), (200_000, 0.2, 4), (50_001, None, 3), (300_000, 0.5001, 2)]:
+        text = synth.gen_c4(nbytes, match_at)
+        exp = c.regex_buffer(text)
+        d_text = torch.from_numpy(text).cuda()
+        keys, und = [], 0
+        for rank in range(world):
+            lo, hi = fxd.slab_bounds(nbytes, world, rank)
+            w_lo, w_hi = fxd.window_for_slab(nbytes, lo, hi, 1024)
+            win = d_text[w_lo:w_hi].clone()
+            best = torch.tensor([-1, 0], dtype=torch.int64, device="cuda")
+            p.buffer_scan_dev(win, w_hi - w_lo, lo - w_lo, hi - w_lo, w_lo, w_lo == 0, w_hi == nbytes, best)
+            b = best.cpu().numpy().view(np.uint64)
+            keys.append(int(b[0]))
+            und += int(b[1])
+        assert und == 0
+        key = min(keys)
+        if key == fxd.NO_START:
+            assert exp == (0, 0)
+            continue
+        owner = keys.index(key)
+        lo, hi = fxd.slab_bounds(nbytes, world, owner)
+        w_lo, w_hi = fxd.window_for_slab(nbytes, lo, hi, 1024)
+        win = d_text[w_lo:w_hi].clone()
+        ft = torch.zeros(2, dtype=torch.int64, device="cuda")
+        p.buffer_finish_dev(win, w_hi - w_lo, w_lo, w_hi == nbytes, torch.tensor([key], dtype=torch.int64, device="cuda"), ft)
+        assert tuple(ft.cpu().tolist()) == exp, (nbytes, match_at, world)
