@@ -229,6 +229,13 @@ def _oracle_worker(args):
     return time.perf_counter() - t0, r
 
 
+_REF_SHARDS = None
+
+
+def _ref_step(i):
+    return _oracle_worker(_REF_SHARDS[i])[0]
+
+
 def host_sample(cfg, w, torch, nunits):
     """first nunits units of this rank's device data, on the host"""
     if cfg in ("c2", "c3"):
@@ -286,11 +293,13 @@ def reference_arm(args):
     nunits = sum((len(s[2]) - 1) if s[2] is not None else (len(s[1]) // s[3] if s[3] else 1) for s in shards)
     from tests import oracle_lib as O
     O.build()
+    global _REF_SHARDS
+    _REF_SHARDS = shards          # inherited by the forked workers: a step only ships shard indices and timings
     times = []
     with mp.get_context("fork").Pool(cores) as pool:
         for it in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            pool.map(_oracle_worker, shards)
+            pool.map(_ref_step, range(len(shards)), chunksize=1)
             dt = time.perf_counter() - t0
             if it >= args.warmup:
                 times.append(dt)

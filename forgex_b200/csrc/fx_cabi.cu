@@ -319,6 +319,37 @@ int launch_ragged_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int
 }
 
 template <int OP, int KIND>
+int launch_pairs_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int64_t* off, int64_t n, int64_t total,
+                   uint8_t* out, cudaStream_t s) {
+    auto kern = k_bool_ragged_pairs<OP, KIND>;
+    int table_smem = (int)staged_bytes(pl);
+    int64_t avg = n > 0 ? (total + n - 1) / n : 1;
+    if (avg < 1) avg = 1;
+    int ctas = env_int("FX_CTAS_PER_SM", 4);
+    int64_t per_cta = (227 * 1024) / ctas - 1024;
+    int64_t cap = per_cta - (tile_offset_pairs(table_smem, 256) + 64 + 128);
+    if (cap < 8192) cap = 8192;
+    cap &= ~(int64_t)127;
+    int64_t spt = (cap * 4 / 5) / avg;
+    spt = (spt / 32) * 32;
+    if (spt < 32) spt = 32;
+    if (spt > 256) spt = 256;
+    spt = env_int("FX_TILE_STRINGS", (int)spt);
+    if (spt > 256) spt = 256;
+    size_t smem = (size_t)tile_offset_pairs(table_smem, (int)spt) + (size_t)cap + 64;
+    int64_t ntiles = (n + spt - 1) / spt;
+    int bps = 0;
+    int rc = occupancy_grid(kern, 128, smem, p->dev.sm_count, bps);
+    if (rc) return rc;
+    long long capg = (long long)p->dev.sm_count * bps;
+    int grid = (int)(ntiles < capg ? ntiles : capg);
+    if (grid < 1) grid = 1;
+    kern<<<grid, 128, smem, s>>>(pl.kp, buf, off, n, total, out, (int)spt, (int)cap, ntiles, table_smem);
+    g_launches++;
+    return cuda_status(cudaGetLastError());
+}
+
+template <int OP, int KIND>
 int launch_stream_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int64_t* off, int64_t n, int64_t total,
                     uint8_t* out, cudaStream_t s) {
     auto kern = k_bool_stream<OP, KIND>;
@@ -347,6 +378,11 @@ int launch_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, int64_t
     int rc = make_plan(p, pl);
     if (rc) return rc;
     int generic = generic_mode(pl, OP);
+    if (!generic && env_int("FX_RAGGED_FORM", 0) == 2) {      // length-balanced pairs (K2p)
+        if (pl.kind == 0) return launch_pairs_t<OP, 0>(p, pl, buf, off, n, total, out, s);
+        if (pl.kind == 2) return launch_pairs_t<OP, 2>(p, pl, buf, off, n, total, out, s);
+        return launch_pairs_t<OP, 3>(p, pl, buf, off, n, total, out, s);
+    }
     if (!generic && env_int("FX_RAGGED_FORM", 0) == 1) {      // streaming form (K2s)
         if (pl.kind == 0) return launch_stream_t<OP, 0>(p, pl, buf, off, n, total, out, s);
         if (pl.kind == 2) return launch_stream_t<OP, 2>(p, pl, buf, off, n, total, out, s);

@@ -621,6 +621,109 @@ __global__ void __launch_bounds__(256, 4) k_bool_ragged(KParams p, const uint8_t
 }
 
 // ---------------------------------------------------------------------------------------------
+// K2p: K2 with length-balanced lanes.  A table lookup costs one shared-memory wavefront per warp instruction no
+// matter how many of the 32 lanes are still walking, so in K2 a warp whose strings are 64..256 bytes long wastes
+// a third of its lookups on lanes that have already finished.  Here a CTA of 128 threads takes a tile of up to
+// 256 strings, orders them by length (counting sort over 8-byte buckets, longest first) and gives thread j the
+// j-th longest and the j-th shortest string, one after the other: every lane then walks about the same number
+// of bytes and all warps of the CTA reach the tile barrier together.
+// ---------------------------------------------------------------------------------------------
+// layout: [0,16) mbarrier | classmap 256 | table | offsets (spt+4) x int32 | results spt | perm spt x u16 |
+//         hist 65 x int32 | pad to 128 | tile (cap+64)
+__host__ __device__ __forceinline__ int tile_offset_pairs(int table_smem_bytes, int spt) {
+    return (16 + 256 + table_smem_bytes + (spt + 4) * 4 + spt + spt * 2 + 65 * 4 + 127) & ~127;
+}
+
+template <int OP, int KIND>
+__global__ void __launch_bounds__(128, 8) k_bool_ragged_pairs(KParams p, const uint8_t* __restrict__ buf,
+                                                             const int64_t* __restrict__ offsets, int64_t n,
+                                                             int64_t total, uint8_t* __restrict__ out, int spt, int cap,
+                                                             int64_t ntiles, int table_smem_bytes) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_cmap = smem + 16;
+    uint8_t* s_table = smem + 16 + 256;
+    int32_t* s_off = reinterpret_cast<int32_t*>(smem + 16 + 256 + table_smem_bytes);
+    uint8_t* s_res = reinterpret_cast<uint8_t*>(s_off + spt + 4);
+    uint16_t* s_perm = reinterpret_cast<uint16_t*>(s_res + spt);
+    int32_t* s_hist = reinterpret_cast<int32_t*>(s_perm + spt);
+    uint8_t* tile = smem + tile_offset_pairs(table_smem_bytes, spt);
+    const uint32_t mbar = smem_u32(smem);
+    Table<KIND> T = stage_table<KIND>(p, s_table, s_cmap);
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
+    const uint32_t tile_addr = smem_u32(tile);
+    const int tid = threadIdx.x;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const TileCtx c = load_tile(buf, offsets, n, total, t, spt, cap, tile, s_off, mbar, phase);
+        // ---- order by length: counting sort, 2 strings per thread (spt <= 256) ----
+        if (tid < 65) s_hist[tid] = 0;
+        __syncthreads();
+        int bucket[2], slot[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int i = tid + k * 128;
+            if (i < c.count) {
+                const int32_t r0 = s_off[i], r1 = s_off[i + 1];
+                const int len = r1 == OFF_BEYOND ? 0x7FFFFFF : r1 - r0;
+                int b = 63 - (len >> 3);
+                b = b < 0 ? 0 : b;
+                bucket[k] = b;
+                slot[k] = atomicAdd(&s_hist[b], 1);
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {
+            const int a = s_hist[2 * tid], b2 = s_hist[2 * tid + 1];
+            const int sum = a + b2;
+            int inc = sum;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, d);
+                if (tid >= d) inc += v;
+            }
+            s_hist[2 * tid] = inc - sum;
+            s_hist[2 * tid + 1] = inc - sum + a;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int i = tid + k * 128;
+            if (i < c.count) s_perm[s_hist[bucket[k]] + slot[k]] = (uint16_t)i;
+        }
+        __syncthreads();
+        // ---- thread j: the j-th longest, then the j-th shortest ----
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int j = k == 0 ? tid : c.count - 1 - tid;
+            const bool mine = k == 0 ? (2 * tid < c.count + 0 && tid < c.count && tid <= c.count - 1 - tid)
+                                     : (c.count - 1 - tid > tid);
+            if (!mine) continue;
+            const int i = s_perm[j];
+            const int32_t r0 = s_off[i], r1 = s_off[i + 1];
+            bool r;
+            if (r1 == OFF_BEYOND) {
+                const int64_t o0 = __ldg(offsets + c.first + i), o1 = __ldg(offsets + c.first + i + 1);
+                r = eval_bool_slow<OP>(p, buf + o0, o1 - o0);
+            } else {
+                const int len = r1 - r0;
+                const uint32_t a = tile_addr + (uint32_t)r0;
+                if (degenerate_text<OP>(len, len ? lds_u8(a) : 0)) r = p.q0_accepting != 0;
+                else {
+                    uint32_t high = 0;
+                    r = result_flag(p, walk_smem(T, (uint32_t)p.start, a, len, high));
+                    if (OP == 1 && r && p.prefix_mode == 1 && (high & 0x80808080u))
+                        r = recheck_in_with_prefix(p, buf + (c.base + r0), len);
+                }
+            }
+            s_res[i] = r ? 1 : 0;
+        }
+        __syncthreads();
+        for (int i = tid; i < c.count; i += 128) out[c.first + i] = s_res[i];
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K2s: ragged batch, boolean result, streaming form.
 // The flat buffer is cut into windows of `window` bytes; a thread owns the strings that START inside its
 // window and streams through them in address order (they are contiguous), reading the text straight from

@@ -255,8 +255,9 @@ def test_invalid_pattern_and_wrong_op_errors():
     assert fx.op_in(b"(a", b"a") is False and fx.op_match(b"a)", b"a") is False
 
 
-def test_streaming_form_matches_tile_form(monkeypatch):
-    """K2s (streaming windows) and K2 (TMA tiles) are two forms of the same ragged boolean kernel"""
+@pytest.mark.parametrize("form", ["1", "2"])
+def test_alternative_ragged_forms(monkeypatch, form):
+    """K2s (streaming windows, form 1) and K2p (length-balanced pairs, form 2) against the oracle"""
     rng = np.random.default_rng(3)
     strings = [b"", b"", b" ", b"foobar", b"x" * 3000 + b"foobaz", b"", b"fooba", b"\xc1\xa6oobar fooba!"]
     strings += [bytes(rng.integers(0x20, 0x7F, size=int(k), dtype=np.uint8)) for k in rng.integers(0, 300, size=3000)]
@@ -264,7 +265,7 @@ def test_streaming_form_matches_tile_form(monkeypatch):
     buf, off = pack(strings)
     buf2, off2 = synth.gen_c2(40000)
     for window in ("64", "1024", "100000"):
-        monkeypatch.setenv("FX_RAGGED_FORM", "1")
+        monkeypatch.setenv("FX_RAGGED_FORM", form)
         monkeypatch.setenv("FX_WINDOW", window)
         for pat, op in [(b"foo(bar|baz)", "in"), (rb"\d{3}-\d{4}", "match"), (b"[a-z]+", "in"), (b"a*", "in"), (b"x*y+", "match")]:
             p = fx.Pattern(pat, op)
