@@ -305,6 +305,69 @@ __device__ __forceinline__ void brute_force_flat(const Anchored& A, const TBL& T
     }
 }
 
+// brute_force_flat specialised for a string that sits in shared memory (32-bit indices, no functor): the hot form
+// of K3.  Same semantics, leaner loop.  (Measured on C3: the work per string varies ~3x between the lanes of a warp
+// -- it depends on where, or whether, the string matches -- so a warp averages ~10 busy lanes; claiming strings
+// dynamically per lane and a warp-vote loop were both tried and gave no gain.  See DESIGN.md section 5.)
+template <class TBL>
+__device__ __forceinline__ void brute_force_smem(const Anchored& A, const TBL& T, uint32_t a, int len,
+                                                 int64_t& from, int64_t& to) {
+    from = 0; to = 0;
+    int cur = -1;              // start of the attempt in flight (-1: the leading NUL sentinel)
+    int j = 0, seq = 0, last = -1;
+    uint32_t w = (uint32_t)A.start_nul;
+    bool inter = false;
+    if (A.start_nul != 0) {
+        last = (__ldg(A.flags + A.start_nul) & SF_ACC) ? 0 : -1;
+    } else {
+        cur = 0;
+        w = (uint32_t)A.q0;
+    }
+    const uint32_t q0 = (uint32_t)A.q0;
+    while (true) {
+        const uint32_t b = j < len ? lds_u8(a + j) : 0u;     // virtual trailing NUL at j == len
+        if (inter && (b & 0xC0) != 0x80) {                   // sequence broken: pending bytes replay as U+FFFF
+            const uint32_t f = __ldg(A.flags + (w & W_STATE));
+            for (int k = 1; k <= j - seq; k++)
+                if (f & (SF_FAILACC1 << (k - 1))) last = seq + k;
+            inter = false;
+        }
+        const uint32_t nw = T.next(w & W_STATE, b);
+        if ((nw & W_INTER) && !inter) seq = j;
+        inter = (nw & W_INTER) != 0;
+        w = nw;
+        j++;
+        if (w & W_ACC) last = j;
+        if ((w & W_STATE) == 0 || j > len) {                 // this attempt is over
+            if (last >= 0) {
+                const int e = last < len ? last : len;
+                if (cur < 0) { if (e > 0) { from = 1; to = e; } }
+                else { from = cur + 1; to = e; }
+                return;
+            }
+            if (cur < 0) cur = 0;
+            else {
+                const uint32_t c0 = lds_u8(a + cur);
+                int n = 1;
+                if (c0 >= 0xC0 && c0 < 0xF8) {               // lead byte: the character is n bytes only if well formed
+                    n = c0 < 0xE0 ? 2 : c0 < 0xF0 ? 3 : 4;
+                    bool ok = cur + n <= len;
+                    if (ok) ok = (lds_u8(a + cur + 1) & 0xC0) == 0x80;
+                    if (ok && n > 2) ok = (lds_u8(a + cur + 2) & 0xC0) == 0x80;
+                    if (ok && n > 3) ok = (lds_u8(a + cur + 3) & 0xC0) == 0x80;
+                    if (!ok) n = 1;
+                }
+                cur += n;
+            }
+            if (cur >= len) return;
+            w = q0;
+            j = cur;
+            last = -1;
+            inter = false;
+        }
+    }
+}
+
 // do_matching_including for a non-blank text (api_internal_m.F90:76-164): candidate starts are either
 // every character boundary (no usable prefix) or the non-overlapping occurrences of the extracted
 // prefix in S (utility_m.f90:58-117), cut short by the last occurrence of the extracted suffix.
@@ -860,6 +923,7 @@ __global__ void __launch_bounds__(256) k_regex_ragged(KParams p, const uint8_t* 
     __syncthreads();
     uint32_t phase = 0;
     const uint32_t tile_addr = smem_u32(tile);
+    const bool plain = !p.all_active && !p.pre_active;   // brute-force starts, no literal machinery
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const TileCtx c = load_tile(buf, offsets, n, total, t, spt, cap, tile, s_off, mbar, phase);
         for (int i = threadIdx.x; i < c.count; i += blockDim.x) {
@@ -868,6 +932,15 @@ __global__ void __launch_bounds__(256) k_regex_ragged(KParams p, const uint8_t* 
             if (r1 == OFF_BEYOND) {
                 const int64_t o0 = __ldg(offsets + c.first + i), o1 = __ldg(offsets + c.first + i + 1);
                 eval_regex(p, T, FetchGlobal{buf + o0}, o1 - o0, f, e);
+            } else if (plain) {
+                const int len = r1 - r0;
+                const uint32_t a = tile_addr + (uint32_t)r0;
+                f = 0; e = 0;
+                if (!(len == 0 || (len == 1 && lds_u8(a) == 0x20))) {            // api_internal_m.F90:68-74
+                    int64_t ff, tt;
+                    brute_force_smem(Anchored{p.flags, p.start_nul, p.q0}, T, a, len, ff, tt);
+                    if (ff > 0 && tt > 0) { f = ff; e = tt; }                        // forgex.F90:332-343
+                }
             } else {
                 eval_regex(p, T, FetchShared{tile_addr + (uint32_t)r0}, (int64_t)(r1 - r0), f, e);
             }
