@@ -125,6 +125,23 @@ class Pattern:
             "row_shift": rs,
         }
 
+    def span_tables(self):
+        """tables of the linear-time span path (None if the pattern has none)"""
+        ptrs = [C.c_void_p() for _ in range(5)]
+        sc, rsc = (C.c_int32 * 4)(), (C.c_int32 * 4)()
+        rc = L.lib().fx_pattern_span_tables(self.h, C.byref(ptrs[0]), C.byref(ptrs[1]), C.byref(sc), C.byref(ptrs[2]),
+                                            C.byref(ptrs[3]), C.byref(ptrs[4]), C.byref(rsc))
+        if rc == 1:
+            return None
+        _check(rc, "fx_pattern_span_tables")
+
+        def arr(p, n, dt):
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(dt)), shape=(n,)).copy()
+        ns, nr, nc = sc[0], rsc[0], rsc[1]
+        return {"direct": arr(ptrs[0], ns * 256, C.c_uint16).reshape(ns, 256), "flags": arr(ptrs[1], ns, C.c_uint8),
+                "start": sc[1], "rdelta": arr(ptrs[2], nr * nc, C.c_uint16).reshape(nr, nc),
+                "rstartok": arr(ptrs[3], nr, C.c_uint8), "cuts": arr(ptrs[4], nc + 1, C.c_int32), "rstart": rsc[2]}
+
     # ---- host-buffer batch calls (numpy in, numpy out; copies happen inside the library) ----
     def _bool_fixed(self, fn, buf, n, stride):
         buf = np.ascontiguousarray(buf, dtype=np.uint8)

@@ -348,6 +348,205 @@ int build_cp_automaton(const Nfa& nfa, Mode mode, int state_cap, CpAutomaton& a)
 }
 
 // ---------------------------------------------------------------------------------------------
+// spans in linear time: forward "ordered groups" automaton + reverse automaton
+// ---------------------------------------------------------------------------------------------
+// Forgex's search (api_internal_m.F90:108-155) tries the starts in order and returns at the first start whose
+// anchored run accepts after >= 1 symbol, with that run's LAST accept as the end.  All runs can be advanced
+// together if the automaton state remembers the ORDER of the runs: a state is a list of groups of NFA states, one
+// group per start still in play, earliest start first.  Per symbol: a new group is injected for the start at this
+// position (until something has matched), every group steps, an NFA state already held by an earlier group is
+// dropped from later groups (same future, and the earlier start wins), empty groups vanish, and as soon as a group
+// holds the exit every later group is cut off and injection stops ("matched").  Whenever the state holds the exit
+// the kernel records the position: what it holds at the end is the last accept of the earliest start that ever
+// accepted -- the end of Forgex's answer.  The start is then found by the reverse automaton walking backwards from
+// that end: the leftmost position at which it holds the NFA entry.
+namespace {
+
+struct GroupState {
+    bool matched = false;
+    std::vector<Bits> groups;
+    std::vector<uint64_t> key(size_t words) const {
+        std::vector<uint64_t> k;
+        k.push_back(matched ? 1 : 0);
+        k.push_back(groups.size());
+        for (const Bits& g : groups) k.insert(k.end(), g.begin(), g.end());
+        (void)words;
+        return k;
+    }
+};
+
+}  // namespace
+
+static int build_span_forward(const Nfa& nfa, int state_cap, CpAutomaton& a) {
+    Subsets ss(nfa);
+    const int ncls = (int)nfa.cuts.size() - 1;
+    a = CpAutomaton();
+    a.nclasses = ncls;
+    a.cuts = nfa.cuts;
+    const int nul_class = a.class_of(0);
+    a.q0_accepting = Subsets::has(ss.entry_closure, nfa.exit);
+    const size_t W = ss.words;
+
+    // one step of a single group on every class at once
+    auto step_group = [&](const Bits& g, std::vector<Bits>& out) { ss.step_all(g, false, out); };
+    std::vector<Bits> injected;                    // closure(move(closure(entry), c)) per class
+    step_group(ss.entry_closure, injected);
+
+    std::map<std::vector<uint64_t>, int> index;
+    std::vector<GroupState> states;
+    std::vector<uint8_t> accept;
+    auto intern = [&](const GroupState& st, bool acc) -> int {
+        if (st.groups.empty() && st.matched) return 0;           // nothing can happen any more
+        auto k = st.key(W);
+        k.push_back(acc ? 1 : 0);
+        auto it = index.find(k);
+        if (it != index.end()) return it->second;
+        int id = (int)states.size();
+        states.push_back(st);
+        accept.push_back(acc ? 1 : 0);
+        index.emplace(k, id);
+        return id;
+    };
+    // successor of `st` on class c; *acc tells whether the new state holds the exit
+    auto successor = [&](const GroupState& st, const std::vector<std::vector<Bits> >& stepped, int c, bool inject,
+                         bool* acc) -> GroupState {
+        GroupState n;
+        n.matched = st.matched;
+        Bits seen(W, 0);
+        auto add = [&](Bits g) {
+            bool any = false;
+            for (size_t w = 0; w < W; w++) { g[w] &= ~seen[w]; seen[w] |= g[w]; any = any || g[w]; }
+            if (any) n.groups.push_back(g);
+        };
+        for (size_t gi = 0; gi < st.groups.size(); gi++) add(stepped[gi][(size_t)c]);
+        if (inject && !st.matched) add(injected[(size_t)c]);
+        *acc = false;
+        for (size_t gi = 0; gi < n.groups.size(); gi++)
+            if (Subsets::has(n.groups[gi], nfa.exit)) {
+                n.groups.resize(gi + 1);                          // later starts can never win any more
+                n.matched = true;
+                *acc = true;
+                break;
+            }
+        return n;
+    };
+
+    states.push_back(GroupState());                               // state 0: dead
+    accept.push_back(0);
+    GroupState empty;                                             // before any symbol: no run, nothing matched
+    std::vector<int> delta;
+    std::vector<uint8_t> end_accept;
+    // the start state = after the leading NUL (start position 1 injected)
+    {
+        std::vector<std::vector<Bits> > none;
+        bool acc;
+        GroupState s0 = successor(empty, none, nul_class, true, &acc);
+        a.start = intern(s0, acc);
+        if (a.start == 0) {                                       // cannot happen (unmatched states are alive)
+            a.start = intern(empty, false);
+        }
+    }
+    for (size_t cur = 1; cur < states.size(); cur++) {
+        GroupState st = states[cur];                              // copy: `states` grows below
+        std::vector<std::vector<Bits> > stepped(st.groups.size());
+        for (size_t gi = 0; gi < st.groups.size(); gi++) step_group(st.groups[gi], stepped[gi]);
+        delta.resize(states.size() * (size_t)ncls, 0);
+        end_accept.resize(states.size(), 0);
+        for (int c = 0; c < ncls; c++) {
+            bool acc;
+            GroupState n = successor(st, stepped, c, true, &acc);
+            int dst = intern(n, acc);
+            if ((int)states.size() > state_cap) return ERR_DFA_STATE_CAP;
+            delta.resize(states.size() * (size_t)ncls, 0);
+            delta[cur * (size_t)ncls + (size_t)c] = dst;
+        }
+        bool eacc;
+        successor(st, stepped, nul_class, false, &eacc);          // the trailing NUL is consumed but is not a start
+        end_accept.resize(states.size(), 0);
+        end_accept[cur] = eacc ? 1 : 0;
+    }
+    a.nstates = (int)states.size();
+    delta.resize((size_t)a.nstates * (size_t)ncls, 0);
+    end_accept.resize((size_t)a.nstates, 0);
+    a.delta = delta;
+    a.accept = accept;
+    a.end_accept = end_accept;
+    a.q0 = a.start;
+    a.start_nul = a.start;
+    a.matched = -1;
+    return OK;
+}
+
+int build_rev_automaton(const Nfa& nfa, int state_cap, RevAutomaton& r) {
+    const int ncls = (int)nfa.cuts.size() - 1;
+    const size_t W = ((size_t)nfa.n + 64) / 64;
+    // reversed adjacency
+    std::vector<std::vector<int> > reps((size_t)nfa.n + 1);
+    std::vector<std::vector<std::pair<int, int> > > redges((size_t)nfa.n + 1);   // dst -> (class, src)
+    for (int s = 1; s <= nfa.n; s++) {
+        for (int d : nfa.eps[(size_t)s]) reps[(size_t)d].push_back(s);
+        for (auto& e : nfa.edges[(size_t)s]) {
+            int c0 = (int)(std::lower_bound(nfa.cuts.begin(), nfa.cuts.end(), e.first.lo) - nfa.cuts.begin());
+            for (int c = c0; c < ncls && nfa.cuts[(size_t)c] <= e.first.hi; c++) redges[(size_t)e.second].push_back({c, s});
+        }
+    }
+    auto has = [](const Bits& b, int s) { return (b[(size_t)s >> 6] >> (s & 63)) & 1; };
+    auto put = [](Bits& b, int s) { b[(size_t)s >> 6] |= 1ull << (s & 63); };
+    auto close = [&](Bits& b) {
+        std::vector<int> stack;
+        for (int s = 1; s <= nfa.n; s++) if (has(b, s)) stack.push_back(s);
+        while (!stack.empty()) {
+            int u = stack.back();
+            stack.pop_back();
+            for (int v : reps[(size_t)u]) if (!has(b, v)) { put(b, v); stack.push_back(v); }
+        }
+    };
+    r = RevAutomaton();
+    r.nclasses = ncls;
+    r.cuts = nfa.cuts;
+    std::unordered_map<Bits, int, BitsHash> index;
+    std::vector<Bits> sets;
+    sets.push_back(Bits(W, 0));
+    auto intern = [&](const Bits& b) -> int {
+        bool any = false;
+        for (uint64_t w : b) any = any || w;
+        if (!any) return 0;
+        auto it = index.find(b);
+        if (it != index.end()) return it->second;
+        int id = (int)sets.size();
+        sets.push_back(b);
+        index.emplace(b, id);
+        return id;
+    };
+    Bits s0(W, 0);
+    put(s0, nfa.exit);
+    close(s0);
+    r.start = intern(s0);
+    std::vector<uint16_t> delta;
+    for (size_t cur = 1; cur < sets.size(); cur++) {
+        std::vector<Bits> next((size_t)ncls, Bits(W, 0));
+        Bits x = sets[cur];
+        for (int d = 1; d <= nfa.n; d++)
+            if (has(x, d))
+                for (auto& cs : redges[(size_t)d]) put(next[(size_t)cs.first], cs.second);
+        delta.resize(sets.size() * (size_t)ncls, 0);
+        for (int c = 0; c < ncls; c++) {
+            close(next[(size_t)c]);
+            int dst = intern(next[(size_t)c]);
+            if ((int)sets.size() > state_cap) return ERR_DFA_STATE_CAP;
+            delta.resize(sets.size() * (size_t)ncls, 0);
+            delta[cur * (size_t)ncls + (size_t)c] = (uint16_t)dst;
+        }
+    }
+    r.nstates = (int)sets.size();
+    delta.resize((size_t)r.nstates * (size_t)ncls, 0);
+    r.delta = delta;
+    r.startok.assign((size_t)r.nstates, 0);
+    for (int s = 1; s < r.nstates; s++) r.startok[(size_t)s] = has(sets[(size_t)s], nfa.entry) ? 1 : 0;
+    return OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // byte-level DFA
 // ---------------------------------------------------------------------------------------------
 // Boundary states are the code-point automaton's states.  A lead byte moves to an INTER state
@@ -585,6 +784,12 @@ int compile_program(const std::string& pattern, int op, int state_cap, Program& 
     if (rc != OK) { p.status = rc; return rc; }
     rc = build_byte_table(p.cp, op == MODE_REGEX, p.bt);
     if (rc != OK) { p.status = rc; return rc; }
+    if (op == MODE_REGEX && !p.literal_only && !p.prefix_active) {
+        // linear-time span path; silently absent when a cap is exceeded (the anchored tables above still serve)
+        if (build_span_forward(nfa, state_cap, p.span_cp) == OK && build_byte_table(p.span_cp, true, p.span_bt) == OK &&
+            build_rev_automaton(nfa, 0xFFFF, p.rev) == OK)
+            p.has_span = true;
+    }
     return OK;
 }
 

@@ -37,6 +37,10 @@ struct DeviceTables {
     uint16_t* a_table = nullptr;
     uint8_t* a_classmap = nullptr;
     uint8_t* a_flags = nullptr;
+    // linear-time span path (FX_OP_REGEX, when the pattern has one)
+    uint16_t* sp_table = nullptr; uint16_t* sp_direct = nullptr;
+    uint8_t* sp_classmap = nullptr; uint8_t* sp_flags = nullptr;
+    uint16_t* r_delta = nullptr; uint8_t* r_startok = nullptr; int32_t* r_cuts = nullptr; uint8_t* r_ascii = nullptr;
     // grow-only scratch for the host-pointer entry points
     uint8_t* w_buf = nullptr; size_t w_buf_cap = 0;
     int64_t* w_off = nullptr; size_t w_off_cap = 0;
@@ -137,6 +141,33 @@ int ensure_device(fx_pattern* p) {
         CUDA_TRY(cudaMemcpy(d.a_classmap, at.classmap, 256, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMalloc(&d.a_flags, at.flags.size() + 16));
         CUDA_TRY(cudaMemcpy(d.a_flags, at.flags.data(), at.flags.size(), cudaMemcpyHostToDevice));
+    }
+    if (p->prog.has_span) {
+        const fx::ByteTable& st = p->prog.span_bt;
+        const fx::RevAutomaton& rv = p->prog.rev;
+        CUDA_TRY(cudaMalloc(&d.sp_table, st.table.size() * 2 + 32));
+        CUDA_TRY(cudaMemset(d.sp_table, 0, st.table.size() * 2 + 32));
+        CUDA_TRY(cudaMemcpy(d.sp_table, st.table.data(), st.table.size() * 2, cudaMemcpyHostToDevice));
+        if ((int)st.direct.size() * 2 <= DIRECT_LIMIT_BYTES) {
+            CUDA_TRY(cudaMalloc(&d.sp_direct, st.direct.size() * 2 + 32));
+            CUDA_TRY(cudaMemset(d.sp_direct, 0, st.direct.size() * 2 + 32));
+            CUDA_TRY(cudaMemcpy(d.sp_direct, st.direct.data(), st.direct.size() * 2, cudaMemcpyHostToDevice));
+        }
+        CUDA_TRY(cudaMalloc(&d.sp_classmap, 256));
+        CUDA_TRY(cudaMemcpy(d.sp_classmap, st.classmap, 256, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&d.sp_flags, st.flags.size() + 16));
+        CUDA_TRY(cudaMemcpy(d.sp_flags, st.flags.data(), st.flags.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&d.r_delta, rv.delta.size() * 2 + 16));
+        CUDA_TRY(cudaMemcpy(d.r_delta, rv.delta.data(), rv.delta.size() * 2, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&d.r_startok, rv.startok.size() + 16));
+        CUDA_TRY(cudaMemcpy(d.r_startok, rv.startok.data(), rv.startok.size(), cudaMemcpyHostToDevice));
+        std::vector<int32_t> cuts(rv.cuts.begin(), rv.cuts.end());
+        CUDA_TRY(cudaMalloc(&d.r_cuts, cuts.size() * 4 + 16));
+        CUDA_TRY(cudaMemcpy(d.r_cuts, cuts.data(), cuts.size() * 4, cudaMemcpyHostToDevice));
+        uint8_t ascii[128];
+        for (int c = 0; c < 128; c++) ascii[c] = (uint8_t)p->prog.span_cp.class_of(c);
+        CUDA_TRY(cudaMalloc(&d.r_ascii, 128));
+        CUDA_TRY(cudaMemcpy(d.r_ascii, ascii, 128, cudaMemcpyHostToDevice));
     }
     CUDA_TRY(cudaMalloc(&d.w_best, 16));
     CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
@@ -409,6 +440,24 @@ int launch_regex_ragged_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, con
     return cuda_status(cudaGetLastError());
 }
 
+template <int KIND>
+int launch_span_t(fx_pattern* p, const Plan& pl, const SpanParams& sp, int table_bytes, const uint8_t* buf,
+                  const int64_t* off, int64_t n, int64_t total, int64_t* from, int64_t* to, cudaStream_t s) {
+    auto kern = k_span_ragged<KIND>;
+    Plan tp = pl;
+    tp.table_bytes = KIND == 3 ? 0 : table_bytes;
+    Tiling t = make_tiling(tp, n, total);
+    int bps = 0;
+    int rc = occupancy_grid(kern, 256, t.smem, p->dev.sm_count, bps);
+    if (rc) return rc;
+    long long cap = (long long)p->dev.sm_count * bps;
+    int grid = (int)(t.ntiles < cap ? t.ntiles : cap);
+    if (grid < 1) grid = 1;
+    kern<<<grid, 256, t.smem, s>>>(pl.kp, sp, buf, off, n, total, from, to, t.spt, t.cap, t.ntiles, t.table_smem);
+    g_launches++;
+    return cuda_status(cudaGetLastError());
+}
+
 int launch_regex_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, int64_t n, int64_t total,
                         int64_t* from, int64_t* to, cudaStream_t s) {
     if (n < 0 || total < 0) return FX_ERR_BAD_ARGUMENT;
@@ -416,6 +465,29 @@ int launch_regex_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, i
     Plan pl;
     int rc = make_plan(p, pl);
     if (rc) return rc;
+    if (p->prog.has_span && env_int("FX_SPAN_LINEAR", 1)) {       // linear-time span path (K3f)
+        const fx::ByteTable& st = p->prog.span_bt;
+        const fx::RevAutomaton& rv = p->prog.rev;
+        const DeviceTables& d = p->dev;
+        SpanParams sp;
+        int classed_bytes = (int)st.table.size() * 2, direct_bytes = (int)st.direct.size() * 2;
+        int kind = p->residency == FX_TABLE_GLOBAL ? 3 : d.sp_direct ? 1 : classed_bytes <= SMEM_TABLE_LIMIT_BYTES ? 2 : 3;
+        sp.table = kind == 1 ? d.sp_direct : d.sp_table;
+        sp.classmap = d.sp_classmap;
+        sp.flags = d.sp_flags;
+        sp.table_words = (kind == 1 ? direct_bytes : classed_bytes) / 2;
+        sp.nstates = st.nstates;
+        sp.row_shift = kind == 1 ? 8 : st.row_shift;
+        sp.start = st.start;
+        sp.rdelta = d.r_delta; sp.rstartok = d.r_startok; sp.cuts = d.r_cuts; sp.ascii_class = d.r_ascii;
+        sp.rclasses = rv.nclasses; sp.rstart = rv.start;
+        sp.nul_class = p->prog.span_cp.class_of(0);
+        sp.ffff_class = p->prog.span_cp.class_of(0xFFFF);
+        int tb = kind == 1 ? direct_bytes : classed_bytes;
+        if (kind == 1) return launch_span_t<1>(p, pl, sp, tb, buf, off, n, total, from, to, s);
+        if (kind == 2) return launch_span_t<2>(p, pl, sp, tb, buf, off, n, total, from, to, s);
+        return launch_span_t<3>(p, pl, sp, tb, buf, off, n, total, from, to, s);
+    }
     if (pl.kind == 1) return launch_regex_ragged_t<1>(p, pl, buf, off, n, total, from, to, s);
     if (pl.kind == 2) return launch_regex_ragged_t<2>(p, pl, buf, off, n, total, from, to, s);
     return launch_regex_ragged_t<3>(p, pl, buf, off, n, total, from, to, s);
@@ -528,6 +600,8 @@ int fx_pattern_free(fx_pattern* p) {
     if (d.device >= 0) {
         cudaFree(d.table); cudaFree(d.direct); cudaFree(d.table8); cudaFree(d.classmap); cudaFree(d.flags); cudaFree(d.lits);
         cudaFree(d.a_table); cudaFree(d.a_classmap); cudaFree(d.a_flags);
+        cudaFree(d.sp_table); cudaFree(d.sp_direct); cudaFree(d.sp_classmap); cudaFree(d.sp_flags);
+        cudaFree(d.r_delta); cudaFree(d.r_startok); cudaFree(d.r_cuts); cudaFree(d.r_ascii);
         cudaFree(d.w_buf); cudaFree(d.w_off); cudaFree(d.w_out); cudaFree(d.w_span); cudaFree(d.w_best);
     }
     delete p;
@@ -586,6 +660,23 @@ int fx_pattern_tables(const fx_pattern* p, const uint16_t** table, const uint16_
         scalars[4] = bt.q0_accepting ? 1 : 0;
         scalars[5] = bt.result_threshold;
     }
+    return FX_OK;
+}
+
+int fx_pattern_span_tables(const fx_pattern* p, const uint16_t** direct, const uint8_t** flags, int32_t scalars[4],
+                           const uint16_t** rdelta, const uint8_t** rstartok, const int32_t** cuts, int32_t rscalars[4]) {
+    if (!p || p->prog.status != fx::OK) return FX_ERR_BAD_ARGUMENT;
+    if (!p->prog.has_span) return 1;      // the pattern has no linear-time span path
+    const fx::ByteTable& st = p->prog.span_bt;
+    const fx::RevAutomaton& rv = p->prog.rev;
+    if (direct) *direct = st.direct.data();
+    if (flags) *flags = st.flags.data();
+    if (scalars) { scalars[0] = st.nstates; scalars[1] = st.start; scalars[2] = 0; scalars[3] = 0; }
+    if (rdelta) *rdelta = rv.delta.data();
+    if (rstartok) *rstartok = rv.startok.data();
+    static_assert(sizeof(int) == sizeof(int32_t), "cuts are exposed as int32");
+    if (cuts) *cuts = reinterpret_cast<const int32_t*>(rv.cuts.data());
+    if (rscalars) { rscalars[0] = rv.nstates; rscalars[1] = rv.nclasses; rscalars[2] = rv.start; rscalars[3] = 0; }
     return FX_OK;
 }
 

@@ -114,7 +114,20 @@ struct CpAutomaton {
     int class_of(int cp) const;
 };
 
-enum Mode { MODE_MATCH = 0, MODE_IN = 1, MODE_REGEX = 2 };
+enum Mode { MODE_MATCH = 0, MODE_IN = 1, MODE_REGEX = 2, MODE_SPAN_FWD = 3 };
+
+// Reverse automaton over the same code-point classes: determinised reversal of the NFA.  Walking the text
+// backwards from the end of a match, state X = NFA states from which the exit is reachable through the symbols
+// read so far; a position is a valid match start when X holds the entry (startok).
+struct RevAutomaton {
+    int nstates = 0;               // state 0 = dead
+    int nclasses = 0;
+    int start = 0;                 // reverse closure of {exit}
+    std::vector<int> cuts;
+    std::vector<uint16_t> delta;   // nstates x nclasses
+    std::vector<uint8_t> startok;  // nstates
+};
+int build_rev_automaton(const Nfa& nfa, int state_cap, RevAutomaton& out);
 
 int build_nfa(const Syntax& syn, Nfa& nfa);
 int build_cp_automaton(const Nfa& nfa, Mode mode, int state_cap, CpAutomaton& out);
@@ -166,6 +179,12 @@ struct Program {
     int nfa_states = 0;
     CpAutomaton cp;
     ByteTable bt;
+    // FX_OP_REGEX only: the linear-time span path (forward "ordered groups" automaton + reverse automaton);
+    // absent (has_span == false) when a cap is exceeded or the pattern uses the prefix prefilter
+    bool has_span = false;
+    CpAutomaton span_cp;
+    ByteTable span_bt;
+    RevAutomaton rev;
 };
 
 int compile_program(const std::string& pattern, int op, int state_cap, Program& out);

@@ -952,6 +952,155 @@ __global__ void __launch_bounds__(256) k_regex_ragged(KParams p, const uint8_t* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// K3f: ragged batch, span result, linear time (config C3).
+// Forward: ONE walk of the "ordered groups" automaton (fx_automata.cpp, build_span_forward) yields the end of
+// Forgex's leftmost-longest match: the last position at which the state held the exit.  Backward: the reverse
+// automaton walks from that end towards the front, decoding characters backwards with the reference's decoder
+// rule (a well-formed sequence that ends exactly here, else one byte = U+FFFF); the leftmost position at which
+// it holds the NFA entry is the start.  Same tiling as K2 (TMA-staged tile, one string per thread).
+// ---------------------------------------------------------------------------------------------
+struct SpanParams {
+    // forward table (flag-bit words), selected form
+    const uint16_t* table;
+    const uint8_t* classmap;
+    const uint8_t* flags;
+    int table_words, nstates, row_shift, start;
+    // reverse automaton over code-point classes
+    const uint16_t* rdelta;     // rstates x rclasses
+    const uint8_t* rstartok;
+    const int32_t* cuts;        // rclasses + 1 ascending code points
+    const uint8_t* ascii_class; // class of code points 0..127
+    int rclasses, rstart, nul_class, ffff_class;
+};
+
+__device__ __forceinline__ int cp_class(const SpanParams& sp, uint32_t cp) {
+    if (cp < 128) return __ldg(sp.ascii_class + cp);
+    int lo = 0, hi = sp.rclasses;              // largest c with cuts[c] <= cp
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((uint32_t)__ldg(sp.cuts + mid) <= cp) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+template <class TBL>
+__device__ __forceinline__ void span_linear_smem(const SpanParams& sp, const TBL& T, uint32_t a, int len,
+                                                 int64_t& from, int64_t& to) {
+    from = 0; to = 0;
+    // ---- forward: end of the leftmost-longest match ----
+    uint32_t w = (uint32_t)sp.start;
+    int last = (__ldg(sp.flags + sp.start) & SF_ACC) ? 0 : -1;
+    int seq = 0;
+    bool inter = false;
+    int j = 0;
+    for (; j < len; j++) {
+        const uint32_t b = lds_u8(a + j);
+        if (inter && (b & 0xC0) != 0x80) {                  // sequence broken: pending bytes replay as U+FFFF
+            const uint32_t f = __ldg(sp.flags + (w & W_STATE));
+            for (int k = 1; k <= j - seq; k++)
+                if (f & (SF_FAILACC1 << (k - 1))) last = seq + k;
+            inter = false;
+        }
+        const uint32_t nw = T.next(w & W_STATE, b);
+        if ((nw & W_INTER) && !inter) seq = j;
+        inter = (nw & W_INTER) != 0;
+        w = nw;
+        if (w & W_ACC) last = j + 1;
+        if ((w & W_STATE) == 0) break;
+    }
+    if (j >= len && (w & W_STATE) != 0) {                  // text exhausted: the trailing NUL follows (not a start)
+        const uint32_t f = __ldg(sp.flags + (w & W_STATE));
+        if (inter)
+            for (int k = 1; k <= len - seq; k++)
+                if (f & (SF_FAILACC1 << (k - 1))) last = seq + k;
+        if (f & SF_END) last = len + 1;
+    }
+    if (last <= 0) return;                                  // no match, or only the leading NUL matched (to = 0)
+    // ---- backward: leftmost start of a match that ends at `last` ----
+    uint32_t r = (uint32_t)sp.rstart;
+    int pos = last;
+    if (last > len) { r = __ldg(sp.rdelta + r * sp.rclasses + sp.nul_class); pos = len; }
+    int best = -2;                                          // -2 none, -1 the leading NUL, >= 0 text index
+    while (r != 0 && pos > 0) {
+        // the character that ends at pos
+        uint32_t c = lds_u8(a + pos - 1);
+        int q = pos - 1;
+        uint32_t cp = c;
+        if (c >= 0x80) {
+            cp = 0xFFFF;                                    // stray / malformed byte unless a well-formed sequence ends here
+            if ((c & 0xC0) == 0x80) {
+                uint32_t acc = c & 0x3F;
+                int shift = 6;
+                for (int back = 2; back <= 4 && pos - back >= 0; back++) {
+                    const uint32_t d = lds_u8(a + pos - back);
+                    if ((d & 0xC0) == 0x80) { acc |= (d & 0x3F) << shift; shift += 6; continue; }
+                    const int n = (d >> 5) == 6 ? 2 : (d >> 4) == 14 ? 3 : (d >> 3) == 30 ? 4 : 1;
+                    if (n == back) {
+                        const uint32_t lead_bits = n == 2 ? (d & 0x1F) : n == 3 ? (d & 0x0F) : (d & 0x07);
+                        cp = acc | (lead_bits << shift);
+                        q = pos - back;
+                    }
+                    break;
+                }
+            }
+        }
+        r = __ldg(sp.rdelta + r * sp.rclasses + cp_class(sp, cp));
+        if (r == 0) break;
+        pos = q;
+        if (__ldg(sp.rstartok + r)) best = pos;
+    }
+    if (r != 0 && pos == 0) {                               // the leading NUL sentinel (start position 1)
+        r = __ldg(sp.rdelta + r * sp.rclasses + sp.nul_class);
+        if (r != 0 && __ldg(sp.rstartok + r)) best = -1;
+    }
+    if (best == -2) return;                                 // cannot happen for a consistent pair of automata
+    from = best < 0 ? 1 : best + 1;
+    to = last < len ? last : len;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) k_span_ragged(KParams p, SpanParams sp, const uint8_t* __restrict__ buf,
+                                                     const int64_t* __restrict__ offsets, int64_t n, int64_t total,
+                                                     int64_t* __restrict__ from, int64_t* __restrict__ to,
+                                                     int spt, int cap, int64_t ntiles, int table_smem_bytes) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_cmap = smem + 16;
+    uint8_t* s_table = smem + 16 + 256;
+    int32_t* s_off = reinterpret_cast<int32_t*>(smem + 16 + 256 + table_smem_bytes);
+    uint8_t* tile = smem + tile_offset(table_smem_bytes, spt);
+    const uint32_t mbar = smem_u32(smem);
+    KParams fwd = p;                       // stage_table reads table / classmap / sizes from a KParams
+    fwd.table = sp.table; fwd.classmap = sp.classmap; fwd.table_words = sp.table_words; fwd.row_shift = sp.row_shift;
+    fwd.nstates = sp.nstates;
+    Table<KIND> T = stage_table<KIND>(fwd, s_table, s_cmap);
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
+    const uint32_t tile_addr = smem_u32(tile);
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const TileCtx c = load_tile(buf, offsets, n, total, t, spt, cap, tile, s_off, mbar, phase);
+        for (int i = threadIdx.x; i < c.count; i += blockDim.x) {
+            const int32_t r0 = s_off[i], r1 = s_off[i + 1];
+            int64_t f = 0, e = 0;
+            if (r1 == OFF_BEYOND) {          // not staged (longer than a tile): the anchored emulation from global memory
+                const int64_t o0 = __ldg(offsets + c.first + i), o1 = __ldg(offsets + c.first + i + 1);
+                Table<3> G;
+                G.g_table = p.ctable; G.g_cmap = p.classmap; G.shift = p.c_row_shift; G.s_table = 0; G.s_cmap = 0;
+                eval_regex(p, G, FetchGlobal{buf + o0}, o1 - o0, f, e);
+            } else {
+                const int len = r1 - r0;
+                const uint32_t a = tile_addr + (uint32_t)r0;
+                if (!(len == 0 || (len == 1 && lds_u8(a) == 0x20)))              // api_internal_m.F90:68-74
+                    span_linear_smem(sp, T, a, len, f, e);
+            }
+            from[c.first + i] = f;
+            to[c.first + i] = e;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K4: one long buffer, span result (config C4).
 // The reference tries every character boundary as a start, in order, and returns at the first one
 // whose anchored run accepts after >= 1 symbol (api_internal_m.F90:108-155).  The attempts are

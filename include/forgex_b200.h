@@ -102,6 +102,12 @@ int fx_pattern_literals(const fx_pattern* p, void* all, void* prefix, void* suff
  * classmap: 256 bytes; flags: byte_states bytes; scalars: {start, start_nul, q0, matched, q0_accepting, result_threshold} */
 int fx_pattern_tables(const fx_pattern* p, const uint16_t** table, const uint16_t** direct,
                       const uint8_t** classmap, const uint8_t** flags, int32_t scalars[6]);
+/* FX_OP_REGEX patterns without prefix prefilter also carry a linear-time span path (tests / tools): the 256-column
+ * table of the forward "ordered groups" automaton (scalars = {states, start}), and the reverse automaton over
+ * code-point classes (rscalars = {states, classes, start}; cuts: classes+1 ascending code points).  Returns 1 when
+ * the pattern has no such path. */
+int fx_pattern_span_tables(const fx_pattern* p, const uint16_t** direct, const uint8_t** flags, int32_t scalars[4],
+                           const uint16_t** rdelta, const uint8_t** rstartok, const int32_t** cuts, int32_t rscalars[4]);
 int fx_is_valid_regex(const void* pattern, int64_t plen, int* status);
 
 /* ---- device-pointer entry points (asynchronous on `stream`) ---------------------------- */

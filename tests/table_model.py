@@ -236,3 +236,99 @@ class Model:
 
     def regex(self, s: bytes):
         return self.anch.regex(s)
+
+
+class SpanLinear:
+    """span_linear_smem (K3f): forward ordered-groups automaton, then the reverse automaton"""
+
+    def __init__(self, pattern_obj):
+        self.t = pattern_obj.span_tables()
+        assert self.t is not None
+        self.cuts = [int(x) for x in self.t["cuts"]]
+
+    def cls(self, cp):
+        import bisect
+        return bisect.bisect_right(self.cuts, cp) - 1
+
+    def regex(self, s: bytes):
+        t = self.t
+        n = len(s)
+        if n == 0 or s == b" ":
+            return (0, 0)
+        direct, flags = t["direct"], t["flags"]
+        w = t["start"]
+        last = 0 if (flags[t["start"]] & SF_ACC) else -1
+        seq, inter = 0, False
+        j = 0
+        dead = False
+        while j < n:
+            b = s[j]
+            if inter and (b & 0xC0) != 0x80:
+                f = int(flags[w & W_STATE])
+                for k in range(1, j - seq + 1):
+                    if f & (SF_FAILACC1 << (k - 1)):
+                        last = seq + k
+                inter = False
+            nw = int(direct[w & W_STATE, b])
+            if (nw & W_INTER) and not inter:
+                seq = j
+            inter = bool(nw & W_INTER)
+            w = nw
+            if w & W_ACC:
+                last = j + 1
+            if (w & W_STATE) == 0:
+                dead = True
+                break
+            j += 1
+        if not dead:
+            f = int(flags[w & W_STATE])
+            if inter:
+                for k in range(1, n - seq + 1):
+                    if f & (SF_FAILACC1 << (k - 1)):
+                        last = seq + k
+            if f & SF_END:
+                last = n + 1
+        if last <= 0:
+            return (0, 0)
+        rd, ok = t["rdelta"], t["rstartok"]
+        nul = self.cls(0)
+        r = t["rstart"]
+        pos = last
+        if last > n:
+            r = int(rd[r, nul])
+            pos = n
+        best = -2
+        while r != 0 and pos > 0:
+            c = s[pos - 1]
+            q = pos - 1
+            cp = c
+            if c >= 0x80:
+                cp = 0xFFFF
+                if (c & 0xC0) == 0x80:
+                    acc, shift = c & 0x3F, 6
+                    for back in range(2, 5):
+                        if pos - back < 0:
+                            break
+                        d = s[pos - back]
+                        if (d & 0xC0) == 0x80:
+                            acc |= (d & 0x3F) << shift
+                            shift += 6
+                            continue
+                        nn = 2 if (d >> 5) == 6 else 3 if (d >> 4) == 14 else 4 if (d >> 3) == 30 else 1
+                        if nn == back:
+                            lead = (d & 0x1F) if nn == 2 else (d & 0x0F) if nn == 3 else (d & 0x07)
+                            cp = acc | (lead << shift)
+                            q = pos - back
+                        break
+            r = int(rd[r, self.cls(cp)])
+            if r == 0:
+                break
+            pos = q
+            if ok[r]:
+                best = pos
+        if r != 0 and pos == 0:
+            r = int(rd[r, nul])
+            if r != 0 and ok[r]:
+                best = -1
+        assert best != -2, "forward and reverse automata disagree"
+        return (1 if best < 0 else best + 1, min(last, n))

@@ -13,7 +13,7 @@ import pytest
 import forgex_b200 as fx
 from forgex_b200 import _lib
 from tests import oracle_lib as O
-from tests.table_model import Model
+from tests.table_model import Model, SpanLinear
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 OPS = {"match": "match", "in": "in", "regex": "regex"}
@@ -37,6 +37,14 @@ def model_for(pattern, op):
         p = fx.Pattern(pattern, op)
         _cache[key] = (p, Model(p, use_direct=(len(_cache) % 2 == 0)) if p.status == 0 else None)
     return _cache[key]
+
+
+def linear_answer(pattern, text):
+    p, _ = model_for(pattern, "regex")
+    if p.status != 0 or p.span_tables() is None:
+        return None
+    f, t = SpanLinear(p).regex(text)
+    return text[f - 1:t] if f > 0 and t > 0 else b""
 
 
 def product_answer(kind, pattern, text):
@@ -74,6 +82,10 @@ def test_reference_api_vectors_through_product_tables():
         exp = bytes.fromhex(v["expect"]) if v["kind"] == "regex" else v["expect"]
         if got != exp:
             bad.append("%s %s %r -> %r, expected %r" % (v["src"], v["kind"], pat, got, exp))
+        if v["kind"] == "regex":
+            lin = linear_answer(pat, text)
+            if lin is not None and lin != exp:
+                bad.append("%s regex(linear) %r -> %r, expected %r" % (v["src"], pat, lin, exp))
     assert not bad, "%d vectors fail:\n%s" % (len(bad), "\n".join(bad[:40]))
     assert capped == 4
 
@@ -175,6 +187,7 @@ def test_generated_patterns_match_oracle(seed):
             if p.status != 0:
                 continue  # cap
             m = Model(p, use_direct=rng.random() < 0.5)
+            span = SpanLinear(p) if kind == "regex" and p.span_tables() is not None else None
             for t in texts:
                 checked += 1
                 if kind == "regex":
@@ -182,6 +195,10 @@ def test_generated_patterns_match_oracle(seed):
                     got = m.regex(t)
                     if st != 0 or got != (f, to):
                         bad.append("regex %r on %r: product %r oracle %r (status %d)" % (pat, t, got, (f, to), st))
+                    if span is not None:
+                        got2 = span.regex(t)
+                        if got2 != (f, to):
+                            bad.append("regex(linear) %r on %r: product %r oracle %r" % (pat, t, got2, (f, to)))
                 else:
                     o = O.op_match(pat, t) if kind == "match" else O.op_in(pat, t)
                     got = m.boolean(t)
