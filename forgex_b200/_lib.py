@@ -29,7 +29,9 @@ class PatternInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "op", "status", "nfa_states", "cp_states", "cp_classes", "byte_states", "byte_classes", "row_shift",
         "table_bytes", "direct_bytes", "literal_all_len", "literal_prefix_len", "literal_suffix_len",
-        "literal_only", "residency", "direct", "prefix_mode")]
+        "literal_only", "residency", "direct", "prefix_mode", "sparse", "sparse_ranges")] + [
+        ("sparse_lo", C.c_int32 * 4), ("sparse_hi", C.c_int32 * 4), ("sparse_high", C.c_int32),
+        ("sparse_used", C.c_int32)]
 
 
 _lib = None

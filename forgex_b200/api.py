@@ -96,7 +96,10 @@ class Pattern:
     def info(self):
         inf = L.PatternInfo()
         _check(L.lib().fx_pattern_get_info(self.h, C.byref(inf)), "fx_pattern_get_info")
-        return {n: getattr(inf, n) for n, _ in inf._fields_}
+        out = {n: getattr(inf, n) for n, _ in inf._fields_}
+        for k in ("sparse_lo", "sparse_hi"):
+            out[k] = list(out[k])[:out["sparse_ranges"]]
+        return out
 
     def literals(self):
         inf = self.info()

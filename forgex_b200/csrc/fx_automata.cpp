@@ -766,7 +766,7 @@ int build_byte_table(const CpAutomaton& a, bool flag_bits, ByteTable& out) {
 // ---------------------------------------------------------------------------------------------
 // whole program
 // ---------------------------------------------------------------------------------------------
-int compile_program(const std::string& pattern, int op, int state_cap, Program& p) {
+int compile_program(const std::string& pattern, int op, int state_cap, Program& p, bool want_span) {
     p = Program();
     p.op = op;
     p.prepared = prepare_pattern(pattern, op == MODE_MATCH);
@@ -784,7 +784,7 @@ int compile_program(const std::string& pattern, int op, int state_cap, Program& 
     if (rc != OK) { p.status = rc; return rc; }
     rc = build_byte_table(p.cp, op == MODE_REGEX, p.bt);
     if (rc != OK) { p.status = rc; return rc; }
-    if (op == MODE_REGEX && !p.literal_only && !p.prefix_active) {
+    if (want_span && op == MODE_REGEX && !p.literal_only && !p.prefix_active) {
         // linear-time span path; silently absent when a cap is exceeded (the anchored tables above still serve)
         if (build_span_forward(nfa, state_cap, p.span_cp) == OK && build_byte_table(p.span_cp, true, p.span_bt) == OK &&
             build_rev_automaton(nfa, 0xFFFF, p.rev) == OK)

@@ -22,6 +22,7 @@ namespace {
 std::atomic<long long> g_launches{0};
 
 constexpr int STATE_CAP = 16383;                 // Forgex's own ceiling (lazy_dfa_graph_m.F90:90-92 with parameters_m.f90:126-130)
+constexpr int SPARSE_STATE_CAP = 2048;           // optional anchored automaton of a prefix-less `.in.` pattern
 constexpr int DIRECT_LIMIT_BYTES = 40 * 1024;    // 256-column table kept in shared memory up to this size
 constexpr int SMEM_TABLE_LIMIT_BYTES = 160 * 1024;
 
@@ -50,15 +51,25 @@ struct DeviceTables {
     int sm_count = 0;
 };
 
+// first-byte set F of an anchored automaton: at most 4 ASCII ranges, plus "some bytes >= 0xC0"
+struct FirstSet {
+    int nr = 0;
+    uint8_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+    bool high = false;
+};
+
 }  // namespace
 
 struct fx_pattern {
     fx::Program prog;
     int residency = FX_TABLE_AUTO;
     int last_residency = 0, last_direct = 0;
-    fx::Program anchored;        // only for FX_OP_IN with an active prefix
+    fx::Program anchored;        // FX_OP_IN: the anchored (REGEX-mode) automaton, for the prefix replay and for K2c
     bool has_anchored = false;
     int prefix_mode = 0;         // see KParams::prefix_mode
+    FirstSet first;              // bytes that survive the first step out of q0 of the anchored automaton
+    bool sparse = false;         // the sparse-start kernel (K2c) may serve `.in.` batches
+    int last_sparse = 0;
     DeviceTables dev;
     std::mutex mu;
 };
@@ -104,6 +115,43 @@ bool prefilter_is_neutral(const fx::Program& anchored) {
         if (st == 0) return false;
     }
     return true;
+}
+
+// tuning knobs for experiments (environment, read per launch)
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+// Can the sparse-start kernel (fx_kernels.cuh, K2c) serve this `.in.` pattern?  F = bytes b with a live (or accepting)
+// transition out of q0.  Required: F is non-empty, holds no continuation byte (so every candidate is a character
+// boundary), its ASCII part fits 4 ranges; and the leading-NUL start does not accept by itself (no "empty winner" that would stop the
+// reference's search early, api_internal_m.F90:139-150).  Worth it only when candidates are rare: without knowing the
+// text, "F holds at most FX_SPARSE_MAX_FIRST (default 6) ASCII bytes" stands in for that.
+bool sparse_first_set(const fx::ByteTable& at, FirstSet& fs) {
+    fs = FirstSet();
+    if (at.q0 == 0) return false;
+    if (at.start_nul != 0 && (at.flags[(size_t)at.start_nul] & fxk::SF_ACC)) return false;
+    bool in_f[256];
+    for (int b = 0; b < 256; b++) {
+        const uint16_t w = at.table[((size_t)at.q0 << at.row_shift) + at.classmap[b]];
+        in_f[b] = (w & (fxk::W_STATE | fxk::W_ACC)) != 0;
+    }
+    for (int b = 0x80; b < 0xC0; b++) if (in_f[b]) return false;
+    for (int b = 0xC0; b < 256; b++) fs.high |= in_f[b];
+    int ascii = 0;
+    for (int b = 0; b < 128; b++) ascii += in_f[b];
+    if (ascii > env_int("FX_SPARSE_MAX_FIRST", 6)) return false;
+    int b = 0;
+    while (b < 128) {
+        if (!in_f[b]) { b++; continue; }
+        int e = b;
+        while (e + 1 < 128 && in_f[e + 1]) e++;
+        if (fs.nr == 4) return false;
+        fs.lo[fs.nr] = (uint8_t)b; fs.hi[fs.nr] = (uint8_t)e; fs.nr++;
+        b = e + 1;
+    }
+    return fs.nr > 0 || fs.high;
 }
 
 int ensure_device(fx_pattern* p) {
@@ -180,12 +228,6 @@ struct Plan {
     int table_bytes;   // bytes of the table staged in shared memory (0 for kind 3)
     KParams kp;
 };
-
-// tuning knobs for experiments (environment, read per launch)
-int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
-}
 
 int make_plan(fx_pattern* p, Plan& pl) {
     const fx::ByteTable& bt = p->prog.bt;
@@ -306,7 +348,7 @@ struct Tiling {
     size_t smem;
 };
 
-Tiling make_tiling(const Plan& pl, int64_t n, int64_t total) {
+Tiling make_tiling(const Plan& pl, int64_t n, int64_t total, int extra = 0, int64_t max_cap = 1 << 30) {
     Tiling t;
     int64_t avg = n > 0 ? (total + n - 1) / n : 1;
     if (avg < 1) avg = 1;
@@ -316,9 +358,10 @@ Tiling make_tiling(const Plan& pl, int64_t n, int64_t total) {
     // strings per tile: about one per thread, fewer when strings are long, more when they are short
     int64_t spt = 0, cap = 0;
     for (int iter = 0; iter < 2; iter++) {
-        int64_t fixed = tile_offset(t.table_smem, (int)(spt ? spt : 256)) + 64 + 128;
+        int64_t fixed = tile_offset(t.table_smem, (int)(spt ? spt : 256)) + 64 + 128 + extra;
         cap = per_cta - fixed;
         if (cap < 8192) cap = 8192;
+        if (cap > max_cap) cap = max_cap;
         cap &= ~(int64_t)127;
         spt = (cap * 4 / 5) / avg;           // expect the tile to fill ~80 % of the staged capacity
         spt = (spt / 32) * 32;
@@ -329,7 +372,7 @@ Tiling make_tiling(const Plan& pl, int64_t n, int64_t total) {
     t.spt = (int)spt;
     t.cap = (int)cap;
     t.ntiles = (n + spt - 1) / spt;
-    t.smem = (size_t)tile_offset(t.table_smem, t.spt) + (size_t)t.cap + 64;
+    t.smem = (size_t)tile_offset(t.table_smem, t.spt) + (size_t)extra + (size_t)t.cap + 64;
     return t;
 }
 
@@ -400,6 +443,64 @@ int launch_stream_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int
     return cuda_status(cudaGetLastError());
 }
 
+template <int KIND, int NR, bool HIGH>
+int launch_sparse_t(fx_pattern* p, const Plan& pl, const SparseParams& sp, int table_bytes, const uint8_t* buf,
+                    const int64_t* off, int64_t n, int64_t total, uint8_t* out, cudaStream_t s) {
+    auto kern = k_in_sparse<KIND, NR, HIGH>;
+    Plan tp = pl;
+    tp.table_bytes = KIND == 3 ? 0 : table_bytes;
+    Tiling t = make_tiling(tp, n, total, SPARSE_EXTRA, SPARSE_MAX_TILE - 128);
+    int bps = 0;
+    int rc = occupancy_grid(kern, 256, t.smem, p->dev.sm_count, bps);
+    if (rc) return rc;
+    long long cap = (long long)p->dev.sm_count * bps;
+    int grid = (int)(t.ntiles < cap ? t.ntiles : cap);
+    if (grid < 1) grid = 1;
+    kern<<<grid, 256, t.smem, s>>>(pl.kp, sp, buf, off, n, total, out, t.spt, t.cap, t.ntiles, t.table_smem);
+    g_launches++;
+    return cuda_status(cudaGetLastError());
+}
+
+template <int KIND, bool HIGH>
+int launch_sparse_k(fx_pattern* p, const Plan& pl, const SparseParams& sp, int tb, const uint8_t* buf, const int64_t* off,
+                    int64_t n, int64_t total, uint8_t* out, cudaStream_t s) {
+    if (p->first.nr == 1 && p->first.lo[0] == p->first.hi[0]) {      // one byte value: the cheaper zero-byte test
+        SparseParams one = sp;
+        one.add_lo[0] = p->first.lo[0] * 0x01010101u;
+        return launch_sparse_t<KIND, -1, HIGH>(p, pl, one, tb, buf, off, n, total, out, s);
+    }
+    switch (p->first.nr) {
+        case 0: return launch_sparse_t<KIND, 0, true>(p, pl, sp, tb, buf, off, n, total, out, s);
+        case 1: return launch_sparse_t<KIND, 1, HIGH>(p, pl, sp, tb, buf, off, n, total, out, s);
+        case 2: return launch_sparse_t<KIND, 2, HIGH>(p, pl, sp, tb, buf, off, n, total, out, s);
+        case 3: return launch_sparse_t<KIND, 3, HIGH>(p, pl, sp, tb, buf, off, n, total, out, s);
+        default: return launch_sparse_t<KIND, 4, HIGH>(p, pl, sp, tb, buf, off, n, total, out, s);
+    }
+}
+
+int launch_sparse(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int64_t* off, int64_t n, int64_t total,
+                  uint8_t* out, cudaStream_t s) {
+    const fx::ByteTable& at = p->anchored.bt;
+    const DeviceTables& d = p->dev;
+    SparseParams sp;
+    sp.table = d.a_table; sp.classmap = d.a_classmap; sp.flags = d.a_flags;
+    sp.table_words = (int)at.table.size();
+    sp.row_shift = at.row_shift;
+    sp.q0 = at.q0; sp.start_nul = at.start_nul;
+    for (int r = 0; r < 4; r++) {
+        const int k = r < p->first.nr ? r : 0;       // unused slots repeat range 0
+        sp.add_lo[r] = (0x80u - p->first.lo[k]) * 0x01010101u;
+        sp.add_hi[r] = (0x7Fu - p->first.hi[k]) * 0x01010101u;
+    }
+    const int tb = (int)at.table.size() * 2;
+    const bool smem_table = p->residency != FX_TABLE_GLOBAL && tb <= env_int("FX_SPARSE_SMEM_TABLE_BYTES", 24 * 1024);
+    if (smem_table)
+        return p->first.high ? launch_sparse_k<2, true>(p, pl, sp, tb, buf, off, n, total, out, s)
+                             : launch_sparse_k<2, false>(p, pl, sp, tb, buf, off, n, total, out, s);
+    return p->first.high ? launch_sparse_k<3, true>(p, pl, sp, tb, buf, off, n, total, out, s)
+                         : launch_sparse_k<3, false>(p, pl, sp, tb, buf, off, n, total, out, s);
+}
+
 template <int OP>
 int launch_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, int64_t n, int64_t total, uint8_t* out,
                   cudaStream_t s) {
@@ -409,6 +510,11 @@ int launch_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, int64_t
     int rc = make_plan(p, pl);
     if (rc) return rc;
     int generic = generic_mode(pl, OP);
+    p->last_sparse = 0;
+    if (OP == 1 && !generic && p->sparse && env_int("FX_SPARSE", 1)) {      // sparse starts (K2c)
+        p->last_sparse = 1;
+        return launch_sparse(p, pl, buf, off, n, total, out, s);
+    }
     if (!generic && env_int("FX_RAGGED_FORM", 0) == 2) {      // length-balanced pairs (K2p)
         if (pl.kind == 0) return launch_pairs_t<OP, 0>(p, pl, buf, off, n, total, out, s);
         if (pl.kind == 2) return launch_pairs_t<OP, 2>(p, pl, buf, off, n, total, out, s);
@@ -581,13 +687,17 @@ int fx_compile(const void* pattern, int64_t plen, int op, fx_pattern** out) {
     if (!p) return fx::ERR_ALLOCATION;
     std::string pat(static_cast<const char*>(pattern), (size_t)plen);
     fx::compile_program(pat, op, STATE_CAP, p->prog);
-    if (p->prog.status == fx::OK && op == FX_OP_IN && p->prog.prefix_active && !p->prog.literal_only) {
-        // `.in.` consults the prefix prefilter; keep the anchored automaton to replay it exactly when needed
-        fx::compile_program(pat, FX_OP_REGEX, STATE_CAP, p->anchored);
-        if (p->anchored.status != fx::OK) p->prog.status = p->anchored.status;
-        else {
+    if (p->prog.status == fx::OK && op == FX_OP_IN && !p->prog.literal_only) {
+        // `.in.` consults the prefix prefilter: keep the anchored automaton to replay it exactly when needed.  The same
+        // automaton drives the sparse-start kernel; without a prefix it is optional and built under a smaller cap.
+        const bool needed = p->prog.prefix_active;
+        fx::compile_program(pat, FX_OP_REGEX, needed ? STATE_CAP : SPARSE_STATE_CAP, p->anchored, false);
+        if (p->anchored.status == fx::OK) {
             p->has_anchored = true;
-            p->prefix_mode = prefilter_is_neutral(p->anchored) ? 1 : 2;
+            if (needed) p->prefix_mode = prefilter_is_neutral(p->anchored) ? 1 : 2;
+            p->sparse = p->prefix_mode != 2 && sparse_first_set(p->anchored.bt, p->first);
+        } else if (needed) {
+            p->prog.status = p->anchored.status;
         }
     }
     *out = p;
@@ -629,6 +739,14 @@ int fx_pattern_get_info(const fx_pattern* p, fx_pattern_info* info) {
     info->residency = p->last_residency;
     info->direct = p->last_direct;
     info->prefix_mode = p->prefix_mode;
+    info->sparse = p->sparse ? 1 : 0;
+    info->sparse_ranges = p->sparse ? p->first.nr : 0;
+    info->sparse_high = p->sparse && p->first.high ? 1 : 0;
+    for (int r = 0; r < 4; r++) {
+        info->sparse_lo[r] = p->sparse && r < p->first.nr ? p->first.lo[r] : 0;
+        info->sparse_hi[r] = p->sparse && r < p->first.nr ? p->first.hi[r] : 0;
+    }
+    info->sparse_used = p->last_sparse;
     return FX_OK;
 }
 

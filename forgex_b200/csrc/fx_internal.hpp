@@ -187,6 +187,6 @@ struct Program {
     RevAutomaton rev;
 };
 
-int compile_program(const std::string& pattern, int op, int state_cap, Program& out);
+int compile_program(const std::string& pattern, int op, int state_cap, Program& out, bool want_span = true);
 
 }  // namespace fx

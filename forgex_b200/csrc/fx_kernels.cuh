@@ -684,6 +684,261 @@ __global__ void __launch_bounds__(256, 4) k_bool_ragged(KParams p, const uint8_t
 }
 
 // ---------------------------------------------------------------------------------------------
+// K2c: ragged batch, boolean `.in.`, sparse starts.
+// `.in.` is true when SOME start of the brute-force search wins (api_internal_m.F90:108-155).  A start whose first
+// byte kills the anchored automaton cannot win, so when the set F of first bytes that survive the step out of q0 is
+// small (a few byte ranges: 'f' for foo(bar|baz); NUL/LF/CR for ^ERROR...), almost every position of the text is
+// ruled out by a compare.  The kernel therefore does not walk the strings at all.  Per tile, three phases, each with
+// every lane doing the same work whatever the string lengths are:
+//   S  sweep: the warps read the staged tile LINEARLY, 32 bytes per lane and step out of two conflict-free LDS.128,
+//      and test them against F with SWAR arithmetic (3-4 integer instructions per 4 bytes); 32-byte units that hold
+//      a candidate go into a CTA-wide queue;
+//   C  confirm: one queued unit per lane; each candidate takes its first table step and, unless that already accepts
+//      or enters a multi-byte sequence, the second one (with the next text byte, and with the NUL that would end the
+//      string there).  Two bytes kill almost every candidate; the survivors' positions go into a second queue;
+//   A  attempts: one survivor per thread: binary search over the staged offsets for its string, then the anchored
+//      attempt -- the reference's own inner loop, on the anchored flag-bit table -- until the first counted accept.
+//
+// Preconditions (checked on the host, fx_cabi.cu sparse_plan): F holds no continuation byte 0x80..0xBF -- ASCII,
+// lead and invalid bytes always sit on a character boundary of the reference's decoder, so every candidate is a
+// legal start; the start on the leading NUL (tried per string in the prologue) is not accepting by itself, so no
+// start can "win with an empty span" and stop the search early; the prefix prefilter is absent or neutral
+// (prefix_mode 0/1; for mode 1 matched strings near bytes >= 0x80 are re-checked exactly, as in K2).
+// ---------------------------------------------------------------------------------------------
+struct SparseParams {
+    const uint16_t* table;      // anchored flag-bit table, class-compressed
+    const uint8_t* classmap;
+    const uint8_t* flags;
+    int table_words, row_shift, q0, start_nul;
+    // ASCII range r of the sweep filter, 7-bit bounds folded into SWAR addends
+    uint32_t add_lo[4];         // (0x80 - lo) * 0x01010101: bit 7 of (y + add_lo) <=> y >= lo   (NR = -1: value * 0x01010101)
+    uint32_t add_hi[4];         // (0x7F - hi) * 0x01010101: bit 7 of (y + add_hi) <=> y >  hi
+};
+// shared-memory extras of K2c, between the common header (tile_offset) and the tile:
+//   high-byte bitmap (one bit per 32-byte unit) | hit queue (unit indices) | survivor queue (positions) | 2 counters
+static constexpr int SPARSE_MAX_TILE = 48 * 1024;                      // staged bytes per tile (16-bit positions, queue sizes)
+static constexpr int SPARSE_HIGH_WORDS = SPARSE_MAX_TILE / 32 / 32 + 2;
+static constexpr int SPARSE_HITS = SPARSE_MAX_TILE / 32 + 32;
+static constexpr int SPARSE_SURVIVORS = 512;
+static constexpr int SPARSE_EXTRA = (SPARSE_HIGH_WORDS * 4 + SPARSE_HITS * 2 + SPARSE_SURVIVORS * 2 + 16 + 127) & ~127;
+
+// Sweep filter: bit 7 set in every byte of w that may be in F (callers mask with 0x80808080).  A superset is fine --
+// every candidate is confirmed by the first table step before anything else happens -- so bit 7 of the text byte is
+// ignored here (a byte >= 0x80 whose low bits fall into a range is a false candidate, in non-ASCII text only), and
+// with HIGH every byte >= 0x80 passes (F holds lead bytes: e.g. the overlong forms 0xC1 0xE0 0xF0 of an ASCII first
+// character, which the reference's structural decoder accepts).
+// NR = -1: F's ASCII part is ONE byte value (add_lo[0] holds it in all four bytes): the zero-byte test on w ^ value,
+//          three instructions per word (its false positives sit above a true hit, in the same word).
+template <int NR, bool HIGH>
+__device__ __forceinline__ uint32_t first_mask(const SparseParams& sp, uint32_t w) {
+    uint32_t m = 0;
+    if (NR == -1) {
+        const uint32_t x = w ^ sp.add_lo[0];
+        m = (x - 0x01010101u) & ~x;
+    } else {
+        const uint32_t y = w & 0x7F7F7F7Fu;
+#pragma unroll
+        for (int r = 0; r < NR; r++) m |= (y + sp.add_lo[r]) & ~(y + sp.add_hi[r]);
+    }
+    if (HIGH) m |= w;
+    return m;
+}
+// bits 7, 15, 23, 31 of m -> bits 0..3
+__device__ __forceinline__ uint32_t pack_byte_flags(uint32_t m) { return ((((m >> 7) & 0x01010101u) * 0x00204081u) >> 21) & 0xFu; }
+// does the anchored attempt that starts in state `st` before byte `pos` of the staged string [a, a+len) see a counted
+// accept?  run_attempt() reduced to what a boolean needs: 32-bit indices, out at the first accept.
+template <class TBL>
+__device__ __forceinline__ bool attempt_wins_smem(const Anchored& A, const TBL& T, uint32_t a, int len, uint32_t st, int pos) {
+    uint32_t w = st;
+    int seq = 0;
+    bool inter = false;
+    for (int j = pos; j <= len; j++) {
+        const uint32_t b = j < len ? lds_u8(a + j) : 0u;          // virtual trailing NUL at j == len
+        if (inter && (b & 0xC0) != 0x80) {                        // sequence broken: pending bytes replay as U+FFFF
+            const uint32_t f = __ldg(A.flags + (w & W_STATE));
+            if (f & ((SF_FAILACC1 << (j - seq)) - SF_FAILACC1)) return true;
+            inter = false;
+        }
+        const uint32_t nw = T.next(w & W_STATE, b);
+        if ((nw & W_INTER) && !inter) seq = j;
+        inter = (nw & W_INTER) != 0;
+        w = nw;
+        if (w & W_ACC) return true;
+        if ((w & W_STATE) == 0) return false;
+    }
+    return false;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+template <int KIND, int NR, bool HIGH>
+__global__ void __launch_bounds__(256, 4) k_in_sparse(KParams p, SparseParams sp, const uint8_t* __restrict__ buf,
+                                                      const int64_t* __restrict__ offsets, int64_t n, int64_t total,
+                                                      uint8_t* __restrict__ out, int spt, int cap, int64_t ntiles,
+                                                      int table_smem_bytes) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_cmap = smem + 16;
+    uint8_t* s_table = smem + 16 + 256;
+    int32_t* s_off = reinterpret_cast<int32_t*>(smem + 16 + 256 + table_smem_bytes);
+    uint8_t* s_res = reinterpret_cast<uint8_t*>(s_off + spt + 4);
+    uint8_t* s_extra = smem + tile_offset(table_smem_bytes, spt);
+    uint32_t* s_high = reinterpret_cast<uint32_t*>(s_extra);
+    uint16_t* s_hits = reinterpret_cast<uint16_t*>(s_extra + SPARSE_HIGH_WORDS * 4);
+    uint16_t* s_surv = s_hits + SPARSE_HITS;
+    int* s_cnt = reinterpret_cast<int*>(s_surv + SPARSE_SURVIVORS);      // [0] hits, [1] survivors
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* tile = s_extra + SPARSE_EXTRA;
+    const uint32_t mbar = smem_u32(smem);
+    KParams anch = p;                       // stage_table reads table / classmap / sizes from a KParams
+    anch.table = sp.table; anch.classmap = sp.classmap; anch.table_words = sp.table_words; anch.row_shift = sp.row_shift;
+    Table<KIND> T = stage_table<KIND>(anch, s_table, s_cmap);
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
+    const uint32_t tile_addr = smem_u32(tile);
+    const Anchored A{sp.flags, sp.start_nul, sp.q0};
+    const uint32_t FULL = 0xffffffffu;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const TileCtx c = load_tile(buf, offsets, n, total, t, spt, cap, tile, s_off, mbar, phase);
+        // ---- prologue, one string per thread: degenerate texts, unstaged strings, the start on the leading NUL ----
+        for (int i = threadIdx.x; i < c.count; i += blockDim.x) {
+            const int32_t r0 = s_off[i], r1 = s_off[i + 1];
+            bool r = false;
+            if (r1 == OFF_BEYOND) {
+                const int64_t o0 = __ldg(offsets + c.first + i), o1 = __ldg(offsets + c.first + i + 1);
+                r = eval_bool_slow<1>(p, buf + o0, o1 - o0);
+            } else {
+                const int len = r1 - r0;
+                const uint32_t a = tile_addr + (uint32_t)r0;
+                if (degenerate_text<1>(len, len ? lds_u8(a) : 0)) r = p.q0_accepting != 0;
+                else if (sp.start_nul != 0)
+                    r = run_attempt(A, T, FetchShared{a}, (int64_t)len, (uint32_t)sp.start_nul, 0, -1) >= 0;
+            }
+            s_res[i] = r ? 1 : 0;
+        }
+        __syncthreads();
+        if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        // ---- S: linear sweep of the staged bytes [lo, hi), 32 bytes per lane and step; units with a candidate are queued ----
+        const int lo = s_off[0];
+        const int staged_end = (int)(c.t1 - c.base);
+        const int hi = s_off[c.count] == OFF_BEYOND ? staged_end : s_off[c.count];
+        const int unit0 = lo >> 5, nunits = (hi + 31) >> 5;
+        for (int row = unit0 + warp * 32; row < nunits; row += 256) {
+            const int unit = row + lane;
+            const bool valid = unit < nunits;
+            uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+            if (valid) {
+                v0 = lds_v4(tile_addr + ((uint32_t)unit << 5));
+                v1 = lds_v4(tile_addr + ((uint32_t)unit << 5) + 16);
+            }
+            const uint32_t any = first_mask<NR, HIGH>(sp, v0.x) | first_mask<NR, HIGH>(sp, v0.y) |
+                                 first_mask<NR, HIGH>(sp, v0.z) | first_mask<NR, HIGH>(sp, v0.w) |
+                                 first_mask<NR, HIGH>(sp, v1.x) | first_mask<NR, HIGH>(sp, v1.y) |
+                                 first_mask<NR, HIGH>(sp, v1.z) | first_mask<NR, HIGH>(sp, v1.w);
+            const uint32_t hb = __ballot_sync(FULL, ((v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) & 0x80808080u) != 0);
+            if (lane == 0) s_high[(row - unit0) >> 5] = hb;
+            const bool hit = valid && (any & 0x80808080u) != 0;
+            const uint32_t hm = __ballot_sync(FULL, hit);
+            if (hm) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_cnt[0], __popc(hm));
+                base = __shfl_sync(FULL, base, 0);
+                if (hit) s_hits[base + __popc(hm & ((1u << lane) - 1))] = (uint16_t)unit;
+            }
+        }
+        __syncthreads();
+        // ---- C: confirm.  One queued unit per lane; its candidates are taken in rounds (round k = every lane's k-th
+        // candidate).  A candidate survives unless two bytes prove the start dead: the first step must stay alive, and
+        // then either the next text byte or the NUL that ends a string must.  Survivors (rare) are queued. ----
+        const int nhits = s_cnt[0];
+        for (int i0 = warp * 32; i0 < nhits; i0 += 256) {
+            const int i = i0 + lane;
+            uint32_t cand = 0;                           // one bit per byte of this lane's unit
+            int P = 0;
+            if (i < nhits) {
+                const int unit = s_hits[i];
+                const uint32_t ua = tile_addr + ((uint32_t)unit << 5);
+                const uint4 v0 = lds_v4(ua), v1 = lds_v4(ua + 16);
+                cand = pack_byte_flags(first_mask<NR, HIGH>(sp, v0.x)) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.y)) << 4) |
+                       (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.z)) << 8) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.w)) << 12) |
+                       (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.x)) << 16) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.y)) << 20) |
+                       (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.z)) << 24) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.w)) << 28);
+                P = unit << 5;
+                if (P < lo) cand &= 0xFFFFFFFFu << (lo - P);
+                if (P + 32 > hi) cand &= 0xFFFFFFFFu >> (P + 32 - hi);
+            }
+            while (__any_sync(FULL, cand != 0)) {
+                bool sv = false;
+                int pos = 0;
+                if (cand) {
+                    pos = P + __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    const uint32_t b = lds_u8(tile_addr + (uint32_t)pos);
+                    const uint32_t w1 = T.next((uint32_t)sp.q0, b);
+                    if (w1 & (W_ACC | W_INTER)) sv = true;
+                    else if (w1 & W_STATE) {
+                        const uint32_t b1 = lds_u8(tile_addr + (uint32_t)pos + 1);      // may belong to the next string
+                        sv = ((T.next(w1, b1) | T.next(w1, 0u)) & (W_STATE | W_ACC)) != 0;
+                    }
+                }
+                const uint32_t sm = __ballot_sync(FULL, sv);
+                if (sm) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_cnt[1], __popc(sm));
+                    base = __shfl_sync(FULL, base, 0);
+                    if (sv) {
+                        const int slot = base + __popc(sm & ((1u << lane) - 1));
+                        if (slot < SPARSE_SURVIVORS) s_surv[slot] = (uint16_t)pos;
+                        else {                                   // queue full: run this attempt right here
+                            int s = 0, sh = c.count;
+                            while (sh - s > 1) { const int mid = (s + sh) >> 1; if (s_off[mid] <= pos) s = mid; else sh = mid; }
+                            const int32_t r0 = s_off[s], r1 = s_off[s + 1];
+                            if (r1 != OFF_BEYOND && !(r1 - r0 == 1 && lds_u8(tile_addr + (uint32_t)pos) == 0x20) &&
+                                attempt_wins_smem(A, T, tile_addr + (uint32_t)r0, r1 - r0, (uint32_t)sp.q0, pos - r0))
+                                s_res[s] = 1;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- A: the surviving starts, one per thread: find the string, run the anchored attempt ----
+        const int nsurv = s_cnt[1] < SPARSE_SURVIVORS ? s_cnt[1] : SPARSE_SURVIVORS;
+        for (int i = threadIdx.x; i < nsurv; i += blockDim.x) {
+            const int pos = s_surv[i];
+            int s = 0, sh = c.count;                     // largest s with s_off[s] <= pos  (pos >= lo = s_off[0])
+            while (sh - s > 1) {
+                const int mid = (s + sh) >> 1;
+                if (s_off[mid] <= pos) s = mid; else sh = mid;
+            }
+            const int32_t r0 = s_off[s], r1 = s_off[s + 1];
+            if (r1 == OFF_BEYOND || s_res[s]) continue;                  // not fully staged: answered by the prologue
+            if (r1 - r0 == 1 && lds_u8(tile_addr + (uint32_t)pos) == 0x20) continue;   // a lone blank never reaches the loop
+            if (attempt_wins_smem(A, T, tile_addr + (uint32_t)r0, r1 - r0, (uint32_t)sp.q0, pos - r0)) s_res[s] = 1;
+        }
+        __syncthreads();                 // results and high-byte bitmap complete; everyone is done with the tile text
+        for (int i = threadIdx.x; i < c.count; i += blockDim.x) {
+            uint8_t r = s_res[i];
+            if (r && p.prefix_mode == 1) {
+                const int32_t r0 = s_off[i], r1 = s_off[i + 1];
+                if (r1 != OFF_BEYOND && r1 > r0) {       // (unstaged strings went through the exact slow path already)
+                    bool high = false;
+                    for (int u = (r0 >> 5) - unit0; u <= ((r1 - 1) >> 5) - unit0; u++)
+                        high |= (s_high[u >> 5] >> (u & 31)) & 1;
+                    if (high) r = recheck_in_with_prefix(p, buf + (c.base + r0), r1 - r0) ? 1 : 0;
+                }
+            }
+            out[c.first + i] = r;
+        }
+        __syncthreads();                 // before the next tile overwrites offsets / results / text
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K2p: K2 with length-balanced lanes.  A table lookup costs one shared-memory wavefront per warp instruction no
 // matter how many of the 32 lanes are still walking, so in K2 a warp whose strings are 64..256 bytes long wastes
 // a third of its lookups on lanes that have already finished.  Here a CTA of 128 threads takes a tile of up to

@@ -84,6 +84,13 @@ typedef struct fx_pattern_info {
     int32_t direct;           /* 1: last launch used the 256-column table */
     int32_t prefix_mode;      /* `.in.` with an extracted prefix: 0 none, 1 prefilter is result-neutral for ASCII
                                  text (texts with bytes >= 0x80 are re-checked exactly), 2 always replayed exactly */
+    int32_t sparse;           /* `.in.`: 1 when ragged batches run on the sparse-start kernel (the set F of first bytes
+                                 that can begin a match is small) */
+    int32_t sparse_ranges;    /* ASCII part of F as byte ranges [sparse_lo[i], sparse_hi[i]] */
+    int32_t sparse_lo[4];
+    int32_t sparse_hi[4];
+    int32_t sparse_high;      /* 1: F also holds bytes >= 0xC0 (lead bytes; every such byte is tried as a start) */
+    int32_t sparse_used;      /* 1: the last ragged `.in.` launch used the sparse-start kernel */
 } fx_pattern_info;
 
 /* ---- host-only ------------------------------------------------------------------------- */

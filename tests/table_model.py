@@ -238,6 +238,46 @@ class Model:
         return self.anch.regex(s)
 
 
+class SparseIn:
+    """k_in_sparse: `.in.` as "some candidate start wins" -- candidates are the leading NUL and the positions whose
+    byte passes the sweep filter (ASCII ranges, optionally every byte >= 0xC0) and survives the first table step"""
+
+    def __init__(self, pattern_obj):
+        inf = pattern_obj.info()
+        assert inf["sparse"]
+        self.ranges = list(zip(inf["sparse_lo"], inf["sparse_hi"]))
+        self.high = bool(inf["sparse_high"])
+        self.prefix_mode = inf["prefix_mode"]
+        self.q0_accepting = pattern_obj.tables()["q0_accepting"]
+        self._anch_pat = fx.Pattern(pattern_obj.pattern, "regex")
+        self.anch = Anchored(self._anch_pat, False)
+
+    def sweep(self, b):
+        return any(lo <= b <= hi for lo, hi in self.ranges) or (self.high and b >= 0xC0)
+
+    def boolean(self, s: bytes):
+        if len(s) == 0 or s == b" ":
+            return self.q0_accepting
+        a, t = self.anch, self.anch.t
+        r = False
+        if t["start_nul"] != 0:
+            assert not (t["flags"][t["start_nul"]] & SF_ACC)
+            r = a.attempt(s, t["start_nul"], 0, -1) >= 0
+        for pos, b in enumerate(s):
+            if r:
+                break
+            if not self.sweep(b):
+                assert (a.nxt(t["q0"], b) & (W_STATE | W_ACC)) == 0   # the filter never drops a byte of F
+                continue
+            if (a.nxt(t["q0"], b) & (W_STATE | W_ACC)) == 0:
+                continue
+            r = a.attempt(s, t["q0"], pos, -1) >= 0
+        if r and self.prefix_mode == 1 and any(b >= 0x80 for b in s):
+            f, to = a.including_exact(s)
+            r = f > 0 and to > 0
+        return r
+
+
 class SpanLinear:
     """span_linear_smem (K3f): forward ordered-groups automaton, then the reverse automaton"""
 

@@ -255,6 +255,43 @@ def test_invalid_pattern_and_wrong_op_errors():
     assert fx.op_in(b"(a", b"a") is False and fx.op_match(b"a)", b"a") is False
 
 
+def test_sparse_start_kernel(monkeypatch):
+    """K2c (linear sweep + candidate starts) against the oracle, and against K2 with the sparse path switched off"""
+    monkeypatch.setenv("FX_SPARSE_MAX_FIRST", "128")      # every eligible pattern, however dense its first-byte set
+    rng = np.random.default_rng(17)
+    pieces = [b"a", b"z", b" ", b"f", b"foo", b"bar", b"foobar", "あ".encode(), "α".encode(), b"\x80", b"\xbf", b"\xc3", b"\xe3\x81",
+              b"\xff", b"\xc0\x80", b"\xc1\xa6", b"\xe0\x81\xa6", b"\xf0\x80\x81\xa6", b"\n", b"\r\n", b"\r", b"\x00", b"7", b"-",
+              b"ERROR", b"timeout=", b"x", b"h\xc3\xa9llo"]
+    s1 = [b"".join(pieces[i] for i in rng.integers(0, len(pieces), size=int(k))) for k in rng.integers(0, 30, size=6000)]
+    s2 = [b"", b" ", b"a", b"", b"", b"foobar", b"x" * 5000 + b"foobaz", b"y" * 70000 + b"foobar", b"foobar" * 3, b"",
+          bytes(rng.integers(0, 256, size=300, dtype=np.uint8)), b"\x00", b"\xe3\x81", b"fooba", b"", b"f", b"\nfoobar", b"foobar\n"]
+    s2 += [bytes(rng.integers(0x20, 0x7F, size=int(k), dtype=np.uint8)) for k in rng.integers(0, 400, size=3000)]
+    s2 += [b"f" * 3000, b"", b""]
+    sets = [pack(s1), pack(s2), synth.gen_c2(30000)]
+    used = 0
+    for pat in [b"foo(bar|baz)", b"^foo", b"a*", rb"\d{3}-\d{4}", b"[a-z]+r", b"x$", rb"^ERROR.*timeout=\d+$", "héllo|x".encode(),
+                "[ぁ-ん]+a".encode(), b"(|^)a", b"f.*r$", b"(foo|bar)+", rb"\s\S+", b"^", b"$", b"f{2,}", b"z?y", b"(a|b)*a(a|b){3}"]:
+        monkeypatch.setenv("FX_SPARSE", "1")
+        p = fx.Pattern(pat, "in")
+        for buf, off in sets:
+            got = p.in_batch(buf, off)
+            info = p.info()
+            assert info["sparse_used"] == info["sparse"]
+            exp = oracle_bool(pat, "in", buf, offsets=off)
+            assert np.array_equal(got, exp), (pat, np.nonzero(got != exp)[0][:10])
+        used += info["sparse_used"]
+        if info["sparse"]:
+            monkeypatch.setenv("FX_SPARSE", "0")
+            buf, off = sets[0]
+            assert np.array_equal(p.in_batch(buf, off), oracle_bool(pat, "in", buf, offsets=off))
+            assert p.info()["sparse_used"] == 0
+    assert used >= 10
+    monkeypatch.setenv("FX_SPARSE", "1")
+    monkeypatch.delenv("FX_SPARSE_MAX_FIRST")
+    assert fx.Pattern(b"foo(bar|baz)", "in").info()["sparse"] == 1     # the C2 pattern takes this path by default
+    assert fx.Pattern(rb"\w+@\w+", "in").info()["sparse"] == 0
+
+
 @pytest.mark.parametrize("form", ["1", "2"])
 def test_alternative_ragged_forms(monkeypatch, form):
     """K2s (streaming windows, form 1) and K2p (length-balanced pairs, form 2) against the oracle"""

@@ -13,7 +13,7 @@ import pytest
 import forgex_b200 as fx
 from forgex_b200 import _lib
 from tests import oracle_lib as O
-from tests.table_model import Model, SpanLinear
+from tests.table_model import Model, SpanLinear, SparseIn
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 OPS = {"match": "match", "in": "in", "regex": "regex"}
@@ -70,8 +70,22 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
 
 
-def test_reference_api_vectors_through_product_tables():
-    bad, capped = [], 0
+_sparse_cache = {}
+
+
+def sparse_answer(pattern, text):
+    """the `.in.` answer of the sparse-start kernel's model, or None when the pattern does not take that path"""
+    p, _ = model_for(pattern, "in")
+    if p.status != 0 or not p.info()["sparse"]:
+        return None
+    if pattern not in _sparse_cache:
+        _sparse_cache[pattern] = SparseIn(p)
+    return _sparse_cache[pattern].boolean(text)
+
+
+def test_reference_api_vectors_through_product_tables(monkeypatch):
+    monkeypatch.setenv("FX_SPARSE_MAX_FIRST", "128")
+    bad, capped, nsparse = [], 0, 0
     for v in load("api"):
         pat, text = bytes.fromhex(v["pattern"]), bytes.fromhex(v["text"])
         got = product_answer(v["kind"], pat, text)
@@ -86,8 +100,14 @@ def test_reference_api_vectors_through_product_tables():
             lin = linear_answer(pat, text)
             if lin is not None and lin != exp:
                 bad.append("%s regex(linear) %r -> %r, expected %r" % (v["src"], pat, lin, exp))
+        if v["kind"] == "in":
+            sp = sparse_answer(pat, text)
+            nsparse += sp is not None
+            if sp is not None and sp != exp:
+                bad.append("%s in(sparse) %r -> %r, expected %r" % (v["src"], pat, sp, exp))
     assert not bad, "%d vectors fail:\n%s" % (len(bad), "\n".join(bad[:40]))
     assert capped == 4
+    assert nsparse > 50
 
 
 def f_eq(a, b):
@@ -164,10 +184,12 @@ def gen_text(rng):
 
 
 @pytest.mark.parametrize("seed", range(12))
-def test_generated_patterns_match_oracle(seed):
+def test_generated_patterns_match_oracle(seed, monkeypatch):
+    monkeypatch.setenv("FX_SPARSE_MAX_FIRST", "128")    # let every eligible pattern through the sparse-start model
     rng = random.Random(1000 + seed)
     bad = []
     checked = 0
+    nsparse = 0
     for _ in range(120):
         pat = gen_pattern(rng).encode()
         texts = [gen_text(rng) for _ in range(12)] + [b"", b" "]
@@ -188,6 +210,8 @@ def test_generated_patterns_match_oracle(seed):
                 continue  # cap
             m = Model(p, use_direct=rng.random() < 0.5)
             span = SpanLinear(p) if kind == "regex" and p.span_tables() is not None else None
+            sparse = SparseIn(p) if kind == "in" and p.info()["sparse"] else None
+            nsparse += sparse is not None
             for t in texts:
                 checked += 1
                 if kind == "regex":
@@ -204,5 +228,8 @@ def test_generated_patterns_match_oracle(seed):
                     got = m.boolean(t)
                     if o < 0 or bool(o) != got:
                         bad.append("%s %r on %r: product %r oracle %r" % (kind, pat, t, got, o))
+                    if sparse is not None and sparse.boolean(t) != bool(o):
+                        bad.append("in(sparse) %r on %r: product %r oracle %r" % (pat, t, sparse.boolean(t), o))
     assert not bad, "%d mismatches (of %d):\n%s" % (len(bad), checked, "\n".join(bad[:30]))
     assert checked > 1000
+    assert nsparse > 5
