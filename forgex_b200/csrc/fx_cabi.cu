@@ -443,22 +443,59 @@ int launch_stream_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int
     return cuda_status(cudaGetLastError());
 }
 
-template <int KIND, int NR, bool HIGH>
-int launch_sparse_t(fx_pattern* p, const Plan& pl, const SparseParams& sp, int table_bytes, const uint8_t* buf,
+// K2c tiling: every warp stages its own tile; 8 warp regions + the table fill a CTA's share of shared memory
+struct SparseTiling {
+    int spt, cap, table_smem;
+    int64_t ntiles;
+    size_t smem;
+};
+
+SparseTiling make_sparse_tiling(int table_bytes, int64_t n, int64_t total, int ctas) {
+    SparseTiling t;
+    int64_t avg = n > 0 ? (total + n - 1) / n : 1;
+    if (avg < 1) avg = 1;
+    t.table_smem = (table_bytes + 15) & ~15;
+    const int head = sparse_shared_head(t.table_smem);
+    int per_warp = (((227 * 1024) / ctas - 1024 - head) / 8) & ~127;
+    if (per_warp < 2048) per_warp = 2048;
+    int cap = per_warp < SPARSE_MAX_CAP ? per_warp : SPARSE_MAX_CAP, spt = 1;
+    for (;;) {
+        int64_t want = ((int64_t)cap * 4 / 5) / avg;       // expect the tile to fill ~80 % of the staged capacity
+        spt = (int)(want < 1 ? 1 : want > 256 ? 256 : want);
+        if (cap <= 1024 || sparse_layout(spt, cap).warp_bytes <= per_warp) break;
+        cap -= 128;
+    }
+    spt = env_int("FX_TILE_STRINGS", spt);
+    if (spt > 256) spt = 256;
+    t.spt = spt;
+    t.cap = cap;
+    t.ntiles = (n + spt - 1) / spt;
+    t.smem = (size_t)head + 8 * (size_t)sparse_layout(spt, cap).warp_bytes;
+    return t;
+}
+
+template <int KIND, int NR, bool HIGH, int MINB>
+int launch_sparse_b(fx_pattern* p, const Plan& pl, const SparseParams& sp, int table_bytes, const uint8_t* buf,
                     const int64_t* off, int64_t n, int64_t total, uint8_t* out, cudaStream_t s) {
-    auto kern = k_in_sparse<KIND, NR, HIGH>;
-    Plan tp = pl;
-    tp.table_bytes = KIND == 3 ? 0 : table_bytes;
-    Tiling t = make_tiling(tp, n, total, SPARSE_EXTRA, SPARSE_MAX_TILE - 128);
+    auto kern = k_in_sparse<KIND, NR, HIGH, MINB>;
+    SparseTiling t = make_sparse_tiling(KIND == 3 ? 0 : table_bytes, n, total, MINB);
     int bps = 0;
     int rc = occupancy_grid(kern, 256, t.smem, p->dev.sm_count, bps);
     if (rc) return rc;
     long long cap = (long long)p->dev.sm_count * bps;
-    int grid = (int)(t.ntiles < cap ? t.ntiles : cap);
+    long long want = (t.ntiles + 7) / 8;
+    int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
     kern<<<grid, 256, t.smem, s>>>(pl.kp, sp, buf, off, n, total, out, t.spt, t.cap, t.ntiles, t.table_smem);
     g_launches++;
     return cuda_status(cudaGetLastError());
+}
+
+template <int KIND, int NR, bool HIGH>
+int launch_sparse_t(fx_pattern* p, const Plan& pl, const SparseParams& sp, int table_bytes, const uint8_t* buf,
+                    const int64_t* off, int64_t n, int64_t total, uint8_t* out, cudaStream_t s) {
+    if (env_int("FX_SPARSE_CTAS", 4) == 3) return launch_sparse_b<KIND, NR, HIGH, 3>(p, pl, sp, table_bytes, buf, off, n, total, out, s);
+    return launch_sparse_b<KIND, NR, HIGH, 4>(p, pl, sp, table_bytes, buf, off, n, total, out, s);
 }
 
 template <int KIND, bool HIGH>
@@ -511,7 +548,7 @@ int launch_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, int64_t
     if (rc) return rc;
     int generic = generic_mode(pl, OP);
     p->last_sparse = 0;
-    if (OP == 1 && !generic && p->sparse && env_int("FX_SPARSE", 1)) {      // sparse starts (K2c)
+    if (OP == 1 && !generic && p->sparse && n < (1ll << 31) && env_int("FX_SPARSE", 1)) {      // sparse starts (K2c)
         p->last_sparse = 1;
         return launch_sparse(p, pl, buf, off, n, total, out, s);
     }

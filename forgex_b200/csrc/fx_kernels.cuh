@@ -688,22 +688,27 @@ __global__ void __launch_bounds__(256, 4) k_bool_ragged(KParams p, const uint8_t
 // `.in.` is true when SOME start of the brute-force search wins (api_internal_m.F90:108-155).  A start whose first
 // byte kills the anchored automaton cannot win, so when the set F of first bytes that survive the step out of q0 is
 // small (a few byte ranges: 'f' for foo(bar|baz); NUL/LF/CR for ^ERROR...), almost every position of the text is
-// ruled out by a compare.  The kernel therefore does not walk the strings at all.  Per tile, three phases, each with
-// every lane doing the same work whatever the string lengths are:
-//   S  sweep: the warps read the staged tile LINEARLY, 32 bytes per lane and step out of two conflict-free LDS.128,
+// ruled out by a compare.  The kernel therefore does not walk the strings at all, and it has no block-wide step:
+// every WARP owns its tiles (a few KB of consecutive strings, staged by its own TMA bulk copy on its own mbarrier),
+// so warps never wait for each other and the 32 warps of an SM hide each other's load latency.  Per tile:
+//   S  sweep: the lanes read the staged tile LINEARLY, 32 bytes per lane and step out of two conflict-free LDS.128,
 //      and test them against F with SWAR arithmetic (3-4 integer instructions per 4 bytes); 32-byte units that hold
-//      a candidate go into a CTA-wide queue;
+//      a candidate are queued;
 //   C  confirm: one queued unit per lane; each candidate takes its first table step and, unless that already accepts
 //      or enters a multi-byte sequence, the second one (with the next text byte, and with the NUL that would end the
-//      string there).  Two bytes kill almost every candidate; the survivors' positions go into a second queue;
-//   A  attempts: one survivor per thread: binary search over the staged offsets for its string, then the anchored
-//      attempt -- the reference's own inner loop, on the anchored flag-bit table -- until the first counted accept.
+//      string there).  Two bytes kill almost every candidate;
+//   A  attempts: survivors go to a queue that outlives the tile; whenever 32 are waiting the 32 lanes run them side
+//      by side from global memory (the bytes are in L2): binary search over the tile's offsets for the string, then
+//      the anchored attempt -- the reference's own inner loop, on the anchored flag-bit table -- until the first
+//      counted accept, which sets the string's result.
+// The per-string part (degenerate texts, the start on the leading NUL, strings too long to stage) is one string per
+// lane and writes the tile's results before any attempt of that tile can run.
 //
-// Preconditions (checked on the host, fx_cabi.cu sparse_plan): F holds no continuation byte 0x80..0xBF -- ASCII,
-// lead and invalid bytes always sit on a character boundary of the reference's decoder, so every candidate is a
-// legal start; the start on the leading NUL (tried per string in the prologue) is not accepting by itself, so no
-// start can "win with an empty span" and stop the search early; the prefix prefilter is absent or neutral
-// (prefix_mode 0/1; for mode 1 matched strings near bytes >= 0x80 are re-checked exactly, as in K2).
+// Preconditions (checked on the host, fx_cabi.cu sparse_first_set): F holds no continuation byte 0x80..0xBF --
+// ASCII, lead and invalid bytes always sit on a character boundary of the reference's decoder, so every candidate is
+// a legal start; the start on the leading NUL is not accepting by itself, so no start can "win with an empty span"
+// and stop the search early; the prefix prefilter is absent or neutral (prefix_mode 0/1; for mode 1 a winning string
+// from a tile that holds bytes >= 0x80 is re-checked exactly, as in K2).
 // ---------------------------------------------------------------------------------------------
 struct SparseParams {
     const uint16_t* table;      // anchored flag-bit table, class-compressed
@@ -714,13 +719,21 @@ struct SparseParams {
     uint32_t add_lo[4];         // (0x80 - lo) * 0x01010101: bit 7 of (y + add_lo) <=> y >= lo   (NR = -1: value * 0x01010101)
     uint32_t add_hi[4];         // (0x7F - hi) * 0x01010101: bit 7 of (y + add_hi) <=> y >  hi
 };
-// shared-memory extras of K2c, between the common header (tile_offset) and the tile:
-//   high-byte bitmap (one bit per 32-byte unit) | hit queue (unit indices) | survivor queue (positions) | 2 counters
-static constexpr int SPARSE_MAX_TILE = 48 * 1024;                      // staged bytes per tile (16-bit positions, queue sizes)
-static constexpr int SPARSE_HIGH_WORDS = SPARSE_MAX_TILE / 32 / 32 + 2;
-static constexpr int SPARSE_HITS = SPARSE_MAX_TILE / 32 + 32;
-static constexpr int SPARSE_SURVIVORS = 512;
-static constexpr int SPARSE_EXTRA = (SPARSE_HIGH_WORDS * 4 + SPARSE_HITS * 2 + SPARSE_SURVIVORS * 2 + 16 + 127) & ~127;
+
+// shared memory of K2c: classmap 256 | table | pad to 128 | 8 warp regions of `warp_bytes`:
+//   [0,16) mbarrier | offsets (spt+4) x int32 | hit queue (cap/32 + 8) x u16 | pad to 8 | survivor queue 64 x uint2 |
+//   pad to 128 | tile (cap + 64)
+static constexpr int SPARSE_MAX_CAP = 60 * 1024;          // 16-bit tile positions
+struct SparseLayout { int off_hits, off_surv, off_tile, warp_bytes; };
+__host__ __device__ __forceinline__ SparseLayout sparse_layout(int spt, int cap) {
+    SparseLayout L;
+    L.off_hits = 16 + (spt + 4) * 4;
+    L.off_surv = (L.off_hits + ((cap >> 5) + 8) * 2 + 7) & ~7;
+    L.off_tile = (L.off_surv + 64 * 8 + 127) & ~127;
+    L.warp_bytes = (L.off_tile + cap + 64 + 127) & ~127;
+    return L;
+}
+__host__ __device__ __forceinline__ int sparse_shared_head(int table_smem_bytes) { return (256 + table_smem_bytes + 127) & ~127; }
 
 // Sweep filter: bit 7 set in every byte of w that may be in F (callers mask with 0x80808080).  A superset is fine --
 // every candidate is confirmed by the first table step before anything else happens -- so bit 7 of the text byte is
@@ -745,15 +758,16 @@ __device__ __forceinline__ uint32_t first_mask(const SparseParams& sp, uint32_t 
 }
 // bits 7, 15, 23, 31 of m -> bits 0..3
 __device__ __forceinline__ uint32_t pack_byte_flags(uint32_t m) { return ((((m >> 7) & 0x01010101u) * 0x00204081u) >> 21) & 0xFu; }
-// does the anchored attempt that starts in state `st` before byte `pos` of the staged string [a, a+len) see a counted
-// accept?  run_attempt() reduced to what a boolean needs: 32-bit indices, out at the first accept.
-template <class TBL>
-__device__ __forceinline__ bool attempt_wins_smem(const Anchored& A, const TBL& T, uint32_t a, int len, uint32_t st, int pos) {
+
+// does the anchored attempt that starts in state `st` before byte `pos` of a string of `len` bytes see a counted
+// accept?  run_attempt() reduced to what a boolean needs: out at the first accept.
+template <class TBL, class FETCH>
+__device__ __forceinline__ bool attempt_wins(const Anchored& A, const TBL& T, FETCH fetch, int len, uint32_t st, int pos) {
     uint32_t w = st;
     int seq = 0;
     bool inter = false;
     for (int j = pos; j <= len; j++) {
-        const uint32_t b = j < len ? lds_u8(a + j) : 0u;          // virtual trailing NUL at j == len
+        const uint32_t b = j < len ? fetch(j) : 0u;               // virtual trailing NUL at j == len
         if (inter && (b & 0xC0) != 0x80) {                        // sequence broken: pending bytes replay as U+FFFF
             const uint32_t f = __ldg(A.flags + (w & W_STATE));
             if (f & ((SF_FAILACC1 << (j - seq)) - SF_FAILACC1)) return true;
@@ -774,104 +788,204 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
     return v;
 }
 
-template <int KIND, int NR, bool HIGH>
-__global__ void __launch_bounds__(256, 4) k_in_sparse(KParams p, SparseParams sp, const uint8_t* __restrict__ buf,
-                                                      const int64_t* __restrict__ offsets, int64_t n, int64_t total,
-                                                      uint8_t* __restrict__ out, int spt, int cap, int64_t ntiles,
-                                                      int table_smem_bytes) {
+// Deferred work of K2c: `count` (<= 32) queue entries {tile, payload}, one per lane, everything read from global memory.
+//   payload = position relative to the tile's first byte (bits 0..27) | kind << 28 | tile holds bytes >= 0x80 << 31
+//   kind 0  a surviving start: find its string (binary search over the tile's offsets), run the anchored attempt
+//   kind 1  string number `position` of the tile was too long to stage: the whole wrapper from global memory
+//   kind 2  string number `position` won from the leading NUL in a tile with bytes >= 0x80: exact prefix replay
+// Out of line on purpose, and called only from the outer loop of the kernel: a call inside the sweep / confirm loops
+// makes the compiler keep their whole state in callee-saved registers and spill it (measured: 200 bytes per thread).
+static constexpr uint32_t SPARSE_KIND_SHIFT = 28, SPARSE_POS_MASK = 0x0FFFFFFFu;
+template <int KIND>
+__device__ __noinline__ void sparse_run_deferred(const KParams& p, const SparseParams& sp, const Table<KIND>& T,
+                                                 const uint2* s_queue, int count, int spt, int64_t n,
+                                                 const int64_t* __restrict__ offsets, const uint8_t* __restrict__ buf,
+                                                 uint8_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const Anchored A{sp.flags, sp.start_nul, sp.q0};
+    __syncwarp();
+    if (lane < count) {
+        const uint2 e = s_queue[lane];
+        const int64_t first = (int64_t)e.x * spt;
+        const int64_t* off = offsets + first;
+        const uint32_t kind = (e.y >> SPARSE_KIND_SHIFT) & 7u, val = e.y & SPARSE_POS_MASK;
+        if (kind == 0) {
+            const int cnt = (int)((n - first) < spt ? (n - first) : spt);
+            const int64_t gpos = __ldg(off) + (int64_t)val;
+            int s = 0, sh = cnt;                                   // largest s with off[s] <= gpos
+            while (sh - s > 1) {
+                const int mid = (s + sh) >> 1;
+                if (__ldg(off + mid) <= gpos) s = mid; else sh = mid;
+            }
+            const int64_t o0 = __ldg(off + s), o1 = __ldg(off + s + 1);
+            const uint8_t* str = buf + o0;
+            if (!(o1 - o0 == 1 && __ldg(str) == 0x20)) {           // a lone blank never reaches the loop
+                bool win = attempt_wins(A, T, FetchGlobal{str}, (int)(o1 - o0), (uint32_t)sp.q0, (int)(gpos - o0));
+                if (win && p.prefix_mode == 1 && (e.y >> 31)) win = recheck_in_with_prefix(p, str, o1 - o0);
+                if (win) out[first + s] = 1;
+            }
+        } else {
+            const int64_t o0 = __ldg(off + val), o1 = __ldg(off + val + 1);
+            const bool r = kind == 1 ? eval_bool_slow<1>(p, buf + o0, o1 - o0) : recheck_in_with_prefix(p, buf + o0, o1 - o0);
+            out[first + val] = r ? 1 : 0;
+        }
+    }
+    __syncwarp();
+}
+
+template <int KIND, int NR, bool HIGH, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_in_sparse(KParams p, SparseParams sp, const uint8_t* __restrict__ buf,
+                                                         const int64_t* __restrict__ offsets, int64_t n, int64_t total,
+                                                         uint8_t* __restrict__ out, int spt, int cap, int64_t ntiles,
+                                                         int table_smem_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* s_cmap = smem + 16;
-    uint8_t* s_table = smem + 16 + 256;
-    int32_t* s_off = reinterpret_cast<int32_t*>(smem + 16 + 256 + table_smem_bytes);
-    uint8_t* s_res = reinterpret_cast<uint8_t*>(s_off + spt + 4);
-    uint8_t* s_extra = smem + tile_offset(table_smem_bytes, spt);
-    uint32_t* s_high = reinterpret_cast<uint32_t*>(s_extra);
-    uint16_t* s_hits = reinterpret_cast<uint16_t*>(s_extra + SPARSE_HIGH_WORDS * 4);
-    uint16_t* s_surv = s_hits + SPARSE_HITS;
-    int* s_cnt = reinterpret_cast<int*>(s_surv + SPARSE_SURVIVORS);      // [0] hits, [1] survivors
+    uint8_t* s_cmap = smem;
+    uint8_t* s_table = smem + 256;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* tile = s_extra + SPARSE_EXTRA;
-    const uint32_t mbar = smem_u32(smem);
+    const SparseLayout L = sparse_layout(spt, cap);
+    uint8_t* region = smem + sparse_shared_head(table_smem_bytes) + warp * L.warp_bytes;
+    int32_t* s_off = reinterpret_cast<int32_t*>(region + 16);
+    uint16_t* s_hits = reinterpret_cast<uint16_t*>(region + L.off_hits);
+    uint2* s_queue = reinterpret_cast<uint2*>(region + L.off_surv);
+    uint8_t* tile = region + L.off_tile;
+    const uint32_t mbar = smem_u32(region);
     KParams anch = p;                       // stage_table reads table / classmap / sizes from a KParams
     anch.table = sp.table; anch.classmap = sp.classmap; anch.table_words = sp.table_words; anch.row_shift = sp.row_shift;
     Table<KIND> T = stage_table<KIND>(anch, s_table, s_cmap);
-    if (threadIdx.x == 0) mbar_init(mbar, 1);
-    __syncthreads();
-    uint32_t phase = 0;
+    if (lane == 0) mbar_init(mbar, 1);
+    __syncthreads();                        // the only block-wide step: the table is staged
     const uint32_t tile_addr = smem_u32(tile);
     const Anchored A{sp.flags, sp.start_nul, sp.q0};
     const uint32_t FULL = 0xffffffffu;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const TileCtx c = load_tile(buf, offsets, n, total, t, spt, cap, tile, s_off, mbar, phase);
-        // ---- prologue, one string per thread: degenerate texts, unstaged strings, the start on the leading NUL ----
-        for (int i = threadIdx.x; i < c.count; i += blockDim.x) {
-            const int32_t r0 = s_off[i], r1 = s_off[i + 1];
-            bool r = false;
-            if (r1 == OFF_BEYOND) {
-                const int64_t o0 = __ldg(offsets + c.first + i), o1 = __ldg(offsets + c.first + i + 1);
-                r = eval_bool_slow<1>(p, buf + o0, o1 - o0);
-            } else {
-                const int len = r1 - r0;
-                const uint32_t a = tile_addr + (uint32_t)r0;
-                if (degenerate_text<1>(len, len ? lds_u8(a) : 0)) r = p.q0_accepting != 0;
-                else if (sp.start_nul != 0)
-                    r = run_attempt(A, T, FetchShared{a}, (int64_t)len, (uint32_t)sp.start_nul, 0, -1) >= 0;
+    const int nt = (int)ntiles;             // the host keeps n (hence ntiles) below 2^31
+
+    // The warp's state machine.  The inner loop (no calls) advances it until 32 deferred entries are waiting or the
+    // tiles are used up; the outer loop runs the deferred entries and comes back.
+    enum { ST_NEW = 0, ST_STRINGS = 1, ST_CONFIRM = 2 };
+    int t = blockIdx.x * 8 + warp;          // tile in progress / next tile
+    int st = ST_NEW, it = 0;                // it: next string (ST_STRINGS) or next queued unit (ST_CONFIRM)
+    int count = 0, lo = 0, hi = 0, qn = 0, sqn = 0;
+    bool high = false;
+    uint32_t phase = 0, cand = 0;           // cand: candidate bytes of this lane's unit still to be confirmed
+    int P = 0;                              // tile position of that unit
+
+    auto push = [&](bool yes, uint32_t payload) {                    // warp-wide append to the deferred queue
+        const uint32_t m = __ballot_sync(FULL, yes);
+        if (yes) s_queue[sqn + __popc(m & ((1u << lane) - 1))] = make_uint2((uint32_t)t, payload | (high ? 0x80000000u : 0u));
+        sqn += __popc(m);
+    };
+
+    for (;;) {
+        for (;;) {
+            if (sqn >= 32) break;
+            if (st == ST_NEW) {
+                if (t >= nt) break;
+                // ---- stage the tile: strings [first, first + count), up to `cap` bytes of them ----
+                const int64_t first = (int64_t)t * spt;
+                count = (int)((n - first) < spt ? (n - first) : spt);
+                const int64_t t0 = __ldg(offsets + first), tend = __ldg(offsets + first + count);
+                const int64_t t1 = tend - t0 > cap ? t0 + cap : tend;
+                const uintptr_t gbuf = reinterpret_cast<uintptr_t>(buf);
+                const uintptr_t g0 = gbuf + (uintptr_t)t0;
+                lo = (int)(g0 & 15);                               // tile[lo] = byte t0 (the bulk source is 16-byte aligned)
+                const int64_t base = t0 - lo;
+                const uintptr_t gsrc = g0 & ~(uintptr_t)15;
+                uintptr_t gcopy_end = (gbuf + (uintptr_t)t1 + 15) & ~(uintptr_t)15;
+                const uintptr_t gsafe_end = (gbuf + (uintptr_t)total) & ~(uintptr_t)15;   // never bulk-read past the last whole 16-byte block
+                if (gcopy_end > gsafe_end) gcopy_end = gsafe_end;
+                const uint32_t bulk = gcopy_end > gsrc ? (uint32_t)(gcopy_end - gsrc) : 0u;
+                __syncwarp();                                      // every lane is done with the previous tile
+                if (bulk && lane == 0) {
+                    mbar_expect_tx(mbar, bulk);
+                    bulk_g2s(tile_addr, reinterpret_cast<const void*>(gsrc), bulk, mbar);
+                }
+                for (int64_t x = (int64_t)(gsrc + bulk) - (int64_t)gbuf + lane; x < t1; x += 32)   // < 16 bytes at the very end of the buffer
+                    if (x >= t0) tile[x - base] = __ldg(buf + x);
+                for (int i = lane; i <= count; i += 32) {          // overlaps with the bulk copy in flight
+                    const int64_t o = __ldg(offsets + first + i);
+                    s_off[i] = o > t1 ? OFF_BEYOND : (int32_t)(o - base);
+                }
+                if (bulk) { mbar_wait(mbar, phase); phase ^= 1; }
+                hi = (int)(t1 - base);
+                const int nunits = (hi + 31) >> 5;
+                if (hi + lane < (nunits << 5)) tile[hi + lane] = 0;    // the sweep reads whole 32-byte units: no stale bytes
+                __syncwarp();
+                // ---- S: linear sweep of the staged bytes [lo, hi) ----
+                qn = 0;
+                uint32_t tile_high = 0;
+                for (int row = 0; row < nunits; row += 32) {
+                    const int unit = row + lane;
+                    const bool valid = unit < nunits;
+                    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+                    if (valid) {
+                        v0 = lds_v4(tile_addr + ((uint32_t)unit << 5));
+                        v1 = lds_v4(tile_addr + ((uint32_t)unit << 5) + 16);
+                    }
+                    const uint32_t any = first_mask<NR, HIGH>(sp, v0.x) | first_mask<NR, HIGH>(sp, v0.y) |
+                                         first_mask<NR, HIGH>(sp, v0.z) | first_mask<NR, HIGH>(sp, v0.w) |
+                                         first_mask<NR, HIGH>(sp, v1.x) | first_mask<NR, HIGH>(sp, v1.y) |
+                                         first_mask<NR, HIGH>(sp, v1.z) | first_mask<NR, HIGH>(sp, v1.w);
+                    tile_high |= v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w;
+                    const bool hit = valid && (any & 0x80808080u) != 0;
+                    const uint32_t hm = __ballot_sync(FULL, hit);
+                    if (hit) s_hits[qn + __popc(hm & ((1u << lane) - 1))] = (uint16_t)unit;
+                    qn += __popc(hm);
+                }
+                high = __any_sync(FULL, (tile_high & 0x80808080u) != 0);   // (up to 15 bytes in front of the tile are counted in: harmless)
+                st = ST_STRINGS;
+                it = 0;
             }
-            s_res[i] = r ? 1 : 0;
-        }
-        __syncthreads();
-        if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
-        __syncthreads();
-        // ---- S: linear sweep of the staged bytes [lo, hi), 32 bytes per lane and step; units with a candidate are queued ----
-        const int lo = s_off[0];
-        const int staged_end = (int)(c.t1 - c.base);
-        const int hi = s_off[c.count] == OFF_BEYOND ? staged_end : s_off[c.count];
-        const int unit0 = lo >> 5, nunits = (hi + 31) >> 5;
-        for (int row = unit0 + warp * 32; row < nunits; row += 256) {
-            const int unit = row + lane;
-            const bool valid = unit < nunits;
-            uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
-            if (valid) {
-                v0 = lds_v4(tile_addr + ((uint32_t)unit << 5));
-                v1 = lds_v4(tile_addr + ((uint32_t)unit << 5) + 16);
+            if (st == ST_STRINGS) {
+                // ---- per string: degenerate texts, the start on the leading NUL; strings too long to stage are deferred ----
+                const int64_t first = (int64_t)t * spt;
+                while (it < count && sqn < 32) {
+                    const int i = it + lane;
+                    bool r = false;
+                    uint32_t defer = 0;
+                    if (i < count) {
+                        const int32_t r0 = s_off[i], r1 = s_off[i + 1];
+                        if (r1 == OFF_BEYOND) defer = 1;
+                        else {
+                            const int len = r1 - r0;
+                            const uint32_t a = tile_addr + (uint32_t)r0;
+                            if (degenerate_text<1>(len, len ? lds_u8(a) : 0)) r = p.q0_accepting != 0;
+                            else if (sp.start_nul != 0) {
+                                r = attempt_wins(A, T, FetchShared{a}, len, (uint32_t)sp.start_nul, 0);
+                                if (r && p.prefix_mode == 1 && high) { r = false; defer = 2; }
+                            }
+                        }
+                        out[first + i] = r ? 1 : 0;                // provisional for deferred strings
+                    }
+                    push(defer != 0, (uint32_t)i | (defer << SPARSE_KIND_SHIFT));
+                    it += 32;
+                }
+                if (it < count) continue;                          // queue full: flush, then resume here
+                __syncwarp();                                      // results written before any attempt of this tile sets one
+                st = ST_CONFIRM;
+                it = 0;
+                cand = 0;
             }
-            const uint32_t any = first_mask<NR, HIGH>(sp, v0.x) | first_mask<NR, HIGH>(sp, v0.y) |
-                                 first_mask<NR, HIGH>(sp, v0.z) | first_mask<NR, HIGH>(sp, v0.w) |
-                                 first_mask<NR, HIGH>(sp, v1.x) | first_mask<NR, HIGH>(sp, v1.y) |
-                                 first_mask<NR, HIGH>(sp, v1.z) | first_mask<NR, HIGH>(sp, v1.w);
-            const uint32_t hb = __ballot_sync(FULL, ((v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) & 0x80808080u) != 0);
-            if (lane == 0) s_high[(row - unit0) >> 5] = hb;
-            const bool hit = valid && (any & 0x80808080u) != 0;
-            const uint32_t hm = __ballot_sync(FULL, hit);
-            if (hm) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_cnt[0], __popc(hm));
-                base = __shfl_sync(FULL, base, 0);
-                if (hit) s_hits[base + __popc(hm & ((1u << lane) - 1))] = (uint16_t)unit;
-            }
-        }
-        __syncthreads();
-        // ---- C: confirm.  One queued unit per lane; its candidates are taken in rounds (round k = every lane's k-th
-        // candidate).  A candidate survives unless two bytes prove the start dead: the first step must stay alive, and
-        // then either the next text byte or the NUL that ends a string must.  Survivors (rare) are queued. ----
-        const int nhits = s_cnt[0];
-        for (int i0 = warp * 32; i0 < nhits; i0 += 256) {
-            const int i = i0 + lane;
-            uint32_t cand = 0;                           // one bit per byte of this lane's unit
-            int P = 0;
-            if (i < nhits) {
-                const int unit = s_hits[i];
-                const uint32_t ua = tile_addr + ((uint32_t)unit << 5);
-                const uint4 v0 = lds_v4(ua), v1 = lds_v4(ua + 16);
-                cand = pack_byte_flags(first_mask<NR, HIGH>(sp, v0.x)) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.y)) << 4) |
-                       (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.z)) << 8) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.w)) << 12) |
-                       (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.x)) << 16) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.y)) << 20) |
-                       (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.z)) << 24) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.w)) << 28);
-                P = unit << 5;
-                if (P < lo) cand &= 0xFFFFFFFFu << (lo - P);
-                if (P + 32 > hi) cand &= 0xFFFFFFFFu >> (P + 32 - hi);
-            }
-            while (__any_sync(FULL, cand != 0)) {
+            // ---- C: confirm.  One queued unit per lane; its candidates are taken in rounds (round k = every lane's
+            // k-th candidate).  A candidate survives unless two bytes prove the start dead. ----
+            while (sqn < 32) {
+                if (!__any_sync(FULL, cand != 0)) {
+                    if (it >= qn) { st = ST_NEW; t += gridDim.x * 8; break; }     // tile finished
+                    const int i = it + lane;
+                    if (i < qn) {
+                        const int unit = s_hits[i];
+                        const uint32_t ua = tile_addr + ((uint32_t)unit << 5);
+                        const uint4 v0 = lds_v4(ua), v1 = lds_v4(ua + 16);
+                        cand = pack_byte_flags(first_mask<NR, HIGH>(sp, v0.x)) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.y)) << 4) |
+                               (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.z)) << 8) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.w)) << 12) |
+                               (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.x)) << 16) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.y)) << 20) |
+                               (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.z)) << 24) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.w)) << 28);
+                        P = unit << 5;
+                        if (P < lo) cand &= 0xFFFFFFFFu << (lo - P);
+                        if (P + 32 > hi) cand &= 0xFFFFFFFFu >> (P + 32 - hi);
+                    }
+                    it += 32;
+                    continue;
+                }
                 bool sv = false;
                 int pos = 0;
                 if (cand) {
@@ -885,56 +999,15 @@ __global__ void __launch_bounds__(256, 4) k_in_sparse(KParams p, SparseParams sp
                         sv = ((T.next(w1, b1) | T.next(w1, 0u)) & (W_STATE | W_ACC)) != 0;
                     }
                 }
-                const uint32_t sm = __ballot_sync(FULL, sv);
-                if (sm) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&s_cnt[1], __popc(sm));
-                    base = __shfl_sync(FULL, base, 0);
-                    if (sv) {
-                        const int slot = base + __popc(sm & ((1u << lane) - 1));
-                        if (slot < SPARSE_SURVIVORS) s_surv[slot] = (uint16_t)pos;
-                        else {                                   // queue full: run this attempt right here
-                            int s = 0, sh = c.count;
-                            while (sh - s > 1) { const int mid = (s + sh) >> 1; if (s_off[mid] <= pos) s = mid; else sh = mid; }
-                            const int32_t r0 = s_off[s], r1 = s_off[s + 1];
-                            if (r1 != OFF_BEYOND && !(r1 - r0 == 1 && lds_u8(tile_addr + (uint32_t)pos) == 0x20) &&
-                                attempt_wins_smem(A, T, tile_addr + (uint32_t)r0, r1 - r0, (uint32_t)sp.q0, pos - r0))
-                                s_res[s] = 1;
-                        }
-                    }
-                }
+                push(sv, (uint32_t)(pos - lo));
             }
         }
-        __syncthreads();
-        // ---- A: the surviving starts, one per thread: find the string, run the anchored attempt ----
-        const int nsurv = s_cnt[1] < SPARSE_SURVIVORS ? s_cnt[1] : SPARSE_SURVIVORS;
-        for (int i = threadIdx.x; i < nsurv; i += blockDim.x) {
-            const int pos = s_surv[i];
-            int s = 0, sh = c.count;                     // largest s with s_off[s] <= pos  (pos >= lo = s_off[0])
-            while (sh - s > 1) {
-                const int mid = (s + sh) >> 1;
-                if (s_off[mid] <= pos) s = mid; else sh = mid;
-            }
-            const int32_t r0 = s_off[s], r1 = s_off[s + 1];
-            if (r1 == OFF_BEYOND || s_res[s]) continue;                  // not fully staged: answered by the prologue
-            if (r1 - r0 == 1 && lds_u8(tile_addr + (uint32_t)pos) == 0x20) continue;   // a lone blank never reaches the loop
-            if (attempt_wins_smem(A, T, tile_addr + (uint32_t)r0, r1 - r0, (uint32_t)sp.q0, pos - r0)) s_res[s] = 1;
-        }
-        __syncthreads();                 // results and high-byte bitmap complete; everyone is done with the tile text
-        for (int i = threadIdx.x; i < c.count; i += blockDim.x) {
-            uint8_t r = s_res[i];
-            if (r && p.prefix_mode == 1) {
-                const int32_t r0 = s_off[i], r1 = s_off[i + 1];
-                if (r1 != OFF_BEYOND && r1 > r0) {       // (unstaged strings went through the exact slow path already)
-                    bool high = false;
-                    for (int u = (r0 >> 5) - unit0; u <= ((r1 - 1) >> 5) - unit0; u++)
-                        high |= (s_high[u >> 5] >> (u & 31)) & 1;
-                    if (high) r = recheck_in_with_prefix(p, buf + (c.base + r0), r1 - r0) ? 1 : 0;
-                }
-            }
-            out[c.first + i] = r;
-        }
-        __syncthreads();                 // before the next tile overwrites offsets / results / text
+        if (sqn == 0) break;                                       // nothing waiting, no tiles left
+        const int run = sqn < 32 ? sqn : 32;
+        sparse_run_deferred<KIND>(p, sp, T, s_queue, run, spt, n, offsets, buf, out);
+        if (lane < sqn - run) { const uint2 x = s_queue[run + lane]; s_queue[lane] = x; }
+        sqn -= run;
+        __syncwarp();
     }
 }
 
