@@ -31,7 +31,7 @@ class PatternInfo(C.Structure):
         "table_bytes", "direct_bytes", "literal_all_len", "literal_prefix_len", "literal_suffix_len",
         "literal_only", "residency", "direct", "prefix_mode", "sparse", "sparse_ranges")] + [
         ("sparse_lo", C.c_int32 * 4), ("sparse_hi", C.c_int32 * 4), ("sparse_high", C.c_int32),
-        ("sparse_used", C.c_int32)]
+        ("sparse_second", C.c_int32), ("sparse_used", C.c_int32)]
 
 
 _lib = None

@@ -56,6 +56,9 @@ struct FirstSet {
     int nr = 0;
     uint8_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
     bool high = false;
+    bool two = false;            // one first byte, and after it one ASCII byte (plus, maybe, lead bytes) keeps the automaton alive
+    uint8_t second = 0;
+    bool second_high = false;
 };
 
 }  // namespace
@@ -151,7 +154,25 @@ bool sparse_first_set(const fx::ByteTable& at, FirstSet& fs) {
         fs.lo[fs.nr] = (uint8_t)b; fs.hi[fs.nr] = (uint8_t)e; fs.nr++;
         b = e + 1;
     }
-    return fs.nr > 0 || fs.high;
+    if (fs.nr == 0 && !fs.high) return false;
+    // the two-byte sweep filter: F's ASCII part is one byte V1, the step q0 -V1-> w1 neither accepts nor enters a
+    // sequence, and from w1 exactly one ASCII byte V2 != NUL survives (no continuation byte does)
+    if (fs.nr == 1 && fs.lo[0] == fs.hi[0]) {
+        const uint16_t w1 = at.table[((size_t)at.q0 << at.row_shift) + at.classmap[fs.lo[0]]];
+        if ((w1 & (fxk::W_ACC | fxk::W_INTER)) == 0 && (w1 & fxk::W_STATE) != 0) {
+            int nascii = 0, v2 = 0;
+            bool cont = false, hi2 = false;
+            for (int c = 0; c < 256; c++) {
+                const uint16_t w2 = at.table[((size_t)(w1 & fxk::W_STATE) << at.row_shift) + at.classmap[c]];
+                if ((w2 & (fxk::W_STATE | fxk::W_ACC)) == 0) continue;
+                if (c < 0x80) { nascii++; v2 = c; }
+                else if (c < 0xC0) cont = true;
+                else hi2 = true;
+            }
+            if (nascii == 1 && v2 != 0 && !cont) { fs.two = true; fs.second = (uint8_t)v2; fs.second_high = hi2; }
+        }
+    }
+    return true;
 }
 
 int ensure_device(fx_pattern* p) {
@@ -443,59 +464,39 @@ int launch_stream_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int
     return cuda_status(cudaGetLastError());
 }
 
-// K2c tiling: every warp stages its own tile; 8 warp regions + the table fill a CTA's share of shared memory
-struct SparseTiling {
-    int spt, cap, table_smem;
-    int64_t ntiles;
-    size_t smem;
-};
-
-SparseTiling make_sparse_tiling(int table_bytes, int64_t n, int64_t total, int ctas) {
-    SparseTiling t;
+// K2c: a warp sweeps tiles of `spt` consecutive strings, about 16 KB of text each
+template <int KIND, int NR, bool HIGH, bool TWO, int MINB, int ROWS>
+int launch_sparse_v(fx_pattern* p, const Plan& pl, const SparseParams& sp, int table_bytes, const uint8_t* buf,
+                    const int64_t* off, int64_t n, int64_t total, uint8_t* out, cudaStream_t s) {
+    auto kern = k_in_sparse<KIND, NR, HIGH, TWO, MINB, ROWS>;
     int64_t avg = n > 0 ? (total + n - 1) / n : 1;
     if (avg < 1) avg = 1;
-    t.table_smem = (table_bytes + 15) & ~15;
-    const int head = sparse_shared_head(t.table_smem);
-    int per_warp = (((227 * 1024) / ctas - 1024 - head) / 8) & ~127;
-    if (per_warp < 2048) per_warp = 2048;
-    int cap = per_warp < SPARSE_MAX_CAP ? per_warp : SPARSE_MAX_CAP, spt = 1;
-    for (;;) {
-        int64_t want = ((int64_t)cap * 4 / 5) / avg;       // expect the tile to fill ~80 % of the staged capacity
-        spt = (int)(want < 1 ? 1 : want > 256 ? 256 : want);
-        if (cap <= 1024 || sparse_layout(spt, cap).warp_bytes <= per_warp) break;
-        cap -= 128;
-    }
+    int64_t want = env_int("FX_SPARSE_TILE_BYTES", 16 * 1024) / avg;
+    int spt = (int)(want < 32 ? 32 : want > 4096 ? 4096 : want);
     spt = env_int("FX_TILE_STRINGS", spt);
-    if (spt > 256) spt = 256;
-    t.spt = spt;
-    t.cap = cap;
-    t.ntiles = (n + spt - 1) / spt;
-    t.smem = (size_t)head + 8 * (size_t)sparse_layout(spt, cap).warp_bytes;
-    return t;
-}
-
-template <int KIND, int NR, bool HIGH, int MINB>
-int launch_sparse_b(fx_pattern* p, const Plan& pl, const SparseParams& sp, int table_bytes, const uint8_t* buf,
-                    const int64_t* off, int64_t n, int64_t total, uint8_t* out, cudaStream_t s) {
-    auto kern = k_in_sparse<KIND, NR, HIGH, MINB>;
-    SparseTiling t = make_sparse_tiling(KIND == 3 ? 0 : table_bytes, n, total, MINB);
+    const int64_t ntiles = (n + spt - 1) / spt;
+    const int table_smem = KIND == 3 ? 0 : (table_bytes + 15) & ~15;
+    const size_t smem = (size_t)sparse_shared_head(table_smem) + 8 * (size_t)SPARSE_WARP_BYTES;
     int bps = 0;
-    int rc = occupancy_grid(kern, 256, t.smem, p->dev.sm_count, bps);
+    int rc = occupancy_grid(kern, 256, smem, p->dev.sm_count, bps);
     if (rc) return rc;
     long long cap = (long long)p->dev.sm_count * bps;
-    long long want = (t.ntiles + 7) / 8;
-    int grid = (int)(want < cap ? want : cap);
+    long long wantg = (ntiles + 7) / 8;
+    int grid = (int)(wantg < cap ? wantg : cap);
     if (grid < 1) grid = 1;
-    kern<<<grid, 256, t.smem, s>>>(pl.kp, sp, buf, off, n, total, out, t.spt, t.cap, t.ntiles, t.table_smem);
+    kern<<<grid, 256, smem, s>>>(pl.kp, sp, buf, off, n, total, out, spt, ntiles, table_smem);
     g_launches++;
     return cuda_status(cudaGetLastError());
 }
 
-template <int KIND, int NR, bool HIGH>
+template <int KIND, int NR, bool HIGH, bool TWO>
 int launch_sparse_t(fx_pattern* p, const Plan& pl, const SparseParams& sp, int table_bytes, const uint8_t* buf,
                     const int64_t* off, int64_t n, int64_t total, uint8_t* out, cudaStream_t s) {
-    if (env_int("FX_SPARSE_CTAS", 4) == 3) return launch_sparse_b<KIND, NR, HIGH, 3>(p, pl, sp, table_bytes, buf, off, n, total, out, s);
-    return launch_sparse_b<KIND, NR, HIGH, 4>(p, pl, sp, table_bytes, buf, off, n, total, out, s);
+    const int v = env_int("FX_SPARSE_VARIANT", 44);      // experiment knob: CTAs per SM x rows in flight
+    if (v == 34) return launch_sparse_v<KIND, NR, HIGH, TWO, 3, 4>(p, pl, sp, table_bytes, buf, off, n, total, out, s);
+    if (v == 44) return launch_sparse_v<KIND, NR, HIGH, TWO, 4, 4>(p, pl, sp, table_bytes, buf, off, n, total, out, s);
+    if (v == 32) return launch_sparse_v<KIND, NR, HIGH, TWO, 3, 2>(p, pl, sp, table_bytes, buf, off, n, total, out, s);
+    return launch_sparse_v<KIND, NR, HIGH, TWO, 4, 2>(p, pl, sp, table_bytes, buf, off, n, total, out, s);
 }
 
 template <int KIND, bool HIGH>
@@ -504,14 +505,15 @@ int launch_sparse_k(fx_pattern* p, const Plan& pl, const SparseParams& sp, int t
     if (p->first.nr == 1 && p->first.lo[0] == p->first.hi[0]) {      // one byte value: the cheaper zero-byte test
         SparseParams one = sp;
         one.add_lo[0] = p->first.lo[0] * 0x01010101u;
-        return launch_sparse_t<KIND, -1, HIGH>(p, pl, one, tb, buf, off, n, total, out, s);
+        if (p->first.two && env_int("FX_SPARSE_TWO", 1)) return launch_sparse_t<KIND, -1, HIGH, true>(p, pl, one, tb, buf, off, n, total, out, s);
+        return launch_sparse_t<KIND, -1, HIGH, false>(p, pl, one, tb, buf, off, n, total, out, s);
     }
     switch (p->first.nr) {
-        case 0: return launch_sparse_t<KIND, 0, true>(p, pl, sp, tb, buf, off, n, total, out, s);
-        case 1: return launch_sparse_t<KIND, 1, HIGH>(p, pl, sp, tb, buf, off, n, total, out, s);
-        case 2: return launch_sparse_t<KIND, 2, HIGH>(p, pl, sp, tb, buf, off, n, total, out, s);
-        case 3: return launch_sparse_t<KIND, 3, HIGH>(p, pl, sp, tb, buf, off, n, total, out, s);
-        default: return launch_sparse_t<KIND, 4, HIGH>(p, pl, sp, tb, buf, off, n, total, out, s);
+        case 0: return launch_sparse_t<KIND, 0, true, false>(p, pl, sp, tb, buf, off, n, total, out, s);
+        case 1: return launch_sparse_t<KIND, 1, HIGH, false>(p, pl, sp, tb, buf, off, n, total, out, s);
+        case 2: return launch_sparse_t<KIND, 2, HIGH, false>(p, pl, sp, tb, buf, off, n, total, out, s);
+        case 3: return launch_sparse_t<KIND, 3, HIGH, false>(p, pl, sp, tb, buf, off, n, total, out, s);
+        default: return launch_sparse_t<KIND, 4, HIGH, false>(p, pl, sp, tb, buf, off, n, total, out, s);
     }
 }
 
@@ -529,6 +531,8 @@ int launch_sparse(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int64
         sp.add_lo[r] = (0x80u - p->first.lo[k]) * 0x01010101u;
         sp.add_hi[r] = (0x7Fu - p->first.hi[k]) * 0x01010101u;
     }
+    sp.second = p->first.second * 0x01010101u;
+    sp.second_high = p->first.second_high ? 0xFFFFFFFFu : 0u;
     const int tb = (int)at.table.size() * 2;
     const bool smem_table = p->residency != FX_TABLE_GLOBAL && tb <= env_int("FX_SPARSE_SMEM_TABLE_BYTES", 24 * 1024);
     if (smem_table)
@@ -779,6 +783,7 @@ int fx_pattern_get_info(const fx_pattern* p, fx_pattern_info* info) {
     info->sparse = p->sparse ? 1 : 0;
     info->sparse_ranges = p->sparse ? p->first.nr : 0;
     info->sparse_high = p->sparse && p->first.high ? 1 : 0;
+    info->sparse_second = p->sparse && p->first.two ? p->first.second : -1;
     for (int r = 0; r < 4; r++) {
         info->sparse_lo[r] = p->sparse && r < p->first.nr ? p->first.lo[r] : 0;
         info->sparse_hi[r] = p->sparse && r < p->first.nr ? p->first.hi[r] : 0;

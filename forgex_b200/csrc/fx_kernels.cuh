@@ -688,21 +688,23 @@ __global__ void __launch_bounds__(256, 4) k_bool_ragged(KParams p, const uint8_t
 // `.in.` is true when SOME start of the brute-force search wins (api_internal_m.F90:108-155).  A start whose first
 // byte kills the anchored automaton cannot win, so when the set F of first bytes that survive the step out of q0 is
 // small (a few byte ranges: 'f' for foo(bar|baz); NUL/LF/CR for ^ERROR...), almost every position of the text is
-// ruled out by a compare.  The kernel therefore does not walk the strings at all, and it has no block-wide step:
-// every WARP owns its tiles (a few KB of consecutive strings, staged by its own TMA bulk copy on its own mbarrier),
-// so warps never wait for each other and the 32 warps of an SM hide each other's load latency.  Per tile:
-//   S  sweep: the lanes read the staged tile LINEARLY, 32 bytes per lane and step out of two conflict-free LDS.128,
-//      and test them against F with SWAR arithmetic (3-4 integer instructions per 4 bytes); 32-byte units that hold
-//      a candidate are queued;
-//   C  confirm: one queued unit per lane; each candidate takes its first table step and, unless that already accepts
-//      or enters a multi-byte sequence, the second one (with the next text byte, and with the NUL that would end the
-//      string there).  Two bytes kill almost every candidate;
-//   A  attempts: survivors go to a queue that outlives the tile; whenever 32 are waiting the 32 lanes run them side
-//      by side from global memory (the bytes are in L2): binary search over the tile's offsets for the string, then
-//      the anchored attempt -- the reference's own inner loop, on the anchored flag-bit table -- until the first
-//      counted accept, which sets the string's result.
-// The per-string part (degenerate texts, the start on the leading NUL, strings too long to stage) is one string per
-// lane and writes the tile's results before any attempt of that tile can run.
+// ruled out by a compare.  The kernel therefore does not walk the strings at all, it has no block-wide step, and
+// the text never passes through shared memory:
+//   S  sweep: a warp owns tiles of consecutive strings (about 16 KB of text).  Its lanes read the tile's bytes
+//      LINEARLY, 32 bytes per lane and step, as coalesced 16-byte loads straight from global memory (two rows = 2 KB
+//      per warp in flight), and test them against F with SWAR arithmetic (3-4 integer instructions per 4 bytes).
+//      When the automaton has ONE first byte and ONE possible second byte (a pattern that begins with a literal), the
+//      test is for that byte pair.  32-byte units that pass are queued;
+//   U  units: whenever 32 units are waiting, the lanes take one each (its bytes are in L2 now): every candidate
+//      takes its first table step and, unless that already accepts or enters a multi-byte sequence, the second one
+//      (with the next text byte, and with the NUL that would end the string there).  Two bytes kill almost every
+//      candidate; survivors are queued as starts;
+//   A  starts: whenever 32 starts are waiting, the lanes run them side by side: binary search over the tile's
+//      offsets for the string, then the anchored attempt -- the reference's own inner loop, on the anchored
+//      flag-bit table -- until the first counted accept, which sets the string's result.
+// The per-string part (degenerate texts, the start on the leading NUL) is one string per lane and writes the
+// tile's results before any start of that tile can run.  Every phase has all 32 lanes doing the same work whatever
+// the string lengths are.
 //
 // Preconditions (checked on the host, fx_cabi.cu sparse_first_set): F holds no continuation byte 0x80..0xBF --
 // ASCII, lead and invalid bytes always sit on a character boundary of the reference's decoder, so every candidate is
@@ -718,28 +720,20 @@ struct SparseParams {
     // ASCII range r of the sweep filter, 7-bit bounds folded into SWAR addends
     uint32_t add_lo[4];         // (0x80 - lo) * 0x01010101: bit 7 of (y + add_lo) <=> y >= lo   (NR = -1: value * 0x01010101)
     uint32_t add_hi[4];         // (0x7F - hi) * 0x01010101: bit 7 of (y + add_hi) <=> y >  hi
+    uint32_t second;            // TWO: the one ASCII byte that keeps the automaton alive after the first, in all four bytes
+    uint32_t second_high;       // TWO: 0xFFFFFFFF when bytes >= 0xC0 keep it alive as well (lead bytes), else 0
 };
 
-// shared memory of K2c: classmap 256 | table | pad to 128 | 8 warp regions of `warp_bytes`:
-//   [0,16) mbarrier | offsets (spt+4) x int32 | hit queue (cap/32 + 8) x u16 | pad to 8 | survivor queue 64 x uint2 |
-//   pad to 128 | tile (cap + 64)
-static constexpr int SPARSE_MAX_CAP = 60 * 1024;          // 16-bit tile positions
-struct SparseLayout { int off_hits, off_surv, off_tile, warp_bytes; };
-__host__ __device__ __forceinline__ SparseLayout sparse_layout(int spt, int cap) {
-    SparseLayout L;
-    L.off_hits = 16 + (spt + 4) * 4;
-    L.off_surv = (L.off_hits + ((cap >> 5) + 8) * 2 + 7) & ~7;
-    L.off_tile = (L.off_surv + 64 * 8 + 127) & ~127;
-    L.warp_bytes = (L.off_tile + cap + 64 + 127) & ~127;
-    return L;
-}
-__host__ __device__ __forceinline__ int sparse_shared_head(int table_smem_bytes) { return (256 + table_smem_bytes + 127) & ~127; }
+// shared memory of K2c: classmap 256 | table | pad to 16 | 8 warps x (unit queue 64 x uint4 | start queue 64 x uint4)
+//   queue entry = {tile, kind | high << 31, low word, high word}
+static constexpr int SPARSE_WARP_BYTES = 2 * 64 * 16;
+__host__ __device__ __forceinline__ int sparse_shared_head(int table_smem_bytes) { return (256 + table_smem_bytes + 15) & ~15; }
 
-// Sweep filter: bit 7 set in every byte of w that may be in F (callers mask with 0x80808080).  A superset is fine --
-// every candidate is confirmed by the first table step before anything else happens -- so bit 7 of the text byte is
-// ignored here (a byte >= 0x80 whose low bits fall into a range is a false candidate, in non-ASCII text only), and
-// with HIGH every byte >= 0x80 passes (F holds lead bytes: e.g. the overlong forms 0xC1 0xE0 0xF0 of an ASCII first
-// character, which the reference's structural decoder accepts).
+// Sweep filter for one 4-byte word: bit 7 set in every byte of w that may be in F (callers mask with 0x80808080).
+// A superset is fine -- every candidate is confirmed by the first table step before anything else happens -- so bit 7
+// of the text byte is ignored here (a byte >= 0x80 whose low bits fall into a range is a false candidate, in
+// non-ASCII text only), and with HIGH every byte >= 0x80 passes (F holds lead bytes: e.g. the overlong forms 0xC1 0xE0
+// 0xF0 of an ASCII first character, which the reference's structural decoder accepts).
 // NR = -1: F's ASCII part is ONE byte value (add_lo[0] holds it in all four bytes): the zero-byte test on w ^ value,
 //          three instructions per word (its false positives sit above a true hit, in the same word).
 template <int NR, bool HIGH>
@@ -756,21 +750,48 @@ __device__ __forceinline__ uint32_t first_mask(const SparseParams& sp, uint32_t 
     if (HIGH) m |= w;
     return m;
 }
+// Sweep filter for one 32-byte unit: non-zero when the unit may hold a candidate.  TWO (with NR = -1): a candidate
+// is the first byte FOLLOWED BY the second byte (or by a lead byte, if lead bytes can follow); whatever follows the
+// unit's last byte is assumed to match.  `seen` collects the OR of the unit's words (bytes >= 0x80 in the tile?).
+template <int NR, bool HIGH, bool TWO>
+__device__ __forceinline__ uint32_t unit_any(const SparseParams& sp, const uint4& a, const uint4& b, uint32_t& seen) {
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const uint32_t all = w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7];
+    seen |= all;
+    uint32_t any = 0;
+    if (TWO) {
+        uint32_t z2_next = 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+            const uint32_t x1 = w[k] ^ sp.add_lo[0], x2 = w[k] ^ sp.second;
+            uint32_t z2 = (x2 - 0x01010101u) & ~x2;
+            if (!HIGH) z2 |= w[k] & sp.second_high;            // (with HIGH every byte >= 0x80 makes the unit pass anyway)
+            any |= (x1 - 0x01010101u) & ~x1 & __funnelshift_r(z2, z2_next, 8);   // first byte at j and second byte at j + 1
+            z2_next = z2;
+        }
+        if (HIGH) any |= all;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) any |= first_mask<NR, false>(sp, w[k]);
+        if (HIGH) any |= all;
+    }
+    return any & 0x80808080u;
+}
 // bits 7, 15, 23, 31 of m -> bits 0..3
 __device__ __forceinline__ uint32_t pack_byte_flags(uint32_t m) { return ((((m >> 7) & 0x01010101u) * 0x00204081u) >> 21) & 0xFu; }
 
 // does the anchored attempt that starts in state `st` before byte `pos` of a string of `len` bytes see a counted
 // accept?  run_attempt() reduced to what a boolean needs: out at the first accept.
 template <class TBL, class FETCH>
-__device__ __forceinline__ bool attempt_wins(const Anchored& A, const TBL& T, FETCH fetch, int len, uint32_t st, int pos) {
+__device__ __forceinline__ bool attempt_wins(const Anchored& A, const TBL& T, FETCH fetch, int64_t len, uint32_t st, int64_t pos) {
     uint32_t w = st;
-    int seq = 0;
+    int64_t seq = 0;
     bool inter = false;
-    for (int j = pos; j <= len; j++) {
+    for (int64_t j = pos; j <= len; j++) {
         const uint32_t b = j < len ? fetch(j) : 0u;               // virtual trailing NUL at j == len
         if (inter && (b & 0xC0) != 0x80) {                        // sequence broken: pending bytes replay as U+FFFF
             const uint32_t f = __ldg(A.flags + (w & W_STATE));
-            if (f & ((SF_FAILACC1 << (j - seq)) - SF_FAILACC1)) return true;
+            if (f & ((SF_FAILACC1 << (int)(j - seq)) - SF_FAILACC1)) return true;
             inter = false;
         }
         const uint32_t nw = T.next(w & W_STATE, b);
@@ -782,232 +803,264 @@ __device__ __forceinline__ bool attempt_wins(const Anchored& A, const TBL& T, FE
     }
     return false;
 }
-__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
 
-// Deferred work of K2c: `count` (<= 32) queue entries {tile, payload}, one per lane, everything read from global memory.
-//   payload = position relative to the tile's first byte (bits 0..27) | kind << 28 | tile holds bytes >= 0x80 << 31
-//   kind 0  a surviving start: find its string (binary search over the tile's offsets), run the anchored attempt
-//   kind 1  string number `position` of the tile was too long to stage: the whole wrapper from global memory
-//   kind 2  string number `position` won from the leading NUL in a tile with bytes >= 0x80: exact prefix replay
-// Out of line on purpose, and called only from the outer loop of the kernel: a call inside the sweep / confirm loops
-// makes the compiler keep their whole state in callee-saved registers and spill it (measured: 200 bytes per thread).
-static constexpr uint32_t SPARSE_KIND_SHIFT = 28, SPARSE_POS_MASK = 0x0FFFFFFFu;
+// per-warp context of the deferred phases (everything but the queues' fill levels is read-only)
+struct SparseCtx {
+    const uint8_t* buf;
+    const int64_t* offsets;
+    uint8_t* out;
+    int64_t n, total;
+    int spt;
+    uint4* units;     // queue of 32-byte units to look at
+    uint4* starts;    // queue of starts to attempt
+};
+static constexpr uint32_t SPARSE_START = 0, SPARSE_RECHECK = 2;
+
+// Phase A: `count` (<= 32) queued starts, one per lane.
+//   kind SPARSE_START    {tile, kind|high, position (64 bit) relative to the tile's first byte}: find the string, attempt
+//   kind SPARSE_RECHECK  {tile, kind, string number in the tile}: the string won from the leading NUL in a tile with
+//                        bytes >= 0x80 and the pattern has a prefix: exact prefix replay decides
+// Out of line on purpose, and called only from the outer loop of the kernel: a call inside the sweep loop makes the
+// compiler keep that loop's whole state in callee-saved registers and spill it (measured: 200 bytes per thread).
 template <int KIND>
-__device__ __noinline__ void sparse_run_deferred(const KParams& p, const SparseParams& sp, const Table<KIND>& T,
-                                                 const uint2* s_queue, int count, int spt, int64_t n,
-                                                 const int64_t* __restrict__ offsets, const uint8_t* __restrict__ buf,
-                                                 uint8_t* __restrict__ out) {
+__device__ __noinline__ void sparse_run_starts(const KParams& p, const SparseParams& sp, const Table<KIND>& T,
+                                               const SparseCtx& c, int count) {
     const int lane = threadIdx.x & 31;
     const Anchored A{sp.flags, sp.start_nul, sp.q0};
     __syncwarp();
     if (lane < count) {
-        const uint2 e = s_queue[lane];
-        const int64_t first = (int64_t)e.x * spt;
-        const int64_t* off = offsets + first;
-        const uint32_t kind = (e.y >> SPARSE_KIND_SHIFT) & 7u, val = e.y & SPARSE_POS_MASK;
-        if (kind == 0) {
-            const int cnt = (int)((n - first) < spt ? (n - first) : spt);
-            const int64_t gpos = __ldg(off) + (int64_t)val;
+        const uint4 e = c.starts[lane];
+        const int64_t first = (int64_t)e.x * c.spt;
+        const int64_t* off = c.offsets + first;
+        const uint32_t kind = e.y & 7u;
+        const int64_t val = (int64_t)(((unsigned long long)e.w << 32) | e.z);
+        if (kind == SPARSE_START) {
+            const int cnt = (int)((c.n - first) < c.spt ? (c.n - first) : c.spt);
+            const int64_t gpos = __ldg(off) + val;
             int s = 0, sh = cnt;                                   // largest s with off[s] <= gpos
             while (sh - s > 1) {
                 const int mid = (s + sh) >> 1;
                 if (__ldg(off + mid) <= gpos) s = mid; else sh = mid;
             }
             const int64_t o0 = __ldg(off + s), o1 = __ldg(off + s + 1);
-            const uint8_t* str = buf + o0;
+            const uint8_t* str = c.buf + o0;
             if (!(o1 - o0 == 1 && __ldg(str) == 0x20)) {           // a lone blank never reaches the loop
-                bool win = attempt_wins(A, T, FetchGlobal{str}, (int)(o1 - o0), (uint32_t)sp.q0, (int)(gpos - o0));
+                bool win = attempt_wins(A, T, FetchGlobal{str}, o1 - o0, (uint32_t)sp.q0, gpos - o0);
                 if (win && p.prefix_mode == 1 && (e.y >> 31)) win = recheck_in_with_prefix(p, str, o1 - o0);
-                if (win) out[first + s] = 1;
+                if (win) c.out[first + s] = 1;
             }
         } else {
             const int64_t o0 = __ldg(off + val), o1 = __ldg(off + val + 1);
-            const bool r = kind == 1 ? eval_bool_slow<1>(p, buf + o0, o1 - o0) : recheck_in_with_prefix(p, buf + o0, o1 - o0);
-            out[first + val] = r ? 1 : 0;
+            c.out[first + val] = recheck_in_with_prefix(p, c.buf + o0, o1 - o0) ? 1 : 0;
         }
     }
     __syncwarp();
 }
 
-template <int KIND, int NR, bool HIGH, int MINB>
+// Phase U: `count` (<= 32) queued units {tile, high << 31, unit number (64 bit) from the tile's 32-byte aligned base},
+// one per lane.  Candidates are taken in rounds (round k = every lane's k-th candidate); a candidate survives unless
+// two bytes prove the start dead.  Survivors go to the start queue (sqn = its fill level), which is run when full.
+template <int KIND, int NR, bool HIGH>
+__device__ __noinline__ void sparse_run_units(const KParams& p, const SparseParams& sp, const Table<KIND>& T,
+                                              const SparseCtx& c, int count, int& sqn) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t FULL = 0xffffffffu;
+    __syncwarp();
+    uint32_t cand = 0, tile = 0, flag = 0;
+    int64_t P = 0, t0 = 0;                                         // buffer position of the unit's byte 0; of the tile's
+    if (lane < count) {
+        const uint4 e = c.units[lane];
+        tile = e.x; flag = e.y & 0x80000000u;
+        const int64_t first = (int64_t)e.x * c.spt;
+        const int cnt = (int)((c.n - first) < c.spt ? (c.n - first) : c.spt);
+        t0 = __ldg(c.offsets + first);
+        const int64_t tend = __ldg(c.offsets + first + cnt);
+        const uintptr_t gbuf = reinterpret_cast<uintptr_t>(c.buf);
+        const uintptr_t ua = ((gbuf + (uintptr_t)t0) & ~(uintptr_t)31) + ((((uintptr_t)e.w << 32) | e.z) << 5);
+        const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(ua)), v1 = __ldg(reinterpret_cast<const uint4*>(ua + 16));
+        cand = pack_byte_flags(first_mask<NR, HIGH>(sp, v0.x)) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.y)) << 4) |
+               (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.z)) << 8) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.w)) << 12) |
+               (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.x)) << 16) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.y)) << 20) |
+               (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.z)) << 24) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.w)) << 28);
+        P = (int64_t)ua - (int64_t)gbuf;
+        if (P < t0) cand &= 0xFFFFFFFFu << (int)(t0 - P);
+        if (P + 32 > tend) cand &= (P >= tend) ? 0u : (0xFFFFFFFFu >> (int)(P + 32 - tend));
+    }
+    while (__any_sync(FULL, cand != 0)) {
+        bool sv = false;
+        int64_t pos = 0;
+        if (cand) {
+            pos = P + __ffs(cand) - 1;
+            cand &= cand - 1;
+            const uint32_t b = __ldg(c.buf + pos);
+            const uint32_t w1 = T.next((uint32_t)sp.q0, b);
+            if (w1 & (W_ACC | W_INTER)) sv = true;
+            else if (w1 & W_STATE) {
+                const uint32_t b1 = pos + 1 < c.total ? __ldg(c.buf + pos + 1) : 0u;      // may belong to the next string
+                sv = ((T.next(w1, b1) | T.next(w1, 0u)) & (W_STATE | W_ACC)) != 0;
+            }
+        }
+        const uint32_t m = __ballot_sync(FULL, sv);
+        if (m) {
+            const unsigned long long rel = (unsigned long long)(pos - t0);
+            if (sv) c.starts[sqn + __popc(m & ((1u << lane) - 1))] = make_uint4(tile, SPARSE_START | flag, (uint32_t)rel, (uint32_t)(rel >> 32));
+            sqn += __popc(m);
+            if (sqn >= 32) {
+                sparse_run_starts<KIND>(p, sp, T, c, 32);
+                if (lane < sqn - 32) { const uint4 x = c.starts[32 + lane]; c.starts[lane] = x; }
+                sqn -= 32;
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <int KIND, int NR, bool HIGH, bool TWO, int MINB, int ROWS>
 __global__ void __launch_bounds__(256, MINB) k_in_sparse(KParams p, SparseParams sp, const uint8_t* __restrict__ buf,
-                                                         const int64_t* __restrict__ offsets, int64_t n, int64_t total,
-                                                         uint8_t* __restrict__ out, int spt, int cap, int64_t ntiles,
-                                                         int table_smem_bytes) {
+                                                      const int64_t* __restrict__ offsets, int64_t n, int64_t total,
+                                                      uint8_t* __restrict__ out, int spt, int64_t ntiles,
+                                                      int table_smem_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_cmap = smem;
     uint8_t* s_table = smem + 256;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const SparseLayout L = sparse_layout(spt, cap);
-    uint8_t* region = smem + sparse_shared_head(table_smem_bytes) + warp * L.warp_bytes;
-    int32_t* s_off = reinterpret_cast<int32_t*>(region + 16);
-    uint16_t* s_hits = reinterpret_cast<uint16_t*>(region + L.off_hits);
-    uint2* s_queue = reinterpret_cast<uint2*>(region + L.off_surv);
-    uint8_t* tile = region + L.off_tile;
-    const uint32_t mbar = smem_u32(region);
+    uint4* s_units = reinterpret_cast<uint4*>(smem + sparse_shared_head(table_smem_bytes) + warp * SPARSE_WARP_BYTES);
+    uint4* s_starts = s_units + 64;
     KParams anch = p;                       // stage_table reads table / classmap / sizes from a KParams
     anch.table = sp.table; anch.classmap = sp.classmap; anch.table_words = sp.table_words; anch.row_shift = sp.row_shift;
     Table<KIND> T = stage_table<KIND>(anch, s_table, s_cmap);
-    if (lane == 0) mbar_init(mbar, 1);
     __syncthreads();                        // the only block-wide step: the table is staged
-    const uint32_t tile_addr = smem_u32(tile);
     const Anchored A{sp.flags, sp.start_nul, sp.q0};
     const uint32_t FULL = 0xffffffffu;
     const int nt = (int)ntiles;             // the host keeps n (hence ntiles) below 2^31
+    SparseCtx c;
+    c.buf = buf; c.offsets = offsets; c.out = out; c.n = n; c.total = total; c.spt = spt; c.units = s_units; c.starts = s_starts;
 
-    // The warp's state machine.  The inner loop (no calls) advances it until 32 deferred entries are waiting or the
-    // tiles are used up; the outer loop runs the deferred entries and comes back.
-    enum { ST_NEW = 0, ST_STRINGS = 1, ST_CONFIRM = 2 };
+    // The warp's state machine.  The inner loop (no calls) advances it until 32 units or 32 starts are waiting or
+    // the tiles are used up; the outer loop runs the queues and comes back.
+    enum { ST_NEW = 0, ST_SWEEP = 1, ST_STRINGS = 2, ST_PUSH = 3 };
     int t = blockIdx.x * 8 + warp;          // tile in progress / next tile
-    int st = ST_NEW, it = 0;                // it: next string (ST_STRINGS) or next queued unit (ST_CONFIRM)
-    int count = 0, lo = 0, hi = 0, qn = 0, sqn = 0;
+    int st = ST_NEW, it = 0;                // it: next string (ST_STRINGS) or next row (ST_PUSH)
+    int uqn = 0, sqn = 0;                   // queue fill levels (warp-uniform)
+    int count = 0, nrows = 0;
+    int64_t seg = 0, nunits = 0;            // rows [seg, seg + nrows) of the tile's units are being swept / pushed
+    uintptr_t ubase = 0;                    // 32-byte aligned address of the tile's unit 0
+    uint32_t hitbits = 0;                   // bit r: this lane's unit in row seg + r passed the filter
     bool high = false;
-    uint32_t phase = 0, cand = 0;           // cand: candidate bytes of this lane's unit still to be confirmed
-    int P = 0;                              // tile position of that unit
-
-    auto push = [&](bool yes, uint32_t payload) {                    // warp-wide append to the deferred queue
-        const uint32_t m = __ballot_sync(FULL, yes);
-        if (yes) s_queue[sqn + __popc(m & ((1u << lane) - 1))] = make_uint2((uint32_t)t, payload | (high ? 0x80000000u : 0u));
-        sqn += __popc(m);
-    };
+    int64_t nx0 = 0, nx1 = 0;               // byte range of the warp's next tile
+    bool have_next = false;
 
     for (;;) {
         for (;;) {
-            if (sqn >= 32) break;
+            if (uqn >= 32 || sqn >= 32) break;
             if (st == ST_NEW) {
                 if (t >= nt) break;
-                // ---- stage the tile: strings [first, first + count), up to `cap` bytes of them ----
                 const int64_t first = (int64_t)t * spt;
                 count = (int)((n - first) < spt ? (n - first) : spt);
-                const int64_t t0 = __ldg(offsets + first), tend = __ldg(offsets + first + count);
-                const int64_t t1 = tend - t0 > cap ? t0 + cap : tend;
-                const uintptr_t gbuf = reinterpret_cast<uintptr_t>(buf);
-                const uintptr_t g0 = gbuf + (uintptr_t)t0;
-                lo = (int)(g0 & 15);                               // tile[lo] = byte t0 (the bulk source is 16-byte aligned)
-                const int64_t base = t0 - lo;
-                const uintptr_t gsrc = g0 & ~(uintptr_t)15;
-                uintptr_t gcopy_end = (gbuf + (uintptr_t)t1 + 15) & ~(uintptr_t)15;
-                const uintptr_t gsafe_end = (gbuf + (uintptr_t)total) & ~(uintptr_t)15;   // never bulk-read past the last whole 16-byte block
-                if (gcopy_end > gsafe_end) gcopy_end = gsafe_end;
-                const uint32_t bulk = gcopy_end > gsrc ? (uint32_t)(gcopy_end - gsrc) : 0u;
-                __syncwarp();                                      // every lane is done with the previous tile
-                if (bulk && lane == 0) {
-                    mbar_expect_tx(mbar, bulk);
-                    bulk_g2s(tile_addr, reinterpret_cast<const void*>(gsrc), bulk, mbar);
+                const int64_t t0 = have_next ? nx0 : __ldg(offsets + first), tend = have_next ? nx1 : __ldg(offsets + first + count);
+                {   // the next tile's extents, asked for now, used when this tile is done
+                    const int64_t fn = first + (int64_t)gridDim.x * 8 * spt;
+                    have_next = fn < n;
+                    if (have_next) { nx0 = __ldg(offsets + fn); nx1 = __ldg(offsets + (fn + spt < n ? fn + spt : n)); }
                 }
-                for (int64_t x = (int64_t)(gsrc + bulk) - (int64_t)gbuf + lane; x < t1; x += 32)   // < 16 bytes at the very end of the buffer
-                    if (x >= t0) tile[x - base] = __ldg(buf + x);
-                for (int i = lane; i <= count; i += 32) {          // overlaps with the bulk copy in flight
-                    const int64_t o = __ldg(offsets + first + i);
-                    s_off[i] = o > t1 ? OFF_BEYOND : (int32_t)(o - base);
-                }
-                if (bulk) { mbar_wait(mbar, phase); phase ^= 1; }
-                hi = (int)(t1 - base);
-                const int nunits = (hi + 31) >> 5;
-                if (hi + lane < (nunits << 5)) tile[hi + lane] = 0;    // the sweep reads whole 32-byte units: no stale bytes
-                __syncwarp();
-                // ---- S: linear sweep of the staged bytes [lo, hi) ----
-                qn = 0;
-                uint32_t tile_high = 0;
-                for (int row = 0; row < nunits; row += 32) {
-                    const int unit = row + lane;
-                    const bool valid = unit < nunits;
-                    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
-                    if (valid) {
-                        v0 = lds_v4(tile_addr + ((uint32_t)unit << 5));
-                        v1 = lds_v4(tile_addr + ((uint32_t)unit << 5) + 16);
+                const uintptr_t g0 = reinterpret_cast<uintptr_t>(buf) + (uintptr_t)t0;
+                ubase = g0 & ~(uintptr_t)31;
+                nunits = tend > t0 ? (int64_t)((reinterpret_cast<uintptr_t>(buf) + (uintptr_t)tend - ubase + 31) >> 5) : 0;
+                seg = 0;
+                high = nunits > 1024;       // a tile swept in several segments: its winners are always re-checked
+                st = ST_SWEEP;
+            }
+            if (st == ST_SWEEP) {
+                // ---- S: up to 32 rows of 32 units, ROWS rows (ROWS KB per warp) in flight ----
+                const int64_t left = nunits - seg;
+                nrows = (int)((left < 1024 ? left : 1024) + 31) >> 5;
+                hitbits = 0;
+                uint32_t seen = 0;
+                for (int r = 0; r < nrows; r += ROWS) {
+                    uint4 va[ROWS], vb[ROWS];
+#pragma unroll
+                    for (int k = 0; k < ROWS; k++) {               // all loads first: ROWS KB per warp in flight
+                        const int64_t u = seg + ((int64_t)(r + k) << 5) + lane;
+                        va[k] = make_uint4(0, 0, 0, 0); vb[k] = va[k];
+                        if (u < nunits && r + k < nrows) {
+                            va[k] = ldg_nc_v4(reinterpret_cast<const void*>(ubase + ((uintptr_t)u << 5)));
+                            vb[k] = ldg_nc_v4(reinterpret_cast<const void*>(ubase + ((uintptr_t)u << 5) + 16));
+                        }
                     }
-                    const uint32_t any = first_mask<NR, HIGH>(sp, v0.x) | first_mask<NR, HIGH>(sp, v0.y) |
-                                         first_mask<NR, HIGH>(sp, v0.z) | first_mask<NR, HIGH>(sp, v0.w) |
-                                         first_mask<NR, HIGH>(sp, v1.x) | first_mask<NR, HIGH>(sp, v1.y) |
-                                         first_mask<NR, HIGH>(sp, v1.z) | first_mask<NR, HIGH>(sp, v1.w);
-                    tile_high |= v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w;
-                    const bool hit = valid && (any & 0x80808080u) != 0;
-                    const uint32_t hm = __ballot_sync(FULL, hit);
-                    if (hit) s_hits[qn + __popc(hm & ((1u << lane) - 1))] = (uint16_t)unit;
-                    qn += __popc(hm);
+#pragma unroll
+                    for (int k = 0; k < ROWS; k++) {
+                        const int64_t u = seg + ((int64_t)(r + k) << 5) + lane;
+                        const uint32_t h = (u < nunits && r + k < nrows) ? unit_any<NR, HIGH, TWO>(sp, va[k], vb[k], seen) : 0u;
+                        hitbits |= (h ? 1u : 0u) << (r + k);
+                    }
                 }
-                high = __any_sync(FULL, (tile_high & 0x80808080u) != 0);   // (up to 15 bytes in front of the tile are counted in: harmless)
-                st = ST_STRINGS;
+                high = high || __any_sync(FULL, (seen & 0x80808080u) != 0);   // (bytes next to the tile are counted in: harmless)
+                st = seg == 0 ? ST_STRINGS : ST_PUSH;              // the strings' own results are written before any unit is queued
                 it = 0;
             }
             if (st == ST_STRINGS) {
-                // ---- per string: degenerate texts, the start on the leading NUL; strings too long to stage are deferred ----
+                // ---- per string: degenerate texts, the start on the leading NUL ----
                 const int64_t first = (int64_t)t * spt;
+                if (sp.start_nul == 0 && p.q0_accepting == 0) {    // no string of the tile is decided here: all provisionally false
+                    for (int i = lane; i < count; i += 32) out[first + i] = 0;
+                    it = count;
+                }
                 while (it < count && sqn < 32) {
                     const int i = it + lane;
-                    bool r = false;
-                    uint32_t defer = 0;
+                    bool r = false, defer = false;
                     if (i < count) {
-                        const int32_t r0 = s_off[i], r1 = s_off[i + 1];
-                        if (r1 == OFF_BEYOND) defer = 1;
-                        else {
-                            const int len = r1 - r0;
-                            const uint32_t a = tile_addr + (uint32_t)r0;
-                            if (degenerate_text<1>(len, len ? lds_u8(a) : 0)) r = p.q0_accepting != 0;
-                            else if (sp.start_nul != 0) {
-                                r = attempt_wins(A, T, FetchShared{a}, len, (uint32_t)sp.start_nul, 0);
-                                if (r && p.prefix_mode == 1 && high) { r = false; defer = 2; }
-                            }
+                        const int64_t o0 = __ldg(offsets + first + i), o1 = __ldg(offsets + first + i + 1);
+                        const int64_t len = o1 - o0;
+                        if (len == 0 || (len == 1 && __ldg(buf + o0) == 0x20)) r = p.q0_accepting != 0;   // api_internal_m.F90:68-74
+                        else if (sp.start_nul != 0) {
+                            r = attempt_wins(A, T, FetchGlobal{buf + o0}, len, (uint32_t)sp.start_nul, 0);
+                            if (r && p.prefix_mode == 1 && high) { r = false; defer = true; }
                         }
-                        out[first + i] = r ? 1 : 0;                // provisional for deferred strings
+                        out[first + i] = r ? 1 : 0;                // provisional for a deferred string
                     }
-                    push(defer != 0, (uint32_t)i | (defer << SPARSE_KIND_SHIFT));
+                    const uint32_t m = __ballot_sync(FULL, defer);
+                    if (defer) s_starts[sqn + __popc(m & ((1u << lane) - 1))] = make_uint4((uint32_t)t, SPARSE_RECHECK, (uint32_t)i, 0u);
+                    sqn += __popc(m);
                     it += 32;
                 }
-                if (it < count) continue;                          // queue full: flush, then resume here
-                __syncwarp();                                      // results written before any attempt of this tile sets one
-                st = ST_CONFIRM;
+                if (it < count) continue;                          // queue full: run it, then resume here
+                __syncwarp();                                      // results written before any start of this tile sets one
+                st = ST_PUSH;
                 it = 0;
-                cand = 0;
             }
-            // ---- C: confirm.  One queued unit per lane; its candidates are taken in rounds (round k = every lane's
-            // k-th candidate).  A candidate survives unless two bytes prove the start dead. ----
-            while (sqn < 32) {
-                if (!__any_sync(FULL, cand != 0)) {
-                    if (it >= qn) { st = ST_NEW; t += gridDim.x * 8; break; }     // tile finished
-                    const int i = it + lane;
-                    if (i < qn) {
-                        const int unit = s_hits[i];
-                        const uint32_t ua = tile_addr + ((uint32_t)unit << 5);
-                        const uint4 v0 = lds_v4(ua), v1 = lds_v4(ua + 16);
-                        cand = pack_byte_flags(first_mask<NR, HIGH>(sp, v0.x)) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.y)) << 4) |
-                               (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.z)) << 8) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.w)) << 12) |
-                               (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.x)) << 16) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.y)) << 20) |
-                               (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.z)) << 24) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.w)) << 28);
-                        P = unit << 5;
-                        if (P < lo) cand &= 0xFFFFFFFFu << (lo - P);
-                        if (P + 32 > hi) cand &= 0xFFFFFFFFu >> (P + 32 - hi);
-                    }
-                    it += 32;
-                    continue;
+            // ---- queue the units that passed the filter ----
+            while (it < nrows && uqn < 32) {
+                const bool hit = (hitbits >> it) & 1u;
+                const uint32_t m = __ballot_sync(FULL, hit);
+                if (hit) {
+                    const unsigned long long u = (unsigned long long)(seg + ((int64_t)it << 5) + lane);
+                    s_units[uqn + __popc(m & ((1u << lane) - 1))] = make_uint4((uint32_t)t, high ? 0x80000000u : 0u, (uint32_t)u, (uint32_t)(u >> 32));
                 }
-                bool sv = false;
-                int pos = 0;
-                if (cand) {
-                    pos = P + __ffs(cand) - 1;
-                    cand &= cand - 1;
-                    const uint32_t b = lds_u8(tile_addr + (uint32_t)pos);
-                    const uint32_t w1 = T.next((uint32_t)sp.q0, b);
-                    if (w1 & (W_ACC | W_INTER)) sv = true;
-                    else if (w1 & W_STATE) {
-                        const uint32_t b1 = lds_u8(tile_addr + (uint32_t)pos + 1);      // may belong to the next string
-                        sv = ((T.next(w1, b1) | T.next(w1, 0u)) & (W_STATE | W_ACC)) != 0;
-                    }
-                }
-                push(sv, (uint32_t)(pos - lo));
+                uqn += __popc(m);
+                it++;
             }
+            if (it < nrows) continue;                              // queue full: run it, then resume here
+            seg += (int64_t)nrows << 5;
+            if (seg < nunits) st = ST_SWEEP;
+            else { st = ST_NEW; t += gridDim.x * 8; }
         }
-        if (sqn == 0) break;                                       // nothing waiting, no tiles left
-        const int run = sqn < 32 ? sqn : 32;
-        sparse_run_deferred<KIND>(p, sp, T, s_queue, run, spt, n, offsets, buf, out);
-        if (lane < sqn - run) { const uint2 x = s_queue[run + lane]; s_queue[lane] = x; }
-        sqn -= run;
-        __syncwarp();
+        // ---- outer loop: run a queue (the only calls of the kernel) ----
+        if (uqn >= 32 || (uqn > 0 && sqn < 32)) {                  // (uqn < 32 here means the tiles are used up)
+            const int run = uqn < 32 ? uqn : 32;
+            sparse_run_units<KIND, NR, HIGH>(p, sp, T, c, run, sqn);
+            if (lane < uqn - run) { const uint4 x = s_units[run + lane]; s_units[lane] = x; }
+            uqn -= run;
+            __syncwarp();
+        } else if (sqn > 0) {
+            const int run = sqn < 32 ? sqn : 32;
+            sparse_run_starts<KIND>(p, sp, T, c, run);
+            if (lane < sqn - run) { const uint4 x = s_starts[run + lane]; s_starts[lane] = x; }
+            sqn -= run;
+            __syncwarp();
+        } else {
+            break;                                                 // nothing waiting, no tiles left
+        }
     }
 }
 

@@ -90,6 +90,8 @@ typedef struct fx_pattern_info {
     int32_t sparse_lo[4];
     int32_t sparse_hi[4];
     int32_t sparse_high;      /* 1: F also holds bytes >= 0xC0 (lead bytes; every such byte is tried as a start) */
+    int32_t sparse_second;    /* >= 0: F is one byte and only this ASCII byte (or a lead byte) can follow it: the sweep
+                                 tests for the byte pair; -1 otherwise */
     int32_t sparse_used;      /* 1: the last ragged `.in.` launch used the sparse-start kernel */
 } fx_pattern_info;
 
