@@ -471,7 +471,7 @@ int launch_sparse_v(fx_pattern* p, const Plan& pl, const SparseParams& sp, int t
     auto kern = k_in_sparse<KIND, NR, HIGH, TWO, MINB, ROWS>;
     int64_t avg = n > 0 ? (total + n - 1) / n : 1;
     if (avg < 1) avg = 1;
-    int64_t want = env_int("FX_SPARSE_TILE_BYTES", 16 * 1024) / avg;
+    int64_t want = env_int("FX_SPARSE_TILE_BYTES", 24 * 1024) / avg;    // (one sweep segment holds 32 KB)
     int spt = (int)(want < 32 ? 32 : want > 4096 ? 4096 : want);
     spt = env_int("FX_TILE_STRINGS", spt);
     const int64_t ntiles = (n + spt - 1) / spt;
@@ -484,7 +484,12 @@ int launch_sparse_v(fx_pattern* p, const Plan& pl, const SparseParams& sp, int t
     long long wantg = (ntiles + 7) / 8;
     int grid = (int)(wantg < cap ? wantg : cap);
     if (grid < 1) grid = 1;
-    kern<<<grid, 256, smem, s>>>(pl.kp, sp, buf, off, n, total, out, spt, ntiles, table_smem);
+    // a pattern that neither accepts the empty text nor starts on the leading NUL decides no string in the per-string
+    // phase: every result is "false unless a start wins", so the results are cleared here, at copy speed
+    const int prezeroed = sp.start_nul == 0 && pl.kp.q0_accepting == 0;
+    if (prezeroed) CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)n, s));
+    kern<<<grid, 256, smem, s>>>(pl.kp, sp, buf, off, n, total, out, spt, ntiles, table_smem, prezeroed, env_int("FX_SPARSE_FLUSH", 0),
+                                   env_int("FX_SPARSE_STREAM_HINT", 1));
     g_launches++;
     return cuda_status(cudaGetLastError());
 }
@@ -492,11 +497,8 @@ int launch_sparse_v(fx_pattern* p, const Plan& pl, const SparseParams& sp, int t
 template <int KIND, int NR, bool HIGH, bool TWO>
 int launch_sparse_t(fx_pattern* p, const Plan& pl, const SparseParams& sp, int table_bytes, const uint8_t* buf,
                     const int64_t* off, int64_t n, int64_t total, uint8_t* out, cudaStream_t s) {
-    const int v = env_int("FX_SPARSE_VARIANT", 44);      // experiment knob: CTAs per SM x rows in flight
-    if (v == 34) return launch_sparse_v<KIND, NR, HIGH, TWO, 3, 4>(p, pl, sp, table_bytes, buf, off, n, total, out, s);
-    if (v == 44) return launch_sparse_v<KIND, NR, HIGH, TWO, 4, 4>(p, pl, sp, table_bytes, buf, off, n, total, out, s);
-    if (v == 32) return launch_sparse_v<KIND, NR, HIGH, TWO, 3, 2>(p, pl, sp, table_bytes, buf, off, n, total, out, s);
-    return launch_sparse_v<KIND, NR, HIGH, TWO, 4, 2>(p, pl, sp, table_bytes, buf, off, n, total, out, s);
+    // 4 CTAs per SM, 4 rows (4 KB per warp) in flight: the best of the measured combinations
+    return launch_sparse_v<KIND, NR, HIGH, TWO, 4, 4>(p, pl, sp, table_bytes, buf, off, n, total, out, s);
 }
 
 template <int KIND, bool HIGH>

@@ -726,8 +726,12 @@ struct SparseParams {
 
 // shared memory of K2c: classmap 256 | table | pad to 16 | 8 warps x (unit queue 64 x uint4 | start queue 64 x uint4)
 //   queue entry = {tile, kind | high << 31, low word, high word}
+//   in front of the queues: copies of the kernel parameters (KParams, SparseParams) and one SparseCtx per warp, for the
+//   out-of-line phases -- handed to them by reference from the kernel's parameter space they would be copied to every
+//   thread's local memory and read back through L1/L2 (measured: +20 % DRAM traffic)
 static constexpr int SPARSE_WARP_BYTES = 2 * 64 * 16;
-__host__ __device__ __forceinline__ int sparse_shared_head(int table_smem_bytes) { return (256 + table_smem_bytes + 15) & ~15; }
+static constexpr int SPARSE_PARAM_BYTES = 1024;
+__host__ __device__ __forceinline__ int sparse_shared_head(int table_smem_bytes) { return ((256 + table_smem_bytes + 15) & ~15) + SPARSE_PARAM_BYTES; }
 
 // Sweep filter for one 4-byte word: bit 7 set in every byte of w that may be in F (callers mask with 0x80808080).
 // A superset is fine -- every candidate is confirmed by the first table step before anything else happens -- so bit 7
@@ -823,8 +827,16 @@ static constexpr uint32_t SPARSE_START = 0, SPARSE_RECHECK = 2;
 // Out of line on purpose, and called only from the outer loop of the kernel: a call inside the sweep loop makes the
 // compiler keep that loop's whole state in callee-saved registers and spill it (measured: 200 bytes per thread).
 template <int KIND>
-__device__ __noinline__ void sparse_run_starts(const KParams& p, const SparseParams& sp, const Table<KIND>& T,
+__device__ __forceinline__ Table<KIND> sparse_table(const SparseParams& sp, uint32_t s_table, uint32_t s_cmap) {
+    Table<KIND> T;
+    T.s_table = s_table; T.s_cmap = s_cmap; T.g_table = sp.table; T.g_cmap = sp.classmap; T.shift = sp.row_shift;
+    return T;
+}
+
+template <int KIND>
+__device__ __noinline__ void sparse_run_starts(const KParams& p, const SparseParams& sp, uint32_t s_table, uint32_t s_cmap,
                                                const SparseCtx& c, int count) {
+    const Table<KIND> T = sparse_table<KIND>(sp, s_table, s_cmap);
     const int lane = threadIdx.x & 31;
     const Anchored A{sp.flags, sp.start_nul, sp.q0};
     __syncwarp();
@@ -836,11 +848,20 @@ __device__ __noinline__ void sparse_run_starts(const KParams& p, const SparsePar
         const int64_t val = (int64_t)(((unsigned long long)e.w << 32) | e.z);
         if (kind == SPARSE_START) {
             const int cnt = (int)((c.n - first) < c.spt ? (c.n - first) : c.spt);
-            const int64_t gpos = __ldg(off) + val;
-            int s = 0, sh = cnt;                                   // largest s with off[s] <= gpos
-            while (sh - s > 1) {
-                const int mid = (s + sh) >> 1;
-                if (__ldg(off + mid) <= gpos) s = mid; else sh = mid;
+            // largest s with off[s] <= gpos.  Interpolation search: the probes land next to the answer (one or two
+            // 32-byte sectors of offsets instead of the log2(cnt) scattered ones of a bisection); bisection takes over
+            // if the lengths are too uneven for that to converge
+            int64_t vlo = __ldg(off), vhi = __ldg(off + cnt);
+            const int64_t gpos = vlo + val;
+            int s = 0, sh = cnt;
+            for (int iter = 0; sh - s > 1; iter++) {
+                int mid = (s + sh) >> 1;
+                if (iter < 6) {
+                    mid = s + (int)((float)(gpos - vlo) * (float)(sh - s) / (float)(vhi - vlo));
+                    mid = mid <= s ? s + 1 : mid >= sh ? sh - 1 : mid;
+                }
+                const int64_t v = __ldg(off + mid);
+                if (v <= gpos) { s = mid; vlo = v; } else { sh = mid; vhi = v; }
             }
             const int64_t o0 = __ldg(off + s), o1 = __ldg(off + s + 1);
             const uint8_t* str = c.buf + o0;
@@ -861,8 +882,9 @@ __device__ __noinline__ void sparse_run_starts(const KParams& p, const SparsePar
 // one per lane.  Candidates are taken in rounds (round k = every lane's k-th candidate); a candidate survives unless
 // two bytes prove the start dead.  Survivors go to the start queue (sqn = its fill level), which is run when full.
 template <int KIND, int NR, bool HIGH>
-__device__ __noinline__ void sparse_run_units(const KParams& p, const SparseParams& sp, const Table<KIND>& T,
-                                              const SparseCtx& c, int count, int& sqn) {
+__device__ __noinline__ int sparse_run_units(const KParams& p, const SparseParams& sp, uint32_t s_table, uint32_t s_cmap,
+                                             const SparseCtx& c, int count, int sqn) {
+    const Table<KIND> T = sparse_table<KIND>(sp, s_table, s_cmap);
     const int lane = threadIdx.x & 31;
     const uint32_t FULL = 0xffffffffu;
     __syncwarp();
@@ -906,7 +928,7 @@ __device__ __noinline__ void sparse_run_units(const KParams& p, const SparsePara
             if (sv) c.starts[sqn + __popc(m & ((1u << lane) - 1))] = make_uint4(tile, SPARSE_START | flag, (uint32_t)rel, (uint32_t)(rel >> 32));
             sqn += __popc(m);
             if (sqn >= 32) {
-                sparse_run_starts<KIND>(p, sp, T, c, 32);
+                sparse_run_starts<KIND>(p, sp, s_table, s_cmap, c, 32);
                 if (lane < sqn - 32) { const uint4 x = c.starts[32 + lane]; c.starts[lane] = x; }
                 sqn -= 32;
                 __syncwarp();
@@ -914,13 +936,14 @@ __device__ __noinline__ void sparse_run_units(const KParams& p, const SparsePara
         }
     }
     __syncwarp();
+    return sqn;                                                    // the start queue's new fill level
 }
 
 template <int KIND, int NR, bool HIGH, bool TWO, int MINB, int ROWS>
 __global__ void __launch_bounds__(256, MINB) k_in_sparse(KParams p, SparseParams sp, const uint8_t* __restrict__ buf,
                                                       const int64_t* __restrict__ offsets, int64_t n, int64_t total,
                                                       uint8_t* __restrict__ out, int spt, int64_t ntiles,
-                                                      int table_smem_bytes) {
+                                                      int table_smem_bytes, int prezeroed, int flush_min, int stream_hint) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_cmap = smem;
     uint8_t* s_table = smem + 256;
@@ -930,12 +953,21 @@ __global__ void __launch_bounds__(256, MINB) k_in_sparse(KParams p, SparseParams
     KParams anch = p;                       // stage_table reads table / classmap / sizes from a KParams
     anch.table = sp.table; anch.classmap = sp.classmap; anch.table_words = sp.table_words; anch.row_shift = sp.row_shift;
     Table<KIND> T = stage_table<KIND>(anch, s_table, s_cmap);
-    __syncthreads();                        // the only block-wide step: the table is staged
+    // shared copies of the parameters for the out-of-line phases
+    static_assert(sizeof(KParams) + sizeof(SparseParams) + 8 * sizeof(SparseCtx) <= SPARSE_PARAM_BYTES, "parameter block");
+    uint8_t* s_params = smem + sparse_shared_head(table_smem_bytes) - SPARSE_PARAM_BYTES;
+    KParams* sh_p = reinterpret_cast<KParams*>(s_params);
+    SparseParams* sh_sp = reinterpret_cast<SparseParams*>(s_params + sizeof(KParams));
+    SparseCtx* sh_c = reinterpret_cast<SparseCtx*>(s_params + sizeof(KParams) + sizeof(SparseParams)) + warp;
+    if (threadIdx.x == 0) { *sh_p = p; *sh_sp = sp; }
+    if (lane == 0) {
+        sh_c->buf = buf; sh_c->offsets = offsets; sh_c->out = out; sh_c->n = n; sh_c->total = total; sh_c->spt = spt;
+        sh_c->units = s_units; sh_c->starts = s_starts;
+    }
+    __syncthreads();                        // the only block-wide step: table and parameter copies are staged
     const Anchored A{sp.flags, sp.start_nul, sp.q0};
     const uint32_t FULL = 0xffffffffu;
     const int nt = (int)ntiles;             // the host keeps n (hence ntiles) below 2^31
-    SparseCtx c;
-    c.buf = buf; c.offsets = offsets; c.out = out; c.n = n; c.total = total; c.spt = spt; c.units = s_units; c.starts = s_starts;
 
     // The warp's state machine.  The inner loop (no calls) advances it until 32 units or 32 starts are waiting or
     // the tiles are used up; the outer loop runs the queues and comes back.
@@ -951,11 +983,12 @@ __global__ void __launch_bounds__(256, MINB) k_in_sparse(KParams p, SparseParams
     int64_t nx0 = 0, nx1 = 0;               // byte range of the warp's next tile
     bool have_next = false;
 
+    bool drain = false;                     // run the queues even if they are not full (end of a tile, end of the tiles)
     for (;;) {
         for (;;) {
-            if (uqn >= 32 || sqn >= 32) break;
+            if (uqn >= 32 || sqn >= 32 || drain) break;
             if (st == ST_NEW) {
-                if (t >= nt) break;
+                if (t >= nt) { drain = true; break; }
                 const int64_t first = (int64_t)t * spt;
                 count = (int)((n - first) < spt ? (n - first) : spt);
                 const int64_t t0 = have_next ? nx0 : __ldg(offsets + first), tend = have_next ? nx1 : __ldg(offsets + first + count);
@@ -984,8 +1017,13 @@ __global__ void __launch_bounds__(256, MINB) k_in_sparse(KParams p, SparseParams
                         const int64_t u = seg + ((int64_t)(r + k) << 5) + lane;
                         va[k] = make_uint4(0, 0, 0, 0); vb[k] = va[k];
                         if (u < nunits && r + k < nrows) {
-                            va[k] = ldg_nc_v4(reinterpret_cast<const void*>(ubase + ((uintptr_t)u << 5)));
-                            vb[k] = ldg_nc_v4(reinterpret_cast<const void*>(ubase + ((uintptr_t)u << 5) + 16));
+                            if (stream_hint) {
+                                va[k] = ldg_nc_v4(reinterpret_cast<const void*>(ubase + ((uintptr_t)u << 5)));
+                                vb[k] = ldg_nc_v4(reinterpret_cast<const void*>(ubase + ((uintptr_t)u << 5) + 16));
+                            } else {
+                                va[k] = __ldg(reinterpret_cast<const uint4*>(ubase + ((uintptr_t)u << 5)));
+                                vb[k] = __ldg(reinterpret_cast<const uint4*>(ubase + ((uintptr_t)u << 5) + 16));
+                            }
                         }
                     }
 #pragma unroll
@@ -1002,10 +1040,7 @@ __global__ void __launch_bounds__(256, MINB) k_in_sparse(KParams p, SparseParams
             if (st == ST_STRINGS) {
                 // ---- per string: degenerate texts, the start on the leading NUL ----
                 const int64_t first = (int64_t)t * spt;
-                if (sp.start_nul == 0 && p.q0_accepting == 0) {    // no string of the tile is decided here: all provisionally false
-                    for (int i = lane; i < count; i += 32) out[first + i] = 0;
-                    it = count;
-                }
+                if (prezeroed) it = count;                         // no string is decided here, and the host has cleared `out`
                 while (it < count && sqn < 32) {
                     const int i = it + lane;
                     bool r = false, defer = false;
@@ -1043,23 +1078,30 @@ __global__ void __launch_bounds__(256, MINB) k_in_sparse(KParams p, SparseParams
             if (it < nrows) continue;                              // queue full: run it, then resume here
             seg += (int64_t)nrows << 5;
             if (seg < nunits) st = ST_SWEEP;
-            else { st = ST_NEW; t += gridDim.x * 8; }
+            else {
+                // Tile finished.  What it queued is still in L2 now -- a tile later it no longer is (the whole grid streams
+                // through L2 at once) -- so the queues are run here unless they hold next to nothing.
+                st = ST_NEW;
+                t += gridDim.x * 8;
+                drain = flush_min > 0 && uqn + sqn >= flush_min;
+            }
         }
         // ---- outer loop: run a queue (the only calls of the kernel) ----
-        if (uqn >= 32 || (uqn > 0 && sqn < 32)) {                  // (uqn < 32 here means the tiles are used up)
+        if (uqn >= 32 || (drain && uqn > 0)) {
             const int run = uqn < 32 ? uqn : 32;
-            sparse_run_units<KIND, NR, HIGH>(p, sp, T, c, run, sqn);
+            sqn = sparse_run_units<KIND, NR, HIGH>(*sh_p, *sh_sp, T.s_table, T.s_cmap, *sh_c, run, sqn);
             if (lane < uqn - run) { const uint4 x = s_units[run + lane]; s_units[lane] = x; }
             uqn -= run;
             __syncwarp();
-        } else if (sqn > 0) {
+        } else if (sqn >= 32 || (drain && sqn > 0)) {
             const int run = sqn < 32 ? sqn : 32;
-            sparse_run_starts<KIND>(p, sp, T, c, run);
+            sparse_run_starts<KIND>(*sh_p, *sh_sp, T.s_table, T.s_cmap, *sh_c, run);
             if (lane < sqn - run) { const uint4 x = s_starts[run + lane]; s_starts[lane] = x; }
             sqn -= run;
             __syncwarp();
         } else {
-            break;                                                 // nothing waiting, no tiles left
+            drain = false;                                         // both queues are empty
+            if (st == ST_NEW && t >= nt) break;                    // ... and no tiles are left
         }
     }
 }
