@@ -56,6 +56,8 @@ struct FirstSet {
     int nr = 0;
     uint8_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
     bool high = false;
+    int sweep_nr = 0;            // the ranges the sweep tests: lo/hi with close neighbours merged (a superset of F)
+    uint8_t sweep_lo[4] = {0, 0, 0, 0}, sweep_hi[4] = {0, 0, 0, 0};
     bool two = false;            // one first byte, and after it one ASCII byte (plus, maybe, lead bytes) keeps the automaton alive
     uint8_t second = 0;
     bool second_high = false;
@@ -131,10 +133,10 @@ int env_int(const char* name, int dflt) {
 // boundary), its ASCII part fits 4 ranges; and the leading-NUL start does not accept by itself (no "empty winner" that would stop the
 // reference's search early, api_internal_m.F90:139-150).  Worth it only when candidates are rare: without knowing the
 // text, "F holds at most FX_SPARSE_MAX_FIRST (default 6) ASCII bytes" stands in for that.
-bool sparse_first_set(const fx::ByteTable& at, FirstSet& fs) {
+bool sparse_first_set(const fx::ByteTable& at, FirstSet& fs, bool for_in) {
     fs = FirstSet();
     if (at.q0 == 0) return false;
-    if (at.start_nul != 0 && (at.flags[(size_t)at.start_nul] & fxk::SF_ACC)) return false;
+    if (for_in && at.start_nul != 0 && (at.flags[(size_t)at.start_nul] & fxk::SF_ACC)) return false;
     bool in_f[256];
     for (int b = 0; b < 256; b++) {
         const uint16_t w = at.table[((size_t)at.q0 << at.row_shift) + at.classmap[b]];
@@ -155,6 +157,13 @@ bool sparse_first_set(const fx::ByteTable& at, FirstSet& fs) {
         b = e + 1;
     }
     if (fs.nr == 0 && !fs.high) return false;
+    // Sweep ranges may over-approximate F (every candidate is confirmed by the table): neighbours at most 9 byte
+    // values apart are merged -- {NUL, LF, CR}, the bytes `^` can consume, become the one range [0x00, 0x0D].
+    fs.sweep_nr = 0;
+    for (int r = 0; r < fs.nr; r++) {
+        if (fs.sweep_nr > 0 && fs.lo[r] - fs.sweep_hi[fs.sweep_nr - 1] <= 10) fs.sweep_hi[fs.sweep_nr - 1] = fs.hi[r];
+        else { fs.sweep_lo[fs.sweep_nr] = fs.lo[r]; fs.sweep_hi[fs.sweep_nr] = fs.hi[r]; fs.sweep_nr++; }
+    }
     // the two-byte sweep filter: F's ASCII part is one byte V1, the step q0 -V1-> w1 neither accepts nor enters a
     // sequence, and from w1 exactly one ASCII byte V2 != NUL survives (no continuation byte does)
     if (fs.nr == 1 && fs.lo[0] == fs.hi[0]) {
@@ -504,19 +513,29 @@ int launch_sparse_t(fx_pattern* p, const Plan& pl, const SparseParams& sp, int t
 template <int KIND, bool HIGH>
 int launch_sparse_k(fx_pattern* p, const Plan& pl, const SparseParams& sp, int tb, const uint8_t* buf, const int64_t* off,
                     int64_t n, int64_t total, uint8_t* out, cudaStream_t s) {
-    if (p->first.nr == 1 && p->first.lo[0] == p->first.hi[0]) {      // one byte value: the cheaper zero-byte test
-        SparseParams one = sp;
-        one.add_lo[0] = p->first.lo[0] * 0x01010101u;
+    if (p->first.sweep_nr == 1 && p->first.sweep_lo[0] == p->first.sweep_hi[0]) {      // one byte value: the cheaper zero-byte test
+        const SparseParams& one = sp;      // (fill_sweep has put the byte value into add_lo[0])
         if (p->first.two && env_int("FX_SPARSE_TWO", 1)) return launch_sparse_t<KIND, -1, HIGH, true>(p, pl, one, tb, buf, off, n, total, out, s);
         return launch_sparse_t<KIND, -1, HIGH, false>(p, pl, one, tb, buf, off, n, total, out, s);
     }
-    switch (p->first.nr) {
+    switch (p->first.sweep_nr) {
         case 0: return launch_sparse_t<KIND, 0, true, false>(p, pl, sp, tb, buf, off, n, total, out, s);
         case 1: return launch_sparse_t<KIND, 1, HIGH, false>(p, pl, sp, tb, buf, off, n, total, out, s);
         case 2: return launch_sparse_t<KIND, 2, HIGH, false>(p, pl, sp, tb, buf, off, n, total, out, s);
         case 3: return launch_sparse_t<KIND, 3, HIGH, false>(p, pl, sp, tb, buf, off, n, total, out, s);
         default: return launch_sparse_t<KIND, 4, HIGH, false>(p, pl, sp, tb, buf, off, n, total, out, s);
     }
+}
+
+void fill_sweep(const FirstSet& f, SparseParams& sp) {
+    for (int r = 0; r < 4; r++) {
+        const int k = r < f.sweep_nr ? r : 0;       // unused slots repeat range 0
+        sp.add_lo[r] = (0x80u - f.sweep_lo[k]) * 0x01010101u;
+        sp.add_hi[r] = (0x7Fu - f.sweep_hi[k]) * 0x01010101u;
+    }
+    if (f.sweep_nr == 1 && f.sweep_lo[0] == f.sweep_hi[0]) sp.add_lo[0] = f.sweep_lo[0] * 0x01010101u;   // NR = -1 form
+    sp.second = f.second * 0x01010101u;
+    sp.second_high = f.second_high ? 0xFFFFFFFFu : 0u;
 }
 
 int launch_sparse(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int64_t* off, int64_t n, int64_t total,
@@ -528,13 +547,7 @@ int launch_sparse(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int64
     sp.table_words = (int)at.table.size();
     sp.row_shift = at.row_shift;
     sp.q0 = at.q0; sp.start_nul = at.start_nul;
-    for (int r = 0; r < 4; r++) {
-        const int k = r < p->first.nr ? r : 0;       // unused slots repeat range 0
-        sp.add_lo[r] = (0x80u - p->first.lo[k]) * 0x01010101u;
-        sp.add_hi[r] = (0x7Fu - p->first.hi[k]) * 0x01010101u;
-    }
-    sp.second = p->first.second * 0x01010101u;
-    sp.second_high = p->first.second_high ? 0xFFFFFFFFu : 0u;
+    fill_sweep(p->first, sp);
     const int tb = (int)at.table.size() * 2;
     const bool smem_table = p->residency != FX_TABLE_GLOBAL && tb <= env_int("FX_SPARSE_SMEM_TABLE_BYTES", 24 * 1024);
     if (smem_table)
@@ -661,6 +674,42 @@ int launch_scan_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const ScanW
     return cuda_status(cudaGetLastError());
 }
 
+template <int KIND, int NR, bool HIGH>
+int launch_scan_sparse_t(fx_pattern* p, const Plan& pl, const SparseParams& sp, const uint8_t* buf, const ScanWindow& W,
+                         unsigned long long* best, cudaStream_t s) {
+    auto kern = k_buffer_scan_sparse<KIND, NR, HIGH>;
+    int table_smem = (int)staged_bytes(pl);
+    size_t smem = (size_t)scan_sparse_smem_bytes(table_smem);
+    int bps = 0;
+    int rc = occupancy_grid(kern, 256, smem, p->dev.sm_count, bps);
+    if (rc) return rc;
+    long long groups = ((W.start_hi - W.start_lo) >> 12) + 1;       // 4 KB per warp and step
+    long long want = (groups + 7) / 8;
+    long long cap = (long long)p->dev.sm_count * bps;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    kern<<<grid, 256, smem, s>>>(pl.kp, sp, buf, W, best, table_smem);
+    g_launches++;
+    return cuda_status(cudaGetLastError());
+}
+
+template <int KIND>
+int launch_scan_sparse(fx_pattern* p, const Plan& pl, const uint8_t* buf, const ScanWindow& W, unsigned long long* best,
+                       cudaStream_t s) {
+    SparseParams sp;
+    memset(&sp, 0, sizeof(sp));
+    fill_sweep(p->first, sp);
+    const FirstSet& f = p->first;
+    const bool one = f.sweep_nr == 1 && f.sweep_lo[0] == f.sweep_hi[0];
+    if (f.sweep_nr == 0) return launch_scan_sparse_t<KIND, 0, true>(p, pl, sp, buf, W, best, s);
+    if (one) return f.high ? launch_scan_sparse_t<KIND, -1, true>(p, pl, sp, buf, W, best, s)
+                           : launch_scan_sparse_t<KIND, -1, false>(p, pl, sp, buf, W, best, s);
+    if (f.sweep_nr == 1) return f.high ? launch_scan_sparse_t<KIND, 1, true>(p, pl, sp, buf, W, best, s)
+                                       : launch_scan_sparse_t<KIND, 1, false>(p, pl, sp, buf, W, best, s);
+    return f.high ? launch_scan_sparse_t<KIND, 2, true>(p, pl, sp, buf, W, best, s)
+                  : launch_scan_sparse_t<KIND, 2, false>(p, pl, sp, buf, W, best, s);
+}
+
 // scan starts [start_lo, start_hi) of a window; d_best[0] (min key) and d_best[1] (undecided attempts) must have been
 // initialised by the caller
 int launch_scan(fx_pattern* p, const uint8_t* buf, const ScanWindow& W, unsigned long long* best, cudaStream_t s) {
@@ -672,6 +721,13 @@ int launch_scan(fx_pattern* p, const uint8_t* buf, const ScanWindow& W, unsigned
     int rc = make_plan(p, pl);
     if (rc) return rc;
     if (pl.kp.all_active || W.start_lo == W.start_hi) return FX_OK;
+    p->last_sparse = 0;
+    if (p->sparse && p->first.sweep_nr <= 2 && env_int("FX_SPARSE", 1)) {     // SWAR first-byte filter
+        p->last_sparse = 1;
+        if (pl.kind == 1) return launch_scan_sparse<1>(p, pl, buf, W, best, s);
+        if (pl.kind == 2) return launch_scan_sparse<2>(p, pl, buf, W, best, s);
+        return launch_scan_sparse<3>(p, pl, buf, W, best, s);
+    }
     if (pl.kind == 1) return launch_scan_t<1>(p, pl, buf, W, best, s);
     if (pl.kind == 2) return launch_scan_t<2>(p, pl, buf, W, best, s);
     return launch_scan_t<3>(p, pl, buf, W, best, s);
@@ -738,11 +794,13 @@ int fx_compile(const void* pattern, int64_t plen, int op, fx_pattern** out) {
         if (p->anchored.status == fx::OK) {
             p->has_anchored = true;
             if (needed) p->prefix_mode = prefilter_is_neutral(p->anchored) ? 1 : 2;
-            p->sparse = p->prefix_mode != 2 && sparse_first_set(p->anchored.bt, p->first);
+            p->sparse = p->prefix_mode != 2 && sparse_first_set(p->anchored.bt, p->first, true);
         } else if (needed) {
             p->prog.status = p->anchored.status;
         }
     }
+    if (p->prog.status == fx::OK && op == FX_OP_REGEX && !p->prog.literal_only && !p->prog.prefix_active)
+        p->sparse = sparse_first_set(p->prog.bt, p->first, false);      // the long-buffer scan can use the SWAR filter
     *out = p;
     return p->prog.status;
 }

@@ -1728,6 +1728,135 @@ __global__ void __launch_bounds__(256) k_buffer_scan(KParams p, const uint8_t* _
     if (qn > 0) run_batch(qn);
 }
 
+// K4 with the SWAR first-byte filter of K2c, for patterns whose set F of possible first bytes is small (C4: the
+// bytes that `^` can consume).  Same result as k_buffer_scan -- the smallest start whose anchored attempt wins -- but
+// the sweep costs a few integer instructions per 4 bytes instead of one shared-memory lookup per byte:
+//   sweep   warps take groups of 4 rows x 32 lanes x 32 bytes (4 KB in flight per warp), front to back, and stop
+//           behind the best start found so far; 32-byte units that may hold a candidate are queued per warp;
+//   units   32 at a time, one per lane: per-byte candidate mask, candidates confirmed in rounds by the first two
+//           table steps (an open window end leaves the second undecided); survivors are queued;
+//   starts  32 at a time: boundary check + anchored attempt from global memory (try_start), 64-bit atomicMin.
+// shared memory: classmap 256 | table | 8 warps x (unit queue 64 x int64 | start queue 64 x int64)
+__host__ __device__ __forceinline__ int scan_sparse_smem_bytes(int table_smem_bytes) {
+    return ((256 + table_smem_bytes + 15) & ~15) + 8 * 2 * 64 * 8;
+}
+
+template <int KIND, int NR, bool HIGH>
+__global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparseParams sp, const uint8_t* __restrict__ buf,
+                                                            ScanWindow W, unsigned long long* __restrict__ best,
+                                                            int table_smem_bytes) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_cmap = smem;
+    uint8_t* s_table = smem + 256;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t* s_units = reinterpret_cast<int64_t*>(smem + ((256 + table_smem_bytes + 15) & ~15)) + warp * 128;
+    int64_t* s_starts = s_units + 64;
+    Table<KIND> T = stage_table<KIND>(p, s_table, s_cmap);
+    __syncthreads();
+    const uint32_t q0 = (uint32_t)p.q0;
+    const int64_t len = W.len;
+    const bool open_end = !W.last;
+    unsigned long long* overflow = best + 1;
+    const uint32_t FULL = 0xffffffffu;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && W.first) {   // start 1 = the leading NUL sentinel
+        const Anchored A{p.flags, p.start_nul, p.q0};
+        if (attempt_at(A, T, FetchGlobal{buf}, len, 1) >= 0) atomicMin(best, 1ull);
+    }
+    const uintptr_t gbuf = reinterpret_cast<uintptr_t>(buf);
+    const uintptr_t ubase = (gbuf + (uintptr_t)W.start_lo) & ~(uintptr_t)31;      // 32-byte units aligned to the buffer ADDRESS
+    const int64_t nunits = W.start_hi > W.start_lo ? (int64_t)((gbuf + (uintptr_t)W.start_hi - ubase + 31) >> 5) : 0;
+    const int64_t pos_base = (int64_t)ubase - (int64_t)gbuf;                      // window position of unit 0's first byte (may be < start_lo)
+    int uqn = 0, sqn = 0;
+
+    auto run_starts = [&](int count) {
+        __syncwarp();
+        if (lane < count) {
+            const int64_t pos = s_starts[lane];
+            if (try_start(p, T, buf, len, pos, __ldg(buf + pos), open_end, overflow))
+                atomicMin(best, (unsigned long long)(W.origin + pos) + 2);
+        }
+        __syncwarp();
+    };
+    auto run_units = [&](int count) {
+        __syncwarp();
+        uint32_t cand = 0;
+        int64_t P = 0;
+        if (lane < count) {
+            const int64_t u = s_units[lane];
+            const uintptr_t ua = ubase + ((uintptr_t)u << 5);
+            const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(ua)), v1 = __ldg(reinterpret_cast<const uint4*>(ua + 16));
+            cand = pack_byte_flags(first_mask<NR, HIGH>(sp, v0.x)) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.y)) << 4) |
+                   (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.z)) << 8) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.w)) << 12) |
+                   (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.x)) << 16) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.y)) << 20) |
+                   (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.z)) << 24) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.w)) << 28);
+            P = pos_base + (u << 5);
+            if (P < W.start_lo) cand &= 0xFFFFFFFFu << (int)(W.start_lo - P);
+            if (P + 32 > W.start_hi) cand &= (P >= W.start_hi) ? 0u : (0xFFFFFFFFu >> (int)(P + 32 - W.start_hi));
+        }
+        while (__any_sync(FULL, cand != 0)) {
+            bool sv = false;
+            int64_t pos = 0;
+            if (cand) {
+                pos = P + __ffs(cand) - 1;
+                cand &= cand - 1;
+                const uint32_t b = __ldg(buf + pos);
+                const uint32_t w1 = T.next(q0, b);
+                if (w1 & (W_ACC | W_INTER)) sv = true;               // undecidable in two bytes: keep
+                else if (w1 & W_STATE) {
+                    if (pos + 1 < len) sv = (T.next(w1, __ldg(buf + pos + 1)) & (W_STATE | W_ACC)) != 0;
+                    else sv = open_end ? true : (T.next(w1, 0u) & (W_STATE | W_ACC)) != 0;   // the trailing NUL, or unknown
+                }
+            }
+            const uint32_t m = __ballot_sync(FULL, sv);
+            if (m) {
+                if (sv) s_starts[sqn + __popc(m & ((1u << lane) - 1))] = pos;
+                sqn += __popc(m);
+                if (sqn >= 32) {
+                    run_starts(32);
+                    if (lane < sqn - 32) { const int64_t x = s_starts[32 + lane]; s_starts[lane] = x; }
+                    sqn -= 32;
+                    __syncwarp();
+                }
+            }
+        }
+    };
+
+    const int64_t gwarp = (int64_t)blockIdx.x * 8 + warp, nwarps = (int64_t)gridDim.x * 8;
+    for (int64_t g0 = gwarp * 128; g0 < nunits; g0 += nwarps * 128) {
+        unsigned long long cur = 0;
+        if (lane == 0) cur = *reinterpret_cast<volatile unsigned long long*>(best);
+        cur = __shfl_sync(FULL, cur, 0);
+        if (cur != NO_START && (unsigned long long)(W.origin + pos_base + (g0 << 5)) + 2 > cur) break;   // behind the winner
+        uint4 va[4], vb[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t u = g0 + k * 32 + lane;
+            va[k] = make_uint4(0, 0, 0, 0); vb[k] = va[k];
+            if (u < nunits) {
+                va[k] = ldg_nc_v4(reinterpret_cast<const void*>(ubase + ((uintptr_t)u << 5)));
+                vb[k] = ldg_nc_v4(reinterpret_cast<const void*>(ubase + ((uintptr_t)u << 5) + 16));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t u = g0 + k * 32 + lane;
+            uint32_t seen = 0;
+            const bool hit = u < nunits && unit_any<NR, HIGH, false>(sp, va[k], vb[k], seen) != 0;
+            const uint32_t m = __ballot_sync(FULL, hit);
+            if (hit) s_units[uqn + __popc(m & ((1u << lane) - 1))] = u;
+            uqn += __popc(m);
+            if (uqn >= 32) {
+                run_units(32);
+                if (lane < uqn - 32) { const int64_t x = s_units[32 + lane]; s_units[lane] = x; }
+                uqn -= 32;
+                __syncwarp();
+            }
+        }
+    }
+    if (uqn > 0) run_units(uqn);
+    if (sqn > 0) run_starts(sqn);
+}
+
 // second step: longest end for the winning start; also the literal / degenerate cases.  `key` is the winning
 // start as an S position of the whole text; the window must hold the text from that start to the end of its match.
 __global__ void k_buffer_finish(KParams p, const uint8_t* __restrict__ buf, ScanWindow W,
