@@ -1562,12 +1562,24 @@ __device__ __forceinline__ bool try_start(const KParams& p, const Table<KIND>& T
                                           unsigned long long* overflow) {
     if ((b & 0xC0) == 0x80 && !continuation_is_boundary(buf, len, pos)) return false;
     const Anchored A{p.flags, p.start_nul, p.q0};
-    if (!open_end) return run_attempt(A, T, FetchGlobal{buf}, len, (uint32_t)p.q0, pos, -1) >= 0;
+    // The plain stretch first: as long as the next state neither accepts nor enters a multi-byte sequence, a step is
+    // one load and one lookup (for C4 that is the whole line behind `^ERROR`).  Whatever comes then goes through the
+    // general loop, from the state and position reached (no accept has been seen so far).
+    uint32_t st = (uint32_t)p.q0;
+    int64_t at = pos;
+    while (at < len) {
+        const uint32_t nw = T.next(st, __ldg(buf + at));
+        if (nw & (W_ACC | W_INTER)) break;
+        if (nw == 0) return false;
+        st = nw;
+        at++;
+    }
+    if (!open_end) return run_attempt(A, T, FetchGlobal{buf}, len, st, at, -1) >= 0;
     // open end: walk only the bytes we have; alive at the end -> undecided
-    uint32_t w = (uint32_t)p.q0;
+    uint32_t w = st;
     int64_t seq = 0, last = -1;
     bool inter = false;
-    for (int64_t j = pos; j < len; j++) {
+    for (int64_t j = at; j < len; j++) {
         const uint32_t c = __ldg(buf + j);
         if (inter && (c & 0xC0) != 0x80) {
             const uint32_t f = __ldg(A.flags + (w & W_STATE));
@@ -1799,13 +1811,20 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
             if (cand) {
                 pos = P + __ffs(cand) - 1;
                 cand &= cand - 1;
-                const uint32_t b = __ldg(buf + pos);
-                const uint32_t w1 = T.next(q0, b);
-                if (w1 & (W_ACC | W_INTER)) sv = true;               // undecidable in two bytes: keep
-                else if (w1 & W_STATE) {
-                    if (pos + 1 < len) sv = (T.next(w1, __ldg(buf + pos + 1)) & (W_STATE | W_ACC)) != 0;
-                    else sv = open_end ? true : (T.next(w1, 0u) & (W_STATE | W_ACC)) != 0;   // the trailing NUL, or unknown
+                // up to four plain steps: a start survives unless they prove it dead (undecided -- an accept, a multi-byte
+                // sequence, the end of the window -- keeps it).  Four rather than two so that what reaches the attempt
+                // phase is uniformly long-lived (C4: `CR LF I...` dies here, only ERROR lines go on).
+                uint32_t st = q0;
+                int64_t q = pos;
+                sv = true;
+                for (int k = 0; k < 4 && q < len; k++, q++) {
+                    const uint32_t nw = T.next(st, __ldg(buf + q));
+                    if (nw & (W_ACC | W_INTER)) break;
+                    if (nw == 0) { sv = false; break; }
+                    st = nw;
                 }
+                if (sv && q >= len && !open_end && (st & (W_ACC | W_INTER)) == 0 && st != q0)   // only the trailing NUL is left
+                    sv = (T.next(st, 0u) & (W_STATE | W_ACC)) != 0;
             }
             const uint32_t m = __ballot_sync(FULL, sv);
             if (m) {
