@@ -19,7 +19,7 @@ SYMBOLS = [
     "fx_status_message", "fx_compile", "fx_pattern_free", "fx_pattern_get_info", "fx_pattern_set_residency",
     "fx_pattern_literals", "fx_pattern_tables", "fx_pattern_span_tables", "fx_is_valid_regex",
     "fx_match_fixed_dev", "fx_in_fixed_dev", "fx_match_batch_dev", "fx_in_batch_dev", "fx_regex_batch_dev",
-    "fx_regex_buffer_work_bytes", "fx_regex_buffer_dev", "fx_buffer_scan_dev", "fx_buffer_finish_dev",
+    "fx_regex_buffer_work_bytes", "fx_regex_buffer_dev", "fx_buffer_scan_dev", "fx_buffer_scan_all_dev", "fx_buffer_finish_dev",
     "fx_match_fixed", "fx_in_fixed", "fx_match_batch", "fx_in_batch", "fx_regex_batch", "fx_regex_buffer",
     "fx_in", "fx_match", "fx_regex", "fx_launch_count",
 ]
@@ -31,7 +31,7 @@ class PatternInfo(C.Structure):
         "table_bytes", "direct_bytes", "literal_all_len", "literal_prefix_len", "literal_suffix_len",
         "literal_only", "residency", "direct", "prefix_mode", "sparse", "sparse_ranges")] + [
         ("sparse_lo", C.c_int32 * 4), ("sparse_hi", C.c_int32 * 4), ("sparse_high", C.c_int32),
-        ("sparse_second", C.c_int32), ("sparse_used", C.c_int32)]
+        ("sparse_second", C.c_int32), ("sparse_used", C.c_int32), ("prefix_scan", C.c_int32)]
 
 
 _lib = None
@@ -67,6 +67,7 @@ def lib():
     L.fx_regex_buffer_work_bytes.argtypes = [i64]
     L.fx_regex_buffer_dev.argtypes = [vp, u8p, i64, vp, vp, vp]
     L.fx_buffer_scan_dev.argtypes = [vp, u8p, i64, i64, i64, i64, C.c_int, C.c_int, vp, vp]
+    L.fx_buffer_scan_all_dev.argtypes = [vp, u8p, i64, i64, i64, i64, C.c_int, C.c_int, vp, vp]
     L.fx_buffer_finish_dev.argtypes = [vp, u8p, i64, i64, C.c_int, vp, vp, vp]
     for name in ("fx_match_fixed", "fx_in_fixed"):
         getattr(L, name).argtypes = [vp, u8p, i64, i64, u8p]

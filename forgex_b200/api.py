@@ -223,6 +223,11 @@ class Pattern:
         _check(L.lib().fx_buffer_scan_dev(self.h, _ptr(d_window), window_len, start_lo, start_hi, origin,
                                           int(is_first), int(is_last), _ptr(d_best), self._stream()), "fx_buffer_scan_dev")
 
+    def buffer_scan_all_dev(self, d_window, window_len, start_lo, start_hi, origin, is_first, is_last, d_best):
+        _check(L.lib().fx_buffer_scan_all_dev(self.h, _ptr(d_window), window_len, start_lo, start_hi, origin,
+                                              int(is_first), int(is_last), _ptr(d_best), self._stream()),
+               "fx_buffer_scan_all_dev")
+
     def buffer_finish_dev(self, d_window, window_len, origin, is_last, d_key, d_from_to):
         _check(L.lib().fx_buffer_finish_dev(self.h, _ptr(d_window), window_len, origin, int(is_last), _ptr(d_key),
                                             _ptr(d_from_to), self._stream()), "fx_buffer_finish_dev")

@@ -72,6 +72,7 @@ struct fx_pattern {
     fx::Program anchored;        // FX_OP_IN: the anchored (REGEX-mode) automaton, for the prefix replay and for K2c
     bool has_anchored = false;
     int prefix_mode = 0;         // see KParams::prefix_mode
+    bool prefix_scan = false;    // FX_OP_REGEX: the long-buffer path can take the prefix literal's occurrences as its candidates
     FirstSet first;              // bytes that survive the first step out of q0 of the anchored automaton
     bool sparse = false;         // the sparse-start kernel (K2c) may serve `.in.` batches
     int last_sparse = 0;
@@ -247,7 +248,7 @@ int ensure_device(fx_pattern* p) {
         CUDA_TRY(cudaMalloc(&d.r_ascii, 128));
         CUDA_TRY(cudaMemcpy(d.r_ascii, ascii, 128, cudaMemcpyHostToDevice));
     }
-    CUDA_TRY(cudaMalloc(&d.w_best, 16));
+    CUDA_TRY(cudaMalloc(&d.w_best, 32));
     CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
     d.device = dev;
     return FX_OK;
@@ -657,7 +658,7 @@ int launch_regex_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, i
 
 template <int KIND>
 int launch_scan_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const ScanWindow& W, unsigned long long* best,
-                  cudaStream_t s) {
+                  cudaStream_t s, const unsigned long long* gate) {
     auto kern = k_buffer_scan<KIND>;
     int table_smem = (int)staged_bytes(pl);
     size_t smem = (size_t)scan_smem_bytes(table_smem);
@@ -669,15 +670,15 @@ int launch_scan_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const ScanW
     long long cap = (long long)p->dev.sm_count * bps;
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    kern<<<grid, 256, smem, s>>>(pl.kp, buf, W, best, table_smem);
+    kern<<<grid, 256, smem, s>>>(pl.kp, buf, W, best, table_smem, gate);
     g_launches++;
     return cuda_status(cudaGetLastError());
 }
 
-template <int KIND, int NR, bool HIGH>
+template <int KIND, int NR, bool HIGH, bool PREFIX>
 int launch_scan_sparse_t(fx_pattern* p, const Plan& pl, const SparseParams& sp, const uint8_t* buf, const ScanWindow& W,
-                         unsigned long long* best, cudaStream_t s) {
-    auto kern = k_buffer_scan_sparse<KIND, NR, HIGH>;
+                         unsigned long long* best, cudaStream_t s, const unsigned long long* gate) {
+    auto kern = k_buffer_scan_sparse<KIND, NR, HIGH, PREFIX>;
     int table_smem = (int)staged_bytes(pl);
     size_t smem = (size_t)scan_sparse_smem_bytes(table_smem);
     int bps = 0;
@@ -688,49 +689,70 @@ int launch_scan_sparse_t(fx_pattern* p, const Plan& pl, const SparseParams& sp, 
     long long cap = (long long)p->dev.sm_count * bps;
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    kern<<<grid, 256, smem, s>>>(pl.kp, sp, buf, W, best, table_smem);
+    kern<<<grid, 256, smem, s>>>(pl.kp, sp, buf, W, best, table_smem, gate);
     g_launches++;
     return cuda_status(cudaGetLastError());
 }
 
 template <int KIND>
 int launch_scan_sparse(fx_pattern* p, const Plan& pl, const uint8_t* buf, const ScanWindow& W, unsigned long long* best,
-                       cudaStream_t s) {
+                       cudaStream_t s, const unsigned long long* gate) {
     SparseParams sp;
     memset(&sp, 0, sizeof(sp));
     fill_sweep(p->first, sp);
     const FirstSet& f = p->first;
     const bool one = f.sweep_nr == 1 && f.sweep_lo[0] == f.sweep_hi[0];
-    if (f.sweep_nr == 0) return launch_scan_sparse_t<KIND, 0, true>(p, pl, sp, buf, W, best, s);
-    if (one) return f.high ? launch_scan_sparse_t<KIND, -1, true>(p, pl, sp, buf, W, best, s)
-                           : launch_scan_sparse_t<KIND, -1, false>(p, pl, sp, buf, W, best, s);
-    if (f.sweep_nr == 1) return f.high ? launch_scan_sparse_t<KIND, 1, true>(p, pl, sp, buf, W, best, s)
-                                       : launch_scan_sparse_t<KIND, 1, false>(p, pl, sp, buf, W, best, s);
-    return f.high ? launch_scan_sparse_t<KIND, 2, true>(p, pl, sp, buf, W, best, s)
-                  : launch_scan_sparse_t<KIND, 2, false>(p, pl, sp, buf, W, best, s);
+    if (f.sweep_nr == 0) return launch_scan_sparse_t<KIND, 0, true, false>(p, pl, sp, buf, W, best, s, gate);
+    if (one) return f.high ? launch_scan_sparse_t<KIND, -1, true, false>(p, pl, sp, buf, W, best, s, gate)
+                           : launch_scan_sparse_t<KIND, -1, false, false>(p, pl, sp, buf, W, best, s, gate);
+    if (f.sweep_nr == 1) return f.high ? launch_scan_sparse_t<KIND, 1, true, false>(p, pl, sp, buf, W, best, s, gate)
+                                       : launch_scan_sparse_t<KIND, 1, false, false>(p, pl, sp, buf, W, best, s, gate);
+    return f.high ? launch_scan_sparse_t<KIND, 2, true, false>(p, pl, sp, buf, W, best, s, gate)
+                  : launch_scan_sparse_t<KIND, 2, false, false>(p, pl, sp, buf, W, best, s, gate);
 }
 
-// scan starts [start_lo, start_hi) of a window; d_best[0] (min key) and d_best[1] (undecided attempts) must have been
-// initialised by the caller
-int launch_scan(fx_pattern* p, const uint8_t* buf, const ScanWindow& W, unsigned long long* best, cudaStream_t s) {
+// candidates = the occurrences of the prefix literal: sweep for its first byte
+template <int KIND>
+int launch_scan_prefix(fx_pattern* p, const Plan& pl, const uint8_t* buf, const ScanWindow& W, unsigned long long* best,
+                       cudaStream_t s) {
+    SparseParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.add_lo[0] = (unsigned char)p->prog.lit.prefix[0] * 0x01010101u;      // NR = -1 form
+    return launch_scan_sparse_t<KIND, -1, false, true>(p, pl, sp, buf, W, best, s, nullptr);
+}
+
+// scan starts [start_lo, start_hi) of a window; d_best[0] (min key), d_best[1] (undecided attempts) and d_best[2]
+// (prefix occurrences seen) must have been initialised by the caller.
+//   mode SCAN_AUTO   the pattern's own candidates: the occurrences of its prefix literal if it has one, else every
+//                    character boundary
+//   mode SCAN_ALL    every character boundary, whatever the pattern (what the reference does when the prefix occurs
+//                    nowhere in the text); `gate`, if given, cancels the launch when *gate != 0
+enum { SCAN_AUTO = 0, SCAN_ALL = 1 };
+int launch_scan(fx_pattern* p, const uint8_t* buf, const ScanWindow& W, unsigned long long* best, cudaStream_t s,
+                int mode = SCAN_AUTO, const unsigned long long* gate = nullptr) {
     if (W.len < 0 || W.start_lo < 0 || W.start_hi > W.len || W.start_lo > W.start_hi) return FX_ERR_BAD_ARGUMENT;
-    // the parallel start sweep tries every character boundary; a pattern whose extracted prefix restricts
-    // the candidate starts (api_internal_m.F90:76-104) is not handled on this path yet
-    if (p->prog.prefix_active && !p->prog.literal_only) return FX_ERR_PREFILTER_UNSUPPORTED;
+    const bool prefixed = p->prog.prefix_active && !p->prog.literal_only;
+    // a prefix whose occurrences can overlap, or a non-empty suffix, make the candidate list sequential: not handled
+    if (prefixed && !p->prefix_scan) return FX_ERR_PREFILTER_UNSUPPORTED;
     Plan pl;
     int rc = make_plan(p, pl);
     if (rc) return rc;
     if (pl.kp.all_active || W.start_lo == W.start_hi) return FX_OK;
     p->last_sparse = 0;
+    if (prefixed && mode == SCAN_AUTO) {
+        if (pl.kind == 1) return launch_scan_prefix<1>(p, pl, buf, W, best, s);
+        if (pl.kind == 2) return launch_scan_prefix<2>(p, pl, buf, W, best, s);
+        return launch_scan_prefix<3>(p, pl, buf, W, best, s);
+    }
     if (p->sparse && p->first.sweep_nr <= 2 && env_int("FX_SPARSE", 1)) {     // SWAR first-byte filter
         p->last_sparse = 1;
-        if (pl.kind == 1) return launch_scan_sparse<1>(p, pl, buf, W, best, s);
-        if (pl.kind == 2) return launch_scan_sparse<2>(p, pl, buf, W, best, s);
-        return launch_scan_sparse<3>(p, pl, buf, W, best, s);
+        if (pl.kind == 1) return launch_scan_sparse<1>(p, pl, buf, W, best, s, gate);
+        if (pl.kind == 2) return launch_scan_sparse<2>(p, pl, buf, W, best, s, gate);
+        return launch_scan_sparse<3>(p, pl, buf, W, best, s, gate);
     }
-    if (pl.kind == 1) return launch_scan_t<1>(p, pl, buf, W, best, s);
-    if (pl.kind == 2) return launch_scan_t<2>(p, pl, buf, W, best, s);
-    return launch_scan_t<3>(p, pl, buf, W, best, s);
+    if (pl.kind == 1) return launch_scan_t<1>(p, pl, buf, W, best, s, gate);
+    if (pl.kind == 2) return launch_scan_t<2>(p, pl, buf, W, best, s, gate);
+    return launch_scan_t<3>(p, pl, buf, W, best, s, gate);
 }
 
 int launch_finish(fx_pattern* p, const uint8_t* buf, const ScanWindow& W, const unsigned long long* best,
@@ -747,13 +769,17 @@ int launch_buffer(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* from_
                   cudaStream_t s) {
     if (len < 0) return FX_ERR_BAD_ARGUMENT;
     CUDA_TRY(cudaMemsetAsync(best, 0xFF, 8, s));
-    CUDA_TRY(cudaMemsetAsync(best + 1, 0, 8, s));
+    CUDA_TRY(cudaMemsetAsync(best + 1, 0, 16, s));
     ScanWindow W{len, 0, len, 0, 1, 1};
-    if (len > 1) {
-        int rc = launch_scan(p, buf, W, best, s);
+    const bool prefixed = p->prog.prefix_active && !p->prog.literal_only;
+    if (prefixed && !p->prefix_scan) return FX_ERR_PREFILTER_UNSUPPORTED;
+    if (len >= 1) {
+        int rc = launch_scan(p, buf, W, best, s, SCAN_AUTO);
         if (rc) return rc;
-    } else if (p->prog.prefix_active && !p->prog.literal_only) {
-        return FX_ERR_PREFILTER_UNSUPPORTED;
+        if (prefixed) {          // no occurrence of the prefix anywhere: every boundary is a candidate (gated on best[2])
+            rc = launch_scan(p, buf, W, best, s, SCAN_ALL, best + 2);
+            if (rc) return rc;
+        }
     }
     return launch_finish(p, buf, W, best, from_to, 1, s);
 }
@@ -799,8 +825,19 @@ int fx_compile(const void* pattern, int64_t plen, int op, fx_pattern** out) {
             p->prog.status = p->anchored.status;
         }
     }
-    if (p->prog.status == fx::OK && op == FX_OP_REGEX && !p->prog.literal_only && !p->prog.prefix_active)
+    if (p->prog.status == fx::OK && op == FX_OP_REGEX && !p->prog.literal_only) {
         p->sparse = sparse_first_set(p->prog.bt, p->first, false);      // the long-buffer scan can use the SWAR filter
+        if (p->prog.prefix_active) {
+            // the long-buffer path takes the prefix literal's occurrences as candidates when "non-overlapping occurrences,
+            // left to right" (utility_m.f90:58-117) means "all occurrences" -- the literal has no border -- and no suffix
+            // literal cuts the list short; a NUL inside the literal would tangle with the frame
+            const std::string& pre = p->prog.lit.prefix;
+            bool ok = p->prog.lit.suffix.empty() && !pre.empty() && pre.find('\0') == std::string::npos;
+            for (size_t k = 1; k < pre.size() && ok; k++)
+                if (pre.compare(0, k, pre, pre.size() - k, k) == 0) ok = false;
+            p->prefix_scan = ok;
+        }
+    }
     *out = p;
     return p->prog.status;
 }
@@ -849,6 +886,7 @@ int fx_pattern_get_info(const fx_pattern* p, fx_pattern_info* info) {
         info->sparse_hi[r] = p->sparse && r < p->first.nr ? p->first.hi[r] : 0;
     }
     info->sparse_used = p->last_sparse;
+    info->prefix_scan = p->prefix_scan ? 1 : 0;
     return FX_OK;
 }
 
@@ -951,7 +989,15 @@ int fx_buffer_scan_dev(fx_pattern* p, const uint8_t* d_window, int64_t window_le
     if (rc) return rc;
     if (!d_best) return FX_ERR_BAD_ARGUMENT;
     ScanWindow W{window_len, start_lo, start_hi, origin, is_first ? 1 : 0, is_last ? 1 : 0};
-    return launch_scan(p, d_window, W, reinterpret_cast<unsigned long long*>(d_best), (cudaStream_t)stream);
+    return launch_scan(p, d_window, W, reinterpret_cast<unsigned long long*>(d_best), (cudaStream_t)stream, SCAN_AUTO);
+}
+int fx_buffer_scan_all_dev(fx_pattern* p, const uint8_t* d_window, int64_t window_len, int64_t start_lo, int64_t start_hi,
+                           int64_t origin, int is_first, int is_last, uint64_t* d_best, void* stream) {
+    int rc = check_ready(p, FX_OP_REGEX);
+    if (rc) return rc;
+    if (!d_best) return FX_ERR_BAD_ARGUMENT;
+    ScanWindow W{window_len, start_lo, start_hi, origin, is_first ? 1 : 0, is_last ? 1 : 0};
+    return launch_scan(p, d_window, W, reinterpret_cast<unsigned long long*>(d_best), (cudaStream_t)stream, SCAN_ALL);
 }
 int fx_buffer_finish_dev(fx_pattern* p, const uint8_t* d_window, int64_t window_len, int64_t origin, int is_last,
                          const uint64_t* d_key, int64_t* d_from_to, void* stream) {

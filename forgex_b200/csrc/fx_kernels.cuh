@@ -1618,7 +1618,9 @@ __host__ __device__ __forceinline__ int scan_smem_bytes(int table_smem_bytes) {
 // through L1/L2), so the rare long attempts never leave 31 lanes idle.
 template <int KIND>
 __global__ void __launch_bounds__(256) k_buffer_scan(KParams p, const uint8_t* __restrict__ buf, ScanWindow W,
-                                                     unsigned long long* __restrict__ best, int table_smem_bytes) {
+                                                     unsigned long long* __restrict__ best, int table_smem_bytes,
+                                                     const unsigned long long* __restrict__ gate) {
+    if (gate != nullptr && *gate != 0) return;      // the prefix occurs in the text: its occurrences were the candidates
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_cmap = smem;
     uint8_t* s_table = smem + 256;
@@ -1753,10 +1755,19 @@ __host__ __device__ __forceinline__ int scan_sparse_smem_bytes(int table_smem_by
     return ((256 + table_smem_bytes + 15) & ~15) + 8 * 2 * 64 * 8;
 }
 
-template <int KIND, int NR, bool HIGH>
+//
+// PREFIX: the pattern has an extracted prefix literal and the reference takes its candidate starts from the
+// occurrences of that literal in the text (api_internal_m.F90:76-104, utility_m.f90:58-117) instead of from every
+// character boundary.  The host takes this form only for a prefix without border (its occurrences cannot overlap, so
+// "non-overlapping occurrences, left to right" is simply "all occurrences") and an empty suffix.  The sweep looks for
+// the literal's first byte, the unit phase compares the whole literal, and best[2] counts the occurrences seen: when
+// the literal occurs nowhere the reference falls back to all boundaries -- the caller then runs the plain scan, which
+// is gated on best[2] == 0.  The start on the leading NUL is tried iff the literal sits at the very front of the text.
+template <int KIND, int NR, bool HIGH, bool PREFIX>
 __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparseParams sp, const uint8_t* __restrict__ buf,
                                                             ScanWindow W, unsigned long long* __restrict__ best,
-                                                            int table_smem_bytes) {
+                                                            int table_smem_bytes, const unsigned long long* __restrict__ gate) {
+    if (gate != nullptr && *gate != 0) return;      // (plain scan of a prefix pattern) the prefix occurs in the text
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_cmap = smem;
     uint8_t* s_table = smem + 256;
@@ -1770,9 +1781,18 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
     const bool open_end = !W.last;
     unsigned long long* overflow = best + 1;
     const uint32_t FULL = 0xffffffffu;
+    const uint8_t* pre = p.lits + p.all_len;                // PREFIX: the literal
+    const int plen = p.pre_len;
+    auto prefix_at = [&](int64_t pos) -> int {              // 1: the literal is at pos; 0: it is not; -1: the window ends first
+        if (pos + plen > len) return open_end ? -1 : 0;
+        for (int k = 0; k < plen; k++)
+            if (__ldg(buf + pos + k) != __ldg(pre + k)) return 0;
+        return 1;
+    };
     if (blockIdx.x == 0 && threadIdx.x == 0 && W.first) {   // start 1 = the leading NUL sentinel
         const Anchored A{p.flags, p.start_nul, p.q0};
-        if (attempt_at(A, T, FetchGlobal{buf}, len, 1) >= 0) atomicMin(best, 1ull);
+        if (!PREFIX || (W.start_lo == 0 && prefix_at(0) == 1))
+            if (attempt_at(A, T, FetchGlobal{buf}, len, 1) >= 0) atomicMin(best, 1ull);
     }
     const uintptr_t gbuf = reinterpret_cast<uintptr_t>(buf);
     const uintptr_t ubase = (gbuf + (uintptr_t)W.start_lo) & ~(uintptr_t)31;      // 32-byte units aligned to the buffer ADDRESS
@@ -1808,7 +1828,13 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
         while (__any_sync(FULL, cand != 0)) {
             bool sv = false;
             int64_t pos = 0;
-            if (cand) {
+            if (cand && PREFIX) {
+                pos = P + __ffs(cand) - 1;
+                cand &= cand - 1;
+                const int occ = prefix_at(pos);
+                if (occ < 0) atomicAdd(overflow, 1ull);              // cannot be decided in this window
+                if (occ > 0) { best[2] = 1; sv = true; }
+            } else if (cand) {
                 pos = P + __ffs(cand) - 1;
                 cand &= cand - 1;
                 // up to four plain steps: a start survives unless they prove it dead (undecided -- an accept, a multi-byte

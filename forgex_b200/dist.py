@@ -64,11 +64,16 @@ def count_matches(local_count, group=None, device=None):
     return all_reduce_int(int(local_count), dist.ReduceOp.SUM, group, device)
 
 
-def buffer_search(scan, finish, length, rank, world, slab, window, group=None, device=None):
+def buffer_search(scan, finish, length, rank, world, slab, window, group=None, device=None, scan_all=None):
     """Leftmost-longest search of one pattern in one buffer that is split across ranks.
 
-    scan(start_lo, start_hi) -> (key, undecided): smallest winning start of this rank's slab as a 1-based position
-        in NUL||text||NUL of the whole text (NO_START if none) and the number of attempts that ran off the window.
+    scan(start_lo, start_hi) -> (key, undecided[, occurrences]): smallest winning start of this rank's slab as a
+        1-based position in NUL||text||NUL of the whole text (NO_START if none), the number of attempts that ran off
+        the window and -- for a pattern with a prefix literal -- how many occurrences of the literal the slab holds.
+    scan_all(start_lo, start_hi) -> (key, undecided): the same over EVERY character boundary.  Given for a pattern
+        with a prefix literal: Forgex takes its candidate starts from the literal's occurrences, and from every
+        boundary when the literal occurs nowhere in the text (api_internal_m.F90:76-104) -- "nowhere" is a property
+        of the whole text, hence one more 8-byte all-reduce.
     finish(key) -> (from, to) computed by the rank whose window holds the winner (or (-1, -1) if its window is
         too short).
     Returns (from, to, undecided_total); every rank gets the same answer.
@@ -76,7 +81,13 @@ def buffer_search(scan, finish, length, rank, world, slab, window, group=None, d
     import torch
     import torch.distributed as dist
     lo, hi = slab
-    key, undecided = scan(lo, hi) if hi > lo or (rank == 0 and length == 0) else (NO_START, 0)
+    active = hi > lo or (rank == 0 and length == 0)
+    res = scan(lo, hi) if active else (NO_START, 0, 0)
+    key, undecided = res[0], res[1]
+    if scan_all is not None:
+        occurrences = all_reduce_int(res[2] if len(res) > 2 else 0, dist.ReduceOp.SUM, group, device)
+        if occurrences == 0:
+            key, undecided = scan_all(lo, hi) if active else (NO_START, 0)
     # uint64 MIN through int64: keys are < 2**63 except NO_START, which maps to the largest int64
     k64 = key if key != NO_START else (1 << 63) - 1
     best = all_reduce_int(k64, dist.ReduceOp.MIN, group, device)
@@ -103,16 +114,24 @@ def gpu_buffer_search(pattern_obj, d_window, window_origin, length, rank, world,
     wlen = d_window.numel()
     is_first = window_origin == 0
     is_last = window_origin + wlen == length
-    best = torch.empty(2, dtype=torch.int64, device=dev)
+    best = torch.empty(3, dtype=torch.int64, device=dev)
     ft = torch.zeros(2, dtype=torch.int64, device=dev)
+    prefixed = bool(pattern_obj.info()["prefix_scan"])
 
-    def scan(lo, hi):
+    def run(lo, hi, every_boundary):
         best[0] = -1          # all ones
         best[1] = 0
-        pattern_obj.buffer_scan_dev(d_window, wlen, lo - window_origin, hi - window_origin, window_origin,
-                                    is_first, is_last, best)
+        best[2] = 0
+        call = pattern_obj.buffer_scan_all_dev if every_boundary else pattern_obj.buffer_scan_dev
+        call(d_window, wlen, lo - window_origin, hi - window_origin, window_origin, is_first, is_last, best)
         b = best.cpu().numpy().view(np.uint64)
-        return int(b[0]), int(b[1])
+        return int(b[0]), int(b[1]), int(b[2])
+
+    def scan(lo, hi):
+        return run(lo, hi, False)
+
+    def scan_all(lo, hi):
+        return run(lo, hi, True)[:2]
 
     def finish(key):
         k = torch.tensor([key], dtype=torch.int64, device=dev)
@@ -120,4 +139,4 @@ def gpu_buffer_search(pattern_obj, d_window, window_origin, length, rank, world,
         r = ft.cpu().numpy()
         return int(r[0]), int(r[1])
 
-    return buffer_search(scan, finish, length, rank, world, slab, None, group, dev)
+    return buffer_search(scan, finish, length, rank, world, slab, None, group, dev, scan_all if prefixed else None)

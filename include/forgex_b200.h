@@ -92,7 +92,9 @@ typedef struct fx_pattern_info {
     int32_t sparse_high;      /* 1: F also holds bytes >= 0xC0 (lead bytes; every such byte is tried as a start) */
     int32_t sparse_second;    /* >= 0: F is one byte and only this ASCII byte (or a lead byte) can follow it: the sweep
                                  tests for the byte pair; -1 otherwise */
-    int32_t sparse_used;      /* 1: the last ragged `.in.` launch used the sparse-start kernel */
+    int32_t sparse_used;      /* 1: the last ragged `.in.` launch / buffer scan used the SWAR first-byte sweep */
+    int32_t prefix_scan;      /* FX_OP_REGEX with an extracted prefix literal: 1 when the long-buffer path handles it (the
+                                 literal has no border and there is no suffix literal); 0: FX_ERR_PREFILTER_UNSUPPORTED */
 } fx_pattern_info;
 
 /* ---- host-only ------------------------------------------------------------------------- */
@@ -139,12 +141,18 @@ int fx_regex_buffer_dev(fx_pattern* p, const uint8_t* d_buf, int64_t len, int64_
  * [start_lo, start_hi) of the window (attempts may read on to the end of the window) and lowers d_best[0] to the
  * smallest winning start, expressed as a 1-based position in NUL||text||NUL of the WHOLE text (so results of several
  * GPUs combine with a plain MIN); d_best[1] counts attempts that were still alive at an open window end (they could
- * not be decided: widen the halo).  The caller initialises d_best[0] = ~0, d_best[1] = 0.  is_first / is_last say
+ * not be decided: widen the halo).  A pattern with an extracted prefix literal (fx_pattern_info.prefix_scan) takes its
+ * candidate starts from the literal's occurrences, as the reference does (src/api_internal_m.F90:76-104), and d_best[2]
+ * becomes non-zero when the scanned starts hold an occurrence; when the literal occurs NOWHERE in the whole text the
+ * reference tries every boundary instead: the caller then repeats the scan with fx_buffer_scan_all_dev.
+ * The caller initialises d_best[0] = ~0, d_best[1] = d_best[2] = 0 (3 words).  is_first / is_last say
  * whether the window begins / ends where the text does.  Windows that do not begin the text need >= 3 bytes in
  * front of start_lo (character-boundary look-back).  fx_buffer_finish_dev turns a winning start (*d_key) into the
  * (from, to) span; it needs a window that holds the whole match, and answers (-1, -1) if the window ends first. */
 int fx_buffer_scan_dev(fx_pattern* p, const uint8_t* d_window, int64_t window_len, int64_t start_lo, int64_t start_hi,
                        int64_t origin, int is_first, int is_last, uint64_t* d_best, void* stream);
+int fx_buffer_scan_all_dev(fx_pattern* p, const uint8_t* d_window, int64_t window_len, int64_t start_lo, int64_t start_hi,
+                           int64_t origin, int is_first, int is_last, uint64_t* d_best, void* stream);
 int fx_buffer_finish_dev(fx_pattern* p, const uint8_t* d_window, int64_t window_len, int64_t origin, int is_last,
                          const uint64_t* d_key, int64_t* d_from_to, void* stream);
 

@@ -278,6 +278,43 @@ class SparseIn:
         return r
 
 
+class BufferPrefix:
+    """the long-buffer path for a pattern with a prefix literal (k_buffer_scan_sparse<..., PREFIX> + gated plain scan
+    + k_buffer_finish): winner = the smallest candidate start whose attempt wins, candidates = the literal's
+    occurrences (plus the leading NUL if the literal sits at the front), or every boundary if it occurs nowhere"""
+
+    def __init__(self, pattern_obj):
+        assert pattern_obj.info()["prefix_scan"]
+        self.anch = Anchored(pattern_obj, False)
+        self.pre = pattern_obj.literals()[1]
+
+    def regex(self, s: bytes):
+        a = self.anch
+        if len(s) == 0 or s == b" ":
+            return (0, 0)
+        pre, n = self.pre, len(s)
+        occ = [i for i in range(0, n - len(pre) + 1) if s[i:i + len(pre)] == pre]
+        key = None
+        if occ:
+            starts = ([1] if occ[0] == 0 else []) + [i + 2 for i in occ]
+        else:
+            starts = [1]
+            pos = 0
+            while pos < n:
+                starts.append(pos + 2)
+                pos += a.char_len(s, pos)
+        for st in starts:                     # ascending, so the first winner is the minimum
+            if a.attempt_at(s, st) >= 0:
+                key = st
+                break
+        if key is None:
+            return (0, 0)
+        last = a.attempt_at(s, key)
+        f = max(key - 1, 1)
+        t = min(last, n)
+        return (f, t) if f > 0 and t > 0 else (0, 0)
+
+
 class SpanLinear:
     """span_linear_smem (K3f): forward ordered-groups automaton, then the reverse automaton"""
 

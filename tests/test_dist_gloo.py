@@ -72,6 +72,32 @@ def model_scan(anch, text, window_lo, window_hi, lo, hi, length):
     return best, undecided
 
 
+def model_scan_prefix(anch, pre, text, window_lo, window_hi, lo, hi, length):
+    """fx_buffer_scan_dev for a pattern with a prefix literal: candidates = the literal's occurrences that start in
+    [lo, hi); returns (key, undecided, occurrences)"""
+    wtext = text[window_lo:window_hi]
+    is_last = window_hi == length
+    best, undecided, occ = fxd.NO_START, 0, 0
+    t = anch.t
+    for pos in range(lo, hi):
+        rel = pos - window_lo
+        if rel + len(pre) > len(wtext):
+            if not is_last and wtext[rel:] == pre[:len(wtext) - rel]:
+                undecided += 1
+            continue
+        if wtext[rel:rel + len(pre)] != pre:
+            continue
+        occ += 1
+        if pos == 0 and t["start_nul"] != 0 and is_last and anch.attempt_at(wtext, 1) >= 0:
+            best = min(best, 1)
+        if best != fxd.NO_START:
+            continue
+        assert is_last or rel + 64 < len(wtext)          # (test texts keep matches short: no open-end bookkeeping here)
+        if anch.attempt(wtext, t["q0"], rel, -1) >= 0:
+            best = pos + 2
+    return best, undecided, occ
+
+
 def worker(rank, world, port, cfg, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -101,7 +127,15 @@ def worker(rank, world, port, cfg, ret):
             def finish(key):
                 f, t = anch.regex(text)   # the owner holds the match in its window; same attempt, whole-text coordinates
                 return f, t
-            ret[rank] = fxd.buffer_search(scan, finish, length, rank, world, (lo, hi), (w_lo, w_hi))
+            if cfg.get("prefixed"):
+                assert p.info()["prefix_scan"] == 1
+                pre = p.literals()[1]
+
+                def scan_pre(a, b):
+                    return model_scan_prefix(anch, pre, text, w_lo, w_hi, a, b, length)
+                ret[rank] = fxd.buffer_search(scan_pre, finish, length, rank, world, (lo, hi), (w_lo, w_hi), scan_all=scan)
+            else:
+                ret[rank] = fxd.buffer_search(scan, finish, length, rank, world, (lo, hi), (w_lo, w_hi))
     finally:
         dist.destroy_process_group()
 
@@ -159,3 +193,23 @@ def test_short_halo_is_reported():
     text = b"INFO x\n" * 30 + line + b"\n" + b"INFO y\n" * 30
     res = run(2, {"kind": "buffer", "text": text, "pattern": synth.PATTERNS["c4"], "halo": 8, "align": 1})
     assert res[0][2] >= 1   # an attempt ran off rank 0's window: the caller must widen the halo
+
+
+@pytest.mark.parametrize("world,case", [(2, 0), (2, 1), (3, 2), (2, 3), (2, 4)])
+def test_sharded_buffer_search_with_prefix_literal(world, case):
+    """candidates are the prefix literal's occurrences; "occurs nowhere" is decided over ALL ranks (one more 8-byte
+    all-reduce) before the search falls back to every boundary"""
+    import random
+    rng = random.Random(5)
+    filler = bytes(rng.choice(b"abcdeghijklmnpqrstuvwxyz .,;:-_0123456789") for _ in range(3000))
+    text = [filler + b"foobaz" + filler,                           # one occurrence, in the middle
+            filler + filler + b"foobar",                            # only the last rank sees the literal
+            filler + b"\xc1\xa6oobar" + filler,                     # literal nowhere: the overlong start wins by brute force
+            b"\xc1\xa6oobar" + filler + b"fooba " + filler,         # literal somewhere: the overlong start is never tried
+            filler + filler][case]
+    res = run(world, {"kind": "buffer", "text": text, "pattern": b"foo(bar|baz)", "halo": 512, "prefixed": True})
+    exp = O.Compiled(b"foo(bar|baz)", 0).regex_buffer(np.frombuffer(text, dtype=np.uint8))
+    assert (exp[0] > 0) == (case in (0, 1, 2))
+    for r in res:
+        assert (r[0], r[1]) == exp
+        assert r[2] == 0

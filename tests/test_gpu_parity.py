@@ -163,6 +163,43 @@ def test_c4_unaligned_and_tiny_buffers():
             assert p.regex_buffer(arr) == c.regex_buffer(np.ascontiguousarray(arr)), (text, shift)
 
 
+def test_buffer_one_byte_texts():
+    for pat in [b"[a-z]+", b"a", b"ab*", b".", b"^", b"x|y"]:
+        p = fx.Pattern(pat, "regex")
+        c = O.Compiled(pat, 0)
+        for text in [b"a", b"x", b" ", b"\n", b"\xff", b"b"]:
+            arr = np.frombuffer(text, dtype=np.uint8)
+            assert p.regex_buffer(arr) == c.regex_buffer(arr), (pat, text)
+
+
+def test_buffer_patterns_with_a_prefix_literal():
+    """candidates = the occurrences of the extracted prefix (api_internal_m.F90:76-104); every boundary when the
+    literal occurs nowhere; FX_ERR_PREFILTER_UNSUPPORTED for a bordered prefix or a suffix literal"""
+    rng = np.random.default_rng(23)
+    filler = bytes(rng.integers(0x20, 0x7F, size=200000, dtype=np.uint8)).replace(b"foo", b"f0o").replace(b"ERR", b"E_R")
+    texts = [b"xx foobar foobaz", b"fooba foobar", b"foobar", b"\xc1\xa6oobar", b"x\xc1\xa6oobar foobaz", b"zzz", b"", b" ", b"f",
+             b"fooba", b"foobafoobar", filler + b"foobaz" + filler, filler + b"\xc1\xa6oobar" + filler, filler,
+             filler[:70001] + b"fooba" + filler[:33] + b"foobar", b"foobar" + filler,
+             b"ERROR x timeout=12 ERROR timeout=5", filler + b"ERROR a timeout=777\n" + filler, b"ERROR timeout=", b"ERROR"]
+    used = 0
+    for pat in [b"foo(bar|baz)", rb"ERROR.*timeout=\d+", b"ab+", b"hello (world|there)", "\u3042\u3044+".encode(), b"key=[0-9]*"]:
+        p = fx.Pattern(pat, "regex")
+        assert p.info()["prefix_scan"] == 1, pat
+        c = O.Compiled(pat, 0)
+        for text in texts + [b"hello there hello world", b"xabbb ab", "\u3042\u3044\u3044 \u3042".encode(), b"fooobar", b"key", b"a key=12 key="]:
+            for shift in (0, 3):
+                arr = np.frombuffer(b"#" * shift + text, dtype=np.uint8)[shift:]
+                assert p.regex_buffer(arr) == c.regex_buffer(np.ascontiguousarray(arr)), (pat, text[:60], len(text), shift)
+        used += 1
+    assert used == 6
+    for pat in [b"ab+c", b"aab*", b"abab+", b"fo+bar"]:          # suffix literal / bordered prefix
+        p = fx.Pattern(pat, "regex")
+        assert p.info()["prefix_scan"] == 0
+        with pytest.raises(fx.ForgexError) as e:
+            p.regex_buffer(np.frombuffer(b"xx aabab abc", dtype=np.uint8))
+        assert e.value.status == _lib.FX_ERR_PREFILTER_UNSUPPORTED
+
+
 @pytest.mark.parametrize("residency", ["auto", "global"])
 def test_c5_in_fixed_big_table(residency):
     buf, n, stride = synth.gen_c5(3000)
@@ -328,7 +365,7 @@ def test_buffer_windows_like_two_gpus():
             lo, hi = fxd.slab_bounds(nbytes, world, rank)
             w_lo, w_hi = fxd.window_for_slab(nbytes, lo, hi, 1024)
             win = d_text[w_lo:w_hi].clone()
-            best = torch.tensor([-1, 0], dtype=torch.int64, device="cuda")
+            best = torch.tensor([-1, 0, 0], dtype=torch.int64, device="cuda")
             p.buffer_scan_dev(win, w_hi - w_lo, lo - w_lo, hi - w_lo, w_lo, w_lo == 0, w_hi == nbytes, best)
             b = best.cpu().numpy().view(np.uint64)
             keys.append(int(b[0]))
@@ -345,3 +382,53 @@ def test_buffer_windows_like_two_gpus():
         ft = torch.zeros(2, dtype=torch.int64, device="cuda")
         p.buffer_finish_dev(win, w_hi - w_lo, w_lo, w_hi == nbytes, torch.tensor([key], dtype=torch.int64, device="cuda"), ft)
         assert tuple(ft.cpu().tolist()) == exp, (nbytes, match_at, world)
+
+
+def test_prefix_literal_windows_like_two_gpus():
+    """a pattern with a prefix literal over slabs: occurrences are counted per slab (d_best[2]); only when NO slab holds
+    one does the search fall back to every boundary (fx_buffer_scan_all_dev) -- forgex_b200.dist.buffer_search's protocol"""
+    import torch
+    from forgex_b200 import dist as fxd
+    pat = b"foo(bar|baz)"
+    p = fx.Pattern(pat, "regex")
+    c = O.Compiled(pat, 0)
+    rng = np.random.default_rng(29)
+    filler = bytes(rng.integers(0x20, 0x7F, size=90000, dtype=np.uint8)).replace(b"foo", b"f0o")
+    cases = [filler + b"foobaz" + filler, filler + filler[:5000] + b"fooba!" + filler + b"foobar",
+             filler + b"\xc1\xa6oobar" + filler,                      # the literal occurs nowhere: overlong start wins by brute force
+             filler + b"\xc1\xa6oobar" + filler + b"fooba",           # ... but here it does occur, so the overlong start is never tried
+             filler + filler, b"foobar" + filler]
+    for text in cases:
+        text = np.frombuffer(text, dtype=np.uint8)
+        nbytes = len(text)
+        exp = c.regex_buffer(text)
+        d_text = torch.from_numpy(text.copy()).cuda()
+        for world in (2, 3):
+            def scan_all_ranks(every):
+                keys, und, occ = [], 0, 0
+                for rank in range(world):
+                    lo, hi = fxd.slab_bounds(nbytes, world, rank)
+                    w_lo, w_hi = fxd.window_for_slab(nbytes, lo, hi, 1024)
+                    win = d_text[w_lo:w_hi].clone()
+                    best = torch.tensor([-1, 0, 0], dtype=torch.int64, device="cuda")
+                    call = p.buffer_scan_all_dev if every else p.buffer_scan_dev
+                    call(win, w_hi - w_lo, lo - w_lo, hi - w_lo, w_lo, w_lo == 0, w_hi == nbytes, best)
+                    b = best.cpu().numpy().view(np.uint64)
+                    keys.append(int(b[0])); und += int(b[1]); occ += int(b[2])
+                return keys, und, occ
+            keys, und, occ = scan_all_ranks(False)
+            assert occ == (0 if bytes(text).find(b"fooba") < 0 else occ) and (occ > 0) == (bytes(text).find(b"fooba") >= 0)
+            if occ == 0:
+                keys, und, _ = scan_all_ranks(True)
+            assert und == 0
+            key = min(keys)
+            if key == fxd.NO_START:
+                assert exp == (0, 0), (len(text), world)
+                continue
+            owner = keys.index(key)
+            lo, hi = fxd.slab_bounds(nbytes, world, owner)
+            w_lo, w_hi = fxd.window_for_slab(nbytes, lo, hi, 1024)
+            win = d_text[w_lo:w_hi].clone()
+            ft = torch.zeros(2, dtype=torch.int64, device="cuda")
+            p.buffer_finish_dev(win, w_hi - w_lo, w_lo, w_hi == nbytes, torch.tensor([key], dtype=torch.int64, device="cuda"), ft)
+            assert tuple(ft.cpu().tolist()) == exp, (len(text), world)

@@ -13,7 +13,7 @@ import pytest
 import forgex_b200 as fx
 from forgex_b200 import _lib
 from tests import oracle_lib as O
-from tests.table_model import Model, SpanLinear, SparseIn
+from tests.table_model import BufferPrefix, Model, SpanLinear, SparseIn
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 OPS = {"match": "match", "in": "in", "regex": "regex"}
@@ -190,6 +190,7 @@ def test_generated_patterns_match_oracle(seed, monkeypatch):
     bad = []
     checked = 0
     nsparse = 0
+    nbufpre = 0
     for _ in range(120):
         pat = gen_pattern(rng).encode()
         texts = [gen_text(rng) for _ in range(12)] + [b"", b" "]
@@ -210,6 +211,8 @@ def test_generated_patterns_match_oracle(seed, monkeypatch):
                 continue  # cap
             m = Model(p, use_direct=rng.random() < 0.5)
             span = SpanLinear(p) if kind == "regex" and p.span_tables() is not None else None
+            bufpre = BufferPrefix(p) if kind == "regex" and p.info()["prefix_scan"] else None
+            nbufpre += bufpre is not None
             sparse = SparseIn(p) if kind == "in" and p.info()["sparse"] else None
             nsparse += sparse is not None
             for t in texts:
@@ -223,6 +226,10 @@ def test_generated_patterns_match_oracle(seed, monkeypatch):
                         got2 = span.regex(t)
                         if got2 != (f, to):
                             bad.append("regex(linear) %r on %r: product %r oracle %r" % (pat, t, got2, (f, to)))
+                    if bufpre is not None:
+                        got3 = bufpre.regex(t)
+                        if got3 != (f, to):
+                            bad.append("regex(buffer, prefix) %r on %r: product %r oracle %r" % (pat, t, got3, (f, to)))
                 else:
                     o = O.op_match(pat, t) if kind == "match" else O.op_in(pat, t)
                     got = m.boolean(t)
@@ -233,3 +240,37 @@ def test_generated_patterns_match_oracle(seed, monkeypatch):
     assert not bad, "%d mismatches (of %d):\n%s" % (len(bad), checked, "\n".join(bad[:30]))
     assert checked > 1000
     assert nsparse > 5
+
+
+PREFIX_HEADS = [b"foo", b"ab", b"ERROR", b"x-", b"key=", "\u3042\u3044".encode(), b"a\\.b", b"q", b"zz", b"abab"]
+PREFIX_TAILS = [b"(bar|baz)", b".*end", b"[0-9]+", b"b*", b"(x|y)?z", b"\\s\\w+", b"+", b"{2,3}c", b"(|^)k", b".", b"[^ ]*$"]
+PREFIX_PIECES = [b"foo", b"fo", b"foobar", b"foobaz", b"ab", b"abab", b"a", b"b", b"ERROR", b"ERR", b" end", b"end", b"x-", b"x",
+                 b"key=", b"key", b"7", b"42", b" ", b"\n", b"\r\n", b"z", b"zz", b"q", b"k", "\u3042\u3044".encode(), "\u3042".encode(),
+                 b"\xc1\xa6oo", b"\xc1\xa1b", b"\xe3\x81", b"\xff", b"a.b", b"a-b", b"c", b"y", b"_w"]
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_prefix_literal_patterns_on_the_buffer_path(seed):
+    """patterns that begin with a literal: the long-buffer formulation (prefix occurrences as candidates, every
+    boundary when the literal occurs nowhere) against the oracle"""
+    rng = random.Random(7000 + seed)
+    bad, eligible, rejected = [], 0, 0
+    for _ in range(60):
+        pat = rng.choice(PREFIX_HEADS) + rng.choice(PREFIX_TAILS)
+        p = fx.Pattern(pat, "regex")
+        if p.status != 0:
+            continue
+        inf = p.info()
+        if not inf["prefix_scan"]:
+            rejected += 1
+            continue
+        eligible += 1
+        m = BufferPrefix(p)
+        for _ in range(25):
+            text = b"".join(rng.choice(PREFIX_PIECES) for _ in range(rng.randint(0, 9)))
+            res, ln, f, to, st = O.regex(pat, text)
+            got = m.regex(text)
+            if st != 0 or got != (f, to):
+                bad.append("%r on %r: model %r oracle %r" % (pat, text, got, (f, to)))
+    assert not bad, "%d mismatches:\n%s" % (len(bad), "\n".join(bad[:30]))
+    assert eligible > 15 and rejected > 0
