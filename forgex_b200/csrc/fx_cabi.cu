@@ -607,16 +607,33 @@ template <int KIND>
 int launch_span_t(fx_pattern* p, const Plan& pl, const SpanParams& sp, int table_bytes, const uint8_t* buf,
                   const int64_t* off, int64_t n, int64_t total, int64_t* from, int64_t* to, cudaStream_t s) {
     auto kern = k_span_ragged<KIND>;
-    Plan tp = pl;
-    tp.table_bytes = KIND == 3 ? 0 : table_bytes;
-    Tiling t = make_tiling(tp, n, total);
+    // every warp stages its own tile; SPAN_WARPS warp regions + the table fill half an SM's shared memory (2 CTAs/SM)
+    int64_t avg = n > 0 ? (total + n - 1) / n : 1;
+    if (avg < 1) avg = 1;
+    const int table_smem = KIND == 3 ? 0 : (table_bytes + 15) & ~15;
+    const int head = span_shared_head(table_smem);
+    int per_warp = (((227 * 1024) / 2 - 1024 - head) / SPAN_WARPS) & ~127;
+    if (per_warp < 1024) per_warp = 1024;
+    int cap = per_warp, spt = 1;
+    for (;;) {
+        int64_t want = ((int64_t)cap * 4 / 5) / avg;       // expect the tile to fill ~80 % of the staged capacity
+        if (want >= 32) want = (want / 32) * 32;           // whole passes of 32 lanes
+        spt = (int)(want < 1 ? 1 : want > 256 ? 256 : want);
+        if (cap <= 512 || span_layout(spt, cap).warp_bytes <= per_warp) break;
+        cap -= 128;
+    }
+    spt = env_int("FX_TILE_STRINGS", spt);
+    if (spt > 256) spt = 256;
+    const int64_t ntiles = (n + spt - 1) / spt;
+    const size_t smem = (size_t)head + (size_t)SPAN_WARPS * (size_t)span_layout(spt, cap).warp_bytes;
     int bps = 0;
-    int rc = occupancy_grid(kern, 256, t.smem, p->dev.sm_count, bps);
+    int rc = occupancy_grid(kern, SPAN_WARPS * 32, smem, p->dev.sm_count, bps);
     if (rc) return rc;
-    long long cap = (long long)p->dev.sm_count * bps;
-    int grid = (int)(t.ntiles < cap ? t.ntiles : cap);
+    long long capg = (long long)p->dev.sm_count * bps;
+    long long want = (ntiles + SPAN_WARPS - 1) / SPAN_WARPS;
+    int grid = (int)(want < capg ? want : capg);
     if (grid < 1) grid = 1;
-    kern<<<grid, 256, t.smem, s>>>(pl.kp, sp, buf, off, n, total, from, to, t.spt, t.cap, t.ntiles, t.table_smem);
+    kern<<<grid, SPAN_WARPS * 32, smem, s>>>(pl.kp, sp, buf, off, n, total, from, to, spt, cap, ntiles, table_smem);
     g_launches++;
     return cuda_status(cudaGetLastError());
 }

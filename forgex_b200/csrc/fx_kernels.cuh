@@ -1406,39 +1406,10 @@ __device__ __forceinline__ int cp_class(const SpanParams& sp, uint32_t cp) {
     return lo;
 }
 
-template <class TBL>
-__device__ __forceinline__ void span_linear_smem(const SpanParams& sp, const TBL& T, uint32_t a, int len,
-                                                 int64_t& from, int64_t& to) {
+// backward half of the linear-time span search: the leftmost start of a match that ends at `last` (> 0)
+__device__ __forceinline__ void span_backward_smem(const SpanParams& sp, uint32_t a, int len, int last,
+                                                   int64_t& from, int64_t& to) {
     from = 0; to = 0;
-    // ---- forward: end of the leftmost-longest match ----
-    uint32_t w = (uint32_t)sp.start;
-    int last = (__ldg(sp.flags + sp.start) & SF_ACC) ? 0 : -1;
-    int seq = 0;
-    bool inter = false;
-    int j = 0;
-    for (; j < len; j++) {
-        const uint32_t b = lds_u8(a + j);
-        if (inter && (b & 0xC0) != 0x80) {                  // sequence broken: pending bytes replay as U+FFFF
-            const uint32_t f = __ldg(sp.flags + (w & W_STATE));
-            for (int k = 1; k <= j - seq; k++)
-                if (f & (SF_FAILACC1 << (k - 1))) last = seq + k;
-            inter = false;
-        }
-        const uint32_t nw = T.next(w & W_STATE, b);
-        if ((nw & W_INTER) && !inter) seq = j;
-        inter = (nw & W_INTER) != 0;
-        w = nw;
-        if (w & W_ACC) last = j + 1;
-        if ((w & W_STATE) == 0) break;
-    }
-    if (j >= len && (w & W_STATE) != 0) {                  // text exhausted: the trailing NUL follows (not a start)
-        const uint32_t f = __ldg(sp.flags + (w & W_STATE));
-        if (inter)
-            for (int k = 1; k <= len - seq; k++)
-                if (f & (SF_FAILACC1 << (k - 1))) last = seq + k;
-        if (f & SF_END) last = len + 1;
-    }
-    if (last <= 0) return;                                  // no match, or only the leading NUL matched (to = 0)
     // ---- backward: leftmost start of a match that ends at `last` ----
     uint32_t r = (uint32_t)sp.rstart;
     int pos = last;
@@ -1481,32 +1452,115 @@ __device__ __forceinline__ void span_linear_smem(const SpanParams& sp, const TBL
     to = last < len ? last : len;
 }
 
+template <class TBL>
+__device__ __forceinline__ void span_linear_smem(const SpanParams& sp, const TBL& T, uint32_t a, int len,
+                                                 int64_t& from, int64_t& to) {
+    from = 0; to = 0;
+    // ---- forward: end of the leftmost-longest match ----
+    uint32_t w = (uint32_t)sp.start;
+    int last = (__ldg(sp.flags + sp.start) & SF_ACC) ? 0 : -1;
+    int seq = 0;
+    bool inter = false;
+    int j = 0;
+    for (; j < len; j++) {
+        const uint32_t b = lds_u8(a + j);
+        if (inter && (b & 0xC0) != 0x80) {                  // sequence broken: pending bytes replay as U+FFFF
+            const uint32_t f = __ldg(sp.flags + (w & W_STATE));
+            for (int k = 1; k <= j - seq; k++)
+                if (f & (SF_FAILACC1 << (k - 1))) last = seq + k;
+            inter = false;
+        }
+        const uint32_t nw = T.next(w & W_STATE, b);
+        if ((nw & W_INTER) && !inter) seq = j;
+        inter = (nw & W_INTER) != 0;
+        w = nw;
+        if (w & W_ACC) last = j + 1;
+        if ((w & W_STATE) == 0) break;
+    }
+    if (j >= len && (w & W_STATE) != 0) {                  // text exhausted: the trailing NUL follows (not a start)
+        const uint32_t f = __ldg(sp.flags + (w & W_STATE));
+        if (inter)
+            for (int k = 1; k <= len - seq; k++)
+                if (f & (SF_FAILACC1 << (k - 1))) last = seq + k;
+        if (f & SF_END) last = len + 1;
+    }
+    if (last <= 0) return;                                  // no match, or only the leading NUL matched (to = 0)
+    span_backward_smem(sp, a, len, last, from, to);
+}
+
+// shared memory of K3f: classmap 256 | table | pad to 128 | SPAN_WARPS warp regions of `warp_bytes`:
+//   [0,16) mbarrier | offsets (spt+4) x int32 | pad to 128 | tile (cap + 64)
+// Every warp stages its own tiles (its own TMA bulk copy on its own mbarrier): no block-wide step after the table is
+// staged, so a warp never waits for the block's slowest string (measured on the block-tile version: 39 % of all warp
+// samples sat at the tile barrier).
+static constexpr int SPAN_WARPS = 16;
+struct SpanLayout { int off_tile, warp_bytes; };
+__host__ __device__ __forceinline__ SpanLayout span_layout(int spt, int cap) {
+    SpanLayout L;
+    L.off_tile = (16 + (spt + 4) * 4 + 127) & ~127;
+    L.warp_bytes = (L.off_tile + cap + 64 + 127) & ~127;
+    return L;
+}
+__host__ __device__ __forceinline__ int span_shared_head(int table_smem_bytes) { return (256 + table_smem_bytes + 127) & ~127; }
+
 template <int KIND>
-__global__ void __launch_bounds__(256) k_span_ragged(KParams p, SpanParams sp, const uint8_t* __restrict__ buf,
-                                                     const int64_t* __restrict__ offsets, int64_t n, int64_t total,
-                                                     int64_t* __restrict__ from, int64_t* __restrict__ to,
-                                                     int spt, int cap, int64_t ntiles, int table_smem_bytes) {
+__global__ void __launch_bounds__(SPAN_WARPS * 32, 2) k_span_ragged(KParams p, SpanParams sp, const uint8_t* __restrict__ buf,
+                                                                   const int64_t* __restrict__ offsets, int64_t n, int64_t total,
+                                                                   int64_t* __restrict__ from, int64_t* __restrict__ to,
+                                                                   int spt, int cap, int64_t ntiles, int table_smem_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* s_cmap = smem + 16;
-    uint8_t* s_table = smem + 16 + 256;
-    int32_t* s_off = reinterpret_cast<int32_t*>(smem + 16 + 256 + table_smem_bytes);
-    uint8_t* tile = smem + tile_offset(table_smem_bytes, spt);
-    const uint32_t mbar = smem_u32(smem);
+    uint8_t* s_cmap = smem;
+    uint8_t* s_table = smem + 256;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const SpanLayout L = span_layout(spt, cap);
+    uint8_t* region = smem + span_shared_head(table_smem_bytes) + warp * L.warp_bytes;
+    int32_t* s_off = reinterpret_cast<int32_t*>(region + 16);
+    uint8_t* tile = region + L.off_tile;
+    const uint32_t mbar = smem_u32(region);
     KParams fwd = p;                       // stage_table reads table / classmap / sizes from a KParams
     fwd.table = sp.table; fwd.classmap = sp.classmap; fwd.table_words = sp.table_words; fwd.row_shift = sp.row_shift;
     fwd.nstates = sp.nstates;
     Table<KIND> T = stage_table<KIND>(fwd, s_table, s_cmap);
-    if (threadIdx.x == 0) mbar_init(mbar, 1);
-    __syncthreads();
+    if (lane == 0) mbar_init(mbar, 1);
+    __syncthreads();                        // the only block-wide step
     uint32_t phase = 0;
     const uint32_t tile_addr = smem_u32(tile);
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const TileCtx c = load_tile(buf, offsets, n, total, t, spt, cap, tile, s_off, mbar, phase);
-        for (int i = threadIdx.x; i < c.count; i += blockDim.x) {
+    const uintptr_t gbuf = reinterpret_cast<uintptr_t>(buf);
+    const int64_t nwarps = (int64_t)gridDim.x * SPAN_WARPS;
+    for (int64_t t = (int64_t)blockIdx.x * SPAN_WARPS + warp; t < ntiles; t += nwarps) {
+        // ---- stage the tile: strings [first, first + count), up to `cap` bytes of them ----
+        const int64_t first = t * spt;
+        const int count = (int)((n - first) < spt ? (n - first) : spt);
+        const int64_t t0 = __ldg(offsets + first), tend = __ldg(offsets + first + count);
+        const int64_t t1 = tend - t0 > cap ? t0 + cap : tend;
+        const uintptr_t g0 = gbuf + (uintptr_t)t0;
+        const int64_t base = t0 - (int64_t)(g0 & 15);              // tile[0] = byte `base` (the bulk source is 16-byte aligned)
+        const uintptr_t gsrc = g0 & ~(uintptr_t)15;
+        uintptr_t gcopy_end = (gbuf + (uintptr_t)t1 + 15) & ~(uintptr_t)15;
+        const uintptr_t gsafe_end = (gbuf + (uintptr_t)total) & ~(uintptr_t)15;   // never bulk-read past the last whole 16-byte block
+        if (gcopy_end > gsafe_end) gcopy_end = gsafe_end;
+        const uint32_t bulk = gcopy_end > gsrc ? (uint32_t)(gcopy_end - gsrc) : 0u;
+        __syncwarp();                                              // every lane is done with the previous tile
+        if (bulk && lane == 0) {
+            mbar_expect_tx(mbar, bulk);
+            bulk_g2s(tile_addr, reinterpret_cast<const void*>(gsrc), bulk, mbar);
+        }
+        for (int64_t x = (int64_t)(gsrc + bulk) - (int64_t)gbuf + lane; x < t1; x += 32)   // < 16 bytes at the very end of the buffer
+            if (x >= t0) tile[x - base] = __ldg(buf + x);
+        for (int i = lane; i <= count; i += 32) {                  // overlaps with the bulk copy in flight
+            const int64_t o = __ldg(offsets + first + i);
+            s_off[i] = o > t1 ? OFF_BEYOND : (int32_t)(o - base);
+        }
+        if (bulk) { mbar_wait(mbar, phase); phase ^= 1; }
+        __syncwarp();
+        // ---- one string per lane.  (Tried: the lanes as a work queue -- a lane that finishes its string claims the
+        // tile's next one, one byte step per iteration: 18 instead of 12 busy lanes, but the per-step ballots and the
+        // claim path cost more than that buys: 252 vs 360 GB/s on C3.) ----
+        for (int i = lane; i < count; i += 32) {
             const int32_t r0 = s_off[i], r1 = s_off[i + 1];
             int64_t f = 0, e = 0;
             if (r1 == OFF_BEYOND) {          // not staged (longer than a tile): the anchored emulation from global memory
-                const int64_t o0 = __ldg(offsets + c.first + i), o1 = __ldg(offsets + c.first + i + 1);
+                const int64_t o0 = __ldg(offsets + first + i), o1 = __ldg(offsets + first + i + 1);
                 Table<3> G;
                 G.g_table = p.ctable; G.g_cmap = p.classmap; G.shift = p.c_row_shift; G.s_table = 0; G.s_cmap = 0;
                 eval_regex(p, G, FetchGlobal{buf + o0}, o1 - o0, f, e);
@@ -1516,10 +1570,9 @@ __global__ void __launch_bounds__(256) k_span_ragged(KParams p, SpanParams sp, c
                 if (!(len == 0 || (len == 1 && lds_u8(a) == 0x20)))              // api_internal_m.F90:68-74
                     span_linear_smem(sp, T, a, len, f, e);
             }
-            from[c.first + i] = f;
-            to[c.first + i] = e;
+            from[first + i] = f;
+            to[first + i] = e;
         }
-        __syncthreads();
     }
 }
 
