@@ -357,6 +357,9 @@ inline int generic_mode(const Plan& pl, int op) {
     return (pl.kp.all_active || (op == 0 && (pl.kp.pre_active || pl.kp.suf_active)) || (op == 1 && pl.kp.prefix_mode == 2)) ? 1 : 0;
 }
 
+int launch_sparse(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int64_t* off, int64_t n, int64_t total,
+                  uint8_t* out, cudaStream_t s, int64_t stride);
+
 template <int OP>
 int launch_fixed(fx_pattern* p, const uint8_t* buf, int64_t n, int64_t stride, uint8_t* out, cudaStream_t s) {
     if (n < 0 || stride < 0) return FX_ERR_BAD_ARGUMENT;
@@ -365,6 +368,11 @@ int launch_fixed(fx_pattern* p, const uint8_t* buf, int64_t n, int64_t stride, u
     int rc = make_plan(p, pl);
     if (rc) return rc;
     int generic = generic_mode(pl, OP);
+    p->last_sparse = 0;
+    if (OP == 1 && !generic && p->sparse && stride > 0 && n < (1ll << 31) && env_int("FX_SPARSE", 1)) {   // sparse starts (K2c)
+        p->last_sparse = 1;
+        return launch_sparse(p, pl, buf, nullptr, n, n * stride, out, s, stride);
+    }
     if (pl.kind == 0) return launch_fixed_v<OP, 0>(p, pl, buf, n, stride, out, s, generic);
     if (pl.kind == 2) return launch_fixed_v<OP, 2>(p, pl, buf, n, stride, out, s, generic);
     return launch_fixed_v<OP, 3>(p, pl, buf, n, stride, out, s, generic);
@@ -477,7 +485,7 @@ int launch_stream_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int
 // K2c: a warp sweeps tiles of `spt` consecutive strings, about 16 KB of text each
 template <int KIND, int NR, bool HIGH, bool TWO, int MINB, int ROWS>
 int launch_sparse_v(fx_pattern* p, const Plan& pl, const SparseParams& sp, int table_bytes, const uint8_t* buf,
-                    const int64_t* off, int64_t n, int64_t total, uint8_t* out, cudaStream_t s) {
+                    const int64_t* off, int64_t n, int64_t total, uint8_t* out, cudaStream_t s, int64_t stride) {
     auto kern = k_in_sparse<KIND, NR, HIGH, TWO, MINB, ROWS>;
     int64_t avg = n > 0 ? (total + n - 1) / n : 1;
     if (avg < 1) avg = 1;
@@ -499,32 +507,32 @@ int launch_sparse_v(fx_pattern* p, const Plan& pl, const SparseParams& sp, int t
     const int prezeroed = sp.start_nul == 0 && pl.kp.q0_accepting == 0;
     if (prezeroed) CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)n, s));
     kern<<<grid, 256, smem, s>>>(pl.kp, sp, buf, off, n, total, out, spt, ntiles, table_smem, prezeroed, env_int("FX_SPARSE_FLUSH", 0),
-                                   env_int("FX_SPARSE_STREAM_HINT", 1));
+                                   env_int("FX_SPARSE_STREAM_HINT", 1), stride);
     g_launches++;
     return cuda_status(cudaGetLastError());
 }
 
 template <int KIND, int NR, bool HIGH, bool TWO>
 int launch_sparse_t(fx_pattern* p, const Plan& pl, const SparseParams& sp, int table_bytes, const uint8_t* buf,
-                    const int64_t* off, int64_t n, int64_t total, uint8_t* out, cudaStream_t s) {
+                    const int64_t* off, int64_t n, int64_t total, uint8_t* out, cudaStream_t s, int64_t stride) {
     // 4 CTAs per SM, 4 rows (4 KB per warp) in flight: the best of the measured combinations
-    return launch_sparse_v<KIND, NR, HIGH, TWO, 4, 4>(p, pl, sp, table_bytes, buf, off, n, total, out, s);
+    return launch_sparse_v<KIND, NR, HIGH, TWO, 4, 4>(p, pl, sp, table_bytes, buf, off, n, total, out, s, stride);
 }
 
 template <int KIND, bool HIGH>
 int launch_sparse_k(fx_pattern* p, const Plan& pl, const SparseParams& sp, int tb, const uint8_t* buf, const int64_t* off,
-                    int64_t n, int64_t total, uint8_t* out, cudaStream_t s) {
+                    int64_t n, int64_t total, uint8_t* out, cudaStream_t s, int64_t stride) {
     if (p->first.sweep_nr == 1 && p->first.sweep_lo[0] == p->first.sweep_hi[0]) {      // one byte value: the cheaper zero-byte test
         const SparseParams& one = sp;      // (fill_sweep has put the byte value into add_lo[0])
-        if (p->first.two && env_int("FX_SPARSE_TWO", 1)) return launch_sparse_t<KIND, -1, HIGH, true>(p, pl, one, tb, buf, off, n, total, out, s);
-        return launch_sparse_t<KIND, -1, HIGH, false>(p, pl, one, tb, buf, off, n, total, out, s);
+        if (p->first.two && env_int("FX_SPARSE_TWO", 1)) return launch_sparse_t<KIND, -1, HIGH, true>(p, pl, one, tb, buf, off, n, total, out, s, stride);
+        return launch_sparse_t<KIND, -1, HIGH, false>(p, pl, one, tb, buf, off, n, total, out, s, stride);
     }
     switch (p->first.sweep_nr) {
-        case 0: return launch_sparse_t<KIND, 0, true, false>(p, pl, sp, tb, buf, off, n, total, out, s);
-        case 1: return launch_sparse_t<KIND, 1, HIGH, false>(p, pl, sp, tb, buf, off, n, total, out, s);
-        case 2: return launch_sparse_t<KIND, 2, HIGH, false>(p, pl, sp, tb, buf, off, n, total, out, s);
-        case 3: return launch_sparse_t<KIND, 3, HIGH, false>(p, pl, sp, tb, buf, off, n, total, out, s);
-        default: return launch_sparse_t<KIND, 4, HIGH, false>(p, pl, sp, tb, buf, off, n, total, out, s);
+        case 0: return launch_sparse_t<KIND, 0, true, false>(p, pl, sp, tb, buf, off, n, total, out, s, stride);
+        case 1: return launch_sparse_t<KIND, 1, HIGH, false>(p, pl, sp, tb, buf, off, n, total, out, s, stride);
+        case 2: return launch_sparse_t<KIND, 2, HIGH, false>(p, pl, sp, tb, buf, off, n, total, out, s, stride);
+        case 3: return launch_sparse_t<KIND, 3, HIGH, false>(p, pl, sp, tb, buf, off, n, total, out, s, stride);
+        default: return launch_sparse_t<KIND, 4, HIGH, false>(p, pl, sp, tb, buf, off, n, total, out, s, stride);
     }
 }
 
@@ -540,7 +548,7 @@ void fill_sweep(const FirstSet& f, SparseParams& sp) {
 }
 
 int launch_sparse(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int64_t* off, int64_t n, int64_t total,
-                  uint8_t* out, cudaStream_t s) {
+                  uint8_t* out, cudaStream_t s, int64_t stride) {
     const fx::ByteTable& at = p->anchored.bt;
     const DeviceTables& d = p->dev;
     SparseParams sp;
@@ -552,10 +560,10 @@ int launch_sparse(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int64
     const int tb = (int)at.table.size() * 2;
     const bool smem_table = p->residency != FX_TABLE_GLOBAL && tb <= env_int("FX_SPARSE_SMEM_TABLE_BYTES", 24 * 1024);
     if (smem_table)
-        return p->first.high ? launch_sparse_k<2, true>(p, pl, sp, tb, buf, off, n, total, out, s)
-                             : launch_sparse_k<2, false>(p, pl, sp, tb, buf, off, n, total, out, s);
-    return p->first.high ? launch_sparse_k<3, true>(p, pl, sp, tb, buf, off, n, total, out, s)
-                         : launch_sparse_k<3, false>(p, pl, sp, tb, buf, off, n, total, out, s);
+        return p->first.high ? launch_sparse_k<2, true>(p, pl, sp, tb, buf, off, n, total, out, s, stride)
+                             : launch_sparse_k<2, false>(p, pl, sp, tb, buf, off, n, total, out, s, stride);
+    return p->first.high ? launch_sparse_k<3, true>(p, pl, sp, tb, buf, off, n, total, out, s, stride)
+                         : launch_sparse_k<3, false>(p, pl, sp, tb, buf, off, n, total, out, s, stride);
 }
 
 template <int OP>
@@ -570,7 +578,7 @@ int launch_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, int64_t
     p->last_sparse = 0;
     if (OP == 1 && !generic && p->sparse && n < (1ll << 31) && env_int("FX_SPARSE", 1)) {      // sparse starts (K2c)
         p->last_sparse = 1;
-        return launch_sparse(p, pl, buf, off, n, total, out, s);
+        return launch_sparse(p, pl, buf, off, n, total, out, s, 0);
     }
     if (!generic && env_int("FX_RAGGED_FORM", 0) == 2) {      // length-balanced pairs (K2p)
         if (pl.kind == 0) return launch_pairs_t<OP, 0>(p, pl, buf, off, n, total, out, s);

@@ -811,7 +811,8 @@ __device__ __forceinline__ bool attempt_wins(const Anchored& A, const TBL& T, FE
 // per-warp context of the deferred phases (everything but the queues' fill levels is read-only)
 struct SparseCtx {
     const uint8_t* buf;
-    const int64_t* offsets;
+    const int64_t* offsets;   // nullptr: fixed-stride batch, string i = [i * stride, (i + 1) * stride)
+    int64_t stride;
     uint8_t* out;
     int64_t n, total;
     int spt;
@@ -819,6 +820,10 @@ struct SparseCtx {
     uint4* starts;    // queue of starts to attempt
 };
 static constexpr uint32_t SPARSE_START = 0, SPARSE_RECHECK = 2;
+// start of string i: from the offsets array, or i * stride for a fixed-stride batch
+__device__ __forceinline__ int64_t sparse_off(const int64_t* __restrict__ offsets, int64_t stride, int64_t i) {
+    return offsets ? __ldg(offsets + i) : i * stride;
+}
 
 // Phase A: `count` (<= 32) queued starts, one per lane.
 //   kind SPARSE_START    {tile, kind|high, position (64 bit) relative to the tile's first byte}: find the string, attempt
@@ -846,7 +851,19 @@ __device__ __noinline__ void sparse_run_starts(const KParams& p, const SparsePar
         const int64_t* off = c.offsets + first;
         const uint32_t kind = e.y & 7u;
         const int64_t val = (int64_t)(((unsigned long long)e.w << 32) | e.z);
-        if (kind == SPARSE_START) {
+        if (c.offsets == nullptr) {                                // fixed stride: the string is a division away
+            const int64_t s = kind == SPARSE_START ? val / c.stride : val;
+            const uint8_t* str = c.buf + (first + s) * c.stride;
+            bool win;
+            if (kind == SPARSE_START) {
+                win = !(c.stride == 1 && __ldg(str) == 0x20) &&
+                      attempt_wins(A, T, FetchGlobal{str}, c.stride, (uint32_t)sp.q0, val - s * c.stride);
+                if (win && p.prefix_mode == 1 && (e.y >> 31)) win = recheck_in_with_prefix(p, str, c.stride);
+                if (win) c.out[first + s] = 1;
+            } else {
+                c.out[first + s] = recheck_in_with_prefix(p, str, c.stride) ? 1 : 0;
+            }
+        } else if (kind == SPARSE_START) {
             const int cnt = (int)((c.n - first) < c.spt ? (c.n - first) : c.spt);
             // largest s with off[s] <= gpos.  Interpolation search: the probes land next to the answer (one or two
             // 32-byte sectors of offsets instead of the log2(cnt) scattered ones of a bisection); bisection takes over
@@ -895,8 +912,8 @@ __device__ __noinline__ int sparse_run_units(const KParams& p, const SparseParam
         tile = e.x; flag = e.y & 0x80000000u;
         const int64_t first = (int64_t)e.x * c.spt;
         const int cnt = (int)((c.n - first) < c.spt ? (c.n - first) : c.spt);
-        t0 = __ldg(c.offsets + first);
-        const int64_t tend = __ldg(c.offsets + first + cnt);
+        t0 = sparse_off(c.offsets, c.stride, first);
+        const int64_t tend = sparse_off(c.offsets, c.stride, first + cnt);
         const uintptr_t gbuf = reinterpret_cast<uintptr_t>(c.buf);
         const uintptr_t ua = ((gbuf + (uintptr_t)t0) & ~(uintptr_t)31) + ((((uintptr_t)e.w << 32) | e.z) << 5);
         const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(ua)), v1 = __ldg(reinterpret_cast<const uint4*>(ua + 16));
@@ -943,7 +960,8 @@ template <int KIND, int NR, bool HIGH, bool TWO, int MINB, int ROWS>
 __global__ void __launch_bounds__(256, MINB) k_in_sparse(KParams p, SparseParams sp, const uint8_t* __restrict__ buf,
                                                       const int64_t* __restrict__ offsets, int64_t n, int64_t total,
                                                       uint8_t* __restrict__ out, int spt, int64_t ntiles,
-                                                      int table_smem_bytes, int prezeroed, int flush_min, int stream_hint) {
+                                                      int table_smem_bytes, int prezeroed, int flush_min, int stream_hint,
+                                                      int64_t stride) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_cmap = smem;
     uint8_t* s_table = smem + 256;
@@ -961,7 +979,8 @@ __global__ void __launch_bounds__(256, MINB) k_in_sparse(KParams p, SparseParams
     SparseCtx* sh_c = reinterpret_cast<SparseCtx*>(s_params + sizeof(KParams) + sizeof(SparseParams)) + warp;
     if (threadIdx.x == 0) { *sh_p = p; *sh_sp = sp; }
     if (lane == 0) {
-        sh_c->buf = buf; sh_c->offsets = offsets; sh_c->out = out; sh_c->n = n; sh_c->total = total; sh_c->spt = spt;
+        sh_c->buf = buf; sh_c->offsets = offsets; sh_c->stride = stride; sh_c->out = out; sh_c->n = n; sh_c->total = total;
+        sh_c->spt = spt;
         sh_c->units = s_units; sh_c->starts = s_starts;
     }
     __syncthreads();                        // the only block-wide step: table and parameter copies are staged
@@ -991,11 +1010,12 @@ __global__ void __launch_bounds__(256, MINB) k_in_sparse(KParams p, SparseParams
                 if (t >= nt) { drain = true; break; }
                 const int64_t first = (int64_t)t * spt;
                 count = (int)((n - first) < spt ? (n - first) : spt);
-                const int64_t t0 = have_next ? nx0 : __ldg(offsets + first), tend = have_next ? nx1 : __ldg(offsets + first + count);
+                const int64_t t0 = have_next ? nx0 : sparse_off(offsets, stride, first);
+                const int64_t tend = have_next ? nx1 : sparse_off(offsets, stride, first + count);
                 {   // the next tile's extents, asked for now, used when this tile is done
                     const int64_t fn = first + (int64_t)gridDim.x * 8 * spt;
                     have_next = fn < n;
-                    if (have_next) { nx0 = __ldg(offsets + fn); nx1 = __ldg(offsets + (fn + spt < n ? fn + spt : n)); }
+                    if (have_next) { nx0 = sparse_off(offsets, stride, fn); nx1 = sparse_off(offsets, stride, fn + spt < n ? fn + spt : n); }
                 }
                 const uintptr_t g0 = reinterpret_cast<uintptr_t>(buf) + (uintptr_t)t0;
                 ubase = g0 & ~(uintptr_t)31;
@@ -1045,7 +1065,7 @@ __global__ void __launch_bounds__(256, MINB) k_in_sparse(KParams p, SparseParams
                     const int i = it + lane;
                     bool r = false, defer = false;
                     if (i < count) {
-                        const int64_t o0 = __ldg(offsets + first + i), o1 = __ldg(offsets + first + i + 1);
+                        const int64_t o0 = sparse_off(offsets, stride, first + i), o1 = sparse_off(offsets, stride, first + i + 1);
                         const int64_t len = o1 - o0;
                         if (len == 0 || (len == 1 && __ldg(buf + o0) == 0x20)) r = p.q0_accepting != 0;   // api_internal_m.F90:68-74
                         else if (sp.start_nul != 0) {

@@ -432,3 +432,27 @@ def test_prefix_literal_windows_like_two_gpus():
             ft = torch.zeros(2, dtype=torch.int64, device="cuda")
             p.buffer_finish_dev(win, w_hi - w_lo, w_lo, w_hi == nbytes, torch.tensor([key], dtype=torch.int64, device="cuda"), ft)
             assert tuple(ft.cpu().tolist()) == exp, (len(text), world)
+
+
+def test_sparse_start_kernel_fixed_stride(monkeypatch):
+    """fixed-stride `.in.` batches take the sparse-start kernel too (a Fortran character array is one)"""
+    monkeypatch.setenv("FX_SPARSE_MAX_FIRST", "128")
+    rng = np.random.default_rng(31)
+    for stride in (1, 3, 8, 16, 24, 64, 100, 160, 4099):
+        n = 3000 if stride < 1000 else 40
+        raw = rng.integers(0x20, 0x7F, size=n * stride + 64, dtype=np.uint8)
+        raw[rng.random(raw.size) < 0.05] = ord("f")
+        for k in rng.integers(0, max(1, n * stride - 8), size=n // 3):
+            raw[k:k + 6] = np.frombuffer(b"foobar" if k & 1 else b"fooba!", dtype=np.uint8)
+        raw[rng.random(raw.size) < 0.002] = 0xC1
+        for shift in (0, 5):
+            buf = raw[shift:shift + n * stride]
+            for pat in [b"foo(bar|baz)", b"f+o", b"^f", b"r$", b"a*", b"[fz]o+"]:
+                monkeypatch.setenv("FX_SPARSE", "1")
+                p = fx.Pattern(pat, "in")
+                got = p.in_fixed(buf, n, stride)
+                assert p.info()["sparse_used"] == p.info()["sparse"]
+                exp = oracle_bool(pat, "in", np.ascontiguousarray(buf), n=n, stride=stride)
+                assert np.array_equal(got, exp), (stride, shift, pat, np.nonzero(got != exp)[0][:10])
+                monkeypatch.setenv("FX_SPARSE", "0")
+                assert np.array_equal(p.in_fixed(buf, n, stride), exp), (stride, shift, pat, "K1")
