@@ -1,0 +1,51 @@
+"""small run of every kernel family, meant for `compute-sanitizer --tool memcheck python tools/sanitize_smoke.py`.
+
+Round 1: one attempt at the original (larger) sizes did not finish within 20 GPU-minutes under memcheck and was cut
+off without a verdict; the sizes below are a tenth of that.  Still unverified -- run it early in round 2.
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import forgex_b200 as fx  # noqa: E402
+from tools import synth  # noqa: E402
+
+
+def pack(strings):
+    off = np.zeros(len(strings) + 1, dtype=np.int64)
+    np.cumsum([len(s) for s in strings], out=off[1:])
+    return np.frombuffer(b"".join(strings), dtype=np.uint8).copy(), off
+
+
+def main():
+    rng = np.random.default_rng(3)
+    buf, off = synth.gen_c2(300)
+    strings = [b"", b" ", b"foobar", b"x" * 9000 + b"foobaz", b"\xc1\xa6oobar fooba!", b"f"] + \
+              [bytes(rng.integers(0x20, 0x7F, size=int(k), dtype=np.uint8)) for k in rng.integers(0, 300, size=200)]
+    b2, o2 = pack(strings)
+    total = 0
+    for pat in [b"foo(bar|baz)", b"^foo", b"[a-z]+r", rb"\d{3}-\d{4}", "[ぁ-ん]+a".encode()]:
+        p = fx.Pattern(pat, "in")
+        total += int(p.in_batch(buf, off).sum()) + int(p.in_batch(b2, o2).sum())
+        total += int(fx.Pattern(pat, "match").match_batch(b2, o2).sum())
+        f, t = fx.Pattern(pat, "regex").regex_batch(b2, o2)
+        total += int(f.sum())
+    fb, n, stride = synth.gen_c1(400)
+    total += int(fx.Pattern(synth.PATTERNS["c1"], "match").match_fixed(fb, n, stride).sum())
+    fb, n, stride = synth.gen_c5(50)
+    total += int(fx.Pattern(synth.PATTERNS["c5"], "in").in_fixed(fb, n, stride).sum())
+    raw = rng.integers(0x20, 0x7F, size=100 * 160 + 7, dtype=np.uint8)
+    total += int(fx.Pattern(b"foo(bar|baz)", "in").in_fixed(raw[7:], 100, 160).sum())
+    for nbytes in (4099, 30001):
+        text = synth.gen_c4(nbytes, 0.7)
+        total += sum(fx.Pattern(synth.PATTERNS["c4"], "regex").regex_buffer(text))
+        total += sum(fx.Pattern(b"foo(bar|baz)", "regex").regex_buffer(text))
+        total += sum(fx.Pattern(rb"ERROR.*timeout=\d+", "regex").regex_buffer(text[3:]))
+        total += sum(fx.Pattern(rb"\w+@\w+", "regex").regex_buffer(text))
+    print("sanitize smoke checksum", total)
+
+
+if __name__ == "__main__":
+    main()
