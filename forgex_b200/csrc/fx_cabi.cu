@@ -1042,7 +1042,7 @@ static int host_bool_fixed(fx_pattern* p, int op, const uint8_t* buf, int64_t n,
     std::lock_guard<std::mutex> lock(p->mu);
     DeviceTables& d = p->dev;
     size_t bytes = (size_t)n * (size_t)stride;
-    if ((rc = grow(d.w_buf, d.w_buf_cap, bytes + 16))) return rc;
+    if ((rc = grow(d.w_buf, d.w_buf_cap, bytes + 64))) return rc;
     if ((rc = grow(d.w_out, d.w_out_cap, (size_t)n))) return rc;
     if (bytes) CUDA_TRY(cudaMemcpyAsync(d.w_buf, buf, bytes, cudaMemcpyHostToDevice, 0));
     rc = op == FX_OP_MATCH ? launch_fixed<0>(p, d.w_buf, n, stride, d.w_out, 0) : launch_fixed<1>(p, d.w_buf, n, stride, d.w_out, 0);
@@ -1064,7 +1064,7 @@ static int host_stage_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* o
     total = offsets[n] - base;
     if (total < 0 || base != 0) return FX_ERR_BAD_ARGUMENT;   // offsets must start at 0
     int rc;
-    if ((rc = grow(d.w_buf, d.w_buf_cap, (size_t)total + 16))) return rc;
+    if ((rc = grow(d.w_buf, d.w_buf_cap, (size_t)total + 64))) return rc;
     if ((rc = grow(d.w_off, d.w_off_cap, (size_t)(n + 1) * 8))) return rc;
     if (total) CUDA_TRY(cudaMemcpyAsync(d.w_buf, buf, (size_t)total, cudaMemcpyHostToDevice, 0));
     CUDA_TRY(cudaMemcpyAsync(d.w_off, offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, 0));
@@ -1116,7 +1116,7 @@ int fx_regex_buffer(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* fro
     if (len < 0) return FX_ERR_BAD_ARGUMENT;
     std::lock_guard<std::mutex> lock(p->mu);
     DeviceTables& d = p->dev;
-    if ((rc = grow(d.w_buf, d.w_buf_cap, (size_t)len + 16))) return rc;
+    if ((rc = grow(d.w_buf, d.w_buf_cap, (size_t)len + 64))) return rc;
     if ((rc = grow(d.w_span, d.w_span_cap, 16))) return rc;
     if (len) CUDA_TRY(cudaMemcpyAsync(d.w_buf, buf, (size_t)len, cudaMemcpyHostToDevice, 0));
     rc = launch_buffer(p, d.w_buf, len, d.w_span, d.w_best, 0);

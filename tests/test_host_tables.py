@@ -274,3 +274,22 @@ def test_prefix_literal_patterns_on_the_buffer_path(seed):
                 bad.append("%r on %r: model %r oracle %r" % (pat, text, got, (f, to)))
     assert not bad, "%d mismatches:\n%s" % (len(bad), "\n".join(bad[:30]))
     assert eligible > 15 and rejected > 0
+
+
+def test_sparse_start_and_prefix_scan_eligibility():
+    """which patterns the host sends to the sparse-start sweep (K2c / K4) and to the prefix-candidate buffer scan"""
+    def inf(pat, op):
+        return fx.Pattern(pat, op).info()
+    i = inf(b"foo(bar|baz)", "in")
+    assert (i["sparse"], i["sparse_lo"], i["sparse_hi"], i["sparse_high"], i["sparse_second"], i["prefix_mode"]) == \
+        (1, [0x66], [0x66], 1, 0x6F, 1)           # 'f', then only 'o' (or a lead byte: overlong forms) can follow
+    i = inf(rb"^ERROR.*timeout=\d+$", "in")
+    assert (i["sparse"], i["sparse_lo"], i["sparse_hi"], i["sparse_second"]) == (1, [0, 10, 13], [0, 10, 13], -1)
+    assert inf(rb"\w+@\w+", "in")["sparse"] == 0       # 63 possible first bytes: not sparse
+    assert inf(b"[^a]b", "in")["sparse"] == 0          # a stray continuation byte (U+FFFF) can start a match
+    assert inf(b"^", "in")["sparse"] == 0              # the leading NUL alone already accepts
+    assert inf(b"(a|b)*a(a|b){12}", "in")["sparse"] == 0   # anchored automaton above the optional-build cap
+    assert inf(b"foobar", "in")["sparse"] == 0         # literal-only: the automaton is never consulted
+    for pat, ok in [(rb"ERROR.*timeout=\d+", 1), (b"foo(bar|baz)", 1), (b"key=[0-9]*", 1), ("\u3042\u3044+".encode(), 1),
+                    (b"ab+c", 0), (b"aab*", 0), (b"abab+", 0), (b"fo+bar", 0), (rb"^ERROR.*timeout=\d+$", 0), (b"[a-z]+", 0)]:
+        assert inf(pat, "regex")["prefix_scan"] == ok, pat
