@@ -482,7 +482,7 @@ int launch_stream_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int
     return cuda_status(cudaGetLastError());
 }
 
-// K2c: a warp sweeps tiles of `spt` consecutive strings, about 16 KB of text each
+// K2c: a warp sweeps tiles of `spt` consecutive strings, about 24 KB of text each
 template <int KIND, int NR, bool HIGH, bool TWO, int MINB, int ROWS>
 int launch_sparse_v(fx_pattern* p, const Plan& pl, const SparseParams& sp, int table_bytes, const uint8_t* buf,
                     const int64_t* off, int64_t n, int64_t total, uint8_t* out, cudaStream_t s, int64_t stride) {

@@ -690,8 +690,8 @@ __global__ void __launch_bounds__(256, 4) k_bool_ragged(KParams p, const uint8_t
 // small (a few byte ranges: 'f' for foo(bar|baz); NUL/LF/CR for ^ERROR...), almost every position of the text is
 // ruled out by a compare.  The kernel therefore does not walk the strings at all, it has no block-wide step, and
 // the text never passes through shared memory:
-//   S  sweep: a warp owns tiles of consecutive strings (about 16 KB of text).  Its lanes read the tile's bytes
-//      LINEARLY, 32 bytes per lane and step, as coalesced 16-byte loads straight from global memory (two rows = 2 KB
+//   S  sweep: a warp owns tiles of consecutive strings (about 24 KB of text).  Its lanes read the tile's bytes
+//      LINEARLY, 32 bytes per lane and step, as coalesced 16-byte loads straight from global memory (four rows = 4 KB
 //      per warp in flight), and test them against F with SWAR arithmetic (3-4 integer instructions per 4 bytes).
 //      When the automaton has ONE first byte and ONE possible second byte (a pattern that begins with a literal), the
 //      test is for that byte pair.  32-byte units that pass are queued;
