@@ -1427,8 +1427,9 @@ __device__ __forceinline__ int cp_class(const SpanParams& sp, uint32_t cp) {
 }
 
 // backward half of the linear-time span search: the leftmost start of a match that ends at `last` (> 0)
-__device__ __forceinline__ void span_backward_smem(const SpanParams& sp, uint32_t a, int len, int last,
-                                                   int64_t& from, int64_t& to) {
+template <class FETCH>
+__device__ __forceinline__ void span_backward(const SpanParams& sp, FETCH fetch, int len, int last,
+                                              int64_t& from, int64_t& to) {
     from = 0; to = 0;
     // ---- backward: leftmost start of a match that ends at `last` ----
     uint32_t r = (uint32_t)sp.rstart;
@@ -1437,7 +1438,7 @@ __device__ __forceinline__ void span_backward_smem(const SpanParams& sp, uint32_
     int best = -2;                                          // -2 none, -1 the leading NUL, >= 0 text index
     while (r != 0 && pos > 0) {
         // the character that ends at pos
-        uint32_t c = lds_u8(a + pos - 1);
+        uint32_t c = fetch(pos - 1);
         int q = pos - 1;
         uint32_t cp = c;
         if (c >= 0x80) {
@@ -1446,7 +1447,7 @@ __device__ __forceinline__ void span_backward_smem(const SpanParams& sp, uint32_
                 uint32_t acc = c & 0x3F;
                 int shift = 6;
                 for (int back = 2; back <= 4 && pos - back >= 0; back++) {
-                    const uint32_t d = lds_u8(a + pos - back);
+                    const uint32_t d = fetch(pos - back);
                     if ((d & 0xC0) == 0x80) { acc |= (d & 0x3F) << shift; shift += 6; continue; }
                     const int n = (d >> 5) == 6 ? 2 : (d >> 4) == 14 ? 3 : (d >> 3) == 30 ? 4 : 1;
                     if (n == back) {
@@ -1472,9 +1473,10 @@ __device__ __forceinline__ void span_backward_smem(const SpanParams& sp, uint32_
     to = last < len ? last : len;
 }
 
-template <class TBL>
-__device__ __forceinline__ void span_linear_smem(const SpanParams& sp, const TBL& T, uint32_t a, int len,
-                                                 int64_t& from, int64_t& to) {
+// the linear-time span search over any byte source: forward walk to the match end, backward walk to its start
+template <class TBL, class FETCH>
+__device__ __forceinline__ void span_linear(const SpanParams& sp, const TBL& T, FETCH fetch, int len,
+                                            int64_t& from, int64_t& to) {
     from = 0; to = 0;
     // ---- forward: end of the leftmost-longest match ----
     uint32_t w = (uint32_t)sp.start;
@@ -1483,7 +1485,7 @@ __device__ __forceinline__ void span_linear_smem(const SpanParams& sp, const TBL
     bool inter = false;
     int j = 0;
     for (; j < len; j++) {
-        const uint32_t b = lds_u8(a + j);
+        const uint32_t b = fetch(j);
         if (inter && (b & 0xC0) != 0x80) {                  // sequence broken: pending bytes replay as U+FFFF
             const uint32_t f = __ldg(sp.flags + (w & W_STATE));
             for (int k = 1; k <= j - seq; k++)
@@ -1505,7 +1507,12 @@ __device__ __forceinline__ void span_linear_smem(const SpanParams& sp, const TBL
         if (f & SF_END) last = len + 1;
     }
     if (last <= 0) return;                                  // no match, or only the leading NUL matched (to = 0)
-    span_backward_smem(sp, a, len, last, from, to);
+    span_backward(sp, fetch, len, last, from, to);
+}
+template <class TBL>
+__device__ __forceinline__ void span_linear_smem(const SpanParams& sp, const TBL& T, uint32_t a, int len,
+                                                 int64_t& from, int64_t& to) {
+    span_linear(sp, T, FetchShared{a}, len, from, to);
 }
 
 // shared memory of K3f: classmap 256 | table | pad to 128 | SPAN_WARPS warp regions of `warp_bytes`:
@@ -1579,11 +1586,15 @@ __global__ void __launch_bounds__(SPAN_WARPS * 32, 2) k_span_ragged(KParams p, S
         for (int i = lane; i < count; i += 32) {
             const int32_t r0 = s_off[i], r1 = s_off[i + 1];
             int64_t f = 0, e = 0;
-            if (r1 == OFF_BEYOND) {          // not staged (longer than a tile): the anchored emulation from global memory
+            if (r1 == OFF_BEYOND) {          // not staged (longer than a warp's tile): the same two walks, text from global memory
                 const int64_t o0 = __ldg(offsets + first + i), o1 = __ldg(offsets + first + i + 1);
-                Table<3> G;
-                G.g_table = p.ctable; G.g_cmap = p.classmap; G.shift = p.c_row_shift; G.s_table = 0; G.s_cmap = 0;
-                eval_regex(p, G, FetchGlobal{buf + o0}, o1 - o0, f, e);
+                if (o1 - o0 < 0x7FFFFFF0ll) {
+                    span_linear(sp, T, FetchGlobal{buf + o0}, (int)(o1 - o0), f, e);
+                } else {                     // 2 GiB and more in one string: 64-bit positions, the anchored emulation
+                    Table<3> G;
+                    G.g_table = p.ctable; G.g_cmap = p.classmap; G.shift = p.c_row_shift; G.s_table = 0; G.s_cmap = 0;
+                    eval_regex(p, G, FetchGlobal{buf + o0}, o1 - o0, f, e);
+                }
             } else {
                 const int len = r1 - r0;
                 const uint32_t a = tile_addr + (uint32_t)r0;

@@ -216,6 +216,7 @@ def test_ragged_edge_cases():
     strings = [b"", b" ", b"a", b"", b"", b"foobar", b"x" * 5000 + b"foobaz", b"y" * 70000, b"foobar" * 3, b"",
                bytes(rng.integers(0, 256, size=300, dtype=np.uint8)), b"\x00", b"\xe3\x81", b"fooba", b""]
     strings += [bytes(rng.integers(0x20, 0x7F, size=int(k), dtype=np.uint8)) for k in rng.integers(0, 40, size=500)]
+    strings += [b"7" * 20000 + b"abcr" + b"7" * 3000, b"7" * 9000 + "\u3042\u3044 ab".encode() + b"7" * 9000]   # longer than a warp's tile
     strings += [b"", b""]
     buf, off = pack(strings)
     for pat, op in [(b"foo(bar|baz)", "in"), (rb"\d{3}-\d{4}", "match"), (b"[a-z]+", "in"), (b"", "match"), (b"a*", "in"),
@@ -224,9 +225,18 @@ def test_ragged_edge_cases():
         got = p.in_batch(buf, off) if op == "in" else p.match_batch(buf, off)
         exp = oracle_bool(pat, op, buf, offsets=off)
         assert np.array_equal(got, exp), (pat, op, np.nonzero(got != exp)[0][:10])
-    for pat in [b"[a-z]+", b"o+b", b"foobar", b"(foo|y+)$", b"^", b"\\s\\S+", b"aa[bc]"]:
+    for pat in [b"[a-z]+", b"o+b", b"foobar", b"(foo|y+)$", b"^", b"\\s\\S+", b"aa[bc]", synth.PATTERNS["c3"]]:
         p = fx.Pattern(pat, "regex")
         f, t = p.regex_batch(buf, off)
+        ef, et = O.Compiled(pat, 0).regex_batch(buf, off)
+        assert np.array_equal(f, ef) and np.array_equal(t, et), pat
+    # a pattern whose attempts run long (quadratic for the reference's brute force, hence for the oracle): only on
+    # strings where every failing start dies at once; they are longer than a warp's tile and take the linear path
+    # from global memory
+    long_strings = [b"7" * 20000 + b"abcr" + b"7" * 3000, b"abc", b"7" * 30000, b"", b"7" * 6000 + b"zr", b"r" * 9]
+    buf, off = pack(long_strings)
+    for pat in [b"[a-z]+r", b"[a-z]*r7", rb"\d+r"]:
+        f, t = fx.Pattern(pat, "regex").regex_batch(buf, off)
         ef, et = O.Compiled(pat, 0).regex_batch(buf, off)
         assert np.array_equal(f, ef) and np.array_equal(t, et), pat
 

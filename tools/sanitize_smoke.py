@@ -19,7 +19,25 @@ def pack(strings):
     return np.frombuffer(b"".join(strings), dtype=np.uint8).copy(), off
 
 
+def quick():
+    """the round's new kernels only: K2c (ragged + fixed), K4 sparse sweep, prefix scan, K3f"""
+    buf, off = synth.gen_c2(300)
+    total = int(fx.Pattern(b"foo(bar|baz)", "in").in_batch(buf, off).sum())
+    total += int(fx.Pattern(b"^foo", "in").in_batch(buf, off).sum())
+    raw = np.random.default_rng(1).integers(0x20, 0x7F, size=50 * 160 + 7, dtype=np.uint8)
+    total += int(fx.Pattern(b"foo(bar|baz)", "in").in_fixed(raw[7:], 50, 160).sum())
+    text = synth.gen_c4(4099, 0.7)
+    total += sum(fx.Pattern(synth.PATTERNS["c4"], "regex").regex_buffer(text))
+    total += sum(fx.Pattern(b"foo(bar|baz)", "regex").regex_buffer(text[3:]))
+    b3, o3 = synth.gen_c3(200)
+    f, t = fx.Pattern(synth.PATTERNS["c3"], "regex").regex_batch(b3, o3)
+    total += int(f.sum()) + int(t.sum())
+    print("sanitize quick checksum", total)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "quick":
+        return quick()
     rng = np.random.default_rng(3)
     buf, off = synth.gen_c2(300)
     strings = [b"", b" ", b"foobar", b"x" * 9000 + b"foobaz", b"\xc1\xa6oobar fooba!", b"f"] + \
