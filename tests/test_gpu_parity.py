@@ -235,7 +235,7 @@ def test_ragged_edge_cases():
     # from global memory
     long_strings = [b"7" * 20000 + b"abcr" + b"7" * 3000, b"abc", b"7" * 30000, b"", b"7" * 6000 + b"zr", b"r" * 9]
     buf, off = pack(long_strings)
-    for pat in [b"[a-z]+r", b"[a-z]*r7", rb"\d+r"]:
+    for pat in [b"[a-z]+r", b"[a-z]*r7", rb"\d{3}r"]:
         f, t = fx.Pattern(pat, "regex").regex_batch(buf, off)
         ef, et = O.Compiled(pat, 0).regex_batch(buf, off)
         assert np.array_equal(f, ef) and np.array_equal(t, et), pat
