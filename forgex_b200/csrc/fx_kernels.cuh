@@ -529,6 +529,37 @@ __global__ void __launch_bounds__(256) k_bool_fixed(KParams p, const uint8_t* __
     Table<KIND> T = stage_table<KIND>(p, s_table, s_cmap);
     if (KIND != 3) __syncthreads();
     const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    if ((VEC == 8 || VEC == 16) && !generic && stride == VEC) {
+        // One load covers a whole string (C1: 8 bytes): the walk is 8-16 lookups, short against the latency of the load
+        // in front of it, so a thread takes FOUR strings per step -- all loads first, then the four walks.
+        for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * gstride) {
+            constexpr int NW = VEC == 16 ? 4 : 2;          // 32-bit words per string
+            uint32_t w[4][NW];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t i = i0 + u * gstride;
+#pragma unroll
+                for (int q = 0; q < NW; q++) w[u][q] = 0;
+                if (i < n) {
+                    if (VEC == 16) { const uint4 v = ldg_nc_v4(buf + i * stride); w[u][0] = v.x; w[u][1] = v.y; w[u][NW - 2] = v.z; w[u][NW - 1] = v.w; }
+                    else { const uint2 v = ldg_nc_v2(buf + i * stride); w[u][0] = v.x; w[u][1] = v.y; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t i = i0 + u * gstride;
+                if (i < n) {
+                    uint32_t st = (uint32_t)p.start, high = 0;
+#pragma unroll
+                    for (int q = 0; q < NW; q++) { high |= w[u][q]; st = step4(T, st, w[u][q]); }
+                    bool r = result_flag(p, st);
+                    if (OP == 1 && r && p.prefix_mode == 1 && (high & 0x80808080u)) r = recheck_in_with_prefix(p, buf + i * stride, stride);
+                    out[i] = r ? 1 : 0;
+                }
+            }
+        }
+        return;
+    }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gstride) {
         const uint8_t* s = buf + i * stride;
         bool r;
