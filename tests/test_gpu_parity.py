@@ -466,3 +466,50 @@ def test_sparse_start_kernel_fixed_stride(monkeypatch):
                 assert np.array_equal(got, exp), (stride, shift, pat, np.nonzero(got != exp)[0][:10])
                 monkeypatch.setenv("FX_SPARSE", "0")
                 assert np.array_equal(p.in_fixed(buf, n, stride), exp), (stride, shift, pat, "K1")
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_generated_patterns_on_gpu(seed, monkeypatch):
+    """random patterns (the generator of the CPU fuzz) through every batch kernel and the buffer path, against the
+    oracle: whatever kernel the host picks for a pattern -- sparse starts, tile walk, linear spans, emulation, sparse
+    or LUT buffer scan, prefix candidates -- must give the oracle's answer"""
+    import random
+    from tests.test_host_tables import gen_pattern, gen_text
+    monkeypatch.setenv("FX_SPARSE_MAX_FIRST", "128")
+    rng = random.Random(9000 + seed)
+    texts = [gen_text(rng) for _ in range(700)] + [b"", b" ", b"", b"a" * 300, gen_text(rng) * 40]
+    buf, off = pack(texts)
+    stride = 12
+    nfix = len(buf) // stride
+    joined = b"\n".join(texts[:300])
+    jarr = np.frombuffer(joined, dtype=np.uint8)
+    tried = {"in": 0, "match": 0, "regex": 0, "buffer": 0, "sparse": 0, "unsupported": 0}
+    for _ in range(70):
+        pat = gen_pattern(rng).encode()
+        for op in ("in", "match", "regex"):
+            p = fx.Pattern(pat, op)
+            if p.status != 0:
+                continue
+            c = O.Compiled(pat, 1 if op == "match" else 0)
+            if op == "regex":
+                f, t = p.regex_batch(buf, off)
+                ef, et = c.regex_batch(buf, off)
+                assert np.array_equal(f, ef) and np.array_equal(t, et), (pat, np.nonzero((f != ef) | (t != et))[0][:5])
+                tried["regex"] += 1
+                try:
+                    got = p.regex_buffer(jarr)
+                except fx.ForgexError as e:
+                    assert e.status == _lib.FX_ERR_PREFILTER_UNSUPPORTED and p.info()["prefix_scan"] == 0, (pat, e)
+                    tried["unsupported"] += 1
+                else:
+                    assert got == c.regex_buffer(jarr), (pat, "buffer")
+                    tried["buffer"] += 1
+            else:
+                o = 1 if op == "match" else 0
+                got = p.in_batch(buf, off) if op == "in" else p.match_batch(buf, off)
+                assert np.array_equal(got, c.bool_batch(o, buf, off)), (pat, op, np.nonzero(got != c.bool_batch(o, buf, off))[0][:5])
+                gotf = p.in_fixed(buf, nfix, stride) if op == "in" else p.match_fixed(buf, nfix, stride)
+                assert np.array_equal(gotf, c.bool_fixed(o, buf, nfix, stride)), (pat, op, "fixed")
+                tried[op] += 1
+                tried["sparse"] += p.info()["sparse_used"] if op == "in" else 0
+    assert tried["in"] > 30 and tried["regex"] > 30 and tried["buffer"] > 20 and tried["sparse"] > 5, tried
