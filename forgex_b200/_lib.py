@@ -17,7 +17,7 @@ FX_ERR_BAD_ARGUMENT, FX_ERR_NO_DEVICE = 104, 105
 # every symbol include/forgex_b200.h declares (tests check that the library exports them all)
 SYMBOLS = [
     "fx_status_message", "fx_compile", "fx_pattern_free", "fx_pattern_get_info", "fx_pattern_set_residency",
-    "fx_pattern_literals", "fx_pattern_tables", "fx_pattern_span_tables", "fx_is_valid_regex",
+    "fx_pattern_literals", "fx_pattern_tables", "fx_pattern_span_tables", "fx_is_valid_regex", "fx_is_valid_regex_batch",
     "fx_match_fixed_dev", "fx_in_fixed_dev", "fx_match_batch_dev", "fx_in_batch_dev", "fx_regex_batch_dev",
     "fx_regex_buffer_work_bytes", "fx_regex_buffer_dev", "fx_buffer_scan_dev", "fx_buffer_scan_all_dev", "fx_buffer_finish_dev",
     "fx_match_fixed", "fx_in_fixed", "fx_match_batch", "fx_in_batch", "fx_regex_batch", "fx_regex_buffer",
@@ -58,6 +58,7 @@ def lib():
     L.fx_pattern_span_tables.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32 * 4), C.POINTER(vp),
                                          C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32 * 4)]
     L.fx_is_valid_regex.argtypes = [C.c_char_p, i64, C.POINTER(C.c_int)]
+    L.fx_is_valid_regex_batch.argtypes = [vp, vp, i64, vp, vp]
     for name in ("fx_match_fixed_dev", "fx_in_fixed_dev"):
         getattr(L, name).argtypes = [vp, u8p, i64, i64, u8p, vp]
     for name in ("fx_match_batch_dev", "fx_in_batch_dev"):

@@ -240,6 +240,18 @@ def is_valid_regex(pattern):
     return bool(L.lib().fx_is_valid_regex(p, len(p), C.byref(st)))
 
 
+def is_valid_regex_batch(patterns):
+    """is_valid_regex over a list of patterns (elemental in the reference): returns (valid uint8[n], status int32[n])"""
+    pats = [_b(x) for x in patterns]
+    n = len(pats)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in pats], out=off[1:])
+    buf = np.frombuffer(b"".join(pats) + b"\0", dtype=np.uint8)
+    valid, status = np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.int32)
+    _check(L.lib().fx_is_valid_regex_batch(_ptr(buf), _ptr(off), n, _ptr(valid), _ptr(status)), "fx_is_valid_regex_batch")
+    return valid, status
+
+
 def op_in(pattern, text):
     """`pattern .in. text` (src/forgex.F90:74)"""
     p, t = _b(pattern), _b(text)

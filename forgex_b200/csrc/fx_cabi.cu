@@ -77,7 +77,9 @@ struct fx_pattern {
     bool sparse = false;         // the sparse-start kernel (K2c) may serve `.in.` batches
     int last_sparse = 0;
     DeviceTables dev;
-    std::mutex mu;
+    std::mutex mu;               // serialises the host-pointer entry points (they share the grow-only scratch)
+    std::mutex dev_mu;           // serialises the lazy upload of the tables (ensure_device)
+    bool dev_touched = false;    // some allocation may exist even if the upload failed half-way
 };
 
 namespace {
@@ -186,11 +188,14 @@ bool sparse_first_set(const fx::ByteTable& at, FirstSet& fs, bool for_in) {
 }
 
 int ensure_device(fx_pattern* p) {
+    std::lock_guard<std::mutex> lock(p->dev_mu);    // two threads may make the first call on one handle
     DeviceTables& d = p->dev;
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (d.device == dev) return FX_OK;
     if (d.device >= 0) return FX_ERR_BAD_ARGUMENT;  // one device per handle
+    if (p->dev_touched) return FX_ERR_BAD_ARGUMENT; // an earlier upload failed half-way: the handle is unusable
+    p->dev_touched = true;
     const fx::ByteTable& bt = p->prog.bt;
     size_t tb = (bt.table.size() * 2 + 15) & ~(size_t)15, db = (bt.direct.size() * 2 + 15) & ~(size_t)15;
     CUDA_TRY(cudaMalloc(&d.table, tb + 16));
@@ -762,8 +767,19 @@ int launch_scan(fx_pattern* p, const uint8_t* buf, const ScanWindow& W, unsigned
     Plan pl;
     int rc = make_plan(p, pl);
     if (rc) return rc;
-    if (pl.kp.all_active || W.start_lo == W.start_hi) return FX_OK;
+    if (W.start_lo == W.start_hi) return FX_OK;
     p->last_sparse = 0;
+    if (pl.kp.all_active) {          // the pattern is one literal: parallel index() (K4L)
+        SparseParams sp;
+        memset(&sp, 0, sizeof(sp));
+        sp.add_lo[0] = (unsigned char)p->prog.lit.all[0] * 0x01010101u;      // NR = -1 form
+        long long groups = ((W.start_hi - W.start_lo) >> 12) + 1;
+        long long want = (groups + 7) / 8, cap = (long long)p->dev.sm_count * 8;
+        int grid = (int)(want < cap ? want : cap);
+        k_buffer_literal<<<grid < 1 ? 1 : grid, 256, 0, s>>>(pl.kp, sp, buf, W, best);
+        g_launches++;
+        return cuda_status(cudaGetLastError());
+    }
     if (prefixed && mode == SCAN_AUTO) {
         if (pl.kind == 1) return launch_scan_prefix<1>(p, pl, buf, W, best, s);
         if (pl.kind == 2) return launch_scan_prefix<2>(p, pl, buf, W, best, s);
@@ -870,7 +886,7 @@ int fx_compile(const void* pattern, int64_t plen, int op, fx_pattern** out) {
 int fx_pattern_free(fx_pattern* p) {
     if (!p) return FX_OK;
     DeviceTables& d = p->dev;
-    if (d.device >= 0) {
+    if (p->dev_touched) {             // also after an upload that failed half-way (every pointer is null or live)
         cudaFree(d.table); cudaFree(d.direct); cudaFree(d.table8); cudaFree(d.classmap); cudaFree(d.flags); cudaFree(d.lits);
         cudaFree(d.a_table); cudaFree(d.a_classmap); cudaFree(d.a_flags);
         cudaFree(d.sp_table); cudaFree(d.sp_direct); cudaFree(d.sp_classmap); cudaFree(d.sp_flags);
@@ -971,6 +987,23 @@ int fx_is_valid_regex(const void* pattern, int64_t plen, int* status) {  // forg
     return syn.valid() ? 1 : 0;
 }
 
+// is_valid_regex is `pure elemental` in the reference (forgex.F90:58-71): over an array of patterns it answers per
+// element.  Batch form: patterns as a flat buffer + n+1 ascending offsets; valid[i] = 1/0, status[i] = SYNTAX_* code
+// (error_m.F90:12-38).  Host-only, like the reference's (pattern parsing is not part of the matching loop).
+int fx_is_valid_regex_batch(const void* patterns, const int64_t* offsets, int64_t n, uint8_t* valid, int32_t* status) {
+    if (n < 0 || (n > 0 && (!offsets || (!valid && !status)))) return FX_ERR_BAD_ARGUMENT;
+    const char* base = static_cast<const char*>(patterns);
+    for (int64_t i = 0; i < n; i++) {
+        const int64_t a = offsets[i], b = offsets[i + 1];
+        if (a < 0 || b < a || (b > a && !base)) return FX_ERR_BAD_ARGUMENT;
+        fx::Syntax syn;
+        fx::parse_pattern(fx::prepare_pattern(std::string(base ? base + a : "", (size_t)(b - a)), false), syn);
+        if (valid) valid[i] = syn.valid() ? 1 : 0;
+        if (status) status[i] = syn.status;
+    }
+    return FX_OK;
+}
+
 // ---- device-pointer entry points ------------------------------------------------------------
 int fx_match_fixed_dev(fx_pattern* p, const uint8_t* d_buf, int64_t n, int64_t stride, uint8_t* d_out, void* stream) {
     int rc = check_ready(p, FX_OP_MATCH);
@@ -1041,6 +1074,7 @@ static int host_bool_fixed(fx_pattern* p, int op, const uint8_t* buf, int64_t n,
     if (n == 0) return FX_OK;
     std::lock_guard<std::mutex> lock(p->mu);
     DeviceTables& d = p->dev;
+    if (stride > 0 && n > (int64_t)((~(size_t)0 >> 2) / (size_t)stride)) return FX_ERR_BAD_ARGUMENT;   // n * stride overflows
     size_t bytes = (size_t)n * (size_t)stride;
     if ((rc = grow(d.w_buf, d.w_buf_cap, bytes + 64))) return rc;
     if ((rc = grow(d.w_out, d.w_out_cap, (size_t)n))) return rc;
@@ -1066,8 +1100,20 @@ static int host_stage_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* o
     int rc;
     if ((rc = grow(d.w_buf, d.w_buf_cap, (size_t)total + 64))) return rc;
     if ((rc = grow(d.w_off, d.w_off_cap, (size_t)(n + 1) * 8))) return rc;
-    if (total) CUDA_TRY(cudaMemcpyAsync(d.w_buf, buf, (size_t)total, cudaMemcpyHostToDevice, 0));
+    // offsets first: they are checked on the device (ascending, inside [0, total]) while the text is still on its way
     CUDA_TRY(cudaMemcpyAsync(d.w_off, offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, 0));
+    int* d_bad = reinterpret_cast<int*>(d.w_best + 3);
+    CUDA_TRY(cudaMemsetAsync(d_bad, 0, 4, 0));
+    {
+        long long want = (n + 255) / 256, cap = (long long)d.sm_count * 8;
+        k_check_offsets<<<(int)(want < cap ? want : cap), 256, 0, 0>>>(d.w_off, n, total, d_bad);
+        g_launches++;
+    }
+    int bad = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, 0));
+    if (total) CUDA_TRY(cudaMemcpyAsync(d.w_buf, buf, (size_t)total, cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    if (bad) return FX_ERR_BAD_ARGUMENT;      // no kernel has touched the text through these offsets
     return FX_OK;
 }
 static int host_bool_ragged(fx_pattern* p, int op, const uint8_t* buf, const int64_t* offsets, int64_t n, uint8_t* out) {

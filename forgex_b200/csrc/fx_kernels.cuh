@@ -515,6 +515,18 @@ __device__ __forceinline__ uint32_t step4(const Table<KIND>& T, uint32_t st, uin
     return st;
 }
 
+// offsets of a ragged batch as the host handed them over: ascending, first 0, none past `total`?  (*bad != 0 if not.)
+// The host-pointer entry points run this before any kernel reads text through those offsets.
+__global__ void k_check_offsets(const int64_t* __restrict__ off, int64_t n, int64_t total, int* __restrict__ bad) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    bool wrong = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t a = __ldg(off + i), b = __ldg(off + i + 1);
+        wrong |= a > b || a < 0 || b > total;
+    }
+    if (wrong) *bad = 1;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1: fixed-stride batch, boolean result (configs C1 `.match.` 8-byte strings, C5 `.in.` 64-byte)
 // One thread per string; consecutive threads read consecutive strings, so a warp's loads cover a
@@ -1619,7 +1631,10 @@ __global__ void __launch_bounds__(SPAN_WARPS * 32, 2) k_span_ragged(KParams p, S
             int64_t f = 0, e = 0;
             if (r1 == OFF_BEYOND) {          // not staged (longer than a warp's tile): the same two walks, text from global memory
                 const int64_t o0 = __ldg(offsets + first + i), o1 = __ldg(offsets + first + i + 1);
-                if (o1 - o0 < 0x7FFFFFF0ll) {
+                if (o1 - o0 == 0 || (o1 - o0 == 1 && __ldg(buf + o0) == 0x20)) {
+                    // api_internal_m.F90:68-74: empty text or a lone blank never reaches the loop -> (0, 0).  (A short
+                    // string lands here when it follows an over-long one in the same tile: its end is past the staged bytes.)
+                } else if (o1 - o0 < 0x7FFFFFF0ll) {
                     span_linear(sp, T, FetchGlobal{buf + o0}, (int)(o1 - o0), f, e);
                 } else {                     // 2 GiB and more in one string: 64-bit positions, the anchored emulation
                     Table<3> G;
@@ -2017,6 +2032,62 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
     if (sqn > 0) run_starts(sqn);
 }
 
+// K4L: a pattern that is ONE literal (`all` is not blank).  The reference never consults the automaton for it:
+// regex() answers with index(text, all) -- plain bytes, no framing, no decoding (forgex.F90:281-307).  Same sweep as
+// above for the literal's first byte; a hit compares the whole literal; the smallest occurrence wins (64-bit atomicMin,
+// key = S position of its first byte, so that the keys of several windows combine with MIN like any other start).
+// An occurrence that would run past an open window end cannot be decided here: counted in best[1].
+__global__ void __launch_bounds__(256) k_buffer_literal(KParams p, SparseParams sp, const uint8_t* __restrict__ buf, ScanWindow W,
+                                                        unsigned long long* __restrict__ best) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t FULL = 0xffffffffu;
+    const uint8_t* lit = p.lits;
+    const int n = p.all_len;
+    const int64_t len = W.len;
+    const bool open_end = !W.last;
+    const uintptr_t gbuf = reinterpret_cast<uintptr_t>(buf);
+    const uintptr_t ubase = (gbuf + (uintptr_t)W.start_lo) & ~(uintptr_t)31;
+    const int64_t nunits = W.start_hi > W.start_lo ? (int64_t)((gbuf + (uintptr_t)W.start_hi - ubase + 31) >> 5) : 0;
+    const int64_t pos_base = (int64_t)ubase - (int64_t)gbuf;
+    const int64_t gwarp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+    for (int64_t g0 = gwarp * 128; g0 < nunits; g0 += nwarps * 128) {
+        unsigned long long cur = 0;
+        if (lane == 0) cur = *reinterpret_cast<volatile unsigned long long*>(best);
+        cur = __shfl_sync(FULL, cur, 0);
+        if (cur != NO_START && (unsigned long long)(W.origin + pos_base + (g0 << 5)) + 2 > cur) break;   // behind the winner
+        uint4 va[4], vb[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t u = g0 + k * 32 + lane;
+            va[k] = make_uint4(0, 0, 0, 0); vb[k] = va[k];
+            if (u < nunits) {
+                va[k] = ldg_nc_v4(reinterpret_cast<const void*>(ubase + ((uintptr_t)u << 5)));
+                vb[k] = ldg_nc_v4(reinterpret_cast<const void*>(ubase + ((uintptr_t)u << 5) + 16));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t u = g0 + k * 32 + lane;
+            if (u >= nunits) continue;
+            const uint32_t w[8] = {va[k].x, va[k].y, va[k].z, va[k].w, vb[k].x, vb[k].y, vb[k].z, vb[k].w};
+            uint32_t cand = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) cand |= pack_byte_flags(first_mask<-1, false>(sp, w[q])) << (4 * q);
+            const int64_t P = pos_base + (u << 5);
+            if (P < W.start_lo) cand &= 0xFFFFFFFFu << (int)(W.start_lo - P);
+            if (P + 32 > W.start_hi) cand &= (P >= W.start_hi) ? 0u : (0xFFFFFFFFu >> (int)(P + 32 - W.start_hi));
+            while (cand) {                                     // ascending: the first occurrence of the unit ends the loop
+                const int64_t pos = P + __ffs(cand) - 1;
+                cand &= cand - 1;
+                if (pos + n > len) { if (open_end) atomicAdd(best + 1, 1ull); break; }
+                bool eq = true;
+                for (int j = 0; j < n && eq; j++) eq = __ldg(buf + pos + j) == __ldg(lit + j);
+                if (eq) { atomicMin(best, (unsigned long long)(W.origin + pos) + 2); break; }
+            }
+        }
+    }
+}
+
 // second step: longest end for the winning start; also the literal / degenerate cases.  `key` is the winning
 // start as an S position of the whole text; the window must hold the text from that start to the end of its match.
 __global__ void k_buffer_finish(KParams p, const uint8_t* __restrict__ buf, ScanWindow W,
@@ -2026,8 +2097,11 @@ __global__ void k_buffer_finish(KParams p, const uint8_t* __restrict__ buf, Scan
     FetchGlobal fetch{buf};
     const int64_t len = W.len;
     int64_t from = 0, to = 0;
-    if (whole_text && (p.all_active || len == 0 || (len == 1 && fetch(0) == 0x20))) {
-        eval_regex(p, T, fetch, len, from, to);
+    if (p.all_active) {                                      // literal pattern: k_buffer_literal has found its first occurrence
+        const unsigned long long key = *best;
+        if (key != NO_START) { from = (int64_t)key - 1; to = from + p.all_len - 1; }
+    } else if (whole_text && (len == 0 || (len == 1 && fetch(0) == 0x20))) {
+        eval_regex(p, T, fetch, len, from, to);              // api_internal_m.F90:68-74 -> (0, 0)
     } else {
         const unsigned long long key = *best;
         const Anchored A{p.flags, p.start_nul, p.q0};

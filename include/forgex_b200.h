@@ -120,6 +120,10 @@ int fx_pattern_tables(const fx_pattern* p, const uint16_t** table, const uint16_
 int fx_pattern_span_tables(const fx_pattern* p, const uint16_t** direct, const uint8_t** flags, int32_t scalars[4],
                            const uint16_t** rdelta, const uint8_t** rstartok, const int32_t** cuts, int32_t rscalars[4]);
 int fx_is_valid_regex(const void* pattern, int64_t plen, int* status);
+/* is_valid_regex over an array of patterns (it is `pure elemental` in the reference, src/forgex.F90:58-71): patterns as
+ * one flat buffer + n+1 ascending offsets; valid[i] = 1/0, status[i] = the SYNTAX_* code of pattern i
+ * (src/essential/error_m.F90:12-38).  Either output may be NULL.  Host-only. */
+int fx_is_valid_regex_batch(const void* patterns, const int64_t* offsets, int64_t n, uint8_t* valid, int32_t* status);
 
 /* ---- device-pointer entry points (asynchronous on `stream`) ---------------------------- */
 int fx_match_fixed_dev(fx_pattern* p, const uint8_t* d_buf, int64_t n, int64_t stride, uint8_t* d_out, void* stream);

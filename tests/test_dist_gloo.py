@@ -121,7 +121,16 @@ def worker(rank, world, port, cfg, ret):
             lo, hi = fxd.slab_bounds(length, world, rank, align=cfg.get("align", 16))
             w_lo, w_hi = fxd.window_for_slab(length, lo, hi, cfg["halo"])
 
+            win = None
+            if cfg.get("widen"):      # the rank keeps its window as a tensor; a too-short halo grows by P2P reads from the successors
+                win = fxd._GpuWindow(torch.from_numpy(np.frombuffer(text, dtype=np.uint8)[w_lo:w_hi].copy()), w_lo, length,
+                                     rank, world, (lo, hi), None)
+
             def scan(a, b):
+                if win is not None:
+                    held = bytes(win.t.numpy())
+                    assert held == text[w_lo:win.end()]           # what arrived over P2P is the text itself
+                    return model_scan(anch, text, w_lo, win.end(), a, b, length)
                 return model_scan(anch, text, w_lo, w_hi, a, b, length)
 
             def finish(key):
@@ -135,7 +144,10 @@ def worker(rank, world, port, cfg, ret):
                     return model_scan_prefix(anch, pre, text, w_lo, w_hi, a, b, length)
                 ret[rank] = fxd.buffer_search(scan_pre, finish, length, rank, world, (lo, hi), (w_lo, w_hi), scan_all=scan)
             else:
-                ret[rank] = fxd.buffer_search(scan, finish, length, rank, world, (lo, hi), (w_lo, w_hi))
+                stats = {}
+                r = fxd.buffer_search(scan, finish, length, rank, world, (lo, hi), (w_lo, w_hi),
+                                      widen=win.widen if win is not None else None, stats=stats)
+                ret[rank] = r + (stats.get("widenings", 0),) if win is not None else r
     finally:
         dist.destroy_process_group()
 
@@ -193,6 +205,19 @@ def test_short_halo_is_reported():
     text = b"INFO x\n" * 30 + line + b"\n" + b"INFO y\n" * 30
     res = run(2, {"kind": "buffer", "text": text, "pattern": synth.PATTERNS["c4"], "halo": 8, "align": 1})
     assert res[0][2] >= 1   # an attempt ran off rank 0's window: the caller must widen the halo
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_short_halo_is_widened_over_p2p(world):
+    """with a widen callback the undecided attempt is resolved: the halo doubles (bytes sent by the ranks that own them)
+    until the attempt that ran off the window can be decided"""
+    line = synth.C4_MATCH_LINE
+    text = b"INFO x\n" * (30 * (world - 1)) + line + b"\n" + b"INFO y\n" * 30
+    res = run(world, {"kind": "buffer", "text": text, "pattern": synth.PATTERNS["c4"], "halo": 8, "align": 1, "widen": True})
+    exp = O.Compiled(synth.PATTERNS["c4"], 0).regex_buffer(np.frombuffer(text, dtype=np.uint8))
+    assert exp[0] > 0
+    for r in res:
+        assert (r[0], r[1]) == exp and r[2] == 0 and r[3] >= 1
 
 
 @pytest.mark.parametrize("world,case", [(2, 0), (2, 1), (3, 2), (2, 3), (2, 4)])

@@ -150,6 +150,22 @@ def test_reference_status_and_validity_vectors():
     assert not bad, "\n".join(bad[:40])
 
 
+def test_batch_validity_and_status_vectors():
+    """fx_is_valid_regex_batch: all 125 status + 207 validity vectors in ONE call each (is_valid_regex is elemental in
+    the reference, forgex.F90:58-71); element i must equal the single-pattern answer"""
+    err, val = load("error"), load("validate")
+    pats = [bytes.fromhex(v["pattern"]) for v in err + val] + [b"", b"   ", b"a b  "]
+    valid, status = fx.is_valid_regex_batch(pats)
+    assert len(valid) == len(pats)
+    for i, v in enumerate(err):
+        assert status[i] == v["expect"] and valid[i] == (v["expect"] == 0), (v["src"], pats[i])
+    for i, v in enumerate(val):
+        assert bool(valid[len(err) + i]) == v["expect"], (v["src"], pats[len(err) + i])
+    for i, pat in enumerate(pats):
+        assert bool(valid[i]) == fx.is_valid_regex(pat)
+    assert fx.is_valid_regex_batch([])[0].size == 0
+
+
 # ---- generated patterns and texts: product tables vs oracle -------------------------------------
 ATOMS = ["a", "b", "c", "ab", "ba", ".", "\\d", "\\w", "\\s", "\\S", "\\D", "[ab]", "[^a]", "[a-c]", "[^a-cx]", "\\n",
          "^", "$", "x", " ", "é", "あ", "[ぁ-ん]", "[α-ω]", "\\x41", "\\x{3042}", "[\\x00-\\x20]", "\\t", "-", "}",
