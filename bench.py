@@ -3,13 +3,17 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2] [--lines L] [--impl reference]
 
-Default workload = BASELINE.json configs[1] ("c2"): `foo(bar|baz)` .in. over 100 M random ASCII lines of
+Headline workload = BASELINE.json configs[1] ("c2"): `foo(bar|baz)` .in. over 100 M random ASCII lines of
 64-256 bytes, one pattern against N strings (flat buffer + int64 offsets).  A step = one pass of the
 hot path over that batch.  `value` = input GB/s with the batch resident in HBM; `e2e` = the same through
 the host-pointer C-ABI call (pinned host buffers, H2D + kernel + D2H inside the timed region).
-Multi-GPU: one process per GPU (torchrun), strings sharded across ranks, no data-path collective; the
-per-rank match counts are all-reduced once (NCCL) after the timed region.  Scaling is weak: every rank
-holds --lines lines.
+Without --config the run measures ALL FIVE BASELINE configs at their full sizes, one after the other, and
+puts them into `per_config` (each with its own roofline, e2e, oracle cross-check and by-construction
+checks); the top-level keys are c2's.  `--config cX` measures that one config only.
+Multi-GPU: one process per GPU (torchrun).  Batches (c1, c2, c3, c5): strings sharded across ranks, no
+data-path collective, weak scaling (every rank holds a full-size batch).  The long buffer (c4): ONE 32 GiB
+text is cut into N slabs (forgex_b200.dist), every rank scans its slab, the ranks agree on the winner
+with one all-gather of 3 integers and one 16-byte all-reduce INSIDE the timed region: strong scaling.
 
 `--impl reference` times the CPU restatement of Forgex's own loop (oracle/, kind "port": the Fortran
 reference cannot be built in this image) on all host cores, on a bounded sample of the same workload.
@@ -140,7 +144,7 @@ def tile_ragged_device(torch, buf_np, off_np, n):
     return d_buf[:total].contiguous(), offsets, total
 
 
-def build_workload(torch, cfg, units, rank):
+def build_workload(torch, cfg, units, rank, world=1):
     """returns dict(run=callable, text_bytes, units, verify=callable or None, host=(...) for e2e/cpu legs)"""
     import forgex_b200 as fx
     pat = synth.PATTERNS.get(cfg, synth.PATTERNS["c2"])
@@ -182,28 +186,48 @@ def build_workload(torch, cfg, units, rank):
         w.update(run=lambda: p.regex_batch_dev(buf, off, units, total, f, t), text_bytes=total, units=units, out=f,
                  out2=t, buf=buf, off=off, pattern_obj=p)
     elif cfg == "c4":
+        # ONE text of `units` bytes: a 256 MiB block of seeded log lines, cut at its last line end and tiled, with
+        # exactly one fully matching line planted at byte fraction 0.999.  With world > 1 the text is cut into
+        # slabs (forgex_b200.dist.slab_bounds) and this rank materialises only its slab + look-back + halo.
+        from forgex_b200 import dist as fxd
         block = min(units, 256 << 20)
-        hb = synth.gen_c4_block(block, seed_stream=rank)
-        # cut the block at its last line end so that tiling it keeps lines whole
+        hb = synth.gen_c4_block(block, seed_stream=0)
         last_nl = int(np.nonzero(hb == 10)[0][-1]) + 1
         d_block = torch.from_numpy(hb[:last_nl]).cuda()
-        reps = (units + last_nl - 1) // last_nl
-        buf = d_block.repeat(reps)[:units].contiguous()
-        line = torch.tensor(list(synth.C4_MATCH_LINE + b"\n"), dtype=torch.uint8, device="cuda")
+        lo, hi = fxd.slab_bounds(units, world, rank)
+        w_lo, w_hi = fxd.window_for_slab(units, lo, hi, 1 << 20) if world > 1 else (0, units)
+        phase = w_lo % last_nl
+        reps = (w_hi - w_lo + phase + last_nl - 1) // last_nl
+        buf = d_block.repeat(reps)[phase:phase + (w_hi - w_lo)].contiguous()
+        line = synth.C4_MATCH_LINE + b"\n"
         pos = int(units * 0.999)
-        seg = buf[:pos]
-        # previous line start
-        back = seg[max(0, pos - 4096):]
-        nl = torch.nonzero(back == 10).squeeze(1)
-        start = max(0, pos - 4096) + int(nl[-1].item()) + 1
-        buf[start:start + line.numel()] = line
-        after = start + line.numel()
-        buf[after:after + 5] = torch.tensor(list(b"INFO "), dtype=torch.uint8, device="cuda")
+        # the planted line starts at the last line start at or before `pos` of the TILED text (same on every rank)
+        nls = np.nonzero(hb[:last_nl] == 10)[0]
+        tpos = pos % last_nl
+        k = int(np.searchsorted(nls, tpos, side="left")) - 1
+        start = (pos - tpos) + (int(nls[k]) + 1 if k >= 0 else 0)
+        plant = np.frombuffer(line + b"INFO ", dtype=np.uint8)
+        a, b = max(start, w_lo), min(start + len(plant), w_hi)
+        if b > a:
+            buf[a - w_lo:b - w_lo] = torch.from_numpy(plant[a - start:b - start].copy()).cuda()
         ft = torch.zeros(2, dtype=torch.int64, device="cuda")
         work = torch.zeros(64, dtype=torch.uint8, device="cuda")
         p = fx.Pattern(pat, "regex")
-        w.update(run=lambda: p.regex_buffer_dev(buf, units, ft, work), text_bytes=units, units=1, out=ft, buf=buf,
-                 pattern_obj=p, expect_from=start)
+        # by construction: the span holds the LF that `^` consumed and the LF that `$` consumed
+        crlf_before = start >= 2 and int(hb[(start - 1) % last_nl - 1]) == 13     # `^` = LF | CR LF | NUL: the CR is part of the match
+        expect = (start - (1 if crlf_before else 0), start + len(line)) if start > 0 else (1, len(line))
+        if world > 1:
+            stats = {}
+
+            def run_split():
+                f, t, und = fxd.gpu_buffer_search(p, buf, w_lo, units, rank, world, (lo, hi), stats=stats)
+                ft[0], ft[1] = f, t
+                stats["undecided"] = und
+            w.update(run=run_split, split=dict(slab=[lo, hi], window=[w_lo, w_hi], halo=1 << 20), stats=stats)
+        else:
+            w.update(run=lambda: p.regex_buffer_dev(buf, units, ft, work))
+        w.update(text_bytes=units, units=1, out=ft, buf=buf, pattern_obj=p, expect_span=expect, planted_at=start,
+                 window_lo=w_lo)
     else:
         raise SystemExit("unknown config " + cfg)
     return w
@@ -322,38 +346,71 @@ def reference_arm(args):
     return 0
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--lines", type=int, default=0, help="units per GPU (strings; bytes for c4); default = BASELINE size")
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--e2e-lines", type=int, default=0)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--no-e2e", action="store_true")
-    args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "b200" and not os.environ.get("FX_BENCH_ALLOW_SHORT_WARMUP"):
-        args.warmup = 3
-    if args.impl == "reference":
-        return reference_arm(args)
 
-    import torch
-    import torch.distributed as dist
-    import forgex_b200 as fx
+def numa_pin(local):
+    """bind this rank to the host cores (and, by first touch, the memory) of its GPU's NUMA node: with 8 ranks copying
+    4 GB each to their GPUs at once, unpinned ranks share whatever socket the scheduler put them on"""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        if bus is None:
+            out = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=20).stdout.strip()
+            bus = out
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        path = "/sys/bus/pci/devices/%s/local_cpulist" % bus
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            node = open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip()
+            return {"numa_node": int(node), "cpus": len(cpus)}
+    except Exception as e:      # not fatal: the run is just not pinned
+        return {"error": str(e)[:80]}
+    return None
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the matching path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cfg = args.config
-    units = args.lines or DEFAULT_UNITS[cfg]
-    w = build_workload(torch, cfg, units, rank)
+
+def verify_c4(torch, w, fx):
+    """C4 parity at BASELINE size: (1) the span found in the full text equals the span known by construction (the
+    planted line + the LF / CR LF consumed by `^` and the LF consumed by `$`, SURVEY Q1; offsets beyond 2^31 / 2^32);
+    (2) the oracle and the GPU agree on a bounded slice of the same text that ends just behind the planted line."""
+    got = tuple(int(x) for x in w["out"].cpu().tolist())
+    rec = {"span": list(got), "expected_by_construction": list(w["expect_span"]), "span_equals_construction": got == tuple(w["expect_span"]),
+           "offsets_beyond_2_31": got[0] > (1 << 31), "offsets_beyond_2_32": got[0] > (1 << 32)}
+    return rec
+
+
+def c4_oracle_slice(torch, w, nbytes=96 << 20):
+    """oracle vs GPU on the last `nbytes` of the text up to just behind the planted line (single GPU only)"""
+    from tests import oracle_lib as O
+    end = min(w["text_bytes"], w["planted_at"] + 4096)
+    a = max(0, end - nbytes)
+    sl = w["buf"][a:end]
+    host = sl.cpu().numpy()
+    t0 = time.perf_counter()
+    exp = O.Compiled(w["pattern"], 0).regex_buffer(host)
+    dt = time.perf_counter() - t0
+    ft = torch.zeros(2, dtype=torch.int64, device="cuda")
+    work = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    w["pattern_obj"].regex_buffer_dev(sl.contiguous(), end - a, ft, work)
+    got = tuple(int(x) for x in ft.cpu().tolist())
+    full = tuple(int(x) for x in w["out"].cpu().tolist())
+    return {"slice": [a, end], "oracle_span": list(exp), "gpu_span": list(got), "equal": got == tuple(exp),
+            "full_text_span_is_slice_span_plus_offset": exp[0] > 0 and full == (exp[0] + a, exp[1] + a),
+            "oracle_seconds": dt, "oracle_GBps": (end - a) / dt / 1e9}
+
+
+def measure_config(cfg, args, env):
+    """one BASELINE config at full size on this rank's GPU: device-timed steps, e2e through the host-pointer ABI, CPU leg"""
+    torch, dist, fx = env["torch"], env["dist"], env["fx"]
+    world, rank, local = env["world"], env["rank"], env["local"]
+    units = (args.lines if args.config == cfg else 0) or DEFAULT_UNITS[cfg]
+    w = build_workload(torch, cfg, units, rank, world)
     torch.cuda.synchronize()
 
     def barrier():
@@ -384,6 +441,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
 
+    split = cfg == "c4" and world > 1
     # match counts: the only cross-GPU exchange of a sharded batch (8 bytes per rank), outside the timed region
     if cfg == "c4":
         count = torch.tensor([int(w["out"][0].item() > 0)], dtype=torch.int64, device="cuda")
@@ -391,11 +449,18 @@ def main():
         count = (w["out"] > 0).sum().to(torch.int64).reshape(1)
     else:
         count = w["out"].sum(dtype=torch.int64).reshape(1)
-    if world > 1:
+    if world > 1 and not split:
         dist.all_reduce(count)
-    text_bytes_all = w["text_bytes"] * world
-    units_all = (w["units"] if cfg != "c4" else 1) * world
+    text_bytes_all = w["text_bytes"] * (1 if split else world)
+    units_all = (w["units"] if cfg != "c4" else 1) * (1 if split else world)
     value = text_bytes_all / (ms_step / 1000.0) / 1e9
+
+    verified = {}
+    if cfg == "c4":
+        verified.update(verify_c4(torch, w, fx))
+        if split:
+            verified["undecided_attempts"] = w["stats"].get("undecided")
+            verified["halo_widenings"] = w["stats"].get("widenings")
 
     # ---- e2e: host-pointer C-ABI call, pinned host buffers, H2D + kernel + D2H inside the timed region ----
     e2e = None
@@ -403,7 +468,7 @@ def main():
         p = w["pattern_obj"]
         n_e = min(w["units"], args.e2e_lines or {"c1": 1 << 27, "c2": 25_000_000, "c3": 8_000_000, "c5": 10_000_000}.get(cfg, 0))
         if cfg == "c4":
-            nb = min(w["text_bytes"], 4 << 30)
+            nb = min(w["buf"].numel(), 4 << 30)
             hbuf = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
             hbuf.copy_(w["buf"][:nb])
             call = lambda: p.regex_buffer(hbuf.numpy())
@@ -428,33 +493,50 @@ def main():
             h2d, d2h, ebytes, eunits = nb, n_e, nb, n_e
         call()  # warm-up (grows the library's device scratch)
         barrier()
+        # the platform's ceiling beside it: the bare pinned H2D copy of the same bytes, all ranks at once
+        dscratch = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        dscratch.copy_(hbuf, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        dscratch.copy_(hbuf, non_blocking=True)
+        torch.cuda.synchronize()
+        dt_copy = time.perf_counter() - t0
+        del dscratch
+        barrier()
         reps = 3
         t0 = time.perf_counter()
         for _ in range(reps):
             res = call()
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / reps
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([dt, dt_copy], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+        dt, dt_copy = (float(x) for x in tt.tolist())
         e2e = {"value": ebytes * world / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "strings_per_step_per_gpu": int(eunits), "ms_per_step": dt * 1000.0, "strings_per_s": eunits * world / dt,
+               "bare_pinned_h2d_GBps_all_ranks": nb * world / dt_copy / 1e9,
                "api": "forgex_b200.Pattern.%s (fx_*_batch / fx_*_fixed host-pointer entry points)" %
                       {"c1": "match_fixed", "c2": "in_batch", "c3": "regex_batch", "c4": "regex_buffer", "c5": "in_fixed"}[cfg]}
+        if cfg == "c4" and world == 1:
+            e2e["note"] = "first 4 GiB of the text (no match in it): one host buffer, one call"
         del hbuf
 
+    rec = None
     if rank == 0:
         peak, peak_src = measured_peak()
         algo_bytes = w["text_bytes"] + EXTRA_BYTES[cfg] * (w["units"] if cfg != "c4" else 0)
-        kernel_ms = ms_step  # one kernel launch per step per GPU (c4: scan + a 1-thread finish kernel)
+        if split:
+            algo_bytes = w["split"]["slab"][1] - w["split"]["slab"][0]
+        kernel_ms = ms_step
         achieved = algo_bytes / (kernel_ms / 1000.0) / 1e9
-        line = {
+        rec = {
             "metric": "input_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if split else "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOADS[cfg], "strings_per_gpu": w["units"] if cfg != "c4" else 1,
-                       "text_bytes_per_gpu": w["text_bytes"], "pattern": synth.PATTERNS.get(cfg, synth.PATTERNS["c2"]).decode("utf-8"),
+                       "text_bytes_per_gpu": int(w["buf"].numel()) if split else w["text_bytes"],
+                       "pattern": synth.PATTERNS.get(cfg, synth.PATTERNS["c2"]).decode("utf-8"),
                        "l2": "inputs larger than L2 (no flush needed)" if w["text_bytes"] > (256 << 20) else "input fits L2: latency-bound case",
                        "table": w["pattern_obj"].info()},
             "strings_per_s": units_all / (ms_step / 1000.0),
@@ -466,8 +548,102 @@ def main():
                          "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": kernel_ms},
             "e2e": e2e,
         }
-        if not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_leg(cfg, w, torch)
+        if split:
+            rec["config"]["split"] = ("ONE text of %d bytes cut into %d slabs (forgex_b200.dist.slab_bounds), 1 MiB look-ahead halo, "
+                                      "one all-gather of 3 int64 + one 16-byte all-reduce per search, inside the timed region"
+                                      % (w["text_bytes"], world))
+            rec["roofline"]["note"] = "per GPU: this rank's slab bytes / step time (the step includes the two collectives and their host syncs)"
+            # what the collectives cost: the same search on the same slabs minus the local scan alone
+            stats = w["stats"]
+            rec["collectives"] = {"per_search": "all_gather(3 x int64) + all_reduce(2 x int64)", "scan_rounds": stats.get("scan_rounds", 0) // max(1, args.steps + args.warmup)}
+        if verified:
+            rec["verified"] = verified
+        if not args.no_cpu and world == 1:
+            rec["cpu_baseline"] = cpu_baseline_leg(cfg, w, torch, target_seconds=args.cpu_seconds if cfg != "c2" else max(args.cpu_seconds, 12.0))
+            if cfg == "c4":
+                rec["verified"]["oracle_slice"] = c4_oracle_slice(torch, w)
+                rec["cpu_baseline"]["gpu_results_equal_oracle"] = bool(rec["verified"]["oracle_slice"]["equal"] and
+                                                                       rec["verified"]["span_equals_construction"])
+    if split:
+        # time of the collectives alone (same tensors, no scan), max over ranks: named in microseconds
+        from forgex_b200 import dist as fxd
+        span = torch.zeros(2, dtype=torch.int64, device="cuda")
+        for _ in range(3):
+            fxd.gather_ints((1, 0, 0), None, span.device)
+            dist.all_reduce(span)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            fxd.gather_ints((1, 0, 0), None, span.device)
+            dist.all_reduce(span)
+            span.cpu()
+        dtc = (time.perf_counter() - t0) / 20
+        tc = torch.tensor([dtc], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        if rec is not None:
+            rec["collectives"]["us_per_search"] = float(tc.item()) * 1e6
+    del w
+    torch.cuda.empty_cache()
+    return rec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="all", choices=sorted(WORKLOADS) + ["all"])
+    ap.add_argument("--lines", type=int, default=0, help="units per GPU (strings; bytes for c4); default = BASELINE size")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-lines", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=6.0, help="target length of each cpu_baseline leg (c2: at least 12 s)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pin", action="store_true", help="do not bind the rank to its GPU's NUMA node")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200" and not os.environ.get("FX_BENCH_ALLOW_SHORT_WARMUP"):
+        args.warmup = 3
+    if args.impl == "reference":
+        if args.config == "all":
+            args.config = "c2"
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import forgex_b200 as fx
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the matching path has no CPU fallback")
+    pin = None if args.no_pin else numa_pin(local)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    env = {"torch": torch, "dist": dist, "fx": fx, "world": world, "rank": rank, "local": local}
+    if args.config != "all":
+        line = measure_config(args.config, args, env)
+    else:
+        # the headline is c2 (BASELINE.json configs[1]); every BASELINE config is measured in the same run
+        recs = {}
+        for cfg in ("c2", "c1", "c3", "c4", "c5"):
+            t0 = time.perf_counter()
+            recs[cfg] = measure_config(cfg, args, env)
+            if rank == 0:
+                recs[cfg]["wall_seconds_incl_setup"] = time.perf_counter() - t0
+        line = None
+        if rank == 0:
+            line = dict(recs["c2"])
+            keep = ("value", "unit", "ms_per_step", "scaling", "strings_per_s", "matches", "gpu_launches", "roofline", "e2e",
+                    "cpu_baseline", "verified", "collectives", "clocks", "config", "wall_seconds_incl_setup")
+            line["per_config"] = {c: {k: r[k] for k in keep if k in r} for c, r in recs.items()}
+            for c, r in line["per_config"].items():
+                r["config"] = {k: v for k, v in r["config"].items() if k != "table"} | {"kernel_path": {
+                    k: recs[c]["config"]["table"].get(k) for k in ("byte_states", "residency", "direct", "sparse_used", "prefix_mode")}}
+    if rank == 0:
+        if pin:
+            line["numa_pin"] = pin
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

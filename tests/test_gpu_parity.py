@@ -513,3 +513,104 @@ def test_generated_patterns_on_gpu(seed, monkeypatch):
                 tried[op] += 1
                 tried["sparse"] += p.info()["sparse_used"] if op == "in" else 0
     assert tried["in"] > 30 and tried["regex"] > 30 and tried["buffer"] > 20 and tried["sparse"] > 5, tried
+
+
+def test_span_kernel_degenerate_strings_behind_a_long_one():
+    """a "" or " " that shares a tile with an over-long string is not staged (its end lies past the staged bytes) and
+    takes the global-memory walk: the blank-text rule (api_internal_m.F90:68-74) must hold there too"""
+    strings = [b"y" * 70000, b"", b" ", b"a", b" ", b"", b"x" * 40000 + b" ", b" ", b""] + [b" ", b""] * 20
+    buf, off = pack(strings)
+    for pat in [b"^$", rb"\s", b".", b"[ a]", b"a*", b" *", rb"\s*$"]:
+        p = fx.Pattern(pat, "regex")
+        f, t = p.regex_batch(buf, off)
+        ef, et = O.Compiled(pat, 0).regex_batch(buf, off)
+        assert np.array_equal(f, ef) and np.array_equal(t, et), (pat, f[:9], ef[:9], t[:9], et[:9])
+
+
+def test_literal_patterns_on_the_buffer_and_window_paths():
+    """a pattern that is one literal never consults the automaton: regex() = index(text, literal), plain bytes
+    (forgex.F90:281-307).  On the long-buffer path that is a parallel sweep (k_buffer_literal), also over windows."""
+    import torch
+    from forgex_b200 import dist as fxd
+    rng = np.random.default_rng(41)
+    filler = bytes(rng.integers(0x20, 0x7F, size=300000, dtype=np.uint8)).replace(b"ERR", b"E_R").replace(b"fo", b"f0")
+    texts = [filler + b"ERROR" + filler + b"ERROR", b"ERROR", b"ERRO", b"", b" ", filler, b"xERROR", filler[:70001] + b"foo" + filler[:5],
+             b"\xc0\xaf/", b"a{1,7}aaa", b"aaa"]
+    for pat in [b"ERROR", b"foo", b"/", b"a{1,7}", b"[/]", rb"\x41", b"o"]:
+        p = fx.Pattern(pat, "regex")
+        assert p.info()["literal_only"] == 1
+        c = O.Compiled(pat, 0)
+        for text in texts:
+            for shift in (0, 5):
+                arr = np.frombuffer(b"#" * shift + text, dtype=np.uint8)[shift:]
+                assert p.regex_buffer(arr) == c.regex_buffer(np.ascontiguousarray(arr)), (pat, len(text), shift)
+    # windows: two "GPUs", literal in the second slab / across the cut / nowhere
+    p = fx.Pattern(b"ERROR", "regex")
+    c = O.Compiled(b"ERROR", 0)
+    cut_text = filler[:100014] + b"ERROR" + filler[:99984]           # straddles the 2-rank cut at 100016
+    for text in [filler + b"ERROR" + filler[:1000], cut_text, filler, b"ERROR" + filler]:
+        text = np.frombuffer(text, dtype=np.uint8)
+        nbytes = len(text)
+        exp = c.regex_buffer(text)
+        d_text = torch.from_numpy(text.copy()).cuda()
+        for world in (2, 3):
+            keys, und = [], 0
+            for rank in range(world):
+                lo, hi = fxd.slab_bounds(nbytes, world, rank)
+                w_lo, w_hi = fxd.window_for_slab(nbytes, lo, hi, 64)
+                win = d_text[w_lo:w_hi].clone()
+                best = torch.tensor([-1, 0, 0], dtype=torch.int64, device="cuda")
+                p.buffer_scan_dev(win, w_hi - w_lo, lo - w_lo, hi - w_lo, w_lo, w_lo == 0, w_hi == nbytes, best)
+                b = best.cpu().numpy().view(np.uint64)
+                keys.append(int(b[0])); und += int(b[1])
+            assert und == 0
+            key = min(keys)
+            if key == fxd.NO_START:
+                assert exp == (0, 0)
+                continue
+            owner = keys.index(key)
+            lo, hi = fxd.slab_bounds(nbytes, world, owner)
+            w_lo, w_hi = fxd.window_for_slab(nbytes, lo, hi, 64)
+            win = d_text[w_lo:w_hi].clone()
+            ft = torch.zeros(2, dtype=torch.int64, device="cuda")
+            p.buffer_finish_dev(win, w_hi - w_lo, w_lo, w_hi == nbytes, torch.tensor([key], dtype=torch.int64, device="cuda"), ft)
+            assert tuple(ft.cpu().tolist()) == exp, (nbytes, world)
+
+
+def test_c4_buffer_beyond_4_gib():
+    """the reason the long-buffer path is 64-bit: a 4.5 GiB text whose only match starts past offset 2^32.
+    The span is known by construction (planted line + the LF consumed by `^` + the LF consumed by `$`) and is
+    cross-checked against the oracle on the slice that ends behind the planted line."""
+    import torch
+    nbytes = (4 << 30) + (512 << 20)
+    hb = synth.gen_c4_block(64 << 20, seed_stream=3)
+    last_nl = int(np.nonzero(hb == 10)[0][-1]) + 1
+    d_block = torch.from_numpy(hb[:last_nl]).cuda()
+    buf = d_block.repeat((nbytes + last_nl - 1) // last_nl)[:nbytes].contiguous()
+    pos = (1 << 32) + (100 << 20) + 12345
+    nls = np.nonzero(hb[:last_nl] == 10)[0]
+    tpos = pos % last_nl
+    k = int(np.searchsorted(nls, tpos, side="left")) - 1
+    start = (pos - tpos) + int(nls[k]) + 1
+    assert start > (1 << 32)
+    line = synth.C4_MATCH_LINE + b"\n"
+    buf[start:start + len(line) + 5] = torch.from_numpy(np.frombuffer(line + b"INFO ", dtype=np.uint8).copy()).cuda()
+    crlf_before = int(hb[(start - 1) % last_nl - 1]) == 13
+    expect = (start - (1 if crlf_before else 0), start + len(line))
+    p = fx.Pattern(synth.PATTERNS["c4"], "regex")
+    ft = torch.zeros(2, dtype=torch.int64, device="cuda")
+    work = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    p.regex_buffer_dev(buf, nbytes, ft, work)
+    got = tuple(ft.cpu().tolist())
+    assert got == expect and got[0] > (1 << 32), (got, expect)
+    # oracle on the last 24 MiB up to just behind the planted line: same span, shifted
+    a, b = start - (24 << 20), start + 1000
+    sl = buf[a:b].contiguous()
+    exp = O.Compiled(synth.PATTERNS["c4"], 0).regex_buffer(sl.cpu().numpy())
+    assert exp[0] > 0 and (exp[0] + a, exp[1] + a) == got
+    p.regex_buffer_dev(sl, b - a, ft, work)
+    assert tuple(ft.cpu().tolist()) == exp
+    # the same text without the planted line: no match anywhere
+    buf[start:start + 5] = torch.from_numpy(np.frombuffer(b"WARN ", dtype=np.uint8).copy()).cuda()
+    p.regex_buffer_dev(buf, nbytes, ft, work)
+    assert tuple(ft.cpu().tolist()) == (0, 0)
