@@ -211,8 +211,8 @@ def build_workload(torch, cfg, units, rank, world=1):
         if b > a:
             buf[a - w_lo:b - w_lo] = torch.from_numpy(plant[a - start:b - start].copy()).cuda()
         ft = torch.zeros(2, dtype=torch.int64, device="cuda")
-        work = torch.zeros(64, dtype=torch.uint8, device="cuda")
         p = fx.Pattern(pat, "regex")
+        work = torch.zeros(p.buffer_work_bytes(units), dtype=torch.uint8, device="cuda")
         # by construction: the span holds the LF that `^` consumed and the LF that `$` consumed
         crlf_before = start >= 2 and int(hb[(start - 1) % last_nl - 1]) == 13     # `^` = LF | CR LF | NUL: the CR is part of the match
         expect = (start - (1 if crlf_before else 0), start + len(line)) if start > 0 else (1, len(line))
@@ -351,12 +351,8 @@ def numa_pin(local):
     """bind this rank to the host cores (and, by first touch, the memory) of its GPU's NUMA node: with 8 ranks copying
     4 GB each to their GPUs at once, unpinned ranks share whatever socket the scheduler put them on"""
     try:
-        import torch
-        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
-        if bus is None:
-            out = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
-                                 capture_output=True, text=True, timeout=20).stdout.strip()
-            bus = out
+        bus = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip()
         bus = bus.lower()
         if len(bus.split(":")[0]) == 8:
             bus = bus[4:]
@@ -396,7 +392,7 @@ def c4_oracle_slice(torch, w, nbytes=96 << 20):
     exp = O.Compiled(w["pattern"], 0).regex_buffer(host)
     dt = time.perf_counter() - t0
     ft = torch.zeros(2, dtype=torch.int64, device="cuda")
-    work = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    work = torch.zeros(w["pattern_obj"].buffer_work_bytes(end - a), dtype=torch.uint8, device="cuda")
     w["pattern_obj"].regex_buffer_dev(sl.contiguous(), end - a, ft, work)
     got = tuple(int(x) for x in ft.cpu().tolist())
     full = tuple(int(x) for x in w["out"].cpu().tolist())
@@ -481,7 +477,14 @@ def measure_config(cfg, args, env):
             hoff = torch.empty(n_e + 1, dtype=torch.int64, pin_memory=True)
             hoff.copy_(off)
             hb, ho = hbuf.numpy(), hoff.numpy()
-            call = (lambda: p.in_batch(hb, ho)) if cfg == "c2" else (lambda: p.regex_batch(hb, ho))
+            # results land in caller-provided pinned buffers (what a host program that cares about throughput passes)
+            if cfg == "c2":
+                hout = torch.empty(n_e, dtype=torch.uint8, pin_memory=True).numpy()
+                call = lambda: p.in_batch(hb, ho, out=hout)
+            else:
+                hf = torch.empty(n_e, dtype=torch.int64, pin_memory=True).numpy()
+                ht = torch.empty(n_e, dtype=torch.int64, pin_memory=True).numpy()
+                call = lambda: p.regex_batch(hb, ho, out=(hf, ht))
             h2d, d2h, ebytes, eunits = nb + 8 * (n_e + 1), n_e * (1 if cfg == "c2" else 16), nb, n_e
         else:
             nb = n_e * w["stride"]
@@ -489,7 +492,8 @@ def measure_config(cfg, args, env):
             hbuf.copy_(w["buf"][:nb])
             hb = hbuf.numpy()
             fn = p.match_fixed if cfg == "c1" else p.in_fixed
-            call = lambda: fn(hb, n_e, w["stride"])
+            hout = torch.empty(n_e, dtype=torch.uint8, pin_memory=True).numpy()
+            call = lambda: fn(hb, n_e, w["stride"], out=hout)
             h2d, d2h, ebytes, eunits = nb, n_e, nb, n_e
         call()  # warm-up (grows the library's device scratch)
         barrier()

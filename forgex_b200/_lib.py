@@ -31,7 +31,8 @@ class PatternInfo(C.Structure):
         "table_bytes", "direct_bytes", "literal_all_len", "literal_prefix_len", "literal_suffix_len",
         "literal_only", "residency", "direct", "prefix_mode", "sparse", "sparse_ranges")] + [
         ("sparse_lo", C.c_int32 * 4), ("sparse_hi", C.c_int32 * 4), ("sparse_high", C.c_int32),
-        ("sparse_second", C.c_int32), ("sparse_used", C.c_int32), ("prefix_scan", C.c_int32)]
+        ("sparse_second", C.c_int32), ("sparse_used", C.c_int32), ("prefix_scan", C.c_int32), ("statemap", C.c_int32),
+        ("statemap_used", C.c_int32)]
 
 
 _lib = None
@@ -56,7 +57,7 @@ def lib():
     L.fx_pattern_tables.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
                                     C.POINTER(C.c_int32 * 6)]
     L.fx_pattern_span_tables.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32 * 4), C.POINTER(vp),
-                                         C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32 * 4)]
+                                         C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32 * 4)]
     L.fx_is_valid_regex.argtypes = [C.c_char_p, i64, C.POINTER(C.c_int)]
     L.fx_is_valid_regex_batch.argtypes = [vp, vp, i64, vp, vp]
     for name in ("fx_match_fixed_dev", "fx_in_fixed_dev"):

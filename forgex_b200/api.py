@@ -130,57 +130,67 @@ class Pattern:
 
     def span_tables(self):
         """tables of the linear-time span path (None if the pattern has none)"""
-        ptrs = [C.c_void_p() for _ in range(5)]
+        ptrs = [C.c_void_p() for _ in range(6)]
         sc, rsc = (C.c_int32 * 4)(), (C.c_int32 * 4)()
         rc = L.lib().fx_pattern_span_tables(self.h, C.byref(ptrs[0]), C.byref(ptrs[1]), C.byref(sc), C.byref(ptrs[2]),
-                                            C.byref(ptrs[3]), C.byref(ptrs[4]), C.byref(rsc))
+                                            C.byref(ptrs[3]), C.byref(ptrs[4]), C.byref(ptrs[5]), C.byref(rsc))
         if rc == 1:
             return None
         _check(rc, "fx_pattern_span_tables")
 
         def arr(p, n, dt):
             return np.ctypeslib.as_array(C.cast(p, C.POINTER(dt)), shape=(n,)).copy()
-        ns, nr, nc = sc[0], rsc[0], rsc[1]
-        return {"direct": arr(ptrs[0], ns * 256, C.c_uint16).reshape(ns, 256), "flags": arr(ptrs[1], ns, C.c_uint8),
-                "start": sc[1], "rdelta": arr(ptrs[2], nr * nc, C.c_uint16).reshape(nr, nc),
-                "rstartok": arr(ptrs[3], nr, C.c_uint8), "cuts": arr(ptrs[4], nc + 1, C.c_int32), "rstart": rsc[2]}
+        ns, nr, nc, nm = sc[0], rsc[0], rsc[1], rsc[3]
+        return {"direct": arr(ptrs[0], ns * 256, C.c_uint16).reshape(ns, 256), "endinfo": arr(ptrs[1], ns, C.c_uint8),
+                "start": sc[1], "start_acc": bool(sc[2]), "rdelta": arr(ptrs[2], nr * nc, C.c_uint16).reshape(nr, nc),
+                "rpage": arr(ptrs[3], 1024, C.c_uint8) if ptrs[3].value else None,
+                "rmixed": arr(ptrs[4], nm * 64, C.c_uint8) if ptrs[4].value and nm else None,
+                "cuts": arr(ptrs[5], nc + 1, C.c_int32), "rstart": rsc[2]}
 
     # ---- host-buffer batch calls (numpy in, numpy out; copies happen inside the library) ----
-    def _bool_fixed(self, fn, buf, n, stride):
+    # `out=`: caller-provided result arrays (e.g. pinned host memory: the device-to-host copy then runs at PCIe speed)
+    @staticmethod
+    def _out(out, n, dtype):
+        if out is None:
+            return np.empty(n, dtype=dtype)
+        assert out.dtype == dtype and out.size >= n and out.flags["C_CONTIGUOUS"]
+        return out
+
+    def _bool_fixed(self, fn, buf, n, stride, out=None):
         buf = np.ascontiguousarray(buf, dtype=np.uint8)
         assert buf.size >= n * stride
-        out = np.empty(n, dtype=np.uint8)
+        out = self._out(out, n, np.uint8)
         _check(fn(self.h, _ptr(buf), n, stride, _ptr(out)), fn.__name__)
-        return out
+        return out[:n]
 
-    def match_fixed(self, buf, n, stride):
-        return self._bool_fixed(L.lib().fx_match_fixed, buf, n, stride)
+    def match_fixed(self, buf, n, stride, out=None):
+        return self._bool_fixed(L.lib().fx_match_fixed, buf, n, stride, out)
 
-    def in_fixed(self, buf, n, stride):
-        return self._bool_fixed(L.lib().fx_in_fixed, buf, n, stride)
+    def in_fixed(self, buf, n, stride, out=None):
+        return self._bool_fixed(L.lib().fx_in_fixed, buf, n, stride, out)
 
-    def _bool_batch(self, fn, buf, offsets):
+    def _bool_batch(self, fn, buf, offsets, out=None):
         buf = np.ascontiguousarray(buf, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         n = len(offsets) - 1
-        out = np.empty(n, dtype=np.uint8)
+        out = self._out(out, n, np.uint8)
         _check(fn(self.h, _ptr(buf), _ptr(offsets), n, _ptr(out)), fn.__name__)
-        return out
+        return out[:n]
 
-    def match_batch(self, buf, offsets):
-        return self._bool_batch(L.lib().fx_match_batch, buf, offsets)
+    def match_batch(self, buf, offsets, out=None):
+        return self._bool_batch(L.lib().fx_match_batch, buf, offsets, out)
 
-    def in_batch(self, buf, offsets):
-        return self._bool_batch(L.lib().fx_in_batch, buf, offsets)
+    def in_batch(self, buf, offsets, out=None):
+        return self._bool_batch(L.lib().fx_in_batch, buf, offsets, out)
 
-    def regex_batch(self, buf, offsets):
+    def regex_batch(self, buf, offsets, out=None):
         buf = np.ascontiguousarray(buf, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         n = len(offsets) - 1
-        f = np.empty(n, dtype=np.int64)
-        t = np.empty(n, dtype=np.int64)
+        f = self._out(None if out is None else out[0], n, np.int64)
+        t = self._out(None if out is None else out[1], n, np.int64)
         _check(L.lib().fx_regex_batch(self.h, _ptr(buf), _ptr(offsets), n, _ptr(f), _ptr(t)), "fx_regex_batch")
-        return f, t
+        return f[:n], t[:n]
 
     def regex_buffer(self, buf):
         buf = np.ascontiguousarray(buf, dtype=np.uint8)
@@ -214,7 +224,14 @@ class Pattern:
         _check(L.lib().fx_regex_batch_dev(self.h, _ptr(d_buf), _ptr(d_offsets), n, total, _ptr(d_from), _ptr(d_to),
                                           self._stream()), "fx_regex_batch_dev")
 
+    @staticmethod
+    def buffer_work_bytes(length):
+        """size of the device scratch fx_regex_buffer_dev needs for a text of `length` bytes"""
+        return int(L.lib().fx_regex_buffer_work_bytes(length))
+
     def regex_buffer_dev(self, d_buf, length, d_from_to, d_work):
+        assert d_work.numel() * d_work.element_size() >= self.buffer_work_bytes(length), "d_work is too small"
+
         _check(L.lib().fx_regex_buffer_dev(self.h, _ptr(d_buf), length, _ptr(d_from_to), _ptr(d_work),
                                            self._stream()), "fx_regex_buffer_dev")
 

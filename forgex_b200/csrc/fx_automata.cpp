@@ -543,6 +543,27 @@ int build_rev_automaton(const Nfa& nfa, int state_cap, RevAutomaton& r) {
     r.delta = delta;
     r.startok.assign((size_t)r.nstates, 0);
     for (int s = 1; s < r.nstates; s++) r.startok[(size_t)s] = has(sets[(size_t)s], nfa.entry) ? 1 : 0;
+    if (r.nstates > 0x7FFF) return ERR_DFA_STATE_CAP;
+    r.delta16.assign(r.delta.size(), 0);
+    for (size_t i = 0; i < r.delta.size(); i++)
+        r.delta16[i] = (uint16_t)(r.delta[i] | (r.startok[r.delta[i]] ? 0x8000 : 0));
+    // two-level class map of the BMP
+    r.page.clear();
+    r.mixed.clear();
+    if (ncls <= 127) {
+        auto class_of = [&](int cp) { return (int)(std::upper_bound(r.cuts.begin(), r.cuts.end(), cp) - r.cuts.begin()) - 1; };
+        std::vector<uint8_t> page(1024, 0), mixed;
+        bool ok = true;
+        for (int k = 0; k < 1024 && ok; k++) {
+            const int lo = class_of(k << 6), hi = class_of((k << 6) + 63);
+            if (lo == hi) { page[(size_t)k] = (uint8_t)lo; continue; }
+            const size_t idx = mixed.size() / 64;
+            if (idx > 127) { ok = false; break; }
+            page[(size_t)k] = (uint8_t)(0x80 | idx);
+            for (int x = 0; x < 64; x++) mixed.push_back((uint8_t)class_of((k << 6) + x));
+        }
+        if (ok) { r.page.swap(page); r.mixed.swap(mixed); }
+    }
     return OK;
 }
 
@@ -568,11 +589,13 @@ namespace {
 struct InterKey {
     int missing;
     int failacc;
+    int pending = 0;        // span tables: part of the identity when a replay accepts (RA counts back from the breaking byte)
     std::vector<int> tail;  // replay states chain[pending-1 .. total-2]
     std::vector<int> sig;   // (window-relative lo, dst) pairs, run-length form
     bool operator<(const InterKey& o) const {
         if (missing != o.missing) return missing < o.missing;
         if (failacc != o.failacc) return failacc < o.failacc;
+        if (pending != o.pending) return pending < o.pending;
         if (tail != o.tail) return tail < o.tail;
         return sig < o.sig;
     }
@@ -581,6 +604,7 @@ struct InterKey {
 struct ByteBuilder {
     const CpAutomaton& a;
     bool flag_bits;
+    bool span_words = false;
     std::map<InterKey, int> inter_index;
     struct Inter { int origin, total, missing; long long lo; int chain[3]; int failacc; };  // window = [lo, lo + 64^missing)
     std::vector<Inter> inters;
@@ -621,6 +645,7 @@ struct ByteBuilder {
         for (int i = 1; i <= pending; i++)
             if (a.accept[(size_t)chain[i - 1]]) k.failacc |= 1 << (i - 1);
         if (!flag_bits) k.failacc = 0;  // only the span kernels look at the replay marks
+        if (span_words && k.failacc != 0) k.pending = pending;
         for (int i = pending - 1; i <= total - 2; i++) k.tail.push_back(chain[i]);
         k.sig = signature(origin, lo, lo + span - 1);
         if (k.sig.size() == 2 && k.sig[1] == 0 && k.failacc == 0) {
@@ -668,7 +693,7 @@ struct ByteBuilder {
             rows.push_back(row);
         }
         int total_states = a.nstates + (int)inters.size();
-        if (total_states > (flag_bits ? (int)W_STATE : 0xFFFF)) return ERR_DFA_STATE_CAP;
+        if (total_states > (span_words ? (int)W_SSTATE : flag_bits ? (int)W_STATE : 0xFFFF)) return ERR_DFA_STATE_CAP;
         // flags
         flags.assign((size_t)total_states, 0);
         for (int s = 0; s < a.nstates; s++) {
@@ -712,12 +737,34 @@ struct ByteBuilder {
             flags.swap(nflags);
             remap = perm;
         }
-        // byte classes: bytes whose columns agree in every state
-        std::map<std::vector<int>, int> colid;
+        // the words the kernels read: destination id + flag bits (flag-bit tables), + the replay mark RA of a
+        // transition that breaks a multi-byte sequence (span tables)
+        auto ra_of = [&](int s) -> int {       // RA of in-sequence state s: pending - (last replayed byte that accepts) + 1
+            if (!span_words || s < a.nstates) return 0;
+            const Inter& in = inters[(size_t)(s - a.nstates)];
+            const int pending = in.total - in.missing;
+            for (int k = pending; k >= 1; k--)
+                if (in.failacc & (1 << (k - 1))) return pending - k + 1;
+            return 0;
+        };
+        auto word = [&](int src, int b, int dst) -> uint16_t {
+            uint16_t w = (uint16_t)dst;
+            if (!flag_bits) return w;  // boolean kernels only read flags[] at the end of the text
+            uint8_t f = flags[(size_t)dst];
+            if (f & (SF_ACC | SF_MATCHED)) w |= W_ACC;
+            if (f & SF_INTER) w |= W_INTER;
+            if (span_words && (b >> 6) != 2) w |= (uint16_t)(ra_of(src) << W_RA_SHIFT);
+            return w;
+        };
+        std::vector<std::vector<uint16_t> > words((size_t)total_states, std::vector<uint16_t>(256, 0));
+        for (int s = 0; s < total_states; s++)
+            for (int b = 0; b < 256; b++) words[(size_t)s][(size_t)b] = word(s, b, rows[(size_t)s][(size_t)b]);
+        // byte classes: bytes whose columns (of words) agree in every state
+        std::map<std::vector<uint16_t>, int> colid;
         out.nclasses = 0;
         for (int b = 0; b < 256; b++) {
-            std::vector<int> col((size_t)total_states);
-            for (int s = 0; s < total_states; s++) col[(size_t)s] = rows[(size_t)s][(size_t)b];
+            std::vector<uint16_t> col((size_t)total_states);
+            for (int s = 0; s < total_states; s++) col[(size_t)s] = words[(size_t)s][(size_t)b];
             auto it = colid.find(col);
             if (it == colid.end()) { it = colid.emplace(col, out.nclasses++).first; }
             out.classmap[b] = (uint8_t)it->second;
@@ -726,21 +773,23 @@ struct ByteBuilder {
         while ((1 << out.row_shift) < out.nclasses) out.row_shift++;
         out.nstates = total_states;
         out.nboundary = a.nstates;
-        auto word = [&](int dst) -> uint16_t {
-            uint16_t w = (uint16_t)dst;
-            if (!flag_bits) return w;  // boolean kernels only read flags[] at the end of the text
-            uint8_t f = flags[(size_t)dst];
-            if (f & (SF_ACC | SF_MATCHED)) w |= W_ACC;
-            if (f & SF_INTER) w |= W_INTER;
-            return w;
-        };
         out.table.assign((size_t)total_states << out.row_shift, 0);
         for (int s = 0; s < total_states; s++)
             for (int b = 0; b < 256; b++)
-                out.table[((size_t)s << out.row_shift) + out.classmap[b]] = word(rows[(size_t)s][(size_t)b]);
+                out.table[((size_t)s << out.row_shift) + out.classmap[b]] = words[(size_t)s][(size_t)b];
         out.direct.assign((size_t)total_states * 256, 0);
         for (int s = 0; s < total_states; s++)
-            for (int b = 0; b < 256; b++) out.direct[(size_t)s * 256 + (size_t)b] = word(rows[(size_t)s][(size_t)b]);
+            for (int b = 0; b < 256; b++) out.direct[(size_t)s * 256 + (size_t)b] = words[(size_t)s][(size_t)b];
+        out.span_words = span_words;
+        out.endinfo.clear();
+        if (span_words) {
+            out.endinfo.assign((size_t)total_states, 0);
+            for (int s = 0; s < total_states; s++) {
+                uint8_t e = (uint8_t)ra_of(s);
+                if (flags[(size_t)s] & SF_END) e |= EI_NUL;
+                out.endinfo[(size_t)s] = e;
+            }
+        }
         out.direct8.clear();
         if (!flag_bits && total_states <= 255) {
             out.direct8.assign((size_t)total_states * 256, 0);
@@ -758,8 +807,9 @@ struct ByteBuilder {
 
 }  // namespace
 
-int build_byte_table(const CpAutomaton& a, bool flag_bits, ByteTable& out) {
+int build_byte_table(const CpAutomaton& a, bool flag_bits, ByteTable& out, bool span_words) {
     ByteBuilder bb(a, flag_bits);
+    bb.span_words = span_words;
     return bb.build(out);
 }
 
@@ -786,7 +836,7 @@ int compile_program(const std::string& pattern, int op, int state_cap, Program& 
     if (rc != OK) { p.status = rc; return rc; }
     if (want_span && op == MODE_REGEX && !p.literal_only && !p.prefix_active) {
         // linear-time span path; silently absent when a cap is exceeded (the anchored tables above still serve)
-        if (build_span_forward(nfa, state_cap, p.span_cp) == OK && build_byte_table(p.span_cp, true, p.span_bt) == OK &&
+        if (build_span_forward(nfa, state_cap, p.span_cp) == OK && build_byte_table(p.span_cp, true, p.span_bt, true) == OK &&
             build_rev_automaton(nfa, 0xFFFF, p.rev) == OK)
             p.has_span = true;
     }

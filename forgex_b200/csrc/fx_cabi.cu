@@ -2,6 +2,7 @@
 // Product code; never links oracle/.  No CPU fallback: every matching entry point needs a CUDA device.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -25,6 +26,9 @@ constexpr int STATE_CAP = 16383;                 // Forgex's own ceiling (lazy_d
 constexpr int SPARSE_STATE_CAP = 2048;           // optional anchored automaton of a prefix-less `.in.` pattern
 constexpr int DIRECT_LIMIT_BYTES = 40 * 1024;    // 256-column table kept in shared memory up to this size
 constexpr int SMEM_TABLE_LIMIT_BYTES = 160 * 1024;
+constexpr int SPAN_DIRECT_MAX_STATES = 127;      // span forward table as padded 256-column rows in shared memory (<= 64 KB)
+constexpr int SPAN_CLASSED_SMEM_BYTES = 96 * 1024;
+constexpr int SPAN_REV_SMEM_BYTES = 24 * 1024;
 
 struct DeviceTables {
     int device = -1;
@@ -40,8 +44,10 @@ struct DeviceTables {
     uint8_t* a_flags = nullptr;
     // linear-time span path (FX_OP_REGEX, when the pattern has one)
     uint16_t* sp_table = nullptr; uint16_t* sp_direct = nullptr;
-    uint8_t* sp_classmap = nullptr; uint8_t* sp_flags = nullptr;
-    uint16_t* r_delta = nullptr; uint8_t* r_startok = nullptr; int32_t* r_cuts = nullptr; uint8_t* r_ascii = nullptr;
+    uint8_t* sp_classmap = nullptr; uint8_t* sp_endinfo = nullptr;
+    uint16_t* r_delta = nullptr; int32_t* r_cuts = nullptr; uint8_t* r_page = nullptr; uint8_t* r_mixed = nullptr;
+    uint16_t* sm_reach = nullptr; uint16_t* sm_img = nullptr;
+    uint8_t* w_work = nullptr; size_t w_work_cap = 0;
     // grow-only scratch for the host-pointer entry points
     uint8_t* w_buf = nullptr; size_t w_buf_cap = 0;
     int64_t* w_off = nullptr; size_t w_off_cap = 0;
@@ -73,6 +79,11 @@ struct fx_pattern {
     bool has_anchored = false;
     int prefix_mode = 0;         // see KParams::prefix_mode
     bool prefix_scan = false;    // FX_OP_REGEX: the long-buffer path can take the prefix literal's occurrences as its candidates
+    // long-buffer state-map scan (K5): reachable live states of the span forward automaton and, per byte value, the
+    // image of ALL of them under that byte (count, then up to SM_M states; 0xFFFF = wider)
+    std::vector<uint16_t> sm_reach, sm_img;
+    bool statemap = false;
+    int last_statemap = 0;       // 1: the last fx_regex_buffer* call was answered by the state-map scan
     FirstSet first;              // bytes that survive the first step out of q0 of the anchored automaton
     bool sparse = false;         // the sparse-start kernel (K2c) may serve `.in.` batches
     int last_sparse = 0;
@@ -232,28 +243,33 @@ int ensure_device(fx_pattern* p) {
         CUDA_TRY(cudaMalloc(&d.sp_table, st.table.size() * 2 + 32));
         CUDA_TRY(cudaMemset(d.sp_table, 0, st.table.size() * 2 + 32));
         CUDA_TRY(cudaMemcpy(d.sp_table, st.table.data(), st.table.size() * 2, cudaMemcpyHostToDevice));
-        if ((int)st.direct.size() * 2 <= DIRECT_LIMIT_BYTES) {
+        if (st.nstates <= SPAN_DIRECT_MAX_STATES) {
             CUDA_TRY(cudaMalloc(&d.sp_direct, st.direct.size() * 2 + 32));
-            CUDA_TRY(cudaMemset(d.sp_direct, 0, st.direct.size() * 2 + 32));
             CUDA_TRY(cudaMemcpy(d.sp_direct, st.direct.data(), st.direct.size() * 2, cudaMemcpyHostToDevice));
         }
         CUDA_TRY(cudaMalloc(&d.sp_classmap, 256));
         CUDA_TRY(cudaMemcpy(d.sp_classmap, st.classmap, 256, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMalloc(&d.sp_flags, st.flags.size() + 16));
-        CUDA_TRY(cudaMemcpy(d.sp_flags, st.flags.data(), st.flags.size(), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMalloc(&d.r_delta, rv.delta.size() * 2 + 16));
-        CUDA_TRY(cudaMemcpy(d.r_delta, rv.delta.data(), rv.delta.size() * 2, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMalloc(&d.r_startok, rv.startok.size() + 16));
-        CUDA_TRY(cudaMemcpy(d.r_startok, rv.startok.data(), rv.startok.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&d.sp_endinfo, st.endinfo.size() + 16));
+        CUDA_TRY(cudaMemcpy(d.sp_endinfo, st.endinfo.data(), st.endinfo.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&d.r_delta, rv.delta16.size() * 2 + 16));
+        CUDA_TRY(cudaMemcpy(d.r_delta, rv.delta16.data(), rv.delta16.size() * 2, cudaMemcpyHostToDevice));
         std::vector<int32_t> cuts(rv.cuts.begin(), rv.cuts.end());
         CUDA_TRY(cudaMalloc(&d.r_cuts, cuts.size() * 4 + 16));
         CUDA_TRY(cudaMemcpy(d.r_cuts, cuts.data(), cuts.size() * 4, cudaMemcpyHostToDevice));
-        uint8_t ascii[128];
-        for (int c = 0; c < 128; c++) ascii[c] = (uint8_t)p->prog.span_cp.class_of(c);
-        CUDA_TRY(cudaMalloc(&d.r_ascii, 128));
-        CUDA_TRY(cudaMemcpy(d.r_ascii, ascii, 128, cudaMemcpyHostToDevice));
+        if (!rv.page.empty()) {
+            CUDA_TRY(cudaMalloc(&d.r_page, rv.page.size()));
+            CUDA_TRY(cudaMemcpy(d.r_page, rv.page.data(), rv.page.size(), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMalloc(&d.r_mixed, rv.mixed.size() + 64));
+            if (!rv.mixed.empty()) CUDA_TRY(cudaMemcpy(d.r_mixed, rv.mixed.data(), rv.mixed.size(), cudaMemcpyHostToDevice));
+        }
     }
-    CUDA_TRY(cudaMalloc(&d.w_best, 32));
+    if (p->statemap) {
+        CUDA_TRY(cudaMalloc(&d.sm_reach, p->sm_reach.size() * 2 + 16));
+        CUDA_TRY(cudaMemcpy(d.sm_reach, p->sm_reach.data(), p->sm_reach.size() * 2, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&d.sm_img, p->sm_img.size() * 2 + 16));
+        CUDA_TRY(cudaMemcpy(d.sm_img, p->sm_img.data(), p->sm_img.size() * 2, cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(cudaMalloc(&d.w_best, 64));
     CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
     d.device = dev;
     return FX_OK;
@@ -280,7 +296,7 @@ int make_plan(fx_pattern* p, Plan& pl) {
     else if (direct16_ok) pl.kind = 1;
     else if (classed_smem_ok) pl.kind = 2;
     else pl.kind = 3;
-    pl.table_bytes = pl.kind == 0 ? bt.nstates * 256 : pl.kind == 1 ? direct_bytes : pl.kind == 2 ? classed_bytes : 0;
+    pl.table_bytes = pl.kind == 0 ? bt.nstates * ROW8 : pl.kind == 1 ? direct_bytes : pl.kind == 2 ? classed_bytes : 0;
     KParams& k = pl.kp;
     k.table = pl.kind == 1 ? d.direct : d.table;
     k.table8 = d.table8;
@@ -616,29 +632,44 @@ int launch_regex_ragged_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, con
     return cuda_status(cudaGetLastError());
 }
 
-template <int KIND>
-int launch_span_t(fx_pattern* p, const Plan& pl, const SpanParams& sp, int table_bytes, const uint8_t* buf,
+// fills the parameter block of the linear-time span path (K3f, and the long-buffer state-map scan)
+void fill_span_params(fx_pattern* p, SpanParams& sp) {
+    const fx::ByteTable& st = p->prog.span_bt;
+    const fx::RevAutomaton& rv = p->prog.rev;
+    const DeviceTables& d = p->dev;
+    sp.direct = d.sp_direct; sp.table = d.sp_table; sp.classmap = d.sp_classmap; sp.endinfo = d.sp_endinfo;
+    sp.nstates = st.nstates; sp.row_shift = st.row_shift; sp.start = st.start;
+    sp.start_acc = (st.flags[(size_t)st.start] & fxk::SF_ACC) ? 1 : 0;
+    sp.rdelta = d.r_delta; sp.rpage = d.r_page; sp.rmixed = d.r_mixed; sp.cuts = d.r_cuts;
+    sp.rstates = rv.nstates; sp.rclasses = rv.nclasses; sp.rstart = rv.start;
+    sp.nul_class = p->prog.span_cp.class_of(0);
+    sp.ffff_class = p->prog.span_cp.class_of(0xFFFF);
+    sp.nmixed = (int)(rv.mixed.size() / 64);
+}
+
+template <int FK, bool RS>
+int launch_span_t(fx_pattern* p, const Plan& pl, const SpanParams& sp, int fwd_bytes, const uint8_t* buf,
                   const int64_t* off, int64_t n, int64_t total, int64_t* from, int64_t* to, cudaStream_t s) {
-    auto kern = k_span_ragged<KIND>;
-    // every warp stages its own tile; SPAN_WARPS warp regions + the table fill half an SM's shared memory (2 CTAs/SM)
+    auto kern = k_span_ragged<FK, RS>;
+    // one CTA of SPAN_WARPS warps per SM; every warp stages its own tiles: the tables take their share of the SM's
+    // shared memory once, the rest is divided among the warps
     int64_t avg = n > 0 ? (total + n - 1) / n : 1;
     if (avg < 1) avg = 1;
-    const int table_smem = KIND == 3 ? 0 : (table_bytes + 15) & ~15;
-    const int head = span_shared_head(table_smem);
-    int per_warp = (((227 * 1024) / 2 - 1024 - head) / SPAN_WARPS) & ~127;
-    if (per_warp < 1024) per_warp = 1024;
+    const SpanHead H = span_head(fwd_bytes, sp.rstates * sp.rclasses * 2, sp.nmixed, RS);
+    int per_warp = ((227 * 1024 - 1024 - H.bytes) / SPAN_WARPS) & ~127;
+    if (per_warp < 1024) return FX_ERR_BAD_ARGUMENT;
     int cap = per_warp, spt = 1;
     for (;;) {
-        int64_t want = ((int64_t)cap * 4 / 5) / avg;       // expect the tile to fill ~80 % of the staged capacity
-        if (want >= 32) want = (want / 32) * 32;           // whole passes of 32 lanes
-        spt = (int)(want < 1 ? 1 : want > 256 ? 256 : want);
+        int64_t want = ((int64_t)cap * 7 / 8) / avg;       // expect the tile to fill most of the staged capacity
+        spt = (int)(want < 1 ? 1 : want > 512 ? 512 : want);
         if (cap <= 512 || span_layout(spt, cap).warp_bytes <= per_warp) break;
         cap -= 128;
     }
     spt = env_int("FX_TILE_STRINGS", spt);
-    if (spt > 256) spt = 256;
+    if (spt > 512) spt = 512;
+    while (spt > 1 && span_layout(spt, cap).warp_bytes > per_warp) spt--;
     const int64_t ntiles = (n + spt - 1) / spt;
-    const size_t smem = (size_t)head + (size_t)SPAN_WARPS * (size_t)span_layout(spt, cap).warp_bytes;
+    const size_t smem = (size_t)H.bytes + (size_t)SPAN_WARPS * (size_t)span_layout(spt, cap).warp_bytes;
     int bps = 0;
     int rc = occupancy_grid(kern, SPAN_WARPS * 32, smem, p->dev.sm_count, bps);
     if (rc) return rc;
@@ -646,7 +677,7 @@ int launch_span_t(fx_pattern* p, const Plan& pl, const SpanParams& sp, int table
     long long want = (ntiles + SPAN_WARPS - 1) / SPAN_WARPS;
     int grid = (int)(want < capg ? want : capg);
     if (grid < 1) grid = 1;
-    kern<<<grid, SPAN_WARPS * 32, smem, s>>>(pl.kp, sp, buf, off, n, total, from, to, spt, cap, ntiles, table_smem);
+    kern<<<grid, SPAN_WARPS * 32, smem, s>>>(pl.kp, sp, buf, off, n, total, from, to, spt, cap, ntiles, fwd_bytes);
     g_launches++;
     return cuda_status(cudaGetLastError());
 }
@@ -661,25 +692,20 @@ int launch_regex_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, i
     if (p->prog.has_span && env_int("FX_SPAN_LINEAR", 1)) {       // linear-time span path (K3f)
         const fx::ByteTable& st = p->prog.span_bt;
         const fx::RevAutomaton& rv = p->prog.rev;
-        const DeviceTables& d = p->dev;
         SpanParams sp;
-        int classed_bytes = (int)st.table.size() * 2, direct_bytes = (int)st.direct.size() * 2;
-        int kind = p->residency == FX_TABLE_GLOBAL ? 3 : d.sp_direct ? 1 : classed_bytes <= SMEM_TABLE_LIMIT_BYTES ? 2 : 3;
-        sp.table = kind == 1 ? d.sp_direct : d.sp_table;
-        sp.classmap = d.sp_classmap;
-        sp.flags = d.sp_flags;
-        sp.table_words = (kind == 1 ? direct_bytes : classed_bytes) / 2;
-        sp.nstates = st.nstates;
-        sp.row_shift = kind == 1 ? 8 : st.row_shift;
-        sp.start = st.start;
-        sp.rdelta = d.r_delta; sp.rstartok = d.r_startok; sp.cuts = d.r_cuts; sp.ascii_class = d.r_ascii;
-        sp.rclasses = rv.nclasses; sp.rstart = rv.start;
-        sp.nul_class = p->prog.span_cp.class_of(0);
-        sp.ffff_class = p->prog.span_cp.class_of(0xFFFF);
-        int tb = kind == 1 ? direct_bytes : classed_bytes;
-        if (kind == 1) return launch_span_t<1>(p, pl, sp, tb, buf, off, n, total, from, to, s);
-        if (kind == 2) return launch_span_t<2>(p, pl, sp, tb, buf, off, n, total, from, to, s);
-        return launch_span_t<3>(p, pl, sp, tb, buf, off, n, total, from, to, s);
+        fill_span_params(p, sp);
+        const int classed_bytes = (int)st.table.size() * 2;
+        int fk = p->residency == FX_TABLE_GLOBAL ? 2 : p->dev.sp_direct ? 0 : classed_bytes <= SPAN_CLASSED_SMEM_BYTES ? 1 : 2;
+        fk = env_int("FX_SPAN_FK", fk);
+        if (fk == 0 && !p->dev.sp_direct) fk = 1;
+        const int fwd_bytes = fk == 0 ? st.nstates * SPAN_ROW * 2 : fk == 1 ? classed_bytes : 0;
+        const bool rs = !rv.page.empty() && (int)(rv.delta16.size() * 2 + 1024 + rv.mixed.size()) <= SPAN_REV_SMEM_BYTES;
+        if (fk == 0) return rs ? launch_span_t<0, true>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s)
+                               : launch_span_t<0, false>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
+        if (fk == 1) return rs ? launch_span_t<1, true>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s)
+                               : launch_span_t<1, false>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
+        return rs ? launch_span_t<2, true>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s)
+                  : launch_span_t<2, false>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
     }
     if (pl.kind == 1) return launch_regex_ragged_t<1>(p, pl, buf, off, n, total, from, to, s);
     if (pl.kind == 2) return launch_regex_ragged_t<2>(p, pl, buf, off, n, total, from, to, s);
@@ -688,7 +714,7 @@ int launch_regex_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, i
 
 template <int KIND>
 int launch_scan_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const ScanWindow& W, unsigned long long* best,
-                  cudaStream_t s, const unsigned long long* gate) {
+                  cudaStream_t s, const unsigned long long* gate, const unsigned long long* run_if) {
     auto kern = k_buffer_scan<KIND>;
     int table_smem = (int)staged_bytes(pl);
     size_t smem = (size_t)scan_smem_bytes(table_smem);
@@ -700,14 +726,15 @@ int launch_scan_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const ScanW
     long long cap = (long long)p->dev.sm_count * bps;
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    kern<<<grid, 256, smem, s>>>(pl.kp, buf, W, best, table_smem, gate);
+    kern<<<grid, 256, smem, s>>>(pl.kp, buf, W, best, table_smem, gate, run_if);
     g_launches++;
     return cuda_status(cudaGetLastError());
 }
 
 template <int KIND, int NR, bool HIGH, bool PREFIX>
 int launch_scan_sparse_t(fx_pattern* p, const Plan& pl, const SparseParams& sp, const uint8_t* buf, const ScanWindow& W,
-                         unsigned long long* best, cudaStream_t s, const unsigned long long* gate) {
+                         unsigned long long* best, cudaStream_t s, const unsigned long long* gate,
+                         const unsigned long long* run_if = nullptr, ScanBudget budget = ScanBudget{nullptr, nullptr, 0ull}) {
     auto kern = k_buffer_scan_sparse<KIND, NR, HIGH, PREFIX>;
     int table_smem = (int)staged_bytes(pl);
     size_t smem = (size_t)scan_sparse_smem_bytes(table_smem);
@@ -719,26 +746,26 @@ int launch_scan_sparse_t(fx_pattern* p, const Plan& pl, const SparseParams& sp, 
     long long cap = (long long)p->dev.sm_count * bps;
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    kern<<<grid, 256, smem, s>>>(pl.kp, sp, buf, W, best, table_smem, gate);
+    kern<<<grid, 256, smem, s>>>(pl.kp, sp, buf, W, best, table_smem, gate, env_int("FX_K4_PHASES", 3), run_if, budget);
     g_launches++;
     return cuda_status(cudaGetLastError());
 }
 
 template <int KIND>
 int launch_scan_sparse(fx_pattern* p, const Plan& pl, const uint8_t* buf, const ScanWindow& W, unsigned long long* best,
-                       cudaStream_t s, const unsigned long long* gate) {
+                       cudaStream_t s, const unsigned long long* gate, const unsigned long long* run_if, ScanBudget bg) {
     SparseParams sp;
     memset(&sp, 0, sizeof(sp));
     fill_sweep(p->first, sp);
     const FirstSet& f = p->first;
     const bool one = f.sweep_nr == 1 && f.sweep_lo[0] == f.sweep_hi[0];
-    if (f.sweep_nr == 0) return launch_scan_sparse_t<KIND, 0, true, false>(p, pl, sp, buf, W, best, s, gate);
-    if (one) return f.high ? launch_scan_sparse_t<KIND, -1, true, false>(p, pl, sp, buf, W, best, s, gate)
-                           : launch_scan_sparse_t<KIND, -1, false, false>(p, pl, sp, buf, W, best, s, gate);
-    if (f.sweep_nr == 1) return f.high ? launch_scan_sparse_t<KIND, 1, true, false>(p, pl, sp, buf, W, best, s, gate)
-                                       : launch_scan_sparse_t<KIND, 1, false, false>(p, pl, sp, buf, W, best, s, gate);
-    return f.high ? launch_scan_sparse_t<KIND, 2, true, false>(p, pl, sp, buf, W, best, s, gate)
-                  : launch_scan_sparse_t<KIND, 2, false, false>(p, pl, sp, buf, W, best, s, gate);
+    if (f.sweep_nr == 0) return launch_scan_sparse_t<KIND, 0, true, false>(p, pl, sp, buf, W, best, s, gate, run_if, bg);
+    if (one) return f.high ? launch_scan_sparse_t<KIND, -1, true, false>(p, pl, sp, buf, W, best, s, gate, run_if, bg)
+                           : launch_scan_sparse_t<KIND, -1, false, false>(p, pl, sp, buf, W, best, s, gate, run_if, bg);
+    if (f.sweep_nr == 1) return f.high ? launch_scan_sparse_t<KIND, 1, true, false>(p, pl, sp, buf, W, best, s, gate, run_if, bg)
+                                       : launch_scan_sparse_t<KIND, 1, false, false>(p, pl, sp, buf, W, best, s, gate, run_if, bg);
+    return f.high ? launch_scan_sparse_t<KIND, 2, true, false>(p, pl, sp, buf, W, best, s, gate, run_if, bg)
+                  : launch_scan_sparse_t<KIND, 2, false, false>(p, pl, sp, buf, W, best, s, gate, run_if, bg);
 }
 
 // candidates = the occurrences of the prefix literal: sweep for its first byte
@@ -759,7 +786,8 @@ int launch_scan_prefix(fx_pattern* p, const Plan& pl, const uint8_t* buf, const 
 //                    nowhere in the text); `gate`, if given, cancels the launch when *gate != 0
 enum { SCAN_AUTO = 0, SCAN_ALL = 1 };
 int launch_scan(fx_pattern* p, const uint8_t* buf, const ScanWindow& W, unsigned long long* best, cudaStream_t s,
-                int mode = SCAN_AUTO, const unsigned long long* gate = nullptr) {
+                int mode = SCAN_AUTO, const unsigned long long* gate = nullptr, const unsigned long long* run_if = nullptr,
+                ScanBudget bg = ScanBudget{nullptr, nullptr, 0ull}) {
     if (W.len < 0 || W.start_lo < 0 || W.start_hi > W.len || W.start_lo > W.start_hi) return FX_ERR_BAD_ARGUMENT;
     const bool prefixed = p->prog.prefix_active && !p->prog.literal_only;
     // a prefix whose occurrences can overlap, or a non-empty suffix, make the candidate list sequential: not handled
@@ -787,33 +815,133 @@ int launch_scan(fx_pattern* p, const uint8_t* buf, const ScanWindow& W, unsigned
     }
     if (p->sparse && p->first.sweep_nr <= 2 && env_int("FX_SPARSE", 1)) {     // SWAR first-byte filter
         p->last_sparse = 1;
-        if (pl.kind == 1) return launch_scan_sparse<1>(p, pl, buf, W, best, s, gate);
-        if (pl.kind == 2) return launch_scan_sparse<2>(p, pl, buf, W, best, s, gate);
-        return launch_scan_sparse<3>(p, pl, buf, W, best, s, gate);
+        if (pl.kind == 1) return launch_scan_sparse<1>(p, pl, buf, W, best, s, gate, run_if, bg);
+        if (pl.kind == 2) return launch_scan_sparse<2>(p, pl, buf, W, best, s, gate, run_if, bg);
+        return launch_scan_sparse<3>(p, pl, buf, W, best, s, gate, run_if, bg);
     }
-    if (pl.kind == 1) return launch_scan_t<1>(p, pl, buf, W, best, s, gate);
-    if (pl.kind == 2) return launch_scan_t<2>(p, pl, buf, W, best, s, gate);
-    return launch_scan_t<3>(p, pl, buf, W, best, s, gate);
+    if (pl.kind == 1) return launch_scan_t<1>(p, pl, buf, W, best, s, gate, run_if);
+    if (pl.kind == 2) return launch_scan_t<2>(p, pl, buf, W, best, s, gate, run_if);
+    return launch_scan_t<3>(p, pl, buf, W, best, s, gate, run_if);
 }
 
 int launch_finish(fx_pattern* p, const uint8_t* buf, const ScanWindow& W, const unsigned long long* best,
-                  int64_t* from_to, int whole_text, cudaStream_t s) {
+                  int64_t* from_to, int whole_text, cudaStream_t s, const unsigned long long* done = nullptr,
+                  const unsigned long long* use_alt = nullptr, const unsigned long long* best_alt = nullptr) {
     Plan pl;
     int rc = make_plan(p, pl);
     if (rc) return rc;
-    k_buffer_finish<<<1, 1, 0, s>>>(pl.kp, buf, W, best, from_to, whole_text);
+    k_buffer_finish<<<1, 1, 0, s>>>(pl.kp, buf, W, best, from_to, whole_text, done, use_alt, best_alt);
     g_launches++;
     return cuda_status(cudaGetLastError());
 }
 
-int launch_buffer(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* from_to, unsigned long long* best,
+// ---- the long-buffer search: work area layout (64-bit words) -----------------------------------------------
+//   [0] smallest winning start (key), [1] undecided attempts, [2] prefix occurrences      -- K4, first run
+//   [4] 1 = K4 spent its work budget (or was not tried): the state-map scan runs           [5] K4's step counter
+//   [6] state-map scan: end of the match, [7] its status (1 = declined)
+//   [8] 1 = the state-map scan has written the answer        [9] 1 = it declined: K4 runs again, without a budget
+//   [12..14] key / undecided / occurrences of that second run
+//   from byte 4096: the region maps of the state-map scan (rc, re: 32 x u16 per region; rl: 32 x i64 per region)
+constexpr size_t WORK_HEAD = 4096;
+constexpr int64_t SM_SEG = 32 * (int64_t)SM_SUB;                // one segment: 32 lanes x SM_SUB bytes
+inline int64_t statemap_max_regions(int64_t len) {
+    int64_t r = len / SM_SEG + 2;
+    return r > 65536 ? 65536 : r;
+}
+inline size_t buffer_work_bytes(int64_t len) { return WORK_HEAD + (size_t)statemap_max_regions(len < 0 ? 0 : len) * 32 * 12 + 256; }
+
+template <int FK>
+int launch_statemap_t(fx_pattern* p, const SpanParams& sp, StateMapParams mp, int fwd_bytes, const uint8_t* buf, int64_t len,
+                      cudaStream_t s, const unsigned long long* run_if) {
+    auto kern = k_statemap_regions<FK>;
+    const size_t smem = (size_t)((256 + fwd_bytes + 15) & ~15) + 256 * (1 + SM_M) * 2 + SM_WARPS * 32 * sizeof(SubMap) + SM_WARPS * 32 * 2 + 64;
+    int bps = 0;
+    int rc = occupancy_grid(kern, SM_WARPS * 32, smem, p->dev.sm_count, bps);
+    if (rc) return rc;
+    // regions: about four per resident warp, whole segments, at most what the work area holds
+    const int64_t nwarps = (int64_t)p->dev.sm_count * bps * SM_WARPS;
+    int64_t region = (len + nwarps * 4 - 1) / (nwarps * 4);
+    region = (region + SM_SEG - 1) / SM_SEG * SM_SEG;
+    if (region < SM_SEG) region = SM_SEG;
+    const int64_t cap = statemap_max_regions(len);
+    while ((len + 15 + region - 1) / region > cap) region += SM_SEG;
+    mp.region_bytes = region;
+    mp.nregions = (len + 15 + region - 1) / region;
+    if (mp.nregions < 1) mp.nregions = 1;
+    long long want = (mp.nregions + SM_WARPS - 1) / SM_WARPS, capg = (long long)p->dev.sm_count * bps;
+    int grid = (int)(want < capg ? want : capg);
+    kern<<<grid < 1 ? 1 : grid, SM_WARPS * 32, smem, s>>>(sp, mp, buf, len, fwd_bytes, run_if);
+    g_launches++;
+    rc = cuda_status(cudaGetLastError());
+    if (rc) return rc;
+    k_statemap_compose<<<1, 32, 0, s>>>(sp, mp, len, run_if);
+    g_launches++;
+    return cuda_status(cudaGetLastError());
+}
+
+// the state-map scan + its finish, gated on *run_if != 0 (nullptr: always)
+int launch_statemap(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* from_to, unsigned long long* work, cudaStream_t s,
+                    const unsigned long long* run_if) {
+    const fx::ByteTable& st = p->prog.span_bt;
+    SpanParams sp;
+    fill_span_params(p, sp);
+    StateMapParams mp;
+    mp.reach = p->dev.sm_reach; mp.img = p->dev.sm_img; mp.nreach = (int)p->sm_reach.size();
+    uint8_t* maps = reinterpret_cast<uint8_t*>(work) + WORK_HEAD;
+    const int64_t cap = statemap_max_regions(len);
+    mp.rc = reinterpret_cast<uint16_t*>(maps);
+    mp.re = mp.rc + cap * 32;
+    mp.rl = reinterpret_cast<long long*>(maps + (size_t)cap * 32 * 4);
+    mp.result = reinterpret_cast<long long*>(work + 6);
+    mp.region_bytes = 0; mp.nregions = 0;
+    const int classed_bytes = (int)st.table.size() * 2;
+    int fk = p->residency == FX_TABLE_GLOBAL ? 2 : p->dev.sp_direct ? 0 : classed_bytes <= SPAN_CLASSED_SMEM_BYTES ? 1 : 2;
+    fk = env_int("FX_SPAN_FK", fk);
+    if (fk == 0 && !p->dev.sp_direct) fk = 1;
+    const int fwd_bytes = fk == 0 ? st.nstates * SPAN_ROW * 2 : fk == 1 ? classed_bytes : 0;
+    int rc = fk == 0 ? launch_statemap_t<0>(p, sp, mp, fwd_bytes, buf, len, s, run_if)
+           : fk == 1 ? launch_statemap_t<1>(p, sp, mp, fwd_bytes, buf, len, s, run_if)
+                     : launch_statemap_t<2>(p, sp, mp, fwd_bytes, buf, len, s, run_if);
+    if (rc) return rc;
+    k_buffer_finish_span<<<1, 1, 0, s>>>(sp, buf, len, mp.result, from_to, work + 8, work + 9, run_if);
+    g_launches++;
+    return cuda_status(cudaGetLastError());
+}
+
+int launch_buffer(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* from_to, unsigned long long* work,
                   cudaStream_t s) {
     if (len < 0) return FX_ERR_BAD_ARGUMENT;
-    CUDA_TRY(cudaMemsetAsync(best, 0xFF, 8, s));
-    CUDA_TRY(cudaMemsetAsync(best + 1, 0, 16, s));
+    CUDA_TRY(cudaMemsetAsync(work, 0, 128, s));
+    CUDA_TRY(cudaMemsetAsync(work, 0xFF, 8, s));
+    CUDA_TRY(cudaMemsetAsync(work + 12, 0xFF, 8, s));
+    unsigned long long* best = work;
     ScanWindow W{len, 0, len, 0, 1, 1};
     const bool prefixed = p->prog.prefix_active && !p->prog.literal_only;
     if (prefixed && !p->prefix_scan) return FX_ERR_PREFILTER_UNSUPPORTED;
+    p->last_statemap = 0;
+    // Patterns with a linear-time span path: the candidate-start scan (K4) is the fast path when candidates are rare
+    // (sparse first-byte set) -- under a work budget; past the budget, and for every other such pattern, the chunked
+    // state-map scan (K5) answers in linear time; should that scan decline (too many states can arrive at a region
+    // boundary), K4 runs without a budget.  All gating is on device flags: no host round trip.
+    const int sm_mode = env_int("FX_STATEMAP", 1);             // 0 off, 1 as described, 2 always the state-map scan
+    const bool sm_ok = p->statemap && !p->prog.literal_only && !prefixed && len >= 2 && sm_mode != 0;
+    if (sm_ok) {
+        const bool k4_first = p->sparse && p->first.sweep_nr <= 2 && env_int("FX_SPARSE", 1) && sm_mode != 2;
+        int rc;
+        if (k4_first) {
+            ScanBudget bg{work + 5, work + 4, (unsigned long long)len * 16ull + (4ull << 20)};
+            rc = launch_scan(p, buf, W, best, s, SCAN_AUTO, nullptr, nullptr, bg);
+            if (rc) return rc;
+        } else {
+            CUDA_TRY(cudaMemsetAsync(work + 4, 0x01, 1, s));  // no budgeted run: straight to the state-map scan
+        }
+        rc = launch_statemap(p, buf, len, from_to, work, s, work + 4);
+        if (rc) return rc;
+        rc = launch_scan(p, buf, W, work + 12, s, SCAN_AUTO, nullptr, work + 9);      // only if the state-map scan declined
+        if (rc) return rc;
+        p->last_statemap = k4_first ? 2 : 1;
+        return launch_finish(p, buf, W, best, from_to, 1, s, work + 8, work + 9, work + 12);
+    }
     if (len >= 1) {
         int rc = launch_scan(p, buf, W, best, s, SCAN_AUTO);
         if (rc) return rc;
@@ -866,6 +994,33 @@ int fx_compile(const void* pattern, int64_t plen, int op, fx_pattern** out) {
             p->prog.status = p->anchored.status;
         }
     }
+    if (p->prog.status == fx::OK && op == FX_OP_REGEX && p->prog.has_span) {
+        // state-map scan tables: the live states reachable from the start, and the image of all of them under each byte
+        const fx::ByteTable& st = p->prog.span_bt;
+        std::vector<char> seen((size_t)st.nstates, 0);
+        std::vector<int> work{st.start};
+        seen[(size_t)st.start] = 1;
+        while (!work.empty()) {
+            const int u = work.back();
+            work.pop_back();
+            for (int b = 0; b < 256; b++) {
+                const int v = st.direct[(size_t)u * 256 + (size_t)b] & fx::W_SSTATE;
+                if (v != 0 && !seen[(size_t)v]) { seen[(size_t)v] = 1; work.push_back(v); }
+            }
+        }
+        for (int u = 1; u < st.nstates; u++) if (seen[(size_t)u]) p->sm_reach.push_back((uint16_t)u);
+        p->sm_img.assign(256 * (1 + SM_M), 0);
+        for (int b = 0; b < 256; b++) {
+            std::vector<int> im;
+            for (uint16_t u : p->sm_reach) {
+                const int v = st.direct[(size_t)u * 256 + (size_t)b] & fx::W_SSTATE;
+                if (v != 0 && std::find(im.begin(), im.end(), v) == im.end()) im.push_back(v);
+            }
+            p->sm_img[(size_t)b * (1 + SM_M)] = im.size() <= (size_t)SM_M ? (uint16_t)im.size() : (uint16_t)0xFFFF;
+            for (size_t k = 0; k < im.size() && k < (size_t)SM_M; k++) p->sm_img[(size_t)b * (1 + SM_M) + 1 + k] = (uint16_t)im[k];
+        }
+        p->statemap = true;
+    }
     if (p->prog.status == fx::OK && op == FX_OP_REGEX && !p->prog.literal_only) {
         p->sparse = sparse_first_set(p->prog.bt, p->first, false);      // the long-buffer scan can use the SWAR filter
         if (p->prog.prefix_active) {
@@ -889,8 +1044,9 @@ int fx_pattern_free(fx_pattern* p) {
     if (p->dev_touched) {             // also after an upload that failed half-way (every pointer is null or live)
         cudaFree(d.table); cudaFree(d.direct); cudaFree(d.table8); cudaFree(d.classmap); cudaFree(d.flags); cudaFree(d.lits);
         cudaFree(d.a_table); cudaFree(d.a_classmap); cudaFree(d.a_flags);
-        cudaFree(d.sp_table); cudaFree(d.sp_direct); cudaFree(d.sp_classmap); cudaFree(d.sp_flags);
-        cudaFree(d.r_delta); cudaFree(d.r_startok); cudaFree(d.r_cuts); cudaFree(d.r_ascii);
+        cudaFree(d.sp_table); cudaFree(d.sp_direct); cudaFree(d.sp_classmap); cudaFree(d.sp_endinfo);
+        cudaFree(d.r_delta); cudaFree(d.r_cuts); cudaFree(d.r_page); cudaFree(d.r_mixed);
+        cudaFree(d.sm_reach); cudaFree(d.sm_img); cudaFree(d.w_work);
         cudaFree(d.w_buf); cudaFree(d.w_off); cudaFree(d.w_out); cudaFree(d.w_span); cudaFree(d.w_best);
     }
     delete p;
@@ -928,6 +1084,8 @@ int fx_pattern_get_info(const fx_pattern* p, fx_pattern_info* info) {
     }
     info->sparse_used = p->last_sparse;
     info->prefix_scan = p->prefix_scan ? 1 : 0;
+    info->statemap = p->statemap ? 1 : 0;
+    info->statemap_used = p->last_statemap;
     return FX_OK;
 }
 
@@ -962,20 +1120,22 @@ int fx_pattern_tables(const fx_pattern* p, const uint16_t** table, const uint16_
     return FX_OK;
 }
 
-int fx_pattern_span_tables(const fx_pattern* p, const uint16_t** direct, const uint8_t** flags, int32_t scalars[4],
-                           const uint16_t** rdelta, const uint8_t** rstartok, const int32_t** cuts, int32_t rscalars[4]) {
+int fx_pattern_span_tables(const fx_pattern* p, const uint16_t** direct, const uint8_t** endinfo, int32_t scalars[4],
+                           const uint16_t** rdelta, const uint8_t** rpage, const uint8_t** rmixed, const int32_t** cuts,
+                           int32_t rscalars[4]) {
     if (!p || p->prog.status != fx::OK) return FX_ERR_BAD_ARGUMENT;
     if (!p->prog.has_span) return 1;      // the pattern has no linear-time span path
     const fx::ByteTable& st = p->prog.span_bt;
     const fx::RevAutomaton& rv = p->prog.rev;
     if (direct) *direct = st.direct.data();
-    if (flags) *flags = st.flags.data();
-    if (scalars) { scalars[0] = st.nstates; scalars[1] = st.start; scalars[2] = 0; scalars[3] = 0; }
-    if (rdelta) *rdelta = rv.delta.data();
-    if (rstartok) *rstartok = rv.startok.data();
+    if (endinfo) *endinfo = st.endinfo.data();
+    if (scalars) { scalars[0] = st.nstates; scalars[1] = st.start; scalars[2] = (st.flags[(size_t)st.start] & fxk::SF_ACC) ? 1 : 0; scalars[3] = 0; }
+    if (rdelta) *rdelta = rv.delta16.data();
+    if (rpage) *rpage = rv.page.empty() ? nullptr : rv.page.data();
+    if (rmixed) *rmixed = rv.mixed.empty() ? nullptr : rv.mixed.data();
     static_assert(sizeof(int) == sizeof(int32_t), "cuts are exposed as int32");
     if (cuts) *cuts = reinterpret_cast<const int32_t*>(rv.cuts.data());
-    if (rscalars) { rscalars[0] = rv.nstates; rscalars[1] = rv.nclasses; rscalars[2] = rv.start; rscalars[3] = 0; }
+    if (rscalars) { rscalars[0] = rv.nstates; rscalars[1] = rv.nclasses; rscalars[2] = rv.start; rscalars[3] = (int32_t)(rv.mixed.size() / 64); }
     return FX_OK;
 }
 
@@ -1033,7 +1193,7 @@ int fx_regex_batch_dev(fx_pattern* p, const uint8_t* d_buf, const int64_t* d_off
     if (rc) return rc;
     return launch_regex_ragged(p, d_buf, d_offsets, n, total_bytes, d_from, d_to, (cudaStream_t)stream);
 }
-int64_t fx_regex_buffer_work_bytes(int64_t len) { (void)len; return 64; }
+int64_t fx_regex_buffer_work_bytes(int64_t len) { return (int64_t)buffer_work_bytes(len); }
 int fx_regex_buffer_dev(fx_pattern* p, const uint8_t* d_buf, int64_t len, int64_t* d_from_to, void* d_work, void* stream) {
     int rc = check_ready(p, FX_OP_REGEX);
     if (rc) return rc;
@@ -1164,8 +1324,9 @@ int fx_regex_buffer(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* fro
     DeviceTables& d = p->dev;
     if ((rc = grow(d.w_buf, d.w_buf_cap, (size_t)len + 64))) return rc;
     if ((rc = grow(d.w_span, d.w_span_cap, 16))) return rc;
+    if ((rc = grow(d.w_work, d.w_work_cap, buffer_work_bytes(len)))) return rc;
     if (len) CUDA_TRY(cudaMemcpyAsync(d.w_buf, buf, (size_t)len, cudaMemcpyHostToDevice, 0));
-    rc = launch_buffer(p, d.w_buf, len, d.w_span, d.w_best, 0);
+    rc = launch_buffer(p, d.w_buf, len, d.w_span, reinterpret_cast<unsigned long long*>(d.w_work), 0);
     if (rc) return rc;
     int64_t ft[2] = {0, 0};
     CUDA_TRY(cudaMemcpyAsync(ft, d.w_span, 16, cudaMemcpyDeviceToHost, 0));

@@ -126,6 +126,13 @@ struct RevAutomaton {
     std::vector<int> cuts;
     std::vector<uint16_t> delta;   // nstates x nclasses
     std::vector<uint8_t> startok;  // nstates
+    // device form: delta16[r * nclasses + c] = next state | 0x8000 if the next state holds the NFA entry (<= 32767 states),
+    // and a two-level class map of the code points below U+10000 so that the backward walk finds the class of a decoded
+    // character with one or two shared-memory loads instead of a binary search over `cuts`:
+    //   page[cp >> 6] < 0x80 : the class of all 64 code points of the block;  >= 0x80 : mixed[(page & 0x7F) * 64 + (cp & 63)]
+    std::vector<uint16_t> delta16;
+    std::vector<uint8_t> page;     // 1024 entries; empty when the automaton has more than 127 classes or mixed blocks
+    std::vector<uint8_t> mixed;
 };
 int build_rev_automaton(const Nfa& nfa, int state_cap, RevAutomaton& out);
 
@@ -137,6 +144,17 @@ int build_cp_automaton(const Nfa& nfa, Mode mode, int state_cap, CpAutomaton& ou
 //   REGEX tables (flag_bits): word = state id (bits 0..13) | INTER (bit 14) | ACC (bit 15), <= 16383 states
 //   MATCH / IN tables:        word = state id (16 bits), <= 65535 states; flags[] is read once, at the end
 static const uint16_t W_ACC = 0x8000, W_INTER = 0x4000, W_STATE = 0x3FFF;
+//   SPAN tables (span_words; the forward "ordered groups" automaton of the linear-time span path and of the long-buffer
+//   state-map scan): word = state id (bits 0..11, <= 4095 states) | RA (bits 12..13) | INTER (bit 14) | ACC (bit 15).
+//   RA != 0 marks a transition out of an in-sequence state on a byte that breaks the sequence: the pending bytes replay
+//   as U+FFFF (api_internal_m.F90:129-133) and the last accepting boundary passed on the way lies RA-1 bytes before the
+//   byte just read -- so a walker needs neither the start of the sequence nor a look at the flags:
+//       if (w & W_RA) last = j + 1 - RA;   if (w & W_ACC) last = j + 1;        (j = index of the byte just read)
+static const uint16_t W_SSTATE = 0x0FFF, W_RA = 0x3000;
+static const int W_RA_SHIFT = 12;
+// endinfo[state] of a SPAN table: what the end of the text does in this state.  bits 0..1 = RA of the pending bytes'
+// replay (last = len + 1 - RA), bit 2 = the trailing NUL is consumed into an accept (last = len + 1)
+enum EndInfo : uint8_t { EI_RA = 3, EI_NUL = 4 };
 enum StateFlag : uint8_t {
     SF_ACC = 1,        // boundary state whose NFA set holds the exit
     SF_END = 2,        // "result is true if the text ends in this state" (MATCH / IN modes)
@@ -164,9 +182,12 @@ struct ByteTable {
     // and with <= 255 states a one-byte-per-entry 256-column table exists
     int result_threshold = 0;
     std::vector<uint8_t> direct8;  // nstates * 256, or empty
+    // SPAN tables only (see W_RA above)
+    bool span_words = false;
+    std::vector<uint8_t> endinfo;  // nstates
 };
 
-int build_byte_table(const CpAutomaton& a, bool flag_bits, ByteTable& out);
+int build_byte_table(const CpAutomaton& a, bool flag_bits, ByteTable& out, bool span_words = false);
 
 // Whole compiled pattern (host side).
 struct Program {

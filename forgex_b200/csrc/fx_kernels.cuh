@@ -99,6 +99,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // KIND 1: 16-bit entries, 256 columns, shared memory (span tables, flag bits in the word)
 // KIND 2: 16-bit entries, class-compressed rows + classmap, shared memory
 // KIND 3: 16-bit entries, class-compressed rows + classmap, global memory through L1/L2
+// KIND 0 rows are padded to 65 words in shared memory: with 64-word rows the bank of a lookup depends on the byte
+// alone, so lanes that sit in DIFFERENT states and read the same byte value (digits, the dead state's row ...) collide.
+static constexpr int ROW8 = 260;
 template <int KIND>
 struct Table {
     uint32_t s_table, s_cmap;  // shared addresses
@@ -106,7 +109,7 @@ struct Table {
     const uint8_t* g_cmap;
     int shift;
     __device__ __forceinline__ uint32_t next(uint32_t state, uint32_t byte) const {
-        if (KIND == 0) return lds_u8(s_table + ((state << 8) | byte));
+        if (KIND == 0) return lds_u8(s_table + state * ROW8 + byte);
         if (KIND == 1) return lds_u16(s_table + (((state << 8) | byte) << 1));
         if (KIND == 2) return lds_u16(s_table + (((state << shift) + lds_u8(s_cmap + byte)) << 1));
         return __ldg(g_table + ((state << shift) + __ldg(g_cmap + byte)));
@@ -123,7 +126,8 @@ __device__ __forceinline__ Table<KIND> stage_table(const KParams& p, uint8_t* sm
         const uint32_t* src = reinterpret_cast<const uint32_t*>(KIND == 0 ? (const void*)p.table8 : (const void*)p.table);
         uint32_t* dst = reinterpret_cast<uint32_t*>(smem_table);
         const int words32 = KIND == 0 ? p.nstates * 64 : (p.table_words + 1) >> 1;
-        for (int i = threadIdx.x; i < words32; i += blockDim.x) dst[i] = __ldg(src + i);
+        if (KIND == 0) for (int i = threadIdx.x; i < words32; i += blockDim.x) dst[(i >> 6) * (ROW8 / 4) + (i & 63)] = __ldg(src + i);
+        else for (int i = threadIdx.x; i < words32; i += blockDim.x) dst[i] = __ldg(src + i);
         if (KIND == 2)
             for (int i = threadIdx.x; i < 64; i += blockDim.x)
                 reinterpret_cast<uint32_t*>(smem_cmap)[i] = __ldg(reinterpret_cast<const uint32_t*>(p.classmap) + i);
@@ -543,32 +547,37 @@ __global__ void __launch_bounds__(256) k_bool_fixed(KParams p, const uint8_t* __
     const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
     if ((VEC == 8 || VEC == 16) && !generic && stride == VEC) {
         // One load covers a whole string (C1: 8 bytes): the walk is 8-16 lookups, short against the latency of the load
-        // in front of it, so a thread takes FOUR strings per step -- all loads first, then the four walks.
-        for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * gstride) {
-            constexpr int NW = VEC == 16 ? 4 : 2;          // 32-bit words per string
+        // in front of it, so a thread takes FOUR CONSECUTIVE strings per step -- all loads first (a warp reads one
+        // contiguous KB), then the four walks, then one 4-byte store of the four results (a warp writes whole lines).
+        constexpr int NW = VEC == 16 ? 4 : 2;          // 32-bit words per string
+        const bool word_out = (reinterpret_cast<uintptr_t>(out) & 3) == 0;
+        const int64_t ngroups = (n + 3) >> 2;
+        for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += gstride) {
+            const int64_t i0 = g << 2;
             uint32_t w[4][NW];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int64_t i = i0 + u * gstride;
 #pragma unroll
                 for (int q = 0; q < NW; q++) w[u][q] = 0;
-                if (i < n) {
-                    if (VEC == 16) { const uint4 v = ldg_nc_v4(buf + i * stride); w[u][0] = v.x; w[u][1] = v.y; w[u][NW - 2] = v.z; w[u][NW - 1] = v.w; }
-                    else { const uint2 v = ldg_nc_v2(buf + i * stride); w[u][0] = v.x; w[u][1] = v.y; }
+                if (i0 + u < n) {
+                    if (VEC == 16) { const uint4 v = ldg_nc_v4(buf + (i0 + u) * stride); w[u][0] = v.x; w[u][1] = v.y; w[u][NW - 2] = v.z; w[u][NW - 1] = v.w; }
+                    else { const uint2 v = ldg_nc_v2(buf + (i0 + u) * stride); w[u][0] = v.x; w[u][1] = v.y; }
                 }
             }
+            uint32_t res = 0;
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int64_t i = i0 + u * gstride;
-                if (i < n) {
+                if (i0 + u < n) {
                     uint32_t st = (uint32_t)p.start, high = 0;
 #pragma unroll
                     for (int q = 0; q < NW; q++) { high |= w[u][q]; st = step4(T, st, w[u][q]); }
                     bool r = result_flag(p, st);
-                    if (OP == 1 && r && p.prefix_mode == 1 && (high & 0x80808080u)) r = recheck_in_with_prefix(p, buf + i * stride, stride);
-                    out[i] = r ? 1 : 0;
+                    if (OP == 1 && r && p.prefix_mode == 1 && (high & 0x80808080u)) r = recheck_in_with_prefix(p, buf + (i0 + u) * stride, stride);
+                    res |= (r ? 1u : 0u) << (8 * u);
                 }
             }
+            if (word_out && i0 + 3 < n) *reinterpret_cast<uint32_t*>(out + i0) = res;
+            else for (int u = 0; u < 4 && i0 + u < n; u++) out[i0 + u] = (uint8_t)(res >> (8 * u));
         }
         return;
     }
@@ -1440,159 +1449,216 @@ __global__ void __launch_bounds__(256) k_regex_ragged(KParams p, const uint8_t* 
 // ---------------------------------------------------------------------------------------------
 // K3f: ragged batch, span result, linear time (config C3).
 // Forward: ONE walk of the "ordered groups" automaton (fx_automata.cpp, build_span_forward) yields the end of
-// Forgex's leftmost-longest match: the last position at which the state held the exit.  Backward: the reverse
-// automaton walks from that end towards the front, decoding characters backwards with the reference's decoder
-// rule (a well-formed sequence that ends exactly here, else one byte = U+FFFF); the leftmost position at which
-// it holds the NFA entry is the start.  Same tiling as K2 (TMA-staged tile, one string per thread).
+// Forgex's leftmost-longest match: the last position at which the state held the exit.  Its table words carry every
+// event of a step -- ACC (the new state holds the exit), RA (a broken multi-byte sequence replayed as U+FFFF bytes and
+// passed an accept on the way; fx_internal.hpp W_RA) -- so a step is one lookup and, rarely, an update of `last`;
+// the walker keeps no per-sequence bookkeeping.  Backward: the reverse automaton (over code-point classes) walks from
+// that end towards the front, decoding characters backwards with the reference's decoder rule (a well-formed sequence
+// that ends exactly here, else one byte = U+FFFF); the class of a character comes from a two-level table in shared
+// memory, the transition word carries "this state holds the NFA entry"; the leftmost such position is the start.
 // ---------------------------------------------------------------------------------------------
+static constexpr uint32_t W_SSTATE = 0x0FFFu, W_RA = 0x3000u;
+static constexpr int SPAN_ROW = 258;             // u16 entries per state row in shared memory: 129 words, an odd stride, so that
+                                                 // lanes in different states reading the same byte value hit different banks
 struct SpanParams {
-    // forward table (flag-bit words), selected form
-    const uint16_t* table;
+    // forward automaton (span words)
+    const uint16_t* direct;     // nstates x 256
+    const uint16_t* table;      // class-compressed: nstates << row_shift
     const uint8_t* classmap;
-    const uint8_t* flags;
-    int table_words, nstates, row_shift, start;
+    const uint8_t* endinfo;     // nstates
+    int nstates, row_shift, start, start_acc;
     // reverse automaton over code-point classes
-    const uint16_t* rdelta;     // rstates x rclasses
-    const uint8_t* rstartok;
+    const uint16_t* rdelta;     // rstates x rclasses, bit 15 = the destination holds the NFA entry
+    const uint8_t* rpage;       // 1024 (nullptr: no two-level map, binary search)
+    const uint8_t* rmixed;
     const int32_t* cuts;        // rclasses + 1 ascending code points
-    const uint8_t* ascii_class; // class of code points 0..127
-    int rclasses, rstart, nul_class, ffff_class;
+    int rstates, rclasses, rstart, nul_class, ffff_class, nmixed;
 };
 
-__device__ __forceinline__ int cp_class(const SpanParams& sp, uint32_t cp) {
-    if (cp < 128) return __ldg(sp.ascii_class + cp);
-    int lo = 0, hi = sp.rclasses;              // largest c with cuts[c] <= cp
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if ((uint32_t)__ldg(sp.cuts + mid) <= cp) lo = mid; else hi = mid;
+// forward table access.  FK 0: 256 columns, padded rows, shared memory; FK 1: class-compressed, shared; FK 2: class-compressed, global
+template <int FK>
+struct SpanFwd {
+    uint32_t s_table, s_cmap;
+    const uint16_t* g_table;
+    const uint8_t* g_cmap;
+    int shift;
+    __device__ __forceinline__ uint32_t next(uint32_t st, uint32_t b) const {
+        if (FK == 0) return lds_u16(s_table + st * (SPAN_ROW * 2) + b * 2);
+        if (FK == 1) return lds_u16(s_table + (((st << shift) + lds_u8(s_cmap + b)) << 1));
+        return __ldg(g_table + ((st << shift) + __ldg(g_cmap + b)));
     }
-    return lo;
+};
+// reverse tables.  RS true: rdelta / page / mixed in shared memory
+template <bool RS>
+struct SpanRev {
+    uint32_t s_delta, s_page, s_mixed;
+    __device__ __forceinline__ uint32_t delta(const SpanParams& sp, uint32_t r, uint32_t c) const {
+        if (RS) return lds_u16(s_delta + ((r * (uint32_t)sp.rclasses + c) << 1));
+        return __ldg(sp.rdelta + r * (uint32_t)sp.rclasses + c);
+    }
+    __device__ __forceinline__ uint32_t cls(const SpanParams& sp, uint32_t cp) const {
+        if (cp < 0x10000u && sp.rpage != nullptr) {
+            const uint32_t pg = RS ? lds_u8(s_page + (cp >> 6)) : (uint32_t)__ldg(sp.rpage + (cp >> 6));
+            if (pg < 0x80u) return pg;
+            const uint32_t i = ((pg & 0x7Fu) << 6) | (cp & 63u);
+            return RS ? lds_u8(s_mixed + i) : (uint32_t)__ldg(sp.rmixed + i);
+        }
+        int lo = 0, hi = sp.rclasses;              // largest c with cuts[c] <= cp
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if ((uint32_t)__ldg(sp.cuts + mid) <= cp) lo = mid; else hi = mid;
+        }
+        return (uint32_t)lo;
+    }
+};
+
+// one forward step: the byte at text index jj
+#define FX_SPAN_STEP(T, st, last, b, jj)                                         \
+    {                                                                             \
+        const uint32_t nw_ = (T).next((st), (b));                                 \
+        if (nw_ & 0xB000u) {                                                      \
+            if (nw_ & W_RA) (last) = (jj) + 1 - (int)((nw_ >> 12) & 3u);          \
+            if (nw_ & W_ACC) (last) = (jj) + 1;                                   \
+        }                                                                         \
+        (st) = nw_ & W_SSTATE;                                                    \
+    }
+
+// what the end of the text does in state st (the pending bytes of an unfinished sequence replay as U+FFFF; the
+// trailing NUL is consumed but is not a start)
+__device__ __forceinline__ int span_end_of_text(const SpanParams& sp, uint32_t st, int len, int last) {
+    const uint32_t e = __ldg(sp.endinfo + st);
+    if (e & 3u) last = len + 1 - (int)(e & 3u);
+    if (e & 4u) last = len + 1;
+    return last;
 }
 
-// backward half of the linear-time span search: the leftmost start of a match that ends at `last` (> 0)
-template <class FETCH>
-__device__ __forceinline__ void span_backward(const SpanParams& sp, FETCH fetch, int len, int last,
-                                              int64_t& from, int64_t& to) {
-    from = 0; to = 0;
-    // ---- backward: leftmost start of a match that ends at `last` ----
+// backward half: the leftmost start of a match that ends at `last` (> 0).  Returns from (1-based), 0 if none.
+template <bool RS, class FETCH>
+__device__ __forceinline__ int span_backward(const SpanParams& sp, const SpanRev<RS>& R, FETCH fetch, int len, int last) {
     uint32_t r = (uint32_t)sp.rstart;
     int pos = last;
-    if (last > len) { r = __ldg(sp.rdelta + r * sp.rclasses + sp.nul_class); pos = len; }
+    if (last > len) { r = R.delta(sp, r, (uint32_t)sp.nul_class) & 0x7FFFu; pos = len; }
     int best = -2;                                          // -2 none, -1 the leading NUL, >= 0 text index
     while (r != 0 && pos > 0) {
-        // the character that ends at pos
-        uint32_t c = fetch(pos - 1);
+        uint32_t c = fetch(pos - 1);                        // the character that ends at pos
         int q = pos - 1;
         uint32_t cp = c;
-        if (c >= 0x80) {
-            cp = 0xFFFF;                                    // stray / malformed byte unless a well-formed sequence ends here
-            if ((c & 0xC0) == 0x80) {
-                uint32_t acc = c & 0x3F;
-                int shift = 6;
-                for (int back = 2; back <= 4 && pos - back >= 0; back++) {
-                    const uint32_t d = fetch(pos - back);
-                    if ((d & 0xC0) == 0x80) { acc |= (d & 0x3F) << shift; shift += 6; continue; }
-                    const int n = (d >> 5) == 6 ? 2 : (d >> 4) == 14 ? 3 : (d >> 3) == 30 ? 4 : 1;
-                    if (n == back) {
-                        const uint32_t lead_bits = n == 2 ? (d & 0x1F) : n == 3 ? (d & 0x0F) : (d & 0x07);
-                        cp = acc | (lead_bits << shift);
-                        q = pos - back;
+        if (c >= 0x80u) {
+            cp = 0xFFFFu;                                   // stray / malformed byte unless a well-formed sequence ends here
+            if ((c & 0xC0u) == 0x80u && pos >= 2) {
+                const uint32_t d1 = fetch(pos - 2);
+                if ((d1 & 0xE0u) == 0xC0u) { cp = ((d1 & 0x1Fu) << 6) | (c & 0x3Fu); q = pos - 2; }
+                else if ((d1 & 0xC0u) == 0x80u && pos >= 3) {
+                    const uint32_t d2 = fetch(pos - 3);
+                    if ((d2 & 0xF0u) == 0xE0u) { cp = ((d2 & 0x0Fu) << 12) | ((d1 & 0x3Fu) << 6) | (c & 0x3Fu); q = pos - 3; }
+                    else if ((d2 & 0xC0u) == 0x80u && pos >= 4) {
+                        const uint32_t d3 = fetch(pos - 4);
+                        if ((d3 & 0xF8u) == 0xF0u) {
+                            cp = ((d3 & 0x07u) << 18) | ((d2 & 0x3Fu) << 12) | ((d1 & 0x3Fu) << 6) | (c & 0x3Fu);
+                            q = pos - 4;
+                        }
                     }
-                    break;
                 }
             }
         }
-        r = __ldg(sp.rdelta + r * sp.rclasses + cp_class(sp, cp));
+        const uint32_t w = R.delta(sp, r, R.cls(sp, cp));
+        r = w & 0x7FFFu;
         if (r == 0) break;
         pos = q;
-        if (__ldg(sp.rstartok + r)) best = pos;
+        if (w & 0x8000u) best = pos;
     }
     if (r != 0 && pos == 0) {                               // the leading NUL sentinel (start position 1)
-        r = __ldg(sp.rdelta + r * sp.rclasses + sp.nul_class);
-        if (r != 0 && __ldg(sp.rstartok + r)) best = -1;
+        const uint32_t w = R.delta(sp, r, (uint32_t)sp.nul_class);
+        if ((w & 0x7FFFu) != 0 && (w & 0x8000u)) best = -1;
     }
-    if (best == -2) return;                                 // cannot happen for a consistent pair of automata
-    from = best < 0 ? 1 : best + 1;
-    to = last < len ? last : len;
+    if (best == -2) return 0;                               // cannot happen for a consistent pair of automata
+    return best < 0 ? 1 : best + 1;
 }
 
-// the linear-time span search over any byte source: forward walk to the match end, backward walk to its start
-template <class TBL, class FETCH>
-__device__ __forceinline__ void span_linear(const SpanParams& sp, const TBL& T, FETCH fetch, int len,
-                                            int64_t& from, int64_t& to) {
+// the linear-time span search over any byte source (strings that are not staged: longer than a warp's tile)
+template <int FK, bool RS, class FETCH>
+__device__ __noinline__ void span_linear(const SpanParams& sp, const SpanFwd<FK>& T, const SpanRev<RS>& R, FETCH fetch, int len,
+                                         int64_t& from, int64_t& to) {
     from = 0; to = 0;
-    // ---- forward: end of the leftmost-longest match ----
-    uint32_t w = (uint32_t)sp.start;
-    int last = (__ldg(sp.flags + sp.start) & SF_ACC) ? 0 : -1;
-    int seq = 0;
-    bool inter = false;
+    uint32_t st = (uint32_t)sp.start;
+    int last = sp.start_acc ? 0 : -1;
     int j = 0;
-    for (; j < len; j++) {
-        const uint32_t b = fetch(j);
-        if (inter && (b & 0xC0) != 0x80) {                  // sequence broken: pending bytes replay as U+FFFF
-            const uint32_t f = __ldg(sp.flags + (w & W_STATE));
-            for (int k = 1; k <= j - seq; k++)
-                if (f & (SF_FAILACC1 << (k - 1))) last = seq + k;
-            inter = false;
-        }
-        const uint32_t nw = T.next(w & W_STATE, b);
-        if ((nw & W_INTER) && !inter) seq = j;
-        inter = (nw & W_INTER) != 0;
-        w = nw;
-        if (w & W_ACC) last = j + 1;
-        if ((w & W_STATE) == 0) break;
-    }
-    if (j >= len && (w & W_STATE) != 0) {                  // text exhausted: the trailing NUL follows (not a start)
-        const uint32_t f = __ldg(sp.flags + (w & W_STATE));
-        if (inter)
-            for (int k = 1; k <= len - seq; k++)
-                if (f & (SF_FAILACC1 << (k - 1))) last = seq + k;
-        if (f & SF_END) last = len + 1;
-    }
+    for (; j < len && st != 0; j++) { const uint32_t b = fetch(j); FX_SPAN_STEP(T, st, last, b, j); }
+    if (st != 0) last = span_end_of_text(sp, st, len, last);
     if (last <= 0) return;                                  // no match, or only the leading NUL matched (to = 0)
-    span_backward(sp, fetch, len, last, from, to);
-}
-template <class TBL>
-__device__ __forceinline__ void span_linear_smem(const SpanParams& sp, const TBL& T, uint32_t a, int len,
-                                                 int64_t& from, int64_t& to) {
-    span_linear(sp, T, FetchShared{a}, len, from, to);
+    const int f = span_backward(sp, R, fetch, len, last);
+    if (f > 0) { from = f; to = last < len ? last : len; }
 }
 
-// shared memory of K3f: classmap 256 | table | pad to 128 | SPAN_WARPS warp regions of `warp_bytes`:
-//   [0,16) mbarrier | offsets (spt+4) x int32 | pad to 128 | tile (cap + 64)
-// Every warp stages its own tiles (its own TMA bulk copy on its own mbarrier): no block-wide step after the table is
-// staged, so a warp never waits for the block's slowest string (measured on the block-tile version: 39 % of all warp
-// samples sat at the tile barrier).
-static constexpr int SPAN_WARPS = 16;
-struct SpanLayout { int off_tile, warp_bytes; };
+// shared memory of K3f: classmap 256 | forward table | reverse tables (delta, page 1024, mixed) | pad to 128 |
+//   SPAN_WARPS warp regions of `warp_bytes`:
+//   [0,16) mbarrier | offsets (spt+4) x int32 | results spt x int2 | queue spt x uint32 | pad to 128 | tile (cap + 64)
+// Every warp stages its own tiles (its own TMA bulk copy on its own mbarrier): no block-wide step after the tables are
+// staged.  One CTA of 32 warps per SM: one copy of the tables, the rest of the shared memory is tile space.
+static constexpr int SPAN_WARPS = 32;
+struct SpanLayout { int off_res, off_queue, off_tile, warp_bytes; };
 __host__ __device__ __forceinline__ SpanLayout span_layout(int spt, int cap) {
     SpanLayout L;
-    L.off_tile = (16 + (spt + 4) * 4 + 127) & ~127;
+    L.off_res = 16 + (spt + 4) * 4;
+    L.off_queue = L.off_res + spt * 8;
+    L.off_tile = (L.off_queue + spt * 4 + 127) & ~127;
     L.warp_bytes = (L.off_tile + cap + 64 + 127) & ~127;
     return L;
 }
-__host__ __device__ __forceinline__ int span_shared_head(int table_smem_bytes) { return (256 + table_smem_bytes + 127) & ~127; }
+struct SpanHead { int off_rdelta, off_page, off_mixed, bytes; };
+__host__ __device__ __forceinline__ SpanHead span_head(int fwd_bytes, int rdelta_bytes, int nmixed, bool rs) {
+    SpanHead H;
+    H.off_rdelta = (256 + fwd_bytes + 15) & ~15;
+    H.off_page = H.off_rdelta + (rs ? ((rdelta_bytes + 15) & ~15) : 0);
+    H.off_mixed = H.off_page + (rs ? 1024 : 0);
+    H.bytes = (H.off_mixed + (rs ? nmixed * 64 : 0) + 127) & ~127;
+    return H;
+}
+static constexpr int SPAN_ROUND = 32;            // bytes a lane walks before the warp looks for idle lanes again
 
-template <int KIND>
-__global__ void __launch_bounds__(SPAN_WARPS * 32, 2) k_span_ragged(KParams p, SpanParams sp, const uint8_t* __restrict__ buf,
+template <int FK, bool RS>
+__global__ void __launch_bounds__(SPAN_WARPS * 32, 1) k_span_ragged(KParams p, SpanParams sp, const uint8_t* __restrict__ buf,
                                                                    const int64_t* __restrict__ offsets, int64_t n, int64_t total,
                                                                    int64_t* __restrict__ from, int64_t* __restrict__ to,
-                                                                   int spt, int cap, int64_t ntiles, int table_smem_bytes) {
+                                                                   int spt, int cap, int64_t ntiles, int fwd_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* s_cmap = smem;
-    uint8_t* s_table = smem + 256;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t FULL = 0xffffffffu;
+    const SpanHead H = span_head(fwd_bytes, sp.rstates * sp.rclasses * 2, sp.nmixed, RS);
     const SpanLayout L = span_layout(spt, cap);
-    uint8_t* region = smem + span_shared_head(table_smem_bytes) + warp * L.warp_bytes;
+    // ---- stage the tables (the only block-wide step) ----
+    SpanFwd<FK> T;
+    T.s_cmap = smem_u32(smem); T.s_table = smem_u32(smem + 256); T.g_table = sp.table; T.g_cmap = sp.classmap; T.shift = sp.row_shift;
+    if (FK == 0) {                                           // rows of 256 entries -> rows of SPAN_ROW entries
+        uint16_t* dst = reinterpret_cast<uint16_t*>(smem + 256);
+        for (int i = threadIdx.x; i < sp.nstates * 128; i += blockDim.x) {
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(sp.direct) + i);
+            const int st = i >> 7, c = (i & 127) << 1;
+            *reinterpret_cast<uint32_t*>(dst + st * SPAN_ROW + c) = v;
+        }
+    } else if (FK == 1) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem + 256);
+        const int words32 = ((sp.nstates << sp.row_shift) + 1) >> 1;
+        for (int i = threadIdx.x; i < words32; i += blockDim.x) dst[i] = __ldg(reinterpret_cast<const uint32_t*>(sp.table) + i);
+        for (int i = threadIdx.x; i < 64; i += blockDim.x)
+            reinterpret_cast<uint32_t*>(smem)[i] = __ldg(reinterpret_cast<const uint32_t*>(sp.classmap) + i);
+    }
+    SpanRev<RS> R;
+    R.s_delta = smem_u32(smem + H.off_rdelta); R.s_page = smem_u32(smem + H.off_page); R.s_mixed = smem_u32(smem + H.off_mixed);
+    if (RS) {
+        uint16_t* d = reinterpret_cast<uint16_t*>(smem + H.off_rdelta);
+        for (int i = threadIdx.x; i < sp.rstates * sp.rclasses; i += blockDim.x) d[i] = __ldg(sp.rdelta + i);
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) smem[H.off_page + i] = __ldg(sp.rpage + i);
+        for (int i = threadIdx.x; i < sp.nmixed * 64; i += blockDim.x) smem[H.off_mixed + i] = __ldg(sp.rmixed + i);
+    }
+    uint8_t* region = smem + H.bytes + warp * L.warp_bytes;
     int32_t* s_off = reinterpret_cast<int32_t*>(region + 16);
+    int2* s_res = reinterpret_cast<int2*>(region + L.off_res);
+    uint32_t* s_queue = reinterpret_cast<uint32_t*>(region + L.off_queue);
     uint8_t* tile = region + L.off_tile;
     const uint32_t mbar = smem_u32(region);
-    KParams fwd = p;                       // stage_table reads table / classmap / sizes from a KParams
-    fwd.table = sp.table; fwd.classmap = sp.classmap; fwd.table_words = sp.table_words; fwd.row_shift = sp.row_shift;
-    fwd.nstates = sp.nstates;
-    Table<KIND> T = stage_table<KIND>(fwd, s_table, s_cmap);
     if (lane == 0) mbar_init(mbar, 1);
-    __syncthreads();                        // the only block-wide step
+    __syncthreads();
     uint32_t phase = 0;
     const uint32_t tile_addr = smem_u32(tile);
     const uintptr_t gbuf = reinterpret_cast<uintptr_t>(buf);
@@ -1623,32 +1689,86 @@ __global__ void __launch_bounds__(SPAN_WARPS * 32, 2) k_span_ragged(KParams p, S
         }
         if (bulk) { mbar_wait(mbar, phase); phase ^= 1; }
         __syncwarp();
-        // ---- one string per lane.  (Tried: the lanes as a work queue -- a lane that finishes its string claims the
-        // tile's next one, one byte step per iteration: 18 instead of 12 busy lanes, but the per-step ballots and the
-        // claim path cost more than that buys: 252 vs 360 GB/s on C3.) ----
-        for (int i = lane; i < count; i += 32) {
-            const int32_t r0 = s_off[i], r1 = s_off[i + 1];
-            int64_t f = 0, e = 0;
-            if (r1 == OFF_BEYOND) {          // not staged (longer than a warp's tile): the same two walks, text from global memory
-                const int64_t o0 = __ldg(offsets + first + i), o1 = __ldg(offsets + first + i + 1);
-                if (o1 - o0 == 0 || (o1 - o0 == 1 && __ldg(buf + o0) == 0x20)) {
-                    // api_internal_m.F90:68-74: empty text or a lone blank never reaches the loop -> (0, 0).  (A short
-                    // string lands here when it follows an over-long one in the same tile: its end is past the staged bytes.)
-                } else if (o1 - o0 < 0x7FFFFFF0ll) {
-                    span_linear(sp, T, FetchGlobal{buf + o0}, (int)(o1 - o0), f, e);
-                } else {                     // 2 GiB and more in one string: 64-bit positions, the anchored emulation
-                    Table<3> G;
-                    G.g_table = p.ctable; G.g_cmap = p.classmap; G.shift = p.c_row_shift; G.s_table = 0; G.s_cmap = 0;
-                    eval_regex(p, G, FetchGlobal{buf + o0}, o1 - o0, f, e);
+        // ---- forward walks.  The lanes are a pool of walkers: a lane that has no string claims the tile's next one;
+        // all lanes then walk up to SPAN_ROUND bytes (whole 32-bit words of the tile) and the warp looks again.  A string
+        // whose walk ends with a match is queued for the backward phase; the others get (0, 0).
+        int next = 0, nq = 0;                                      // warp-uniform: next unclaimed string, queue fill
+        bool have = false;
+        int sidx = 0, len = 0, j = 0, last = -1;
+        uint32_t a = 0, st = 0;
+        for (;;) {
+            const uint32_t idle = __ballot_sync(FULL, !have);
+            if (idle) {
+                const int mine = next + __popc(idle & ((1u << lane) - 1));
+                if (!have && mine < count) {
+                    sidx = mine;
+                    const int32_t r0 = s_off[sidx], r1 = s_off[sidx + 1];
+                    if (r1 == OFF_BEYOND) {      // not staged (longer than a warp's tile): the same two walks, text from global memory
+                        const int64_t o0 = __ldg(offsets + first + sidx), o1 = __ldg(offsets + first + sidx + 1);
+                        int64_t f = 0, e = 0;
+                        if (o1 - o0 == 0 || (o1 - o0 == 1 && __ldg(buf + o0) == 0x20)) {
+                            // api_internal_m.F90:68-74: empty text or a lone blank never reaches the loop -> (0, 0)
+                        } else if (o1 - o0 < 0x7FFFFFF0ll) {
+                            span_linear(sp, T, R, FetchGlobal{buf + o0}, (int)(o1 - o0), f, e);
+                        } else {                 // 2 GiB and more in one string: 64-bit positions, the anchored emulation
+                            Table<3> G;
+                            G.g_table = p.ctable; G.g_cmap = p.classmap; G.shift = p.c_row_shift; G.s_table = 0; G.s_cmap = 0;
+                            eval_regex(p, G, FetchGlobal{buf + o0}, o1 - o0, f, e);
+                        }
+                        from[first + sidx] = f; to[first + sidx] = e;
+                        s_res[sidx] = make_int2(-1, -1);           // already written
+                    } else {
+                        len = r1 - r0;
+                        a = tile_addr + (uint32_t)r0;
+                        if (len == 0 || (len == 1 && lds_u8(a) == 0x20)) s_res[sidx] = make_int2(0, 0);   // api_internal_m.F90:68-74
+                        else { have = true; j = 0; st = (uint32_t)sp.start; last = sp.start_acc ? 0 : -1; }
+                    }
                 }
-            } else {
-                const int len = r1 - r0;
-                const uint32_t a = tile_addr + (uint32_t)r0;
-                if (!(len == 0 || (len == 1 && lds_u8(a) == 0x20)))              // api_internal_m.F90:68-74
-                    span_linear_smem(sp, T, a, len, f, e);
+                next += __popc(idle);
+                if (next > count) next = count;
             }
-            from[first + i] = f;
-            to[first + i] = e;
+            if (!__any_sync(FULL, have)) { if (next >= count) break; else continue; }
+            if (have) {
+                int jend = (int)(((a + (uint32_t)j + SPAN_ROUND) & ~3u) - a);     // the round ends on a word boundary of the tile
+                if (jend > len) jend = len;
+                while (j < jend && ((a + (uint32_t)j) & 3u)) { const uint32_t b = lds_u8(a + j); FX_SPAN_STEP(T, st, last, b, j); j++; }
+                for (; j + 4 <= jend && st != 0; j += 4) {
+                    const uint32_t w4 = lds_u32(a + j);
+                    FX_SPAN_STEP(T, st, last, w4 & 0xFFu, j);
+                    FX_SPAN_STEP(T, st, last, (w4 >> 8) & 0xFFu, j + 1);
+                    FX_SPAN_STEP(T, st, last, (w4 >> 16) & 0xFFu, j + 2);
+                    FX_SPAN_STEP(T, st, last, w4 >> 24, j + 3);
+                }
+                if (st != 0) for (; j < jend; j++) { const uint32_t b = lds_u8(a + j); FX_SPAN_STEP(T, st, last, b, j); }
+                if (st == 0 || j >= len) {                          // this walk is over
+                    if (st != 0) last = span_end_of_text(sp, st, len, last);
+                    have = false;
+                    if (last <= 0) s_res[sidx] = make_int2(0, 0);   // no match, or only the leading NUL matched (to = 0)
+                }
+            }
+            // queue the strings whose walk ended with a match
+            const bool push = !have && last > 0;
+            const uint32_t pm = __ballot_sync(FULL, push);
+            if (push) { s_queue[nq + __popc(pm & ((1u << lane) - 1))] = ((uint32_t)sidx << 16) | (uint32_t)last; last = -1; }
+            nq += __popc(pm);
+        }
+        __syncwarp();
+        // ---- backward walks, 32 queued strings at a time ----
+        for (int q0 = 0; q0 < nq; q0 += 32) {
+            if (q0 + lane < nq) {
+                const uint32_t e = s_queue[q0 + lane];
+                const int si = (int)(e >> 16), lst = (int)(e & 0xFFFFu);
+                const int32_t r0 = s_off[si];
+                const int ln = s_off[si + 1] - r0;
+                const int f = span_backward(sp, R, FetchShared{tile_addr + (uint32_t)r0}, ln, lst);
+                s_res[si] = f > 0 ? make_int2(f, lst < ln ? lst : ln) : make_int2(0, 0);
+            }
+        }
+        __syncwarp();
+        // ---- results, coalesced ----
+        for (int i = lane; i < count; i += 32) {
+            const int2 r = s_res[i];
+            if (r.x >= 0) { from[first + i] = r.x; to[first + i] = r.y; }
         }
     }
 }
@@ -1686,10 +1806,25 @@ __device__ inline bool continuation_is_boundary(const uint8_t* __restrict__ s, i
 // One candidate start (text index pos, first byte b): boundary check, then the anchored attempt, reading the text
 // from global memory.  `open_end`: the window is followed by more text that this GPU does not hold; an attempt
 // that is still alive at the window end cannot be decided here and is reported through *overflow.
+// Work budget of a scan (K4): the attempts count their byte steps; when their sum passes `limit` the scan gives up
+// (*abort = 1, every warp leaves) and the linear-time state-map scan (K5) answers instead.  limit == 0: no budget.
+struct ScanBudget {
+    unsigned long long* work;    // steps so far (all warps)
+    unsigned long long* abort;   // set once the budget is spent
+    unsigned long long limit;
+};
+static constexpr int BUDGET_TICK = 4096;
+__device__ __forceinline__ bool budget_spent(const ScanBudget& B, unsigned long long steps) {
+    if (B.limit == 0) return false;
+    const unsigned long long before = atomicAdd(B.work, steps);
+    if (before + steps > B.limit) { *reinterpret_cast<volatile unsigned long long*>(B.abort) = 1ull; return true; }
+    return *reinterpret_cast<volatile unsigned long long*>(B.abort) != 0;
+}
+
 template <int KIND>
 __device__ __forceinline__ bool try_start(const KParams& p, const Table<KIND>& T, const uint8_t* __restrict__ buf,
                                           int64_t len, int64_t pos, uint32_t b, bool open_end,
-                                          unsigned long long* overflow) {
+                                          unsigned long long* overflow, const ScanBudget& B, uint32_t& acc) {
     if ((b & 0xC0) == 0x80 && !continuation_is_boundary(buf, len, pos)) return false;
     const Anchored A{p.flags, p.start_nul, p.q0};
     // The plain stretch first: as long as the next state neither accepts nor enters a multi-byte sequence, a step is
@@ -1697,12 +1832,42 @@ __device__ __forceinline__ bool try_start(const KParams& p, const Table<KIND>& T
     // general loop, from the state and position reached (no accept has been seen so far).
     uint32_t st = (uint32_t)p.q0;
     int64_t at = pos;
-    while (at < len) {
-        const uint32_t nw = T.next(st, __ldg(buf + at));
-        if (nw & (W_ACC | W_INTER)) break;
-        if (nw == 0) return false;
-        st = nw;
-        at++;
+    for (;;) {
+        int64_t stop = at + BUDGET_TICK < len ? at + BUDGET_TICK : len;
+        const int64_t from = at;
+        bool out = false;
+        while (at < stop) {
+            const uint32_t nw = T.next(st, __ldg(buf + at));
+            if (nw & (W_ACC | W_INTER)) { out = true; break; }
+            if (nw == 0) { acc += (uint32_t)(at - from); return false; }
+            st = nw;
+            at++;
+        }
+        acc += (uint32_t)(at - from);
+        if (acc >= BUDGET_TICK) { const uint32_t a = acc; acc = 0; if (budget_spent(B, a)) return false; }
+        if (out || at >= len) break;
+    }
+    if (B.limit != 0) {          // a budgeted scan: the general loop in ticks as well (it is the rare part of an attempt)
+        uint32_t w = st;
+        int64_t seq = 0, last = -1;
+        bool inter = false;
+        for (int64_t j = at; j <= len; j++) {
+            if (((j - at) & (BUDGET_TICK - 1)) == BUDGET_TICK - 1 && budget_spent(B, BUDGET_TICK)) return false;
+            if (j == len && open_end) { if (last >= 0) return true; atomicAdd(overflow, 1ull); return false; }
+            const uint32_t c = j < len ? __ldg(buf + j) : 0u;
+            if (inter && (c & 0xC0) != 0x80) {
+                const uint32_t f = __ldg(A.flags + (w & W_STATE));
+                for (int k = 1; k <= (int)(j - seq); k++) if (f & (SF_FAILACC1 << (k - 1))) last = seq + k;
+                inter = false;
+            }
+            const uint32_t nw = T.next(w & W_STATE, c);
+            if ((nw & W_INTER) && !inter) seq = j;
+            inter = (nw & W_INTER) != 0;
+            w = nw;
+            if (w & W_ACC) last = j + 1;
+            if ((w & W_STATE) == 0) break;
+        }
+        return last >= 0;
     }
     if (!open_end) return run_attempt(A, T, FetchGlobal{buf}, len, st, at, -1) >= 0;
     // open end: walk only the bytes we have; alive at the end -> undecided
@@ -1749,8 +1914,12 @@ __host__ __device__ __forceinline__ int scan_smem_bytes(int table_smem_bytes) {
 template <int KIND>
 __global__ void __launch_bounds__(256) k_buffer_scan(KParams p, const uint8_t* __restrict__ buf, ScanWindow W,
                                                      unsigned long long* __restrict__ best, int table_smem_bytes,
-                                                     const unsigned long long* __restrict__ gate) {
+                                                     const unsigned long long* __restrict__ gate,
+                                                     const unsigned long long* __restrict__ run_if) {
     if (gate != nullptr && *gate != 0) return;      // the prefix occurs in the text: its occurrences were the candidates
+    if (run_if != nullptr && *run_if == 0) return;  // fallback behind the state-map scan: only if that scan declined
+    const ScanBudget B{nullptr, nullptr, 0ull};
+    uint32_t acc = 0;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_cmap = smem;
     uint8_t* s_table = smem + 256;
@@ -1784,7 +1953,7 @@ __global__ void __launch_bounds__(256) k_buffer_scan(KParams p, const uint8_t* _
         __syncwarp();
         if (lane < count) {
             const int64_t pos = queue[lane];
-            if (try_start(p, T, buf, len, pos, __ldg(buf + pos), open_end, overflow))
+            if (try_start(p, T, buf, len, pos, __ldg(buf + pos), open_end, overflow, B, acc))
                 atomicMin(best, (unsigned long long)(W.origin + pos) + 2);
         }
         __syncwarp();
@@ -1896,8 +2065,11 @@ __host__ __device__ __forceinline__ int scan_sparse_smem_bytes(int table_smem_by
 template <int KIND, int NR, bool HIGH, bool PREFIX>
 __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparseParams sp, const uint8_t* __restrict__ buf,
                                                             ScanWindow W, unsigned long long* __restrict__ best,
-                                                            int table_smem_bytes, const unsigned long long* __restrict__ gate) {
+                                                            int table_smem_bytes, const unsigned long long* __restrict__ gate,
+                                                            int phases, const unsigned long long* __restrict__ run_if, ScanBudget B) {
     if (gate != nullptr && *gate != 0) return;      // (plain scan of a prefix pattern) the prefix occurs in the text
+    if (run_if != nullptr && *run_if == 0) return;  // fallback behind the state-map scan: only if that scan declined
+    uint32_t acc = 0;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_cmap = smem;
     uint8_t* s_table = smem + 256;
@@ -1932,9 +2104,9 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
 
     auto run_starts = [&](int count) {
         __syncwarp();
-        if (lane < count) {
+        if (lane < count && (phases & 2)) {
             const int64_t pos = s_starts[lane];
-            if (try_start(p, T, buf, len, pos, __ldg(buf + pos), open_end, overflow))
+            if (try_start(p, T, buf, len, pos, __ldg(buf + pos), open_end, overflow, B, acc))
                 atomicMin(best, (unsigned long long)(W.origin + pos) + 2);
         }
         __syncwarp();
@@ -1943,7 +2115,7 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
         __syncwarp();
         uint32_t cand = 0;
         int64_t P = 0;
-        if (lane < count) {
+        if (lane < count && (phases & 1)) {
             const int64_t u = s_units[lane];
             const uintptr_t ua = ubase + ((uintptr_t)u << 5);
             const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(ua)), v1 = __ldg(reinterpret_cast<const uint4*>(ua + 16));
@@ -2002,6 +2174,11 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
         if (lane == 0) cur = *reinterpret_cast<volatile unsigned long long*>(best);
         cur = __shfl_sync(FULL, cur, 0);
         if (cur != NO_START && (unsigned long long)(W.origin + pos_base + (g0 << 5)) + 2 > cur) break;   // behind the winner
+        if (B.limit != 0) {                                  // budget spent somewhere: this scan is over
+            unsigned long long ab = 0;
+            if (lane == 0) ab = *reinterpret_cast<volatile unsigned long long*>(B.abort);
+            if (__shfl_sync(FULL, ab, 0) != 0) return;
+        }
         uint4 va[4], vb[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -2030,6 +2207,383 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
     }
     if (uqn > 0) run_units(uqn);
     if (sqn > 0) run_starts(sqn);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: one long buffer in LINEAR time -- the chunked state-map scan.
+// K4 above runs the reference's own loop (one anchored attempt per candidate start) in parallel; its work is the sum of
+// the attempt lengths, which is unbounded on text whose attempts run long ([a].*b over a megabyte of `a`).  K5 walks the
+// text ONCE with the forward "ordered groups" automaton of the span path (fx_automata.cpp build_span_forward): the last
+// position at which that automaton holds the exit is the end of Forgex's leftmost-longest match.  A DFA walk is a
+// prefix computation over state maps, so it parallelises:
+//   sub-chunks   a lane walks SUB bytes from a small CANDIDATE set of states that provably holds the state the true walk
+//                arrives in: the image of ALL reachable states under the byte in front of the sub-chunk (host table
+//                `img`, at most 4 live states for most bytes; one more byte back when that byte's image is wide).
+//                Candidates that reach the same state merge (checked every 16 bytes); after a few bytes one trajectory
+//                is left.  Result: a map candidate -> (end state, last accept).  An accept while candidates still
+//                differ, or a byte context whose image is wide, makes the map "unknown";
+//   chain        the 32 lanes of a warp chain their maps in text order (maps are broadcast through shared memory);
+//                the warp carries up to 32 chain states side by side -- the region's own candidates -- and a chain
+//                state that meets an unknown map simply walks that sub-chunk itself (all lanes in parallel);
+//   regions      a warp owns a contiguous region (many segments of 32 sub-chunks).  Its candidates come from a full
+//                enumeration: every reachable state is walked over the 64 bytes in front of the region and the
+//                distinct survivors (<= 32, else the scan declines) are the keys of the region's map;
+//   compose      one warp applies the region maps in order, starting from the automaton's start state
+//                (k_statemap_compose).  No text is read twice, nothing is quadratic.
+// The start of the match comes from one backward walk of the reverse automaton (k_buffer_finish_span).
+// Model + proof by fuzz of the candidate argument: tests/table_model.py StateMapScan.
+// ---------------------------------------------------------------------------------------------
+static constexpr int SM_SUB = 512;               // bytes per lane and segment
+static constexpr int SM_M = 4;                   // candidates per sub-chunk
+static constexpr int SM_LOOKBACK = 64;           // bytes in front of a region over which every reachable state is walked
+static constexpr int SM_WARPS = 16;
+struct StateMapParams {
+    const uint16_t* reach;      // reachable live states of the forward automaton
+    const uint16_t* img;        // 256 x (1 + SM_M): count (0xFFFF = more than SM_M) then the live image states of the byte
+    int nreach;
+    int64_t region_bytes;       // multiple of 32 * SM_SUB
+    int64_t nregions;
+    uint16_t* rc;               // nregions x 32: region candidates (0xFFFF = unused lane; all 0xFFFF = the region declined)
+    uint16_t* re;               // nregions x 32: end state per candidate
+    long long* rl;              // nregions x 32: last accept (text position, -1 none) per candidate
+    long long* result;          // [0] = last accept of the whole text (-1 none), [1] = status (0 ok, 1 declined)
+};
+
+// one forward step on 64-bit positions
+#define FX_SM_STEP(T, st, last, b, jj)                                            \
+    {                                                                             \
+        const uint32_t nw_ = (T).next((st), (b));                                 \
+        if (nw_ & 0xB000u) {                                                      \
+            if (nw_ & W_RA) (last) = (jj) + 1 - (long long)((nw_ >> 12) & 3u);    \
+            if (nw_ & W_ACC) (last) = (jj) + 1;                                   \
+        }                                                                         \
+        (st) = nw_ & W_SSTATE;                                                    \
+    }
+
+// a lane's map for one sub-chunk, as it sits in shared memory
+struct SubMap {
+    uint16_t cand[SM_M];
+    uint16_t end[SM_M];
+    int32_t last;               // position relative to the sub-chunk's first byte (may be -2..SM_SUB), INT32_MIN = none
+    uint16_t owner_mask;        // candidates that follow the trajectory the accepts belong to
+    uint8_t ncand;              // 0xFF = unknown: whoever arrives walks the sub-chunk
+    uint8_t pad;
+};
+
+template <int FK>
+__global__ void __launch_bounds__(SM_WARPS * 32, 2) k_statemap_regions(SpanParams sp, StateMapParams mp,
+                                                                      const uint8_t* __restrict__ buf, int64_t len, int fwd_bytes,
+                                                                      const unsigned long long* __restrict__ run_if) {
+    if (run_if != nullptr && *run_if == 0) return;            // the budgeted candidate scan has answered
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t FULL = 0xffffffffu;
+    SpanFwd<FK> T;
+    T.s_cmap = smem_u32(smem); T.s_table = smem_u32(smem + 256); T.g_table = sp.table; T.g_cmap = sp.classmap; T.shift = sp.row_shift;
+    if (FK == 0) {
+        uint16_t* dst = reinterpret_cast<uint16_t*>(smem + 256);
+        for (int i = threadIdx.x; i < sp.nstates * 128; i += blockDim.x) {
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(sp.direct) + i);
+            *reinterpret_cast<uint32_t*>(dst + (i >> 7) * SPAN_ROW + ((i & 127) << 1)) = v;
+        }
+    } else if (FK == 1) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem + 256);
+        const int words32 = ((sp.nstates << sp.row_shift) + 1) >> 1;
+        for (int i = threadIdx.x; i < words32; i += blockDim.x) dst[i] = __ldg(reinterpret_cast<const uint32_t*>(sp.table) + i);
+        for (int i = threadIdx.x; i < 64; i += blockDim.x)
+            reinterpret_cast<uint32_t*>(smem)[i] = __ldg(reinterpret_cast<const uint32_t*>(sp.classmap) + i);
+    }
+    const int head = (256 + fwd_bytes + 15) & ~15;
+    uint16_t* s_img = reinterpret_cast<uint16_t*>(smem + head);                          // 256 x 5 x u16
+    for (int i = threadIdx.x; i < 256 * (1 + SM_M); i += blockDim.x) s_img[i] = __ldg(mp.img + i);
+    SubMap* s_maps = reinterpret_cast<SubMap*>(smem + head + 256 * (1 + SM_M) * 2) + warp * 32;
+    uint16_t* s_rc = reinterpret_cast<uint16_t*>(smem + head + 256 * (1 + SM_M) * 2 + SM_WARPS * 32 * sizeof(SubMap)) + warp * 32;
+    __syncthreads();
+    const uintptr_t gbuf = reinterpret_cast<uintptr_t>(buf);
+    const int64_t shift = (int64_t)(gbuf & 15);          // sub-chunk k covers text [k * SUB - shift, (k+1) * SUB - shift): 16-byte aligned ADDRESSES
+    const int64_t gwarp = (int64_t)blockIdx.x * SM_WARPS + warp, nwarps = (int64_t)gridDim.x * SM_WARPS;
+    for (int64_t reg = gwarp; reg < mp.nregions; reg += nwarps) {
+        const int64_t r0 = reg == 0 ? 0 : reg * mp.region_bytes - shift;
+        int64_t r1 = (reg + 1) * mp.region_bytes - shift;
+        if (r1 > len) r1 = len;
+        // ---- region candidates: every reachable state walked over the look-back window, distinct survivors ----
+        int cnt = 0;
+        bool wide = false;
+        __syncwarp();
+        if (r0 == 0) {
+            if (lane == 0) s_rc[0] = (uint16_t)sp.start;
+            cnt = 1;
+        } else {
+            const int64_t w0 = r0 > SM_LOOKBACK ? r0 - SM_LOOKBACK : 0;
+            for (int k = 0; k < mp.nreach && !wide; k += 32) {
+                uint32_t st = k + lane < mp.nreach ? (uint32_t)__ldg(mp.reach + k + lane) : 0u;
+                for (int64_t j = w0; j < r0; j++) st = T.next(st, (uint32_t)__ldg(buf + j)) & W_SSTATE;
+                const uint32_t peers = __match_any_sync(FULL, st);
+                bool isnew = st != 0 && (__ffs(peers) - 1) == lane;
+                for (int i = 0; i < cnt; i++) if (s_rc[i] == st) isnew = false;
+                const uint32_t m = __ballot_sync(FULL, isnew);
+                if (cnt + __popc(m) > 32) { wide = true; break; }
+                if (isnew) s_rc[cnt + __popc(m & ((1u << lane) - 1))] = (uint16_t)st;
+                cnt += __popc(m);
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+        if (wide) {                                          // the scan declines: too many states can arrive here
+            mp.rc[reg * 32 + lane] = 0xFFFFu; mp.re[reg * 32 + lane] = 0; mp.rl[reg * 32 + lane] = -1;
+            continue;
+        }
+        const uint32_t mycand = lane < cnt ? (uint32_t)s_rc[lane] : 0u;
+        uint32_t c = mycand;                                 // this lane's chain state
+        long long L = -1;                                    // its last accept
+        // ---- segments of 32 sub-chunks ----
+        for (int64_t seg = r0; seg < r1; ) {
+            // sub-chunk bounds: the first of the text is short by `shift` bytes so that the others start on 16-byte addresses
+            const int64_t k0 = (seg + shift) / SM_SUB;                       // index of the segment's first sub-chunk
+            const int64_t kb = k0 + lane;
+            int64_t b = kb * SM_SUB - shift, e = b + SM_SUB;
+            if (b < seg) b = seg;
+            if (e > r1) e = r1;
+            const int64_t seg_end = (k0 + 32) * SM_SUB - shift < r1 ? (k0 + 32) * SM_SUB - shift : r1;
+            SubMap mine;
+            mine.ncand = 0; mine.last = INT32_MIN; mine.owner_mask = 0; mine.pad = 0;
+#pragma unroll
+            for (int k = 0; k < SM_M; k++) { mine.cand[k] = 0; mine.end[k] = 0; }
+            if (b < e) {
+                // ---- candidates ----
+                uint32_t st[SM_M] = {0, 0, 0, 0};
+                int nc = 0;
+                bool unknown = false;
+                if (b == 0) { st[0] = (uint32_t)sp.start; nc = 1; }
+                else {
+                    const uint32_t c1 = __ldg(buf + b - 1);
+                    const uint32_t n1 = s_img[c1 * (1 + SM_M)];
+                    if (n1 <= SM_M) {
+                        nc = (int)n1;
+#pragma unroll
+                        for (int k = 0; k < SM_M; k++) if (k < nc) st[k] = s_img[c1 * (1 + SM_M) + 1 + k];
+                    } else if (b >= 2) {
+                        const uint32_t c2 = __ldg(buf + b - 2);
+                        const uint32_t n2 = s_img[c2 * (1 + SM_M)];
+                        if (n2 <= SM_M) {
+#pragma unroll
+                            for (int k = 0; k < SM_M; k++) {
+                                if (k < (int)n2) {
+                                    const uint32_t v = T.next((uint32_t)s_img[c2 * (1 + SM_M) + 1 + k], c1) & W_SSTATE;
+                                    bool dup = v == 0;
+#pragma unroll
+                                    for (int q = 0; q < SM_M; q++) if (q < nc && st[q] == v) dup = true;
+                                    if (!dup) {
+#pragma unroll
+                                        for (int q = 0; q < SM_M; q++) if (q == nc) st[q] = v;
+                                        nc++;
+                                    }
+                                }
+                            }
+                        } else unknown = true;
+                    } else unknown = true;
+                }
+                if (unknown) mine.ncand = 0xFF;
+                else {
+                    mine.ncand = (uint8_t)nc;
+#pragma unroll
+                    for (int k = 0; k < SM_M; k++) mine.cand[k] = (uint16_t)st[k];
+                    // ---- walk: all candidates until they have merged, 16 bytes between merge checks ----
+                    uint32_t active = 0, root = 0x3210u;     // bit k: candidate k is walked; nibble k of root: whom k follows
+#pragma unroll
+                    for (int k = 0; k < SM_M; k++) if (k < nc && st[k] != 0) active |= 1u << k;
+                    long long last = -1;
+                    int owner = -1;
+                    bool complex = false;
+                    int64_t j = b;
+                    while (j < e && active != 0 && !complex) {
+                        int nb = (int)(e - j < 16 ? e - j : 16);
+                        const uintptr_t ga = gbuf + (uintptr_t)j;
+                        uint32_t w[4];
+                        if ((ga & 15) == 0 && nb == 16) {
+                            const uint4 v = __ldg(reinterpret_cast<const uint4*>(ga));
+                            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+                        } else {                             // the first block of the text / the last of the region: bytes
+                            const int room = (int)(16 - (ga & 15));
+                            if (nb > room) nb = room;
+                            w[0] = w[1] = w[2] = w[3] = 0;
+                            for (int i = 0; i < nb; i++) w[i >> 2] |= (uint32_t)__ldg(buf + j + i) << (8 * (i & 3));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            if (i < nb) {
+                                const uint32_t byte = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+#pragma unroll
+                                for (int k = 0; k < SM_M; k++) {
+                                    if (active & (1u << k)) {
+                                        const uint32_t nw = T.next(st[k], byte);
+                                        if (nw & 0xB000u) {
+                                            if (active & (active - 1)) complex = true;       // an accept while trajectories still differ
+                                            owner = k;
+                                            if (nw & W_RA) last = j + i + 1 - (long long)((nw >> 12) & 3u);
+                                            if (nw & W_ACC) last = j + i + 1;
+                                        }
+                                        st[k] = nw & W_SSTATE;
+                                        if (st[k] == 0) active &= ~(1u << k);
+                                    }
+                                }
+                            }
+                        }
+                        j += nb;
+                        if (active & (active - 1)) {          // merge check
+#pragma unroll
+                            for (int k = 1; k < SM_M; k++) {
+#pragma unroll
+                                for (int m = 0; m < k; m++) {
+                                    if ((active & (1u << k)) && (active & (1u << m)) && st[k] == st[m]) {
+                                        active &= ~(1u << k);
+#pragma unroll
+                                        for (int q = 0; q < SM_M; q++)
+                                            if (((root >> (4 * q)) & 15u) == (uint32_t)k) root = (root & ~(15u << (4 * q))) | ((uint32_t)m << (4 * q));
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (complex) mine.ncand = 0xFF;
+                    else {
+                        uint32_t om = 0;
+#pragma unroll
+                        for (int k = 0; k < SM_M; k++) {
+                            const uint32_t r = (root >> (4 * k)) & 15u;
+                            uint32_t es = 0;
+#pragma unroll
+                            for (int q = 0; q < SM_M; q++) if (q == (int)r) es = st[q];
+                            mine.end[k] = (uint16_t)es;
+                            if ((int)r == owner) om |= 1u << k;
+                        }
+                        mine.owner_mask = (uint16_t)om;
+                        mine.last = last >= 0 ? (int32_t)(last - b) : INT32_MIN;
+                    }
+                }
+            }
+            s_maps[lane] = mine;
+            __syncwarp();
+            // ---- chain the 32 maps in text order; every lane carries its own chain state ----
+            const int nsub = (int)((seg_end - (k0 * SM_SUB - shift) + SM_SUB - 1) / SM_SUB);
+            for (int t = 0; t < nsub && t < 32; t++) {
+                const SubMap m = s_maps[t];
+                int64_t tb = (k0 + t) * SM_SUB - shift, te = tb + SM_SUB;
+                if (tb < seg) tb = seg;
+                if (te > r1) te = r1;
+                if (tb >= te) continue;
+                bool need = false;
+                if (c != 0) {
+                    int hit = -1;
+                    if (m.ncand != 0xFF) {
+#pragma unroll
+                        for (int k = 0; k < SM_M; k++) if (k < m.ncand && m.cand[k] == c) hit = k;
+                    }
+                    if (hit >= 0) {
+                        c = m.end[hit];
+                        if (m.last != INT32_MIN && ((m.owner_mask >> hit) & 1u)) L = tb + m.last;
+                    } else need = true;
+                }
+                if (__any_sync(FULL, need)) {                 // unknown map (or, never, a missing key): walk the sub-chunk
+                    if (need) for (int64_t j = tb; j < te && c != 0; j++) { const uint32_t byte = __ldg(buf + j); FX_SM_STEP(T, c, L, byte, j); }
+                }
+            }
+            __syncwarp();
+            seg = seg_end;
+        }
+        mp.rc[reg * 32 + lane] = lane < cnt ? (uint16_t)mycand : (uint16_t)0xFFFFu;
+        mp.re[reg * 32 + lane] = (uint16_t)c;
+        mp.rl[reg * 32 + lane] = L;
+    }
+}
+
+// one warp: apply the region maps in order
+__global__ void __launch_bounds__(32) k_statemap_compose(SpanParams sp, StateMapParams mp, int64_t len,
+                                                         const unsigned long long* __restrict__ run_if) {
+    if (run_if != nullptr && *run_if == 0) return;
+    const int lane = threadIdx.x;
+    const uint32_t FULL = 0xffffffffu;
+    uint32_t s = (uint32_t)sp.start;
+    long long L = sp.start_acc ? 0 : -1;
+    int status = 0;
+    for (int64_t r = 0; r < mp.nregions && s != 0; r++) {
+        const uint32_t key = mp.rc[r * 32 + lane];
+        const uint32_t end = mp.re[r * 32 + lane];
+        const long long l = mp.rl[r * 32 + lane];
+        const uint32_t m = __ballot_sync(FULL, key == s);
+        if (m == 0) { status = 1; break; }                    // the region declined (or does not know s): no answer from this scan
+        const int src = __ffs(m) - 1;
+        s = __shfl_sync(FULL, end, src);
+        const long long ll = __shfl_sync(FULL, l, src);
+        if (ll >= 0) L = ll;
+    }
+    if (status == 0 && s != 0) {                              // end of the text: pending bytes replay, the trailing NUL is consumed
+        const uint32_t e = __ldg(sp.endinfo + s);
+        if (e & 3u) L = len + 1 - (long long)(e & 3u);
+        if (e & 4u) L = len + 1;
+    }
+    if (lane == 0) { mp.result[0] = status == 0 ? L : -1; mp.result[1] = status; }
+}
+
+// backward half on 64-bit positions (one thread): the leftmost start of the match that ends at `last`
+__device__ inline long long span_backward64(const SpanParams& sp, const uint8_t* __restrict__ buf, long long len, long long last) {
+    SpanRev<false> R;
+    R.s_delta = R.s_page = R.s_mixed = 0;
+    uint32_t r = (uint32_t)sp.rstart;
+    long long pos = last;
+    if (last > len) { r = R.delta(sp, r, (uint32_t)sp.nul_class) & 0x7FFFu; pos = len; }
+    long long best = -2;
+    while (r != 0 && pos > 0) {
+        uint32_t c = __ldg(buf + pos - 1);
+        long long q = pos - 1;
+        uint32_t cp = c;
+        if (c >= 0x80u) {
+            cp = 0xFFFFu;
+            if ((c & 0xC0u) == 0x80u && pos >= 2) {
+                const uint32_t d1 = __ldg(buf + pos - 2);
+                if ((d1 & 0xE0u) == 0xC0u) { cp = ((d1 & 0x1Fu) << 6) | (c & 0x3Fu); q = pos - 2; }
+                else if ((d1 & 0xC0u) == 0x80u && pos >= 3) {
+                    const uint32_t d2 = __ldg(buf + pos - 3);
+                    if ((d2 & 0xF0u) == 0xE0u) { cp = ((d2 & 0x0Fu) << 12) | ((d1 & 0x3Fu) << 6) | (c & 0x3Fu); q = pos - 3; }
+                    else if ((d2 & 0xC0u) == 0x80u && pos >= 4) {
+                        const uint32_t d3 = __ldg(buf + pos - 4);
+                        if ((d3 & 0xF8u) == 0xF0u) {
+                            cp = ((d3 & 0x07u) << 18) | ((d2 & 0x3Fu) << 12) | ((d1 & 0x3Fu) << 6) | (c & 0x3Fu);
+                            q = pos - 4;
+                        }
+                    }
+                }
+            }
+        }
+        const uint32_t w = R.delta(sp, r, R.cls(sp, cp));
+        r = w & 0x7FFFu;
+        if (r == 0) break;
+        pos = q;
+        if (w & 0x8000u) best = pos;
+    }
+    if (r != 0 && pos == 0) {
+        const uint32_t w = R.delta(sp, r, (uint32_t)sp.nul_class);
+        if ((w & 0x7FFFu) != 0 && (w & 0x8000u)) best = -1;
+    }
+    if (best == -2) return 0;
+    return best < 0 ? 1 : best + 1;
+}
+
+// finish of the state-map scan: (from, to) from the end position the compose step found.  `done`: set to 1 when this
+// kernel has produced the answer (the fallback scan behind it is then skipped).
+__global__ void k_buffer_finish_span(SpanParams sp, const uint8_t* __restrict__ buf, int64_t len, const long long* __restrict__ result,
+                                     int64_t* __restrict__ from_to, unsigned long long* __restrict__ done,
+                                     unsigned long long* __restrict__ declined, const unsigned long long* __restrict__ run_if) {
+    if (run_if != nullptr && *run_if == 0) return;
+    if (result[1] != 0) { *declined = 1; return; }           // the scan declined: the candidate scan runs again, unbudgeted
+    const long long last = result[0];
+    long long from = 0, to = 0;
+    if (!(len == 0 || (len == 1 && __ldg(buf) == 0x20)) && last > 0) {        // api_internal_m.F90:68-74; to = 0 is "no match"
+        const long long f = span_backward64(sp, buf, len, last);
+        if (f > 0) { from = f; to = last < len ? last : len; }
+    }
+    from_to[0] = from; from_to[1] = to;
+    *done = 1;
 }
 
 // K4L: a pattern that is ONE literal (`all` is not blank).  The reference never consults the automaton for it:
@@ -2091,7 +2645,11 @@ __global__ void __launch_bounds__(256) k_buffer_literal(KParams p, SparseParams 
 // second step: longest end for the winning start; also the literal / degenerate cases.  `key` is the winning
 // start as an S position of the whole text; the window must hold the text from that start to the end of its match.
 __global__ void k_buffer_finish(KParams p, const uint8_t* __restrict__ buf, ScanWindow W,
-                                const unsigned long long* __restrict__ best, int64_t* __restrict__ from_to, int whole_text) {
+                                const unsigned long long* __restrict__ best, int64_t* __restrict__ from_to, int whole_text,
+                                const unsigned long long* __restrict__ done, const unsigned long long* __restrict__ use_alt,
+                                const unsigned long long* __restrict__ best_alt) {
+    if (done != nullptr && *done != 0) return;              // the state-map scan has answered
+    if (use_alt != nullptr && *use_alt != 0) best = best_alt;   // the budgeted scan gave up and the state-map scan declined: the re-run's result
     Table<3> T;
     T.g_table = p.ctable; T.g_cmap = p.classmap; T.shift = p.c_row_shift; T.s_table = 0; T.s_cmap = 0;
     FetchGlobal fetch{buf};

@@ -95,6 +95,12 @@ typedef struct fx_pattern_info {
     int32_t sparse_used;      /* 1: the last ragged `.in.` launch / buffer scan used the SWAR first-byte sweep */
     int32_t prefix_scan;      /* FX_OP_REGEX with an extracted prefix literal: 1 when the long-buffer path handles it (the
                                  literal has no border and there is no suffix literal); 0: FX_ERR_PREFILTER_UNSUPPORTED */
+    int32_t statemap;         /* FX_OP_REGEX: 1 when the pattern has the linear-time span path (forward "ordered groups"
+                                 automaton + reverse automaton): ragged batches run on it (K3f), and fx_regex_buffer* can
+                                 fall back on the chunked state-map scan (K5) */
+    int32_t statemap_used;    /* last fx_regex_buffer* call: 0 candidate-start scan only; 1 state-map scan; 2 candidate-start
+                                 scan under a work budget with the state-map scan behind it (which of the two answered is
+                                 decided on the device) */
 } fx_pattern_info;
 
 /* ---- host-only ------------------------------------------------------------------------- */
@@ -113,12 +119,15 @@ int fx_pattern_literals(const fx_pattern* p, void* all, void* prefix, void* suff
  * classmap: 256 bytes; flags: byte_states bytes; scalars: {start, start_nul, q0, matched, q0_accepting, result_threshold} */
 int fx_pattern_tables(const fx_pattern* p, const uint16_t** table, const uint16_t** direct,
                       const uint8_t** classmap, const uint8_t** flags, int32_t scalars[6]);
-/* FX_OP_REGEX patterns without prefix prefilter also carry a linear-time span path (tests / tools): the 256-column
- * table of the forward "ordered groups" automaton (scalars = {states, start}), and the reverse automaton over
- * code-point classes (rscalars = {states, classes, start}; cuts: classes+1 ascending code points).  Returns 1 when
- * the pattern has no such path. */
-int fx_pattern_span_tables(const fx_pattern* p, const uint16_t** direct, const uint8_t** flags, int32_t scalars[4],
-                           const uint16_t** rdelta, const uint8_t** rstartok, const int32_t** cuts, int32_t rscalars[4]);
+/* FX_OP_REGEX patterns also carry a linear-time span path (tests / tools): the 256-column table of the forward
+ * "ordered groups" automaton in its span word format (state | RA << 12 | INTER << 14 | ACC << 15, see fx_internal.hpp;
+ * scalars = {states, start, start state accepts, 0}; endinfo: one byte per state), and the reverse automaton over
+ * code-point classes (rdelta: rstates x rclasses words, bit 15 = the destination holds the NFA entry; rpage / rmixed:
+ * two-level class map of the code points below U+10000, NULL when absent; cuts: classes+1 ascending code points;
+ * rscalars = {states, classes, start, mixed pages}).  Returns 1 when the pattern has no such path. */
+int fx_pattern_span_tables(const fx_pattern* p, const uint16_t** direct, const uint8_t** endinfo, int32_t scalars[4],
+                           const uint16_t** rdelta, const uint8_t** rpage, const uint8_t** rmixed, const int32_t** cuts,
+                           int32_t rscalars[4]);
 int fx_is_valid_regex(const void* pattern, int64_t plen, int* status);
 /* is_valid_regex over an array of patterns (it is `pure elemental` in the reference, src/forgex.F90:58-71): patterns as
  * one flat buffer + n+1 ascending offsets; valid[i] = 1/0, status[i] = the SYNTAX_* code of pattern i
@@ -136,7 +145,8 @@ int fx_in_batch_dev(fx_pattern* p, const uint8_t* d_buf, const int64_t* d_offset
 int fx_regex_batch_dev(fx_pattern* p, const uint8_t* d_buf, const int64_t* d_offsets, int64_t n, int64_t total_bytes,
                        int64_t* d_from, int64_t* d_to, void* stream);
 /* one buffer of `len` bytes; d_from_to[0] = from, d_from_to[1] = to (64-bit, 1-based inclusive, 0/0 = none).
- * d_work: device scratch of fx_regex_buffer_work_bytes(len) bytes. */
+ * d_work: device scratch of fx_regex_buffer_work_bytes(len) bytes, 16-byte aligned (flags of the scans and the region
+ * maps of the state-map scan; a few KB for small texts, at most 25 MB). */
 int64_t fx_regex_buffer_work_bytes(int64_t len);
 int fx_regex_buffer_dev(fx_pattern* p, const uint8_t* d_buf, int64_t len, int64_t* d_from_to, void* d_work, void* stream);
 

@@ -315,8 +315,13 @@ class BufferPrefix:
         return (f, t) if f > 0 and t > 0 else (0, 0)
 
 
+W_SSTATE, W_RA = 0x0FFF, 0x3000
+
+
 class SpanLinear:
-    """span_linear_smem (K3f): forward ordered-groups automaton, then the reverse automaton"""
+    """span_linear / k_span_ragged (K3f): forward ordered-groups automaton in its span word format (every event of a
+    step is in the word: ACC, and RA = a broken sequence's replay passed an accept RA-1 bytes back), then the reverse
+    automaton over code-point classes with its two-level class map"""
 
     def __init__(self, pattern_obj):
         self.t = pattern_obj.span_tables()
@@ -324,55 +329,51 @@ class SpanLinear:
         self.cuts = [int(x) for x in self.t["cuts"]]
 
     def cls(self, cp):
+        t = self.t
+        if cp < 0x10000 and t["rpage"] is not None:
+            pg = int(t["rpage"][cp >> 6])
+            c = pg if pg < 0x80 else int(t["rmixed"][((pg & 0x7F) << 6) | (cp & 63)])
+            import bisect
+            assert c == bisect.bisect_right(self.cuts, cp) - 1      # the two-level map equals the binary search
+            return c
         import bisect
         return bisect.bisect_right(self.cuts, cp) - 1
 
-    def regex(self, s: bytes):
+    def forward(self, s: bytes, st=None, last=None, base=0):
+        """walk s from state st; returns (state, last) with positions offset by base (used by the chunked model too)"""
+        direct = self.t["direct"]
+        if st is None:
+            st = self.t["start"]
+            last = 0 if self.t["start_acc"] else -1
+        for j, b in enumerate(s):
+            if st == 0:
+                break
+            nw = int(direct[st, b])
+            if nw & W_RA:
+                last = base + j + 1 - ((nw >> 12) & 3)
+            if nw & W_ACC:
+                last = base + j + 1
+            st = nw & W_SSTATE
+        return st, last
+
+    def end_of_text(self, st, n, last):
+        if st != 0:
+            e = int(self.t["endinfo"][st])
+            if e & 3:
+                last = n + 1 - (e & 3)
+            if e & 4:
+                last = n + 1
+        return last
+
+    def backward(self, s: bytes, last):
         t = self.t
         n = len(s)
-        if n == 0 or s == b" ":
-            return (0, 0)
-        direct, flags = t["direct"], t["flags"]
-        w = t["start"]
-        last = 0 if (flags[t["start"]] & SF_ACC) else -1
-        seq, inter = 0, False
-        j = 0
-        dead = False
-        while j < n:
-            b = s[j]
-            if inter and (b & 0xC0) != 0x80:
-                f = int(flags[w & W_STATE])
-                for k in range(1, j - seq + 1):
-                    if f & (SF_FAILACC1 << (k - 1)):
-                        last = seq + k
-                inter = False
-            nw = int(direct[w & W_STATE, b])
-            if (nw & W_INTER) and not inter:
-                seq = j
-            inter = bool(nw & W_INTER)
-            w = nw
-            if w & W_ACC:
-                last = j + 1
-            if (w & W_STATE) == 0:
-                dead = True
-                break
-            j += 1
-        if not dead:
-            f = int(flags[w & W_STATE])
-            if inter:
-                for k in range(1, n - seq + 1):
-                    if f & (SF_FAILACC1 << (k - 1)):
-                        last = seq + k
-            if f & SF_END:
-                last = n + 1
-        if last <= 0:
-            return (0, 0)
-        rd, ok = t["rdelta"], t["rstartok"]
+        rd = t["rdelta"]
         nul = self.cls(0)
         r = t["rstart"]
         pos = last
         if last > n:
-            r = int(rd[r, nul])
+            r = int(rd[r, nul]) & 0x7FFF
             pos = n
         best = -2
         while r != 0 and pos > 0:
@@ -381,31 +382,191 @@ class SpanLinear:
             cp = c
             if c >= 0x80:
                 cp = 0xFFFF
-                if (c & 0xC0) == 0x80:
-                    acc, shift = c & 0x3F, 6
-                    for back in range(2, 5):
-                        if pos - back < 0:
-                            break
-                        d = s[pos - back]
-                        if (d & 0xC0) == 0x80:
-                            acc |= (d & 0x3F) << shift
-                            shift += 6
-                            continue
-                        nn = 2 if (d >> 5) == 6 else 3 if (d >> 4) == 14 else 4 if (d >> 3) == 30 else 1
-                        if nn == back:
-                            lead = (d & 0x1F) if nn == 2 else (d & 0x0F) if nn == 3 else (d & 0x07)
-                            cp = acc | (lead << shift)
-                            q = pos - back
-                        break
-            r = int(rd[r, self.cls(cp)])
+                if (c & 0xC0) == 0x80 and pos >= 2:
+                    d1 = s[pos - 2]
+                    if (d1 & 0xE0) == 0xC0:
+                        cp, q = ((d1 & 0x1F) << 6) | (c & 0x3F), pos - 2
+                    elif (d1 & 0xC0) == 0x80 and pos >= 3:
+                        d2 = s[pos - 3]
+                        if (d2 & 0xF0) == 0xE0:
+                            cp, q = ((d2 & 0x0F) << 12) | ((d1 & 0x3F) << 6) | (c & 0x3F), pos - 3
+                        elif (d2 & 0xC0) == 0x80 and pos >= 4:
+                            d3 = s[pos - 4]
+                            if (d3 & 0xF8) == 0xF0:
+                                cp, q = ((d3 & 0x07) << 18) | ((d2 & 0x3F) << 12) | ((d1 & 0x3F) << 6) | (c & 0x3F), pos - 4
+            w = int(rd[r, self.cls(cp)])
+            r = w & 0x7FFF
             if r == 0:
                 break
             pos = q
-            if ok[r]:
+            if w & 0x8000:
                 best = pos
         if r != 0 and pos == 0:
-            r = int(rd[r, nul])
-            if r != 0 and ok[r]:
+            w = int(rd[r, nul])
+            if (w & 0x7FFF) != 0 and (w & 0x8000):
                 best = -1
         assert best != -2, "forward and reverse automata disagree"
-        return (1 if best < 0 else best + 1, min(last, n))
+        return 1 if best < 0 else best + 1
+
+    def regex(self, s: bytes):
+        n = len(s)
+        if n == 0 or s == b" ":
+            return (0, 0)
+        st, last = self.forward(s)
+        last = self.end_of_text(st, n, last)
+        if last <= 0:
+            return (0, 0)
+        return (self.backward(s, last), min(last, n))
+
+
+class StateMapScan:
+    """the long-buffer state-map scan (k_statemap_regions + k_statemap_compose): the text is cut into regions, a region
+    into sub-chunks; every sub-chunk is walked from a small CANDIDATE set of states that is guaranteed to hold the true
+    incoming state (the image of ALL reachable states under the byte(s) in front of it), candidates that reach the same
+    state merge, and the per-sub-chunk maps candidate -> (end state, last accept) are chained.  Model of the algorithm,
+    not of the lane layout: sub-chunk and region sizes are parameters so that tiny texts exercise every boundary."""
+
+    M = 4
+
+    def __init__(self, pattern_obj, sub=8, region=40, lookback=6):
+        self.sl = SpanLinear(pattern_obj)
+        t = self.sl.t
+        self.direct = t["direct"]
+        self.sub, self.region, self.lookback = sub, region, lookback
+        st = self.direct & W_SSTATE
+        reach, work = {int(t["start"])}, [int(t["start"])]
+        while work:
+            s = work.pop()
+            for x in set(int(v) for v in st[s]):
+                if x and x not in reach:
+                    reach.add(x)
+                    work.append(x)
+        self.reach = sorted(reach)
+        self.img = []
+        for b in range(256):
+            im = sorted(set(int(v) for v in st[self.reach, b]) - {0})
+            self.img.append(im if len(im) <= self.M else None)
+        self.stats = {"unknown": 0, "complex": 0, "rewalk": 0, "wide_regions": 0}
+
+    def step(self, s, b):
+        return int(self.direct[s, b]) & W_SSTATE
+
+    def candidates(self, text, b):
+        if b == 0:
+            return [int(self.sl.t["start"])]
+        im = self.img[text[b - 1]]
+        if im is not None:
+            return list(im)
+        if b >= 2 and self.img[text[b - 2]] is not None:
+            out = []
+            for s in self.img[text[b - 2]]:
+                n = self.step(s, text[b - 1])
+                if n and n not in out:
+                    out.append(n)
+            return out if len(out) <= self.M else None
+        return None
+
+    def sub_map(self, text, b, e):
+        """candidate -> (end, last) for text[b:e], or None (unknown candidates / an accept while candidates still differ)"""
+        cands = self.candidates(text, b)
+        if cands is None:
+            self.stats["unknown"] += 1
+            return None
+        st = list(cands)
+        root = list(range(len(st)))          # which trajectory a candidate follows
+        active = [s != 0 for s in st]
+        last, owner = None, -1               # an accept is only recorded while ONE trajectory is active: `owner`
+        for j in range(b, e):
+            for k in range(len(st)):
+                if not active[k]:
+                    continue
+                nw = int(self.direct[st[k], text[j]])
+                if nw & (W_RA | W_ACC):
+                    if sum(active) > 1:
+                        self.stats["complex"] += 1
+                        return None
+                    owner = k
+                    if nw & W_RA:
+                        last = j + 1 - ((nw >> 12) & 3)
+                    if nw & W_ACC:
+                        last = j + 1
+                st[k] = nw & W_SSTATE
+                if st[k] == 0:
+                    active[k] = False
+            if (j - b) % 4 == 3:             # merge check at block ends
+                for k in range(len(st)):
+                    for m in range(k):
+                        if active[k] and active[m] and st[k] == st[m]:
+                            active[k] = False
+                            for q in range(len(st)):
+                                if root[q] == k:
+                                    root[q] = m
+        out = {}
+        for k, c in enumerate(cands):
+            r = root[k]
+            out[c] = (st[r], last if r == owner else None)   # the accepts belong to the candidates that follow the owner
+        return out
+
+    def walk(self, text, b, e, s, last):
+        for j in range(b, e):
+            if s == 0:
+                break
+            nw = int(self.direct[s, text[j]])
+            if nw & W_RA:
+                last = j + 1 - ((nw >> 12) & 3)
+            if nw & W_ACC:
+                last = j + 1
+            s = nw & W_SSTATE
+        return s, last
+
+    def region_map(self, text, r0, r1):
+        """region candidates (full enumeration over a look-back window) -> (end, last)"""
+        if r0 == 0:
+            rc = [int(self.sl.t["start"])]
+        else:
+            lb = min(self.lookback, r0)
+            rc = []
+            for s in self.reach:
+                for j in range(r0 - lb, r0):
+                    s = self.step(s, text[j])
+                    if s == 0:
+                        break
+                if s and s not in rc:
+                    rc.append(s)
+            if len(rc) > 32:
+                self.stats["wide_regions"] += 1
+                return None
+        chain = [(c, None) for c in rc]
+        b = r0
+        while b < r1:
+            e = min(b + self.sub, r1)
+            m = self.sub_map(text, b, e)
+            for i, (c, last) in enumerate(chain):
+                if c == 0:
+                    continue
+                if m is not None and c in m:
+                    ne, nl = m[c]
+                    chain[i] = (ne, nl if nl is not None else last)
+                else:
+                    assert m is None, "the candidate set must hold every state that can arrive here"
+                    self.stats["rewalk"] += 1
+                    chain[i] = self.walk(text, b, e, c, last)
+            b = e
+        return {c: chain[i] for i, c in enumerate(rc)}
+
+    def last(self, text: bytes):
+        """end of the leftmost-longest match as the forward walk defines it (None: the scan declined)"""
+        n = len(text)
+        s = int(self.sl.t["start"])
+        last = 0 if self.sl.t["start_acc"] else -1
+        r0 = 0
+        while r0 < n and s != 0:
+            r1 = min(n, r0 + self.region)
+            m = self.region_map(text, r0, r1)
+            if m is None or s not in m:
+                return None
+            s, l = m[s]
+            if l is not None:
+                last = l
+            r0 = r1
+        return self.sl.end_of_text(s, n, last)

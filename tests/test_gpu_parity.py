@@ -599,7 +599,7 @@ def test_c4_buffer_beyond_4_gib():
     expect = (start - (1 if crlf_before else 0), start + len(line))
     p = fx.Pattern(synth.PATTERNS["c4"], "regex")
     ft = torch.zeros(2, dtype=torch.int64, device="cuda")
-    work = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    work = torch.zeros(p.buffer_work_bytes(nbytes), dtype=torch.uint8, device="cuda")
     p.regex_buffer_dev(buf, nbytes, ft, work)
     got = tuple(ft.cpu().tolist())
     assert got == expect and got[0] > (1 << 32), (got, expect)
@@ -614,3 +614,74 @@ def test_c4_buffer_beyond_4_gib():
     buf[start:start + 5] = torch.from_numpy(np.frombuffer(b"WARN ", dtype=np.uint8).copy()).cuda()
     p.regex_buffer_dev(buf, nbytes, ft, work)
     assert tuple(ft.cpu().tolist()) == (0, 0)
+
+
+def test_statemap_scan_against_the_oracle(monkeypatch):
+    """K5, the chunked state-map scan of the long-buffer path, forced for every pattern that has the span path
+    (FX_STATEMAP=2): same spans as the oracle on texts that cross sub-chunk (512 B), segment (16 KB) and region cuts,
+    with multi-byte sequences and invalid bytes on the cuts"""
+    import random
+    from tests.test_host_tables import gen_pattern, gen_text
+    rng = random.Random(4242)
+    nrng = np.random.default_rng(8)
+    pieces = [b"a", b"z", b" ", "あ".encode(), "ん".encode(), "α".encode(), "　".encode(), b"\x80", b"\xc3", b"\xe3\x81", b"\xf0\x9f\x98",
+              b"\xff", b"\xc0\x80", b"\n", b"\r\n", b"_", b"7", b"ERROR", b"timeout=", b"x" * 40, b"foo", b"bar"]
+    texts = []
+    for size in (700, 5000, 40000, 300000):
+        t = b""
+        while len(t) < size:
+            t += pieces[int(nrng.integers(0, len(pieces)))]
+        texts.append(t)
+    texts += [b"\n".join(gen_text(rng) for _ in range(400)), bytes(synth.gen_c4(200000, 0.7)), bytes(synth.gen_c4(70000, None)),
+              b"x" * 100000 + b"ab" + b"y" * 50000, b"", b" ", b"a", b"\xe3\x81\x82" * 30000]
+    pats = [synth.PATTERNS["c4"], synth.PATTERNS["c3"], b"[a-z]+r", rb"\s\S+$", b"[xy]+a[ab]y", rb"[^a]{2,3}$", rb"^\w", b"(a|b)*a(a|b){3}",
+            "[ぁ-ん]+a".encode(), rb"\d+-\d+", b"[ab].*c", b".+", b"^$", b"(|^)a"]
+    pats += [gen_pattern(rng).encode() for _ in range(60)]
+    used = 0
+    for pat in pats:
+        p = fx.Pattern(pat, "regex")
+        if p.status != 0 or not p.info()["statemap"] or p.info()["literal_only"] or p.info()["literal_prefix_len"]:
+            continue
+        c = O.Compiled(pat, 0)
+        for text in texts:
+            if len(text) > 60000 and pat not in pats[:5]:
+                continue                       # (the oracle is quadratic in the worst case: long texts only for tame patterns)
+            arr = np.frombuffer(b"#" + text, dtype=np.uint8)[1:]       # odd address: the sub-chunk grid is address-aligned
+            exp = c.regex_buffer(np.ascontiguousarray(arr))
+            monkeypatch.setenv("FX_STATEMAP", "2")
+            got = p.regex_buffer(arr)
+            assert p.info()["statemap_used"] == (1 if len(text) >= 2 else 0), pat
+            assert got == exp, (pat, len(text), got, exp)
+            monkeypatch.setenv("FX_STATEMAP", "1")
+            assert p.regex_buffer(arr) == exp, (pat, len(text), "default flow")
+        used += 1
+    assert used >= 25, used
+
+
+def test_long_attempts_are_linear_time():
+    """`[ab].*c` over 64 MiB of `a` without a newline: every byte is a candidate start and every attempt runs to the end
+    of the text -- the reference's loop (and K4) is quadratic here.  The work budget stops K4 and the state-map scan
+    answers: no `c`, no match.  With a `c` at the end of 4 MiB the match is the whole text."""
+    import time
+    import torch
+    p = fx.Pattern(b"[ab].*c", "regex")
+    assert p.info()["statemap"] == 1 and p.info()["sparse"] == 1
+    n = 64 << 20
+    buf = torch.full((n,), ord("a"), dtype=torch.uint8, device="cuda")
+    ft = torch.zeros(2, dtype=torch.int64, device="cuda")
+    work = torch.zeros(p.buffer_work_bytes(n), dtype=torch.uint8, device="cuda")
+    p.regex_buffer_dev(buf, n, ft, work)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    p.regex_buffer_dev(buf, n, ft, work)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert tuple(ft.cpu().tolist()) == (0, 0)
+    assert dt < 0.25, "%.3f s for 64 MiB" % dt
+    assert p.info()["statemap_used"] == 2
+    m = 4 << 20
+    buf[m - 1] = ord("c")
+    p.regex_buffer_dev(buf, m, ft, work)
+    assert tuple(ft.cpu().tolist()) == (1, m)
+    small = np.frombuffer(b"a" * 3000 + b"c" + b"a" * 100, dtype=np.uint8)
+    assert p.regex_buffer(small) == O.Compiled(b"[ab].*c", 0).regex_buffer(small) == (1, 3001)
