@@ -21,6 +21,7 @@ SYMBOLS = [
     "fx_match_fixed_dev", "fx_in_fixed_dev", "fx_match_batch_dev", "fx_in_batch_dev", "fx_regex_batch_dev",
     "fx_regex_buffer_work_bytes", "fx_regex_buffer_dev", "fx_buffer_scan_dev", "fx_buffer_scan_all_dev", "fx_buffer_finish_dev",
     "fx_match_fixed", "fx_in_fixed", "fx_match_batch", "fx_in_batch", "fx_regex_batch", "fx_regex_buffer",
+    "fx_regex_count_batch_dev", "fx_regex_buffer_all_dev", "fx_regex_count_batch", "fx_regex_buffer_all",
     "fx_in", "fx_match", "fx_regex", "fx_launch_count",
 ]
 
@@ -77,6 +78,10 @@ def lib():
         getattr(L, name).argtypes = [vp, u8p, vp, i64, u8p]
     L.fx_regex_batch.argtypes = [vp, u8p, vp, i64, vp, vp]
     L.fx_regex_buffer.argtypes = [vp, u8p, i64, C.POINTER(i64), C.POINTER(i64)]
+    L.fx_regex_count_batch_dev.argtypes = [vp, u8p, vp, i64, i64, vp, vp]
+    L.fx_regex_buffer_all_dev.argtypes = [vp, u8p, i64, vp, vp, i64, C.POINTER(i64), vp, vp]
+    L.fx_regex_count_batch.argtypes = [vp, u8p, vp, i64, vp]
+    L.fx_regex_buffer_all.argtypes = [vp, u8p, i64, vp, vp, i64, C.POINTER(i64)]
     L.fx_in.argtypes = [C.c_char_p, i64, C.c_char_p, i64, C.POINTER(C.c_int)]
     L.fx_match.argtypes = [C.c_char_p, i64, C.c_char_p, i64, C.POINTER(C.c_int)]
     L.fx_regex.argtypes = [C.c_char_p, i64, C.c_char_p, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64),

@@ -198,6 +198,25 @@ class Pattern:
         _check(L.lib().fx_regex_buffer(self.h, _ptr(buf), buf.size, C.byref(f), C.byref(t)), "fx_regex_buffer")
         return f.value, t.value
 
+    def regex_count_batch(self, buf, offsets):
+        """matches per string, counted the way a caller loops regex() on text(to+1:)"""
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        counts = np.zeros(n, dtype=np.int64)
+        _check(L.lib().fx_regex_count_batch(self.h, _ptr(buf), _ptr(offsets), n, _ptr(counts)), "fx_regex_count_batch")
+        return counts
+
+    def regex_buffer_all(self, buf, capacity=1 << 20):
+        """every match of the buffer in order: (from[], to[], count); at most `capacity` spans are returned"""
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        f = np.zeros(max(capacity, 1), dtype=np.int64)
+        t = np.zeros(max(capacity, 1), dtype=np.int64)
+        cnt = C.c_int64(0)
+        _check(L.lib().fx_regex_buffer_all(self.h, _ptr(buf), buf.size, _ptr(f), _ptr(t), capacity, C.byref(cnt)), "fx_regex_buffer_all")
+        k = min(cnt.value, capacity)
+        return f[:k], t[:k], cnt.value
+
     # ---- device-resident calls (torch CUDA tensors; nothing is copied; runs on torch's current stream) ----
     @staticmethod
     def _stream():
@@ -235,6 +254,16 @@ class Pattern:
         _check(L.lib().fx_regex_buffer_dev(self.h, _ptr(d_buf), length, _ptr(d_from_to), _ptr(d_work),
                                            self._stream()), "fx_regex_buffer_dev")
 
+
+    def regex_count_batch_dev(self, d_buf, d_offsets, n, total, d_counts):
+        _check(L.lib().fx_regex_count_batch_dev(self.h, _ptr(d_buf), _ptr(d_offsets), n, total, _ptr(d_counts),
+                                                self._stream()), "fx_regex_count_batch_dev")
+
+    def regex_buffer_all_dev(self, d_buf, length, d_from, d_to, capacity, d_work):
+        cnt = C.c_int64(0)
+        _check(L.lib().fx_regex_buffer_all_dev(self.h, _ptr(d_buf), length, _ptr(d_from), _ptr(d_to), capacity, C.byref(cnt),
+                                               _ptr(d_work), self._stream()), "fx_regex_buffer_all_dev")
+        return cnt.value
 
     def buffer_scan_dev(self, d_window, window_len, start_lo, start_hi, origin, is_first, is_last, d_best):
         _check(L.lib().fx_buffer_scan_dev(self.h, _ptr(d_window), window_len, start_lo, start_hi, origin,

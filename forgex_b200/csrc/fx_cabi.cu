@@ -67,6 +67,10 @@ struct FirstSet {
     bool two = false;            // one first byte, and after it one ASCII byte (plus, maybe, lead bytes) keeps the automaton alive
     uint8_t second = 0;
     bool second_high = false;
+    // any first byte of F, and after it at most two ASCII byte values (plus, maybe, lead bytes) keep the automaton alive
+    bool set2 = false;
+    uint8_t set2_a = 0, set2_b = 0;
+    bool set2_high = false;
 };
 
 }  // namespace
@@ -193,6 +197,32 @@ bool sparse_first_set(const fx::ByteTable& at, FirstSet& fs, bool for_in) {
                 else hi2 = true;
             }
             if (nascii == 1 && v2 != 0 && !cont) { fs.two = true; fs.second = (uint8_t)v2; fs.second_high = hi2; }
+        }
+    }
+    // the same for byte SETS (the long-buffer sweep): every first byte steps into a plain state (no accept, no
+    // sequence), and the union of what may follow is at most two ASCII values != NUL, no continuation byte
+    {
+        bool ok = true, follow[256];
+        for (int c = 0; c < 256; c++) follow[c] = false;
+        for (int b1 = 0; b1 < 256 && ok; b1++) {
+            if (!in_f[b1]) continue;
+            const uint16_t w1 = at.table[((size_t)at.q0 << at.row_shift) + at.classmap[b1]];
+            if ((w1 & (fxk::W_ACC | fxk::W_INTER)) != 0 || (w1 & fxk::W_STATE) == 0) { ok = false; break; }
+            for (int c = 0; c < 256; c++) {
+                const uint16_t w2 = at.table[((size_t)(w1 & fxk::W_STATE) << at.row_shift) + at.classmap[c]];
+                if ((w2 & (fxk::W_STATE | fxk::W_ACC)) != 0) follow[c] = true;
+            }
+        }
+        int nascii = 0, v[2] = {0, 0};
+        bool cont = false, hi2 = false;
+        for (int c = 0; c < 256 && ok; c++) {
+            if (!follow[c]) continue;
+            if (c < 0x80) { if (nascii < 2) v[nascii] = c; nascii++; }
+            else if (c < 0xC0) cont = true;
+            else hi2 = true;
+        }
+        if (ok && nascii >= 1 && nascii <= 2 && !cont && v[0] != 0 && (nascii == 1 || v[1] != 0)) {
+            fs.set2 = true; fs.set2_a = (uint8_t)v[0]; fs.set2_b = (uint8_t)(nascii == 2 ? v[1] : v[0]); fs.set2_high = hi2;
         }
     }
     return true;
@@ -566,6 +596,13 @@ void fill_sweep(const FirstSet& f, SparseParams& sp) {
     if (f.sweep_nr == 1 && f.sweep_lo[0] == f.sweep_hi[0]) sp.add_lo[0] = f.sweep_lo[0] * 0x01010101u;   // NR = -1 form
     sp.second = f.second * 0x01010101u;
     sp.second_high = f.second_high ? 0xFFFFFFFFu : 0u;
+    sp.second_b = sp.second;
+}
+// the SET2 form of the long-buffer sweep
+void fill_sweep_set2(const FirstSet& f, SparseParams& sp) {
+    sp.second = f.set2_a * 0x01010101u;
+    sp.second_b = f.set2_b * 0x01010101u;
+    sp.second_high = f.set2_high ? 0x80808080u : 0u;
 }
 
 int launch_sparse(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int64_t* off, int64_t n, int64_t total,
@@ -731,11 +768,11 @@ int launch_scan_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const ScanW
     return cuda_status(cudaGetLastError());
 }
 
-template <int KIND, int NR, bool HIGH, bool PREFIX>
+template <int KIND, int NR, bool HIGH, bool PREFIX, bool SET2 = false>
 int launch_scan_sparse_t(fx_pattern* p, const Plan& pl, const SparseParams& sp, const uint8_t* buf, const ScanWindow& W,
                          unsigned long long* best, cudaStream_t s, const unsigned long long* gate,
                          const unsigned long long* run_if = nullptr, ScanBudget budget = ScanBudget{nullptr, nullptr, 0ull}) {
-    auto kern = k_buffer_scan_sparse<KIND, NR, HIGH, PREFIX>;
+    auto kern = k_buffer_scan_sparse<KIND, NR, HIGH, PREFIX, SET2>;
     int table_smem = (int)staged_bytes(pl);
     size_t smem = (size_t)scan_sparse_smem_bytes(table_smem);
     int bps = 0;
@@ -759,6 +796,14 @@ int launch_scan_sparse(fx_pattern* p, const Plan& pl, const uint8_t* buf, const 
     fill_sweep(p->first, sp);
     const FirstSet& f = p->first;
     const bool one = f.sweep_nr == 1 && f.sweep_lo[0] == f.sweep_hi[0];
+    // (not for a window whose scanned starts reach its open end: the follower of the last start is not in memory)
+    if (f.set2 && !f.high && f.sweep_nr >= 1 && f.sweep_nr <= 2 && (W.last || W.start_hi < W.len) &&
+        env_int("FX_SWEEP_SET2", 1)) {                                                                  // two-byte test for sets
+        fill_sweep_set2(f, sp);
+        if (one) return launch_scan_sparse_t<KIND, -1, false, false, true>(p, pl, sp, buf, W, best, s, gate, run_if, bg);
+        if (f.sweep_nr == 1) return launch_scan_sparse_t<KIND, 1, false, false, true>(p, pl, sp, buf, W, best, s, gate, run_if, bg);
+        return launch_scan_sparse_t<KIND, 2, false, false, true>(p, pl, sp, buf, W, best, s, gate, run_if, bg);
+    }
     if (f.sweep_nr == 0) return launch_scan_sparse_t<KIND, 0, true, false>(p, pl, sp, buf, W, best, s, gate, run_if, bg);
     if (one) return f.high ? launch_scan_sparse_t<KIND, -1, true, false>(p, pl, sp, buf, W, best, s, gate, run_if, bg)
                            : launch_scan_sparse_t<KIND, -1, false, false>(p, pl, sp, buf, W, best, s, gate, run_if, bg);
@@ -1226,6 +1271,72 @@ int fx_buffer_finish_dev(fx_pattern* p, const uint8_t* d_window, int64_t window_
     return launch_finish(p, d_window, W, reinterpret_cast<const unsigned long long*>(d_key), d_from_to, 0, (cudaStream_t)stream);
 }
 
+// ---- all matches / match counts (the loop a caller of regex() writes: match, then regex() again on text(to+1:)) ----
+int fx_regex_count_batch_dev(fx_pattern* p, const uint8_t* d_buf, const int64_t* d_offsets, int64_t n, int64_t total_bytes,
+                             int64_t* d_counts, void* stream) {
+    int rc = check_ready(p, FX_OP_REGEX);
+    if (rc) return rc;
+    if (n < 0 || total_bytes < 0 || !d_counts) return FX_ERR_BAD_ARGUMENT;
+    if (n == 0) return FX_OK;
+    Plan pl;
+    if ((rc = make_plan(p, pl))) return rc;
+    SpanParams sp;
+    memset(&sp, 0, sizeof(sp));
+    long long want = (n + 255) / 256, cap = (long long)p->dev.sm_count * 16;
+    const int grid = (int)(want < cap ? want : cap);
+    if (p->prog.has_span && env_int("FX_SPAN_LINEAR", 1)) {
+        fill_span_params(p, sp);
+        k_regex_count<true><<<grid, 256, 0, (cudaStream_t)stream>>>(pl.kp, sp, d_buf, d_offsets, n, d_counts);
+    } else {
+        k_regex_count<false><<<grid, 256, 0, (cudaStream_t)stream>>>(pl.kp, sp, d_buf, d_offsets, n, d_counts);
+    }
+    g_launches++;
+    return cuda_status(cudaGetLastError());
+}
+
+// One buffer: every match, in order.  d_from / d_to receive the first `capacity` spans (64-bit, 1-based inclusive, in
+// coordinates of the whole buffer); *count (host) = the number of matches, which may exceed capacity.  The search for
+// the next match is the long-buffer search on the rest; short hops are taken on the device, a thousand per launch.
+// Synchronises `stream` (once per far match / per thousand near ones).
+int fx_regex_buffer_all_dev(fx_pattern* p, const uint8_t* d_buf, int64_t len, int64_t* d_from, int64_t* d_to, int64_t capacity,
+                            int64_t* count, void* d_work, void* stream) {
+    int rc = check_ready(p, FX_OP_REGEX);
+    if (rc) return rc;
+    if (len < 0 || capacity < 0 || !count || !d_work || (capacity > 0 && (!d_from || !d_to))) return FX_ERR_BAD_ARGUMENT;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long* work = static_cast<unsigned long long*>(d_work);
+    // the loop's own state sits behind the scans' flags in the work area: words [24..27] state, [28..29] from_to of a far step
+    int64_t* state = reinterpret_cast<int64_t*>(work + 24);
+    int64_t* ft = reinterpret_cast<int64_t*>(work + 28);
+    CUDA_TRY(cudaMemsetAsync(state, 0, 6 * 8, s));
+    Plan pl;
+    if ((rc = make_plan(p, pl))) return rc;
+    SpanParams sp;
+    memset(&sp, 0, sizeof(sp));
+    const bool local = p->prog.has_span && env_int("FX_ALL_LOCAL", 1);
+    if (local) fill_span_params(p, sp);
+    int64_t host_state[4] = {0, 0, 0, 0};
+    for (;;) {
+        if (local) {
+            k_buffer_all_local<<<1, 1, 0, s>>>(pl.kp, sp, d_buf, len, state, d_from, d_to, capacity, 1024, (int64_t)env_int("FX_ALL_REACH", 1 << 16));
+            g_launches++;
+            CUDA_TRY(cudaMemcpyAsync(host_state, state, 32, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+            if (host_state[2]) break;
+            if (!host_state[3]) continue;                   // a thousand near matches taken: go on
+        }
+        const int64_t pos = host_state[0];
+        if ((rc = launch_buffer(p, d_buf + pos, len - pos, ft, work, s))) return rc;
+        k_buffer_all_take<<<1, 1, 0, s>>>(ft, state, d_from, d_to, capacity);
+        g_launches++;
+        CUDA_TRY(cudaMemcpyAsync(host_state, state, 32, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (host_state[2]) break;
+    }
+    *count = host_state[1];
+    return FX_OK;
+}
+
 // ---- host-pointer entry points ----------------------------------------------------------------
 static int host_bool_fixed(fx_pattern* p, int op, const uint8_t* buf, int64_t n, int64_t stride, uint8_t* out) {
     int rc = check_ready(p, op);
@@ -1314,6 +1425,40 @@ int fx_regex_batch(fx_pattern* p, const uint8_t* buf, const int64_t* offsets, in
     CUDA_TRY(cudaMemcpyAsync(from, d.w_span, (size_t)n * 8, cudaMemcpyDeviceToHost, 0));
     CUDA_TRY(cudaMemcpyAsync(to, d.w_span + n, (size_t)n * 8, cudaMemcpyDeviceToHost, 0));
     CUDA_TRY(cudaStreamSynchronize(0));
+    return FX_OK;
+}
+int fx_regex_count_batch(fx_pattern* p, const uint8_t* buf, const int64_t* offsets, int64_t n, int64_t* counts) {
+    int rc = check_ready(p, FX_OP_REGEX);
+    if (rc) return rc;
+    if (n < 0 || !offsets || !counts) return FX_ERR_BAD_ARGUMENT;
+    if (n == 0) return FX_OK;
+    std::lock_guard<std::mutex> lock(p->mu);
+    DeviceTables& d = p->dev;
+    int64_t total = 0;
+    if ((rc = host_stage_ragged(p, buf, offsets, n, total))) return rc;
+    if ((rc = grow(d.w_span, d.w_span_cap, (size_t)n * 8))) return rc;
+    if ((rc = fx_regex_count_batch_dev(p, d.w_buf, d.w_off, n, total, d.w_span, nullptr))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(counts, d.w_span, (size_t)n * 8, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return FX_OK;
+}
+int fx_regex_buffer_all(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* from, int64_t* to, int64_t capacity, int64_t* count) {
+    int rc = check_ready(p, FX_OP_REGEX);
+    if (rc) return rc;
+    if (len < 0 || capacity < 0 || !count) return FX_ERR_BAD_ARGUMENT;
+    std::lock_guard<std::mutex> lock(p->mu);
+    DeviceTables& d = p->dev;
+    if ((rc = grow(d.w_buf, d.w_buf_cap, (size_t)len + 64))) return rc;
+    if ((rc = grow(d.w_span, d.w_span_cap, (size_t)capacity * 16 + 16))) return rc;
+    if ((rc = grow(d.w_work, d.w_work_cap, buffer_work_bytes(len)))) return rc;
+    if (len) CUDA_TRY(cudaMemcpyAsync(d.w_buf, buf, (size_t)len, cudaMemcpyHostToDevice, 0));
+    if ((rc = fx_regex_buffer_all_dev(p, d.w_buf, len, d.w_span, d.w_span + capacity, capacity, count, d.w_work, nullptr))) return rc;
+    const int64_t k = *count < capacity ? *count : capacity;
+    if (k > 0) {
+        CUDA_TRY(cudaMemcpyAsync(from, d.w_span, (size_t)k * 8, cudaMemcpyDeviceToHost, 0));
+        CUDA_TRY(cudaMemcpyAsync(to, d.w_span + capacity, (size_t)k * 8, cudaMemcpyDeviceToHost, 0));
+        CUDA_TRY(cudaStreamSynchronize(0));
+    }
     return FX_OK;
 }
 int fx_regex_buffer(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* from, int64_t* to) {

@@ -72,6 +72,7 @@ __device__ __forceinline__ uint2 ldg_nc_v2(const void* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
     return r;
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -547,37 +548,35 @@ __global__ void __launch_bounds__(256) k_bool_fixed(KParams p, const uint8_t* __
     const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
     if ((VEC == 8 || VEC == 16) && !generic && stride == VEC) {
         // One load covers a whole string (C1: 8 bytes): the walk is 8-16 lookups, short against the latency of the load
-        // in front of it, so a thread takes FOUR CONSECUTIVE strings per step -- all loads first (a warp reads one
-        // contiguous KB), then the four walks, then one 4-byte store of the four results (a warp writes whole lines).
-        constexpr int NW = VEC == 16 ? 4 : 2;          // 32-bit words per string
-        const bool word_out = (reinterpret_cast<uintptr_t>(out) & 3) == 0;
-        const int64_t ngroups = (n + 3) >> 2;
-        for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += gstride) {
-            const int64_t i0 = g << 2;
+        // in front of it, so a thread takes FOUR strings per step -- all loads first, then the four walks.  The four are
+        // a grid stride apart: every load instruction of a warp reads one contiguous run and every store instruction
+        // writes one whole sector.  (Tried: four CONSECUTIVE strings per thread and one 4-byte store -- the loads then
+        // touch each sector four times, DRAM read traffic 1.19x, 338 vs 298 us per GiB.)
+        for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * gstride) {
+            constexpr int NW = VEC == 16 ? 4 : 2;          // 32-bit words per string
             uint32_t w[4][NW];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
+                const int64_t i = i0 + u * gstride;
 #pragma unroll
                 for (int q = 0; q < NW; q++) w[u][q] = 0;
-                if (i0 + u < n) {
-                    if (VEC == 16) { const uint4 v = ldg_nc_v4(buf + (i0 + u) * stride); w[u][0] = v.x; w[u][1] = v.y; w[u][NW - 2] = v.z; w[u][NW - 1] = v.w; }
-                    else { const uint2 v = ldg_nc_v2(buf + (i0 + u) * stride); w[u][0] = v.x; w[u][1] = v.y; }
+                if (i < n) {
+                    if (VEC == 16) { const uint4 v = ldg_nc_v4(buf + i * stride); w[u][0] = v.x; w[u][1] = v.y; w[u][NW - 2] = v.z; w[u][NW - 1] = v.w; }
+                    else { const uint2 v = ldg_nc_v2(buf + i * stride); w[u][0] = v.x; w[u][1] = v.y; }
                 }
             }
-            uint32_t res = 0;
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                if (i0 + u < n) {
+                const int64_t i = i0 + u * gstride;
+                if (i < n) {
                     uint32_t st = (uint32_t)p.start, high = 0;
 #pragma unroll
                     for (int q = 0; q < NW; q++) { high |= w[u][q]; st = step4(T, st, w[u][q]); }
                     bool r = result_flag(p, st);
-                    if (OP == 1 && r && p.prefix_mode == 1 && (high & 0x80808080u)) r = recheck_in_with_prefix(p, buf + (i0 + u) * stride, stride);
-                    res |= (r ? 1u : 0u) << (8 * u);
+                    if (OP == 1 && r && p.prefix_mode == 1 && (high & 0x80808080u)) r = recheck_in_with_prefix(p, buf + i * stride, stride);
+                    out[i] = r ? 1 : 0;
                 }
             }
-            if (word_out && i0 + 3 < n) *reinterpret_cast<uint32_t*>(out + i0) = res;
-            else for (int u = 0; u < 4 && i0 + u < n; u++) out[i0 + u] = (uint8_t)(res >> (8 * u));
         }
         return;
     }
@@ -774,6 +773,7 @@ struct SparseParams {
     uint32_t add_hi[4];         // (0x7F - hi) * 0x01010101: bit 7 of (y + add_hi) <=> y >  hi
     uint32_t second;            // TWO: the one ASCII byte that keeps the automaton alive after the first, in all four bytes
     uint32_t second_high;       // TWO: 0xFFFFFFFF when bytes >= 0xC0 keep it alive as well (lead bytes), else 0
+    uint32_t second_b;          // SET2 (long-buffer sweep): a second possible follower (== second when there is only one)
 };
 
 // shared memory of K2c: classmap 256 | table | pad to 16 | 8 warps x (unit queue 64 x uint4 | start queue 64 x uint4)
@@ -831,6 +831,25 @@ __device__ __forceinline__ uint32_t unit_any(const SparseParams& sp, const uint4
         for (int k = 0; k < 8; k++) any |= first_mask<NR, false>(sp, w[k]);
         if (HIGH) any |= all;
     }
+    return any & 0x80808080u;
+}
+// Sweep filter of the long-buffer scan when the bytes that can FOLLOW a first byte are few (SET2): a unit passes only
+// if some byte of F's ranges is followed by one of (at most two) byte values, or by a lead byte if those can follow --
+// `^ERROR...`: (NUL | LF | CR) followed by `E` or LF.  That is the two-byte test of K2c for byte SETS; it cuts the
+// units that reach the confirm phase from "every line end" to "line ends in front of an E".
+template <int NR, bool HIGH>
+__device__ __forceinline__ uint32_t unit_any_set2(const SparseParams& sp, const uint4& a, const uint4& b) {
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t any = 0, z2_next = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 7; k >= 0; k--) {
+        const uint32_t m1 = first_mask<NR, false>(sp, w[k]);
+        const uint32_t xa = w[k] ^ sp.second, xb = w[k] ^ sp.second_b;
+        const uint32_t z2 = ((xa - 0x01010101u) & ~xa) | ((xb - 0x01010101u) & ~xb) | (w[k] & sp.second_high);
+        any |= m1 & __funnelshift_r(z2, z2_next, 8);          // a first byte at j and a possible follower at j + 1
+        z2_next = z2;
+    }
+    if (HIGH) any |= w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7];
     return any & 0x80808080u;
 }
 // bits 7, 15, 23, 31 of m -> bits 0..3
@@ -1599,7 +1618,7 @@ static constexpr int SPAN_WARPS = 32;
 struct SpanLayout { int off_res, off_queue, off_tile, warp_bytes; };
 __host__ __device__ __forceinline__ SpanLayout span_layout(int spt, int cap) {
     SpanLayout L;
-    L.off_res = 16 + (spt + 4) * 4;
+    L.off_res = (16 + (spt + 4) * 4 + 7) & ~7;          // int2 entries
     L.off_queue = L.off_res + spt * 8;
     L.off_tile = (L.off_queue + spt * 4 + 127) & ~127;
     L.warp_bytes = (L.off_tile + cap + 64 + 127) & ~127;
@@ -1832,11 +1851,16 @@ __device__ __forceinline__ bool try_start(const KParams& p, const Table<KIND>& T
     // general loop, from the state and position reached (no accept has been seen so far).
     uint32_t st = (uint32_t)p.q0;
     int64_t at = pos;
+    // The 32 lanes of a batch walk 32 different lines byte by byte: without help some lane crosses into a new sector at
+    // almost every step and the whole warp waits for L2.  Ask for the next sectors up front (and keep asking below).
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (pos + 32 * k < len) prefetch_l1(buf + pos + 32 * k);
     for (;;) {
         int64_t stop = at + BUDGET_TICK < len ? at + BUDGET_TICK : len;
         const int64_t from = at;
         bool out = false;
         while (at < stop) {
+            if (((reinterpret_cast<uintptr_t>(buf) + (uintptr_t)at) & 31) == 0 && at + 128 < len) prefetch_l1(buf + at + 128);
             const uint32_t nw = T.next(st, __ldg(buf + at));
             if (nw & (W_ACC | W_INTER)) { out = true; break; }
             if (nw == 0) { acc += (uint32_t)(at - from); return false; }
@@ -2062,7 +2086,7 @@ __host__ __device__ __forceinline__ int scan_sparse_smem_bytes(int table_smem_by
 // the literal's first byte, the unit phase compares the whole literal, and best[2] counts the occurrences seen: when
 // the literal occurs nowhere the reference falls back to all boundaries -- the caller then runs the plain scan, which
 // is gated on best[2] == 0.  The start on the leading NUL is tried iff the literal sits at the very front of the text.
-template <int KIND, int NR, bool HIGH, bool PREFIX>
+template <int KIND, int NR, bool HIGH, bool PREFIX, bool SET2>
 __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparseParams sp, const uint8_t* __restrict__ buf,
                                                             ScanWindow W, unsigned long long* __restrict__ best,
                                                             int table_smem_bytes, const unsigned long long* __restrict__ gate,
@@ -2193,7 +2217,7 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
         for (int k = 0; k < 4; k++) {
             const int64_t u = g0 + k * 32 + lane;
             uint32_t seen = 0;
-            const bool hit = u < nunits && unit_any<NR, HIGH, false>(sp, va[k], vb[k], seen) != 0;
+            const bool hit = u < nunits && (SET2 ? unit_any_set2<NR, HIGH>(sp, va[k], vb[k]) : unit_any<NR, HIGH, false>(sp, va[k], vb[k], seen)) != 0;
             const uint32_t m = __ballot_sync(FULL, hit);
             if (hit) s_units[uqn + __popc(m & ((1u << lane) - 1))] = u;
             uqn += __popc(m);
@@ -2584,6 +2608,96 @@ __global__ void k_buffer_finish_span(SpanParams sp, const uint8_t* __restrict__ 
     }
     from_to[0] = from; from_to[1] = to;
     *done = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// All matches of a pattern in a text, as a caller of the reference collects them: call regex(), take the match, call
+// regex() again on the rest text(to+1:) (README.md:197-222 shows the slicing), until nothing is found.  Every call
+// frames ITS text afresh (api_internal_m.F90:55): the rest begins behind a new leading NUL, so `^` matches at every
+// restart, and the blank-text rule (api_internal_m.F90:68-74) applies to the rest.  Matches are never empty
+// (forgex.F90:332: from > 0 and to > 0), so the loop always advances.
+// ---------------------------------------------------------------------------------------------
+// one regex() on text[0, len): Forgex's (from, to), (0, 0) = none.  SPAN: the linear-time span path, else the emulation
+template <bool SPAN>
+__device__ __forceinline__ void regex_once(const KParams& p, const SpanParams& sp, const uint8_t* __restrict__ s, int64_t len,
+                                           int64_t& from, int64_t& to) {
+    from = 0; to = 0;
+    if (SPAN && len < 0x7FFFFFF0ll) {
+        if (len == 0 || (len == 1 && __ldg(s) == 0x20)) return;
+        SpanFwd<2> T;
+        T.s_cmap = T.s_table = 0; T.g_table = sp.table; T.g_cmap = sp.classmap; T.shift = sp.row_shift;
+        SpanRev<false> R;
+        R.s_delta = R.s_page = R.s_mixed = 0;
+        span_linear(sp, T, R, FetchGlobal{s}, (int)len, from, to);
+    } else {
+        Table<3> G;
+        G.g_table = p.ctable; G.g_cmap = p.classmap; G.shift = p.c_row_shift; G.s_table = 0; G.s_cmap = 0;
+        eval_regex(p, G, FetchGlobal{s}, len, from, to);
+    }
+}
+
+// number of matches per string of a ragged batch (one thread per string)
+template <bool SPAN>
+__global__ void __launch_bounds__(256) k_regex_count(KParams p, SpanParams sp, const uint8_t* __restrict__ buf,
+                                                     const int64_t* __restrict__ offsets, int64_t n, int64_t* __restrict__ counts) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t o0 = __ldg(offsets + i), o1 = __ldg(offsets + i + 1);
+        int64_t pos = 0, cnt = 0;
+        for (;;) {
+            int64_t f, t;
+            regex_once<SPAN>(p, sp, buf + o0 + pos, o1 - o0 - pos, f, t);
+            if (f <= 0 || t <= 0) break;
+            cnt++;
+            pos += t;
+        }
+        counts[i] = cnt;
+    }
+}
+
+// The all-matches loop over ONE buffer, its short steps.  state[0] = position of the rest, state[1] = matches so far,
+// state[2] = 1 when the loop is over, state[3] = 1 when this kernel gave up on a long search (the host then runs the
+// parallel long-buffer search on the rest and comes back).  One thread: from the rest's start the forward automaton is
+// walked at most `reach` bytes; a match that completes in that stretch is recorded and the loop goes on, up to
+// `max_matches` per launch.  Dense matches are collected here at one launch per thousand; the far ones by K4 / K5.
+__global__ void k_buffer_all_local(KParams p, SpanParams sp, const uint8_t* __restrict__ buf, int64_t len, int64_t* __restrict__ state,
+                                   int64_t* __restrict__ out_from, int64_t* __restrict__ out_to, int64_t capacity,
+                                   int max_matches, int64_t reach) {
+    int64_t pos = state[0], cnt = state[1];
+    state[3] = 0;
+    SpanFwd<2> T;
+    T.s_cmap = T.s_table = 0; T.g_table = sp.table; T.g_cmap = sp.classmap; T.shift = sp.row_shift;
+    SpanRev<false> R;
+    R.s_delta = R.s_page = R.s_mixed = 0;
+    for (int it = 0; it < max_matches; it++) {
+        const int64_t rem = len - pos;
+        const uint8_t* s = buf + pos;
+        if (rem == 0 || (rem == 1 && __ldg(s) == 0x20)) { state[2] = 1; break; }      // api_internal_m.F90:68-74: no match
+        const int lim = (int)(rem < reach ? rem : reach);
+        uint32_t st = (uint32_t)sp.start;
+        int last = sp.start_acc ? 0 : -1;
+        int j = 0;
+        for (; j < lim && st != 0; j++) { const uint32_t b = __ldg(s + j); FX_SPAN_STEP(T, st, last, b, j); }
+        if (st != 0 && (int64_t)j < rem) { state[3] = 1; break; }                     // still searching: a job for the parallel scan
+        const int ln = rem < 0x7FFFFFF0ll ? (int)rem : 0x7FFFFFF0;                     // (`last` is at most reach + 1 here)
+        if (st != 0) last = span_end_of_text(sp, st, ln, last);
+        if (last <= 0) { state[2] = 1; break; }                                       // the rest holds no match
+        const int f = span_backward(sp, R, FetchGlobal{s}, ln, last);
+        const int64_t t = last < rem ? last : rem;
+        if (f <= 0) { state[2] = 1; break; }
+        if (cnt < capacity) { out_from[cnt] = pos + f; out_to[cnt] = pos + t; }
+        cnt++;
+        pos += t;
+    }
+    state[0] = pos; state[1] = cnt;
+}
+// the far step: the long-buffer search has run on the rest (from_to relative to it): record, advance
+__global__ void k_buffer_all_take(const int64_t* __restrict__ from_to, int64_t* __restrict__ state, int64_t* __restrict__ out_from,
+                                  int64_t* __restrict__ out_to, int64_t capacity) {
+    const int64_t f = from_to[0], t = from_to[1];
+    if (f <= 0 || t <= 0) { state[2] = 1; return; }
+    const int64_t pos = state[0], cnt = state[1];
+    if (cnt < capacity) { out_from[cnt] = pos + f; out_to[cnt] = pos + t; }
+    state[0] = pos + t; state[1] = cnt + 1;
 }
 
 // K4L: a pattern that is ONE literal (`all` is not blank).  The reference never consults the automaton for it:

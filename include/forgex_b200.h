@@ -150,6 +150,19 @@ int fx_regex_batch_dev(fx_pattern* p, const uint8_t* d_buf, const int64_t* d_off
 int64_t fx_regex_buffer_work_bytes(int64_t len);
 int fx_regex_buffer_dev(fx_pattern* p, const uint8_t* d_buf, int64_t len, int64_t* d_from_to, void* d_work, void* stream);
 
+/* All matches, the way a caller of the reference collects them (README.md:197-222 shows the slicing): regex(), take
+ * the match, regex() again on the rest text(to+1:), until nothing is found.  Stated semantics: every call frames ITS
+ * text afresh (src/api_internal_m.F90:55) -- the rest begins behind a new leading NUL, so `^` matches at every restart
+ * -- and the blank-text rule (src/api_internal_m.F90:68-74) applies to the rest; matches are never empty.
+ * fx_regex_count_batch*: the number of matches per string of a ragged batch (d_counts[n]).
+ * fx_regex_buffer_all*: one buffer; the first `capacity` spans in whole-buffer coordinates, *count (HOST memory in both
+ * forms) = the number of matches (may exceed capacity).  The _dev form synchronises `stream` (per far match, or per
+ * thousand near ones) and needs fx_regex_buffer_work_bytes(len) bytes of scratch. */
+int fx_regex_count_batch_dev(fx_pattern* p, const uint8_t* d_buf, const int64_t* d_offsets, int64_t n, int64_t total_bytes,
+                             int64_t* d_counts, void* stream);
+int fx_regex_buffer_all_dev(fx_pattern* p, const uint8_t* d_buf, int64_t len, int64_t* d_from, int64_t* d_to, int64_t capacity,
+                            int64_t* count, void* d_work, void* stream);
+
 /* Window forms of the buffer search, for a text that is split across GPUs.  A window is a contiguous piece of the
  * text held by this GPU: window byte 0 is text position `origin` (0-based).  fx_buffer_scan_dev tries the starts
  * [start_lo, start_hi) of the window (attempts may read on to the end of the window) and lowers d_best[0] to the
@@ -177,6 +190,8 @@ int fx_match_batch(fx_pattern* p, const uint8_t* buf, const int64_t* offsets, in
 int fx_in_batch(fx_pattern* p, const uint8_t* buf, const int64_t* offsets, int64_t n, uint8_t* out);
 int fx_regex_batch(fx_pattern* p, const uint8_t* buf, const int64_t* offsets, int64_t n, int64_t* from, int64_t* to);
 int fx_regex_buffer(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* from, int64_t* to);
+int fx_regex_count_batch(fx_pattern* p, const uint8_t* buf, const int64_t* offsets, int64_t n, int64_t* counts);
+int fx_regex_buffer_all(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* from, int64_t* to, int64_t capacity, int64_t* count);
 
 /* ---- one pattern, one text: the reference's public API, compiled per call like the reference does */
 int fx_in(const void* pattern, int64_t plen, const void* text, int64_t tlen, int* result);

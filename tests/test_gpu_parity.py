@@ -685,3 +685,51 @@ def test_long_attempts_are_linear_time():
     assert tuple(ft.cpu().tolist()) == (1, m)
     small = np.frombuffer(b"a" * 3000 + b"c" + b"a" * 100, dtype=np.uint8)
     assert p.regex_buffer(small) == O.Compiled(b"[ab].*c", 0).regex_buffer(small) == (1, 3001)
+
+
+def oracle_all(c, text):
+    """the caller's loop: regex(), then regex() again on text(to+1:), each call framed afresh"""
+    out, pos = [], 0
+    arr = np.frombuffer(text, dtype=np.uint8)
+    while True:
+        f, t = c.regex_buffer(np.ascontiguousarray(arr[pos:]))
+        if f <= 0 or t <= 0:
+            return out
+        out.append((pos + f, pos + t))
+        pos += t
+
+
+def test_all_matches_and_counts():
+    """fx_regex_buffer_all / fx_regex_count_batch against the oracle's loop (README.md:197-222): dense and sparse
+    matches, anchors that re-match at every restart (fresh leading NUL), literals, prefix literals, UTF-8"""
+    import random
+    from tests.test_host_tables import gen_pattern, gen_text
+    rng = random.Random(99)
+    log = bytes(synth.gen_c4(60000, 0.3)) + synth.C4_MATCH_LINE + b"\n" + bytes(synth.gen_c4_block(30000, 5)) + synth.C4_MATCH_LINE
+    texts = [b"foobar foobaz fooba foobarfoobaz", b"abc\nabc\r\nabc", b"aaa", b"", b" ", b"x y  z", log,
+             "あいう えお かきく".encode() * 50, b"\n".join(gen_text(rng) for _ in range(300)), b"a" * 5000, b"ab" * 3000 + b"\n" + b"ba" * 200]
+    pats = [b"foo(bar|baz)", b"^abc", b"abc$", b"a", b"[a-z]+", rb"\s", synth.PATTERNS["c4"], "[ぁ-ん]+".encode(), b"a{1,7}", b"(ab)+", b"^", b".",
+            b"[ab]{2,3}", b"ERROR", rb"\w+\s"]
+    pats += [gen_pattern(rng).encode() for _ in range(25)]
+    used = 0
+    for pat in pats:
+        p = fx.Pattern(pat, "regex")
+        if p.status != 0:
+            continue
+        if p.info()["literal_prefix_len"] and not p.info()["prefix_scan"] and not p.info()["literal_only"]:
+            continue                                   # (sequential prefix candidates: not on the buffer path)
+        c = O.Compiled(pat, 0)
+        for text in texts:
+            if len(text) > 20000 and pat not in pats[:15]:
+                continue
+            exp = oracle_all(c, text)
+            f, t, cnt = p.regex_buffer_all(np.frombuffer(text, dtype=np.uint8), capacity=max(1, len(exp) + 3))
+            assert cnt == len(exp) and list(zip(f.tolist(), t.tolist())) == exp, (pat, len(text), cnt, len(exp), exp[:3], list(zip(f, t))[:3])
+            if exp:
+                f2, t2, cnt2 = p.regex_buffer_all(np.frombuffer(text, dtype=np.uint8), capacity=1)
+                assert cnt2 == len(exp) and (f2[0], t2[0]) == exp[0]
+        buf, off = pack(texts)
+        counts = p.regex_count_batch(buf, off)
+        assert counts.tolist() == [len(oracle_all(c, x)) for x in texts], (pat, counts.tolist())
+        used += 1
+    assert used >= 25

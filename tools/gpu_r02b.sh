@@ -16,9 +16,9 @@ FX_K4_PHASES=0 $B --config c4 --lines 8589934592 > gpurun_out/r02b_c4_sweeponly.
 NCU="ncu --set full --clock-control none --import-source on"
 export FX_BENCH_ALLOW_SHORT_WARMUP=1
 $NCU -k regex:k_span_ragged -s 1 -c 1 -f -o gpurun_out/r02b_prof_c3 python bench.py --config c3 --lines 2000000 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/r02b_ncu_c3.log 2>&1
-FX_K4_PHASES=1 $NCU -k regex:k_buffer_scan_sparse -s 1 -c 1 -f -o gpurun_out/r02b_prof_c4_nostarts python bench.py --config c4 --lines 2147483648 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/r02b_ncu_c4a.log 2>&1
-FX_K4_PHASES=0 $NCU -k regex:k_buffer_scan_sparse -s 1 -c 1 -f -o gpurun_out/r02b_prof_c4_sweeponly python bench.py --config c4 --lines 2147483648 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/r02b_ncu_c4b.log 2>&1
-$NCU -k regex:k_buffer_scan_sparse -s 1 -c 1 -f -o gpurun_out/r02b_prof_c4 python bench.py --config c4 --lines 2147483648 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/r02b_ncu_c4.log 2>&1
+FX_K4_PHASES=1 $NCU -k regex:k_buffer_scan_sparse -s 2 -c 1 -f -o gpurun_out/r02b_prof_c4_nostarts python bench.py --config c4 --lines 2147483648 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/r02b_ncu_c4a.log 2>&1
+FX_K4_PHASES=0 $NCU -k regex:k_buffer_scan_sparse -s 2 -c 1 -f -o gpurun_out/r02b_prof_c4_sweeponly python bench.py --config c4 --lines 2147483648 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/r02b_ncu_c4b.log 2>&1
+$NCU -k regex:k_buffer_scan_sparse -s 2 -c 1 -f -o gpurun_out/r02b_prof_c4 python bench.py --config c4 --lines 2147483648 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/r02b_ncu_c4.log 2>&1
 $NCU -k regex:k_bool_fixed -s 1 -c 1 -f -o gpurun_out/r02b_prof_c1 python bench.py --config c1 --lines 134217728 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/r02b_ncu_c1.log 2>&1
 for c in c3 c4_nostarts c4_sweeponly c4 c1; do python tools/ncu_summary.py gpurun_out/r02b_prof_$c.ncu-rep > gpurun_out/r02b_prof_$c.txt 2>&1; done
 # keep the c3 and c4 reports if they fit
