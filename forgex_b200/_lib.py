@@ -16,13 +16,13 @@ FX_ERR_BAD_ARGUMENT, FX_ERR_NO_DEVICE = 104, 105
 
 # every symbol include/forgex_b200.h declares (tests check that the library exports them all)
 SYMBOLS = [
-    "fx_status_message", "fx_compile", "fx_pattern_free", "fx_pattern_get_info", "fx_pattern_set_residency",
+    "fx_status_message", "fx_compile", "fx_compile_from_dfa", "fx_pattern_cp_automaton", "fx_pattern_free", "fx_pattern_get_info", "fx_pattern_set_residency",
     "fx_pattern_literals", "fx_pattern_tables", "fx_pattern_span_tables", "fx_is_valid_regex", "fx_is_valid_regex_batch",
     "fx_match_fixed_dev", "fx_in_fixed_dev", "fx_match_batch_dev", "fx_in_batch_dev", "fx_regex_batch_dev",
     "fx_regex_buffer_work_bytes", "fx_regex_buffer_dev", "fx_buffer_scan_dev", "fx_buffer_scan_all_dev", "fx_buffer_finish_dev",
     "fx_match_fixed", "fx_in_fixed", "fx_match_batch", "fx_in_batch", "fx_regex_batch", "fx_regex_buffer",
     "fx_regex_count_batch_dev", "fx_regex_buffer_all_dev", "fx_regex_count_batch", "fx_regex_buffer_all",
-    "fx_in", "fx_match", "fx_regex", "fx_launch_count",
+    "fx_in", "fx_match", "fx_regex", "fx_in_value", "fx_match_value", "fx_regex_sub", "fx_launch_count",
 ]
 
 
@@ -52,6 +52,14 @@ def lib():
     L.fx_status_message.argtypes = [C.c_int]
     L.fx_compile.argtypes = [C.c_char_p, i64, C.c_int, C.POINTER(vp)]
     L.fx_pattern_free.argtypes = [vp]
+    L.fx_compile_from_dfa.argtypes = [C.c_int, vp, C.c_int32, vp, C.c_int32, vp, C.c_int32, C.c_char_p, i64, C.c_char_p, i64,
+                                      C.c_char_p, i64, C.POINTER(vp)]
+    L.fx_pattern_cp_automaton.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32 * 4)]
+    L.fx_in_value.argtypes = [C.c_char_p, i64, C.c_char_p, i64]
+    L.fx_match_value.argtypes = [C.c_char_p, i64, C.c_char_p, i64]
+    L.fx_regex_sub.restype = None
+    L.fx_regex_sub.argtypes = [C.c_char_p, i64, C.c_char_p, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64),
+                               C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.fx_pattern_get_info.argtypes = [vp, C.POINTER(PatternInfo)]
     L.fx_pattern_set_residency.argtypes = [vp, C.c_int]
     L.fx_pattern_literals.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]

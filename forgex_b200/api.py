@@ -74,6 +74,37 @@ class Pattern:
         if residency != "auto":
             self.set_residency(residency)
 
+    @classmethod
+    def from_dfa(cls, op, cuts, delta, accept, q0, literals=(b"", b"", b""), pattern=b""):
+        """the Fortran-side route: a handle built from an anchored code-point DFA (fx_compile_from_dfa)"""
+        self = cls.__new__(cls)
+        self.pattern = _b(pattern)
+        self.op = cls.OPS[op] if isinstance(op, str) else op
+        cuts = np.ascontiguousarray(cuts, dtype=np.int32)
+        delta = np.ascontiguousarray(delta, dtype=np.int32)
+        accept = np.ascontiguousarray(accept, dtype=np.uint8)
+        nstates, ncls = delta.shape
+        assert len(cuts) == ncls + 1 and len(accept) == nstates
+        a, pre, suf = (_b(x) for x in literals)
+        h = C.c_void_p()
+        self.status = L.lib().fx_compile_from_dfa(self.op, _ptr(cuts), ncls, _ptr(delta), nstates, _ptr(accept), int(q0),
+                                                  a, len(a), pre, len(pre), suf, len(suf), C.byref(h))
+        self.h = h
+        return self
+
+    def cp_automaton(self):
+        """the anchored code-point DFA of a 'regex' handle: dict(cuts, delta[states, classes], accept, q0, start_nul)"""
+        ptrs = [C.c_void_p() for _ in range(3)]
+        sc = (C.c_int32 * 4)()
+        _check(L.lib().fx_pattern_cp_automaton(self.h, C.byref(ptrs[0]), C.byref(ptrs[1]), C.byref(ptrs[2]), C.byref(sc)),
+               "fx_pattern_cp_automaton")
+
+        def arr(p, n, dt):
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(dt)), shape=(n,)).copy()
+        ns, nc = sc[0], sc[1]
+        return {"cuts": arr(ptrs[0], nc + 1, C.c_int32), "delta": arr(ptrs[1], ns * nc, C.c_int32).reshape(ns, nc),
+                "accept": arr(ptrs[2], ns, C.c_uint8), "q0": sc[2], "start_nul": sc[3]}
+
     def close(self):
         if getattr(self, "h", None):
             L.lib().fx_pattern_free(self.h)

@@ -816,19 +816,10 @@ int build_byte_table(const CpAutomaton& a, bool flag_bits, ByteTable& out, bool 
 // ---------------------------------------------------------------------------------------------
 // whole program
 // ---------------------------------------------------------------------------------------------
-int compile_program(const std::string& pattern, int op, int state_cap, Program& p, bool want_span) {
-    p = Program();
-    p.op = op;
-    p.prepared = prepare_pattern(pattern, op == MODE_MATCH);
-    Syntax syn;
-    parse_pattern(p.prepared, syn);
-    p.status = syn.status;
-    if (!syn.valid()) return p.status;
-    extract_literals(syn, p.lit);
+// NFA + literals -> every table the kernels walk (shared by the pattern route and the DFA route below)
+static int compile_from_nfa(const Nfa& nfa, int op, int state_cap, Program& p, bool want_span) {
     p.literal_only = !fortran_blank(p.lit.all);
     p.prefix_active = !fortran_blank(p.lit.prefix);
-    Nfa nfa;
-    build_nfa(syn, nfa);
     p.nfa_states = nfa.n;
     int rc = build_cp_automaton(nfa, (Mode)op, state_cap, p.cp);
     if (rc != OK) { p.status = rc; return rc; }
@@ -841,6 +832,65 @@ int compile_program(const std::string& pattern, int op, int state_cap, Program& 
             p.has_span = true;
     }
     return OK;
+}
+
+int compile_program(const std::string& pattern, int op, int state_cap, Program& p, bool want_span) {
+    p = Program();
+    p.op = op;
+    p.prepared = prepare_pattern(pattern, op == MODE_MATCH);
+    Syntax syn;
+    parse_pattern(p.prepared, syn);
+    p.status = syn.status;
+    if (!syn.valid()) return p.status;
+    extract_literals(syn, p.lit);
+    Nfa nfa;
+    build_nfa(syn, nfa);
+    return compile_from_nfa(nfa, op, state_cap, p, want_span);
+}
+
+// The Fortran-side route: the host has already run Forgex's own front end and explored its automaton
+// eagerly -- a breadth-first search that calls automaton%construct (src/automaton_m.F90:333) for every state and one
+// representative symbol of every alphabet segment -- and hands over the resulting ANCHORED code-point DFA plus the
+// literals extract_literal produced.  A DFA is an NFA: state s of the DFA becomes NFA state s + 2, accepting states get
+// an epsilon move to the exit, and the same builders as above derive every mode's automaton from it (the search
+// automaton of `.in.`, the ordered-groups and reverse automata of the span path are subset constructions over it).
+//   cuts[ncls + 1]: ascending code points, class c = [cuts[c], cuts[c+1] - 1], cuts[0] = 0; delta[nstates x ncls] with
+//   state 0 = dead; accept[nstates]; q0 = the state before any symbol.
+int compile_from_dfa(const DfaInput& in, int op, int state_cap, Program& p, bool want_span) {
+    p = Program();
+    p.op = op;
+    p.status = OK;
+    p.lit.all = in.all; p.lit.prefix = in.prefix; p.lit.suffix = in.suffix;
+    if (in.nstates < 1 || in.ncls < 1 || in.q0 <= 0 || in.q0 >= in.nstates || in.cuts[0] != 0) { p.status = ERR_BAD_ARGUMENT; return p.status; }
+    for (int c = 0; c < in.ncls; c++) if (in.cuts[(size_t)c] >= in.cuts[(size_t)c + 1]) { p.status = ERR_BAD_ARGUMENT; return p.status; }
+    Nfa nfa;
+    nfa.n = in.nstates + 2;             // NFA states 1 (entry), 2 (exit), s + 2 for DFA state s >= 1
+    nfa.entry = 1;
+    nfa.exit = 2;
+    nfa.eps.assign((size_t)nfa.n + 1, {});
+    nfa.edges.assign((size_t)nfa.n + 1, {});
+    nfa.eps[1].push_back(in.q0 + 2);
+    std::vector<int> cuts(in.cuts, in.cuts + in.ncls + 1);
+    if (cuts.back() > CP_MAX + 1) cuts.back() = CP_MAX + 1;     // nothing matches above U+10FFFF
+    for (int s = 1; s < in.nstates; s++) {
+        if (in.accept[(size_t)s]) nfa.eps[(size_t)s + 2].push_back(2);
+        for (int c = 0; c < in.ncls; c++) {
+            const int d = in.delta[(size_t)s * (size_t)in.ncls + (size_t)c];
+            if (d < 0 || d >= in.nstates) { p.status = ERR_BAD_ARGUMENT; return p.status; }
+            if (d == 0 || cuts[(size_t)c] > CP_MAX) continue;
+            int hi = cuts[(size_t)c + 1] - 1;
+            if (hi > CP_MAX) hi = CP_MAX;
+            nfa.edges[(size_t)s + 2].push_back({Range{cuts[(size_t)c], hi}, d + 2});
+        }
+    }
+    std::vector<int> all = cuts;
+    all.push_back(0);
+    all.push_back(CP_MAX + 1);
+    all.push_back(CP_TOP + 1);
+    std::sort(all.begin(), all.end());
+    all.erase(std::unique(all.begin(), all.end()), all.end());
+    nfa.cuts = all;
+    return compile_from_nfa(nfa, op, state_cap, p, want_span);
 }
 
 }  // namespace fx

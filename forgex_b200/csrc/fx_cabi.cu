@@ -1020,17 +1020,22 @@ const char* fx_status_message(int status) {
     return fx::status_message(status);
 }
 
-int fx_compile(const void* pattern, int64_t plen, int op, fx_pattern** out) {
-    if (!out || plen < 0 || (plen > 0 && !pattern) || op < FX_OP_MATCH || op > FX_OP_REGEX) return FX_ERR_BAD_ARGUMENT;
-    fx_pattern* p = new (std::nothrow) fx_pattern();
-    if (!p) return fx::ERR_ALLOCATION;
-    std::string pat(static_cast<const char*>(pattern), (size_t)plen);
-    fx::compile_program(pat, op, STATE_CAP, p->prog);
+// where a pattern handle's automata come from: the pattern text (fx_compile) or an anchored DFA explored by the host
+// (fx_compile_from_dfa); `.in.` handles compile the anchored form of the same source a second time
+struct CompileSource {
+    const std::string* pattern = nullptr;
+    const fx::DfaInput* dfa = nullptr;
+    int compile(int op, int cap, fx::Program& out, bool want_span) const {
+        return pattern ? fx::compile_program(*pattern, op, cap, out, want_span) : fx::compile_from_dfa(*dfa, op, cap, out, want_span);
+    }
+};
+
+static int finish_compile(fx_pattern* p, const CompileSource& src, int op, fx_pattern** out) {
     if (p->prog.status == fx::OK && op == FX_OP_IN && !p->prog.literal_only) {
         // `.in.` consults the prefix prefilter: keep the anchored automaton to replay it exactly when needed.  The same
         // automaton drives the sparse-start kernel; without a prefix it is optional and built under a smaller cap.
         const bool needed = p->prog.prefix_active;
-        fx::compile_program(pat, FX_OP_REGEX, needed ? STATE_CAP : SPARSE_STATE_CAP, p->anchored, false);
+        src.compile(FX_OP_REGEX, needed ? STATE_CAP : SPARSE_STATE_CAP, p->anchored, false);
         if (p->anchored.status == fx::OK) {
             p->has_anchored = true;
             if (needed) p->prefix_mode = prefilter_is_neutral(p->anchored) ? 1 : 2;
@@ -1081,6 +1086,71 @@ int fx_compile(const void* pattern, int64_t plen, int op, fx_pattern** out) {
     }
     *out = p;
     return p->prog.status;
+}
+
+
+int fx_compile(const void* pattern, int64_t plen, int op, fx_pattern** out) {
+    if (!out || plen < 0 || (plen > 0 && !pattern) || op < FX_OP_MATCH || op > FX_OP_REGEX) return FX_ERR_BAD_ARGUMENT;
+    fx_pattern* p = new (std::nothrow) fx_pattern();
+    if (!p) return fx::ERR_ALLOCATION;
+    std::string pat(static_cast<const char*>(pattern), (size_t)plen);
+    CompileSource src;
+    src.pattern = &pat;
+    src.compile(op, STATE_CAP, p->prog, true);
+    return finish_compile(p, src, op, out);
+}
+
+// The Fortran-side route: Forgex's own front end has parsed the pattern, extracted the literals and explored the
+// automaton eagerly (fortran/forgex_b200_tables_m.F90: a breadth-first search over automaton%construct,
+// src/automaton_m.F90:333); this builds every device table from that anchored code-point DFA.
+int fx_compile_from_dfa(int op, const int32_t* cuts, int32_t ncls, const int32_t* delta, int32_t nstates, const uint8_t* accept,
+                        int32_t q0, const void* all, int64_t all_len, const void* prefix, int64_t prefix_len,
+                        const void* suffix, int64_t suffix_len, fx_pattern** out) {
+    if (!out || !cuts || !delta || !accept || op < FX_OP_MATCH || op > FX_OP_REGEX || all_len < 0 || prefix_len < 0 || suffix_len < 0)
+        return FX_ERR_BAD_ARGUMENT;
+    fx_pattern* p = new (std::nothrow) fx_pattern();
+    if (!p) return fx::ERR_ALLOCATION;
+    fx::DfaInput in;
+    in.cuts = cuts; in.delta = delta; in.accept = accept; in.nstates = nstates; in.ncls = ncls; in.q0 = q0;
+    if (all_len) in.all.assign(static_cast<const char*>(all), (size_t)all_len);
+    if (prefix_len) in.prefix.assign(static_cast<const char*>(prefix), (size_t)prefix_len);
+    if (suffix_len) in.suffix.assign(static_cast<const char*>(suffix), (size_t)suffix_len);
+    CompileSource src;
+    src.dfa = &in;
+    src.compile(op, STATE_CAP, p->prog, true);
+    return finish_compile(p, src, op, out);
+}
+
+// the anchored code-point DFA of an FX_OP_REGEX handle (tests: it is what the Fortran-side route would hand over):
+// scalars = {states, classes, q0}; cuts: classes + 1; delta: states x classes (0 = dead); accept: states
+int fx_pattern_cp_automaton(const fx_pattern* p, const int32_t** cuts, const int32_t** delta, const uint8_t** accept, int32_t scalars[4]) {
+    if (!p || p->prog.status != fx::OK || p->prog.op != FX_OP_REGEX) return FX_ERR_BAD_ARGUMENT;
+    const fx::CpAutomaton& a = p->prog.cp;
+    static_assert(sizeof(int) == sizeof(int32_t), "int32 views");
+    if (cuts) *cuts = reinterpret_cast<const int32_t*>(a.cuts.data());
+    if (delta) *delta = reinterpret_cast<const int32_t*>(a.delta.data());
+    if (accept) *accept = a.accept.data();
+    if (scalars) { scalars[0] = a.nstates; scalars[1] = a.nclasses; scalars[2] = a.q0; scalars[3] = a.start_nul; }
+    return FX_OK;
+}
+
+// value-returning / subroutine-shaped forms of the one-pattern-one-text entry points, for `pure` Fortran callers: a
+// pure FUNCTION may only have intent(in) / value arguments, so `.in.` and `.match.` come back as the function value
+// (1 / 0, or -status on failure), and regex as a procedure without a result (a pure SUBROUTINE may have intent(out)).
+int fx_in_value(const void* pattern, int64_t plen, const void* text, int64_t tlen) {
+    int r = 0;
+    const int rc = fx_in(pattern, plen, text, tlen, &r);
+    return rc ? (rc > 0 ? -rc : rc) : r;
+}
+int fx_match_value(const void* pattern, int64_t plen, const void* text, int64_t tlen) {
+    int r = 0;
+    const int rc = fx_match(pattern, plen, text, tlen, &r);
+    return rc ? (rc > 0 ? -rc : rc) : r;
+}
+void fx_regex_sub(const void* pattern, int64_t plen, const void* text, int64_t tlen, int64_t* from, int64_t* to, int64_t* length,
+                  int* status, int* rc) {
+    const int r = fx_regex(pattern, plen, text, tlen, from, to, length, status);
+    if (rc) *rc = r;
 }
 
 int fx_pattern_free(fx_pattern* p) {

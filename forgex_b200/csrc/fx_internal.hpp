@@ -210,4 +210,14 @@ struct Program {
 
 int compile_program(const std::string& pattern, int op, int state_cap, Program& out, bool want_span = true);
 
+// an anchored code-point DFA explored by the host (the Fortran-side route, see compile_from_dfa in fx_automata.cpp)
+struct DfaInput {
+    const int32_t* cuts;      // ncls + 1
+    const int32_t* delta;     // nstates x ncls, 0 = dead
+    const uint8_t* accept;    // nstates
+    int nstates, ncls, q0;
+    std::string all, prefix, suffix;
+};
+int compile_from_dfa(const DfaInput& in, int op, int state_cap, Program& out, bool want_span = true);
+
 }  // namespace fx

@@ -13,6 +13,18 @@
 !                             a flat buffer + offsets (variable length; trailing blanks are text to Forgex)
 !     regex_batch             (from, to) per string
 !     regex_buffer            one pattern against one huge buffer, 64-bit positions
+!     regex_count_batch / regex_buffer_all   every match, the way a caller loops regex on text(to+1:)
+!     is_valid_regex_batch    is_valid_regex over an array of patterns, one call
+!     *_dev / window forms    device pointers (type(c_ptr)) + a CUDA stream, for CUDA Fortran / OpenACC hosts and for
+!                             a text that is split across GPUs
+!
+! `pure`: Forgex's operators are `pure elemental` and `regex` is a `pure subroutine` (src/forgex.F90:24-54).  A bind(C)
+! interface body may be declared PURE -- the declaration is the programmer's promise, the compiler does not look into
+! the C code -- but a pure FUNCTION may only have intent(in) / value dummies.  The C ABI therefore has value-returning
+! forms of the two operators (fx_in_value, fx_match_value) and a subroutine-shaped regex (fx_regex_sub); they are
+! declared pure below, so the operators keep every attribute they have today (INTEGRATION.md 2.1).  The promise holds
+! in the sense Fortran cares about: no Fortran-visible state is touched; the calls allocate and free device memory
+! internally and are re-entrant.
 module forgex_b200_m
    use, intrinsic :: iso_c_binding
    use, intrinsic :: iso_fortran_env, only: int64
@@ -33,7 +45,7 @@ module forgex_b200_m
       procedure :: free    => pattern__free
    end type fx_pattern_t
 
-   public :: match_batch, in_batch, regex_batch, regex_buffer
+   public :: match_batch, in_batch, regex_batch, regex_buffer, regex_count_batch, regex_buffer_all, is_valid_regex_batch
 
    interface match_batch
       module procedure :: match_batch__fixed, match_batch__ragged
@@ -131,8 +143,160 @@ module forgex_b200_m
          integer(c_int), intent(out) :: syntax_status
          integer(c_int) :: status
       end function
+      ! ---- pure forms for the existing pure operators (see the header comment) ----
+      pure function fx_in_value(pattern, plen, text, tlen) bind(c, name='fx_in_value') result(res)
+         import :: c_char, c_int64_t, c_int
+         character(kind=c_char), intent(in) :: pattern(*), text(*)
+         integer(c_int64_t), value :: plen, tlen
+         integer(c_int) :: res                      ! 1 / 0, negative = -status
+      end function
+      pure function fx_match_value(pattern, plen, text, tlen) bind(c, name='fx_match_value') result(res)
+         import :: c_char, c_int64_t, c_int
+         character(kind=c_char), intent(in) :: pattern(*), text(*)
+         integer(c_int64_t), value :: plen, tlen
+         integer(c_int) :: res
+      end function
+      pure subroutine fx_regex_sub(pattern, plen, text, tlen, from, to, length, syntax_status, rc) bind(c, name='fx_regex_sub')
+         import :: c_char, c_int64_t, c_int
+         character(kind=c_char), intent(in) :: pattern(*), text(*)
+         integer(c_int64_t), value :: plen, tlen
+         integer(c_int64_t), intent(out) :: from, to, length
+         integer(c_int), intent(out) :: syntax_status, rc
+      end subroutine
+      pure function fx_is_valid_regex(pattern, plen, status) bind(c, name='fx_is_valid_regex') result(valid)
+         import :: c_char, c_int64_t, c_int, c_ptr
+         character(kind=c_char), intent(in) :: pattern(*)
+         integer(c_int64_t), value :: plen
+         type(c_ptr), value :: status                ! c_null_ptr: not wanted (keeps the function pure)
+         integer(c_int) :: valid
+      end function
+      function fx_is_valid_regex_batch(patterns, offsets, n, valid, status) bind(c, name='fx_is_valid_regex_batch') result(rc)
+         import :: c_char, c_int64_t, c_int8_t, c_int32_t, c_int
+         character(kind=c_char), intent(in) :: patterns(*)
+         integer(c_int64_t), intent(in) :: offsets(*)
+         integer(c_int64_t), value :: n
+         integer(c_int8_t), intent(out) :: valid(*)
+         integer(c_int32_t), intent(out) :: status(*)
+         integer(c_int) :: rc
+      end function
+      ! ---- all matches / counts ----
+      function fx_regex_count_batch(p, buf, offsets, n, counts) bind(c, name='fx_regex_count_batch') result(status)
+         import :: c_ptr, c_char, c_int64_t, c_int
+         type(c_ptr), value :: p
+         character(kind=c_char), intent(in) :: buf(*)
+         integer(c_int64_t), intent(in) :: offsets(*)
+         integer(c_int64_t), value :: n
+         integer(c_int64_t), intent(out) :: counts(*)
+         integer(c_int) :: status
+      end function
+      function fx_regex_buffer_all(p, buf, length, from, to, capacity, count) bind(c, name='fx_regex_buffer_all') result(status)
+         import :: c_ptr, c_char, c_int64_t, c_int
+         type(c_ptr), value :: p
+         character(kind=c_char), intent(in) :: buf(*)
+         integer(c_int64_t), value :: length, capacity
+         integer(c_int64_t), intent(out) :: from(*), to(*), count
+         integer(c_int) :: status
+      end function
+      ! ---- device-pointer forms: buffers are type(c_ptr) device addresses (c_loc of a CUDA Fortran device array,
+      !      acc_deviceptr, ...), stream = a cudaStream_t as c_ptr (c_null_ptr = default stream); asynchronous ----
+      function fx_match_fixed_dev(p, d_buf, n, stride, d_out, stream) bind(c, name='fx_match_fixed_dev') result(status)
+         import :: c_ptr, c_int64_t, c_int
+         type(c_ptr), value :: p, d_buf, d_out, stream
+         integer(c_int64_t), value :: n, stride
+         integer(c_int) :: status
+      end function
+      function fx_in_fixed_dev(p, d_buf, n, stride, d_out, stream) bind(c, name='fx_in_fixed_dev') result(status)
+         import :: c_ptr, c_int64_t, c_int
+         type(c_ptr), value :: p, d_buf, d_out, stream
+         integer(c_int64_t), value :: n, stride
+         integer(c_int) :: status
+      end function
+      function fx_match_batch_dev(p, d_buf, d_offsets, n, total_bytes, d_out, stream) bind(c, name='fx_match_batch_dev') result(status)
+         import :: c_ptr, c_int64_t, c_int
+         type(c_ptr), value :: p, d_buf, d_offsets, d_out, stream
+         integer(c_int64_t), value :: n, total_bytes
+         integer(c_int) :: status
+      end function
+      function fx_in_batch_dev(p, d_buf, d_offsets, n, total_bytes, d_out, stream) bind(c, name='fx_in_batch_dev') result(status)
+         import :: c_ptr, c_int64_t, c_int
+         type(c_ptr), value :: p, d_buf, d_offsets, d_out, stream
+         integer(c_int64_t), value :: n, total_bytes
+         integer(c_int) :: status
+      end function
+      function fx_regex_batch_dev(p, d_buf, d_offsets, n, total_bytes, d_from, d_to, stream) bind(c, name='fx_regex_batch_dev') result(status)
+         import :: c_ptr, c_int64_t, c_int
+         type(c_ptr), value :: p, d_buf, d_offsets, d_from, d_to, stream
+         integer(c_int64_t), value :: n, total_bytes
+         integer(c_int) :: status
+      end function
+      function fx_regex_count_batch_dev(p, d_buf, d_offsets, n, total_bytes, d_counts, stream) bind(c, name='fx_regex_count_batch_dev') result(status)
+         import :: c_ptr, c_int64_t, c_int
+         type(c_ptr), value :: p, d_buf, d_offsets, d_counts, stream
+         integer(c_int64_t), value :: n, total_bytes
+         integer(c_int) :: status
+      end function
+      function fx_regex_buffer_work_bytes(length) bind(c, name='fx_regex_buffer_work_bytes') result(nbytes)
+         import :: c_int64_t
+         integer(c_int64_t), value :: length
+         integer(c_int64_t) :: nbytes
+      end function
+      function fx_regex_buffer_dev(p, d_buf, length, d_from_to, d_work, stream) bind(c, name='fx_regex_buffer_dev') result(status)
+         import :: c_ptr, c_int64_t, c_int
+         type(c_ptr), value :: p, d_buf, d_from_to, d_work, stream
+         integer(c_int64_t), value :: length
+         integer(c_int) :: status
+      end function
+      function fx_regex_buffer_all_dev(p, d_buf, length, d_from, d_to, capacity, count, d_work, stream) &
+            bind(c, name='fx_regex_buffer_all_dev') result(status)
+         import :: c_ptr, c_int64_t, c_int
+         type(c_ptr), value :: p, d_buf, d_from, d_to, d_work, stream
+         integer(c_int64_t), value :: length, capacity
+         integer(c_int64_t), intent(out) :: count          ! host memory
+         integer(c_int) :: status
+      end function
+      ! ---- window forms: one text split across GPUs (one MPI rank / coarray image per GPU; see INTEGRATION.md 3) ----
+      function fx_buffer_scan_dev(p, d_window, window_len, start_lo, start_hi, origin, is_first, is_last, d_best, stream) &
+            bind(c, name='fx_buffer_scan_dev') result(status)
+         import :: c_ptr, c_int64_t, c_int
+         type(c_ptr), value :: p, d_window, d_best, stream
+         integer(c_int64_t), value :: window_len, start_lo, start_hi, origin
+         integer(c_int), value :: is_first, is_last
+         integer(c_int) :: status
+      end function
+      function fx_buffer_scan_all_dev(p, d_window, window_len, start_lo, start_hi, origin, is_first, is_last, d_best, stream) &
+            bind(c, name='fx_buffer_scan_all_dev') result(status)
+         import :: c_ptr, c_int64_t, c_int
+         type(c_ptr), value :: p, d_window, d_best, stream
+         integer(c_int64_t), value :: window_len, start_lo, start_hi, origin
+         integer(c_int), value :: is_first, is_last
+         integer(c_int) :: status
+      end function
+      function fx_buffer_finish_dev(p, d_window, window_len, origin, is_last, d_key, d_from_to, stream) &
+            bind(c, name='fx_buffer_finish_dev') result(status)
+         import :: c_ptr, c_int64_t, c_int
+         type(c_ptr), value :: p, d_window, d_key, d_from_to, stream
+         integer(c_int64_t), value :: window_len, origin
+         integer(c_int), value :: is_last
+         integer(c_int) :: status
+      end function
+      ! ---- the Fortran-side compile route (forgex_b200_tables_m) ----
+      function fx_compile_from_dfa(op, cuts, ncls, delta, nstates, accept, q0, all, all_len, prefix, prefix_len, &
+                                   suffix, suffix_len, out) bind(c, name='fx_compile_from_dfa') result(status)
+         import :: c_ptr, c_char, c_int64_t, c_int32_t, c_int8_t, c_int
+         integer(c_int), value :: op
+         integer(c_int32_t), intent(in) :: cuts(*), delta(*)
+         integer(c_int32_t), value :: ncls, nstates, q0
+         integer(c_int8_t), intent(in) :: accept(*)
+         character(kind=c_char), intent(in) :: all(*), prefix(*), suffix(*)
+         integer(c_int64_t), value :: all_len, prefix_len, suffix_len
+         type(c_ptr), intent(out) :: out
+         integer(c_int) :: status
+      end function
    end interface
-   public :: fx_in, fx_match, fx_regex
+   public :: fx_in, fx_match, fx_regex, fx_in_value, fx_match_value, fx_regex_sub, fx_is_valid_regex, fx_compile_from_dfa
+   public :: fx_match_fixed_dev, fx_in_fixed_dev, fx_match_batch_dev, fx_in_batch_dev, fx_regex_batch_dev, fx_regex_count_batch_dev
+   public :: fx_regex_buffer_work_bytes, fx_regex_buffer_dev, fx_regex_buffer_all_dev
+   public :: fx_buffer_scan_dev, fx_buffer_scan_all_dev, fx_buffer_finish_dev
 
 contains
 
@@ -214,5 +378,44 @@ contains
       integer, intent(out) :: status
       status = fx_regex_buffer(pat%handle, buf, int(len(buf, kind=int64), c_int64_t), from, to)
    end subroutine regex_buffer
+
+   ! matches per string, counted the way a caller loops `regex` on text(to+1:) (README.md:197-222)
+   subroutine regex_count_batch(pat, buf, offsets, counts, status)
+      type(fx_pattern_t), intent(in) :: pat
+      character(len=*), intent(in) :: buf
+      integer(int64), intent(in) :: offsets(0:)
+      integer(int64), intent(out) :: counts(:)
+      integer, intent(out) :: status
+      status = fx_regex_count_batch(pat%handle, buf, offsets, int(size(counts), c_int64_t), counts)
+   end subroutine regex_count_batch
+
+   ! every match of one buffer, in order; at most size(from) spans are stored, count may be larger
+   subroutine regex_buffer_all(pat, buf, from, to, count, status)
+      type(fx_pattern_t), intent(in) :: pat
+      character(len=*), intent(in) :: buf
+      integer(int64), intent(out) :: from(:), to(:), count
+      integer, intent(out) :: status
+      status = fx_regex_buffer_all(pat%handle, buf, int(len(buf, kind=int64), c_int64_t), from, to, &
+                                   int(min(size(from), size(to)), c_int64_t), count)
+   end subroutine regex_buffer_all
+
+   ! is_valid_regex over an array of patterns in one call; trailing blanks of an element are part of the element
+   ! exactly as they are for the elemental is_valid_regex (src/forgex.F90:58-71 trims inside)
+   subroutine is_valid_regex_batch(patterns, valid, codes)
+      character(len=*), intent(in), contiguous :: patterns(:)
+      logical, intent(out) :: valid(:)
+      integer, intent(out), optional :: codes(:)
+      integer(c_int64_t), allocatable :: offsets(:)
+      integer(c_int8_t), allocatable :: v(:)
+      integer(c_int32_t), allocatable :: st(:)
+      integer :: i, rc
+      allocate(offsets(0:size(patterns)), v(size(patterns)), st(size(patterns)))
+      do i = 0, size(patterns)
+         offsets(i) = int(i, c_int64_t) * len(patterns)
+      end do
+      rc = fx_is_valid_regex_batch(patterns, offsets, int(size(patterns), c_int64_t), v, st)
+      valid = v /= 0
+      if (present(codes)) codes = st
+   end subroutine is_valid_regex_batch
 
 end module forgex_b200_m

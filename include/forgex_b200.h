@@ -109,6 +109,19 @@ const char* fx_status_message(int status);
 /* Compile `pattern` for one entry point.  Always returns a handle in *out (unless arguments are
  * bad); the return value is the pattern's status (0 or a SYNTAX_* / FX_ERR_* code). */
 int fx_compile(const void* pattern, int64_t plen, int op, fx_pattern** out);
+/* The Fortran-side compile route (fortran/forgex_b200_tables_m.F90): the host has run Forgex's own front end
+ * (tree%build, extract_literal) and explored the automaton eagerly -- a breadth-first search calling automaton%construct
+ * (src/automaton_m.F90:333) for every state and one representative symbol of each alphabet segment -- and hands over the
+ * ANCHORED code-point DFA: cuts[ncls + 1] ascending code points with cuts[0] = 0 (class c = [cuts[c], cuts[c+1] - 1]),
+ * delta[nstates x ncls] with state 0 = dead, accept[nstates], q0 = the state before any symbol; plus the three literals.
+ * Every automaton and table of the handle (search automaton of `.in.`, span path, byte-level tables) is derived from it.
+ * For FX_OP_MATCH the DFA must be that of the pattern after operator__match's own preprocessing (src/forgex.F90:182-190). */
+int fx_compile_from_dfa(int op, const int32_t* cuts, int32_t ncls, const int32_t* delta, int32_t nstates, const uint8_t* accept,
+                        int32_t q0, const void* all, int64_t all_len, const void* prefix, int64_t prefix_len,
+                        const void* suffix, int64_t suffix_len, fx_pattern** out);
+/* the anchored code-point DFA of an FX_OP_REGEX handle, in exactly that form (tests / tools):
+ * scalars = {states, classes, q0, state after the leading NUL} */
+int fx_pattern_cp_automaton(const fx_pattern* p, const int32_t** cuts, const int32_t** delta, const uint8_t** accept, int32_t scalars[4]);
 int fx_pattern_free(fx_pattern* p);
 int fx_pattern_get_info(const fx_pattern* p, fx_pattern_info* info);
 int fx_pattern_set_residency(fx_pattern* p, int residency);
@@ -200,6 +213,14 @@ int fx_match(const void* pattern, int64_t plen, const void* text, int64_t tlen, 
  * from = to = -9999, length = 0, *status = SYNTAX_* code, return value 0 (src/forgex.F90:266-274). */
 int fx_regex(const void* pattern, int64_t plen, const void* text, int64_t tlen, int64_t* from, int64_t* to,
              int64_t* length, int* status);
+
+/* The same three for `pure` Fortran callers (operator(.in.) / operator(.match.) are `pure elemental`, regex is a `pure
+ * subroutine`, src/forgex.F90:24-54): a pure FUNCTION may only take intent(in) / value arguments, so the booleans come
+ * back as the function value -- 1 / 0, or -status on failure -- and regex as a procedure without a result (*rc = status). */
+int fx_in_value(const void* pattern, int64_t plen, const void* text, int64_t tlen);
+int fx_match_value(const void* pattern, int64_t plen, const void* text, int64_t tlen);
+void fx_regex_sub(const void* pattern, int64_t plen, const void* text, int64_t tlen, int64_t* from, int64_t* to, int64_t* length,
+                  int* status, int* rc);
 
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t fx_launch_count(void);

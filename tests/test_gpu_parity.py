@@ -633,7 +633,7 @@ def test_statemap_scan_against_the_oracle(monkeypatch):
             t += pieces[int(nrng.integers(0, len(pieces)))]
         texts.append(t)
     texts += [b"\n".join(gen_text(rng) for _ in range(400)), bytes(synth.gen_c4(200000, 0.7)), bytes(synth.gen_c4(70000, None)),
-              b"x" * 100000 + b"ab" + b"y" * 50000, b"", b" ", b"a", b"\xe3\x81\x82" * 30000]
+              b"x" * 1500 + b"ab" + b"y" * 900, b"", b" ", b"a", b"\xe3\x81\x82" * 700]
     pats = [synth.PATTERNS["c4"], synth.PATTERNS["c3"], b"[a-z]+r", rb"\s\S+$", b"[xy]+a[ab]y", rb"[^a]{2,3}$", rb"^\w", b"(a|b)*a(a|b){3}",
             "[ぁ-ん]+a".encode(), rb"\d+-\d+", b"[ab].*c", b".+", b"^$", b"(|^)a"]
     pats += [gen_pattern(rng).encode() for _ in range(60)]
@@ -644,8 +644,9 @@ def test_statemap_scan_against_the_oracle(monkeypatch):
             continue
         c = O.Compiled(pat, 0)
         for text in texts:
-            if len(text) > 60000 and pat not in pats[:5]:
-                continue                       # (the oracle is quadratic in the worst case: long texts only for tame patterns)
+            if len(text) > 6000 and pat not in pats[:2]:
+                continue                       # (the oracle is quadratic in the worst case: long texts only for the two config patterns,
+                                               #  whose attempts end at the next line end / separator)
             arr = np.frombuffer(b"#" + text, dtype=np.uint8)[1:]       # odd address: the sub-chunk grid is address-aligned
             exp = c.regex_buffer(np.ascontiguousarray(arr))
             monkeypatch.setenv("FX_STATEMAP", "2")
@@ -733,3 +734,15 @@ def test_all_matches_and_counts():
         assert counts.tolist() == [len(oracle_all(c, x)) for x in texts], (pat, counts.tolist())
         used += 1
     assert used >= 25
+
+
+def test_c_abi_from_compiled_c():
+    """tests/c/cabi_smoke.c, built by the CMake target (`__graft_entry__.build()`), calls the C ABI from compiled C:
+    on a GPU box it runs the matching entry points and compares with the reference's documented answers"""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "c", "cabi_smoke")
+    if not os.path.exists(exe):
+        pytest.skip("cabi_smoke has not been built (cmake --build build)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "device checks ok" in r.stdout, r.stdout

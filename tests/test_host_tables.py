@@ -166,6 +166,48 @@ def test_batch_validity_and_status_vectors():
     assert fx.is_valid_regex_batch([])[0].size == 0
 
 
+def test_fortran_side_route_from_an_anchored_dfa():
+    """fx_compile_from_dfa: what a Fortran host would hand over after exploring automaton%construct
+    breadth-first -- the anchored code-point DFA + the three literals -- must give the same answers as compiling the
+    pattern text: `.in.`, `.match.`, spans (anchored emulation and the linear span path), against the oracle"""
+    rng = random.Random(31337)
+    pats = [b"foo(bar|baz)", rb"\d{3}-\d{4}", "[α-ωぁ-ん]+\\s\\w{2,8}".encode(), rb"^ERROR.*timeout=\d+$", b"(a|b)*a(a|b){3}", b"a*", b"x|y+",
+            rb"\s\S+", b"[^a-c]x?", "あ+い".encode(), rb"\n$", b"(|^)a", b"ab+c", b"aab*"]
+    pats += [gen_pattern(rng).encode() for _ in range(60)]
+    texts = [gen_text(rng) for _ in range(120)] + [b"", b" ", b"foobar", b"123-4567", b"ERROR x timeout=1\n", "αβ ab_1".encode()]
+    checked = 0
+    for pat in pats:
+        ref = fx.Pattern(pat, "regex")
+        if ref.status != 0:
+            continue
+        d = ref.cp_automaton()
+        lits = ref.literals()
+        for op in ("regex", "in", "match"):
+            if op == "match" and (pat.startswith(b"^") or pat.rstrip(b" ").endswith(b"$") or pat != pat.strip(b" ")):
+                continue                  # operator__match preprocesses its pattern (forgex.F90:182-190): another DFA
+            direct = fx.Pattern(pat, op)
+            if direct.status != 0:
+                continue
+            q = fx.Pattern.from_dfa(op, d["cuts"], d["delta"], d["accept"], d["q0"], lits if op != "match" else direct.literals(), pattern=pat)
+            assert q.status == 0, (pat, op, q.status)
+            m = Model(q)
+            c = O.Compiled(pat, 1 if op == "match" else 0)
+            lin = SpanLinear(q) if op == "regex" and q.span_tables() is not None else None
+            for t in texts:
+                if op == "regex":
+                    f, to = m.regex(t)
+                    of, ot = O.regex(pat, t)[2:4]
+                    assert (f, to) == (of, ot), (pat, t, (f, to), (of, ot))
+                    if lin is not None:
+                        assert lin.regex(t) == (of, ot), (pat, t, "linear")
+                else:
+                    got = m.boolean(t)
+                    exp = O.op_match(pat, t) if op == "match" else O.op_in(pat, t)
+                    assert got == bool(exp), (pat, op, t, got, exp)
+                checked += 1
+    assert checked > 10000, checked
+
+
 # ---- generated patterns and texts: product tables vs oracle -------------------------------------
 ATOMS = ["a", "b", "c", "ab", "ba", ".", "\\d", "\\w", "\\s", "\\S", "\\D", "[ab]", "[^a]", "[a-c]", "[^a-cx]", "\\n",
          "^", "$", "x", " ", "é", "あ", "[ぁ-ん]", "[α-ω]", "\\x41", "\\x{3042}", "[\\x00-\\x20]", "\\t", "-", "}",
