@@ -17,7 +17,7 @@ FX_ERR_BAD_ARGUMENT, FX_ERR_NO_DEVICE = 104, 105
 # every symbol include/forgex_b200.h declares (tests check that the library exports them all)
 SYMBOLS = [
     "fx_status_message", "fx_compile", "fx_compile_from_dfa", "fx_pattern_cp_automaton", "fx_pattern_free", "fx_pattern_get_info", "fx_pattern_set_residency",
-    "fx_pattern_literals", "fx_pattern_tables", "fx_pattern_span_tables", "fx_is_valid_regex", "fx_is_valid_regex_batch",
+    "fx_pattern_literals", "fx_pattern_tables", "fx_pattern_span_tables", "fx_pattern_nfa_tables", "fx_is_valid_regex", "fx_is_valid_regex_batch",
     "fx_match_fixed_dev", "fx_in_fixed_dev", "fx_match_batch_dev", "fx_in_batch_dev", "fx_regex_batch_dev",
     "fx_regex_buffer_work_bytes", "fx_regex_buffer_dev", "fx_buffer_scan_dev", "fx_buffer_scan_all_dev", "fx_buffer_finish_dev",
     "fx_match_fixed", "fx_in_fixed", "fx_match_batch", "fx_in_batch", "fx_regex_batch", "fx_regex_buffer",
@@ -33,7 +33,7 @@ class PatternInfo(C.Structure):
         "literal_only", "residency", "direct", "prefix_mode", "sparse", "sparse_ranges")] + [
         ("sparse_lo", C.c_int32 * 4), ("sparse_hi", C.c_int32 * 4), ("sparse_high", C.c_int32),
         ("sparse_second", C.c_int32), ("sparse_used", C.c_int32), ("prefix_scan", C.c_int32), ("statemap", C.c_int32),
-        ("statemap_used", C.c_int32)]
+        ("nfa_engine", C.c_int32), ("statemap_used", C.c_int32)]
 
 
 _lib = None
@@ -67,6 +67,7 @@ def lib():
                                     C.POINTER(C.c_int32 * 6)]
     L.fx_pattern_span_tables.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32 * 4), C.POINTER(vp),
                                          C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32 * 4)]
+    L.fx_pattern_nfa_tables.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32 * 5)]
     L.fx_is_valid_regex.argtypes = [C.c_char_p, i64, C.POINTER(C.c_int)]
     L.fx_is_valid_regex_batch.argtypes = [vp, vp, i64, vp, vp]
     for name in ("fx_match_fixed_dev", "fx_in_fixed_dev"):

@@ -178,6 +178,21 @@ class Pattern:
                 "rmixed": arr(ptrs[4], nm * 64, C.c_uint8) if ptrs[4].value and nm else None,
                 "cuts": arr(ptrs[5], nc + 1, C.c_int32), "rstart": rsc[2]}
 
+    def nfa_tables(self):
+        """tables of the NFA engine (None for a table-engine handle)"""
+        ptrs = [C.c_void_p() for _ in range(3)]
+        sc = (C.c_int32 * 5)()
+        rc = L.lib().fx_pattern_nfa_tables(self.h, C.byref(ptrs[0]), C.byref(ptrs[1]), C.byref(ptrs[2]), C.byref(sc))
+        if rc == 1:
+            return None
+        _check(rc, "fx_pattern_nfa_tables")
+
+        def arr(p, n, dt):
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(dt)), shape=(n,)).copy()
+        ns, w, nc = sc[0], sc[1], sc[2]
+        return {"trans": arr(ptrs[0], (ns + 1) * nc * w, C.c_uint64).reshape(ns + 1, nc, w), "q0": arr(ptrs[1], w, C.c_uint64),
+                "cuts": arr(ptrs[2], nc + 1, C.c_int32), "exit": sc[3], "q0_accepting": bool(sc[4])}
+
     # ---- host-buffer batch calls (numpy in, numpy out; copies happen inside the library) ----
     # `out=`: caller-provided result arrays (e.g. pinned host memory: the device-to-host copy then runs at PCIe speed)
     @staticmethod

@@ -816,12 +816,41 @@ int build_byte_table(const CpAutomaton& a, bool flag_bits, ByteTable& out, bool 
 // ---------------------------------------------------------------------------------------------
 // whole program
 // ---------------------------------------------------------------------------------------------
+int build_nfa_tables(const Nfa& nfa, NfaTables& t) {
+    Subsets ss(nfa);
+    const int ncls = (int)nfa.cuts.size() - 1;
+    t = NfaTables();
+    t.nstates = nfa.n;
+    t.words = (int)ss.words;
+    t.nclasses = ncls;
+    t.exit = nfa.exit;
+    t.cuts = nfa.cuts;
+    t.q0 = ss.entry_closure;
+    t.q0_accepting = Subsets::has(ss.entry_closure, nfa.exit);
+    const size_t total = ((size_t)nfa.n + 1) * (size_t)ncls * ss.words;
+    if (nfa.n > 8191 || total > (size_t)32 << 20) return ERR_DFA_STATE_CAP;        // 8191 NFA states / 256 MB of sets
+    t.trans.assign(total, 0);
+    for (int s = 1; s <= nfa.n; s++)
+        for (auto& cd : ss.by_class[(size_t)s]) {
+            Bits b(ss.words, 0);
+            for (size_t w = 0; w < ss.words; w++) b[w] = t.trans[((size_t)s * (size_t)ncls + (size_t)cd.first) * ss.words + w];
+            if (!Subsets::has(b, cd.second)) ss.close_from(b, cd.second);
+            for (size_t w = 0; w < ss.words; w++) t.trans[((size_t)s * (size_t)ncls + (size_t)cd.first) * ss.words + w] = b[w];
+        }
+    return OK;
+}
+
 // NFA + literals -> every table the kernels walk (shared by the pattern route and the DFA route below)
 static int compile_from_nfa(const Nfa& nfa, int op, int state_cap, Program& p, bool want_span) {
     p.literal_only = !fortran_blank(p.lit.all);
     p.prefix_active = !fortran_blank(p.lit.prefix);
     p.nfa_states = nfa.n;
     int rc = build_cp_automaton(nfa, (Mode)op, state_cap, p.cp);
+    if (rc == ERR_DFA_STATE_CAP && want_span) {
+        // the eager automaton is too large: the device simulates the NFA instead (want_span is false only for the
+        // optional anchored twin of an `.in.` handle, which is simply absent then)
+        if (build_nfa_tables(nfa, p.nfa_tables) == OK) { p.nfa_engine = true; p.cp = CpAutomaton(); return OK; }
+    }
     if (rc != OK) { p.status = rc; return rc; }
     rc = build_byte_table(p.cp, op == MODE_REGEX, p.bt);
     if (rc != OK) { p.status = rc; return rc; }

@@ -47,6 +47,7 @@ struct DeviceTables {
     uint8_t* sp_classmap = nullptr; uint8_t* sp_endinfo = nullptr;
     uint16_t* r_delta = nullptr; int32_t* r_cuts = nullptr; uint8_t* r_page = nullptr; uint8_t* r_mixed = nullptr;
     uint16_t* sm_reach = nullptr; uint16_t* sm_img = nullptr;
+    uint64_t* nfa_trans = nullptr; uint64_t* nfa_q0 = nullptr; int32_t* nfa_cuts = nullptr;     // NFA engine (patterns past the state cap)
     uint8_t* w_work = nullptr; size_t w_work_cap = 0;
     // grow-only scratch for the host-pointer entry points
     uint8_t* w_buf = nullptr; size_t w_buf_cap = 0;
@@ -204,7 +205,7 @@ bool sparse_first_set(const fx::ByteTable& at, FirstSet& fs, bool for_in) {
     {
         bool ok = true, follow[256];
         for (int c = 0; c < 256; c++) follow[c] = false;
-        for (int b1 = 0; b1 < 256 && ok; b1++) {
+        for (int b1 = 0; b1 < 128 && ok; b1++) {           // (lead bytes as first bytes enter a sequence: the filter lets them pass)
             if (!in_f[b1]) continue;
             const uint16_t w1 = at.table[((size_t)at.q0 << at.row_shift) + at.classmap[b1]];
             if ((w1 & (fxk::W_ACC | fxk::W_INTER)) != 0 || (w1 & fxk::W_STATE) == 0) { ok = false; break; }
@@ -237,6 +238,23 @@ int ensure_device(fx_pattern* p) {
     if (d.device >= 0) return FX_ERR_BAD_ARGUMENT;  // one device per handle
     if (p->dev_touched) return FX_ERR_BAD_ARGUMENT; // an earlier upload failed half-way: the handle is unusable
     p->dev_touched = true;
+    if (p->prog.nfa_engine) {                       // NFA engine: the sets, the cuts and the literals are all there is
+        const fx::NfaTables& nt = p->prog.nfa_tables;
+        CUDA_TRY(cudaMalloc(&d.nfa_trans, nt.trans.size() * 8 + 16));
+        CUDA_TRY(cudaMemcpy(d.nfa_trans, nt.trans.data(), nt.trans.size() * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&d.nfa_q0, nt.q0.size() * 8 + 16));
+        CUDA_TRY(cudaMemcpy(d.nfa_q0, nt.q0.data(), nt.q0.size() * 8, cudaMemcpyHostToDevice));
+        std::vector<int32_t> cuts(nt.cuts.begin(), nt.cuts.end());
+        CUDA_TRY(cudaMalloc(&d.nfa_cuts, cuts.size() * 4 + 16));
+        CUDA_TRY(cudaMemcpy(d.nfa_cuts, cuts.data(), cuts.size() * 4, cudaMemcpyHostToDevice));
+        std::string lits = p->prog.lit.all + p->prog.lit.prefix + p->prog.lit.suffix;
+        CUDA_TRY(cudaMalloc(&d.lits, lits.size() + 16));
+        if (!lits.empty()) CUDA_TRY(cudaMemcpy(d.lits, lits.data(), lits.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&d.w_best, 64));
+        CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
+        d.device = dev;
+        return FX_OK;
+    }
     const fx::ByteTable& bt = p->prog.bt;
     size_t tb = (bt.table.size() * 2 + 15) & ~(size_t)15, db = (bt.direct.size() * 2 + 15) & ~(size_t)15;
     CUDA_TRY(cudaMalloc(&d.table, tb + 16));
@@ -375,6 +393,50 @@ int occupancy_grid(K kernel, int threads, size_t smem, int sm_count, int& blocks
     return FX_OK;
 }
 
+// ---- NFA engine (patterns past the eager state cap): parameters and launches ---------------------
+void nfa_params(fx_pattern* p, KParams& k, NfaEngine& N) {
+    const fx::NfaTables& nt = p->prog.nfa_tables;
+    const DeviceTables& d = p->dev;
+    memset(&k, 0, sizeof(k));
+    const fx::Literals& L = p->prog.lit;
+    k.lits = d.lits;
+    k.all_len = (int)L.all.size(); k.pre_len = (int)L.prefix.size(); k.suf_len = (int)L.suffix.size();
+    k.all_active = p->prog.literal_only ? 1 : 0;
+    k.pre_active = fx::fortran_blank(L.prefix) ? 0 : 1;
+    k.suf_active = fx::fortran_blank(L.suffix) ? 0 : 1;
+    k.q0_accepting = nt.q0_accepting ? 1 : 0;
+    N.trans = d.nfa_trans; N.q0 = d.nfa_q0; N.cuts = d.nfa_cuts;
+    N.words = nt.words; N.nclasses = nt.nclasses; N.exit_state = nt.exit;
+    auto class_of = [&](int cp) { return (int)(std::upper_bound(nt.cuts.begin(), nt.cuts.end(), cp) - nt.cuts.begin()) - 1; };
+    N.nul_class = class_of(0); N.ffff_class = class_of(0xFFFF);
+    N.q0_accepting = k.q0_accepting;
+}
+int nfa_grid(fx_pattern* p, int64_t n) {
+    long long want = (n + 63) / 64, cap = (long long)p->dev.sm_count * 16;
+    int g = (int)(want < cap ? want : cap);
+    return g < 1 ? 1 : g;
+}
+int launch_nfa_bool(fx_pattern* p, int op, const uint8_t* buf, const int64_t* off, int64_t stride, int64_t n, uint8_t* out, cudaStream_t s) {
+    if (n <= 0) return n < 0 ? FX_ERR_BAD_ARGUMENT : FX_OK;
+    KParams k;
+    NfaEngine N;
+    nfa_params(p, k, N);
+    if (op == FX_OP_MATCH) k_nfa_bool<0><<<nfa_grid(p, n), 64, 0, s>>>(k, N, buf, off, stride, n, out);
+    else k_nfa_bool<1><<<nfa_grid(p, n), 64, 0, s>>>(k, N, buf, off, stride, n, out);
+    g_launches++;
+    return cuda_status(cudaGetLastError());
+}
+int launch_nfa_regex(fx_pattern* p, const uint8_t* buf, const int64_t* off, int64_t n, int64_t single_len, int64_t* from, int64_t* to,
+                     cudaStream_t s) {
+    if (n <= 0) return n < 0 ? FX_ERR_BAD_ARGUMENT : FX_OK;
+    KParams k;
+    NfaEngine N;
+    nfa_params(p, k, N);
+    k_nfa_regex<<<nfa_grid(p, n), 64, 0, s>>>(k, N, buf, off, n, single_len, from, to);
+    g_launches++;
+    return cuda_status(cudaGetLastError());
+}
+
 // ---- launchers -----------------------------------------------------------------------------
 inline size_t staged_bytes(const Plan& pl) { return (size_t)((pl.table_bytes + 15) & ~15); }
 
@@ -415,6 +477,7 @@ template <int OP>
 int launch_fixed(fx_pattern* p, const uint8_t* buf, int64_t n, int64_t stride, uint8_t* out, cudaStream_t s) {
     if (n < 0 || stride < 0) return FX_ERR_BAD_ARGUMENT;
     if (n == 0) return FX_OK;
+    if (p->prog.nfa_engine) return launch_nfa_bool(p, OP, buf, nullptr, stride, n, out, s);
     Plan pl;
     int rc = make_plan(p, pl);
     if (rc) return rc;
@@ -629,6 +692,7 @@ int launch_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, int64_t
                   cudaStream_t s) {
     if (n < 0 || total < 0) return FX_ERR_BAD_ARGUMENT;
     if (n == 0) return FX_OK;
+    if (p->prog.nfa_engine) return launch_nfa_bool(p, OP, buf, off, 0, n, out, s);
     Plan pl;
     int rc = make_plan(p, pl);
     if (rc) return rc;
@@ -723,6 +787,7 @@ int launch_regex_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, i
                         int64_t* from, int64_t* to, cudaStream_t s) {
     if (n < 0 || total < 0) return FX_ERR_BAD_ARGUMENT;
     if (n == 0) return FX_OK;
+    if (p->prog.nfa_engine) return launch_nfa_regex(p, buf, off, n, 0, from, to, s);
     Plan pl;
     int rc = make_plan(p, pl);
     if (rc) return rc;
@@ -796,13 +861,15 @@ int launch_scan_sparse(fx_pattern* p, const Plan& pl, const uint8_t* buf, const 
     fill_sweep(p->first, sp);
     const FirstSet& f = p->first;
     const bool one = f.sweep_nr == 1 && f.sweep_lo[0] == f.sweep_hi[0];
-    // (not for a window whose scanned starts reach its open end: the follower of the last start is not in memory)
-    if (f.set2 && !f.high && f.sweep_nr >= 1 && f.sweep_nr <= 2 && (W.last || W.start_hi < W.len) &&
-        env_int("FX_SWEEP_SET2", 1)) {                                                                  // two-byte test for sets
+    // the two-byte test of the unit phase (the follower of a unit's last byte is never assumed)
+    if (f.set2 && f.sweep_nr >= 1 && f.sweep_nr <= 2 && env_int("FX_SWEEP_SET2", 1)) {
         fill_sweep_set2(f, sp);
-        if (one) return launch_scan_sparse_t<KIND, -1, false, false, true>(p, pl, sp, buf, W, best, s, gate, run_if, bg);
-        if (f.sweep_nr == 1) return launch_scan_sparse_t<KIND, 1, false, false, true>(p, pl, sp, buf, W, best, s, gate, run_if, bg);
-        return launch_scan_sparse_t<KIND, 2, false, false, true>(p, pl, sp, buf, W, best, s, gate, run_if, bg);
+        if (one) return f.high ? launch_scan_sparse_t<KIND, -1, true, false, true>(p, pl, sp, buf, W, best, s, gate, run_if, bg)
+                               : launch_scan_sparse_t<KIND, -1, false, false, true>(p, pl, sp, buf, W, best, s, gate, run_if, bg);
+        if (f.sweep_nr == 1) return f.high ? launch_scan_sparse_t<KIND, 1, true, false, true>(p, pl, sp, buf, W, best, s, gate, run_if, bg)
+                                           : launch_scan_sparse_t<KIND, 1, false, false, true>(p, pl, sp, buf, W, best, s, gate, run_if, bg);
+        return f.high ? launch_scan_sparse_t<KIND, 2, true, false, true>(p, pl, sp, buf, W, best, s, gate, run_if, bg)
+                      : launch_scan_sparse_t<KIND, 2, false, false, true>(p, pl, sp, buf, W, best, s, gate, run_if, bg);
     }
     if (f.sweep_nr == 0) return launch_scan_sparse_t<KIND, 0, true, false>(p, pl, sp, buf, W, best, s, gate, run_if, bg);
     if (one) return f.high ? launch_scan_sparse_t<KIND, -1, true, false>(p, pl, sp, buf, W, best, s, gate, run_if, bg)
@@ -834,6 +901,7 @@ int launch_scan(fx_pattern* p, const uint8_t* buf, const ScanWindow& W, unsigned
                 int mode = SCAN_AUTO, const unsigned long long* gate = nullptr, const unsigned long long* run_if = nullptr,
                 ScanBudget bg = ScanBudget{nullptr, nullptr, 0ull}) {
     if (W.len < 0 || W.start_lo < 0 || W.start_hi > W.len || W.start_lo > W.start_hi) return FX_ERR_BAD_ARGUMENT;
+    if (p->prog.nfa_engine) return FX_ERR_DFA_STATE_CAP;        // the window forms need the table engine
     const bool prefixed = p->prog.prefix_active && !p->prog.literal_only;
     // a prefix whose occurrences can overlap, or a non-empty suffix, make the candidate list sequential: not handled
     if (prefixed && !p->prefix_scan) return FX_ERR_PREFILTER_UNSUPPORTED;
@@ -872,6 +940,7 @@ int launch_scan(fx_pattern* p, const uint8_t* buf, const ScanWindow& W, unsigned
 int launch_finish(fx_pattern* p, const uint8_t* buf, const ScanWindow& W, const unsigned long long* best,
                   int64_t* from_to, int whole_text, cudaStream_t s, const unsigned long long* done = nullptr,
                   const unsigned long long* use_alt = nullptr, const unsigned long long* best_alt = nullptr) {
+    if (p->prog.nfa_engine) return FX_ERR_DFA_STATE_CAP;
     Plan pl;
     int rc = make_plan(p, pl);
     if (rc) return rc;
@@ -956,6 +1025,8 @@ int launch_statemap(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* fro
 int launch_buffer(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* from_to, unsigned long long* work,
                   cudaStream_t s) {
     if (len < 0) return FX_ERR_BAD_ARGUMENT;
+    if (p->prog.nfa_engine)          // one thread walks the buffer with the reference's own loop: defined, not fast
+        return launch_nfa_regex(p, buf, nullptr, 1, len, from_to, from_to + 1, s);
     CUDA_TRY(cudaMemsetAsync(work, 0, 128, s));
     CUDA_TRY(cudaMemsetAsync(work, 0xFF, 8, s));
     CUDA_TRY(cudaMemsetAsync(work + 12, 0xFF, 8, s));
@@ -1031,6 +1102,7 @@ struct CompileSource {
 };
 
 static int finish_compile(fx_pattern* p, const CompileSource& src, int op, fx_pattern** out) {
+    if (p->prog.status == fx::OK && p->prog.nfa_engine) { *out = p; return fx::OK; }     // NFA engine: no tables to derive
     if (p->prog.status == fx::OK && op == FX_OP_IN && !p->prog.literal_only) {
         // `.in.` consults the prefix prefilter: keep the anchored automaton to replay it exactly when needed.  The same
         // automaton drives the sparse-start kernel; without a prefix it is optional and built under a smaller cap.
@@ -1096,7 +1168,7 @@ int fx_compile(const void* pattern, int64_t plen, int op, fx_pattern** out) {
     std::string pat(static_cast<const char*>(pattern), (size_t)plen);
     CompileSource src;
     src.pattern = &pat;
-    src.compile(op, STATE_CAP, p->prog, true);
+    src.compile(op, env_int("FX_STATE_CAP", STATE_CAP), p->prog, true);      // (FX_STATE_CAP: tests force the NFA engine with a tiny cap)
     return finish_compile(p, src, op, out);
 }
 
@@ -1134,6 +1206,18 @@ int fx_pattern_cp_automaton(const fx_pattern* p, const int32_t** cuts, const int
     return FX_OK;
 }
 
+// the NFA engine's tables (tests / tools): scalars = {NFA states, 64-bit words per set, classes, exit state, q0 accepting}
+int fx_pattern_nfa_tables(const fx_pattern* p, const uint64_t** trans, const uint64_t** q0, const int32_t** cuts, int32_t scalars[5]) {
+    if (!p || p->prog.status != fx::OK) return FX_ERR_BAD_ARGUMENT;
+    if (!p->prog.nfa_engine) return 1;
+    const fx::NfaTables& t = p->prog.nfa_tables;
+    if (trans) *trans = t.trans.data();
+    if (q0) *q0 = t.q0.data();
+    if (cuts) *cuts = reinterpret_cast<const int32_t*>(t.cuts.data());
+    if (scalars) { scalars[0] = t.nstates; scalars[1] = t.words; scalars[2] = t.nclasses; scalars[3] = t.exit; scalars[4] = t.q0_accepting ? 1 : 0; }
+    return FX_OK;
+}
+
 // value-returning / subroutine-shaped forms of the one-pattern-one-text entry points, for `pure` Fortran callers: a
 // pure FUNCTION may only have intent(in) / value arguments, so `.in.` and `.match.` come back as the function value
 // (1 / 0, or -status on failure), and regex as a procedure without a result (a pure SUBROUTINE may have intent(out)).
@@ -1162,6 +1246,7 @@ int fx_pattern_free(fx_pattern* p) {
         cudaFree(d.sp_table); cudaFree(d.sp_direct); cudaFree(d.sp_classmap); cudaFree(d.sp_endinfo);
         cudaFree(d.r_delta); cudaFree(d.r_cuts); cudaFree(d.r_page); cudaFree(d.r_mixed);
         cudaFree(d.sm_reach); cudaFree(d.sm_img); cudaFree(d.w_work);
+        cudaFree(d.nfa_trans); cudaFree(d.nfa_q0); cudaFree(d.nfa_cuts);
         cudaFree(d.w_buf); cudaFree(d.w_off); cudaFree(d.w_out); cudaFree(d.w_span); cudaFree(d.w_best);
     }
     delete p;
@@ -1199,6 +1284,7 @@ int fx_pattern_get_info(const fx_pattern* p, fx_pattern_info* info) {
     }
     info->sparse_used = p->last_sparse;
     info->prefix_scan = p->prefix_scan ? 1 : 0;
+    info->nfa_engine = g.nfa_engine ? 1 : 0;
     info->statemap = p->statemap ? 1 : 0;
     info->statemap_used = p->last_statemap;
     return FX_OK;
@@ -1348,6 +1434,7 @@ int fx_regex_count_batch_dev(fx_pattern* p, const uint8_t* d_buf, const int64_t*
     if (rc) return rc;
     if (n < 0 || total_bytes < 0 || !d_counts) return FX_ERR_BAD_ARGUMENT;
     if (n == 0) return FX_OK;
+    if (p->prog.nfa_engine) return FX_ERR_DFA_STATE_CAP;        // (counting needs the table engine)
     Plan pl;
     if ((rc = make_plan(p, pl))) return rc;
     SpanParams sp;
@@ -1378,6 +1465,7 @@ int fx_regex_buffer_all_dev(fx_pattern* p, const uint8_t* d_buf, int64_t len, in
     // the loop's own state sits behind the scans' flags in the work area: words [24..27] state, [28..29] from_to of a far step
     int64_t* state = reinterpret_cast<int64_t*>(work + 24);
     int64_t* ft = reinterpret_cast<int64_t*>(work + 28);
+    if (p->prog.nfa_engine) return FX_ERR_DFA_STATE_CAP;
     CUDA_TRY(cudaMemsetAsync(state, 0, 6 * 8, s));
     Plan pl;
     if ((rc = make_plan(p, pl))) return rc;

@@ -189,6 +189,23 @@ struct ByteTable {
 
 int build_byte_table(const CpAutomaton& a, bool flag_bits, ByteTable& out, bool span_words = false);
 
+// NFA simulation tables: the engine of patterns whose EAGER automaton passes the state cap.  Forgex builds its DFA
+// lazily and only ever aborts on the number of states a text makes it VISIT (src/lazy_dfa/lazy_dfa_graph_m.F90:90-92);
+// `.*a(a|b){500}c{20}` (test/test_api/test_case_005.f90:76-104) has an astronomically large DFA and a tiny visited one.
+// Such patterns are matched on the device by the subset step itself, like the reference does per character
+// (src/automaton_m.F90:199-381), on bit sets: trans[(s * nclasses + c) * words ..] = closure(move({s}, class c)).
+struct NfaTables {
+    int nstates = 0;     // bits 1..nstates are NFA states (bit 0 unused)
+    int words = 0;       // 64-bit words per set
+    int nclasses = 0;
+    int exit = 2;
+    std::vector<int> cuts;              // nclasses + 1
+    std::vector<uint64_t> trans;        // (nstates + 1) x nclasses x words
+    std::vector<uint64_t> q0;           // closure(entry)
+    bool q0_accepting = false;
+};
+int build_nfa_tables(const Nfa& nfa, NfaTables& out);
+
 // Whole compiled pattern (host side).
 struct Program {
     int op = 0;
@@ -202,6 +219,8 @@ struct Program {
     ByteTable bt;
     // FX_OP_REGEX only: the linear-time span path (forward "ordered groups" automaton + reverse automaton);
     // absent (has_span == false) when a cap is exceeded or the pattern uses the prefix prefilter
+    bool nfa_engine = false;     // the eager automaton passes the cap: matched by NFA simulation on the device (nfa_tables)
+    NfaTables nfa_tables;
     bool has_span = false;
     CpAutomaton span_cp;
     ByteTable span_bt;

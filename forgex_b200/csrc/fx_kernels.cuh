@@ -373,6 +373,105 @@ __device__ __forceinline__ void brute_force_smem(const Anchored& A, const TBL& T
     }
 }
 
+// ---- NFA engine: patterns whose eager automaton passes the state cap -------------------------------------
+// The reference's own per-character step (automaton%construct, src/automaton_m.F90:333-381: reachable set, epsilon
+// closure) on bit sets: cur' = OR over s in cur of trans[s][class(symbol)], closures precomputed by the host.  One
+// thread per text; sets live in local memory.  Same drivers as the table engine: attempt_at / brute_force_flat are
+// overloaded on the engine type, so including_exact / eval_regex below serve both.
+static constexpr int NFA_MAX_WORDS = 128;        // 8191 NFA states
+struct NfaEngine {
+    const uint64_t* trans;      // (nstates + 1) x nclasses x words
+    const uint64_t* q0;         // closure(entry)
+    const int32_t* cuts;        // nclasses + 1 ascending code points
+    int words, nclasses, exit_state, nul_class, ffff_class, q0_accepting;
+};
+__device__ inline int nfa_class(const NfaEngine& N, uint32_t cp) {
+    int lo = 0, hi = N.nclasses;               // largest c with cuts[c] <= cp  (cuts[nclasses] is past every code point)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((uint32_t)__ldg(N.cuts + mid) <= cp) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+// cur <- step(cur, class c); returns false when the result is empty
+__device__ inline bool nfa_step(const NfaEngine& N, uint64_t* cur, uint64_t* nxt, int c) {
+    for (int w = 0; w < N.words; w++) nxt[w] = 0;
+    for (int w = 0; w < N.words; w++) {
+        uint64_t bits = cur[w];
+        while (bits) {
+            const int s = (w << 6) + __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            const uint64_t* row = N.trans + ((size_t)s * (size_t)N.nclasses + (size_t)c) * (size_t)N.words;
+            for (int k = 0; k < N.words; k++) nxt[k] |= __ldg(row + k);
+        }
+    }
+    bool any = false;
+    for (int w = 0; w < N.words; w++) { cur[w] = nxt[w]; any = any || nxt[w] != 0; }
+    return any;
+}
+__device__ __forceinline__ bool nfa_accepting(const NfaEngine& N, const uint64_t* cur) {
+    return (cur[N.exit_state >> 6] >> (N.exit_state & 63)) & 1ull;
+}
+// the symbol at text index j under the reference's strict decoder: class and length in bytes
+template <class FETCH>
+__device__ inline int nfa_symbol(const NfaEngine& N, FETCH fetch, int64_t len, int64_t j, int& nbytes) {
+    const uint32_t b = fetch(j);
+    nbytes = char_len(fetch, len, j);
+    if (b < 0x80) return nfa_class(N, b);
+    if (nbytes == 1) return N.ffff_class;      // stray or malformed byte: U+FFFF (api_internal_m.F90:129-133)
+    uint32_t cp = nbytes == 2 ? (b & 0x1Fu) : nbytes == 3 ? (b & 0x0Fu) : (b & 0x07u);
+    for (int k = 1; k < nbytes; k++) cp = (cp << 6) | (fetch(j + k) & 0x3Fu);
+    return nfa_class(N, cp);
+}
+// attempt from position `start` of S = NUL || text || NUL: same contract as the table engine's attempt_at
+template <class FETCH>
+__device__ inline int64_t attempt_at(const Anchored&, const NfaEngine& N, FETCH fetch, int64_t len, int64_t start) {
+    uint64_t cur[NFA_MAX_WORDS], nxt[NFA_MAX_WORDS];
+    for (int w = 0; w < N.words; w++) cur[w] = __ldg(N.q0 + w);
+    int64_t last = -1, j = start - 2;
+    if (start == 1) {
+        if (!nfa_step(N, cur, nxt, N.nul_class)) return -1;
+        if (nfa_accepting(N, cur)) last = 0;
+        j = 0;
+    }
+    while (j <= len) {
+        int nb = 1;
+        const int c = j < len ? nfa_symbol(N, fetch, len, j, nb) : N.nul_class;      // virtual trailing NUL at j == len
+        if (!nfa_step(N, cur, nxt, c)) break;
+        j += nb;
+        if (nfa_accepting(N, cur)) last = j;
+    }
+    return last;
+}
+// the brute-force search (api_internal_m.F90:108-155): the leading NUL, then every character boundary, in order
+template <class FETCH>
+__device__ inline void brute_force_flat(const Anchored& A, const NfaEngine& N, FETCH fetch, int64_t len, int64_t& from, int64_t& to) {
+    from = 0; to = 0;
+    int64_t last = attempt_at(A, N, fetch, len, 1);
+    if (last >= 0) { const int64_t e = last < len ? last : len; if (e > 0) { from = 1; to = e; } return; }
+    for (int64_t cur = 0; cur < len; cur += char_len(fetch, len, cur)) {
+        last = attempt_at(A, N, fetch, len, cur + 2);
+        if (last >= 0) { from = cur + 1; to = last < len ? last : len; return; }
+    }
+}
+// do_matching_exactly's walk (api_internal_m.F90:247-298) on the NFA
+template <class FETCH>
+__device__ inline bool nfa_match(const NfaEngine& N, FETCH fetch, int64_t len) {
+    if (len == 0) return N.q0_accepting != 0;
+    uint64_t cur[NFA_MAX_WORDS], nxt[NFA_MAX_WORDS], keep[NFA_MAX_WORDS];
+    for (int w = 0; w < N.words; w++) { cur[w] = __ldg(N.q0 + w); keep[w] = cur[w]; }
+    if (!nfa_step(N, cur, nxt, N.nul_class))                  // the leading NUL has no transition: skipped (:280-289)
+        for (int w = 0; w < N.words; w++) cur[w] = keep[w];
+    for (int64_t j = 0; j < len; ) {
+        int nb = 1;
+        const int c = nfa_symbol(N, fetch, len, j, nb);
+        if (!nfa_step(N, cur, nxt, c)) return false;
+        j += nb;
+    }
+    if (nfa_accepting(N, cur)) return true;
+    return nfa_step(N, cur, nxt, N.nul_class) && nfa_accepting(N, cur);
+}
+
 // do_matching_including for a non-blank text (api_internal_m.F90:76-164): candidate starts are either
 // every character boundary (no usable prefix) or the non-overlapping occurrences of the extracted
 // prefix in S (utility_m.f90:58-117), cut short by the last occurrence of the extracted suffix.
@@ -1840,12 +1939,40 @@ __device__ __forceinline__ bool budget_spent(const ScanBudget& B, unsigned long 
     return *reinterpret_cast<volatile unsigned long long*>(B.abort) != 0;
 }
 
+// The part of an anchored attempt behind its plain stretch: from state `st` in front of text index `at` (no accept seen
+// so far) with the full bookkeeping of run_attempt -- accepts, multi-byte sequences and their U+FFFF replay, the
+// virtual trailing NUL.  `open_end`: the window is followed by text this GPU does not hold; an attempt that reaches the
+// window end alive and without an accept cannot be decided here (*overflow).  Budgeted scans tick here as well.
+template <int KIND>
+__device__ __noinline__ bool attempt_tail(const KParams& p, const Table<KIND>& T, const uint8_t* __restrict__ buf, int64_t len,
+                                          uint32_t st, int64_t at, bool open_end, unsigned long long* overflow, const ScanBudget& B) {
+    uint32_t w = st;
+    int64_t seq = 0, last = -1;
+    bool inter = false;
+    for (int64_t j = at; j <= len; j++) {
+        if (B.limit != 0 && ((j - at) & (BUDGET_TICK - 1)) == BUDGET_TICK - 1 && budget_spent(B, BUDGET_TICK)) return false;
+        if (j == len && open_end) { if (last >= 0) return true; atomicAdd(overflow, 1ull); return false; }
+        const uint32_t c = j < len ? __ldg(buf + j) : 0u;            // virtual trailing NUL at j == len
+        if (inter && (c & 0xC0) != 0x80) {                            // sequence broken: pending bytes replay as U+FFFF
+            const uint32_t f = __ldg(p.flags + (w & W_STATE));
+            for (int k = 1; k <= (int)(j - seq); k++) if (f & (SF_FAILACC1 << (k - 1))) last = seq + k;
+            inter = false;
+        }
+        const uint32_t nw = T.next(w & W_STATE, c);
+        if ((nw & W_INTER) && !inter) seq = j;
+        inter = (nw & W_INTER) != 0;
+        w = nw;
+        if (w & W_ACC) last = j + 1;
+        if ((w & W_STATE) == 0) break;
+    }
+    return last >= 0;
+}
+
 template <int KIND>
 __device__ __forceinline__ bool try_start(const KParams& p, const Table<KIND>& T, const uint8_t* __restrict__ buf,
                                           int64_t len, int64_t pos, uint32_t b, bool open_end,
                                           unsigned long long* overflow, const ScanBudget& B, uint32_t& acc) {
     if ((b & 0xC0) == 0x80 && !continuation_is_boundary(buf, len, pos)) return false;
-    const Anchored A{p.flags, p.start_nul, p.q0};
     // The plain stretch first: as long as the next state neither accepts nor enters a multi-byte sequence, a step is
     // one load and one lookup (for C4 that is the whole line behind `^ERROR`).  Whatever comes then goes through the
     // general loop, from the state and position reached (no accept has been seen so far).
@@ -1871,50 +1998,7 @@ __device__ __forceinline__ bool try_start(const KParams& p, const Table<KIND>& T
         if (acc >= BUDGET_TICK) { const uint32_t a = acc; acc = 0; if (budget_spent(B, a)) return false; }
         if (out || at >= len) break;
     }
-    if (B.limit != 0) {          // a budgeted scan: the general loop in ticks as well (it is the rare part of an attempt)
-        uint32_t w = st;
-        int64_t seq = 0, last = -1;
-        bool inter = false;
-        for (int64_t j = at; j <= len; j++) {
-            if (((j - at) & (BUDGET_TICK - 1)) == BUDGET_TICK - 1 && budget_spent(B, BUDGET_TICK)) return false;
-            if (j == len && open_end) { if (last >= 0) return true; atomicAdd(overflow, 1ull); return false; }
-            const uint32_t c = j < len ? __ldg(buf + j) : 0u;
-            if (inter && (c & 0xC0) != 0x80) {
-                const uint32_t f = __ldg(A.flags + (w & W_STATE));
-                for (int k = 1; k <= (int)(j - seq); k++) if (f & (SF_FAILACC1 << (k - 1))) last = seq + k;
-                inter = false;
-            }
-            const uint32_t nw = T.next(w & W_STATE, c);
-            if ((nw & W_INTER) && !inter) seq = j;
-            inter = (nw & W_INTER) != 0;
-            w = nw;
-            if (w & W_ACC) last = j + 1;
-            if ((w & W_STATE) == 0) break;
-        }
-        return last >= 0;
-    }
-    if (!open_end) return run_attempt(A, T, FetchGlobal{buf}, len, st, at, -1) >= 0;
-    // open end: walk only the bytes we have; alive at the end -> undecided
-    uint32_t w = st;
-    int64_t seq = 0, last = -1;
-    bool inter = false;
-    for (int64_t j = at; j < len; j++) {
-        const uint32_t c = __ldg(buf + j);
-        if (inter && (c & 0xC0) != 0x80) {
-            const uint32_t f = __ldg(A.flags + (w & W_STATE));
-            for (int k = 1; k <= (int)(j - seq); k++) if (f & (SF_FAILACC1 << (k - 1))) last = seq + k;
-            inter = false;
-        }
-        const uint32_t nw = T.next(w & W_STATE, c);
-        if ((nw & W_INTER) && !inter) seq = j;
-        inter = (nw & W_INTER) != 0;
-        w = nw;
-        if (w & W_ACC) last = j + 1;
-        if ((w & W_STATE) == 0) return last >= 0;
-    }
-    if (last >= 0) return true;        // already a counted accept: this start wins whatever follows
-    atomicAdd(overflow, 1ull);
-    return false;
+    return attempt_tail(p, T, buf, len, st, at, open_end, overflow, B);
 }
 
 // K4 window description: the kernel scans starts [start_lo, start_hi) of a window of `len` bytes that is a piece of
@@ -2074,8 +2158,10 @@ __global__ void __launch_bounds__(256) k_buffer_scan(KParams p, const uint8_t* _
 //           table steps (an open window end leaves the second undecided); survivors are queued;
 //   starts  32 at a time: boundary check + anchored attempt from global memory (try_start), 64-bit atomicMin.
 // shared memory: classmap 256 | table | 8 warps x (unit queue 64 x int64 | start queue 64 x int64)
+// per warp: unit queue 64 x (index int64 | the unit's 32 bytes) | start queue 64 x int64
+static constexpr int SCAN_WARP_BYTES = 64 * 8 + 64 * 32 + 64 * 8;
 __host__ __device__ __forceinline__ int scan_sparse_smem_bytes(int table_smem_bytes) {
-    return ((256 + table_smem_bytes + 15) & ~15) + 8 * 2 * 64 * 8;
+    return ((256 + table_smem_bytes + 15) & ~15) + 8 * SCAN_WARP_BYTES;
 }
 
 //
@@ -2098,8 +2184,10 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
     uint8_t* s_cmap = smem;
     uint8_t* s_table = smem + 256;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int64_t* s_units = reinterpret_cast<int64_t*>(smem + ((256 + table_smem_bytes + 15) & ~15)) + warp * 128;
-    int64_t* s_starts = s_units + 64;
+    uint8_t* s_warp = smem + ((256 + table_smem_bytes + 15) & ~15) + warp * SCAN_WARP_BYTES;
+    int64_t* s_units = reinterpret_cast<int64_t*>(s_warp);
+    uint4* s_udata = reinterpret_cast<uint4*>(s_warp + 64 * 8);      // the 32 bytes of a queued unit: no second trip to L2 / DRAM
+    int64_t* s_starts = reinterpret_cast<int64_t*>(s_warp + 64 * 8 + 64 * 32);
     Table<KIND> T = stage_table<KIND>(p, s_table, s_cmap);
     __syncthreads();
     const uint32_t q0 = (uint32_t)p.q0;
@@ -2126,12 +2214,54 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
     const int64_t pos_base = (int64_t)ubase - (int64_t)gbuf;                      // window position of unit 0's first byte (may be < start_lo)
     int uqn = 0, sqn = 0;
 
+    // Attempts: the lanes are a pool of walkers over the queued starts.  A lane without an attempt claims the next
+    // start; all lanes walk up to 64 plain steps (one load, one lookup each: for C4 the whole line behind `^ERROR`) and
+    // the warp looks again, so that lines of different lengths do not leave lanes idle.  Whatever lies behind the plain
+    // stretch -- an accept, a multi-byte sequence, the end of the window -- goes through attempt_tail.
     auto run_starts = [&](int count) {
         __syncwarp();
-        if (lane < count && (phases & 2)) {
-            const int64_t pos = s_starts[lane];
-            if (try_start(p, T, buf, len, pos, __ldg(buf + pos), open_end, overflow, B, acc))
-                atomicMin(best, (unsigned long long)(W.origin + pos) + 2);
+        if (!(phases & 2)) return;
+        int next = 0;
+        bool have = false;
+        int64_t pos = 0, at = 0;
+        uint32_t st = 0;
+        for (;;) {
+            const uint32_t idle = __ballot_sync(FULL, !have);
+            if (idle != 0 && next < count) {
+                const int mine = next + __popc(idle & ((1u << lane) - 1));
+                if (!have && mine < count) {
+                    pos = s_starts[mine];
+                    const uint32_t b0 = __ldg(buf + pos);
+                    if (!((b0 & 0xC0) == 0x80 && !continuation_is_boundary(buf, len, pos))) {
+                        have = true; st = q0; at = pos;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) if (pos + 32 * k < len) prefetch_l1(buf + pos + 32 * k);
+                    }
+                }
+                next += __popc(idle);
+            }
+            if (!__any_sync(FULL, have)) { if (next >= count) break; else continue; }
+            if (have) {
+                const int64_t stop = at + 64 < len ? at + 64 : len;
+                const int64_t from = at;
+                bool out = false, dead = false;
+                if (at + 160 < len) prefetch_l1(buf + at + 160);
+                while (at < stop) {
+                    const uint32_t nw = T.next(st, __ldg(buf + at));
+                    if (nw & (W_ACC | W_INTER)) { out = true; break; }
+                    if (nw == 0) { dead = true; break; }
+                    st = nw;
+                    at++;
+                }
+                acc += (uint32_t)(at - from);
+                if (acc >= BUDGET_TICK) { const uint32_t a = acc; acc = 0; if (budget_spent(B, a)) dead = true; }
+                if (dead) have = false;
+                else if (out || at >= len) {
+                    if (attempt_tail(p, T, buf, len, st, at, open_end, overflow, B))
+                        atomicMin(best, (unsigned long long)(W.origin + pos) + 2);
+                    have = false;
+                }
+            }
         }
         __syncwarp();
     };
@@ -2141,12 +2271,26 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
         int64_t P = 0;
         if (lane < count && (phases & 1)) {
             const int64_t u = s_units[lane];
-            const uintptr_t ua = ubase + ((uintptr_t)u << 5);
-            const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(ua)), v1 = __ldg(reinterpret_cast<const uint4*>(ua + 16));
+            const uint4 v0 = s_udata[2 * lane], v1 = s_udata[2 * lane + 1];
             cand = pack_byte_flags(first_mask<NR, HIGH>(sp, v0.x)) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.y)) << 4) |
                    (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.z)) << 8) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.w)) << 12) |
                    (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.x)) << 16) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.y)) << 20) |
                    (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.z)) << 24) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.w)) << 28);
+            if (SET2) {
+                // two-byte test: a candidate whose follower is none of the (at most two) byte values that can follow a
+                // first byte -- nor a lead byte, if those can -- is dead.  The follower of the unit's last byte is not
+                // here: that candidate stays.  (Lead bytes >= 0xC0 as FIRST bytes enter a sequence: they stay as well.)
+                const uint32_t w8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                uint32_t fol = 0, lead = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const uint32_t xa = w8[q] ^ sp.second, xb = w8[q] ^ sp.second_b;
+                    const uint32_t z2 = ((xa - 0x01010101u) & ~xa) | ((xb - 0x01010101u) & ~xb) | (w8[q] & sp.second_high);
+                    fol |= pack_byte_flags(z2) << (4 * q);
+                    lead |= pack_byte_flags(w8[q]) << (4 * q);
+                }
+                cand &= (fol >> 1) | 0x80000000u | lead;
+            }
             P = pos_base + (u << 5);
             if (P < W.start_lo) cand &= 0xFFFFFFFFu << (int)(W.start_lo - P);
             if (P + 32 > W.start_hi) cand &= (P >= W.start_hi) ? 0u : (0xFFFFFFFFu >> (int)(P + 32 - W.start_hi));
@@ -2182,10 +2326,9 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
             if (m) {
                 if (sv) s_starts[sqn + __popc(m & ((1u << lane) - 1))] = pos;
                 sqn += __popc(m);
-                if (sqn >= 32) {
-                    run_starts(32);
-                    if (lane < sqn - 32) { const int64_t x = s_starts[32 + lane]; s_starts[lane] = x; }
-                    sqn -= 32;
+                if (sqn >= 32) {           // (at most 63 are waiting: the pool takes them all)
+                    run_starts(sqn);
+                    sqn = 0;
                     __syncwarp();
                 }
             }
@@ -2217,13 +2360,20 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
         for (int k = 0; k < 4; k++) {
             const int64_t u = g0 + k * 32 + lane;
             uint32_t seen = 0;
-            const bool hit = u < nunits && (SET2 ? unit_any_set2<NR, HIGH>(sp, va[k], vb[k]) : unit_any<NR, HIGH, false>(sp, va[k], vb[k], seen)) != 0;
+            const bool hit = u < nunits && unit_any<NR, HIGH, false>(sp, va[k], vb[k], seen) != 0;
             const uint32_t m = __ballot_sync(FULL, hit);
-            if (hit) s_units[uqn + __popc(m & ((1u << lane) - 1))] = u;
+            if (hit) {
+                const int slot = uqn + __popc(m & ((1u << lane) - 1));
+                s_units[slot] = u; s_udata[2 * slot] = va[k]; s_udata[2 * slot + 1] = vb[k];
+            }
             uqn += __popc(m);
             if (uqn >= 32) {
                 run_units(32);
-                if (lane < uqn - 32) { const int64_t x = s_units[32 + lane]; s_units[lane] = x; }
+                if (lane < uqn - 32) {
+                    const int64_t x = s_units[32 + lane];
+                    const uint4 d0 = s_udata[2 * (32 + lane)], d1 = s_udata[2 * (32 + lane) + 1];
+                    s_units[lane] = x; s_udata[2 * lane] = d0; s_udata[2 * lane + 1] = d1;
+                }
                 uqn -= 32;
                 __syncwarp();
             }
@@ -2813,6 +2963,51 @@ __global__ void k_buffer_finish(KParams p, const uint8_t* __restrict__ buf, Scan
     }
     from_to[0] = from;
     from_to[1] = to;
+}
+
+// ---- NFA engine kernels: one thread per text (patterns past the eager state cap; correctness path, not a fast one) ----
+template <int OP>
+__device__ inline bool nfa_bool(const KParams& p, const NfaEngine& N, const uint8_t* __restrict__ s, int64_t len) {
+    const uint8_t* pre = p.lits + p.all_len;
+    const uint8_t* suf = pre + p.pre_len;
+    FetchGlobal fetch{s};
+    if (OP == 1) {
+        if (len == 0 || (len == 1 && fetch(0) == 0x20)) return p.q0_accepting != 0;
+        Anchored A{nullptr, 0, 0};
+        int64_t f, t;
+        including_exact(A, N, fetch, len, pre, p.pre_len, p.pre_active != 0, suf, p.suf_len, p.suf_active != 0, f, t);
+        return f > 0 && t > 0;
+    }
+    // prefix / suffix gate of do_matching_exactly (api_internal_m.F90:199-233)
+    const int64_t lp = p.pre_len, ls = p.suf_len;
+    if (len > 0 && lp > 0 && lp == len && lit_equal(s, pre, (int)lp)) return true;
+    if (lp > len || ls > len) return false;
+    if (len > 0) {
+        if (p.pre_active && !lit_equal(s, pre, (int)lp)) return false;
+        if (p.suf_active && !lit_equal(s + (len - ls), suf, (int)ls)) return false;
+    } else {
+        if (p.pre_active && lp != 0) return false;
+        if (p.suf_active && ls != 0) return false;
+    }
+    return nfa_match(N, fetch, len);
+}
+template <int OP>
+__global__ void __launch_bounds__(64) k_nfa_bool(KParams p, NfaEngine N, const uint8_t* __restrict__ buf, const int64_t* __restrict__ offsets,
+                                                 int64_t stride, int64_t n, uint8_t* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t o0 = offsets ? __ldg(offsets + i) : i * stride, o1 = offsets ? __ldg(offsets + i + 1) : (i + 1) * stride;
+        out[i] = nfa_bool<OP>(p, N, buf + o0, o1 - o0) ? 1 : 0;
+    }
+}
+__global__ void __launch_bounds__(64) k_nfa_regex(KParams p, NfaEngine N, const uint8_t* __restrict__ buf, const int64_t* __restrict__ offsets,
+                                                  int64_t n, int64_t single_len, int64_t* __restrict__ from, int64_t* __restrict__ to) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t o0 = offsets ? __ldg(offsets + i) : 0, o1 = offsets ? __ldg(offsets + i + 1) : single_len;
+        int64_t f, t;
+        eval_regex(p, N, FetchGlobal{buf + o0}, o1 - o0, f, t);
+        from[i] = f;
+        to[i] = t;
+    }
 }
 
 }  // namespace fxk

@@ -58,7 +58,9 @@ enum {
     FX_OK = 0,
     FX_ERR_TREE_NODE_LIMIT = 101,      /* Forgex `error stop`s here (src/ast/syntax_tree_graph_m.F90:115-117) */
     FX_ERR_DFA_STATE_CAP = 102,        /* eager construction exceeds 16383 states (Forgex's own ceiling for the
-                                          lazily visited states: src/lazy_dfa/lazy_dfa_graph_m.F90:90-92) */
+                                          lazily visited states: src/lazy_dfa/lazy_dfa_graph_m.F90:90-92) AND the NFA
+                                          engine cannot take over (more than 8191 NFA states), or an entry point that
+                                          needs the table engine was called on an NFA-engine handle */
     FX_ERR_PREFILTER_UNSUPPORTED = 103,/* pattern whose literal prefilter (src/api_internal_m.F90:76-104) is not
                                           provably result-neutral; see DESIGN.md "out of contract" */
     FX_ERR_BAD_ARGUMENT = 104,
@@ -98,6 +100,11 @@ typedef struct fx_pattern_info {
     int32_t statemap;         /* FX_OP_REGEX: 1 when the pattern has the linear-time span path (forward "ordered groups"
                                  automaton + reverse automaton): ragged batches run on it (K3f), and fx_regex_buffer* can
                                  fall back on the chunked state-map scan (K5) */
+    int32_t nfa_engine;       /* 1: the eager automaton passes the state cap and the pattern is matched by NFA simulation on
+                                 the device instead (one thread per text, the reference's own subset step on bit sets).
+                                 Forgex builds its DFA lazily, so it answers such patterns (test/test_api/test_case_005.f90:
+                                 76-108).  Correctness path, not a fast one; the window forms and the all-matches / count
+                                 entry points answer FX_ERR_DFA_STATE_CAP for such a handle */
     int32_t statemap_used;    /* last fx_regex_buffer* call: 0 candidate-start scan only; 1 state-map scan; 2 candidate-start
                                  scan under a work budget with the state-map scan behind it (which of the two answered is
                                  decided on the device) */
@@ -141,6 +148,10 @@ int fx_pattern_tables(const fx_pattern* p, const uint16_t** table, const uint16_
 int fx_pattern_span_tables(const fx_pattern* p, const uint16_t** direct, const uint8_t** endinfo, int32_t scalars[4],
                            const uint16_t** rdelta, const uint8_t** rpage, const uint8_t** rmixed, const int32_t** cuts,
                            int32_t rscalars[4]);
+/* the NFA engine's tables of a handle with fx_pattern_info.nfa_engine == 1 (tests / tools): trans[(s * classes + c) * words ..]
+ * = epsilon-closed successor set of NFA state s on class c, q0 = closure of the entry, cuts: classes + 1 code points;
+ * scalars = {NFA states, 64-bit words per set, classes, exit state, q0 accepting}.  Returns 1 for a table-engine handle. */
+int fx_pattern_nfa_tables(const fx_pattern* p, const uint64_t** trans, const uint64_t** q0, const int32_t** cuts, int32_t scalars[5]);
 int fx_is_valid_regex(const void* pattern, int64_t plen, int* status);
 /* is_valid_regex over an array of patterns (it is `pure elemental` in the reference, src/forgex.F90:58-71): patterns as
  * one flat buffer + n+1 ascending offsets; valid[i] = 1/0, status[i] = the SYNTAX_* code of pattern i

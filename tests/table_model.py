@@ -570,3 +570,122 @@ class StateMapScan:
                 last = l
             r0 = r1
         return self.sl.end_of_text(s, n, last)
+
+
+class NfaModel:
+    """the NFA engine (k_nfa_bool / k_nfa_regex): the reference's per-character subset step on bit sets -- here Python
+    integers -- with the same drivers as the table engine (attempt_at, brute force, prefix candidates, .match. walk)"""
+
+    def __init__(self, pattern_obj):
+        t = pattern_obj.nfa_tables()
+        assert t is not None
+        self.op = pattern_obj.op
+        self.lit = pattern_obj.literals()
+        nst, ncls, w = t["trans"].shape
+        self.trans = [[int.from_bytes(t["trans"][s, c].tobytes(), "little") for c in range(ncls)] for s in range(nst)]
+        self.q0 = int.from_bytes(t["q0"].tobytes(), "little")
+        self.cuts = [int(x) for x in t["cuts"]]
+        self.exit = t["exit"]
+        self.q0_accepting = t["q0_accepting"]
+
+    def cls(self, cp):
+        import bisect
+        return bisect.bisect_right(self.cuts, cp) - 1
+
+    def step(self, cur, c):
+        nxt, s = 0, 0
+        while cur:
+            if cur & 1:
+                nxt |= self.trans[s][c]
+            cur >>= 1
+            s += 1
+        return nxt
+
+    def acc(self, cur):
+        return (cur >> self.exit) & 1
+
+    def symbol(self, s, j):
+        n = Anchored.char_len(s, j)
+        b = s[j]
+        if b < 0x80:
+            return self.cls(b), 1
+        if n == 1:
+            return self.cls(0xFFFF), 1
+        cp = b & (0x1F if n == 2 else 0x0F if n == 3 else 0x07)
+        for k in range(1, n):
+            cp = (cp << 6) | (s[j + k] & 0x3F)
+        return self.cls(cp), n
+
+    def attempt_at(self, s, start):
+        n, cur, last, j = len(s), self.q0, -1, start - 2
+        if start == 1:
+            cur = self.step(cur, self.cls(0))
+            if not cur:
+                return -1
+            if self.acc(cur):
+                last = 0
+            j = 0
+        while j <= n:
+            c, nb = self.symbol(s, j) if j < n else (self.cls(0), 1)
+            cur = self.step(cur, c)
+            if not cur:
+                break
+            j += nb
+            if self.acc(cur):
+                last = j
+        return last
+
+    def match(self, s):
+        if len(s) == 0:
+            return self.q0_accepting
+        cur = self.step(self.q0, self.cls(0)) or self.q0
+        j = 0
+        while j < len(s):
+            c, nb = self.symbol(s, j)
+            cur = self.step(cur, c)
+            if not cur:
+                return False
+            j += nb
+        return bool(self.acc(cur)) or bool(self.acc(self.step(cur, self.cls(0))))
+
+    def including(self, s):
+        """including_exact with this engine's attempts (the Anchored class holds the driver; only attempts differ)"""
+        drv = Anchored.__new__(Anchored)
+        drv.lit = self.lit
+        drv.t = {"q0": None}
+        eng = self
+        drv.attempt_at = lambda text, start: eng.attempt_at(text, start)
+        drv.attempt = lambda text, st, pos, last: eng.attempt_at(text, pos + 2)
+        return drv.including_exact(s)
+
+    def boolean(self, s: bytes):
+        _, pre, suf = self.lit
+        if self.op == 1:
+            if len(s) == 0 or s == b" ":
+                return self.q0_accepting
+            f, t = self.including(s)
+            return f > 0 and t > 0
+        lp, ls = len(pre), len(suf)
+        if len(s) > 0 and lp > 0 and lp == len(s) and s == pre:
+            return True
+        if lp > len(s) or ls > len(s):
+            return False
+        if len(s) > 0:
+            if not blank(pre) and s[:lp] != pre:
+                return False
+            if not blank(suf) and s[len(s) - ls:] != suf:
+                return False
+        else:
+            if (not blank(pre) and lp != 0) or (not blank(suf) and ls != 0):
+                return False
+        return self.match(s)
+
+    def regex(self, s: bytes):
+        all_ = self.lit[0]
+        if not blank(all_):
+            i = s.find(all_)
+            return (i + 1, i + len(all_)) if i >= 0 else (0, 0)
+        if len(s) == 0 or s == b" ":
+            return (0, 0)
+        f, t = self.including(s)
+        return (f, t) if f > 0 and t > 0 else (0, 0)

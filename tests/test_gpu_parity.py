@@ -34,26 +34,58 @@ def pack(strings):
 
 # ---- the reference's own vectors through fx_in / fx_match / fx_regex ---------------------------
 def test_reference_vectors_on_gpu():
+    """all 997 API vectors of the reference's own tests through fx_in / fx_match / fx_regex.  Every one gets an answer:
+    the two patterns whose eager automaton passes the state cap (Forgex only ever builds the few states their texts
+    visit) run on the NFA engine"""
     with open(os.path.join(GOLD, "reference_api.json")) as fh:
         vecs = json.load(fh)["vectors"]
     bad, capped = [], 0
     for v in vecs:
         pat, text = bytes.fromhex(v["pattern"]), bytes.fromhex(v["text"])
-        try:
-            if v["kind"] == "match":
-                ok = fx.op_match(pat, text) == v["expect"]
-            elif v["kind"] == "in":
-                ok = fx.op_in(pat, text) == v["expect"]
-            else:
-                ok = fx.regex_f(pat, text) == bytes.fromhex(v["expect"])
-        except fx.ForgexError as e:
-            assert e.status == _lib.FX_ERR_DFA_STATE_CAP and pat in EAGER_CAP_PATTERNS, (v["src"], e)
-            capped += 1
-            continue
+        if v["kind"] == "match":
+            ok = fx.op_match(pat, text) == v["expect"]
+        elif v["kind"] == "in":
+            ok = fx.op_in(pat, text) == v["expect"]
+        else:
+            ok = fx.regex_f(pat, text) == bytes.fromhex(v["expect"])
+        capped += pat in EAGER_CAP_PATTERNS
         if not ok:
-            bad.append("%s %s %r" % (v["src"], v["kind"], pat))
-    assert not bad, "%d reference vectors fail on the GPU path:\n%s" % (len(bad), "\n".join(bad[:40]))
+            bad.append("%s %s %r on %r" % (v["src"], v["kind"], pat, text[:40]))
+    assert not bad, "\n".join(bad[:40])
     assert capped == 4
+    for pat in EAGER_CAP_PATTERNS:
+        assert fx.Pattern(pat, "match").info()["nfa_engine"] == 1
+
+
+def test_nfa_engine_against_the_oracle(monkeypatch):
+    """the NFA engine forced on ordinary patterns (FX_STATE_CAP=3: nearly every eager automaton passes that cap):
+    `.in.`, `.match.`, spans, batches and the buffer path must still give the oracle's answers"""
+    import random
+    from tests.test_host_tables import gen_pattern, gen_text
+    monkeypatch.setenv("FX_STATE_CAP", "3")
+    rng = random.Random(515)
+    texts = [gen_text(rng) for _ in range(150)] + [b"", b" ", b"foobar", b"abc\nabc", b"\xe3\x81\x82a\xff", b"aaaa"]
+    buf, off = pack(texts)
+    used = 0
+    for pat in [b"foo(bar|baz)", rb"\d{3}-\d{4}", synth.PATTERNS["c3"], synth.PATTERNS["c4"], b"(a|b)*a(a|b){3}", b"a*", b"^$", b"aa[bc]", b"ab+c"] + \
+               [gen_pattern(rng).encode() for _ in range(40)]:
+        for op in ("in", "match", "regex"):
+            p = fx.Pattern(pat, op)
+            if p.status != 0 or not p.info()["nfa_engine"]:
+                continue
+            c = O.Compiled(pat, 1 if op == "match" else 0)
+            if op == "regex":
+                f, t = p.regex_batch(buf, off)
+                ef, et = c.regex_batch(buf, off)
+                assert np.array_equal(f, ef) and np.array_equal(t, et), (pat, np.nonzero((f != ef) | (t != et))[0][:5])
+                joined = np.frombuffer(b"\n".join(texts[:40]), dtype=np.uint8)
+                assert p.regex_buffer(joined) == c.regex_buffer(joined), (pat, "buffer")
+            else:
+                o = 1 if op == "match" else 0
+                got = p.in_batch(buf, off) if op == "in" else p.match_batch(buf, off)
+                assert np.array_equal(got, c.bool_batch(o, buf, off)), (pat, op)
+            used += 1
+    assert used > 60, used
 
 
 def test_regex_out_arguments_like_reference():

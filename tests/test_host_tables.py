@@ -13,7 +13,7 @@ import pytest
 import forgex_b200 as fx
 from forgex_b200 import _lib
 from tests import oracle_lib as O
-from tests.table_model import BufferPrefix, Model, SpanLinear, SparseIn
+from tests.table_model import BufferPrefix, Model, NfaModel, SpanLinear, SparseIn
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 OPS = {"match": "match", "in": "in", "regex": "regex"}
@@ -35,7 +35,10 @@ def model_for(pattern, op):
     key = (pattern, op)
     if key not in _cache:
         p = fx.Pattern(pattern, op)
-        _cache[key] = (p, Model(p, use_direct=(len(_cache) % 2 == 0)) if p.status == 0 else None)
+        if p.status == 0 and p.info()["nfa_engine"]:
+            _cache[key] = (p, NfaModel(p))           # past the eager state cap: the NFA engine answers
+        else:
+            _cache[key] = (p, Model(p, use_direct=(len(_cache) % 2 == 0)) if p.status == 0 else None)
     return _cache[key]
 
 
@@ -89,10 +92,10 @@ def test_reference_api_vectors_through_product_tables(monkeypatch):
     for v in load("api"):
         pat, text = bytes.fromhex(v["pattern"]), bytes.fromhex(v["text"])
         got = product_answer(v["kind"], pat, text)
-        if isinstance(got, tuple):
-            assert got[1] == _lib.FX_ERR_DFA_STATE_CAP and pat in EAGER_CAP_PATTERNS, (v["src"], got)
+        assert not isinstance(got, tuple), (v["src"], got)      # every reference vector gets an answer
+        if model_for(pat, v["kind"])[0].info()["nfa_engine"]:
+            assert pat in EAGER_CAP_PATTERNS, pat
             capped += 1
-            continue
         exp = bytes.fromhex(v["expect"]) if v["kind"] == "regex" else v["expect"]
         if got != exp:
             bad.append("%s %s %r -> %r, expected %r" % (v["src"], v["kind"], pat, got, exp))
@@ -148,6 +151,30 @@ def test_reference_status_and_validity_vectors():
         if fx.is_valid_regex(pat) != v["expect"]:
             bad.append("%s %r validity" % (v["src"], pat))
     assert not bad, "\n".join(bad[:40])
+
+
+def test_nfa_engine_tables_against_the_oracle(monkeypatch):
+    """the NFA engine's tables (patterns past the eager state cap), walked by a Python model of k_nfa_bool /
+    k_nfa_regex: forced on ordinary patterns with FX_STATE_CAP=3 and compared with the oracle"""
+    monkeypatch.setenv("FX_STATE_CAP", "3")
+    rng = random.Random(808)
+    texts = [gen_text(rng) for _ in range(60)] + [b"", b" ", b"foobar", b"abc\nabc", b"\xe3\x81\x82a\xff", b"aaaa", b"aaab"]
+    used = 0
+    for pat in [b"foo(bar|baz)", rb"\d{3}-\d{4}", rb"^ERROR.*timeout=\d+$", b"(a|b)*a(a|b){3}", b"a*", b"^$", b"aa[bc]", b"ab+c", "[ぁ-ん]+a".encode()] + \
+               [gen_pattern(rng).encode() for _ in range(50)]:
+        for op in ("in", "match", "regex"):
+            p = fx.Pattern(pat, op)
+            if p.status != 0 or not p.info()["nfa_engine"]:
+                continue
+            m = NfaModel(p)
+            for t in texts:
+                if op == "regex":
+                    assert m.regex(t) == O.regex(pat, t)[2:4], (pat, t)
+                else:
+                    exp = O.op_match(pat, t) if op == "match" else O.op_in(pat, t)
+                    assert m.boolean(t) == bool(exp), (pat, op, t)
+            used += 1
+    assert used > 80, used
 
 
 def test_batch_validity_and_status_vectors():
@@ -267,7 +294,7 @@ def test_generated_patterns_match_oracle(seed, monkeypatch):
                 continue
             if p.status != 0:
                 continue  # cap
-            m = Model(p, use_direct=rng.random() < 0.5)
+            m = NfaModel(p) if p.info()["nfa_engine"] else Model(p, use_direct=rng.random() < 0.5)
             span = SpanLinear(p) if kind == "regex" and p.span_tables() is not None else None
             bufpre = BufferPrefix(p) if kind == "regex" and p.info()["prefix_scan"] else None
             nbufpre += bufpre is not None
