@@ -783,6 +783,39 @@ int launch_span_t(fx_pattern* p, const Plan& pl, const SpanParams& sp, int fwd_b
     return cuda_status(cudaGetLastError());
 }
 
+// K3f, pooled form: one CTA of 1024 walkers per SM, CTA-wide tiles (double buffered), strings claimed from a counter
+template <int FK, bool RS>
+int launch_span_pool_t(fx_pattern* p, const Plan& pl, const SpanParams& sp, int fwd_bytes, const uint8_t* buf,
+                       const int64_t* off, int64_t n, int64_t total, int64_t* from, int64_t* to, cudaStream_t s) {
+    auto kern = k_span_pool<FK, RS>;
+    int64_t avg = n > 0 ? (total + n - 1) / n : 1;
+    if (avg < 1) avg = 1;
+    const SpanHead H = span_head(fwd_bytes, sp.rstates * sp.rclasses * 2, sp.nmixed, RS);
+    const int per_buf = ((227 * 1024 - 1024 - H.bytes - 128) / 2) & ~127;
+    if (per_buf < 8192) return FX_ERR_BAD_ARGUMENT;
+    int cap = per_buf - 256, spt = 1;
+    for (;;) {
+        int64_t want = ((int64_t)cap * 7 / 8) / avg;       // expect the tile to fill most of the staged capacity
+        spt = (int)(want < 1 ? 1 : want > 2048 ? 2048 : want);
+        if (cap <= 4096 || pool_layout(spt, cap).buf_bytes <= per_buf) break;
+        cap -= 128;
+    }
+    spt = env_int("FX_TILE_STRINGS", spt);
+    if (spt > 2048) spt = 2048;
+    while (spt > 1 && pool_layout(spt, cap).buf_bytes > per_buf) spt--;
+    const int64_t ntiles = (n + spt - 1) / spt;
+    const size_t smem = (size_t)H.bytes + 128 + 2 * (size_t)pool_layout(spt, cap).buf_bytes;
+    int bps = 0;
+    int rc = occupancy_grid(kern, POOL_THREADS, smem, p->dev.sm_count, bps);
+    if (rc) return rc;
+    long long capg = (long long)p->dev.sm_count * bps;
+    int grid = (int)(ntiles < capg ? ntiles : capg);
+    if (grid < 1) grid = 1;
+    kern<<<grid, POOL_THREADS, smem, s>>>(pl.kp, sp, buf, off, n, total, from, to, spt, cap, ntiles, fwd_bytes);
+    g_launches++;
+    return cuda_status(cudaGetLastError());
+}
+
 int launch_regex_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, int64_t n, int64_t total,
                         int64_t* from, int64_t* to, cudaStream_t s) {
     if (n < 0 || total < 0) return FX_ERR_BAD_ARGUMENT;
@@ -802,6 +835,14 @@ int launch_regex_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, i
         if (fk == 0 && !p->dev.sp_direct) fk = 1;
         const int fwd_bytes = fk == 0 ? st.nstates * SPAN_ROW * 2 : fk == 1 ? classed_bytes : 0;
         const bool rs = !rv.page.empty() && (int)(rv.delta16.size() * 2 + 1024 + rv.mixed.size()) <= SPAN_REV_SMEM_BYTES;
+        if (env_int("FX_SPAN_POOL", 1)) {          // pooled walkers over CTA-wide tiles (default)
+            if (fk == 0) return rs ? launch_span_pool_t<0, true>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s)
+                                   : launch_span_pool_t<0, false>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
+            if (fk == 1) return rs ? launch_span_pool_t<1, true>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s)
+                                   : launch_span_pool_t<1, false>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
+            return rs ? launch_span_pool_t<2, true>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s)
+                      : launch_span_pool_t<2, false>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
+        }
         if (fk == 0) return rs ? launch_span_t<0, true>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s)
                                : launch_span_t<0, false>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
         if (fk == 1) return rs ? launch_span_t<1, true>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s)
@@ -1033,8 +1074,15 @@ int launch_buffer(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* from_
     unsigned long long* best = work;
     ScanWindow W{len, 0, len, 0, 1, 1};
     const bool prefixed = p->prog.prefix_active && !p->prog.literal_only;
-    if (prefixed && !p->prefix_scan) return FX_ERR_PREFILTER_UNSUPPORTED;
     p->last_statemap = 0;
+    if (prefixed && !p->prefix_scan) {           // sequential candidate list (bordered prefix / suffix literal): one thread, exact
+        Plan pl;
+        int rc = make_plan(p, pl);
+        if (rc) return rc;
+        k_buffer_sequential<<<1, 1, 0, s>>>(pl.kp, buf, len, from_to);
+        g_launches++;
+        return cuda_status(cudaGetLastError());
+    }
     // Patterns with a linear-time span path: the candidate-start scan (K4) is the fast path when candidates are rare
     // (sparse first-byte set) -- under a work budget; past the budget, and for every other such pattern, the chunked
     // state-map scan (K5) answers in linear time; should that scan decline (too many states can arrive at a region

@@ -1892,6 +1892,204 @@ __global__ void __launch_bounds__(SPAN_WARPS * 32, 1) k_span_ragged(KParams p, S
 }
 
 // ---------------------------------------------------------------------------------------------
+// K3f, pooled form (the default).  Same two walks as k_span_ragged above, different division of labour: the tile is the
+// CTA's (about 80 KB of text, hundreds of strings, brought in by ONE TMA bulk copy, double buffered: the next tile lands
+// while this one is walked), and the 1024 threads of the CTA are a pool of walkers that claim the tile's strings one by
+// one from a shared counter.  A lane that finishes its string claims the next; the claim is looked at every 32 bytes
+// walked.  With warp-private tiles a lane walked two strings per tile and then waited for the warp's slowest; here the
+// imbalance is one string per CTA and tile.  The forward step also defers its bookkeeping: four steps run without
+// looking at the flag bits, the OR of the four words is tested once, and only a word that held an event (accept, replay
+// mark: rare) is walked again with the full bookkeeping.
+// ---------------------------------------------------------------------------------------------
+static constexpr int POOL_THREADS = 1024;
+struct PoolLayout { int off_res, off_queue, off_text, buf_bytes; };
+__host__ __device__ __forceinline__ PoolLayout pool_layout(int spt, int cap) {
+    PoolLayout L;
+    L.off_res = (16 + (spt + 4) * 4 + 7) & ~7;
+    L.off_queue = L.off_res + spt * 8;
+    L.off_text = (L.off_queue + spt * 4 + 127) & ~127;
+    L.buf_bytes = (L.off_text + cap + 64 + 127) & ~127;
+    return L;
+}
+
+template <int FK, bool RS>
+__global__ void __launch_bounds__(POOL_THREADS, 1) k_span_pool(KParams p, SpanParams sp, const uint8_t* __restrict__ buf,
+                                                              const int64_t* __restrict__ offsets, int64_t n, int64_t total,
+                                                              int64_t* __restrict__ from, int64_t* __restrict__ to,
+                                                              int spt, int cap, int64_t ntiles, int fwd_bytes) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const uint32_t FULL = 0xffffffffu;
+    const SpanHead H = span_head(fwd_bytes, sp.rstates * sp.rclasses * 2, sp.nmixed, RS);
+    const PoolLayout L = pool_layout(spt, cap);
+    // ---- stage the tables ----
+    SpanFwd<FK> T;
+    T.s_cmap = smem_u32(smem); T.s_table = smem_u32(smem + 256); T.g_table = sp.table; T.g_cmap = sp.classmap; T.shift = sp.row_shift;
+    if (FK == 0) {
+        uint16_t* dst = reinterpret_cast<uint16_t*>(smem + 256);
+        for (int i = threadIdx.x; i < sp.nstates * 128; i += blockDim.x) {
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(sp.direct) + i);
+            *reinterpret_cast<uint32_t*>(dst + (i >> 7) * SPAN_ROW + ((i & 127) << 1)) = v;
+        }
+    } else if (FK == 1) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem + 256);
+        const int words32 = ((sp.nstates << sp.row_shift) + 1) >> 1;
+        for (int i = threadIdx.x; i < words32; i += blockDim.x) dst[i] = __ldg(reinterpret_cast<const uint32_t*>(sp.table) + i);
+        for (int i = threadIdx.x; i < 64; i += blockDim.x)
+            reinterpret_cast<uint32_t*>(smem)[i] = __ldg(reinterpret_cast<const uint32_t*>(sp.classmap) + i);
+    }
+    SpanRev<RS> R;
+    R.s_delta = smem_u32(smem + H.off_rdelta); R.s_page = smem_u32(smem + H.off_page); R.s_mixed = smem_u32(smem + H.off_mixed);
+    if (RS) {
+        uint16_t* d = reinterpret_cast<uint16_t*>(smem + H.off_rdelta);
+        for (int i = threadIdx.x; i < sp.rstates * sp.rclasses; i += blockDim.x) d[i] = __ldg(sp.rdelta + i);
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) smem[H.off_page + i] = __ldg(sp.rpage + i);
+        for (int i = threadIdx.x; i < sp.nmixed * 64; i += blockDim.x) smem[H.off_mixed + i] = __ldg(sp.rmixed + i);
+    }
+    int* s_ctl = reinterpret_cast<int*>(smem + H.bytes);               // [0..1] next unclaimed string, [2..3] queue fill (per buffer)
+    uint8_t* bufs = smem + H.bytes + 128;
+    if (threadIdx.x < 2) mbar_init(smem_u32(bufs + threadIdx.x * L.buf_bytes), 1);
+    __syncthreads();
+    const uintptr_t gbuf = reinterpret_cast<uintptr_t>(buf);
+    uint32_t phase[2] = {0, 0};
+
+    // bring tile t into buffer b: one bulk copy (thread 0), the offsets as tile-relative int32 (everyone)
+    auto prefetch = [&](int64_t t, int b) {
+        uint8_t* B = bufs + b * L.buf_bytes;
+        int32_t* s_off = reinterpret_cast<int32_t*>(B + 16);
+        uint8_t* text = B + L.off_text;
+        const int64_t first = t * spt;
+        const int count = (int)((n - first) < spt ? (n - first) : spt);
+        const int64_t t0 = __ldg(offsets + first), tend = __ldg(offsets + first + count);
+        const int64_t t1 = tend - t0 > cap ? t0 + cap : tend;
+        const uintptr_t g0 = gbuf + (uintptr_t)t0;
+        const int64_t base = t0 - (int64_t)(g0 & 15);
+        const uintptr_t gsrc = g0 & ~(uintptr_t)15;
+        uintptr_t gcopy_end = (gbuf + (uintptr_t)t1 + 15) & ~(uintptr_t)15;
+        const uintptr_t gsafe_end = (gbuf + (uintptr_t)total) & ~(uintptr_t)15;
+        if (gcopy_end > gsafe_end) gcopy_end = gsafe_end;
+        const uint32_t bulk = gcopy_end > gsrc ? (uint32_t)(gcopy_end - gsrc) : 0u;
+        if (threadIdx.x == 0) {
+            s_ctl[b] = 0; s_ctl[2 + b] = 0;
+            const uint32_t mbar = smem_u32(B);
+            if (bulk) { mbar_expect_tx(mbar, bulk); bulk_g2s(smem_u32(text), reinterpret_cast<const void*>(gsrc), bulk, mbar); }
+            else mbar_expect_tx(mbar, 0);                              // (an empty tile still completes its phase)
+        }
+        for (int64_t x = (int64_t)(gsrc + bulk) - (int64_t)gbuf + threadIdx.x; x < t1; x += blockDim.x)
+            if (x >= t0) text[x - base] = __ldg(buf + x);
+        for (int i = threadIdx.x; i <= count; i += blockDim.x) {
+            const int64_t o = __ldg(offsets + first + i);
+            s_off[i] = o > t1 ? OFF_BEYOND : (int32_t)(o - base);
+        }
+    };
+
+    int64_t t = blockIdx.x;
+    if (t < ntiles) prefetch(t, 0);
+    for (int k = 0; t < ntiles; k++, t += gridDim.x) {
+        const int b = k & 1;
+        if (t + gridDim.x < ntiles) prefetch(t + gridDim.x, b ^ 1);    // the other buffer is free: its tile was finished behind a barrier
+        uint8_t* B = bufs + b * L.buf_bytes;
+        int32_t* s_off = reinterpret_cast<int32_t*>(B + 16);
+        int2* s_res = reinterpret_cast<int2*>(B + L.off_res);
+        uint32_t* s_queue = reinterpret_cast<uint32_t*>(B + L.off_queue);
+        const uint32_t text_addr = smem_u32(B + L.off_text);
+        const int64_t first = t * spt;
+        const int count = (int)((n - first) < spt ? (n - first) : spt);
+        mbar_wait(smem_u32(B), phase[b]); phase[b] ^= 1;
+        __syncthreads();                                               // offsets and counters of this tile are visible
+        // ---- forward walks: claim, walk a round, look again ----
+        bool have = false;
+        int sidx = 0, len = 0, j = 0, last = -1;
+        uint32_t a = 0, st = 0;
+        volatile int* v_next = s_ctl + b;
+        for (;;) {
+            const uint32_t idle = __ballot_sync(FULL, !have);
+            bool more = true;
+            if (idle) {
+                int base = 0;
+                if (lane == 0) base = *v_next < count ? atomicAdd(s_ctl + b, __popc(idle)) : count;
+                base = __shfl_sync(FULL, base, 0);
+                more = base < count;
+                const int mine = base + __popc(idle & ((1u << lane) - 1));
+                if (!have && mine < count) {
+                    sidx = mine;
+                    const int32_t r0 = s_off[sidx], r1 = s_off[sidx + 1];
+                    if (r1 == OFF_BEYOND) {      // longer than the tile: the same two walks, text from global memory
+                        const int64_t o0 = __ldg(offsets + first + sidx), o1 = __ldg(offsets + first + sidx + 1);
+                        int64_t f = 0, e = 0;
+                        if (o1 - o0 == 0 || (o1 - o0 == 1 && __ldg(buf + o0) == 0x20)) {
+                        } else if (o1 - o0 < 0x7FFFFFF0ll) {
+                            span_linear(sp, T, R, FetchGlobal{buf + o0}, (int)(o1 - o0), f, e);
+                        } else {
+                            Table<3> G;
+                            G.g_table = p.ctable; G.g_cmap = p.classmap; G.shift = p.c_row_shift; G.s_table = 0; G.s_cmap = 0;
+                            eval_regex(p, G, FetchGlobal{buf + o0}, o1 - o0, f, e);
+                        }
+                        from[first + sidx] = f; to[first + sidx] = e;
+                        s_res[sidx] = make_int2(-1, -1);
+                    } else {
+                        len = r1 - r0;
+                        a = text_addr + (uint32_t)r0;
+                        if (len == 0 || (len == 1 && lds_u8(a) == 0x20)) s_res[sidx] = make_int2(0, 0);   // api_internal_m.F90:68-74
+                        else { have = true; j = 0; st = (uint32_t)sp.start; last = sp.start_acc ? 0 : -1; }
+                    }
+                }
+            }
+            if (!__any_sync(FULL, have)) { if (!more) break; else continue; }
+            if (have) {
+                int jend = (int)(((a + (uint32_t)j + SPAN_ROUND) & ~3u) - a);
+                if (jend > len) jend = len;
+                while (j < jend && ((a + (uint32_t)j) & 3u)) { const uint32_t bb = lds_u8(a + j); FX_SPAN_STEP(T, st, last, bb, j); j++; }
+                for (; j + 4 <= jend && st != 0; j += 4) {
+                    const uint32_t w4 = lds_u32(a + j);
+                    const uint32_t n1 = T.next(st, w4 & 0xFFu);
+                    const uint32_t n2 = T.next(n1 & W_SSTATE, (w4 >> 8) & 0xFFu);
+                    const uint32_t n3 = T.next(n2 & W_SSTATE, (w4 >> 16) & 0xFFu);
+                    const uint32_t n4 = T.next(n3 & W_SSTATE, w4 >> 24);
+                    if ((n1 | n2 | n3 | n4) & 0xB000u) {               // an accept or a replay mark in this word: again, with the books
+                        FX_SPAN_STEP(T, st, last, w4 & 0xFFu, j);
+                        FX_SPAN_STEP(T, st, last, (w4 >> 8) & 0xFFu, j + 1);
+                        FX_SPAN_STEP(T, st, last, (w4 >> 16) & 0xFFu, j + 2);
+                        FX_SPAN_STEP(T, st, last, w4 >> 24, j + 3);
+                    } else st = n4 & W_SSTATE;
+                }
+                if (st != 0) for (; j < jend; j++) { const uint32_t bb = lds_u8(a + j); FX_SPAN_STEP(T, st, last, bb, j); }
+                if (st == 0 || j >= len) {
+                    if (st != 0) last = span_end_of_text(sp, st, len, last);
+                    have = false;
+                    if (last <= 0) s_res[sidx] = make_int2(0, 0);
+                }
+            }
+            const bool push = !have && last > 0;
+            const uint32_t pm = __ballot_sync(FULL, push);
+            if (pm) {
+                int qb = 0;
+                if (lane == 0) qb = atomicAdd(s_ctl + 2 + b, __popc(pm));
+                qb = __shfl_sync(FULL, qb, 0);
+                if (push) { s_queue[qb + __popc(pm & ((1u << lane) - 1))] = ((uint32_t)sidx << 20) | (uint32_t)last; last = -1; }
+            }
+        }
+        __syncthreads();
+        // ---- backward walks over the queue ----
+        const int nq = s_ctl[2 + b];
+        for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+            const uint32_t e = s_queue[q];
+            const int si = (int)(e >> 20), lst = (int)(e & 0xFFFFFu);
+            const int32_t r0 = s_off[si];
+            const int ln = s_off[si + 1] - r0;
+            const int f = span_backward(sp, R, FetchShared{text_addr + (uint32_t)r0}, ln, lst);
+            s_res[si] = f > 0 ? make_int2(f, lst < ln ? lst : ln) : make_int2(0, 0);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < count; i += blockDim.x) {
+            const int2 r = s_res[i];
+            if (r.x >= 0) { from[first + i] = r.x; to[first + i] = r.y; }
+        }
+        __syncthreads();                                               // this buffer may be refilled from the next iteration on
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K4: one long buffer, span result (config C4).
 // The reference tries every character boundary as a start, in order, and returns at the first one
 // whose anchored run accepts after >= 1 symbol (api_internal_m.F90:108-155).  The attempts are
@@ -1944,7 +2142,7 @@ __device__ __forceinline__ bool budget_spent(const ScanBudget& B, unsigned long 
 // virtual trailing NUL.  `open_end`: the window is followed by text this GPU does not hold; an attempt that reaches the
 // window end alive and without an accept cannot be decided here (*overflow).  Budgeted scans tick here as well.
 template <int KIND>
-__device__ __noinline__ bool attempt_tail(const KParams& p, const Table<KIND>& T, const uint8_t* __restrict__ buf, int64_t len,
+__device__ __forceinline__ bool attempt_tail(const KParams& p, const Table<KIND>& T, const uint8_t* __restrict__ buf, int64_t len,
                                           uint32_t st, int64_t at, bool open_end, unsigned long long* overflow, const ScanBudget& B) {
     uint32_t w = st;
     int64_t seq = 0, last = -1;
@@ -2570,7 +2768,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32, 2) k_statemap_regions(SpanParam
                     int owner = -1;
                     bool complex = false;
                     int64_t j = b;
-                    while (j < e && active != 0 && !complex) {
+                    while (j < e && (active & (active - 1)) != 0 && !complex) {     // phase 1: several trajectories, 16 bytes between merge checks
                         int nb = (int)(e - j < 16 ? e - j : 16);
                         const uintptr_t ga = gbuf + (uintptr_t)j;
                         uint32_t w[4];
@@ -2618,6 +2816,39 @@ __global__ void __launch_bounds__(SM_WARPS * 32, 2) k_statemap_regions(SpanParam
                                 }
                             }
                         }
+                    }
+                    if (!complex && active != 0 && j < e) {
+                        // phase 2: ONE trajectory is left (the usual state a few bytes into the sub-chunk).  Four steps run
+                        // without looking at the flag bits; the OR of the four words is tested once and only a word that
+                        // held an event is walked again with the books.
+                        const int k1 = __ffs(active) - 1;
+                        uint32_t cur = k1 == 0 ? st[0] : k1 == 1 ? st[1] : k1 == 2 ? st[2] : st[3];
+                        long long l2 = -1;
+                        while (j < e && cur != 0 && ((gbuf + (uintptr_t)j) & 15) != 0) { const uint32_t byte = __ldg(buf + j); FX_SM_STEP(T, cur, l2, byte, j); j++; }
+                        while (cur != 0 && j + 16 <= e) {
+                            const uint4 v = __ldg(reinterpret_cast<const uint4*>(gbuf + (uintptr_t)j));
+                            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const uint32_t n1 = T.next(cur, w4[q] & 0xFFu);
+                                const uint32_t n2 = T.next(n1 & W_SSTATE, (w4[q] >> 8) & 0xFFu);
+                                const uint32_t n3 = T.next(n2 & W_SSTATE, (w4[q] >> 16) & 0xFFu);
+                                const uint32_t n4 = T.next(n3 & W_SSTATE, w4[q] >> 24);
+                                if ((n1 | n2 | n3 | n4) & 0xB000u) {
+                                    const long long jj = j + 4 * q;
+                                    FX_SM_STEP(T, cur, l2, w4[q] & 0xFFu, jj);
+                                    FX_SM_STEP(T, cur, l2, (w4[q] >> 8) & 0xFFu, jj + 1);
+                                    FX_SM_STEP(T, cur, l2, (w4[q] >> 16) & 0xFFu, jj + 2);
+                                    FX_SM_STEP(T, cur, l2, w4[q] >> 24, jj + 3);
+                                } else cur = n4 & W_SSTATE;
+                            }
+                            j += 16;
+                        }
+                        while (j < e && cur != 0) { const uint32_t byte = __ldg(buf + j); FX_SM_STEP(T, cur, l2, byte, j); j++; }
+                        if (l2 >= 0) { last = l2; owner = k1; }
+#pragma unroll
+                        for (int k = 0; k < SM_M; k++) if (k == k1) st[k] = cur;
+                        if (cur == 0) active = 0;
                     }
                     if (complex) mine.ncand = 0xFF;
                     else {
@@ -2906,6 +3137,20 @@ __global__ void __launch_bounds__(256) k_buffer_literal(KParams p, SparseParams 
     }
 }
 
+// A pattern whose prefix literal can overlap itself, or that has a suffix literal: the reference's candidate list is the
+// NON-OVERLAPPING occurrences of the prefix, left to right, cut short by the last occurrence of the suffix
+// (utility_m.f90:58-117, api_internal_m.F90:76-164) -- a sequential rule.  One thread replays it exactly as the batch
+// kernels do for a string (eval_regex): always right, never fast (tens of MB/s); the parallel scans above serve every
+// other pattern.
+__global__ void k_buffer_sequential(KParams p, const uint8_t* __restrict__ buf, int64_t len, int64_t* __restrict__ from_to) {
+    Table<3> T;
+    T.g_table = p.ctable; T.g_cmap = p.classmap; T.shift = p.c_row_shift; T.s_table = 0; T.s_cmap = 0;
+    int64_t f, t;
+    eval_regex(p, T, FetchGlobal{buf}, len, f, t);
+    from_to[0] = f;
+    from_to[1] = t;
+}
+
 // second step: longest end for the winning start; also the literal / degenerate cases.  `key` is the winning
 // start as an S position of the whole text; the window must hold the text from that start to the end of its match.
 __global__ void k_buffer_finish(KParams p, const uint8_t* __restrict__ buf, ScanWindow W,
@@ -2972,12 +3217,14 @@ __device__ inline bool nfa_bool(const KParams& p, const NfaEngine& N, const uint
     const uint8_t* suf = pre + p.pre_len;
     FetchGlobal fetch{s};
     if (OP == 1) {
+        if (p.all_active) return lit_index(s, len, p.lits, p.all_len) > 0;            // literal fast path (forgex.F90:111-130)
         if (len == 0 || (len == 1 && fetch(0) == 0x20)) return p.q0_accepting != 0;
         Anchored A{nullptr, 0, 0};
         int64_t f, t;
         including_exact(A, N, fetch, len, pre, p.pre_len, p.pre_active != 0, suf, p.suf_len, p.suf_active != 0, f, t);
         return f > 0 && t > 0;
     }
+    if (p.all_active && len == p.all_len) return lit_equal(s, p.lits, p.all_len);     // forgex.F90:207-213
     // prefix / suffix gate of do_matching_exactly (api_internal_m.F90:199-233)
     const int64_t lp = p.pre_len, ls = p.suf_len;
     if (len > 0 && lp > 0 && lp == len && lit_equal(s, pre, (int)lp)) return true;

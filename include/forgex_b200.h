@@ -61,8 +61,10 @@ enum {
                                           lazily visited states: src/lazy_dfa/lazy_dfa_graph_m.F90:90-92) AND the NFA
                                           engine cannot take over (more than 8191 NFA states), or an entry point that
                                           needs the table engine was called on an NFA-engine handle */
-    FX_ERR_PREFILTER_UNSUPPORTED = 103,/* pattern whose literal prefilter (src/api_internal_m.F90:76-104) is not
-                                          provably result-neutral; see DESIGN.md "out of contract" */
+    FX_ERR_PREFILTER_UNSUPPORTED = 103,/* WINDOW forms only (a text split across GPUs): the pattern's candidate list is
+                                          sequential -- a prefix literal that can overlap itself, or a suffix literal
+                                          (src/essential/utility_m.f90:58-117).  fx_regex_buffer* itself answers such
+                                          patterns (one thread replays the reference's rule: exact, slow) */
     FX_ERR_BAD_ARGUMENT = 104,
     FX_ERR_NO_DEVICE = 105
 };
@@ -95,8 +97,10 @@ typedef struct fx_pattern_info {
     int32_t sparse_second;    /* >= 0: F is one byte and only this ASCII byte (or a lead byte) can follow it: the sweep
                                  tests for the byte pair; -1 otherwise */
     int32_t sparse_used;      /* 1: the last ragged `.in.` launch / buffer scan used the SWAR first-byte sweep */
-    int32_t prefix_scan;      /* FX_OP_REGEX with an extracted prefix literal: 1 when the long-buffer path handles it (the
-                                 literal has no border and there is no suffix literal); 0: FX_ERR_PREFILTER_UNSUPPORTED */
+    int32_t prefix_scan;      /* FX_OP_REGEX with an extracted prefix literal: 1 when the long-buffer path takes the literal's
+                                 occurrences as candidates in parallel (the literal has no border and there is no suffix
+                                 literal); 0: the candidate list is sequential -- fx_regex_buffer* replays it on one thread,
+                                 the window forms answer FX_ERR_PREFILTER_UNSUPPORTED */
     int32_t statemap;         /* FX_OP_REGEX: 1 when the pattern has the linear-time span path (forward "ordered groups"
                                  automaton + reverse automaton): ragged batches run on it (K3f), and fx_regex_buffer* can
                                  fall back on the chunked state-map scan (K5) */

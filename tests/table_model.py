@@ -659,12 +659,16 @@ class NfaModel:
         return drv.including_exact(s)
 
     def boolean(self, s: bytes):
-        _, pre, suf = self.lit
+        all_, pre, suf = self.lit
         if self.op == 1:
+            if not blank(all_):
+                return all_ in s
             if len(s) == 0 or s == b" ":
                 return self.q0_accepting
             f, t = self.including(s)
             return f > 0 and t > 0
+        if not blank(all_) and len(s) == len(all_):
+            return s == all_
         lp, ls = len(pre), len(suf)
         if len(s) > 0 and lp > 0 and lp == len(s) and s == pre:
             return True

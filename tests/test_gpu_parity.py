@@ -224,11 +224,21 @@ def test_buffer_patterns_with_a_prefix_literal():
                 assert p.regex_buffer(arr) == c.regex_buffer(np.ascontiguousarray(arr)), (pat, text[:60], len(text), shift)
         used += 1
     assert used == 6
-    for pat in [b"ab+c", b"aab*", b"abab+", b"fo+bar"]:          # suffix literal / bordered prefix
+    # suffix literal / bordered prefix: the candidate list is sequential (non-overlapping occurrences, cut short by the
+    # last suffix occurrence) -- one thread replays the reference's rule; the window forms decline
+    import torch
+    for pat in [b"ab+c", b"aab*", b"abab+", b"fo+bar", b"aa[bc]"]:
         p = fx.Pattern(pat, "regex")
         assert p.info()["prefix_scan"] == 0
+        c = O.Compiled(pat, 0)
+        for text in [b"xx aabab abc", b"aaab", b"aaaab aab", b"ababab abab", b"fobar foobar", b"abbbc abc c", b"", b"c", filler[:3000] + b"aaab abbc foobar",
+                     b"ab" * 500 + b"c", b"a" * 301 + b"b"]:
+            arr = np.frombuffer(text, dtype=np.uint8)
+            assert p.regex_buffer(arr) == c.regex_buffer(arr), (pat, text[:40])
+        win = torch.zeros(64, dtype=torch.uint8, device="cuda")
+        best = torch.tensor([-1, 0, 0], dtype=torch.int64, device="cuda")
         with pytest.raises(fx.ForgexError) as e:
-            p.regex_buffer(np.frombuffer(b"xx aabab abc", dtype=np.uint8))
+            p.buffer_scan_dev(win, 64, 0, 64, 0, True, True, best)
         assert e.value.status == _lib.FX_ERR_PREFILTER_UNSUPPORTED
 
 
@@ -528,14 +538,8 @@ def test_generated_patterns_on_gpu(seed, monkeypatch):
                 ef, et = c.regex_batch(buf, off)
                 assert np.array_equal(f, ef) and np.array_equal(t, et), (pat, np.nonzero((f != ef) | (t != et))[0][:5])
                 tried["regex"] += 1
-                try:
-                    got = p.regex_buffer(jarr)
-                except fx.ForgexError as e:
-                    assert e.status == _lib.FX_ERR_PREFILTER_UNSUPPORTED and p.info()["prefix_scan"] == 0, (pat, e)
-                    tried["unsupported"] += 1
-                else:
-                    assert got == c.regex_buffer(jarr), (pat, "buffer")
-                    tried["buffer"] += 1
+                assert p.regex_buffer(jarr) == c.regex_buffer(jarr), (pat, "buffer")      # every pattern is accepted on the buffer path
+                tried["buffer"] += 1
             else:
                 o = 1 if op == "match" else 0
                 got = p.in_batch(buf, off) if op == "in" else p.match_batch(buf, off)
@@ -749,8 +753,6 @@ def test_all_matches_and_counts():
         p = fx.Pattern(pat, "regex")
         if p.status != 0:
             continue
-        if p.info()["literal_prefix_len"] and not p.info()["prefix_scan"] and not p.info()["literal_only"]:
-            continue                                   # (sequential prefix candidates: not on the buffer path)
         c = O.Compiled(pat, 0)
         for text in texts:
             if len(text) > 20000 and pat not in pats[:15]:

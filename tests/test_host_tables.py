@@ -160,7 +160,8 @@ def test_nfa_engine_tables_against_the_oracle(monkeypatch):
     rng = random.Random(808)
     texts = [gen_text(rng) for _ in range(60)] + [b"", b" ", b"foobar", b"abc\nabc", b"\xe3\x81\x82a\xff", b"aaaa", b"aaab"]
     used = 0
-    for pat in [b"foo(bar|baz)", rb"\d{3}-\d{4}", rb"^ERROR.*timeout=\d+$", b"(a|b)*a(a|b){3}", b"a*", b"^$", b"aa[bc]", b"ab+c", "[ぁ-ん]+a".encode()] + \
+    for pat in [b"foo(bar|baz)", rb"\d{3}-\d{4}", rb"^ERROR.*timeout=\d+$", b"(a|b)*a(a|b){3}", b"a*", b"^$", b"aa[bc]", b"ab+c", "[ぁ-ん]+a".encode(),
+                b"ab", b"a{1,7}", b"[/]"] + \
                [gen_pattern(rng).encode() for _ in range(50)]:
         for op in ("in", "match", "regex"):
             p = fx.Pattern(pat, op)
