@@ -47,6 +47,7 @@ struct DeviceTables {
     uint8_t* sp_classmap = nullptr; uint8_t* sp_endinfo = nullptr;
     uint16_t* r_delta = nullptr; int32_t* r_cuts = nullptr; uint8_t* r_page = nullptr; uint8_t* r_mixed = nullptr;
     uint16_t* sm_reach = nullptr; uint16_t* sm_img = nullptr;
+    uint16_t* ctab4 = nullptr; uint8_t* cmap4 = nullptr;       // compact ASCII-columns table of a big boolean automaton (K1c)
     uint64_t* nfa_trans = nullptr; uint64_t* nfa_q0 = nullptr; int32_t* nfa_cuts = nullptr;     // NFA engine (patterns past the state cap)
     uint8_t* w_work = nullptr; size_t w_work_cap = 0;
     // grow-only scratch for the host-pointer entry points
@@ -89,6 +90,11 @@ struct fx_pattern {
     std::vector<uint16_t> sm_reach, sm_img;
     bool statemap = false;
     int last_statemap = 0;       // 1: the last fx_regex_buffer* call was answered by the state-map scan
+    // K1c: the ASCII columns of a big boolean table (at most 4 byte classes among the ASCII bytes): nstates x 4 words
+    std::vector<uint16_t> ctab4;
+    uint8_t cmap4[256];
+    bool compact = false;
+    int last_compact = 0;
     FirstSet first;              // bytes that survive the first step out of q0 of the anchored automaton
     bool sparse = false;         // the sparse-start kernel (K2c) may serve `.in.` batches
     int last_sparse = 0;
@@ -311,6 +317,12 @@ int ensure_device(fx_pattern* p) {
             if (!rv.mixed.empty()) CUDA_TRY(cudaMemcpy(d.r_mixed, rv.mixed.data(), rv.mixed.size(), cudaMemcpyHostToDevice));
         }
     }
+    if (p->compact) {
+        CUDA_TRY(cudaMalloc(&d.ctab4, p->ctab4.size() * 2 + 16));
+        CUDA_TRY(cudaMemcpy(d.ctab4, p->ctab4.data(), p->ctab4.size() * 2, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&d.cmap4, 256));
+        CUDA_TRY(cudaMemcpy(d.cmap4, p->cmap4, 256, cudaMemcpyHostToDevice));
+    }
     if (p->statemap) {
         CUDA_TRY(cudaMalloc(&d.sm_reach, p->sm_reach.size() * 2 + 16));
         CUDA_TRY(cudaMemcpy(d.sm_reach, p->sm_reach.data(), p->sm_reach.size() * 2, cudaMemcpyHostToDevice));
@@ -483,9 +495,28 @@ int launch_fixed(fx_pattern* p, const uint8_t* buf, int64_t n, int64_t stride, u
     if (rc) return rc;
     int generic = generic_mode(pl, OP);
     p->last_sparse = 0;
+    p->last_compact = 0;
     if (OP == 1 && !generic && p->sparse && stride > 0 && n < (1ll << 31) && env_int("FX_SPARSE", 1)) {   // sparse starts (K2c)
         p->last_sparse = 1;
         return launch_sparse(p, pl, buf, nullptr, n, n * stride, out, s, stride);
+    }
+    if (pl.kind == 3 && p->compact && !generic && pl.kp.prefix_mode == 0 && stride >= 16 && stride % 16 == 0 &&
+        reinterpret_cast<uintptr_t>(buf) % 16 == 0 && env_int("FX_COMPACT", 1)) {       // big automaton, small ASCII alphabet (K1c)
+        const bool in_smem = p->residency != FX_TABLE_GLOBAL;
+        const size_t smem = 256 + (in_smem ? (size_t)p->prog.bt.nstates * 8 + 16 : 0);
+        auto kern_s = k_bool_fixed_compact<OP, true>;
+        auto kern_g = k_bool_fixed_compact<OP, false>;
+        int bps = 0;
+        int rc2 = in_smem ? occupancy_grid(kern_s, 1024, smem, p->dev.sm_count, bps) : occupancy_grid(kern_g, 1024, smem, p->dev.sm_count, bps);
+        if (rc2) return rc2;
+        long long want = (n + 1023) / 1024, cap = (long long)p->dev.sm_count * bps * 2;
+        const int grid = (int)(want < cap ? want : cap);
+        if (in_smem) kern_s<<<grid, 1024, smem, s>>>(pl.kp, p->dev.ctab4, p->dev.cmap4, buf, n, stride, out);
+        else kern_g<<<grid, 1024, smem, s>>>(pl.kp, p->dev.ctab4, p->dev.cmap4, buf, n, stride, out);
+        g_launches++;
+        p->last_compact = in_smem ? 1 : 2;
+        p->last_residency = in_smem ? FX_TABLE_SMEM : FX_TABLE_GLOBAL;
+        return cuda_status(cudaGetLastError());
     }
     if (pl.kind == 0) return launch_fixed_v<OP, 0>(p, pl, buf, n, stride, out, s, generic);
     if (pl.kind == 2) return launch_fixed_v<OP, 2>(p, pl, buf, n, stride, out, s, generic);
@@ -783,37 +814,46 @@ int launch_span_t(fx_pattern* p, const Plan& pl, const SpanParams& sp, int fwd_b
     return cuda_status(cudaGetLastError());
 }
 
-// K3f, pooled form: one CTA of 1024 walkers per SM, CTA-wide tiles (double buffered), strings claimed from a counter
-template <int FK, bool RS>
-int launch_span_pool_t(fx_pattern* p, const Plan& pl, const SpanParams& sp, int fwd_bytes, const uint8_t* buf,
-                       const int64_t* off, int64_t n, int64_t total, int64_t* from, int64_t* to, cudaStream_t s) {
-    auto kern = k_span_pool<FK, RS>;
+// K3f, streaming form: every warp owns a ring of RING_NB small buffers and never waits for a tile to finish
+template <int FK, bool RS, int WARPS>
+int launch_span_stream_t(fx_pattern* p, const Plan& pl, const SpanParams& sp, int fwd_bytes, const uint8_t* buf,
+                         const int64_t* off, int64_t n, int64_t total, int64_t* from, int64_t* to, cudaStream_t s) {
+    auto kern = k_span_stream<FK, RS, WARPS>;
     int64_t avg = n > 0 ? (total + n - 1) / n : 1;
     if (avg < 1) avg = 1;
     const SpanHead H = span_head(fwd_bytes, sp.rstates * sp.rclasses * 2, sp.nmixed, RS);
-    const int per_buf = ((227 * 1024 - 1024 - H.bytes - 128) / 2) & ~127;
-    if (per_buf < 8192) return FX_ERR_BAD_ARGUMENT;
-    int cap = per_buf - 256, spt = 1;
+    const int per_buf = (((227 * 1024 - 1024 - H.bytes) / WARPS) / RING_NB) & ~127;
+    if (per_buf < 512) return FX_ERR_BAD_ARGUMENT;
+    int cap = per_buf, spt = 1;
     for (;;) {
         int64_t want = ((int64_t)cap * 7 / 8) / avg;       // expect the tile to fill most of the staged capacity
-        spt = (int)(want < 1 ? 1 : want > 2048 ? 2048 : want);
-        if (cap <= 4096 || pool_layout(spt, cap).buf_bytes <= per_buf) break;
+        spt = (int)(want < 1 ? 1 : want > 512 ? 512 : want);
+        if (cap <= 256 || ring_layout(spt, cap).buf_bytes <= per_buf) break;
         cap -= 128;
     }
     spt = env_int("FX_TILE_STRINGS", spt);
-    if (spt > 2048) spt = 2048;
-    while (spt > 1 && pool_layout(spt, cap).buf_bytes > per_buf) spt--;
+    if (spt > 512) spt = 512;
+    while (spt > 1 && ring_layout(spt, cap).buf_bytes > per_buf) spt--;
     const int64_t ntiles = (n + spt - 1) / spt;
-    const size_t smem = (size_t)H.bytes + 128 + 2 * (size_t)pool_layout(spt, cap).buf_bytes;
+    const size_t smem = (size_t)H.bytes + (size_t)WARPS * RING_NB * (size_t)ring_layout(spt, cap).buf_bytes;
     int bps = 0;
-    int rc = occupancy_grid(kern, POOL_THREADS, smem, p->dev.sm_count, bps);
+    int rc = occupancy_grid(kern, WARPS * 32, smem, p->dev.sm_count, bps);
     if (rc) return rc;
     long long capg = (long long)p->dev.sm_count * bps;
-    int grid = (int)(ntiles < capg ? ntiles : capg);
+    long long want = (ntiles + WARPS - 1) / WARPS;
+    int grid = (int)(want < capg ? want : capg);
     if (grid < 1) grid = 1;
-    kern<<<grid, POOL_THREADS, smem, s>>>(pl.kp, sp, buf, off, n, total, from, to, spt, cap, ntiles, fwd_bytes);
+    kern<<<grid, WARPS * 32, smem, s>>>(pl.kp, sp, buf, off, n, total, from, to, spt, cap, ntiles, fwd_bytes);
     g_launches++;
     return cuda_status(cudaGetLastError());
+}
+template <int FK, bool RS>
+int launch_span_stream(fx_pattern* p, const Plan& pl, const SpanParams& sp, int fwd_bytes, const uint8_t* buf,
+                       const int64_t* off, int64_t n, int64_t total, int64_t* from, int64_t* to, cudaStream_t s) {
+    // 16 warps per SM: the walker state (ring bookkeeping + a forward walk + a backward job) needs ~110 registers; with
+    // 32 warps (64 registers) ptxas spills 400 bytes per thread
+    if (env_int("FX_SPAN_WARPS", 16) == 32) return launch_span_stream_t<FK, RS, 32>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
+    return launch_span_stream_t<FK, RS, 16>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
 }
 
 int launch_regex_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, int64_t n, int64_t total,
@@ -835,13 +875,13 @@ int launch_regex_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, i
         if (fk == 0 && !p->dev.sp_direct) fk = 1;
         const int fwd_bytes = fk == 0 ? st.nstates * SPAN_ROW * 2 : fk == 1 ? classed_bytes : 0;
         const bool rs = !rv.page.empty() && (int)(rv.delta16.size() * 2 + 1024 + rv.mixed.size()) <= SPAN_REV_SMEM_BYTES;
-        if (env_int("FX_SPAN_POOL", 1)) {          // pooled walkers over CTA-wide tiles (default)
-            if (fk == 0) return rs ? launch_span_pool_t<0, true>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s)
-                                   : launch_span_pool_t<0, false>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
-            if (fk == 1) return rs ? launch_span_pool_t<1, true>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s)
-                                   : launch_span_pool_t<1, false>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
-            return rs ? launch_span_pool_t<2, true>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s)
-                      : launch_span_pool_t<2, false>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
+        if (env_int("FX_SPAN_STREAM", 1)) {        // ring of buffers per warp, continuous claiming (default)
+            if (fk == 0) return rs ? launch_span_stream<0, true>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s)
+                                   : launch_span_stream<0, false>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
+            if (fk == 1) return rs ? launch_span_stream<1, true>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s)
+                                   : launch_span_stream<1, false>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
+            return rs ? launch_span_stream<2, true>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s)
+                      : launch_span_stream<2, false>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
         }
         if (fk == 0) return rs ? launch_span_t<0, true>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s)
                                : launch_span_t<0, false>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
@@ -1151,6 +1191,27 @@ struct CompileSource {
 
 static int finish_compile(fx_pattern* p, const CompileSource& src, int op, fx_pattern** out) {
     if (p->prog.status == fx::OK && p->prog.nfa_engine) { *out = p; return fx::OK; }     // NFA engine: no tables to derive
+    if (p->prog.status == fx::OK && op != FX_OP_REGEX && (int)p->prog.bt.table.size() * 2 > SMEM_TABLE_LIMIT_BYTES &&
+        p->prog.bt.nstates * 8 <= 100 * 1024) {
+        // a big boolean automaton: keep its ASCII columns apart if the ASCII bytes fall into at most 4 classes (K1c)
+        const fx::ByteTable& bt = p->prog.bt;
+        int cols[4] = {-1, -1, -1, -1}, ncols = 0;
+        bool ok = true;
+        memset(p->cmap4, 0, 256);
+        for (int b = 0; b < 128 && ok; b++) {
+            const int c = bt.classmap[b];
+            int k = 0;
+            while (k < ncols && cols[k] != c) k++;
+            if (k == ncols) { if (ncols == 4) { ok = false; break; } cols[ncols++] = c; }
+            p->cmap4[b] = (uint8_t)k;
+        }
+        if (ok) {
+            p->ctab4.assign((size_t)bt.nstates * 4, 0);
+            for (int st = 0; st < bt.nstates; st++)
+                for (int k = 0; k < ncols; k++) p->ctab4[(size_t)st * 4 + (size_t)k] = bt.table[((size_t)st << bt.row_shift) + (size_t)cols[k]];
+            p->compact = true;
+        }
+    }
     if (p->prog.status == fx::OK && op == FX_OP_IN && !p->prog.literal_only) {
         // `.in.` consults the prefix prefilter: keep the anchored automaton to replay it exactly when needed.  The same
         // automaton drives the sparse-start kernel; without a prefix it is optional and built under a smaller cap.
@@ -1294,7 +1355,7 @@ int fx_pattern_free(fx_pattern* p) {
         cudaFree(d.sp_table); cudaFree(d.sp_direct); cudaFree(d.sp_classmap); cudaFree(d.sp_endinfo);
         cudaFree(d.r_delta); cudaFree(d.r_cuts); cudaFree(d.r_page); cudaFree(d.r_mixed);
         cudaFree(d.sm_reach); cudaFree(d.sm_img); cudaFree(d.w_work);
-        cudaFree(d.nfa_trans); cudaFree(d.nfa_q0); cudaFree(d.nfa_cuts);
+        cudaFree(d.nfa_trans); cudaFree(d.nfa_q0); cudaFree(d.nfa_cuts); cudaFree(d.ctab4); cudaFree(d.cmap4);
         cudaFree(d.w_buf); cudaFree(d.w_off); cudaFree(d.w_out); cudaFree(d.w_span); cudaFree(d.w_best);
     }
     delete p;
@@ -1333,6 +1394,7 @@ int fx_pattern_get_info(const fx_pattern* p, fx_pattern_info* info) {
     info->sparse_used = p->last_sparse;
     info->prefix_scan = p->prefix_scan ? 1 : 0;
     info->nfa_engine = g.nfa_engine ? 1 : 0;
+    info->compact_used = p->last_compact;
     info->statemap = p->statemap ? 1 : 0;
     info->statemap_used = p->last_statemap;
     return FX_OK;

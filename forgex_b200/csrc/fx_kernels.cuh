@@ -712,6 +712,52 @@ __global__ void __launch_bounds__(256) k_bool_fixed(KParams p, const uint8_t* __
 }
 
 // ---------------------------------------------------------------------------------------------
+// K1c: fixed-stride batch, boolean result, BIG automaton with a small ASCII alphabet (config C5: 10252 states, but the
+// ASCII bytes fall into three classes -- a, b, everything else).  The class-compressed table of such a pattern (16
+// classes, 328 KB) fits neither shared memory nor L1; its ASCII columns alone do: 4 columns x 2 bytes = 8 bytes per
+// state, 82 KB.  Strings that hold a byte >= 0x80 (multi-byte sequences need the other 12 columns) are decided by the
+// full table (eval_bool_slow); everything else walks the compact one -- from shared memory (SMEM), or, when the caller
+// forces the global path (BASELINE config 5 is stated as the L2/HBM table path), from global memory, where 82 KB stay
+// in L1 and four rows share a 32-byte sector.  The byte -> column map is a 256-byte table in shared memory either way.
+// ---------------------------------------------------------------------------------------------
+template <int OP, bool SMEM>
+__global__ void __launch_bounds__(1024, 2) k_bool_fixed_compact(KParams p, const uint16_t* __restrict__ ctab, const uint8_t* __restrict__ cmap4,
+                                                               const uint8_t* __restrict__ buf, int64_t n, int64_t stride,
+                                                               uint8_t* __restrict__ out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = __ldg(reinterpret_cast<const uint32_t*>(cmap4) + i);
+    if (SMEM)
+        for (int i = threadIdx.x; i < p.nstates * 2; i += blockDim.x)
+            reinterpret_cast<uint32_t*>(smem + 256)[i] = __ldg(reinterpret_cast<const uint32_t*>(ctab) + i);
+    __syncthreads();
+    const uint32_t s_cmap = smem_u32(smem), s_tab = smem_u32(smem + 256);
+    auto next = [&](uint32_t st, uint32_t byte) -> uint32_t {
+        const uint32_t c = lds_u8(s_cmap + byte);
+        return SMEM ? lds_u16(s_tab + st * 8 + c * 2) : (uint32_t)__ldg(ctab + st * 4 + c);
+    };
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gstride) {
+        const uint8_t* s = buf + i * stride;
+        uint32_t st = (uint32_t)p.start, high = 0;
+        for (int64_t k = 0; k < stride; k += 16) {
+            const uint4 v = ldg_nc_v4(s + k);
+            high |= v.x | v.y | v.z | v.w;
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                st = next(st, w[q] & 0xFFu);
+                st = next(st, (w[q] >> 8) & 0xFFu);
+                st = next(st, (w[q] >> 16) & 0xFFu);
+                st = next(st, w[q] >> 24);
+            }
+        }
+        bool r = result_flag(p, st);
+        if (high & 0x80808080u) r = eval_bool_slow<OP>(p, s, stride);      // a non-ASCII byte: the full table decides
+        out[i] = r ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K2: ragged batch (flat buffer + int64 offsets), boolean result (config C2 `.in.`)
 // A CTA owns tile t = strings [t*spt, (t+1)*spt).  Their bytes are contiguous in the flat buffer, so the
 // tile is brought into shared memory by ONE TMA bulk copy (up to `cap` bytes; strings that reach past the
@@ -1851,11 +1897,19 @@ __global__ void __launch_bounds__(SPAN_WARPS * 32, 1) k_span_ragged(KParams p, S
                 if (jend > len) jend = len;
                 while (j < jend && ((a + (uint32_t)j) & 3u)) { const uint32_t b = lds_u8(a + j); FX_SPAN_STEP(T, st, last, b, j); j++; }
                 for (; j + 4 <= jend && st != 0; j += 4) {
+                    // four steps without looking at the flag bits; only a word that held an event (accept, replay mark:
+                    // rare) is walked again with the books
                     const uint32_t w4 = lds_u32(a + j);
-                    FX_SPAN_STEP(T, st, last, w4 & 0xFFu, j);
-                    FX_SPAN_STEP(T, st, last, (w4 >> 8) & 0xFFu, j + 1);
-                    FX_SPAN_STEP(T, st, last, (w4 >> 16) & 0xFFu, j + 2);
-                    FX_SPAN_STEP(T, st, last, w4 >> 24, j + 3);
+                    const uint32_t n1 = T.next(st, w4 & 0xFFu);
+                    const uint32_t n2 = T.next(n1 & W_SSTATE, (w4 >> 8) & 0xFFu);
+                    const uint32_t n3 = T.next(n2 & W_SSTATE, (w4 >> 16) & 0xFFu);
+                    const uint32_t n4 = T.next(n3 & W_SSTATE, w4 >> 24);
+                    if ((n1 | n2 | n3 | n4) & 0xB000u) {
+                        FX_SPAN_STEP(T, st, last, w4 & 0xFFu, j);
+                        FX_SPAN_STEP(T, st, last, (w4 >> 8) & 0xFFu, j + 1);
+                        FX_SPAN_STEP(T, st, last, (w4 >> 16) & 0xFFu, j + 2);
+                        FX_SPAN_STEP(T, st, last, w4 >> 24, j + 3);
+                    } else st = n4 & W_SSTATE;
                 }
                 if (st != 0) for (; j < jend; j++) { const uint32_t b = lds_u8(a + j); FX_SPAN_STEP(T, st, last, b, j); }
                 if (st == 0 || j >= len) {                          // this walk is over
@@ -1892,37 +1946,39 @@ __global__ void __launch_bounds__(SPAN_WARPS * 32, 1) k_span_ragged(KParams p, S
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3f, pooled form (the default).  Same two walks as k_span_ragged above, different division of labour: the tile is the
-// CTA's (about 80 KB of text, hundreds of strings, brought in by ONE TMA bulk copy, double buffered: the next tile lands
-// while this one is walked), and the 1024 threads of the CTA are a pool of walkers that claim the tile's strings one by
-// one from a shared counter.  A lane that finishes its string claims the next; the claim is looked at every 32 bytes
-// walked.  With warp-private tiles a lane walked two strings per tile and then waited for the warp's slowest; here the
-// imbalance is one string per CTA and tile.  The forward step also defers its bookkeeping: four steps run without
-// looking at the flag bits, the OR of the four words is tested once, and only a word that held an event (accept, replay
-// mark: rare) is walked again with the full bookkeeping.
+// K3f, streaming form (the default).  Same walks as k_span_ragged above; what changes is that a warp never waits for a
+// tile to finish.  Every warp owns a RING of NB small buffers (its share of shared memory cut in NB pieces, each filled
+// by its own TMA bulk copy on its own mbarrier).  The 32 lanes are walkers: a lane without a string claims the next
+// unclaimed string of the oldest buffer that has one -- no matter whether the other lanes are still busy with earlier
+// strings -- and walks it 32 bytes per round.  A buffer is flushed (results written as one coalesced run) and refilled
+// with the warp's next tile as soon as its last string is complete, while the lanes are already at work in the next
+// buffer.  A forward walk that ends with a match leaves a backward JOB in the lane (the lane goes on claiming); the
+// jobs of the warp are run together when 16 lanes hold one, when a lane would need a second slot, or when nothing else
+// is left to do -- so both walks run with most lanes busy.
+// With per-tile passes (above) a warp walked ~2 strings per lane and then waited for its slowest lane, and ran its
+// backward walks in half-empty batches: 46 % of the lanes were busy on C3.
 // ---------------------------------------------------------------------------------------------
-static constexpr int POOL_THREADS = 1024;
-struct PoolLayout { int off_res, off_queue, off_text, buf_bytes; };
-__host__ __device__ __forceinline__ PoolLayout pool_layout(int spt, int cap) {
-    PoolLayout L;
+static constexpr int RING_NB = 3;
+struct RingLayout { int off_res, off_text, buf_bytes; };
+__host__ __device__ __forceinline__ RingLayout ring_layout(int spt, int cap) {
+    RingLayout L;
     L.off_res = (16 + (spt + 4) * 4 + 7) & ~7;
-    L.off_queue = L.off_res + spt * 8;
-    L.off_text = (L.off_queue + spt * 4 + 127) & ~127;
+    L.off_text = (L.off_res + spt * 8 + 127) & ~127;
     L.buf_bytes = (L.off_text + cap + 64 + 127) & ~127;
     return L;
 }
 
-template <int FK, bool RS>
-__global__ void __launch_bounds__(POOL_THREADS, 1) k_span_pool(KParams p, SpanParams sp, const uint8_t* __restrict__ buf,
+template <int FK, bool RS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_span_stream(KParams p, SpanParams sp, const uint8_t* __restrict__ buf,
                                                               const int64_t* __restrict__ offsets, int64_t n, int64_t total,
                                                               int64_t* __restrict__ from, int64_t* __restrict__ to,
                                                               int spt, int cap, int64_t ntiles, int fwd_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t FULL = 0xffffffffu;
     const SpanHead H = span_head(fwd_bytes, sp.rstates * sp.rclasses * 2, sp.nmixed, RS);
-    const PoolLayout L = pool_layout(spt, cap);
-    // ---- stage the tables ----
+    const RingLayout L = ring_layout(spt, cap);
+    // ---- stage the tables (the only block-wide step) ----
     SpanFwd<FK> T;
     T.s_cmap = smem_u32(smem); T.s_table = smem_u32(smem + 256); T.g_table = sp.table; T.g_cmap = sp.classmap; T.shift = sp.row_shift;
     if (FK == 0) {
@@ -1946,146 +2002,213 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_span_pool(KParams p, SpanPa
         for (int i = threadIdx.x; i < 1024; i += blockDim.x) smem[H.off_page + i] = __ldg(sp.rpage + i);
         for (int i = threadIdx.x; i < sp.nmixed * 64; i += blockDim.x) smem[H.off_mixed + i] = __ldg(sp.rmixed + i);
     }
-    int* s_ctl = reinterpret_cast<int*>(smem + H.bytes);               // [0..1] next unclaimed string, [2..3] queue fill (per buffer)
-    uint8_t* bufs = smem + H.bytes + 128;
-    if (threadIdx.x < 2) mbar_init(smem_u32(bufs + threadIdx.x * L.buf_bytes), 1);
+    uint8_t* ring = smem + H.bytes + warp * (RING_NB * L.buf_bytes);
+    if (lane < RING_NB) mbar_init(smem_u32(ring + lane * L.buf_bytes), 1);
     __syncthreads();
     const uintptr_t gbuf = reinterpret_cast<uintptr_t>(buf);
-    uint32_t phase[2] = {0, 0};
+    const int64_t nwarps = (int64_t)gridDim.x * WARPS;
+    int64_t next_tile = (int64_t)blockIdx.x * WARPS + warp;          // the warp's tiles: next_tile, next_tile + nwarps, ...
 
-    // bring tile t into buffer b: one bulk copy (thread 0), the offsets as tile-relative int32 (everyone)
-    auto prefetch = [&](int64_t t, int b) {
-        uint8_t* B = bufs + b * L.buf_bytes;
-        int32_t* s_off = reinterpret_cast<int32_t*>(B + 16);
-        uint8_t* text = B + L.off_text;
-        const int64_t first = t * spt;
-        const int count = (int)((n - first) < spt ? (n - first) : spt);
-        const int64_t t0 = __ldg(offsets + first), tend = __ldg(offsets + first + count);
-        const int64_t t1 = tend - t0 > cap ? t0 + cap : tend;
-        const uintptr_t g0 = gbuf + (uintptr_t)t0;
-        const int64_t base = t0 - (int64_t)(g0 & 15);
-        const uintptr_t gsrc = g0 & ~(uintptr_t)15;
-        uintptr_t gcopy_end = (gbuf + (uintptr_t)t1 + 15) & ~(uintptr_t)15;
-        const uintptr_t gsafe_end = (gbuf + (uintptr_t)total) & ~(uintptr_t)15;
-        if (gcopy_end > gsafe_end) gcopy_end = gsafe_end;
-        const uint32_t bulk = gcopy_end > gsrc ? (uint32_t)(gcopy_end - gsrc) : 0u;
-        if (threadIdx.x == 0) {
-            s_ctl[b] = 0; s_ctl[2 + b] = 0;
-            const uint32_t mbar = smem_u32(B);
-            if (bulk) { mbar_expect_tx(mbar, bulk); bulk_g2s(smem_u32(text), reinterpret_cast<const void*>(gsrc), bulk, mbar); }
-            else mbar_expect_tx(mbar, 0);                              // (an empty tile still completes its phase)
-        }
-        for (int64_t x = (int64_t)(gsrc + bulk) - (int64_t)gbuf + threadIdx.x; x < t1; x += blockDim.x)
-            if (x >= t0) text[x - base] = __ldg(buf + x);
-        for (int i = threadIdx.x; i <= count; i += blockDim.x) {
-            const int64_t o = __ldg(offsets + first + i);
-            s_off[i] = o > t1 ? OFF_BEYOND : (int32_t)(o - base);
-        }
-    };
+    // ring bookkeeping (warp-uniform): per buffer the tile it holds, how many strings, how many claimed / complete
+    int64_t b_first[RING_NB];
+    int b_count[RING_NB], b_claimed[RING_NB], b_done[RING_NB];
+    uint32_t b_phase[RING_NB];
+    bool b_loaded[RING_NB], b_ready[RING_NB];
+#pragma unroll
+    for (int x = 0; x < RING_NB; x++) { b_first[x] = 0; b_count[x] = 0; b_claimed[x] = 0; b_done[x] = 0; b_phase[x] = 0; b_loaded[x] = false; b_ready[x] = false; }
+    int oldest = 0;                                                   // claims go through the buffers in ring order from here
 
-    int64_t t = blockIdx.x;
-    if (t < ntiles) prefetch(t, 0);
-    for (int k = 0; t < ntiles; k++, t += gridDim.x) {
-        const int b = k & 1;
-        if (t + gridDim.x < ntiles) prefetch(t + gridDim.x, b ^ 1);    // the other buffer is free: its tile was finished behind a barrier
-        uint8_t* B = bufs + b * L.buf_bytes;
-        int32_t* s_off = reinterpret_cast<int32_t*>(B + 16);
-        int2* s_res = reinterpret_cast<int2*>(B + L.off_res);
-        uint32_t* s_queue = reinterpret_cast<uint32_t*>(B + L.off_queue);
-        const uint32_t text_addr = smem_u32(B + L.off_text);
-        const int64_t first = t * spt;
-        const int count = (int)((n - first) < spt ? (n - first) : spt);
-        mbar_wait(smem_u32(B), phase[b]); phase[b] ^= 1;
-        __syncthreads();                                               // offsets and counters of this tile are visible
-        // ---- forward walks: claim, walk a round, look again ----
-        bool have = false;
-        int sidx = 0, len = 0, j = 0, last = -1;
-        uint32_t a = 0, st = 0;
-        volatile int* v_next = s_ctl + b;
-        for (;;) {
-            const uint32_t idle = __ballot_sync(FULL, !have);
-            bool more = true;
-            if (idle) {
-                int base = 0;
-                if (lane == 0) base = *v_next < count ? atomicAdd(s_ctl + b, __popc(idle)) : count;
-                base = __shfl_sync(FULL, base, 0);
-                more = base < count;
-                const int mine = base + __popc(idle & ((1u << lane) - 1));
-                if (!have && mine < count) {
-                    sidx = mine;
-                    const int32_t r0 = s_off[sidx], r1 = s_off[sidx + 1];
-                    if (r1 == OFF_BEYOND) {      // longer than the tile: the same two walks, text from global memory
-                        const int64_t o0 = __ldg(offsets + first + sidx), o1 = __ldg(offsets + first + sidx + 1);
-                        int64_t f = 0, e = 0;
-                        if (o1 - o0 == 0 || (o1 - o0 == 1 && __ldg(buf + o0) == 0x20)) {
-                        } else if (o1 - o0 < 0x7FFFFFF0ll) {
-                            span_linear(sp, T, R, FetchGlobal{buf + o0}, (int)(o1 - o0), f, e);
-                        } else {
-                            Table<3> G;
-                            G.g_table = p.ctable; G.g_cmap = p.classmap; G.shift = p.c_row_shift; G.s_table = 0; G.s_cmap = 0;
-                            eval_regex(p, G, FetchGlobal{buf + o0}, o1 - o0, f, e);
-                        }
-                        from[first + sidx] = f; to[first + sidx] = e;
-                        s_res[sidx] = make_int2(-1, -1);
+    // lane state: the forward walk in hand, and one backward job
+    bool have = false;
+    int f_buf = 0, f_sidx = 0, f_len = 0, j = 0, last = -1;
+    uint32_t f_a = 0, st = 0;
+    bool job = false, spill = false;                                  // spill: a finished forward walk waits for the job slot
+    int j_buf = 0, j_sidx = 0, j_len = 0, j_last = 0;
+    uint32_t j_a = 0;
+
+    for (;;) {
+        // ---- 1. flush complete buffers, load the warp's next tiles into free ones ----
+#pragma unroll
+        for (int x = 0; x < RING_NB; x++) {
+            if (b_loaded[x] && b_done[x] == b_count[x]) {
+                const int2* s_res = reinterpret_cast<const int2*>(ring + x * L.buf_bytes + L.off_res);
+                __syncwarp();
+                for (int i = lane; i < b_count[x]; i += 32) {
+                    const int2 r = s_res[i];
+                    if (r.x >= 0) { from[b_first[x] + i] = r.x; to[b_first[x] + i] = r.y; }
+                }
+                b_loaded[x] = false;
+                __syncwarp();
+            }
+            if (!b_loaded[x] && next_tile < ntiles) {
+                uint8_t* B = ring + x * L.buf_bytes;
+                int32_t* s_off = reinterpret_cast<int32_t*>(B + 16);
+                uint8_t* text = B + L.off_text;
+                const int64_t first = next_tile * spt;
+                const int count = (int)((n - first) < spt ? (n - first) : spt);
+                const int64_t t0 = __ldg(offsets + first), tend = __ldg(offsets + first + count);
+                const int64_t t1 = tend - t0 > cap ? t0 + cap : tend;
+                const uintptr_t g0 = gbuf + (uintptr_t)t0;
+                const int64_t base = t0 - (int64_t)(g0 & 15);
+                const uintptr_t gsrc = g0 & ~(uintptr_t)15;
+                uintptr_t gcopy_end = (gbuf + (uintptr_t)t1 + 15) & ~(uintptr_t)15;
+                const uintptr_t gsafe_end = (gbuf + (uintptr_t)total) & ~(uintptr_t)15;
+                if (gcopy_end > gsafe_end) gcopy_end = gsafe_end;
+                const uint32_t bulk = gcopy_end > gsrc ? (uint32_t)(gcopy_end - gsrc) : 0u;
+                if (lane == 0) {
+                    const uint32_t mbar = smem_u32(B);
+                    mbar_expect_tx(mbar, bulk);
+                    if (bulk) bulk_g2s(smem_u32(text), reinterpret_cast<const void*>(gsrc), bulk, mbar);
+                }
+                for (int64_t xx = (int64_t)(gsrc + bulk) - (int64_t)gbuf + lane; xx < t1; xx += 32)
+                    if (xx >= t0) text[xx - base] = __ldg(buf + xx);
+                for (int i = lane; i <= count; i += 32) {
+                    const int64_t o = __ldg(offsets + first + i);
+                    s_off[i] = o > t1 ? OFF_BEYOND : (int32_t)(o - base);
+                }
+                b_first[x] = first; b_count[x] = count; b_claimed[x] = 0; b_done[x] = 0;
+                b_loaded[x] = true; b_ready[x] = false;
+                next_tile += nwarps;
+                __syncwarp();
+            }
+        }
+        // ---- 2. idle lanes claim strings, oldest buffer first ----
+        uint32_t idle = __ballot_sync(FULL, !have && !spill);
+        bool starving = false;
+#pragma unroll
+        for (int k = 0; k < RING_NB; k++) {
+            const int x = (oldest + k) % RING_NB;
+            bool usable = false;
+            int cl = 0, cnt = 0;
+#pragma unroll
+            for (int y = 0; y < RING_NB; y++) if (y == x) { usable = b_loaded[y] && b_claimed[y] < b_count[y]; cl = b_claimed[y]; cnt = b_count[y]; }
+            if (idle == 0 || !usable) continue;
+            bool ready = false;
+#pragma unroll
+            for (int y = 0; y < RING_NB; y++) if (y == x) ready = b_ready[y];
+            if (!ready) {
+                // the copy may still be in flight: wait for it only if no lane has anything else to do
+                const bool busy = __any_sync(FULL, have || job);
+                uint32_t ph = 0;
+#pragma unroll
+                for (int y = 0; y < RING_NB; y++) if (y == x) ph = b_phase[y];
+                uint32_t ok = 0;
+                const uint32_t mbar = smem_u32(ring + x * L.buf_bytes);
+                if (busy) {
+                    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(ok) : "r"(mbar), "r"(ph) : "memory");
+                    ok = __all_sync(FULL, ok != 0) ? 1u : 0u;
+                } else { mbar_wait(mbar, ph); ok = 1; }
+                if (!ok) { starving = true; break; }                 // (older strings first: do not skip ahead of a buffer in flight)
+#pragma unroll
+                for (int y = 0; y < RING_NB; y++) if (y == x) { b_ready[y] = true; b_phase[y] ^= 1; }
+                __syncwarp();
+            }
+            const int32_t* s_off = reinterpret_cast<const int32_t*>(ring + x * L.buf_bytes + 16);
+            int2* s_res = reinterpret_cast<int2*>(ring + x * L.buf_bytes + L.off_res);
+            const uint32_t text_addr = smem_u32(ring + x * L.buf_bytes + L.off_text);
+            const int mine = cl + __popc(idle & ((1u << lane) - 1));
+            int finished_here = 0;                                   // strings decided at claim time
+            bool took = false;
+            if (((idle >> lane) & 1u) && mine < cnt) {
+                took = true;
+                const int32_t r0 = s_off[mine], r1 = s_off[mine + 1];
+                int64_t bf = 0;
+#pragma unroll
+                for (int y = 0; y < RING_NB; y++) if (y == x) bf = b_first[y];
+                if (r1 == OFF_BEYOND) {          // longer than a buffer: the same two walks, text from global memory
+                    const int64_t o0 = __ldg(offsets + bf + mine), o1 = __ldg(offsets + bf + mine + 1);
+                    int64_t f = 0, e = 0;
+                    if (o1 - o0 == 0 || (o1 - o0 == 1 && __ldg(buf + o0) == 0x20)) {
+                    } else if (o1 - o0 < 0x7FFFFFF0ll) {
+                        span_linear(sp, T, R, FetchGlobal{buf + o0}, (int)(o1 - o0), f, e);
                     } else {
-                        len = r1 - r0;
-                        a = text_addr + (uint32_t)r0;
-                        if (len == 0 || (len == 1 && lds_u8(a) == 0x20)) s_res[sidx] = make_int2(0, 0);   // api_internal_m.F90:68-74
-                        else { have = true; j = 0; st = (uint32_t)sp.start; last = sp.start_acc ? 0 : -1; }
+                        Table<3> G;
+                        G.g_table = p.ctable; G.g_cmap = p.classmap; G.shift = p.c_row_shift; G.s_table = 0; G.s_cmap = 0;
+                        eval_regex(p, G, FetchGlobal{buf + o0}, o1 - o0, f, e);
                     }
+                    from[bf + mine] = f; to[bf + mine] = e;
+                    s_res[mine] = make_int2(-1, -1);
+                    finished_here = 1;
+                } else {
+                    f_len = r1 - r0;
+                    f_a = text_addr + (uint32_t)r0;
+                    if (f_len == 0 || (f_len == 1 && lds_u8(f_a) == 0x20)) { s_res[mine] = make_int2(0, 0); finished_here = 1; }   // api_internal_m.F90:68-74
+                    else { have = true; f_buf = x; f_sidx = mine; j = 0; st = (uint32_t)sp.start; last = sp.start_acc ? 0 : -1; }
                 }
             }
-            if (!__any_sync(FULL, have)) { if (!more) break; else continue; }
-            if (have) {
-                int jend = (int)(((a + (uint32_t)j + SPAN_ROUND) & ~3u) - a);
-                if (jend > len) jend = len;
-                while (j < jend && ((a + (uint32_t)j) & 3u)) { const uint32_t bb = lds_u8(a + j); FX_SPAN_STEP(T, st, last, bb, j); j++; }
-                for (; j + 4 <= jend && st != 0; j += 4) {
-                    const uint32_t w4 = lds_u32(a + j);
-                    const uint32_t n1 = T.next(st, w4 & 0xFFu);
-                    const uint32_t n2 = T.next(n1 & W_SSTATE, (w4 >> 8) & 0xFFu);
-                    const uint32_t n3 = T.next(n2 & W_SSTATE, (w4 >> 16) & 0xFFu);
-                    const uint32_t n4 = T.next(n3 & W_SSTATE, w4 >> 24);
-                    if ((n1 | n2 | n3 | n4) & 0xB000u) {               // an accept or a replay mark in this word: again, with the books
-                        FX_SPAN_STEP(T, st, last, w4 & 0xFFu, j);
-                        FX_SPAN_STEP(T, st, last, (w4 >> 8) & 0xFFu, j + 1);
-                        FX_SPAN_STEP(T, st, last, (w4 >> 16) & 0xFFu, j + 2);
-                        FX_SPAN_STEP(T, st, last, w4 >> 24, j + 3);
-                    } else st = n4 & W_SSTATE;
-                }
-                if (st != 0) for (; j < jend; j++) { const uint32_t bb = lds_u8(a + j); FX_SPAN_STEP(T, st, last, bb, j); }
-                if (st == 0 || j >= len) {
-                    if (st != 0) last = span_end_of_text(sp, st, len, last);
-                    have = false;
-                    if (last <= 0) s_res[sidx] = make_int2(0, 0);
-                }
+            const int ntook = __popc(__ballot_sync(FULL, took));
+            const int nfin = __popc(__ballot_sync(FULL, finished_here != 0));
+#pragma unroll
+            for (int y = 0; y < RING_NB; y++) if (y == x) { b_claimed[y] += ntook; b_done[y] += nfin; }
+            idle = __ballot_sync(FULL, !have && !spill && !took);    // (a lane that took a degenerate string may claim again next round)
+        }
+        // the oldest buffer moves on once every string of it is claimed
+#pragma unroll
+        for (int k = 0; k < RING_NB; k++) {
+            bool exhausted = false;
+#pragma unroll
+            for (int y = 0; y < RING_NB; y++) if (y == oldest) exhausted = !b_loaded[y] || b_claimed[y] >= b_count[y];
+            bool any_other = false;
+#pragma unroll
+            for (int y = 0; y < RING_NB; y++) if (y != oldest && b_loaded[y] && b_claimed[y] < b_count[y]) any_other = true;
+            if (exhausted && any_other) oldest = (oldest + 1) % RING_NB; else break;
+        }
+        // ---- 3. one round of forward walking ----
+        int fin_buf = -1;                                            // this lane completed a string of buffer fin_buf without a match
+        if (have) {
+            int jend = (int)(((f_a + (uint32_t)j + SPAN_ROUND) & ~3u) - f_a);
+            if (jend > f_len) jend = f_len;
+            while (j < jend && ((f_a + (uint32_t)j) & 3u)) { const uint32_t bb = lds_u8(f_a + j); FX_SPAN_STEP(T, st, last, bb, j); j++; }
+            for (; j + 4 <= jend && st != 0; j += 4) {
+                const uint32_t w4 = lds_u32(f_a + j);
+                const uint32_t n1 = T.next(st, w4 & 0xFFu);
+                const uint32_t n2 = T.next(n1 & W_SSTATE, (w4 >> 8) & 0xFFu);
+                const uint32_t n3 = T.next(n2 & W_SSTATE, (w4 >> 16) & 0xFFu);
+                const uint32_t n4 = T.next(n3 & W_SSTATE, w4 >> 24);
+                if ((n1 | n2 | n3 | n4) & 0xB000u) {
+                    FX_SPAN_STEP(T, st, last, w4 & 0xFFu, j);
+                    FX_SPAN_STEP(T, st, last, (w4 >> 8) & 0xFFu, j + 1);
+                    FX_SPAN_STEP(T, st, last, (w4 >> 16) & 0xFFu, j + 2);
+                    FX_SPAN_STEP(T, st, last, w4 >> 24, j + 3);
+                } else st = n4 & W_SSTATE;
             }
-            const bool push = !have && last > 0;
-            const uint32_t pm = __ballot_sync(FULL, push);
-            if (pm) {
-                int qb = 0;
-                if (lane == 0) qb = atomicAdd(s_ctl + 2 + b, __popc(pm));
-                qb = __shfl_sync(FULL, qb, 0);
-                if (push) { s_queue[qb + __popc(pm & ((1u << lane) - 1))] = ((uint32_t)sidx << 20) | (uint32_t)last; last = -1; }
+            if (st != 0) for (; j < jend; j++) { const uint32_t bb = lds_u8(f_a + j); FX_SPAN_STEP(T, st, last, bb, j); }
+            if (st == 0 || j >= f_len) {
+                if (st != 0) last = span_end_of_text(sp, st, f_len, last);
+                have = false;
+                if (last <= 0) {                                     // no match, or only the leading NUL matched (to = 0)
+                    reinterpret_cast<int2*>(ring + f_buf * L.buf_bytes + L.off_res)[f_sidx] = make_int2(0, 0);
+                    fin_buf = f_buf;
+                } else if (!job) { job = true; j_buf = f_buf; j_sidx = f_sidx; j_len = f_len; j_last = last; j_a = f_a; }
+                else spill = true;                                   // the job slot is taken: the warp runs its jobs now
             }
         }
-        __syncthreads();
-        // ---- backward walks over the queue ----
-        const int nq = s_ctl[2 + b];
-        for (int q = threadIdx.x; q < nq; q += blockDim.x) {
-            const uint32_t e = s_queue[q];
-            const int si = (int)(e >> 20), lst = (int)(e & 0xFFFFFu);
-            const int32_t r0 = s_off[si];
-            const int ln = s_off[si + 1] - r0;
-            const int f = span_backward(sp, R, FetchShared{text_addr + (uint32_t)r0}, ln, lst);
-            s_res[si] = f > 0 ? make_int2(f, lst < ln ? lst : ln) : make_int2(0, 0);
+#pragma unroll
+        for (int y = 0; y < RING_NB; y++) b_done[y] += __popc(__ballot_sync(FULL, fin_buf == y));
+        // ---- 4. backward jobs: when half the lanes hold one, when a lane needs the slot, or when nothing else is left ----
+        const uint32_t jobs = __ballot_sync(FULL, job);
+        const bool any_spill = __any_sync(FULL, spill);
+        const bool any_fwd = __any_sync(FULL, have);
+        (void)starving;
+        if (jobs != 0 && (__popc(jobs) >= 16 || any_spill || !any_fwd)) {      // (!any_fwd: no lane found a string to walk this round)
+            int jb = -1;
+            if (job) {
+                const int f = span_backward(sp, R, FetchShared{j_a}, j_len, j_last);
+                reinterpret_cast<int2*>(ring + j_buf * L.buf_bytes + L.off_res)[j_sidx] =
+                    f > 0 ? make_int2(f, j_last < j_len ? j_last : j_len) : make_int2(0, 0);
+                jb = j_buf;
+                job = false;
+            }
+            if (spill) { job = true; spill = false; j_buf = f_buf; j_sidx = f_sidx; j_len = f_len; j_last = last; j_a = f_a; }
+#pragma unroll
+            for (int y = 0; y < RING_NB; y++) b_done[y] += __popc(__ballot_sync(FULL, jb == y));
         }
-        __syncthreads();
-        for (int i = threadIdx.x; i < count; i += blockDim.x) {
-            const int2 r = s_res[i];
-            if (r.x >= 0) { from[first + i] = r.x; to[first + i] = r.y; }
-        }
-        __syncthreads();                                               // this buffer may be refilled from the next iteration on
+        // ---- 5. done? ----
+        bool pending = __any_sync(FULL, have || job || spill) || next_tile < ntiles;
+#pragma unroll
+        for (int y = 0; y < RING_NB; y++) if (b_loaded[y]) pending = true;
+        if (!pending) break;
     }
 }
 
@@ -2185,7 +2308,6 @@ __device__ __forceinline__ bool try_start(const KParams& p, const Table<KIND>& T
         const int64_t from = at;
         bool out = false;
         while (at < stop) {
-            if (((reinterpret_cast<uintptr_t>(buf) + (uintptr_t)at) & 31) == 0 && at + 128 < len) prefetch_l1(buf + at + 128);
             const uint32_t nw = T.next(st, __ldg(buf + at));
             if (nw & (W_ACC | W_INTER)) { out = true; break; }
             if (nw == 0) { acc += (uint32_t)(at - from); return false; }
@@ -2412,54 +2534,14 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
     const int64_t pos_base = (int64_t)ubase - (int64_t)gbuf;                      // window position of unit 0's first byte (may be < start_lo)
     int uqn = 0, sqn = 0;
 
-    // Attempts: the lanes are a pool of walkers over the queued starts.  A lane without an attempt claims the next
-    // start; all lanes walk up to 64 plain steps (one load, one lookup each: for C4 the whole line behind `^ERROR`) and
-    // the warp looks again, so that lines of different lengths do not leave lanes idle.  Whatever lies behind the plain
-    // stretch -- an accept, a multi-byte sequence, the end of the window -- goes through attempt_tail.
+    // Attempts, 32 at a time (tried: the lanes as a pool over up to 63 queued starts, 64 steps between claims -- 0.48 vs
+    // 0.29 ms per 2 GiB of C4 for this phase; the claim path and the partial last rounds cost more than the idle lanes)
     auto run_starts = [&](int count) {
         __syncwarp();
-        if (!(phases & 2)) return;
-        int next = 0;
-        bool have = false;
-        int64_t pos = 0, at = 0;
-        uint32_t st = 0;
-        for (;;) {
-            const uint32_t idle = __ballot_sync(FULL, !have);
-            if (idle != 0 && next < count) {
-                const int mine = next + __popc(idle & ((1u << lane) - 1));
-                if (!have && mine < count) {
-                    pos = s_starts[mine];
-                    const uint32_t b0 = __ldg(buf + pos);
-                    if (!((b0 & 0xC0) == 0x80 && !continuation_is_boundary(buf, len, pos))) {
-                        have = true; st = q0; at = pos;
-#pragma unroll
-                        for (int k = 0; k < 4; k++) if (pos + 32 * k < len) prefetch_l1(buf + pos + 32 * k);
-                    }
-                }
-                next += __popc(idle);
-            }
-            if (!__any_sync(FULL, have)) { if (next >= count) break; else continue; }
-            if (have) {
-                const int64_t stop = at + 64 < len ? at + 64 : len;
-                const int64_t from = at;
-                bool out = false, dead = false;
-                if (at + 160 < len) prefetch_l1(buf + at + 160);
-                while (at < stop) {
-                    const uint32_t nw = T.next(st, __ldg(buf + at));
-                    if (nw & (W_ACC | W_INTER)) { out = true; break; }
-                    if (nw == 0) { dead = true; break; }
-                    st = nw;
-                    at++;
-                }
-                acc += (uint32_t)(at - from);
-                if (acc >= BUDGET_TICK) { const uint32_t a = acc; acc = 0; if (budget_spent(B, a)) dead = true; }
-                if (dead) have = false;
-                else if (out || at >= len) {
-                    if (attempt_tail(p, T, buf, len, st, at, open_end, overflow, B))
-                        atomicMin(best, (unsigned long long)(W.origin + pos) + 2);
-                    have = false;
-                }
-            }
+        if (lane < count && (phases & 2)) {
+            const int64_t pos = s_starts[lane];
+            if (try_start(p, T, buf, len, pos, __ldg(buf + pos), open_end, overflow, B, acc))
+                atomicMin(best, (unsigned long long)(W.origin + pos) + 2);
         }
         __syncwarp();
     };
@@ -2524,9 +2606,10 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
             if (m) {
                 if (sv) s_starts[sqn + __popc(m & ((1u << lane) - 1))] = pos;
                 sqn += __popc(m);
-                if (sqn >= 32) {           // (at most 63 are waiting: the pool takes them all)
-                    run_starts(sqn);
-                    sqn = 0;
+                if (sqn >= 32) {
+                    run_starts(32);
+                    if (lane < sqn - 32) { const int64_t x = s_starts[32 + lane]; s_starts[lane] = x; }
+                    sqn -= 32;
                     __syncwarp();
                 }
             }

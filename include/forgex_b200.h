@@ -109,6 +109,9 @@ typedef struct fx_pattern_info {
                                  Forgex builds its DFA lazily, so it answers such patterns (test/test_api/test_case_005.f90:
                                  76-108).  Correctness path, not a fast one; the window forms and the all-matches / count
                                  entry points answer FX_ERR_DFA_STATE_CAP for such a handle */
+    int32_t compact_used;     /* last fixed-stride launch: 1 / 2 when a big boolean automaton ran on its ASCII-columns table
+                                 from shared / global memory (K1c: at most 4 byte classes among the ASCII bytes, 8 bytes per
+                                 state; strings with bytes >= 0x80 are decided by the full table), else 0 */
     int32_t statemap_used;    /* last fx_regex_buffer* call: 0 candidate-start scan only; 1 state-map scan; 2 candidate-start
                                  scan under a work budget with the state-map scan behind it (which of the two answered is
                                  decided on the device) */

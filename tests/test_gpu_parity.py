@@ -243,13 +243,28 @@ def test_buffer_patterns_with_a_prefix_literal():
 
 
 @pytest.mark.parametrize("residency", ["auto", "global"])
-def test_c5_in_fixed_big_table(residency):
+@pytest.mark.parametrize("compact", ["1", "0"])
+def test_c5_in_fixed_big_table(residency, compact, monkeypatch):
+    """10252 byte-states x 16 classes (328 KB) fit neither shared memory nor L1.  K1c walks the ASCII columns alone
+    (82 KB: from shared memory, or from global memory when that path is forced as BASELINE config 5 states it); with
+    FX_COMPACT=0 the full class-compressed table is read through L1/L2 (K1).  Strings with bytes >= 0x80 always take
+    the full table."""
+    monkeypatch.setenv("FX_COMPACT", compact)
     buf, n, stride = synth.gen_c5(3000)
+    buf = buf.copy()
+    buf[5 * 64 + 7] = 0xC3; buf[5 * 64 + 8] = 0xA9        # a multi-byte character, a stray continuation byte, an overlong `a`
+    buf[9 * 64 + 60] = 0x80
+    buf[11 * 64 + 3] = 0xC1; buf[11 * 64 + 4] = 0xA1
     p = fx.Pattern(synth.PATTERNS["c5"], "in", residency=residency)
     got = p.in_fixed(buf, n, stride)
     exp = oracle_bool(synth.PATTERNS["c5"], "in", buf, n=n, stride=stride)
     assert np.array_equal(got, exp)
-    assert p.info()["residency"] == _lib.FX_TABLE_GLOBAL   # 10252 byte-states x 16 classes does not fit shared memory
+    info = p.info()
+    if compact == "1":
+        assert info["compact_used"] == (2 if residency == "global" else 1)
+        assert info["residency"] == (_lib.FX_TABLE_GLOBAL if residency == "global" else _lib.FX_TABLE_SMEM)
+    else:
+        assert info["compact_used"] == 0 and info["residency"] == _lib.FX_TABLE_GLOBAL
 
 
 # ---- edge cases: empty / ragged / long / unaligned -------------------------------------------------
