@@ -454,6 +454,36 @@ def measure_config(cfg, args, env):
     value = text_bytes_all / (ms_step / 1000.0) / 1e9
 
     verified = {}
+    general = None
+    if cfg == "c2" and not os.environ.get("FX_BENCH_NO_GENERAL"):
+        # the same batch through the GENERAL walker (K2): `\w+@\w+` has a dense first-byte set, so it cannot take the
+        # sparse-start kernel the headline pattern runs on -- it is what most patterns get
+        gp = fx.Pattern(rb"\w+@\w+", "in")
+        gout = torch.empty(w["units"], dtype=torch.uint8, device="cuda")
+        grun = lambda: gp.in_batch_dev(w["buf"], w["off"], w["units"], w["text_bytes"], gout)
+        for _ in range(args.warmup):
+            grun()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            grun()
+        g1.record()
+        barrier()
+        gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+        gms = float(gt.item()) / args.steps
+        general = {"pattern": "\\w+@\\w+", "op": ".in.", "ms_per_step": gms, "value": w["text_bytes"] * world / (gms / 1000.0) / 1e9, "unit": "GB/s",
+                   "sparse_used": gp.info()["sparse_used"], "matches_rank0": int(gout.sum(dtype=torch.int64).item())}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            from tests import oracle_lib as O
+            ns = 60000
+            off = w["off"][: ns + 1].cpu().numpy().copy()
+            hb = w["buf"][: int(off[-1])].cpu().numpy()
+            general["gpu_results_equal_oracle"] = bool(np.array_equal(gout[:ns].cpu().numpy(), O.Compiled(rb"\w+@\w+", 0).bool_batch(0, hb, off)))
+            general["oracle_sample_strings"] = ns
+        del gout
     if cfg == "c4":
         verified.update(verify_c4(torch, w, fx))
         if split:
@@ -562,6 +592,11 @@ def measure_config(cfg, args, env):
             # what the collectives cost: the same search on the same slabs minus the local scan alone
             stats = w["stats"]
             rec["collectives"] = {"per_search": "all_gather(3 x int64) + all_reduce(2 x int64)", "scan_rounds": stats.get("scan_rounds", 0) // max(1, args.steps + args.warmup)}
+        if general is not None:
+            peak_g, _ = measured_peak()
+            ab = w["text_bytes"] + EXTRA_BYTES[cfg] * w["units"]
+            general["roofline_frac"] = ab / (general["ms_per_step"] / 1000.0) / 1e9 / peak_g
+            rec["general_walker"] = general
         if verified:
             rec["verified"] = verified
         if not args.no_cpu and world == 1:
@@ -642,7 +677,7 @@ def main():
         if rank == 0:
             line = dict(recs["c2"])
             keep = ("value", "unit", "ms_per_step", "scaling", "strings_per_s", "matches", "gpu_launches", "roofline", "e2e",
-                    "cpu_baseline", "verified", "collectives", "clocks", "config", "wall_seconds_incl_setup")
+                    "cpu_baseline", "verified", "collectives", "clocks", "config", "wall_seconds_incl_setup", "general_walker")
             line["per_config"] = {c: {k: r[k] for k in keep if k in r} for c, r in recs.items()}
             for c, r in line["per_config"].items():
                 r["config"] = {k: v for k, v in r["config"].items() if k != "table"} | {"kernel_path": {

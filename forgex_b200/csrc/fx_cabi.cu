@@ -449,6 +449,35 @@ int launch_nfa_regex(fx_pattern* p, const uint8_t* buf, const int64_t* off, int6
     return cuda_status(cudaGetLastError());
 }
 
+// A table that is read from global memory (FX_TABLE_GLOBAL, or too big for shared memory) is marked PERSISTING in L2
+// for the launches that walk it: the text streams through L2 at terabytes per second and would otherwise keep evicting
+// table lines.  Best effort (errors are ignored: the window is a hint); cleared again behind the launch.
+struct L2Window {
+    cudaStream_t s;
+    bool set = false;
+    L2Window(cudaStream_t stream, const void* base, size_t bytes) : s(stream) {
+        if (!base || bytes == 0 || !env_int("FX_L2_PERSIST", 1)) return;
+        static std::once_flag once;
+        std::call_once(once, [] { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 4 << 20); cudaGetLastError(); });
+        cudaStreamAttrValue v;
+        memset(&v, 0, sizeof(v));
+        v.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+        v.accessPolicyWindow.num_bytes = bytes;
+        v.accessPolicyWindow.hitRatio = 1.0f;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        set = cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v) == cudaSuccess;
+        cudaGetLastError();
+    }
+    ~L2Window() {
+        if (!set) return;
+        cudaStreamAttrValue v;
+        memset(&v, 0, sizeof(v));
+        cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v);
+        cudaGetLastError();
+    }
+};
+
 // ---- launchers -----------------------------------------------------------------------------
 inline size_t staged_bytes(const Plan& pl) { return (size_t)((pl.table_bytes + 15) & ~15); }
 
@@ -511,6 +540,7 @@ int launch_fixed(fx_pattern* p, const uint8_t* buf, int64_t n, int64_t stride, u
         if (rc2) return rc2;
         long long want = (n + 1023) / 1024, cap = (long long)p->dev.sm_count * bps * 2;
         const int grid = (int)(want < cap ? want : cap);
+        L2Window keep(s, in_smem ? nullptr : p->dev.ctab4, (size_t)p->prog.bt.nstates * 8);
         if (in_smem) kern_s<<<grid, 1024, smem, s>>>(pl.kp, p->dev.ctab4, p->dev.cmap4, buf, n, stride, out);
         else kern_g<<<grid, 1024, smem, s>>>(pl.kp, p->dev.ctab4, p->dev.cmap4, buf, n, stride, out);
         g_launches++;
@@ -520,6 +550,7 @@ int launch_fixed(fx_pattern* p, const uint8_t* buf, int64_t n, int64_t stride, u
     }
     if (pl.kind == 0) return launch_fixed_v<OP, 0>(p, pl, buf, n, stride, out, s, generic);
     if (pl.kind == 2) return launch_fixed_v<OP, 2>(p, pl, buf, n, stride, out, s, generic);
+    L2Window keep(s, p->dev.table, p->prog.bt.table.size() * 2);
     return launch_fixed_v<OP, 3>(p, pl, buf, n, stride, out, s, generic);
 }
 
@@ -852,7 +883,6 @@ int launch_span_stream(fx_pattern* p, const Plan& pl, const SpanParams& sp, int 
                        const int64_t* off, int64_t n, int64_t total, int64_t* from, int64_t* to, cudaStream_t s) {
     // 16 warps per SM: the walker state (ring bookkeeping + a forward walk + a backward job) needs ~110 registers; with
     // 32 warps (64 registers) ptxas spills 400 bytes per thread
-    if (env_int("FX_SPAN_WARPS", 16) == 32) return launch_span_stream_t<FK, RS, 32>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
     return launch_span_stream_t<FK, RS, 16>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
 }
 
@@ -875,7 +905,7 @@ int launch_regex_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, i
         if (fk == 0 && !p->dev.sp_direct) fk = 1;
         const int fwd_bytes = fk == 0 ? st.nstates * SPAN_ROW * 2 : fk == 1 ? classed_bytes : 0;
         const bool rs = !rv.page.empty() && (int)(rv.delta16.size() * 2 + 1024 + rv.mixed.size()) <= SPAN_REV_SMEM_BYTES;
-        if (env_int("FX_SPAN_STREAM", 1)) {        // ring of buffers per warp, continuous claiming (default)
+        if (env_int("FX_SPAN_STREAM", 0)) {        // experiment: ring of buffers per warp, continuous claiming (lost)
             if (fk == 0) return rs ? launch_span_stream<0, true>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s)
                                    : launch_span_stream<0, false>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
             if (fk == 1) return rs ? launch_span_stream<1, true>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s)

@@ -739,7 +739,20 @@ __global__ void __launch_bounds__(1024, 2) k_bool_fixed_compact(KParams p, const
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gstride) {
         const uint8_t* s = buf + i * stride;
         uint32_t st = (uint32_t)p.start, high = 0;
-        for (int64_t k = 0; k < stride; k += 16) {
+        int64_t k = 0;
+        for (; k + 32 <= stride; k += 32) {            // a whole 32-byte sector per step: both halves asked for back to back
+            const uint4 v0 = ldg_nc_v4(s + k), v1 = ldg_nc_v4(s + k + 16);
+            high |= v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w;
+            const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                st = next(st, w[q] & 0xFFu);
+                st = next(st, (w[q] >> 8) & 0xFFu);
+                st = next(st, (w[q] >> 16) & 0xFFu);
+                st = next(st, w[q] >> 24);
+            }
+        }
+        for (; k < stride; k += 16) {
             const uint4 v = ldg_nc_v4(s + k);
             high |= v.x | v.y | v.z | v.w;
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -1946,7 +1959,10 @@ __global__ void __launch_bounds__(SPAN_WARPS * 32, 1) k_span_ragged(KParams p, S
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3f, streaming form (the default).  Same walks as k_span_ragged above; what changes is that a warp never waits for a
+// K3f, streaming form (EXPERIMENT, FX_SPAN_STREAM=1; not the default: 403 vs 720 GB/s on C3 -- the walker state needs
+// ~110 registers, so 16 warps per SM instead of 32, and the busy-lane count per instruction did not move (14.8 of 32
+// either way: the idle lanes of K3f sit INSIDE the walks -- rounds cut short by a dying state, byte-wise heads and tails,
+// the divergent backward decode -- not between strings).  Same walks as k_span_ragged above; what changes is that a warp never waits for a
 // tile to finish.  Every warp owns a RING of NB small buffers (its share of shared memory cut in NB pieces, each filled
 // by its own TMA bulk copy on its own mbarrier).  The 32 lanes are walkers: a lane without a string claims the next
 // unclaimed string of the oldest buffer that has one -- no matter whether the other lanes are still busy with earlier
@@ -2252,7 +2268,8 @@ struct ScanBudget {
     unsigned long long* abort;   // set once the budget is spent
     unsigned long long limit;
 };
-static constexpr int BUDGET_TICK = 4096;
+static constexpr int BUDGET_TICK = 65536;        // steps a lane walks between two looks at the shared counter (one atomic each:
+                                                 // at 4096 the 420 K same-address atomics of C4's attempts cost 3 ms of its 15)
 __device__ __forceinline__ bool budget_spent(const ScanBudget& B, unsigned long long steps) {
     if (B.limit == 0) return false;
     const unsigned long long before = atomicAdd(B.work, steps);
