@@ -854,11 +854,13 @@ static int compile_from_nfa(const Nfa& nfa, int op, int state_cap, Program& p, b
     if (rc != OK) { p.status = rc; return rc; }
     rc = build_byte_table(p.cp, op == MODE_REGEX, p.bt);
     if (rc != OK) { p.status = rc; return rc; }
-    if (want_span && op == MODE_REGEX && !p.literal_only && !p.prefix_active) {
+    if (want_span && op == MODE_REGEX && !p.literal_only) {
         // linear-time span path; silently absent when a cap is exceeded (the anchored tables above still serve)
         if (build_span_forward(nfa, state_cap, p.span_cp) == OK && build_byte_table(p.span_cp, true, p.span_bt, true) == OK &&
-            build_rev_automaton(nfa, 0xFFFF, p.rev) == OK)
-            p.has_span = true;
+            build_rev_automaton(nfa, 0xFFFF, p.rev) == OK) {
+            p.has_span_tables = true;
+            p.has_span = !p.prefix_active;      // with a prefix literal Forgex's candidates are the literal's occurrences
+        }
     }
     return OK;
 }

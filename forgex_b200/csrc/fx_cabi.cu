@@ -85,6 +85,7 @@ struct fx_pattern {
     bool has_anchored = false;
     int prefix_mode = 0;         // see KParams::prefix_mode
     bool prefix_scan = false;    // FX_OP_REGEX: the long-buffer path can take the prefix literal's occurrences as its candidates
+    bool prefix_neutral = false; // ... and every match provably begins with the literal (prefilter_is_neutral)
     // long-buffer state-map scan (K5): reachable live states of the span forward automaton and, per byte value, the
     // image of ALL of them under that byte (count, then up to SM_M states; 0xFFFF = wider)
     std::vector<uint16_t> sm_reach, sm_img;
@@ -291,7 +292,7 @@ int ensure_device(fx_pattern* p) {
         CUDA_TRY(cudaMalloc(&d.a_flags, at.flags.size() + 16));
         CUDA_TRY(cudaMemcpy(d.a_flags, at.flags.data(), at.flags.size(), cudaMemcpyHostToDevice));
     }
-    if (p->prog.has_span) {
+    if (p->prog.has_span_tables) {
         const fx::ByteTable& st = p->prog.span_bt;
         const fx::RevAutomaton& rv = p->prog.rev;
         CUDA_TRY(cudaMalloc(&d.sp_table, st.table.size() * 2 + 32));
@@ -947,7 +948,7 @@ int launch_scan_t(fx_pattern* p, const Plan& pl, const uint8_t* buf, const ScanW
 template <int KIND, int NR, bool HIGH, bool PREFIX, bool SET2 = false>
 int launch_scan_sparse_t(fx_pattern* p, const Plan& pl, const SparseParams& sp, const uint8_t* buf, const ScanWindow& W,
                          unsigned long long* best, cudaStream_t s, const unsigned long long* gate,
-                         const unsigned long long* run_if = nullptr, ScanBudget budget = ScanBudget{nullptr, nullptr, 0ull}) {
+                         const unsigned long long* run_if = nullptr, ScanBudget budget = ScanBudget{nullptr, nullptr, 0ull, 0}) {
     auto kern = k_buffer_scan_sparse<KIND, NR, HIGH, PREFIX, SET2>;
     int table_smem = (int)staged_bytes(pl);
     size_t smem = (size_t)scan_sparse_smem_bytes(table_smem);
@@ -959,6 +960,7 @@ int launch_scan_sparse_t(fx_pattern* p, const Plan& pl, const SparseParams& sp, 
     long long cap = (long long)p->dev.sm_count * bps;
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
+    budget.flags = env_int("FX_K4_FLAGS", 0);
     kern<<<grid, 256, smem, s>>>(pl.kp, sp, buf, W, best, table_smem, gate, env_int("FX_K4_PHASES", 3), run_if, budget);
     g_launches++;
     return cuda_status(cudaGetLastError());
@@ -973,7 +975,8 @@ int launch_scan_sparse(fx_pattern* p, const Plan& pl, const uint8_t* buf, const 
     const FirstSet& f = p->first;
     const bool one = f.sweep_nr == 1 && f.sweep_lo[0] == f.sweep_hi[0];
     // the two-byte test of the unit phase (the follower of a unit's last byte is never assumed)
-    if (f.set2 && f.sweep_nr >= 1 && f.sweep_nr <= 2 && env_int("FX_SWEEP_SET2", 1)) {
+    // (measured on C4: 15.2 vs 13.1 ms for 32 GiB -- the test costs ~80 instructions per queued unit and saves fewer: off)
+    if (f.set2 && f.sweep_nr >= 1 && f.sweep_nr <= 2 && env_int("FX_SWEEP_SET2", 0)) {
         fill_sweep_set2(f, sp);
         if (one) return f.high ? launch_scan_sparse_t<KIND, -1, true, false, true>(p, pl, sp, buf, W, best, s, gate, run_if, bg)
                                : launch_scan_sparse_t<KIND, -1, false, false, true>(p, pl, sp, buf, W, best, s, gate, run_if, bg);
@@ -994,11 +997,11 @@ int launch_scan_sparse(fx_pattern* p, const Plan& pl, const uint8_t* buf, const 
 // candidates = the occurrences of the prefix literal: sweep for its first byte
 template <int KIND>
 int launch_scan_prefix(fx_pattern* p, const Plan& pl, const uint8_t* buf, const ScanWindow& W, unsigned long long* best,
-                       cudaStream_t s) {
+                       cudaStream_t s, const unsigned long long* run_if, ScanBudget bg) {
     SparseParams sp;
     memset(&sp, 0, sizeof(sp));
     sp.add_lo[0] = (unsigned char)p->prog.lit.prefix[0] * 0x01010101u;      // NR = -1 form
-    return launch_scan_sparse_t<KIND, -1, false, true>(p, pl, sp, buf, W, best, s, nullptr);
+    return launch_scan_sparse_t<KIND, -1, false, true>(p, pl, sp, buf, W, best, s, nullptr, run_if, bg);
 }
 
 // scan starts [start_lo, start_hi) of a window; d_best[0] (min key), d_best[1] (undecided attempts) and d_best[2]
@@ -1010,7 +1013,7 @@ int launch_scan_prefix(fx_pattern* p, const Plan& pl, const uint8_t* buf, const 
 enum { SCAN_AUTO = 0, SCAN_ALL = 1 };
 int launch_scan(fx_pattern* p, const uint8_t* buf, const ScanWindow& W, unsigned long long* best, cudaStream_t s,
                 int mode = SCAN_AUTO, const unsigned long long* gate = nullptr, const unsigned long long* run_if = nullptr,
-                ScanBudget bg = ScanBudget{nullptr, nullptr, 0ull}) {
+                ScanBudget bg = ScanBudget{nullptr, nullptr, 0ull, 0}) {
     if (W.len < 0 || W.start_lo < 0 || W.start_hi > W.len || W.start_lo > W.start_hi) return FX_ERR_BAD_ARGUMENT;
     if (p->prog.nfa_engine) return FX_ERR_DFA_STATE_CAP;        // the window forms need the table engine
     const bool prefixed = p->prog.prefix_active && !p->prog.literal_only;
@@ -1033,9 +1036,9 @@ int launch_scan(fx_pattern* p, const uint8_t* buf, const ScanWindow& W, unsigned
         return cuda_status(cudaGetLastError());
     }
     if (prefixed && mode == SCAN_AUTO) {
-        if (pl.kind == 1) return launch_scan_prefix<1>(p, pl, buf, W, best, s);
-        if (pl.kind == 2) return launch_scan_prefix<2>(p, pl, buf, W, best, s);
-        return launch_scan_prefix<3>(p, pl, buf, W, best, s);
+        if (pl.kind == 1) return launch_scan_prefix<1>(p, pl, buf, W, best, s, run_if, bg);
+        if (pl.kind == 2) return launch_scan_prefix<2>(p, pl, buf, W, best, s, run_if, bg);
+        return launch_scan_prefix<3>(p, pl, buf, W, best, s, run_if, bg);
     }
     if (p->sparse && p->first.sweep_nr <= 2 && env_int("FX_SPARSE", 1)) {     // SWAR first-byte filter
         p->last_sparse = 1;
@@ -1128,7 +1131,10 @@ int launch_statemap(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* fro
            : fk == 1 ? launch_statemap_t<1>(p, sp, mp, fwd_bytes, buf, len, s, run_if)
                      : launch_statemap_t<2>(p, sp, mp, fwd_bytes, buf, len, s, run_if);
     if (rc) return rc;
-    k_buffer_finish_span<<<1, 1, 0, s>>>(sp, buf, len, mp.result, from_to, work + 8, work + 9, run_if);
+    // with a prefix literal the answer only stands if the winner begins with the literal's own bytes (see launch_buffer)
+    const bool check = p->prog.prefix_active && !p->prog.literal_only;
+    k_buffer_finish_span<<<1, 1, 0, s>>>(sp, buf, len, mp.result, from_to, work + 8, work + 9, run_if,
+                                         check ? p->dev.lits + p->prog.lit.all.size() : nullptr, check ? (int)p->prog.lit.prefix.size() : 0);
     g_launches++;
     return cuda_status(cudaGetLastError());
 }
@@ -1159,11 +1165,29 @@ int launch_buffer(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* from_
     // boundary), K4 runs without a budget.  All gating is on device flags: no host round trip.
     const int sm_mode = env_int("FX_STATEMAP", 1);             // 0 off, 1 as described, 2 always the state-map scan
     const bool sm_ok = p->statemap && !p->prog.literal_only && !prefixed && len >= 2 && sm_mode != 0;
+    if (prefixed && p->statemap && p->prefix_neutral && len >= 2 && sm_mode != 0) {
+        // A prefix literal: Forgex's candidates are the literal's occurrences (every boundary when it occurs nowhere).
+        // `a.*b` over a megabyte of `a` makes that quadratic too.  Same remedy: the candidate scan runs under the work
+        // budget; past it the state-map scan answers -- it tries EVERY boundary, which is the same answer whenever the
+        // winner begins with the literal's own bytes (the prefilter is provably neutral for this pattern: every match
+        // begins with the literal's code points; only an overlong encoding of them could differ).  If the winner does
+        // not, or the scan declines, the candidate scan runs again without a budget.
+        ScanBudget bg{work + 5, work + 4, (unsigned long long)len * 16ull + (4ull << 20), 0};
+        int rc = sm_mode == 2 ? FX_OK : launch_scan(p, buf, W, best, s, SCAN_AUTO, nullptr, nullptr, bg);
+        if (rc) return rc;
+        if (sm_mode == 2) CUDA_TRY(cudaMemsetAsync(work + 4, 0x01, 1, s));
+        else if ((rc = launch_scan(p, buf, W, best, s, SCAN_ALL, best + 2, nullptr, bg))) return rc;
+        if ((rc = launch_statemap(p, buf, len, from_to, work, s, work + 4))) return rc;
+        if ((rc = launch_scan(p, buf, W, work + 12, s, SCAN_AUTO, nullptr, work + 9))) return rc;
+        if ((rc = launch_scan(p, buf, W, work + 12, s, SCAN_ALL, work + 14, work + 9))) return rc;
+        p->last_statemap = sm_mode == 2 ? 1 : 2;
+        return launch_finish(p, buf, W, best, from_to, 1, s, work + 8, work + 9, work + 12);
+    }
     if (sm_ok) {
         const bool k4_first = p->sparse && p->first.sweep_nr <= 2 && env_int("FX_SPARSE", 1) && sm_mode != 2;
         int rc;
         if (k4_first) {
-            ScanBudget bg{work + 5, work + 4, (unsigned long long)len * 16ull + (4ull << 20)};
+            ScanBudget bg{work + 5, work + 4, (unsigned long long)len * 16ull + (4ull << 20), 0};
             rc = launch_scan(p, buf, W, best, s, SCAN_AUTO, nullptr, nullptr, bg);
             if (rc) return rc;
         } else {
@@ -1255,7 +1279,7 @@ static int finish_compile(fx_pattern* p, const CompileSource& src, int op, fx_pa
             p->prog.status = p->anchored.status;
         }
     }
-    if (p->prog.status == fx::OK && op == FX_OP_REGEX && p->prog.has_span) {
+    if (p->prog.status == fx::OK && op == FX_OP_REGEX && p->prog.has_span_tables) {
         // state-map scan tables: the live states reachable from the start, and the image of all of them under each byte
         const fx::ByteTable& st = p->prog.span_bt;
         std::vector<char> seen((size_t)st.nstates, 0);
@@ -1293,6 +1317,9 @@ static int finish_compile(fx_pattern* p, const CompileSource& src, int op, fx_pa
             for (size_t k = 1; k < pre.size() && ok; k++)
                 if (pre.compare(0, k, pre, pre.size() - k, k) == 0) ok = false;
             p->prefix_scan = ok;
+            // is trying every boundary the same as trying the literal's occurrences, as long as the winner begins with
+            // the literal's own bytes?  (then the state-map scan may stand in for a candidate scan that ran out of budget)
+            p->prefix_neutral = ok && prefilter_is_neutral(p->prog);
         }
     }
     *out = p;

@@ -221,7 +221,9 @@ struct Program {
     // absent (has_span == false) when a cap is exceeded or the pattern uses the prefix prefilter
     bool nfa_engine = false;     // the eager automaton passes the cap: matched by NFA simulation on the device (nfa_tables)
     NfaTables nfa_tables;
-    bool has_span = false;
+    bool has_span = false;          // ragged batches and the all-matches loop may use the span path (no prefix prefilter)
+    bool has_span_tables = false;   // the span automata exist (also for a pattern with a prefix literal: the long-buffer
+                                    // state-map scan uses them when the prefilter is provably result-neutral)
     CpAutomaton span_cp;
     ByteTable span_bt;
     RevAutomaton rev;

@@ -2267,6 +2267,7 @@ struct ScanBudget {
     unsigned long long* work;    // steps so far (all warps)
     unsigned long long* abort;   // set once the budget is spent
     unsigned long long limit;
+    int flags;                   // experiments (FX_K4_FLAGS): 1 = no prefetch in front of an attempt, 2 = the plain loop without budget chunks
 };
 static constexpr int BUDGET_TICK = 65536;        // steps a lane walks between two looks at the shared counter (one atomic each:
                                                  // at 4096 the 420 K same-address atomics of C4's attempts cost 3 ms of its 15)
@@ -2316,10 +2317,6 @@ __device__ __forceinline__ bool try_start(const KParams& p, const Table<KIND>& T
     // general loop, from the state and position reached (no accept has been seen so far).
     uint32_t st = (uint32_t)p.q0;
     int64_t at = pos;
-    // The 32 lanes of a batch walk 32 different lines byte by byte: without help some lane crosses into a new sector at
-    // almost every step and the whole warp waits for L2.  Ask for the next sectors up front (and keep asking below).
-#pragma unroll
-    for (int k = 0; k < 4; k++) if (pos + 32 * k < len) prefetch_l1(buf + pos + 32 * k);
     for (;;) {
         int64_t stop = at + BUDGET_TICK < len ? at + BUDGET_TICK : len;
         const int64_t from = at;
@@ -2363,7 +2360,7 @@ __global__ void __launch_bounds__(256) k_buffer_scan(KParams p, const uint8_t* _
                                                      const unsigned long long* __restrict__ run_if) {
     if (gate != nullptr && *gate != 0) return;      // the prefix occurs in the text: its occurrences were the candidates
     if (run_if != nullptr && *run_if == 0) return;  // fallback behind the state-map scan: only if that scan declined
-    const ScanBudget B{nullptr, nullptr, 0ull};
+    const ScanBudget B{nullptr, nullptr, 0ull, 0};
     uint32_t acc = 0;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_cmap = smem;
@@ -2495,10 +2492,8 @@ __global__ void __launch_bounds__(256) k_buffer_scan(KParams p, const uint8_t* _
 //           table steps (an open window end leaves the second undecided); survivors are queued;
 //   starts  32 at a time: boundary check + anchored attempt from global memory (try_start), 64-bit atomicMin.
 // shared memory: classmap 256 | table | 8 warps x (unit queue 64 x int64 | start queue 64 x int64)
-// per warp: unit queue 64 x (index int64 | the unit's 32 bytes) | start queue 64 x int64
-static constexpr int SCAN_WARP_BYTES = 64 * 8 + 64 * 32 + 64 * 8;
 __host__ __device__ __forceinline__ int scan_sparse_smem_bytes(int table_smem_bytes) {
-    return ((256 + table_smem_bytes + 15) & ~15) + 8 * SCAN_WARP_BYTES;
+    return ((256 + table_smem_bytes + 15) & ~15) + 8 * 2 * 64 * 8;
 }
 
 //
@@ -2521,10 +2516,8 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
     uint8_t* s_cmap = smem;
     uint8_t* s_table = smem + 256;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* s_warp = smem + ((256 + table_smem_bytes + 15) & ~15) + warp * SCAN_WARP_BYTES;
-    int64_t* s_units = reinterpret_cast<int64_t*>(s_warp);
-    uint4* s_udata = reinterpret_cast<uint4*>(s_warp + 64 * 8);      // the 32 bytes of a queued unit: no second trip to L2 / DRAM
-    int64_t* s_starts = reinterpret_cast<int64_t*>(s_warp + 64 * 8 + 64 * 32);
+    int64_t* s_units = reinterpret_cast<int64_t*>(smem + ((256 + table_smem_bytes + 15) & ~15)) + warp * 128;
+    int64_t* s_starts = s_units + 64;
     Table<KIND> T = stage_table<KIND>(p, s_table, s_cmap);
     __syncthreads();
     const uint32_t q0 = (uint32_t)p.q0;
@@ -2551,10 +2544,13 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
     const int64_t pos_base = (int64_t)ubase - (int64_t)gbuf;                      // window position of unit 0's first byte (may be < start_lo)
     int uqn = 0, sqn = 0;
 
-    // Attempts, 32 at a time (tried: the lanes as a pool over up to 63 queued starts, 64 steps between claims -- 0.48 vs
-    // 0.29 ms per 2 GiB of C4 for this phase; the claim path and the partial last rounds cost more than the idle lanes)
     auto run_starts = [&](int count) {
         __syncwarp();
+        if (B.limit != 0) {                                  // the budget is spent: no more attempts from this scan
+            unsigned long long ab = 0;
+            if (lane == 0) ab = *reinterpret_cast<volatile unsigned long long*>(B.abort);
+            if (__shfl_sync(FULL, ab, 0) != 0) return;
+        }
         if (lane < count && (phases & 2)) {
             const int64_t pos = s_starts[lane];
             if (try_start(p, T, buf, len, pos, __ldg(buf + pos), open_end, overflow, B, acc))
@@ -2568,7 +2564,8 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
         int64_t P = 0;
         if (lane < count && (phases & 1)) {
             const int64_t u = s_units[lane];
-            const uint4 v0 = s_udata[2 * lane], v1 = s_udata[2 * lane + 1];
+            const uintptr_t ua = ubase + ((uintptr_t)u << 5);
+            const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(ua)), v1 = __ldg(reinterpret_cast<const uint4*>(ua + 16));
             cand = pack_byte_flags(first_mask<NR, HIGH>(sp, v0.x)) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.y)) << 4) |
                    (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.z)) << 8) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v0.w)) << 12) |
                    (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.x)) << 16) | (pack_byte_flags(first_mask<NR, HIGH>(sp, v1.y)) << 20) |
@@ -2634,12 +2631,13 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
     };
 
     const int64_t gwarp = (int64_t)blockIdx.x * 8 + warp, nwarps = (int64_t)gridDim.x * 8;
+    int sweep_iter = 0;
     for (int64_t g0 = gwarp * 128; g0 < nunits; g0 += nwarps * 128) {
         unsigned long long cur = 0;
         if (lane == 0) cur = *reinterpret_cast<volatile unsigned long long*>(best);
         cur = __shfl_sync(FULL, cur, 0);
         if (cur != NO_START && (unsigned long long)(W.origin + pos_base + (g0 << 5)) + 2 > cur) break;   // behind the winner
-        if (B.limit != 0) {                                  // budget spent somewhere: this scan is over
+        if (B.limit != 0 && (sweep_iter++ & 7) == 0) {       // budget spent somewhere: this scan is over (looked at every 8th group)
             unsigned long long ab = 0;
             if (lane == 0) ab = *reinterpret_cast<volatile unsigned long long*>(B.abort);
             if (__shfl_sync(FULL, ab, 0) != 0) return;
@@ -2660,18 +2658,11 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
             uint32_t seen = 0;
             const bool hit = u < nunits && unit_any<NR, HIGH, false>(sp, va[k], vb[k], seen) != 0;
             const uint32_t m = __ballot_sync(FULL, hit);
-            if (hit) {
-                const int slot = uqn + __popc(m & ((1u << lane) - 1));
-                s_units[slot] = u; s_udata[2 * slot] = va[k]; s_udata[2 * slot + 1] = vb[k];
-            }
+            if (hit) s_units[uqn + __popc(m & ((1u << lane) - 1))] = u;
             uqn += __popc(m);
             if (uqn >= 32) {
                 run_units(32);
-                if (lane < uqn - 32) {
-                    const int64_t x = s_units[32 + lane];
-                    const uint4 d0 = s_udata[2 * (32 + lane)], d1 = s_udata[2 * (32 + lane) + 1];
-                    s_units[lane] = x; s_udata[2 * lane] = d0; s_udata[2 * lane + 1] = d1;
-                }
+                if (lane < uqn - 32) { const int64_t x = s_units[32 + lane]; s_units[lane] = x; }
                 uqn -= 32;
                 __syncwarp();
             }
@@ -3078,7 +3069,8 @@ __device__ inline long long span_backward64(const SpanParams& sp, const uint8_t*
 // kernel has produced the answer (the fallback scan behind it is then skipped).
 __global__ void k_buffer_finish_span(SpanParams sp, const uint8_t* __restrict__ buf, int64_t len, const long long* __restrict__ result,
                                      int64_t* __restrict__ from_to, unsigned long long* __restrict__ done,
-                                     unsigned long long* __restrict__ declined, const unsigned long long* __restrict__ run_if) {
+                                     unsigned long long* __restrict__ declined, const unsigned long long* __restrict__ run_if,
+                                     const uint8_t* __restrict__ lit, int lit_len) {
     if (run_if != nullptr && *run_if == 0) return;
     if (result[1] != 0) { *declined = 1; return; }           // the scan declined: the candidate scan runs again, unbudgeted
     const long long last = result[0];
@@ -3086,6 +3078,13 @@ __global__ void k_buffer_finish_span(SpanParams sp, const uint8_t* __restrict__ 
     if (!(len == 0 || (len == 1 && __ldg(buf) == 0x20)) && last > 0) {        // api_internal_m.F90:68-74; to = 0 is "no match"
         const long long f = span_backward64(sp, buf, len, last);
         if (f > 0) { from = f; to = last < len ? last : len; }
+    }
+    if (lit_len > 0 && from > 0) {
+        // a pattern with a prefix literal: Forgex only tries the literal's occurrences.  The winner of "every boundary"
+        // is Forgex's winner iff it begins with the literal's own bytes; otherwise (an overlong encoding) decline.
+        bool same = from - 1 + lit_len <= len;
+        for (int k = 0; k < lit_len && same; k++) same = __ldg(buf + from - 1 + k) == __ldg(lit + k);
+        if (!same) { *declined = 1; return; }
     }
     from_to[0] = from; from_to[1] = to;
     *done = 1;
