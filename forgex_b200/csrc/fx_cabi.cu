@@ -46,7 +46,7 @@ struct DeviceTables {
     uint16_t* sp_table = nullptr; uint16_t* sp_direct = nullptr;
     uint8_t* sp_classmap = nullptr; uint8_t* sp_endinfo = nullptr;
     uint16_t* r_delta = nullptr; int32_t* r_cuts = nullptr; uint8_t* r_page = nullptr; uint8_t* r_mixed = nullptr;
-    uint16_t* sm_reach = nullptr; uint16_t* sm_img = nullptr;
+    uint16_t* sm_reach = nullptr; uint16_t* sm_img = nullptr; uint8_t* sm_sync = nullptr;
     uint16_t* ctab4 = nullptr; uint8_t* cmap4 = nullptr;       // compact ASCII-columns table of a big boolean automaton (K1c)
     uint64_t* nfa_trans = nullptr; uint64_t* nfa_q0 = nullptr; int32_t* nfa_cuts = nullptr;     // NFA engine (patterns past the state cap)
     uint8_t* w_work = nullptr; size_t w_work_cap = 0;
@@ -89,6 +89,7 @@ struct fx_pattern {
     // long-buffer state-map scan (K5): reachable live states of the span forward automaton and, per byte value, the
     // image of ALL of them under that byte (count, then up to SM_M states; 0xFFFF = wider)
     std::vector<uint16_t> sm_reach, sm_img;
+    uint8_t sm_sync[256];        // synchronising bytes (see StateMapParams::sync)
     bool statemap = false;
     int last_statemap = 0;       // 1: the last fx_regex_buffer* call was answered by the state-map scan
     // K1c: the ASCII columns of a big boolean table (at most 4 byte classes among the ASCII bytes): nstates x 4 words
@@ -329,6 +330,8 @@ int ensure_device(fx_pattern* p) {
         CUDA_TRY(cudaMemcpy(d.sm_reach, p->sm_reach.data(), p->sm_reach.size() * 2, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMalloc(&d.sm_img, p->sm_img.size() * 2 + 16));
         CUDA_TRY(cudaMemcpy(d.sm_img, p->sm_img.data(), p->sm_img.size() * 2, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&d.sm_sync, 256));
+        CUDA_TRY(cudaMemcpy(d.sm_sync, p->sm_sync, 256, cudaMemcpyHostToDevice));
     }
     CUDA_TRY(cudaMalloc(&d.w_best, 64));
     CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
@@ -1031,7 +1034,7 @@ int launch_scan(fx_pattern* p, const uint8_t* buf, const ScanWindow& W, unsigned
         long long groups = ((W.start_hi - W.start_lo) >> 12) + 1;
         long long want = (groups + 7) / 8, cap = (long long)p->dev.sm_count * 8;
         int grid = (int)(want < cap ? want : cap);
-        k_buffer_literal<<<grid < 1 ? 1 : grid, 256, 0, s>>>(pl.kp, sp, buf, W, best);
+        k_buffer_literal<<<grid < 1 ? 1 : grid, 256, 0, s>>>(pl.kp.lits, pl.kp.all_len, sp, buf, W, best);
         g_launches++;
         return cuda_status(cudaGetLastError());
     }
@@ -1082,7 +1085,7 @@ template <int FK>
 int launch_statemap_t(fx_pattern* p, const SpanParams& sp, StateMapParams mp, int fwd_bytes, const uint8_t* buf, int64_t len,
                       cudaStream_t s, const unsigned long long* run_if) {
     auto kern = k_statemap_regions<FK>;
-    const size_t smem = (size_t)((256 + fwd_bytes + 15) & ~15) + 256 * (1 + SM_M) * 2 + SM_WARPS * 32 * sizeof(SubMap) + SM_WARPS * 32 * 2 + 64;
+    const size_t smem = (size_t)((256 + fwd_bytes + 15) & ~15) + 256 * (1 + SM_M) * 2 + 256 + SM_WARPS * 32 * sizeof(SubMap) + SM_WARPS * 32 * 2 + 64;
     int bps = 0;
     int rc = occupancy_grid(kern, SM_WARPS * 32, smem, p->dev.sm_count, bps);
     if (rc) return rc;
@@ -1114,7 +1117,7 @@ int launch_statemap(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* fro
     SpanParams sp;
     fill_span_params(p, sp);
     StateMapParams mp;
-    mp.reach = p->dev.sm_reach; mp.img = p->dev.sm_img; mp.nreach = (int)p->sm_reach.size();
+    mp.reach = p->dev.sm_reach; mp.img = p->dev.sm_img; mp.sync = p->dev.sm_sync; mp.nreach = (int)p->sm_reach.size();
     uint8_t* maps = reinterpret_cast<uint8_t*>(work) + WORK_HEAD;
     const int64_t cap = statemap_max_regions(len);
     mp.rc = reinterpret_cast<uint16_t*>(maps);
@@ -1155,7 +1158,23 @@ int launch_buffer(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* from_
         Plan pl;
         int rc = make_plan(p, pl);
         if (rc) return rc;
-        k_buffer_sequential<<<1, 1, 0, s>>>(pl.kp, buf, len, from_to);
+        // parallel presence sweeps for the two literals first: "prefix somewhere, suffix nowhere" is an immediate no-match
+        const fx::Literals& L = p->prog.lit;
+        const bool quick = pl.kp.suf_active && pl.kp.pre_active && len >= 1 && L.prefix.find('\0') == std::string::npos &&
+                           L.suffix.find('\0') == std::string::npos;
+        if (quick) {
+            CUDA_TRY(cudaMemsetAsync(work + 16, 0xFF, 16, s));
+            long long groups = (len >> 12) + 1, want = (groups + 7) / 8, cap = (long long)p->dev.sm_count * 8;
+            const int grid = (int)(want < cap ? want : cap);
+            SparseParams sp;
+            memset(&sp, 0, sizeof(sp));
+            sp.add_lo[0] = (unsigned char)L.prefix[0] * 0x01010101u;
+            k_buffer_literal<<<grid, 256, 0, s>>>(pl.kp.lits + pl.kp.all_len, pl.kp.pre_len, sp, buf, W, work + 16);
+            sp.add_lo[0] = (unsigned char)L.suffix[0] * 0x01010101u;
+            k_buffer_literal<<<grid, 256, 0, s>>>(pl.kp.lits + pl.kp.all_len + pl.kp.pre_len, pl.kp.suf_len, sp, buf, W, work + 17);
+            g_launches += 2;
+        }
+        k_buffer_sequential<<<1, 1, 0, s>>>(pl.kp, buf, len, from_to, quick ? work + 16 : nullptr, quick ? work + 17 : nullptr);
         g_launches++;
         return cuda_status(cudaGetLastError());
     }
@@ -1304,6 +1323,24 @@ static int finish_compile(fx_pattern* p, const CompileSource& src, int op, fx_pa
             p->sm_img[(size_t)b * (1 + SM_M)] = im.size() <= (size_t)SM_M ? (uint16_t)im.size() : (uint16_t)0xFFFF;
             for (size_t k = 0; k < im.size() && k < (size_t)SM_M; k++) p->sm_img[(size_t)b * (1 + SM_M) + 1 + k] = (uint16_t)im[k];
         }
+        // synchronising bytes: after c and ANY one more byte at most one live state is left, whatever state read c
+        memset(p->sm_sync, 0, 256);
+        for (int c = 0; c < 256; c++) {
+            const uint16_t n = p->sm_img[(size_t)c * (1 + SM_M)];
+            if (n == 0 || n > SM_M) continue;
+            bool ok = true;
+            for (int d2 = 0; d2 < 256 && ok; d2++) {
+                int live = -1;
+                for (int k = 0; k < (int)n && ok; k++) {
+                    const int u = p->sm_img[(size_t)c * (1 + SM_M) + 1 + (size_t)k];
+                    const int v = st.direct[(size_t)u * 256 + (size_t)d2] & fx::W_SSTATE;
+                    if (v == 0) continue;
+                    if (live >= 0 && live != v) ok = false;
+                    live = v;
+                }
+            }
+            p->sm_sync[c] = ok ? 1 : 0;
+        }
         p->statemap = true;
     }
     if (p->prog.status == fx::OK && op == FX_OP_REGEX && !p->prog.literal_only) {
@@ -1411,7 +1448,7 @@ int fx_pattern_free(fx_pattern* p) {
         cudaFree(d.a_table); cudaFree(d.a_classmap); cudaFree(d.a_flags);
         cudaFree(d.sp_table); cudaFree(d.sp_direct); cudaFree(d.sp_classmap); cudaFree(d.sp_endinfo);
         cudaFree(d.r_delta); cudaFree(d.r_cuts); cudaFree(d.r_page); cudaFree(d.r_mixed);
-        cudaFree(d.sm_reach); cudaFree(d.sm_img); cudaFree(d.w_work);
+        cudaFree(d.sm_reach); cudaFree(d.sm_img); cudaFree(d.sm_sync); cudaFree(d.w_work);
         cudaFree(d.nfa_trans); cudaFree(d.nfa_q0); cudaFree(d.nfa_cuts); cudaFree(d.ctab4); cudaFree(d.cmap4);
         cudaFree(d.w_buf); cudaFree(d.w_off); cudaFree(d.w_out); cudaFree(d.w_span); cudaFree(d.w_best);
     }

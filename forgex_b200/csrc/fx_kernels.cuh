@@ -2700,9 +2700,13 @@ static constexpr int SM_SUB = 512;               // bytes per lane and segment
 static constexpr int SM_M = 4;                   // candidates per sub-chunk
 static constexpr int SM_LOOKBACK = 64;           // bytes in front of a region over which every reachable state is walked
 static constexpr int SM_WARPS = 16;
+static constexpr int SM_SCAN = 256;              // how far behind its nominal start a sub-chunk looks for a synchronising byte (<= SM_SUB)
 struct StateMapParams {
     const uint16_t* reach;      // reachable live states of the forward automaton
     const uint16_t* img;        // 256 x (1 + SM_M): count (0xFFFF = more than SM_M) then the live image states of the byte
+    const uint8_t* sync;        // 256: 1 = a SYNCHRONISING byte: whatever state reads it and then any one more byte ends up
+                                //      in at most one live state, so a walk that starts right behind it is a single
+                                //      trajectory within a byte or two (C4: every line end)
     int nreach;
     int64_t region_bytes;       // multiple of 32 * SM_SUB
     int64_t nregions;
@@ -2725,6 +2729,7 @@ struct StateMapParams {
 
 // a lane's map for one sub-chunk, as it sits in shared memory
 struct SubMap {
+    long long b, e;             // the sub-chunk's bytes [b, e)
     uint16_t cand[SM_M];
     uint16_t end[SM_M];
     int32_t last;               // position relative to the sub-chunk's first byte (may be -2..SM_SUB), INT32_MIN = none
@@ -2759,15 +2764,31 @@ __global__ void __launch_bounds__(SM_WARPS * 32, 2) k_statemap_regions(SpanParam
     const int head = (256 + fwd_bytes + 15) & ~15;
     uint16_t* s_img = reinterpret_cast<uint16_t*>(smem + head);                          // 256 x 5 x u16
     for (int i = threadIdx.x; i < 256 * (1 + SM_M); i += blockDim.x) s_img[i] = __ldg(mp.img + i);
-    SubMap* s_maps = reinterpret_cast<SubMap*>(smem + head + 256 * (1 + SM_M) * 2) + warp * 32;
-    uint16_t* s_rc = reinterpret_cast<uint16_t*>(smem + head + 256 * (1 + SM_M) * 2 + SM_WARPS * 32 * sizeof(SubMap)) + warp * 32;
+    uint8_t* s_sync = smem + head + 256 * (1 + SM_M) * 2;
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) reinterpret_cast<uint32_t*>(s_sync)[i] = __ldg(reinterpret_cast<const uint32_t*>(mp.sync) + i);
+    SubMap* s_maps = reinterpret_cast<SubMap*>(smem + head + 256 * (1 + SM_M) * 2 + 256) + warp * 32;
+    uint16_t* s_rc = reinterpret_cast<uint16_t*>(smem + head + 256 * (1 + SM_M) * 2 + 256 + SM_WARPS * 32 * sizeof(SubMap)) + warp * 32;
     __syncthreads();
     const uintptr_t gbuf = reinterpret_cast<uintptr_t>(buf);
-    const int64_t shift = (int64_t)(gbuf & 15);          // sub-chunk k covers text [k * SUB - shift, (k+1) * SUB - shift): 16-byte aligned ADDRESSES
+    const int64_t shift = (int64_t)(gbuf & 15);          // nominal start of sub-chunk k: text index k * SUB - shift (a 16-byte aligned ADDRESS)
+    // Where sub-chunk k really starts: right behind the first synchronising byte at or after its nominal start's
+    // predecessor (within SM_SCAN bytes), else at the nominal start.  Every lane computes the same function of the text,
+    // so neighbours agree on their common boundary without talking.
+    auto bnd = [&](int64_t k) -> int64_t {
+        if (k <= 0) return 0;
+        const int64_t nom = k * SM_SUB - shift;
+        if (nom >= len) return len;
+        int64_t lim = nom - 1 + SM_SCAN;
+        if (lim > len) lim = len;
+        for (int64_t q = nom - 1; q < lim; q++) if (s_sync[__ldg(buf + q)]) return q + 1;
+        return nom;
+    };
+    const int64_t spr = mp.region_bytes / SM_SUB;         // sub-chunks per region
     const int64_t gwarp = (int64_t)blockIdx.x * SM_WARPS + warp, nwarps = (int64_t)gridDim.x * SM_WARPS;
     for (int64_t reg = gwarp; reg < mp.nregions; reg += nwarps) {
-        const int64_t r0 = reg == 0 ? 0 : reg * mp.region_bytes - shift;
-        int64_t r1 = (reg + 1) * mp.region_bytes - shift;
+        const int64_t kr0 = reg * spr, kr1 = (reg + 1) * spr;
+        const int64_t r0 = bnd(kr0);
+        int64_t r1 = bnd(kr1);
         if (r1 > len) r1 = len;
         // ---- region candidates: every reachable state walked over the look-back window, distinct survivors ----
         int cnt = 0;
@@ -2800,15 +2821,15 @@ __global__ void __launch_bounds__(SM_WARPS * 32, 2) k_statemap_regions(SpanParam
         uint32_t c = mycand;                                 // this lane's chain state
         long long L = -1;                                    // its last accept
         // ---- segments of 32 sub-chunks ----
-        for (int64_t seg = r0; seg < r1; ) {
-            // sub-chunk bounds: the first of the text is short by `shift` bytes so that the others start on 16-byte addresses
-            const int64_t k0 = (seg + shift) / SM_SUB;                       // index of the segment's first sub-chunk
+        for (int64_t k0 = kr0; k0 < kr1; k0 += 32) {
             const int64_t kb = k0 + lane;
-            int64_t b = kb * SM_SUB - shift, e = b + SM_SUB;
-            if (b < seg) b = seg;
-            if (e > r1) e = r1;
-            const int64_t seg_end = (k0 + 32) * SM_SUB - shift < r1 ? (k0 + 32) * SM_SUB - shift : r1;
+            int64_t b = kb < kr1 ? bnd(kb) : r1;
+            if (b > r1) b = r1;
+            int64_t e = __shfl_down_sync(FULL, b, 1);
+            if (lane == 31) { e = kb + 1 < kr1 ? bnd(kb + 1) : r1; if (e > r1) e = r1; }
+            if (__ballot_sync(FULL, b < e) == 0) break;              // behind the end of the text
             SubMap mine;
+            mine.b = b; mine.e = e;
             mine.ncand = 0; mine.last = INT32_MIN; mine.owner_mask = 0; mine.pad = 0;
 #pragma unroll
             for (int k = 0; k < SM_M; k++) { mine.cand[k] = 0; mine.end[k] = 0; }
@@ -2961,12 +2982,9 @@ __global__ void __launch_bounds__(SM_WARPS * 32, 2) k_statemap_regions(SpanParam
             s_maps[lane] = mine;
             __syncwarp();
             // ---- chain the 32 maps in text order; every lane carries its own chain state ----
-            const int nsub = (int)((seg_end - (k0 * SM_SUB - shift) + SM_SUB - 1) / SM_SUB);
-            for (int t = 0; t < nsub && t < 32; t++) {
+            for (int t = 0; t < 32; t++) {
                 const SubMap m = s_maps[t];
-                int64_t tb = (k0 + t) * SM_SUB - shift, te = tb + SM_SUB;
-                if (tb < seg) tb = seg;
-                if (te > r1) te = r1;
+                const int64_t tb = m.b, te = m.e;
                 if (tb >= te) continue;
                 bool need = false;
                 if (c != 0) {
@@ -2985,7 +3003,6 @@ __global__ void __launch_bounds__(SM_WARPS * 32, 2) k_statemap_regions(SpanParam
                 }
             }
             __syncwarp();
-            seg = seg_end;
         }
         mp.rc[reg * 32 + lane] = lane < cnt ? (uint16_t)mycand : (uint16_t)0xFFFFu;
         mp.re[reg * 32 + lane] = (uint16_t)c;
@@ -3185,12 +3202,10 @@ __global__ void k_buffer_all_take(const int64_t* __restrict__ from_to, int64_t* 
 // above for the literal's first byte; a hit compares the whole literal; the smallest occurrence wins (64-bit atomicMin,
 // key = S position of its first byte, so that the keys of several windows combine with MIN like any other start).
 // An occurrence that would run past an open window end cannot be decided here: counted in best[1].
-__global__ void __launch_bounds__(256) k_buffer_literal(KParams p, SparseParams sp, const uint8_t* __restrict__ buf, ScanWindow W,
-                                                        unsigned long long* __restrict__ best) {
+__global__ void __launch_bounds__(256) k_buffer_literal(const uint8_t* __restrict__ lit, int n, SparseParams sp, const uint8_t* __restrict__ buf,
+                                                        ScanWindow W, unsigned long long* __restrict__ best) {
     const int lane = threadIdx.x & 31;
     const uint32_t FULL = 0xffffffffu;
-    const uint8_t* lit = p.lits;
-    const int n = p.all_len;
     const int64_t len = W.len;
     const bool open_end = !W.last;
     const uintptr_t gbuf = reinterpret_cast<uintptr_t>(buf);
@@ -3241,7 +3256,12 @@ __global__ void __launch_bounds__(256) k_buffer_literal(KParams p, SparseParams 
 // (utility_m.f90:58-117, api_internal_m.F90:76-164) -- a sequential rule.  One thread replays it exactly as the batch
 // kernels do for a string (eval_regex): always right, never fast (tens of MB/s); the parallel scans above serve every
 // other pattern.
-__global__ void k_buffer_sequential(KParams p, const uint8_t* __restrict__ buf, int64_t len, int64_t* __restrict__ from_to) {
+__global__ void k_buffer_sequential(KParams p, const uint8_t* __restrict__ buf, int64_t len, int64_t* __restrict__ from_to,
+                                    const unsigned long long* __restrict__ pre_key, const unsigned long long* __restrict__ suf_key) {
+    // Two parallel sweeps have looked for the prefix and the suffix literal (k_buffer_literal).  The prefix occurs and the
+    // suffix occurs nowhere: the reference finds its first candidate, then index(text, suffix, back=.true.) == 0 ends the
+    // search (api_internal_m.F90:94-102) -- no match, without walking anything (`a.*b` over a text without `b`).
+    if (pre_key != nullptr && *pre_key != NO_START && *suf_key == NO_START) { from_to[0] = 0; from_to[1] = 0; return; }
     Table<3> T;
     T.g_table = p.ctable; T.g_cmap = p.classmap; T.shift = p.c_row_shift; T.s_table = 0; T.s_cmap = 0;
     int64_t f, t;

@@ -446,7 +446,31 @@ class StateMapScan:
         for b in range(256):
             im = sorted(set(int(v) for v in st[self.reach, b]) - {0})
             self.img.append(im if len(im) <= self.M else None)
+        # synchronising bytes: after c and any one more byte at most one live state is left (sub-chunks start behind them)
+        self.sync = []
+        for b in range(256):
+            im = self.img[b]
+            ok = im is not None and len(im) >= 1
+            if ok:
+                for d in range(256):
+                    if len(set(int(st[s, d]) for s in im) - {0}) > 1:
+                        ok = False
+                        break
+            self.sync.append(ok)
+        self.scan = max(1, sub // 2)
         self.stats = {"unknown": 0, "complex": 0, "rewalk": 0, "wide_regions": 0}
+
+    def bnd(self, text, k):
+        """where sub-chunk k starts: right behind the first synchronising byte near its nominal start k * sub"""
+        if k <= 0:
+            return 0
+        nom = k * self.sub
+        if nom >= len(text):
+            return len(text)
+        for q in range(nom - 1, min(len(text), nom - 1 + self.scan)):
+            if self.sync[text[q]]:
+                return q + 1
+        return nom
 
     def step(self, s, b):
         return int(self.direct[s, b]) & W_SSTATE
@@ -537,9 +561,10 @@ class StateMapScan:
                 self.stats["wide_regions"] += 1
                 return None
         chain = [(c, None) for c in rc]
-        b = r0
-        while b < r1:
-            e = min(b + self.sub, r1)
+        for k in range(self._k0, self._k1):
+            b, e = min(self.bnd(text, k), r1), min(self.bnd(text, k + 1), r1)
+            if b >= e:
+                continue
             m = self.sub_map(text, b, e)
             for i, (c, last) in enumerate(chain):
                 if c == 0:
@@ -551,7 +576,6 @@ class StateMapScan:
                     assert m is None, "the candidate set must hold every state that can arrive here"
                     self.stats["rewalk"] += 1
                     chain[i] = self.walk(text, b, e, c, last)
-            b = e
         return {c: chain[i] for i, c in enumerate(rc)}
 
     def last(self, text: bytes):
@@ -559,16 +583,18 @@ class StateMapScan:
         n = len(text)
         s = int(self.sl.t["start"])
         last = 0 if self.sl.t["start_acc"] else -1
-        r0 = 0
-        while r0 < n and s != 0:
-            r1 = min(n, r0 + self.region)
+        spr = max(1, self.region // self.sub)          # sub-chunks per region
+        reg = 0
+        while s != 0 and reg * spr * self.sub < max(n, 1):
+            self._k0, self._k1 = reg * spr, (reg + 1) * spr
+            r0, r1 = self.bnd(text, self._k0), min(n, self.bnd(text, self._k1))
             m = self.region_map(text, r0, r1)
             if m is None or s not in m:
                 return None
             s, l = m[s]
             if l is not None:
                 last = l
-            r0 = r1
+            reg += 1
         return self.sl.end_of_text(s, n, last)
 
 
