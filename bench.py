@@ -54,13 +54,17 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def known_traffic(cfg):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if one exists"""
+def known_traffic(cfg, algo_bytes):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json) -- only when
+    that capture was taken on a workload of the same size as this run's (same algorithmic bytes, within 2 %)"""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            return json.load(fh).get(cfg)
+            e = json.load(fh).get(cfg)
+        if isinstance(e, dict) and abs(e["algorithmic_bytes"] - algo_bytes) <= 0.02 * algo_bytes:
+            return int(e["bytes"])
     except Exception:
-        return None
+        pass
+    return None
 
 
 class ClockSampler:
@@ -580,7 +584,7 @@ def measure_config(cfg, args, env):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": known_traffic(cfg), "peak_source": peak_src,
+                         "traffic": known_traffic(cfg, algo_bytes), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": kernel_ms},
             "e2e": e2e,
         }

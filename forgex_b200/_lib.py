@@ -12,7 +12,7 @@ SO = os.path.join(HERE, "libforgex_b200.so")
 FX_OP_MATCH, FX_OP_IN, FX_OP_REGEX = 0, 1, 2
 FX_TABLE_AUTO, FX_TABLE_SMEM, FX_TABLE_GLOBAL = 0, 1, 2
 FX_ERR_TREE_NODE_LIMIT, FX_ERR_DFA_STATE_CAP, FX_ERR_PREFILTER_UNSUPPORTED = 101, 102, 103
-FX_ERR_BAD_ARGUMENT, FX_ERR_NO_DEVICE = 104, 105
+FX_ERR_BAD_ARGUMENT, FX_ERR_NO_DEVICE, FX_ERR_WORK_BUDGET = 104, 105, 106
 
 # every symbol include/forgex_b200.h declares (tests check that the library exports them all)
 SYMBOLS = [

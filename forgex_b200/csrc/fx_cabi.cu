@@ -384,6 +384,7 @@ int make_plan(fx_pattern* p, Plan& pl) {
     k.a_start_nul = p->has_anchored ? p->anchored.bt.start_nul : 0;
     k.a_q0 = p->has_anchored ? p->anchored.bt.q0 : 0;
     k.prefix_mode = p->prefix_mode;
+    k.steps_left = nullptr;
     p->last_residency = pl.kind == 3 ? FX_TABLE_GLOBAL : FX_TABLE_SMEM;
     p->last_direct = pl.kind <= 1 ? 1 : 0;
     return FX_OK;
@@ -964,7 +965,7 @@ int launch_scan_sparse_t(fx_pattern* p, const Plan& pl, const SparseParams& sp, 
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
     budget.flags = env_int("FX_K4_FLAGS", 0);
-    kern<<<grid, 256, smem, s>>>(pl.kp, sp, buf, W, best, table_smem, gate, env_int("FX_K4_PHASES", 3), run_if, budget);
+    kern<<<grid, 256, smem, s>>>(pl.kp, sp, buf, W, best, table_smem, gate, env_int("FX_K4_PHASES", 3) | (env_int("FX_K4_LOAD", 1) << 4), run_if, budget);
     g_launches++;
     return cuda_status(cudaGetLastError());
 }
@@ -1056,12 +1057,13 @@ int launch_scan(fx_pattern* p, const uint8_t* buf, const ScanWindow& W, unsigned
 
 int launch_finish(fx_pattern* p, const uint8_t* buf, const ScanWindow& W, const unsigned long long* best,
                   int64_t* from_to, int whole_text, cudaStream_t s, const unsigned long long* done = nullptr,
-                  const unsigned long long* use_alt = nullptr, const unsigned long long* best_alt = nullptr) {
+                  const unsigned long long* use_alt = nullptr, const unsigned long long* best_alt = nullptr,
+                  const unsigned long long* spent = nullptr) {
     if (p->prog.nfa_engine) return FX_ERR_DFA_STATE_CAP;
     Plan pl;
     int rc = make_plan(p, pl);
     if (rc) return rc;
-    k_buffer_finish<<<1, 1, 0, s>>>(pl.kp, buf, W, best, from_to, whole_text, done, use_alt, best_alt);
+    k_buffer_finish<<<1, 1, 0, s>>>(pl.kp, buf, W, best, from_to, whole_text, done, use_alt, best_alt, spent);
     g_launches++;
     return cuda_status(cudaGetLastError());
 }
@@ -1219,15 +1221,21 @@ int launch_buffer(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* from_
         p->last_statemap = k4_first ? 2 : 1;
         return launch_finish(p, buf, W, best, from_to, 1, s, work + 8, work + 9, work + 12);
     }
+    // What is left: patterns without the span path (a cap was passed), and prefix literals that are not provably neutral.
+    // The candidate scan still runs under the work budget; without a linear-time stand-in a spent budget is reported as
+    // (-2, -2) = FX_ERR_WORK_BUDGET instead of occupying the GPU with the reference's quadratic loop.
+    ScanBudget bg{work + 5, work + 4, (unsigned long long)len * 16ull + (4ull << 20), 0};
+    const bool budgeted = env_int("FX_STATEMAP", 1) != 0;
+    if (!budgeted) bg = ScanBudget{nullptr, nullptr, 0ull, 0};
     if (len >= 1) {
-        int rc = launch_scan(p, buf, W, best, s, SCAN_AUTO);
+        int rc = launch_scan(p, buf, W, best, s, SCAN_AUTO, nullptr, nullptr, bg);
         if (rc) return rc;
         if (prefixed) {          // no occurrence of the prefix anywhere: every boundary is a candidate (gated on best[2])
-            rc = launch_scan(p, buf, W, best, s, SCAN_ALL, best + 2);
+            rc = launch_scan(p, buf, W, best, s, SCAN_ALL, best + 2, nullptr, bg);
             if (rc) return rc;
         }
     }
-    return launch_finish(p, buf, W, best, from_to, 1, s);
+    return launch_finish(p, buf, W, best, from_to, 1, s, nullptr, nullptr, nullptr, budgeted ? work + 4 : nullptr);
 }
 
 template <typename T>
@@ -1677,12 +1685,12 @@ int fx_regex_buffer_all_dev(fx_pattern* p, const uint8_t* d_buf, int64_t len, in
     memset(&sp, 0, sizeof(sp));
     const bool local = p->prog.has_span && env_int("FX_ALL_LOCAL", 1);
     if (local) fill_span_params(p, sp);
-    int64_t host_state[4] = {0, 0, 0, 0};
+    int64_t host_state[5] = {0, 0, 0, 0, 0};
     for (;;) {
         if (local) {
             k_buffer_all_local<<<1, 1, 0, s>>>(pl.kp, sp, d_buf, len, state, d_from, d_to, capacity, 1024, (int64_t)env_int("FX_ALL_REACH", 1 << 16));
             g_launches++;
-            CUDA_TRY(cudaMemcpyAsync(host_state, state, 32, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaMemcpyAsync(host_state, state, 40, cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaStreamSynchronize(s));
             if (host_state[2]) break;
             if (!host_state[3]) continue;                   // a thousand near matches taken: go on
@@ -1691,11 +1699,12 @@ int fx_regex_buffer_all_dev(fx_pattern* p, const uint8_t* d_buf, int64_t len, in
         if ((rc = launch_buffer(p, d_buf + pos, len - pos, ft, work, s))) return rc;
         k_buffer_all_take<<<1, 1, 0, s>>>(ft, state, d_from, d_to, capacity);
         g_launches++;
-        CUDA_TRY(cudaMemcpyAsync(host_state, state, 32, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(host_state, state, 40, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         if (host_state[2]) break;
     }
     *count = host_state[1];
+    if (host_state[4]) return FX_ERR_WORK_BUDGET;
     return FX_OK;
 }
 
@@ -1838,6 +1847,7 @@ int fx_regex_buffer(fx_pattern* p, const uint8_t* buf, int64_t len, int64_t* fro
     int64_t ft[2] = {0, 0};
     CUDA_TRY(cudaMemcpyAsync(ft, d.w_span, 16, cudaMemcpyDeviceToHost, 0));
     CUDA_TRY(cudaStreamSynchronize(0));
+    if (ft[0] == -2 && ft[1] == -2) return FX_ERR_WORK_BUDGET;
     if (from) *from = ft[0];
     if (to) *to = ft[1];
     return FX_OK;

@@ -842,6 +842,7 @@ const char* status_message(int code) {  // error_m.F90:41-211
         case ERR_PREFILTER_UNSUPPORTED: return "forgex_b200: this pattern's literal prefilter is not result-neutral; not supported yet.";
         case ERR_BAD_ARGUMENT: return "forgex_b200: bad argument.";
         case ERR_NO_DEVICE: return "forgex_b200: no CUDA device / CUDA failure.";
+        case ERR_WORK_BUDGET: return "forgex_b200: buffer search stopped; Forgex's candidate loop is super-linear on this text.";
         default: return "ERROR: Fatal error is happened.";
     }
 }

@@ -48,6 +48,7 @@ enum Status : int {
     ERR_PREFILTER_UNSUPPORTED = 103,  // literal prefilter of this pattern is not provably result-neutral
     ERR_BAD_ARGUMENT = 104,
     ERR_NO_DEVICE = 105,
+    ERR_WORK_BUDGET = 106,
 };
 
 const char* status_message(int code);

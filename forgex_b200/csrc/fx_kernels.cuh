@@ -43,6 +43,7 @@ struct KParams {
     // the class-compressed table in global memory, whatever `table` points to (slow paths, finish kernel)
     const uint16_t* ctable;
     int c_row_shift;
+    long long* steps_left;    // nullptr except in k_buffer_sequential (work budget of the single-thread replay)
 };
 
 // ---- small PTX helpers ---------------------------------------------------------------------
@@ -65,6 +66,21 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {  // streaming 16-byte load, no L1 allocation
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+// The sweep load of K4 under a choice of cache policies (FX_K4_LOAD): 0 = no L1 allocation (the K2c choice), 1 = plain
+// read-only load, allocating in L1 (K4's default), 2 = L1 evict_last, 3 = no L1 allocation + L2 evict_last, 4 = no L1
+// allocation + 256-byte L2 prefetch.  Measured on C4 (profiles/r02_prof_c4_sweep_load_policy.txt): under policy 0 the
+// unit phase's re-read of a candidate unit, microseconds after the sweep read it, MISSES L2 and goes to DRAM at 64-byte
+// granularity -- 3.55 GB of DRAM reads for 2.15 GB of text; policies 1-3 bring that to 2.34 GB and the search from
+// 3.43 to 3.27 ms per 8 GiB.
+__device__ __forceinline__ uint4 ldg_v4_policy(const void* p, int lp, unsigned long long pol) {
+    uint4 r;
+    if (lp == 1) asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else if (lp == 2) asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else if (lp == 3) asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    else if (lp == 4) asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
 __device__ __forceinline__ uint2 ldg_nc_v2(const void* p) {
@@ -170,7 +186,9 @@ struct FetchShared {
 struct Anchored {
     const uint8_t* flags;
     int start_nul, q0;
+    long long* steps_left = nullptr;   // single-thread replay over a long buffer: byte steps it may still take (see k_buffer_sequential)
 };
+static constexpr int64_t OUT_OF_BUDGET = -3;     // an attempt that ran out of steps (never a legal `last`)
 
 // One anchored attempt starting with `st` before text index `pos`.  `last` is -1 or the number of
 // text bytes consumed at the last accepting boundary (len+1 = the trailing NUL was consumed too).
@@ -184,6 +202,7 @@ __device__ __forceinline__ int64_t run_attempt(const Anchored& A, const TBL& T, 
     bool inter = false;
     if ((w & W_STATE) == 0) return last;
     for (int64_t j = pos; j <= len; j++) {
+        if (A.steps_left != nullptr && --(*A.steps_left) < 0) return OUT_OF_BUDGET;
         const uint32_t b = j < len ? fetch(j) : 0u;     // virtual trailing NUL at j == len
         if (inter && (b & 0xC0) != 0x80) {              // sequence broken: pending bytes replay as U+FFFF
             const uint32_t f = __ldg(A.flags + (w & W_STATE));
@@ -279,6 +298,7 @@ __device__ __forceinline__ void brute_force_flat(const Anchored& A, const TBL& T
         w = (uint32_t)A.q0;
     }
     while (true) {
+        if (A.steps_left != nullptr && --(*A.steps_left) < 0) { from = -2; to = -2; return; }
         const uint32_t b = j < len ? fetch(j) : 0u;     // virtual trailing NUL at j == len
         if (inter && (b & 0xC0) != 0x80) {              // sequence broken: pending bytes replay as U+FFFF
             const uint32_t f = __ldg(A.flags + (w & W_STATE));
@@ -510,6 +530,7 @@ __device__ inline void including_exact(const Anchored& A, const TBL& T, FETCH fe
     while (start < m) {
         if (text_suf != NONE && text_suf < start) return;
         const int64_t last = attempt_at(A, T, fetch, len, start);
+        if (last == OUT_OF_BUDGET) { from = -2; to = -2; return; }
         if (last >= 0) {
             from = start - 1 < 1 ? 1 : start - 1;
             to = last < len ? last : len;      // max_match >= len(str) -> len(string), else max_match - 2
@@ -553,9 +574,11 @@ __device__ inline void eval_regex(const KParams& p, const TBL& T, FETCH fetch, i
     }
     if (len == 0 || (len == 1 && fetch(0) == 0x20)) return;      // api_internal_m.F90:68-74 -> '' / 0 / 0
     Anchored A{p.flags, p.start_nul, p.q0};
+    A.steps_left = p.steps_left;
     int64_t f, t;
     including_exact(A, T, fetch, len, p.lits + p.all_len, p.pre_len, p.pre_active != 0,
                     p.lits + p.all_len + p.pre_len, p.suf_len, p.suf_active != 0, f, t);
+    if (f == -2) { from = -2; to = -2; return; }                 // out of work budget (k_buffer_sequential only)
     if (f > 0 && t > 0) { from = f; to = t; }                    // forgex.F90:332-343
 }
 
@@ -2632,6 +2655,9 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
 
     const int64_t gwarp = (int64_t)blockIdx.x * 8 + warp, nwarps = (int64_t)gridDim.x * 8;
     int sweep_iter = 0;
+    const int lp = (phases >> 4) & 7;
+    unsigned long long l2pol = 0;
+    if (lp == 3) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(l2pol));
     for (int64_t g0 = gwarp * 128; g0 < nunits; g0 += nwarps * 128) {
         unsigned long long cur = 0;
         if (lane == 0) cur = *reinterpret_cast<volatile unsigned long long*>(best);
@@ -2648,8 +2674,8 @@ __global__ void __launch_bounds__(256) k_buffer_scan_sparse(KParams p, SparsePar
             const int64_t u = g0 + k * 32 + lane;
             va[k] = make_uint4(0, 0, 0, 0); vb[k] = va[k];
             if (u < nunits) {
-                va[k] = ldg_nc_v4(reinterpret_cast<const void*>(ubase + ((uintptr_t)u << 5)));
-                vb[k] = ldg_nc_v4(reinterpret_cast<const void*>(ubase + ((uintptr_t)u << 5) + 16));
+                va[k] = ldg_v4_policy(reinterpret_cast<const void*>(ubase + ((uintptr_t)u << 5)), lp, l2pol);
+                vb[k] = ldg_v4_policy(reinterpret_cast<const void*>(ubase + ((uintptr_t)u << 5) + 16), lp, l2pol);
             }
         }
 #pragma unroll
@@ -3191,6 +3217,7 @@ __global__ void k_buffer_all_local(KParams p, SpanParams sp, const uint8_t* __re
 __global__ void k_buffer_all_take(const int64_t* __restrict__ from_to, int64_t* __restrict__ state, int64_t* __restrict__ out_from,
                                   int64_t* __restrict__ out_to, int64_t capacity) {
     const int64_t f = from_to[0], t = from_to[1];
+    if (f == -2) { state[2] = 1; state[4] = 1; return; }    // the search ran out of its work budget
     if (f <= 0 || t <= 0) { state[2] = 1; return; }
     const int64_t pos = state[0], cnt = state[1];
     if (cnt < capacity) { out_from[cnt] = pos + f; out_to[cnt] = pos + t; }
@@ -3262,6 +3289,11 @@ __global__ void k_buffer_sequential(KParams p, const uint8_t* __restrict__ buf, 
     // suffix occurs nowhere: the reference finds its first candidate, then index(text, suffix, back=.true.) == 0 ends the
     // search (api_internal_m.F90:94-102) -- no match, without walking anything (`a.*b` over a text without `b`).
     if (pre_key != nullptr && *pre_key != NO_START && *suf_key == NO_START) { from_to[0] = 0; from_to[1] = 0; return; }
+    // The reference's loop is quadratic when candidates are many and attempts long (`aa.*[xy]` over a megabyte of `a`), and
+    // for a sequential candidate list there is no linear-time stand-in: the replay stops after 16 byte steps per text byte
+    // and reports (-2, -2) = FX_ERR_WORK_BUDGET instead of occupying the GPU for hours.
+    long long steps = (long long)len * 16 + (4ll << 20);
+    p.steps_left = &steps;
     Table<3> T;
     T.g_table = p.ctable; T.g_cmap = p.classmap; T.shift = p.c_row_shift; T.s_table = 0; T.s_cmap = 0;
     int64_t f, t;
@@ -3275,8 +3307,9 @@ __global__ void k_buffer_sequential(KParams p, const uint8_t* __restrict__ buf, 
 __global__ void k_buffer_finish(KParams p, const uint8_t* __restrict__ buf, ScanWindow W,
                                 const unsigned long long* __restrict__ best, int64_t* __restrict__ from_to, int whole_text,
                                 const unsigned long long* __restrict__ done, const unsigned long long* __restrict__ use_alt,
-                                const unsigned long long* __restrict__ best_alt) {
+                                const unsigned long long* __restrict__ best_alt, const unsigned long long* __restrict__ spent) {
     if (done != nullptr && *done != 0) return;              // the state-map scan has answered
+    if (spent != nullptr && *spent != 0) { from_to[0] = -2; from_to[1] = -2; return; }   // a budgeted scan without a stand-in gave up
     if (use_alt != nullptr && *use_alt != 0) best = best_alt;   // the budgeted scan gave up and the state-map scan declined: the re-run's result
     Table<3> T;
     T.g_table = p.ctable; T.g_cmap = p.classmap; T.shift = p.c_row_shift; T.s_table = 0; T.s_cmap = 0;

@@ -66,7 +66,12 @@ enum {
                                           (src/essential/utility_m.f90:58-117).  fx_regex_buffer* itself answers such
                                           patterns (one thread replays the reference's rule: exact, slow) */
     FX_ERR_BAD_ARGUMENT = 104,
-    FX_ERR_NO_DEVICE = 105
+    FX_ERR_NO_DEVICE = 105,
+    FX_ERR_WORK_BUDGET = 106           /* fx_regex_buffer* only: Forgex's own loop would need more than 16 byte steps per text
+                                          byte on this text (many candidate starts, each running long) and the pattern has
+                                          no linear-time stand-in (a sequential candidate list, or a prefix literal that is
+                                          not provably a prefix of every match).  The reference would grind through it; the
+                                          library stops instead.  The _dev forms report it as (from, to) = (-2, -2). */
 };
 
 typedef struct fx_pattern_info {

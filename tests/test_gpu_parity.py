@@ -844,3 +844,39 @@ def test_prefix_literal_patterns_under_the_budget_and_the_statemap_scan(monkeypa
             for mode in ("2", "1"):
                 monkeypatch.setenv("FX_STATEMAP", mode)
                 assert q.regex_buffer(arr) == exp, (pat, text[:40], len(text), mode)
+
+
+def test_work_budget_is_an_error_where_no_linear_stand_in_exists():
+    """Patterns whose candidate list must be replayed in order (a bordered prefix literal such as `aa`, or a suffix
+    literal) and patterns whose prefix literal is not provably neutral (a non-ASCII prefix) have no linear-time
+    stand-in.  Forgex's loop is quadratic on `aa.*[xy]` over a run of `a`: the reference would grind for hours; the
+    library stops after 16 byte steps per text byte and says so -- FX_ERR_WORK_BUDGET from the host forms, (-2, -2) from the
+    _dev forms -- instead of holding the GPU.  Ordinary texts are untouched (parity with the oracle below)."""
+    import time
+    import torch
+    from forgex_b200 import _lib as L
+    n = 1 << 20
+    cases = [(b"aa.*[xy]", b"a" * n, 0), ("é.*[xy]".encode(), "é".encode() * (n // 2), 1),
+             (b"ab[^c]*cd", b"ab" * (n // 2) + b"ccd", 0)]
+    for pat, text, scan in cases:
+        p = fx.Pattern(pat, "regex")
+        assert p.info()["prefix_scan"] == scan, pat
+        arr = np.frombuffer(text, dtype=np.uint8)
+        t0 = time.perf_counter()
+        with pytest.raises(fx.ForgexError) as e:
+            p.regex_buffer(arr)
+        assert e.value.status == L.FX_ERR_WORK_BUDGET, pat
+        assert time.perf_counter() - t0 < 20.0, pat
+        with pytest.raises(fx.ForgexError) as e:
+            p.regex_buffer_all(arr, capacity=4)
+        assert e.value.status == L.FX_ERR_WORK_BUDGET, pat
+        dev = torch.from_numpy(arr.copy()).cuda()
+        ft = torch.zeros(2, dtype=torch.int64, device="cuda")
+        work = torch.zeros(p.buffer_work_bytes(len(text)), dtype=torch.uint8, device="cuda")
+        p.regex_buffer_dev(dev, len(text), ft, work)
+        assert tuple(ft.cpu().tolist()) == (-2, -2), pat
+        # the same handle right afterwards, on texts within the budget
+        c = O.Compiled(pat, 0)
+        for small in (text[:3000] + b"x", text[:2001], b"zz " + text[:40] + b" y cd", b"", b" "):
+            s = np.frombuffer(b"#" + small, dtype=np.uint8)[1:]
+            assert p.regex_buffer(s) == c.regex_buffer(np.ascontiguousarray(s)), (pat, small[:20])

@@ -22,7 +22,10 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_membar_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio']
+        'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
+        'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'lts__t_sectors_srcunit_tex_op_read.sum',
+        'lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum', 'lts__t_sectors_srcunit_tex_op_read_lookup_hit.sum',
+        'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_hit.sum']
 
 
 def main():

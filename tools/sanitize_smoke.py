@@ -46,9 +46,11 @@ def round2():
     strings = [b"y" * 9000, b"", b" ", "あい ab".encode() * 3, b"\xe3\x81"] + [bytes(b3[o3[i]:o3[i + 1]]) for i in range(60)]
     bb, oo = pack(strings)
     for pat in [synth.PATTERNS["c3"], b"[a-z]+r", rb"\s\S+$"]:
+        print("span batch", pat, flush=True)
         f, t = fx.Pattern(pat, "regex").regex_batch(bb, oo)
         total += int(f.sum()) + int(t.sum())
         total += int(fx.Pattern(pat, "regex").regex_count_batch(bb, oo).sum())
+    print("compact table", flush=True)
     fb, n, stride = synth.gen_c5(300)
     fb = fb.copy()
     fb[70] = 0xC3
@@ -56,6 +58,7 @@ def round2():
         total += int(fx.Pattern(synth.PATTERNS["c5"], "in", residency=res).in_fixed(fb, n, stride).sum())
     text = synth.gen_c4(60001, 0.7)
     for mode in ("1", "2"):
+        print("buffer paths, FX_STATEMAP", mode, flush=True)
         os.environ["FX_STATEMAP"] = mode
         total += sum(fx.Pattern(synth.PATTERNS["c4"], "regex").regex_buffer(text[1:]))
         total += sum(fx.Pattern(rb"\w+@\w+", "regex").regex_buffer(text))
@@ -67,6 +70,7 @@ def round2():
     total += sum(fx.Pattern(b"a.*b", "regex").regex_buffer(np.frombuffer(b"a" * 30000, dtype=np.uint8)))
     f, t, cnt = fx.Pattern(b"[A-Z]+", "regex").regex_buffer_all(text, capacity=64)
     total += cnt + int(f.sum())
+    print("NFA engine", flush=True)
     os.environ["FX_STATE_CAP"] = "3"
     small, so = pack([b"foobar", b"xx foobaz", b"", b" ", "あい".encode(), b"\xff\xc3"])
     for op in ("in", "match", "regex"):
