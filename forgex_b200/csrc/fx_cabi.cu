@@ -815,16 +815,16 @@ void fill_span_params(fx_pattern* p, SpanParams& sp) {
     sp.nmixed = (int)(rv.mixed.size() / 64);
 }
 
-template <int FK, bool RS>
-int launch_span_t(fx_pattern* p, const Plan& pl, const SpanParams& sp, int fwd_bytes, const uint8_t* buf,
+template <int FK, bool RS, int WARPS>
+int launch_span_w(fx_pattern* p, const Plan& pl, const SpanParams& sp, int fwd_bytes, const uint8_t* buf,
                   const int64_t* off, int64_t n, int64_t total, int64_t* from, int64_t* to, cudaStream_t s) {
-    auto kern = k_span_ragged<FK, RS>;
-    // one CTA of SPAN_WARPS warps per SM; every warp stages its own tiles: the tables take their share of the SM's
+    auto kern = k_span_ragged<FK, RS, WARPS>;
+    // one CTA of WARPS warps per SM; every warp stages its own tiles: the tables take their share of the SM's
     // shared memory once, the rest is divided among the warps
     int64_t avg = n > 0 ? (total + n - 1) / n : 1;
     if (avg < 1) avg = 1;
     const SpanHead H = span_head(fwd_bytes, sp.rstates * sp.rclasses * 2, sp.nmixed, RS);
-    int per_warp = ((227 * 1024 - 1024 - H.bytes) / SPAN_WARPS) & ~127;
+    int per_warp = ((227 * 1024 - 1024 - H.bytes) / WARPS) & ~127;
     if (per_warp < 1024) return FX_ERR_BAD_ARGUMENT;
     int cap = per_warp, spt = 1;
     for (;;) {
@@ -837,17 +837,27 @@ int launch_span_t(fx_pattern* p, const Plan& pl, const SpanParams& sp, int fwd_b
     if (spt > 512) spt = 512;
     while (spt > 1 && span_layout(spt, cap).warp_bytes > per_warp) spt--;
     const int64_t ntiles = (n + spt - 1) / spt;
-    const size_t smem = (size_t)H.bytes + (size_t)SPAN_WARPS * (size_t)span_layout(spt, cap).warp_bytes;
+    const size_t smem = (size_t)H.bytes + (size_t)WARPS * (size_t)span_layout(spt, cap).warp_bytes;
     int bps = 0;
-    int rc = occupancy_grid(kern, SPAN_WARPS * 32, smem, p->dev.sm_count, bps);
+    int rc = occupancy_grid(kern, WARPS * 32, smem, p->dev.sm_count, bps);
     if (rc) return rc;
     long long capg = (long long)p->dev.sm_count * bps;
-    long long want = (ntiles + SPAN_WARPS - 1) / SPAN_WARPS;
+    long long want = (ntiles + WARPS - 1) / WARPS;
     int grid = (int)(want < capg ? want : capg);
     if (grid < 1) grid = 1;
-    kern<<<grid, SPAN_WARPS * 32, smem, s>>>(pl.kp, sp, buf, off, n, total, from, to, spt, cap, ntiles, fwd_bytes);
+    int round_bytes = env_int("FX_SPAN_ROUND", SPAN_ROUND) & ~3;
+    if (round_bytes < 4) round_bytes = 4;
+    kern<<<grid, WARPS * 32, smem, s>>>(pl.kp, sp, buf, off, n, total, from, to, spt, cap, ntiles, fwd_bytes, round_bytes);
     g_launches++;
     return cuda_status(cudaGetLastError());
+}
+
+template <int FK, bool RS>
+int launch_span_t(fx_pattern* p, const Plan& pl, const SpanParams& sp, int fwd_bytes, const uint8_t* buf,
+                  const int64_t* off, int64_t n, int64_t total, int64_t* from, int64_t* to, cudaStream_t s) {
+    // (experiment, FX_SPAN_WARPS=24: fewer warps, larger tiles per warp)
+    if (env_int("FX_SPAN_WARPS", SPAN_WARPS) == 24) return launch_span_w<FK, RS, 24>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
+    return launch_span_w<FK, RS, SPAN_WARPS>(p, pl, sp, fwd_bytes, buf, off, n, total, from, to, s);
 }
 
 // K3f, streaming form: every warp owns a ring of RING_NB small buffers and never waits for a tile to finish

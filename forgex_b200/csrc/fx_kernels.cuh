@@ -1723,6 +1723,21 @@ struct SpanRev {
         (st) = nw_ & W_SSTATE;                                                    \
     }
 
+// The books of four transition words that have already been looked up (the deferred-flag loops: four lookups, one OR
+// test).  A step's event ASSIGNS `last` (an accept: the position behind the byte; a replay mark: 1..3 bytes before
+// that), so of the four steps only the last one that holds an event counts -- picked with selects, no second walk.
+// (On C3 some lane of a warp sees an event in nearly every word -- seven accepts in a row per \w{2,8} -- so this runs
+// almost every iteration: it has to be short.)
+#define FX_SPAN_BOOKS4(n1, n2, n3, n4, last, jj)                                  \
+    {                                                                             \
+        uint32_t ev_ = (n1);                                                      \
+        int k_ = 1;                                                               \
+        if ((n2) & 0xB000u) { ev_ = (n2); k_ = 2; }                               \
+        if ((n3) & 0xB000u) { ev_ = (n3); k_ = 3; }                               \
+        if ((n4) & 0xB000u) { ev_ = (n4); k_ = 4; }                               \
+        if (ev_ & 0xB000u) (last) = (jj) + k_ - ((ev_ & W_ACC) ? 0 : (int)((ev_ >> 12) & 3u)); \
+    }
+
 // what the end of the text does in state st (the pending bytes of an unfinished sequence replay as U+FFFF; the
 // trailing NUL is consumed but is not a start)
 __device__ __forceinline__ int span_end_of_text(const SpanParams& sp, uint32_t st, int len, int last) {
@@ -1792,16 +1807,19 @@ __device__ __noinline__ void span_linear(const SpanParams& sp, const SpanFwd<FK>
 
 // shared memory of K3f: classmap 256 | forward table | reverse tables (delta, page 1024, mixed) | pad to 128 |
 //   SPAN_WARPS warp regions of `warp_bytes`:
-//   [0,16) mbarrier | offsets (spt+4) x int32 | results spt x int2 | queue spt x uint32 | pad to 128 | tile (cap + 64)
+//   [0,16) mbarrier | offsets (spt+4) x int32 | results spt x int2 | queue spt x uint32 | claim order spt x uint16 |
+//   32 bucket counters | pad to 128 | tile (cap + 64)
 // Every warp stages its own tiles (its own TMA bulk copy on its own mbarrier): no block-wide step after the tables are
 // staged.  One CTA of 32 warps per SM: one copy of the tables, the rest of the shared memory is tile space.
 static constexpr int SPAN_WARPS = 32;
-struct SpanLayout { int off_res, off_queue, off_tile, warp_bytes; };
+struct SpanLayout { int off_res, off_queue, off_perm, off_hist, off_tile, warp_bytes; };
 __host__ __device__ __forceinline__ SpanLayout span_layout(int spt, int cap) {
     SpanLayout L;
     L.off_res = (16 + (spt + 4) * 4 + 7) & ~7;          // int2 entries
     L.off_queue = L.off_res + spt * 8;
-    L.off_tile = (L.off_queue + spt * 4 + 127) & ~127;
+    L.off_perm = L.off_queue + spt * 4;
+    L.off_hist = (L.off_perm + spt * 2 + 3) & ~3;
+    L.off_tile = (L.off_hist + 128 + 127) & ~127;
     L.warp_bytes = (L.off_tile + cap + 64 + 127) & ~127;
     return L;
 }
@@ -1814,13 +1832,13 @@ __host__ __device__ __forceinline__ SpanHead span_head(int fwd_bytes, int rdelta
     H.bytes = (H.off_mixed + (rs ? nmixed * 64 : 0) + 127) & ~127;
     return H;
 }
-static constexpr int SPAN_ROUND = 32;            // bytes a lane walks before the warp looks for idle lanes again
+static constexpr int SPAN_ROUND = 64;            // bytes a lane walks before the warp looks for idle lanes again (C3: 16 -> 701, 32 -> 777, 64 -> 816 GB/s)
 
-template <int FK, bool RS>
-__global__ void __launch_bounds__(SPAN_WARPS * 32, 1) k_span_ragged(KParams p, SpanParams sp, const uint8_t* __restrict__ buf,
+template <int FK, bool RS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_span_ragged(KParams p, SpanParams sp, const uint8_t* __restrict__ buf,
                                                                    const int64_t* __restrict__ offsets, int64_t n, int64_t total,
                                                                    int64_t* __restrict__ from, int64_t* __restrict__ to,
-                                                                   int spt, int cap, int64_t ntiles, int fwd_bytes) {
+                                                                   int spt, int cap, int64_t ntiles, int fwd_bytes, int round_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t FULL = 0xffffffffu;
@@ -1855,6 +1873,8 @@ __global__ void __launch_bounds__(SPAN_WARPS * 32, 1) k_span_ragged(KParams p, S
     int32_t* s_off = reinterpret_cast<int32_t*>(region + 16);
     int2* s_res = reinterpret_cast<int2*>(region + L.off_res);
     uint32_t* s_queue = reinterpret_cast<uint32_t*>(region + L.off_queue);
+    uint16_t* s_perm = reinterpret_cast<uint16_t*>(region + L.off_perm);
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(region + L.off_hist);
     uint8_t* tile = region + L.off_tile;
     const uint32_t mbar = smem_u32(region);
     if (lane == 0) mbar_init(mbar, 1);
@@ -1862,8 +1882,8 @@ __global__ void __launch_bounds__(SPAN_WARPS * 32, 1) k_span_ragged(KParams p, S
     uint32_t phase = 0;
     const uint32_t tile_addr = smem_u32(tile);
     const uintptr_t gbuf = reinterpret_cast<uintptr_t>(buf);
-    const int64_t nwarps = (int64_t)gridDim.x * SPAN_WARPS;
-    for (int64_t t = (int64_t)blockIdx.x * SPAN_WARPS + warp; t < ntiles; t += nwarps) {
+    const int64_t nwarps = (int64_t)gridDim.x * WARPS;
+    for (int64_t t = (int64_t)blockIdx.x * WARPS + warp; t < ntiles; t += nwarps) {
         // ---- stage the tile: strings [first, first + count), up to `cap` bytes of them ----
         const int64_t first = t * spt;
         const int count = (int)((n - first) < spt ? (n - first) : spt);
@@ -1887,6 +1907,33 @@ __global__ void __launch_bounds__(SPAN_WARPS * 32, 1) k_span_ragged(KParams p, S
             const int64_t o = __ldg(offsets + first + i);
             s_off[i] = o > t1 ? OFF_BEYOND : (int32_t)(o - base);
         }
+        // ---- claim order: the longest strings first (counting sort over 8-byte length buckets; also while the copy is in
+        // flight).  A tile gives a lane one or two strings; claimed in text order, the warp then waits for whichever lane
+        // drew a long string last -- with the long ones out first the short ones fill the gaps (46 % -> 58 % busy lanes
+        // on C3 at 45 strings per tile).  The results do not depend on the order.
+        const bool ordered = count > 32;
+        if (ordered) {
+            s_hist[lane] = 0;
+            __syncwarp();
+            for (int i = lane; i < count; i += 32) {
+                const int32_t r0 = s_off[i], r1 = s_off[i + 1];
+                const int b = r1 == OFF_BEYOND ? 0 : 31 - (((r1 - r0) >> 3) < 31 ? ((r1 - r0) >> 3) : 31);   // bucket 0 = longest
+                atomicAdd(s_hist + b, 1u);
+            }
+            __syncwarp();
+            const uint32_t h = s_hist[lane];
+            uint32_t x = h;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(FULL, x, d); if (lane >= d) x += y; }
+            __syncwarp();
+            s_hist[lane] = x - h;
+            __syncwarp();
+            for (int i = lane; i < count; i += 32) {
+                const int32_t r0 = s_off[i], r1 = s_off[i + 1];
+                const int b = r1 == OFF_BEYOND ? 0 : 31 - (((r1 - r0) >> 3) < 31 ? ((r1 - r0) >> 3) : 31);
+                s_perm[atomicAdd(s_hist + b, 1u)] = (uint16_t)i;
+            }
+        }
         if (bulk) { mbar_wait(mbar, phase); phase ^= 1; }
         __syncwarp();
         // ---- forward walks.  The lanes are a pool of walkers: a lane that has no string claims the tile's next one;
@@ -1901,7 +1948,7 @@ __global__ void __launch_bounds__(SPAN_WARPS * 32, 1) k_span_ragged(KParams p, S
             if (idle) {
                 const int mine = next + __popc(idle & ((1u << lane) - 1));
                 if (!have && mine < count) {
-                    sidx = mine;
+                    sidx = ordered ? (int)s_perm[mine] : mine;
                     const int32_t r0 = s_off[sidx], r1 = s_off[sidx + 1];
                     if (r1 == OFF_BEYOND) {      // not staged (longer than a warp's tile): the same two walks, text from global memory
                         const int64_t o0 = __ldg(offsets + first + sidx), o1 = __ldg(offsets + first + sidx + 1);
@@ -1929,7 +1976,7 @@ __global__ void __launch_bounds__(SPAN_WARPS * 32, 1) k_span_ragged(KParams p, S
             }
             if (!__any_sync(FULL, have)) { if (next >= count) break; else continue; }
             if (have) {
-                int jend = (int)(((a + (uint32_t)j + SPAN_ROUND) & ~3u) - a);     // the round ends on a word boundary of the tile
+                int jend = (int)(((a + (uint32_t)j + (uint32_t)round_bytes) & ~3u) - a);     // the round ends on a word boundary of the tile
                 if (jend > len) jend = len;
                 while (j < jend && ((a + (uint32_t)j) & 3u)) { const uint32_t b = lds_u8(a + j); FX_SPAN_STEP(T, st, last, b, j); j++; }
                 for (; j + 4 <= jend && st != 0; j += 4) {
@@ -1941,11 +1988,9 @@ __global__ void __launch_bounds__(SPAN_WARPS * 32, 1) k_span_ragged(KParams p, S
                     const uint32_t n3 = T.next(n2 & W_SSTATE, (w4 >> 16) & 0xFFu);
                     const uint32_t n4 = T.next(n3 & W_SSTATE, w4 >> 24);
                     if ((n1 | n2 | n3 | n4) & 0xB000u) {
-                        FX_SPAN_STEP(T, st, last, w4 & 0xFFu, j);
-                        FX_SPAN_STEP(T, st, last, (w4 >> 8) & 0xFFu, j + 1);
-                        FX_SPAN_STEP(T, st, last, (w4 >> 16) & 0xFFu, j + 2);
-                        FX_SPAN_STEP(T, st, last, w4 >> 24, j + 3);
-                    } else st = n4 & W_SSTATE;
+                        FX_SPAN_BOOKS4(n1, n2, n3, n4, last, j);
+                    }
+                    st = n4 & W_SSTATE;
                 }
                 if (st != 0) for (; j < jend; j++) { const uint32_t b = lds_u8(a + j); FX_SPAN_STEP(T, st, last, b, j); }
                 if (st == 0 || j >= len) {                          // this walk is over
@@ -2206,11 +2251,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_span_stream(KParams p, SpanPa
                 const uint32_t n3 = T.next(n2 & W_SSTATE, (w4 >> 16) & 0xFFu);
                 const uint32_t n4 = T.next(n3 & W_SSTATE, w4 >> 24);
                 if ((n1 | n2 | n3 | n4) & 0xB000u) {
-                    FX_SPAN_STEP(T, st, last, w4 & 0xFFu, j);
-                    FX_SPAN_STEP(T, st, last, (w4 >> 8) & 0xFFu, j + 1);
-                    FX_SPAN_STEP(T, st, last, (w4 >> 16) & 0xFFu, j + 2);
-                    FX_SPAN_STEP(T, st, last, w4 >> 24, j + 3);
-                } else st = n4 & W_SSTATE;
+                    FX_SPAN_BOOKS4(n1, n2, n3, n4, last, j);
+                }
+                st = n4 & W_SSTATE;
             }
             if (st != 0) for (; j < jend; j++) { const uint32_t bb = lds_u8(f_a + j); FX_SPAN_STEP(T, st, last, bb, j); }
             if (st == 0 || j >= f_len) {
@@ -2974,11 +3017,9 @@ __global__ void __launch_bounds__(SM_WARPS * 32, 2) k_statemap_regions(SpanParam
                                 const uint32_t n4 = T.next(n3 & W_SSTATE, w4[q] >> 24);
                                 if ((n1 | n2 | n3 | n4) & 0xB000u) {
                                     const long long jj = j + 4 * q;
-                                    FX_SM_STEP(T, cur, l2, w4[q] & 0xFFu, jj);
-                                    FX_SM_STEP(T, cur, l2, (w4[q] >> 8) & 0xFFu, jj + 1);
-                                    FX_SM_STEP(T, cur, l2, (w4[q] >> 16) & 0xFFu, jj + 2);
-                                    FX_SM_STEP(T, cur, l2, w4[q] >> 24, jj + 3);
-                                } else cur = n4 & W_SSTATE;
+                                    FX_SPAN_BOOKS4(n1, n2, n3, n4, l2, jj);
+                                }
+                                cur = n4 & W_SSTATE;
                             }
                             j += 16;
                         }
@@ -3045,16 +3086,32 @@ __global__ void __launch_bounds__(32) k_statemap_compose(SpanParams sp, StateMap
     uint32_t s = (uint32_t)sp.start;
     long long L = sp.start_acc ? 0 : -1;
     int status = 0;
-    for (int64_t r = 0; r < mp.nregions && s != 0; r++) {
-        const uint32_t key = mp.rc[r * 32 + lane];
-        const uint32_t end = mp.re[r * 32 + lane];
-        const long long l = mp.rl[r * 32 + lane];
-        const uint32_t m = __ballot_sync(FULL, key == s);
-        if (m == 0) { status = 1; break; }                    // the region declined (or does not know s): no answer from this scan
-        const int src = __ffs(m) - 1;
-        s = __shfl_sync(FULL, end, src);
-        const long long ll = __shfl_sync(FULL, l, src);
-        if (ll >= 0) L = ll;
+    // The chain itself is serial, its loads are not: 16 regions' maps are fetched at once (a region's map is three
+    // coalesced loads; one at a time the ~19 000 regions of a large text cost 0.7 us of load latency each -- 13 ms).
+    constexpr int CB = 16;
+    for (int64_t r0 = 0; r0 < mp.nregions && s != 0 && status == 0; r0 += CB) {
+        uint32_t key[CB], end[CB];
+        long long l[CB];
+#pragma unroll
+        for (int k = 0; k < CB; k++) {
+            const int64_t r = r0 + k < mp.nregions ? r0 + k : mp.nregions - 1;
+            key[k] = mp.rc[r * 32 + lane];
+            end[k] = mp.re[r * 32 + lane];
+            l[k] = mp.rl[r * 32 + lane];
+        }
+#pragma unroll
+        for (int k = 0; k < CB; k++) {
+            if (r0 + k < mp.nregions && s != 0 && status == 0) {
+                const uint32_t m = __ballot_sync(FULL, key[k] == s);
+                if (m == 0) status = 1;                       // the region declined (or does not know s): no answer from this scan
+                else {
+                    const int src = __ffs(m) - 1;
+                    s = __shfl_sync(FULL, end[k], src);
+                    const long long ll = __shfl_sync(FULL, l[k], src);
+                    if (ll >= 0) L = ll;
+                }
+            }
+        }
     }
     if (status == 0 && s != 0) {                              // end of the text: pending bytes replay, the trailing NUL is consumed
         const uint32_t e = __ldg(sp.endinfo + s);
