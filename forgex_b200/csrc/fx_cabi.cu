@@ -1117,7 +1117,7 @@ int launch_statemap_t(fx_pattern* p, const SpanParams& sp, StateMapParams mp, in
     g_launches++;
     rc = cuda_status(cudaGetLastError());
     if (rc) return rc;
-    k_statemap_compose<<<1, 32, 0, s>>>(sp, mp, len, run_if);
+    k_statemap_compose<<<1, 1024, 0, s>>>(sp, mp, len, run_if);
     g_launches++;
     return cuda_status(cudaGetLastError());
 }

@@ -2849,8 +2849,29 @@ __global__ void __launch_bounds__(SM_WARPS * 32, 2) k_statemap_regions(SpanParam
         if (nom >= len) return len;
         int64_t lim = nom - 1 + SM_SCAN;
         if (lim > len) lim = len;
-        for (int64_t q = nom - 1; q < lim; q++) if (s_sync[__ldg(buf + q)]) return q + 1;
+        // (same answer as the byte loop `for q = nom - 1 .. lim - 1: if sync[text[q]] return q + 1`, 16 bytes per load:
+        //  byte by byte this search was a chain of dependent L1 hits, a fifth of a lane's time on C4)
+        int64_t q = nom - 1;
+        if (s_sync[__ldg(buf + q)]) return q + 1;
+        q = nom;                                              // a 16-byte aligned address from here on
+        for (; q + 16 <= lim; q += 16) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(gbuf + (uintptr_t)q));
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+            uint32_t m = 0;
+#pragma unroll
+            for (int i = 0; i < 16; i++) m |= (uint32_t)s_sync[(w4[i >> 2] >> (8 * (i & 3))) & 0xFFu] << i;
+            if (m) return q + __ffs(m);
+        }
+        for (; q < lim; q++) if (s_sync[__ldg(buf + q)]) return q + 1;
         return nom;
+    };
+    // bytes [lo, hi) of one 16-byte block, from registers
+    auto walk_block = [&](const uint4& v, int lo, int hi, uint32_t& cur, long long& l2, int64_t base) {
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if (i >= lo && i < hi) { const uint32_t byte = (w4[i >> 2] >> (8 * (i & 3))) & 0xFFu; FX_SM_STEP(T, cur, l2, byte, base + i); }
+        }
     };
     const int64_t spr = mp.region_bytes / SM_SUB;         // sub-chunks per region
     const int64_t gwarp = (int64_t)blockIdx.x * SM_WARPS + warp, nwarps = (int64_t)gridDim.x * SM_WARPS;
@@ -3005,25 +3026,44 @@ __global__ void __launch_bounds__(SM_WARPS * 32, 2) k_statemap_regions(SpanParam
                         const int k1 = __ffs(active) - 1;
                         uint32_t cur = k1 == 0 ? st[0] : k1 == 1 ? st[1] : k1 == 2 ? st[2] : st[3];
                         long long l2 = -1;
-                        while (j < e && cur != 0 && ((gbuf + (uintptr_t)j) & 15) != 0) { const uint32_t byte = __ldg(buf + j); FX_SM_STEP(T, cur, l2, byte, j); j++; }
-                        while (cur != 0 && j + 16 <= e) {
-                            const uint4 v = __ldg(reinterpret_cast<const uint4*>(gbuf + (uintptr_t)j));
-                            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                const uint32_t n1 = T.next(cur, w4[q] & 0xFFu);
-                                const uint32_t n2 = T.next(n1 & W_SSTATE, (w4[q] >> 8) & 0xFFu);
-                                const uint32_t n3 = T.next(n2 & W_SSTATE, (w4[q] >> 16) & 0xFFu);
-                                const uint32_t n4 = T.next(n3 & W_SSTATE, w4[q] >> 24);
-                                if ((n1 | n2 | n3 | n4) & 0xB000u) {
-                                    const long long jj = j + 4 * q;
-                                    FX_SPAN_BOOKS4(n1, n2, n3, n4, l2, jj);
-                                }
-                                cur = n4 & W_SSTATE;
-                            }
-                            j += 16;
+                        // (whole aligned 16-byte blocks are loaded even where only part of one belongs to the sub-chunk:
+                        //  a block that holds one byte of the text lies inside the text's allocation)
+                        if ((gbuf + (uintptr_t)j) & 15) {                        // head: up to the next 16-byte boundary
+                            const int lo = (int)((gbuf + (uintptr_t)j) & 15);
+                            const int hi = e - j < 16 - lo ? lo + (int)(e - j) : 16;
+                            const uint4 v = __ldg(reinterpret_cast<const uint4*>((gbuf + (uintptr_t)j) & ~(uintptr_t)15));
+                            walk_block(v, lo, hi, cur, l2, j - lo);
+                            j += hi - lo;
                         }
-                        while (j < e && cur != 0) { const uint32_t byte = __ldg(buf + j); FX_SM_STEP(T, cur, l2, byte, j); j++; }
+                        if (cur != 0 && j + 16 <= e) {                           // whole blocks, the next one in flight
+                            uint4 v = __ldg(reinterpret_cast<const uint4*>(gbuf + (uintptr_t)j));
+                            for (;;) {
+                                const bool more = j + 32 <= e;
+                                uint4 vn = make_uint4(0, 0, 0, 0);
+                                if (more) vn = __ldg(reinterpret_cast<const uint4*>(gbuf + (uintptr_t)j + 16));
+                                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                                for (int q = 0; q < 4; q++) {
+                                    const uint32_t n1 = T.next(cur, w4[q] & 0xFFu);
+                                    const uint32_t n2 = T.next(n1 & W_SSTATE, (w4[q] >> 8) & 0xFFu);
+                                    const uint32_t n3 = T.next(n2 & W_SSTATE, (w4[q] >> 16) & 0xFFu);
+                                    const uint32_t n4 = T.next(n3 & W_SSTATE, w4[q] >> 24);
+                                    if ((n1 | n2 | n3 | n4) & 0xB000u) {
+                                        const long long jj = j + 4 * q;
+                                        FX_SPAN_BOOKS4(n1, n2, n3, n4, l2, jj);
+                                    }
+                                    cur = n4 & W_SSTATE;
+                                }
+                                j += 16;
+                                if (!more || cur == 0) break;
+                                v = vn;
+                            }
+                        }
+                        if (cur != 0 && j < e) {                                 // tail: part of one more block (j is aligned here)
+                            const uint4 v = __ldg(reinterpret_cast<const uint4*>(gbuf + (uintptr_t)j));
+                            walk_block(v, 0, (int)(e - j), cur, l2, j);
+                            j = e;
+                        }
                         if (l2 >= 0) { last = l2; owner = k1; }
 #pragma unroll
                         for (int k = 0; k < SM_M; k++) if (k == k1) st[k] = cur;
@@ -3077,44 +3117,73 @@ __global__ void __launch_bounds__(SM_WARPS * 32, 2) k_statemap_regions(SpanParam
     }
 }
 
-// one warp: apply the region maps in order
-__global__ void __launch_bounds__(32) k_statemap_compose(SpanParams sp, StateMapParams mp, int64_t len,
-                                                         const unsigned long long* __restrict__ run_if) {
+// Apply the region maps in order.  The chain is a composition of (partial) maps, so it is done in two levels: each of
+// the 32 warps composes a contiguous RANGE of regions -- lane k carries the k-th candidate of the range's first region
+// through the range (a lookup among a region's 32 keys is 32 shuffles; eight regions' maps are fetched at a time) --
+// and warp 0 then chains the 32 range maps from the automaton's start state.  (One warp walking the ~19 000 regions of
+// a multi-GiB text one after the other took 13 ms, 4.2 ms with batched loads; this form takes a few hundred us.)
+__global__ void __launch_bounds__(1024) k_statemap_compose(SpanParams sp, StateMapParams mp, int64_t len,
+                                                           const unsigned long long* __restrict__ run_if) {
     if (run_if != nullptr && *run_if == 0) return;
-    const int lane = threadIdx.x;
+    __shared__ uint16_t r_key[32][32], r_end[32][32];
+    __shared__ long long r_l[32][32];
+    __shared__ uint8_t r_bad[32][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t FULL = 0xffffffffu;
-    uint32_t s = (uint32_t)sp.start;
-    long long L = sp.start_acc ? 0 : -1;
-    int status = 0;
-    // The chain itself is serial, its loads are not: 16 regions' maps are fetched at once (a region's map is three
-    // coalesced loads; one at a time the ~19 000 regions of a large text cost 0.7 us of load latency each -- 13 ms).
-    constexpr int CB = 16;
-    for (int64_t r0 = 0; r0 < mp.nregions && s != 0 && status == 0; r0 += CB) {
-        uint32_t key[CB], end[CB];
-        long long l[CB];
+    const int64_t n = mp.nregions;
+    const int64_t per = (n + 31) / 32;
+    const int64_t ra = (int64_t)warp * per < n ? (int64_t)warp * per : n;
+    const int64_t rb = ra + per < n ? ra + per : n;
+    {
+        uint32_t key0 = 0xFFFFu, cs = 0xFFFFu;            // this lane's candidate of the range's first region, its chain state
+        long long L = -1;
+        bool bad = false;
+        if (ra < rb) { key0 = mp.rc[ra * 32 + lane]; cs = key0; }
+        constexpr int CB = 8;
+        for (int64_t r0 = ra; r0 < rb; r0 += CB) {
+            uint32_t key[CB], end[CB];
+            long long l[CB];
 #pragma unroll
-        for (int k = 0; k < CB; k++) {
-            const int64_t r = r0 + k < mp.nregions ? r0 + k : mp.nregions - 1;
-            key[k] = mp.rc[r * 32 + lane];
-            end[k] = mp.re[r * 32 + lane];
-            l[k] = mp.rl[r * 32 + lane];
-        }
+            for (int k = 0; k < CB; k++) {
+                const int64_t r = r0 + k < rb ? r0 + k : rb - 1;
+                key[k] = mp.rc[r * 32 + lane];
+                end[k] = mp.re[r * 32 + lane];
+                l[k] = mp.rl[r * 32 + lane];
+            }
 #pragma unroll
-        for (int k = 0; k < CB; k++) {
-            if (r0 + k < mp.nregions && s != 0 && status == 0) {
-                const uint32_t m = __ballot_sync(FULL, key[k] == s);
-                if (m == 0) status = 1;                       // the region declined (or does not know s): no answer from this scan
-                else {
-                    const int src = __ffs(m) - 1;
-                    s = __shfl_sync(FULL, end[k], src);
-                    const long long ll = __shfl_sync(FULL, l[k], src);
-                    if (ll >= 0) L = ll;
+            for (int k = 0; k < CB; k++) {
+                if (r0 + k < rb) {                        // (warp-uniform)
+                    int hit = -1;
+                    for (int q = 0; q < 32; q++) if (__shfl_sync(FULL, key[k], q) == cs) hit = q;
+                    const uint32_t e = __shfl_sync(FULL, end[k], hit < 0 ? 0 : hit);
+                    const long long ll = __shfl_sync(FULL, l[k], hit < 0 ? 0 : hit);
+                    if (cs != 0xFFFFu && cs != 0 && !bad) {
+                        if (hit < 0) bad = true;          // the region declined, or does not know this state
+                        else { cs = e; if (ll >= 0) L = ll; }
+                    }
                 }
             }
         }
+        r_key[warp][lane] = (uint16_t)key0; r_end[warp][lane] = (uint16_t)cs; r_l[warp][lane] = L; r_bad[warp][lane] = bad ? 1 : 0;
     }
-    if (status == 0 && s != 0) {                              // end of the text: pending bytes replay, the trailing NUL is consumed
-        const uint32_t e = __ldg(sp.endinfo + s);
+    __syncthreads();
+    if (warp != 0) return;
+    uint32_t st = (uint32_t)sp.start;
+    long long L = sp.start_acc ? 0 : -1;
+    int status = 0;
+    for (int w = 0; w < 32 && st != 0 && status == 0; w++) {
+        const int64_t wa = (int64_t)w * per;
+        if (wa >= n) break;
+        const uint32_t m = __ballot_sync(FULL, (uint32_t)r_key[w][lane] == st);
+        if (m == 0) { status = 1; break; }                // no answer from this scan
+        const int src = __ffs(m) - 1;
+        if (r_bad[w][src]) { status = 1; break; }
+        st = r_end[w][src];
+        const long long ll = r_l[w][src];
+        if (ll >= 0) L = ll;
+    }
+    if (status == 0 && st != 0) {                         // end of the text: pending bytes replay, the trailing NUL is consumed
+        const uint32_t e = __ldg(sp.endinfo + st);
         if (e & 3u) L = len + 1 - (long long)(e & 3u);
         if (e & 4u) L = len + 1;
     }
