@@ -35,7 +35,7 @@ module forgex_b200_m
    integer(c_int), parameter, public :: FX_OK = 0
    integer(c_int), parameter, public :: FX_ERR_TREE_NODE_LIMIT = 101, FX_ERR_DFA_STATE_CAP = 102, &
                                         FX_ERR_PREFILTER_UNSUPPORTED = 103, FX_ERR_BAD_ARGUMENT = 104, &
-                                        FX_ERR_NO_DEVICE = 105
+                                        FX_ERR_NO_DEVICE = 105, FX_ERR_WORK_BUDGET = 106
 
    type, public :: fx_pattern_t
       type(c_ptr) :: handle = c_null_ptr
