@@ -1239,6 +1239,8 @@ __global__ void __launch_bounds__(256, MINB) k_in_sparse(KParams p, SparseParams
     const Anchored A{sp.flags, sp.start_nul, sp.q0};
     const uint32_t FULL = 0xffffffffu;
     const int nt = (int)ntiles;             // the host keeps n (hence ntiles) below 2^31
+    unsigned long long l2pol = 0;
+    if (stream_hint == 3) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(l2pol));
 
     // The warp's state machine.  The inner loop (no calls) advances it until 32 units or 32 starts are waiting or
     // the tiles are used up; the outer loop runs the queues and comes back.
@@ -1289,7 +1291,10 @@ __global__ void __launch_bounds__(256, MINB) k_in_sparse(KParams p, SparseParams
                         const int64_t u = seg + ((int64_t)(r + k) << 5) + lane;
                         va[k] = make_uint4(0, 0, 0, 0); vb[k] = va[k];
                         if (u < nunits && r + k < nrows) {
-                            if (stream_hint) {
+                            if (stream_hint >= 2) {          // experiment: policies 2.. of ldg_v4_policy (L1 / L2 evict_last, ...)
+                                va[k] = ldg_v4_policy(reinterpret_cast<const void*>(ubase + ((uintptr_t)u << 5)), stream_hint, l2pol);
+                                vb[k] = ldg_v4_policy(reinterpret_cast<const void*>(ubase + ((uintptr_t)u << 5) + 16), stream_hint, l2pol);
+                            } else if (stream_hint) {
                                 va[k] = ldg_nc_v4(reinterpret_cast<const void*>(ubase + ((uintptr_t)u << 5)));
                                 vb[k] = ldg_nc_v4(reinterpret_cast<const void*>(ubase + ((uintptr_t)u << 5) + 16));
                             } else {

@@ -21,7 +21,7 @@ for c in c1 c2 c3 c4 c5 c2_k2; do python tools/ncu_summary.py gpurun_out/r02n_pr
 rm -f gpurun_out/*.ncu-rep
 ( compute-sanitizer --tool memcheck python tools/sanitize_smoke.py round2 2>&1 | tail -6 ) > gpurun_out/r02n_sanitizer_memcheck.log
 ( compute-sanitizer --tool racecheck python tools/sanitize_smoke.py round2 2>&1 | tail -6 ) > gpurun_out/r02n_sanitizer_racecheck.log
-( compute-sanitizer --tool synccheck python tools/sanitize_smoke.py round2 2>&1 | tail -6 ) > gpurun_out/r02n_sanitizer_synccheck.log
+( compute-sanitizer --tool synccheck --num-cuda-barriers 65536 python tools/sanitize_smoke.py round2 2>&1 | tail -6 ) > gpurun_out/r02n_sanitizer_synccheck.log
 python tools/sanitize_smoke.py round2 > gpurun_out/r02n_sanitizer_native.log 2>&1
 tail -3 gpurun_out/r02n_pytest.log
 tail -2 gpurun_out/r02n_sanitizer_*.log
