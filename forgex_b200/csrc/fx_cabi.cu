@@ -512,8 +512,12 @@ int launch_fixed_v(fx_pattern* p, const Plan& pl, const uint8_t* buf, int64_t n,
     return launch_fixed_t<OP, KIND, 1>(p, pl, buf, n, stride, out, s, generic);
 }
 
+// Does every string have to go through the wrapper's literal gates (eval_bool_slow)?  For `.match.` the gates of
+// do_matching_exactly compare LENGTHS as well (api_internal_m.F90:199-233: a text equal to the prefix literal matches, a
+// text shorter than a literal does not), and those two rules hold for a literal that is blank but not empty (`' +x'`
+// has the prefix ' '), which the content compares skip: any non-empty prefix or suffix makes the pattern generic.
 inline int generic_mode(const Plan& pl, int op) {
-    return (pl.kp.all_active || (op == 0 && (pl.kp.pre_active || pl.kp.suf_active)) || (op == 1 && pl.kp.prefix_mode == 2)) ? 1 : 0;
+    return (pl.kp.all_active || (op == 0 && (pl.kp.pre_len > 0 || pl.kp.suf_len > 0)) || (op == 1 && pl.kp.prefix_mode == 2)) ? 1 : 0;
 }
 
 int launch_sparse(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int64_t* off, int64_t n, int64_t total,

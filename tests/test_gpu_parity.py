@@ -880,3 +880,25 @@ def test_work_budget_is_an_error_where_no_linear_stand_in_exists():
         for small in (text[:3000] + b"x", text[:2001], b"zz " + text[:40] + b" y cd", b"", b" "):
             s = np.frombuffer(b"#" + small, dtype=np.uint8)[1:]
             assert p.regex_buffer(s) == c.regex_buffer(np.ascontiguousarray(s)), (pat, small[:20])
+
+
+def test_match_with_a_literal_that_is_blank_but_not_empty():
+    """` +x`: the extracted prefix literal is one blank.  Fortran's `prefix /= ''` treats it as absent, but the gates
+    of do_matching_exactly also compare LENGTHS (api_internal_m.F90:199-233): a text equal to the literal matches, a text
+    shorter than it does not -- `' ' .match. ' +ab'` is true.  Such patterns must take the gated path for every string
+    (found by the extended GPU fuzz, seed 14: the fast path walked the automaton and said false)."""
+    texts = [b" ", b"", b"  ", b" ab", b"  ab.", b"ab", b" a", b"x ", b" ab ", b"ab ", b"ab  ", b"   ", b"a", b" abc.de"]
+    buf, off = pack(texts)
+    for pat in [rb" +(\w{2,3}\.?){1,}", b" +ab", b"ab +", b"  +", rb" \w+ ", b"a* ", b" a*", b" ", b"  ", b" ?", b"( |ab)"]:
+        for op in ("match", "in"):
+            p = fx.Pattern(pat, op)
+            assert p.status == 0, pat
+            o = 1 if op == "match" else 0
+            c = O.Compiled(pat, o)
+            got = p.match_batch(buf, off) if op == "match" else p.in_batch(buf, off)
+            assert np.array_equal(got, c.bool_batch(o, buf, off)), (pat, op, got.tolist())
+            for stride in (1, 2, 3):
+                fb = np.frombuffer(b" a  b ab  a   aab ba", dtype=np.uint8)
+                n = len(fb) // stride
+                gotf = p.match_fixed(fb, n, stride) if op == "match" else p.in_fixed(fb, n, stride)
+                assert np.array_equal(gotf, c.bool_fixed(o, fb, n, stride)), (pat, op, stride)
