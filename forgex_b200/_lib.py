@@ -33,7 +33,7 @@ class PatternInfo(C.Structure):
         "literal_only", "residency", "direct", "prefix_mode", "sparse", "sparse_ranges")] + [
         ("sparse_lo", C.c_int32 * 4), ("sparse_hi", C.c_int32 * 4), ("sparse_high", C.c_int32),
         ("sparse_second", C.c_int32), ("sparse_used", C.c_int32), ("prefix_scan", C.c_int32), ("statemap", C.c_int32),
-        ("nfa_engine", C.c_int32), ("compact_used", C.c_int32), ("statemap_used", C.c_int32)]
+        ("nfa_engine", C.c_int32), ("compact_used", C.c_int32), ("statemap_used", C.c_int32), ("gated", C.c_int32)]
 
 
 _lib = None

@@ -515,9 +515,11 @@ int launch_fixed_v(fx_pattern* p, const Plan& pl, const uint8_t* buf, int64_t n,
 // Does every string have to go through the wrapper's literal gates (eval_bool_slow)?  For `.match.` the gates of
 // do_matching_exactly compare LENGTHS as well (api_internal_m.F90:199-233: a text equal to the prefix literal matches, a
 // text shorter than a literal does not), and those two rules hold for a literal that is blank but not empty (`' +x'`
-// has the prefix ' '), which the content compares skip: any non-empty prefix or suffix makes the pattern generic.
-inline int generic_mode(const Plan& pl, int op) {
-    return (pl.kp.all_active || (op == 0 && (pl.kp.pre_len > 0 || pl.kp.suf_len > 0)) || (op == 1 && pl.kp.prefix_mode == 2)) ? 1 : 0;
+// has the prefix ' '), which the content compares skip: any non-empty prefix or suffix makes the pattern gated.
+// (fx_pattern_info.gated reports this decision; tests/test_host_tables.py checks it against the oracle.)
+inline int gated_mode(const fx_pattern* p, int op) {
+    const fx::Literals& L = p->prog.lit;
+    return (p->prog.literal_only || (op == 0 && (!L.prefix.empty() || !L.suffix.empty())) || (op == 1 && p->prefix_mode == 2)) ? 1 : 0;
 }
 
 int launch_sparse(fx_pattern* p, const Plan& pl, const uint8_t* buf, const int64_t* off, int64_t n, int64_t total,
@@ -531,7 +533,7 @@ int launch_fixed(fx_pattern* p, const uint8_t* buf, int64_t n, int64_t stride, u
     Plan pl;
     int rc = make_plan(p, pl);
     if (rc) return rc;
-    int generic = generic_mode(pl, OP);
+    int generic = gated_mode(p, OP);
     p->last_sparse = 0;
     p->last_compact = 0;
     if (OP == 1 && !generic && p->sparse && stride > 0 && n < (1ll << 31) && env_int("FX_SPARSE", 1)) {   // sparse starts (K2c)
@@ -767,7 +769,7 @@ int launch_ragged(fx_pattern* p, const uint8_t* buf, const int64_t* off, int64_t
     Plan pl;
     int rc = make_plan(p, pl);
     if (rc) return rc;
-    int generic = generic_mode(pl, OP);
+    int generic = gated_mode(p, OP);
     p->last_sparse = 0;
     if (OP == 1 && !generic && p->sparse && n < (1ll << 31) && env_int("FX_SPARSE", 1)) {      // sparse starts (K2c)
         p->last_sparse = 1;
@@ -1513,6 +1515,7 @@ int fx_pattern_get_info(const fx_pattern* p, fx_pattern_info* info) {
     info->compact_used = p->last_compact;
     info->statemap = p->statemap ? 1 : 0;
     info->statemap_used = p->last_statemap;
+    info->gated = g.op == FX_OP_REGEX || g.nfa_engine ? 0 : gated_mode(p, g.op);
     return FX_OK;
 }
 

@@ -120,6 +120,11 @@ typedef struct fx_pattern_info {
     int32_t statemap_used;    /* last fx_regex_buffer* call: 0 candidate-start scan only; 1 state-map scan; 2 candidate-start
                                  scan under a work budget with the state-map scan behind it (which of the two answered is
                                  decided on the device) */
+    int32_t gated;            /* FX_OP_MATCH / FX_OP_IN: 1 when every string of a batch has to pass the wrapper's literal gates
+                                 before (or instead of) the automaton walk -- a literal-only pattern; `.match.` with any
+                                 non-empty prefix or suffix literal (do_matching_exactly compares lengths too, so a literal
+                                 that is blank but not empty counts); `.in.` with a prefix prefilter that is not provably
+                                 neutral.  0: the batch kernels walk the automaton directly */
 } fx_pattern_info;
 
 /* ---- host-only ------------------------------------------------------------------------- */

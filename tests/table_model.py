@@ -170,10 +170,11 @@ class Anchored:
 class Model:
     """one compiled pattern, evaluated the way the kernels evaluate it"""
 
-    def __init__(self, pattern_obj, use_direct=True):
+    def __init__(self, pattern_obj, use_direct=True, gates=True):
         self.p = pattern_obj
         self.op = pattern_obj.op
         self.use_direct = use_direct
+        self.gates = gates          # False: what the batch kernels compute for a pattern the host did NOT mark `gated`
         self.t = pattern_obj.tables()
         self.lit = pattern_obj.literals()
         self.prefix_mode = pattern_obj.info()["prefix_mode"]
@@ -198,7 +199,9 @@ class Model:
     def boolean(self, s: bytes):   # k_bool_* incl. eval_bool_generic
         all_, pre, suf = self.lit
         t = self.t
-        if self.op == 1:
+        if not self.gates:
+            pass                    # un-gated fast path: degenerate texts and the automaton walk only
+        elif self.op == 1:
             if not blank(all_):
                 return all_ in s
             if self.prefix_mode == 2:

@@ -328,6 +328,38 @@ def test_generated_patterns_match_oracle(seed, monkeypatch):
     assert nsparse > 5
 
 
+def test_the_host_decides_correctly_which_patterns_need_the_literal_gates():
+    """fx_pattern_info.gated is the launcher's decision to send every string of a boolean batch through the wrapper's
+    literal gates (eval_bool_slow) instead of walking the automaton directly.  For every pattern the host leaves
+    un-gated, the un-gated evaluation (degenerate texts + automaton walk: Model(gates=False)) must equal the oracle --
+    on the fuzz texts and on the texts the gates exist for: each literal, its prefixes, blanks.  (The launcher once
+    took `' +ab'` -- prefix literal ' ', blank but not empty -- for un-gated: `' ' .match. ' +ab'` is true by the length
+    rule of do_matching_exactly, api_internal_m.F90:199-233; found by the extended GPU fuzz, not by this suite.)"""
+    rng = random.Random(4242)
+    fixed = [rb" +(\w{2,3}\.?){1,}", b" +ab", b"ab +", b"  +", rb" \w+ ", b"a* ", b" a*", b" ", b"  ", b" ?", b"( |ab)", b"ab", b"a b", b"ab.*cd", b"x?ab"]
+    pats = fixed + [gen_pattern(rng).encode() for _ in range(400)]
+    ungated = gated = 0
+    bad = []
+    for pat in pats:
+        for kind in ("match", "in"):
+            p = fx.Pattern(pat, kind)
+            if p.status != 0 or p.info()["nfa_engine"]:
+                continue
+            all_, pre, suf = p.literals()
+            if p.info()["gated"]:
+                gated += 1
+                continue
+            ungated += 1
+            m = Model(p, gates=False)
+            texts = [gen_text(rng) for _ in range(8)] + [b"", b" ", b"  ", b"a", all_, pre, suf, pre[:1], suf[-1:], pre + suf, pre + b"x" + suf]
+            for t in texts:
+                o = O.op_match(pat, t) if kind == "match" else O.op_in(pat, t)
+                if bool(o) != bool(m.boolean(t)):
+                    bad.append((pat, kind, t, o))
+    assert not bad, bad[:10]
+    assert ungated > 100 and gated > 20, (ungated, gated)
+
+
 PREFIX_HEADS = [b"foo", b"ab", b"ERROR", b"x-", b"key=", "\u3042\u3044".encode(), b"a\\.b", b"q", b"zz", b"abab"]
 PREFIX_TAILS = [b"(bar|baz)", b".*end", b"[0-9]+", b"b*", b"(x|y)?z", b"\\s\\w+", b"+", b"{2,3}c", b"(|^)k", b".", b"[^ ]*$"]
 PREFIX_PIECES = [b"foo", b"fo", b"foobar", b"foobaz", b"ab", b"abab", b"a", b"b", b"ERROR", b"ERR", b" end", b"end", b"x-", b"x",
