@@ -902,3 +902,20 @@ def test_match_with_a_literal_that_is_blank_but_not_empty():
                 n = len(fb) // stride
                 gotf = p.match_fixed(fb, n, stride) if op == "match" else p.in_fixed(fb, n, stride)
                 assert np.array_equal(gotf, c.bool_fixed(o, fb, n, stride)), (pat, op, stride)
+
+
+def test_value_forms_for_pure_callers_on_gpu():
+    """fx_in_value / fx_match_value / fx_regex_sub (what a `pure` Fortran operator binds) against the oracle"""
+    import ctypes as C
+    lib = _lib.lib()
+    cases = [(b"foo(bar|baz)", b"xx foobaz"), (b"ab+c", b"abbc"), (b"ab+c", b"abbd"), (b"^a", b"b\na"), (b" +ab", b" "), (b"(", b"abc"),
+             ("[ぁ-ん]+".encode(), "xあいy".encode()), (b"a*", b""), (b"a", b" ")]
+    for pat, text in cases:
+        assert lib.fx_in_value(pat, len(pat), text, len(text)) == max(0, O.op_in(pat, text)), (pat, text)
+        assert lib.fx_match_value(pat, len(pat), text, len(text)) == max(0, O.op_match(pat, text)), (pat, text)
+        f, t, ln, st, rc = C.c_int64(7), C.c_int64(7), C.c_int64(7), C.c_int(7), C.c_int(7)
+        lib.fx_regex_sub(pat, len(pat), text, len(text), C.byref(f), C.byref(t), C.byref(ln), C.byref(st), C.byref(rc))
+        res, eln, ef, et, est = O.regex(pat, text)
+        assert rc.value == 0 and st.value == est and ln.value == eln, (pat, text)
+        if est == 0:
+            assert (f.value, t.value) == (ef, et), (pat, text)

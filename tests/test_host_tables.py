@@ -411,3 +411,26 @@ def test_sparse_start_and_prefix_scan_eligibility():
     for pat, ok in [(rb"ERROR.*timeout=\d+", 1), (b"foo(bar|baz)", 1), (b"key=[0-9]*", 1), ("\u3042\u3044+".encode(), 1),
                     (b"ab+c", 0), (b"aab*", 0), (b"abab+", 0), (b"fo+bar", 0), (rb"^ERROR.*timeout=\d+$", 0), (b"[a-z]+", 0)]:
         assert inf(pat, "regex")["prefix_scan"] == ok, pat
+
+
+def test_value_forms_for_pure_callers():
+    """fx_in_value / fx_match_value / fx_regex_sub (the shapes a `pure` Fortran operator can bind): the
+    boolean comes back as the function value, a failure as -status; an invalid pattern is `false` / status in the
+    regex form, exactly as fx_in / fx_match / fx_regex answer it.  Without a device the matching itself answers
+    FX_ERR_NO_DEVICE (the product has no CPU fallback)."""
+    import ctypes as C
+    import torch
+    from forgex_b200 import _lib as L
+    lib = L.lib()
+    assert lib.fx_in_value(b"(", 1, b"abc", 3) == 0 and lib.fx_match_value(b"a{2,1}", 6, b"aa", 2) == 0    # invalid pattern: false
+    f, t, ln, st, rc = C.c_int64(7), C.c_int64(7), C.c_int64(7), C.c_int(7), C.c_int(7)
+    lib.fx_regex_sub(b"(", 1, b"abc", 3, C.byref(f), C.byref(t), C.byref(ln), C.byref(st), C.byref(rc))
+    assert rc.value == 0 and st.value == O.regex(b"(", b"abc")[4] != 0 and ln.value == 0
+    have = torch.cuda.is_available()
+    assert lib.fx_in_value(b"ab", 2, b"xaby", 4) == (1 if have else -L.FX_ERR_NO_DEVICE)
+    assert lib.fx_match_value(b"ab", 2, b"xaby", 4) == (0 if have else -L.FX_ERR_NO_DEVICE)
+    lib.fx_regex_sub(b"ab", 2, b"xaby", 4, C.byref(f), C.byref(t), C.byref(ln), C.byref(st), C.byref(rc))
+    if have:
+        assert (rc.value, st.value, f.value, t.value, ln.value) == (0, 0, 2, 3, 2)
+    else:
+        assert rc.value == L.FX_ERR_NO_DEVICE
